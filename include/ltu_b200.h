@@ -1,0 +1,167 @@
+/*
+ * ltu_b200.h -- C ABI of libltu_b200.so: the sm_100a kernels behind the drop-in
+ * LinTransUNet `MaskTransUnet` forward (lintransunet_b200/).
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never
+ *     allocates, frees or retains memory, has no hidden global buffers, never syncs;
+ *   - feature maps are channels-last  [B, H, W, D, C]  (the reference's [B,C,H,W,D] with the
+ *     channel axis moved innermost; a token matrix [B, N=H*W*D, C] is the same memory);
+ *   - `dtype` selects the STORAGE type of activations: LTU_F32 or LTU_BF16; all arithmetic and
+ *     all statistics are fp32; parameters are always fp32 unless stated;
+ *   - return 0 = ok, <0 = argument error (nothing launched), >0 = cudaError_t of the launch;
+ *     ltu_last_error() gives the message (thread-local);
+ *   - re-entrant; kernels go to `stream`.
+ *
+ * Each entry point names the reference code (paths relative to the reference repo) it
+ * replaces.
+ */
+#ifndef LTU_B200_H
+#define LTU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* ltu_stream_t; /* == cudaStream_t */
+
+#define LTU_F32 0
+#define LTU_BF16 1
+#define LTU_OK 0
+#define LTU_ERR_ARG (-1)
+
+#define LTU_ACT_NONE 0
+#define LTU_ACT_LRELU 1 /* LeakyReLU(0.01) */
+
+const char* ltu_last_error(void);
+int ltu_version(void);
+/* number of kernels this library has launched in the calling process (all threads) */
+int64_t ltu_launch_count(void);
+
+/* ---- a1: linear_attention, model/trans_block.py:41-67 ------------------------------------
+ * kv_reduce : ctx[b,h,j,e] = sum_n softmax_over_n(K)[b,n,h*32+j] * V[b,n,h*32+e]   (:59-60)
+ *             K,V are [B,N,heads*32] views with row stride ld (elements), e.g. slices of a fused
+ *             QKV projection.  ctx is fp32 [B,heads,32,32].  Deterministic two-stage reduction.
+ * q_readout : out[b,n,h*32+e] = sum_j softmax_over_j(Q[b,n,h*32+:])[j]/sqrt(32) * ctx[b,h,j,e]
+ *             (:50,:65) written in the merged-head [B,N,C] order of :165.                      */
+size_t ltu_kv_reduce_workspace(int B, int64_t N, int heads);
+int ltu_kv_reduce(const void* k, const void* v, int64_t ld, float* ctx, void* workspace,
+                  size_t workspace_bytes, int B, int64_t N, int heads, int dtype,
+                  ltu_stream_t stream);
+int ltu_q_readout(const void* q, int64_t ld_q, const float* ctx, void* out, int64_t ld_out, int B,
+                  int64_t N, int heads, int dtype, ltu_stream_t stream);
+
+/* ---- a3: SelfAttentionLayer glue, model/trans_block.py:205-210 ----------------------------
+ * add_layernorm: y = LayerNorm(x + res) * gamma + beta over C in {128,256} (eps 1e-6, :183)
+ * gelu        : in-place exact erf GELU (:201,:208); the bias is applied by the GEMM.          */
+int ltu_add_layernorm(const void* x, const void* res, const float* gamma, const float* beta,
+                      void* y, int64_t rows, int C, float eps, int dtype, ltu_stream_t stream);
+int ltu_gelu(void* x, int64_t n, int dtype, ltu_stream_t stream);
+
+/* ---- a4: Conv3dPosEmbedding, model/trans_block.py:86-96 -----------------------------------
+ * y = x + bias + depthwise3x3x3(x), zero pad 1, channels-last; w is fp32 [27][C] with the tap
+ * index kh*9+kw*3+kd in the NATIVE (H,W,D) axes (w'[c,kh,kw,kd] = w_ref[c,0,kd,kh,kw]).       */
+int ltu_posenc_dwconv3(const void* x, const float* w27c, const float* bias, void* y, int B, int H,
+                       int W, int D, int C, int dtype, ltu_stream_t stream);
+
+/* ---- a10-a14: nn.Conv3d (+ InstanceNorm3d statistics), model/Unet_3Dblock.py:310-316,
+ * :375,:422,:523-531,:588,:1328,:1353, gates :200-214 ---------------------------------------
+ * Implicit-GEMM direct convolution, kernel 1 or 3, zero padding `pad`, stride (sh,sw,sd).
+ *   in0 [B,Hi,Wi,Di,C0] (+ optional in1 [B,Hi,Wi,Di,C1] = torch.cat((in0,in1),1), :553)
+ *   up2 = 1: the input is nearest-upsampled x2 on H,W,D on the fly (nn.Upsample before the
+ *            up_embed conv, :421-422); Hi,Wi,Di are the STORED sizes.
+ *   weight fp32 packed [taps][C0+C1][Cout], tap = kh*k*k + kw*k + kd;  bias fp32 [Cout] or NULL
+ *   out [B,Ho,Wo,Do,Cout] in `dtype` (or fp32 when out_f32 != 0)
+ *   partials (nullable) fp32 [B][tiles][Cout][2] = per-tile (sum, sum of squares) of the fp32
+ *            results, tiles = ltu_conv3d_tiles(Ho*Wo*Do, Cout); feed to ltu_instnorm_finalize. */
+int ltu_conv3d_tiles(int64_t out_voxels, int Cout);
+int ltu_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di,
+               int up2, int ksize, int sh, int sw, int sd, int pad, const float* weight,
+               const float* bias, int Cout, void* out, int out_f32, int Ho, int Wo, int Do,
+               float* partials, int dtype, ltu_stream_t stream);
+
+/* tcgen05 (UTCHMMA) implicit-GEMM path of the same convolution for bf16 activations:
+ * weight_bf16 packed [taps][Cout][C0+C1] (K-major B operand).  Requirements: ksize 3, pad 1,
+ * (C0+C1) % 16 == 0, C0 % 16 == 0, Cout % 16 == 0 and Cout <= 256.  Same partials layout with
+ * tiles = ltu_conv3d_tc_tiles(out_voxels).                                                    */
+int ltu_conv3d_tc_supported(int C0, int C1, int Cout, int ksize, int pad);
+int ltu_conv3d_tc_tiles(int64_t out_voxels);
+int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di,
+                  int up2, int sh, int sw, int sd, const void* weight_bf16, const float* bias,
+                  int Cout, void* out, int Ho, int Wo, int Do, float* partials,
+                  ltu_stream_t stream);
+
+/* InstanceNorm3d (no affine, eps 1e-5, biased variance):
+ * finalize : partials [B][tiles][C][2] -> stats [B][C][2] = (mean, rstd), fixed summation order
+ * partials : per-chunk (sum,sumsq) of an existing channels-last tensor, `chunks` per sample
+ * apply    : y = act((x - mean) * rstd) (+ residual), DownBlock residual :330-331            */
+int ltu_instnorm_finalize(const float* partials, float* stats, int B, int tiles, int C,
+                          int64_t voxels, float eps, ltu_stream_t stream);
+int ltu_chan_partials(const void* x, float* partials, int B, int64_t voxels, int C, int chunks,
+                      int dtype, ltu_stream_t stream);
+int ltu_instnorm_apply(const void* x, const float* stats, const void* residual, void* y, int B,
+                       int64_t voxels, int C, int act, int dtype, ltu_stream_t stream);
+
+/* ---- a10: windows_embedding, model/Unet_3Dblock.py:123-136 --------------------------------
+ * x fp32 [B,1,H,W,D] -> y [B,H/2,W/2,D,4] channels-last, channel = kh*2+kw                    */
+int ltu_s2d_input(const float* x, void* y, int B, int H, int W, int D, int dtype,
+                  ltu_stream_t stream);
+
+/* ---- a12: nn.Upsample(trilinear, align_corners=True), model/Unet_3Dblock.py:1341-1345 ------
+ * scale factors (2,2,fd) with fd in {1,2}; channels-last                                     */
+int ltu_upsample_trilinear(const void* x, void* y, int B, int H, int W, int D, int C, int fd,
+                           int dtype, ltu_stream_t stream);
+
+/* ---- a12: mask head softmax + foreground, model/Unet_3Dblock.py:1380-1387 ------------------
+ * logits fp32 [B,V,Cout] -> mask fp32 [B,Cout,V] (nullable; the mask_list entry, reference
+ * layout) and fg fp32 [B,V] = 1 - softmax[...,0]                                              */
+int ltu_mask_softmax(const float* logits, float* mask, float* fg, int B, int64_t voxels, int Cout,
+                     ltu_stream_t stream);
+
+/* ---- a13: SpatialAttention3DBlock tail + skip gating, model/Unet_3Dblock.py:217-221,:1384-85
+ * out = skip * sigmoid(psi_b + sum_c psi_w[c] * relu(IN(a)[c] + IN(g)[c])); a,g are the raw
+ * 1x1x1 conv outputs [B,V,Ci] with their InstanceNorm stats [B][Ci][2]; Ci in {16,..,256}     */
+int ltu_gate_fused(const void* a, const float* stats_a, const void* g, const float* stats_g,
+                   const float* psi_w, const float* psi_b, const void* skip, void* out, int B,
+                   int64_t voxels, int Ci, int dtype, ltu_stream_t stream);
+
+/* ---- a8: ROIBridge.get_mask_boundary2 + get_min_max_indice, Unet_3Dblock.py:821-873,:37-49 -
+ * fg fp32 [B,h,w,d] -> box fp32 [B,6] = [x0,y0,0,x1,y1,d-1]; on device, no host sync.
+ * scratch: ltu_roi_bbox_scratch(B,h,w) bytes (int32 row/column profiles, zeroed by the call)  */
+size_t ltu_roi_bbox_scratch(int B, int h, int w);
+int ltu_roi_bbox(const float* fg, float* box, void* scratch, size_t scratch_bytes, int B, int h,
+                 int w, int d, int min_h, int min_w, float thr, ltu_stream_t stream);
+
+/* ---- a9: get_transfer_index/_back_index + grid_sample, Unet_3Dblock.py:51-82,:985-1039,
+ * :1080-1117 -- separable piecewise-linear ("fisheye") bilinear resample, zeros padding,
+ * align_corners=True.  direction 0: x [B,h,w,d,C] -> y [B,eval_h,eval_w,d,C];
+ * direction 1: x [B,eval_h,eval_w,d,C] -> y [B,h,w,d,C].                                       */
+int ltu_roi_resample(const void* x, const float* box, void* y, int B, int h, int w, int d, int C,
+                     int roi_h, int roi_w, int eval_h, int eval_w, int direction, int dtype,
+                     ltu_stream_t stream);
+
+/* ---- a12/a15/a16: windows_unembedding + softmax + argmax one-hot, Unet_3Dblock.py:138-152,
+ * :1392-1394, trans_3DUnet.py:196-202 -------------------------------------------------------
+ * logits fp32 [B,H2,W2,D,4*Cout] (in-channel = c*4+kh*2+kw) -> any of (nullable):
+ *   probs  fp32 [B,Cout,2*H2,2*W2,D], onehot fp32 (same shape), labels uint8 [B,2*H2,2*W2,D]  */
+int ltu_head_d2s_softmax(const float* logits, float* probs, float* onehot, uint8_t* labels, int B,
+                         int H2, int W2, int D, int Cout, ltu_stream_t stream);
+
+/* ---- config 5: constant-blend sliding-window accumulation (MONAI 0.7.0
+ * sliding_window_inference as called at inference_multi_classes.py:143) ----------------------
+ * labels uint8 [nwin,rh,rw,rd] (argmax class of each window) are scattered as one-hot votes
+ * into votes uint8 [C,H,W,D]; starts int32 [nwin,3].                                          */
+int ltu_vote_accumulate(const uint8_t* labels, const int32_t* starts, uint8_t* votes, int nwin,
+                        int rh, int rw, int rd, int C, int H, int W, int D, ltu_stream_t stream);
+/* votes uint8 [C,H,W,D] -> labels uint8 [H,W,D] = argmax_c votes (first max wins, like
+ * torch.argmax over vote fractions with a common denominator)                                */
+int ltu_vote_argmax(const uint8_t* votes, uint8_t* labels, int C, int64_t voxels,
+                    ltu_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTU_B200_H */

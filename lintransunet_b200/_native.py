@@ -1,0 +1,85 @@
+"""ctypes binding of libltu_b200.so (C ABI declared in include/ltu_b200.h).
+
+There is NO fallback: if the shared library is missing or a tensor is not on a CUDA
+device every entry point raises.  The library is built in-tree by
+``python -m lintransunet_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libltu_b200.so")
+
+_lib = None
+_lock = threading.Lock()
+
+P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
+
+# name -> (restype, argtypes); mirrors include/ltu_b200.h one to one
+SIGNATURES = {
+    "ltu_last_error": (c_char_p, []),
+    "ltu_version": (I, []),
+    "ltu_launch_count": (L, []),
+    "ltu_kv_reduce_workspace": (Z, [I, L, I]),
+    "ltu_kv_reduce": (I, [P, P, L, P, P, Z, I, L, I, I, P]),
+    "ltu_q_readout": (I, [P, L, P, P, L, I, L, I, I, P]),
+    "ltu_add_layernorm": (I, [P, P, P, P, P, L, I, F, I, P]),
+    "ltu_gelu": (I, [P, L, I, P]),
+    "ltu_posenc_dwconv3": (I, [P, P, P, P, I, I, I, I, I, I, P]),
+    "ltu_conv3d_tiles": (I, [L, I]),
+    "ltu_conv3d": (I, [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, I, P, I, P]),
+    "ltu_conv3d_tc_supported": (I, [I, I, I, I, I]),
+    "ltu_conv3d_tc_tiles": (I, [L]),
+    "ltu_conv3d_tc": (I, [P, I, P, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, P, P]),
+    "ltu_instnorm_finalize": (I, [P, P, I, I, I, L, F, P]),
+    "ltu_chan_partials": (I, [P, P, I, L, I, I, I, P]),
+    "ltu_instnorm_apply": (I, [P, P, P, P, I, L, I, I, I, P]),
+    "ltu_s2d_input": (I, [P, P, I, I, I, I, I, P]),
+    "ltu_upsample_trilinear": (I, [P, P, I, I, I, I, I, I, I, P]),
+    "ltu_mask_softmax": (I, [P, P, P, I, L, I, P]),
+    "ltu_gate_fused": (I, [P, P, P, P, P, P, P, P, I, L, I, I, P]),
+    "ltu_roi_bbox_scratch": (Z, [I, I, I]),
+    "ltu_roi_bbox": (I, [P, P, P, Z, I, I, I, I, I, I, F, P]),
+    "ltu_roi_resample": (I, [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P]),
+    "ltu_head_d2s_softmax": (I, [P, P, P, P, I, I, I, I, I, P]),
+    "ltu_vote_accumulate": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
+    "ltu_vote_argmax": (I, [P, P, I, L, P]),
+}
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the .so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeLibraryMissing(
+                    f"{LIB_PATH} not found: build it with `python -m lintransunet_b200.build` "
+                    "(there is no CPU / PyTorch fallback for the hot path)")
+            h = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(h, name)          # AttributeError if the export is missing
+                fn.restype = res
+                fn.argtypes = args
+            _lib = h
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ltu_last_error()
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(lib().ltu_launch_count())

@@ -1,0 +1,489 @@
+// Family 1: the linear ("efficient") attention core and the bandwidth-bound glue of
+// SelfAttentionLayer (reference model/trans_block.py:41-67, :203-211, :86-96).
+//
+// Layout: tokens are rows of a [B, N, C] matrix, C = heads*32, heads are the contiguous 32-wide
+// column slices (trans_block.py:156 view(B,N,h,32)).
+//
+// kv_reduce  : one pass over K and V.  Every warp keeps, for ONE head, the online column-softmax
+//              state (running max m[j], running sum s[j]) and the 32x32 context in registers
+//              (lane e owns column e).  Partial states are merged by kv_combine in a fixed order
+//              => bit-reproducible.
+// q_readout  : one pass over Q, writes out.
+#include "common.cuh"
+
+namespace ltu {
+
+constexpr int kHeadDim = 32;
+constexpr int kTileTokens = 32;      // tokens staged per cp.async stage
+constexpr int kAttnThreads = 256;    // 8 warps
+constexpr int kAttnWarps = 8;
+constexpr int kPartialFloats = 32 * 32 + 64;   // ctx[32][32], m[32], s[32]
+
+static inline int kv_chunks_per_batch(int B, int64_t N) {
+    int64_t tiles = ceil_div64(N, kTileTokens);
+    int64_t want = ceil_div64(2 * (int64_t)sm_count(), B);
+    if (want < 1) want = 1;
+    int64_t chunks = tiles < want ? tiles : want;
+    int64_t tiles_per_chunk = ceil_div64(tiles, chunks);
+    return (int)ceil_div64(tiles, tiles_per_chunk);
+}
+
+// Stage `kTileTokens` rows x C columns of `src` (row stride ld) into smem with 16-byte cp.async.
+template <typename T>
+__device__ __forceinline__ void stage_tile(T* smem, const T* src, int64_t ld, int64_t row0,
+                                           int64_t nrows_total, int C) {
+    constexpr int VN = Vec<T>::N;
+    const int chunks_per_row = C / VN;
+    const int total = kTileTokens * chunks_per_row;
+    for (int i = threadIdx.x; i < total; i += kAttnThreads) {
+        int r = i / chunks_per_row, c = i - r * chunks_per_row;
+        int64_t row = row0 + r;
+        bool ok = row < nrows_total;
+        const T* g = src + (ok ? row : row0) * ld + c * VN;
+        cp_async16_zfill(smem + r * C + c * VN, g, ok ? 16 : 0);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kAttnThreads)
+kv_reduce_kernel(const T* __restrict__ K, const T* __restrict__ V, int64_t ld, float* __restrict__ part,
+                 int64_t N, int heads, int chunks, int tiles_per_chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = heads * kHeadDim;
+    const int wph = kAttnWarps / heads;              // warps per head
+    const int ttw = kTileTokens / wph;               // tokens per warp per tile
+    T* sK = reinterpret_cast<T*>(smem_raw);          // [2][TT][C]
+    T* sV = sK + 2 * kTileTokens * C;                // [2][TT][C]
+    float* sP = reinterpret_cast<float*>(sV + 2 * kTileTokens * C);   // [8 warps][ttw][32]
+
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hd = warp % heads, sub = warp / heads;
+    const T* Kb = K + (int64_t)b * N * ld;
+    const T* Vb = V + (int64_t)b * N * ld;
+    float* myP = sP + warp * ttw * kHeadDim;
+
+    const int64_t tile0 = (int64_t)chunk * tiles_per_chunk;
+    int64_t ntiles = ceil_div64(N, kTileTokens) - tile0;
+    if (ntiles > tiles_per_chunk) ntiles = tiles_per_chunk;
+    if (ntiles < 0) ntiles = 0;
+
+    float acc[kHeadDim];
+#pragma unroll
+    for (int j = 0; j < kHeadDim; ++j) acc[j] = 0.f;
+    float m_run = -INFINITY, s_run = 0.f;
+
+    if (ntiles > 0) {
+        stage_tile(sK, Kb, ld, tile0 * kTileTokens, N, C);
+        stage_tile(sV, Vb, ld, tile0 * kTileTokens, N, C);
+    }
+    cp_async_commit();
+    for (int64_t t = 0; t < ntiles; ++t) {
+        const int buf = (int)(t & 1);
+        if (t + 1 < ntiles) {
+            stage_tile(sK + (buf ^ 1) * kTileTokens * C, Kb, ld, (tile0 + t + 1) * kTileTokens, N, C);
+            stage_tile(sV + (buf ^ 1) * kTileTokens * C, Vb, ld, (tile0 + t + 1) * kTileTokens, N, C);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        const T* tk = sK + buf * kTileTokens * C + hd * kHeadDim;
+        const T* tv = sV + buf * kTileTokens * C + hd * kHeadDim;
+        int64_t row0 = (tile0 + t) * kTileTokens;
+        int valid = (int)((N - row0) < kTileTokens ? (N - row0) : kTileTokens);
+        // tokens of this warp inside the tile: sub*ttw .. sub*ttw+ttw-1
+        int n_lo = sub * ttw;
+        int n_cnt = valid - n_lo;
+        if (n_cnt > ttw) n_cnt = ttw;
+        if (n_cnt > 0) {
+            // (A) column max over the warp's tokens, lane j <-> key feature j
+            float mt = -INFINITY;
+            for (int n = 0; n < n_cnt; ++n) mt = fmaxf(mt, to_f32(tk[(n_lo + n) * C + lane]));
+            float m_new = fmaxf(m_run, mt);
+            if (__any_sync(0xffffffffu, m_new > m_run)) {
+                float sc = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
+                s_run *= sc;
+#pragma unroll
+                for (int j = 0; j < kHeadDim; ++j) acc[j] *= __shfl_sync(0xffffffffu, sc, j);
+                m_run = m_new;
+            }
+            // (B) p = exp(k - m) into smem, running sum
+            for (int n = 0; n < n_cnt; ++n) {
+                float p = __expf(to_f32(tk[(n_lo + n) * C + lane]) - m_run);
+                myP[n * kHeadDim + lane] = p;
+                s_run += p;
+            }
+            __syncwarp();
+            // (C) ctx[j][e] += p[n][j] * v[n][e], lane e <-> value feature e
+            for (int n = 0; n < n_cnt; ++n) {
+                float v = to_f32(tv[(n_lo + n) * C + lane]);
+                const float4* pr = reinterpret_cast<const float4*>(myP + n * kHeadDim);
+#pragma unroll
+                for (int q = 0; q < kHeadDim / 4; ++q) {
+                    float4 p4 = pr[q];
+                    acc[4 * q + 0] = fmaf(p4.x, v, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(p4.y, v, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(p4.z, v, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(p4.w, v, acc[4 * q + 3]);
+                }
+            }
+        }
+        __syncthreads();   // tile buffer `buf` is re-filled by the next iteration's prefetch
+    }
+    cp_async_wait<0>();
+
+    // partial index: ((b*chunks + chunk)*wph + sub)*heads + hd
+    float* out = part + ((((int64_t)b * chunks + chunk) * wph + sub) * heads + hd) * kPartialFloats;
+#pragma unroll
+    for (int j = 0; j < kHeadDim; ++j) out[j * kHeadDim + lane] = acc[j];
+    out[1024 + lane] = m_run;
+    out[1056 + lane] = s_run;
+}
+
+// grid (heads, B), 1024 threads: thread (j,e).  Merges the partial states in index order.
+__global__ void __launch_bounds__(1024)
+kv_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx, int heads, int nparts) {
+    const int hd = blockIdx.x, b = blockIdx.y;
+    const int j = threadIdx.x >> 5, e = threadIdx.x & 31;
+    const float* base = part + ((int64_t)b * nparts * heads + hd) * kPartialFloats;
+    const int64_t stride = (int64_t)heads * kPartialFloats;
+    float M = -INFINITY;
+    for (int p = 0; p < nparts; ++p) M = fmaxf(M, base[p * stride + 1024 + j]);
+    float S = 0.f, A = 0.f;
+    for (int p = 0; p < nparts; ++p) {
+        float mp = base[p * stride + 1024 + j];
+        float w = (mp == -INFINITY) ? 0.f : __expf(mp - M);
+        S = fmaf(base[p * stride + 1056 + j], w, S);
+        A = fmaf(base[p * stride + j * kHeadDim + e], w, A);
+    }
+    ctx[(((int64_t)b * heads + hd) * kHeadDim + j) * kHeadDim + e] = A / S;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kAttnThreads)
+q_readout_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restrict__ ctx, T* __restrict__ O,
+                 int64_t ldo, int64_t N, int heads, int tiles_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = heads * kHeadDim;
+    const int wph = kAttnWarps / heads;
+    const int ttw = kTileTokens / wph;
+    T* sQ = reinterpret_cast<T*>(smem_raw);                                 // [2][TT][C]
+    float* sP = reinterpret_cast<float*>(sQ + 2 * kTileTokens * C);         // [8][ttw][32]
+
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hd = warp % heads, sub = warp / heads;
+    const T* Qb = Q + (int64_t)b * N * ldq;
+    T* Ob = O + (int64_t)b * N * ldo;
+    float* myP = sP + warp * ttw * kHeadDim;
+
+    // ctx column e of this head, pre-scaled by 1/sqrt(d_k) (trans_block.py:50)
+    float c[kHeadDim];
+    const float* cb = ctx + ((int64_t)b * heads + hd) * kHeadDim * kHeadDim;
+    const float inv_sqrt_d = 0.17677669529663687f;   // 1/sqrt(32)
+#pragma unroll
+    for (int j = 0; j < kHeadDim; ++j) c[j] = cb[j * kHeadDim + lane] * inv_sqrt_d;
+
+    const int64_t tile0 = (int64_t)blockIdx.x * tiles_per_cta;
+    int64_t ntiles = ceil_div64(N, kTileTokens) - tile0;
+    if (ntiles > tiles_per_cta) ntiles = tiles_per_cta;
+    if (ntiles < 0) ntiles = 0;
+
+    if (ntiles > 0) stage_tile(sQ, Qb, ldq, tile0 * kTileTokens, N, C);
+    cp_async_commit();
+    for (int64_t t = 0; t < ntiles; ++t) {
+        const int buf = (int)(t & 1);
+        if (t + 1 < ntiles)
+            stage_tile(sQ + (buf ^ 1) * kTileTokens * C, Qb, ldq, (tile0 + t + 1) * kTileTokens, N, C);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        const T* tq = sQ + buf * kTileTokens * C + hd * kHeadDim;
+        int64_t row0 = (tile0 + t) * kTileTokens;
+        int valid = (int)((N - row0) < kTileTokens ? (N - row0) : kTileTokens);
+        int n_lo = sub * ttw;
+        int n_cnt = valid - n_lo;
+        if (n_cnt > ttw) n_cnt = ttw;
+        if (n_cnt > 0) {
+            for (int n = 0; n < n_cnt; ++n) {
+                float qv = to_f32(tq[(n_lo + n) * C + lane]);
+                float mx = warp_max(qv);
+                myP[n * kHeadDim + lane] = __expf(qv - mx);
+            }
+            __syncwarp();
+            for (int n = 0; n < n_cnt; ++n) {
+                const float4* pr = reinterpret_cast<const float4*>(myP + n * kHeadDim);
+                float o = 0.f, den = 0.f;
+#pragma unroll
+                for (int q = 0; q < kHeadDim / 4; ++q) {
+                    float4 p4 = pr[q];
+                    o = fmaf(p4.x, c[4 * q + 0], o);
+                    o = fmaf(p4.y, c[4 * q + 1], o);
+                    o = fmaf(p4.z, c[4 * q + 2], o);
+                    o = fmaf(p4.w, c[4 * q + 3], o);
+                    den += (p4.x + p4.y) + (p4.z + p4.w);
+                }
+                Ob[(row0 + n_lo + n) * ldo + hd * kHeadDim + lane] = from_f32<T>(o / den);
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------- add + LayerNorm
+template <typename T, int C>
+__global__ void __launch_bounds__(256)
+add_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, T* __restrict__ y, int64_t rows, float eps) {
+    constexpr int Q = C / 128;   // 4-element chunks per lane
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    float g[Q][4], bt[Q][4];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        load4(gamma + q * 128 + lane * 4, g[q]);
+        load4(beta + q * 128 + lane * 4, bt[q]);
+    }
+    for (int64_t row = warp_global; row < rows; row += nwarps) {
+        float v[Q][4];
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            float a[4], bb[4];
+            load4(x + row * C + q * 128 + lane * 4, a);
+            load4(r + row * C + q * 128 + lane * 4, bb);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { v[q][i] = a[i] + bb[i]; sum += v[q][i]; }
+        }
+        float mean = warp_sum(sum) * (1.f / C);
+        float sq = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { float d = v[q][i] - mean; sq = fmaf(d, d, sq); }
+        float rstd = rsqrtf(warp_sum(sq) * (1.f / C) + eps);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = (v[q][i] - mean) * rstd * g[q][i] + bt[q][i];
+            store4(y + row * C + q * 128 + lane * 4, o);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_kernel(T* __restrict__ x, int64_t nvec) {
+    constexpr int VN = Vec<T>::N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float v[VN];
+        load_vec(x + i * VN, v);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) v[k] = 0.5f * v[k] * (1.f + erff(v[k] * 0.70710678118654752f));
+        store_vec(x + i * VN, v);
+    }
+}
+
+// ---------------------------------------------------------------- depthwise positional conv
+template <typename T>
+__global__ void __launch_bounds__(256)
+posenc_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+              T* __restrict__ y, int B, int H, int W, int D, int C) {
+    const int cv = C / 4;
+    const int64_t total = (int64_t)B * H * W * D * cv;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int c4 = (int)(idx % cv) * 4;
+        int64_t vox = idx / cv;
+        int d = (int)(vox % D);
+        int64_t t = vox / D;
+        int ww = (int)(t % W);
+        t /= W;
+        int h = (int)(t % H);
+        int b = (int)(t / H);
+        float acc[4], ctr[4];
+        load4(x + vox * C + c4, ctr);
+        float bs[4];
+        load4(bias + c4, bs);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = bs[i];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            int hh = h + kh - 1;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                int w2 = ww + kw - 1;
+                if (w2 < 0 || w2 >= W) continue;
+#pragma unroll
+                for (int kd = 0; kd < 3; ++kd) {
+                    int dd = d + kd - 1;
+                    if (dd < 0 || dd >= D) continue;
+                    float xv[4], wv[4];
+                    int64_t nv = (((int64_t)b * H + hh) * W + w2) * D + dd;
+                    load4(x + nv * C + c4, xv);
+                    load4(w + (kh * 9 + kw * 3 + kd) * C + c4, wv);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i] = fmaf(xv[i], wv[i], acc[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += ctr[i];
+        store4(y + vox * C + c4, acc);
+    }
+}
+
+void count_launch(int n = 1);
+
+template <typename T>
+static int kv_reduce_impl(const void* k, const void* v, int64_t ld, float* ctx, void* ws, size_t ws_bytes,
+                          int B, int64_t N, int heads, cudaStream_t st) {
+    const int C = heads * kHeadDim;
+    const int wph = kAttnWarps / heads;
+    const int chunks = kv_chunks_per_batch(B, N);
+    const int64_t tiles = ceil_div64(N, kTileTokens);
+    const int tiles_per_chunk = (int)ceil_div64(tiles, chunks);
+    const size_t need = (size_t)B * chunks * wph * heads * kPartialFloats * sizeof(float);
+    LTU_ARG_CHECK(ws_bytes >= need, "kv_reduce: workspace too small (%zu < %zu)", ws_bytes, need);
+    size_t smem = (size_t)4 * kTileTokens * C * sizeof(T) + (size_t)kAttnWarps * (kTileTokens / wph) * kHeadDim * 4;
+    static thread_local int configured_dev_f32 = -1, configured_dev_bf16 = -1;
+    int dev;
+    cudaGetDevice(&dev);
+    int& conf = sizeof(T) == 4 ? configured_dev_f32 : configured_dev_bf16;
+    if (conf != dev) {
+        cudaFuncSetAttribute(kv_reduce_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        conf = dev;
+    }
+    kv_reduce_kernel<T><<<dim3(chunks, B), kAttnThreads, smem, st>>>(
+        (const T*)k, (const T*)v, ld, (float*)ws, N, heads, chunks, tiles_per_chunk);
+    LTU_LAUNCH_CHECK("kv_reduce");
+    kv_combine_kernel<<<dim3(heads, B), 1024, 0, st>>>((const float*)ws, ctx, heads, chunks * wph);
+    LTU_LAUNCH_CHECK("kv_combine");
+    count_launch(2);
+    return LTU_OK;
+}
+
+template <typename T>
+static int q_readout_impl(const void* q, int64_t ldq, const float* ctx, void* out, int64_t ldo, int B,
+                          int64_t N, int heads, cudaStream_t st) {
+    const int C = heads * kHeadDim;
+    const int wph = kAttnWarps / heads;
+    const int64_t tiles = ceil_div64(N, kTileTokens);
+    int64_t want = ceil_div64(4 * (int64_t)sm_count(), B);
+    int64_t ctas = tiles < want ? tiles : want;
+    if (ctas < 1) ctas = 1;
+    int tiles_per_cta = (int)ceil_div64(tiles, ctas);
+    ctas = ceil_div64(tiles, tiles_per_cta);
+    size_t smem = (size_t)2 * kTileTokens * C * sizeof(T) + (size_t)kAttnWarps * (kTileTokens / wph) * kHeadDim * 4;
+    static thread_local int configured_dev_f32 = -1, configured_dev_bf16 = -1;
+    int dev;
+    cudaGetDevice(&dev);
+    int& conf = sizeof(T) == 4 ? configured_dev_f32 : configured_dev_bf16;
+    if (conf != dev) {
+        cudaFuncSetAttribute(q_readout_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        conf = dev;
+    }
+    q_readout_kernel<T><<<dim3((unsigned)ctas, B), kAttnThreads, smem, st>>>(
+        (const T*)q, ldq, ctx, (T*)out, ldo, N, heads, tiles_per_cta);
+    LTU_LAUNCH_CHECK("q_readout");
+    count_launch(1);
+    return LTU_OK;
+}
+
+}  // namespace ltu
+
+using namespace ltu;
+
+static bool heads_ok(int heads) { return heads == 1 || heads == 2 || heads == 4 || heads == 8; }
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" size_t ltu_kv_reduce_workspace(int B, int64_t N, int heads) {
+    if (B <= 0 || N <= 0 || !heads_ok(heads)) return 0;
+    return (size_t)B * kv_chunks_per_batch(B, N) * (kAttnWarps / heads) * heads * kPartialFloats * sizeof(float);
+}
+
+extern "C" int ltu_kv_reduce(const void* k, const void* v, int64_t ld, float* ctx, void* ws, size_t ws_bytes,
+                             int B, int64_t N, int heads, int dtype, ltu_stream_t stream) {
+    LTU_ARG_CHECK(k && v && ctx && ws, "kv_reduce: null pointer");
+    LTU_ARG_CHECK(B > 0 && N > 0 && B <= 65535, "kv_reduce: bad B=%d N=%lld", B, (long long)N);
+    LTU_ARG_CHECK(heads_ok(heads), "kv_reduce: heads must be 1,2,4 or 8 (got %d)", heads);
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "kv_reduce: bad dtype %d", dtype);
+    const int vn = dtype == LTU_F32 ? 4 : 8;
+    LTU_ARG_CHECK(ld >= heads * 32 && ld % vn == 0, "kv_reduce: row stride %lld not a multiple of %d", (long long)ld, vn);
+    LTU_ARG_CHECK(aligned16(k) && aligned16(v) && aligned16(ws), "kv_reduce: pointers must be 16-byte aligned");
+    if (dtype == LTU_F32) return kv_reduce_impl<float>(k, v, ld, ctx, ws, ws_bytes, B, N, heads, (cudaStream_t)stream);
+    return kv_reduce_impl<bf16>(k, v, ld, ctx, ws, ws_bytes, B, N, heads, (cudaStream_t)stream);
+}
+
+extern "C" int ltu_q_readout(const void* q, int64_t ldq, const float* ctx, void* out, int64_t ldo, int B,
+                             int64_t N, int heads, int dtype, ltu_stream_t stream) {
+    LTU_ARG_CHECK(q && ctx && out, "q_readout: null pointer");
+    LTU_ARG_CHECK(B > 0 && N > 0 && B <= 65535, "q_readout: bad B=%d N=%lld", B, (long long)N);
+    LTU_ARG_CHECK(heads_ok(heads), "q_readout: heads must be 1,2,4 or 8 (got %d)", heads);
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "q_readout: bad dtype %d", dtype);
+    const int vn = dtype == LTU_F32 ? 4 : 8;
+    LTU_ARG_CHECK(ldq >= heads * 32 && ldq % vn == 0 && ldo >= heads * 32, "q_readout: bad row strides");
+    LTU_ARG_CHECK(aligned16(q), "q_readout: q must be 16-byte aligned");
+    if (dtype == LTU_F32) return q_readout_impl<float>(q, ldq, ctx, out, ldo, B, N, heads, (cudaStream_t)stream);
+    return q_readout_impl<bf16>(q, ldq, ctx, out, ldo, B, N, heads, (cudaStream_t)stream);
+}
+
+extern "C" int ltu_add_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* y,
+                                 int64_t rows, int C, float eps, int dtype, ltu_stream_t stream) {
+    LTU_ARG_CHECK(x && res && gamma && beta && y, "add_layernorm: null pointer");
+    LTU_ARG_CHECK(rows > 0, "add_layernorm: rows=%lld", (long long)rows);
+    LTU_ARG_CHECK(C == 128 || C == 256, "add_layernorm: C must be 128 or 256 (got %d)", C);
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "add_layernorm: bad dtype %d", dtype);
+    LTU_ARG_CHECK(aligned16(x) && aligned16(res) && aligned16(y) && aligned16(gamma) && aligned16(beta),
+                  "add_layernorm: pointers must be 16-byte aligned");
+    int64_t blocks = ceil_div64(rows, 8);
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+#define LN_LAUNCH(T, CC) add_layernorm_kernel<T, CC><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, (const T*)res, gamma, beta, (T*)y, rows, eps)
+    if (dtype == LTU_F32) { if (C == 128) LN_LAUNCH(float, 128); else LN_LAUNCH(float, 256); }
+    else                  { if (C == 128) LN_LAUNCH(bf16, 128);  else LN_LAUNCH(bf16, 256); }
+#undef LN_LAUNCH
+    LTU_LAUNCH_CHECK("add_layernorm");
+    count_launch(1);
+    return LTU_OK;
+}
+
+extern "C" int ltu_gelu(void* x, int64_t n, int dtype, ltu_stream_t stream) {
+    LTU_ARG_CHECK(x && n > 0, "gelu: bad arguments");
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "gelu: bad dtype %d", dtype);
+    const int vn = dtype == LTU_F32 ? 4 : 8;
+    LTU_ARG_CHECK(n % vn == 0 && aligned16(x), "gelu: n must be a multiple of %d and x 16-byte aligned", vn);
+    int64_t nvec = n / vn;
+    int64_t blocks = ceil_div64(nvec, 256);
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == LTU_F32) gelu_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float*)x, nvec);
+    else gelu_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)x, nvec);
+    LTU_LAUNCH_CHECK("gelu");
+    count_launch(1);
+    return LTU_OK;
+}
+
+extern "C" int ltu_posenc_dwconv3(const void* x, const float* w, const float* bias, void* y, int B, int H, int W,
+                                  int D, int C, int dtype, ltu_stream_t stream) {
+    LTU_ARG_CHECK(x && w && bias && y, "posenc_dwconv3: null pointer");
+    LTU_ARG_CHECK(B > 0 && H > 0 && W > 0 && D > 0 && C > 0 && C % 4 == 0, "posenc_dwconv3: bad shape");
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "posenc_dwconv3: bad dtype %d", dtype);
+    LTU_ARG_CHECK(x != y, "posenc_dwconv3: in-place is not supported");
+    int64_t total = (int64_t)B * H * W * D * (C / 4);
+    int64_t blocks = ceil_div64(total, 256);
+    int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    if (dtype == LTU_F32) posenc_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, w, bias, (float*)y, B, H, W, D, C);
+    else posenc_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, (bf16*)y, B, H, W, D, C);
+    LTU_LAUNCH_CHECK("posenc_dwconv3");
+    count_launch(1);
+    return LTU_OK;
+}

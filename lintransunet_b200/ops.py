@@ -1,0 +1,320 @@
+"""Tensor-level wrappers of the C ABI (include/ltu_b200.h).
+
+Every function takes CUDA tensors in the channels-last layout ``[B, H, W, D, C]`` (or token
+matrices ``[B, N, C]``), allocates outputs with torch (the library never allocates) and
+launches on the current stream of the tensor's device.  Nothing here computes on the CPU and
+nothing falls back to PyTorch kernels: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native
+from ._native import check
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_LRELU = 0, 1
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported activation dtype {t.dtype} (float32 or bfloat16)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _chk(*ts: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("lintransunet_b200 ops need CUDA tensors: there is no CPU fallback")
+        if not t.is_contiguous():
+            raise RuntimeError("lintransunet_b200 ops need contiguous tensors")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {t.device} vs {dev}")
+    return dev
+
+
+class _Guard:
+    """Make `dev` current for the launch (DataParallel replicas run on foreign devices)."""
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, dev: torch.device):
+        self.dev = dev
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.dev.index is not None and self.dev.index != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.dev)
+        return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+# ------------------------------------------------------------------ a1: attention core
+def kv_reduce(k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """k, v: [B, N, C] views with a common row stride (e.g. slices of a fused QKV buffer).
+    Returns ctx fp32 [B, heads, 32, 32] (model/trans_block.py:59-60)."""
+    B, N, C = k.shape
+    assert C == heads * 32 and v.shape == k.shape
+    assert k.stride(2) == 1 and v.stride(2) == 1 and k.stride(1) == v.stride(1)
+    assert k.stride(0) == N * k.stride(1) and v.stride(0) == N * v.stride(1)
+    if not (k.is_cuda and v.is_cuda):
+        raise RuntimeError("lintransunet_b200 ops need CUDA tensors: there is no CPU fallback")
+    L = _native.lib()
+    with _Guard(k.device) as st:
+        ws_bytes = L.ltu_kv_reduce_workspace(B, N, heads)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=k.device)
+        ctx = torch.empty(B, heads, 32, 32, dtype=torch.float32, device=k.device)
+        check(L.ltu_kv_reduce(_p(k), _p(v), k.stride(1), _p(ctx), _p(ws), ws_bytes, B, N, heads, _dt(k), st),
+              "ltu_kv_reduce")
+    return ctx
+
+
+def q_readout(q: torch.Tensor, ctx: torch.Tensor, heads: int) -> torch.Tensor:
+    """q: [B, N, C] view (row stride free), ctx fp32 [B,heads,32,32] -> out [B, N, C]
+    (model/trans_block.py:50,:65,:165)."""
+    B, N, C = q.shape
+    assert C == heads * 32 and q.stride(2) == 1 and q.stride(0) == N * q.stride(1)
+    _chk(ctx)
+    if not q.is_cuda:
+        raise RuntimeError("lintransunet_b200 ops need CUDA tensors: there is no CPU fallback")
+    out = torch.empty(B, N, C, dtype=q.dtype, device=q.device)
+    with _Guard(q.device) as st:
+        check(_native.lib().ltu_q_readout(_p(q), q.stride(1), _p(ctx), _p(out), C, B, N, heads, _dt(q), st),
+              "ltu_q_readout")
+    return out
+
+
+def add_layernorm(x: torch.Tensor, res: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                  eps: float = 1e-6) -> torch.Tensor:
+    """LayerNorm(x + res) over the last dim (model/trans_block.py:205-206, :209-210)."""
+    dev = _chk(x, res, gamma, beta)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty_like(x)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_add_layernorm(_p(x), _p(res), _p(gamma), _p(beta), _p(y), rows, C, eps, _dt(x), st),
+              "ltu_add_layernorm")
+    return y
+
+
+def gelu_(x: torch.Tensor) -> torch.Tensor:
+    """In-place exact-erf GELU (model/trans_block.py:201,:208)."""
+    dev = _chk(x)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_gelu(_p(x), x.numel(), _dt(x), st), "ltu_gelu")
+    return x
+
+
+def posenc_dwconv3(x: torch.Tensor, w27c: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """x + depthwise 3x3x3 conv(x) + bias on [B,H,W,D,C] (model/trans_block.py:86-96)."""
+    dev = _chk(x, w27c, bias)
+    B, H, W, D, C = x.shape
+    y = torch.empty_like(x)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_posenc_dwconv3(_p(x), _p(w27c), _p(bias), _p(y), B, H, W, D, C, _dt(x), st),
+              "ltu_posenc_dwconv3")
+    return y
+
+
+# ------------------------------------------------------------------ convolution + InstanceNorm
+def conv_out_size(n: int, k: int, s: int, pad: int) -> int:
+    return (n + 2 * pad - k) // s + 1
+
+
+def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ksize: int,
+           stride: Tuple[int, int, int] = (1, 1, 1), pad: int = 1, x1: Optional[torch.Tensor] = None,
+           up2: bool = False, out_f32: bool = False, want_stats: bool = False,
+           w_tc: Optional[torch.Tensor] = None):
+    """nn.Conv3d on channels-last input(s).  Returns (out, partials, tiles); partials is None
+    unless want_stats.  When `w_tc` (bf16 [taps][Cout][Cin]) is given and the shape qualifies the
+    tcgen05 implicit-GEMM kernel is used, otherwise the CUDA-core kernel."""
+    dev = _chk(x0, x1, w_packed, bias, w_tc)
+    L = _native.lib()
+    B, Hi, Wi, Di, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[-1]
+    if x1 is not None:
+        assert x1.shape[:4] == x0.shape[:4] and x1.dtype == x0.dtype
+    He, We, De = (2 * Hi, 2 * Wi, 2 * Di) if up2 else (Hi, Wi, Di)
+    Ho, Wo, Do = (conv_out_size(He, ksize, stride[0], pad), conv_out_size(We, ksize, stride[1], pad),
+                  conv_out_size(De, ksize, stride[2], pad))
+    V = Ho * Wo * Do
+    use_tc = (w_tc is not None and x0.dtype == torch.bfloat16 and not out_f32
+              and L.ltu_conv3d_tc_supported(C0, C1, cout, ksize, pad) == 1)
+    out = torch.empty(B, Ho, Wo, Do, cout, dtype=torch.float32 if out_f32 else x0.dtype, device=dev)
+    tiles = L.ltu_conv3d_tc_tiles(V) if use_tc else L.ltu_conv3d_tiles(V, cout)
+    partials = torch.empty(B, tiles, cout, 2, dtype=torch.float32, device=dev) if want_stats else None
+    with _Guard(dev) as st:
+        if use_tc:
+            check(L.ltu_conv3d_tc(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), stride[0], stride[1],
+                                  stride[2], _p(w_tc), _p(bias), cout, _p(out), Ho, Wo, Do, _p(partials), st),
+                  "ltu_conv3d_tc")
+        else:
+            check(L.ltu_conv3d(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), ksize, stride[0], stride[1],
+                               stride[2], pad, _p(w_packed), _p(bias), cout, _p(out), int(out_f32), Ho, Wo, Do,
+                               _p(partials), _dt(x0), st), "ltu_conv3d")
+    return out, partials, tiles
+
+
+def instnorm_finalize(partials: torch.Tensor, voxels: int, eps: float = 1e-5) -> torch.Tensor:
+    """partials [B,tiles,C,2] -> stats fp32 [B,C,2] = (mean, rstd)."""
+    dev = _chk(partials)
+    B, tiles, C, _ = partials.shape
+    stats = torch.empty(B, C, 2, dtype=torch.float32, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_instnorm_finalize(_p(partials), _p(stats), B, tiles, C, voxels, eps, st),
+              "ltu_instnorm_finalize")
+    return stats
+
+
+def chan_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """InstanceNorm statistics of an existing channels-last tensor [B,...,C]."""
+    dev = _chk(x)
+    B, C = x.shape[0], x.shape[-1]
+    V = x.numel() // (B * C)
+    chunks = max(1, min(256, V // 512))
+    partials = torch.empty(B, chunks, C, 2, dtype=torch.float32, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_chan_partials(_p(x), _p(partials), B, V, C, chunks, _dt(x), st), "ltu_chan_partials")
+    return instnorm_finalize(partials, V, eps)
+
+
+def instnorm_apply(x: torch.Tensor, stats: torch.Tensor, act: int = ACT_LRELU,
+                   residual: Optional[torch.Tensor] = None, inplace: bool = True) -> torch.Tensor:
+    """y = act((x - mean) * rstd) (+ residual)."""
+    dev = _chk(x, stats, residual)
+    B, C = x.shape[0], x.shape[-1]
+    V = x.numel() // (B * C)
+    y = x if inplace else torch.empty_like(x)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_instnorm_apply(_p(x), _p(stats), _p(residual), _p(y), B, V, C, act, _dt(x), st),
+              "ltu_instnorm_apply")
+    return y
+
+
+# ------------------------------------------------------------------ U-Net plumbing
+def s2d_input(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """[B,1,H,W,D] fp32 -> [B,H/2,W/2,D,4] (windows_embedding, model/Unet_3Dblock.py:123-136)."""
+    dev = _chk(x)
+    if x.dtype != torch.float32:
+        raise TypeError("model input must be float32")
+    B, cin, H, W, D = x.shape
+    if cin != 1:
+        raise ValueError("windows_embedding requires dim_input == 1 (model/Unet_3Dblock.py:132)")
+    y = torch.empty(B, H // 2, W // 2, D, 4, dtype=dtype, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_s2d_input(_p(x), _p(y), B, H, W, D, _dt(y), st), "ltu_s2d_input")
+    return y
+
+
+def upsample_trilinear(x: torch.Tensor, fd: int) -> torch.Tensor:
+    """Trilinear x(2,2,fd), align_corners=True (model/Unet_3Dblock.py:1341-1345)."""
+    dev = _chk(x)
+    B, H, W, D, C = x.shape
+    y = torch.empty(B, 2 * H, 2 * W, fd * D, C, dtype=x.dtype, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_upsample_trilinear(_p(x), _p(y), B, H, W, D, C, fd, _dt(x), st),
+              "ltu_upsample_trilinear")
+    return y
+
+
+def mask_softmax(logits: torch.Tensor, want_mask: bool):
+    """logits fp32 [B,h,w,d,Cout] -> (mask fp32 [B,Cout,h,w,d] | None, fg fp32 [B,h,w,d])."""
+    dev = _chk(logits)
+    B, h, w, d, C = logits.shape
+    mask = torch.empty(B, C, h, w, d, dtype=torch.float32, device=dev) if want_mask else None
+    fg = torch.empty(B, h, w, d, dtype=torch.float32, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_mask_softmax(_p(logits), _p(mask), _p(fg), B, h * w * d, C, st), "ltu_mask_softmax")
+    return mask, fg
+
+
+def gate_fused(a: torch.Tensor, stats_a: torch.Tensor, g: torch.Tensor, stats_g: torch.Tensor,
+               psi_w: torch.Tensor, psi_b: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+    dev = _chk(a, stats_a, g, stats_g, psi_w, psi_b, skip)
+    B, Ci = a.shape[0], a.shape[-1]
+    V = a.numel() // (B * Ci)
+    out = torch.empty_like(skip)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_gate_fused(_p(a), _p(stats_a), _p(g), _p(stats_g), _p(psi_w), _p(psi_b), _p(skip),
+                                           _p(out), B, V, Ci, _dt(a), st), "ltu_gate_fused")
+    return out
+
+
+def roi_bbox(fg: torch.Tensor, min_h: int, min_w: int, thr: float = 0.5) -> torch.Tensor:
+    """fg fp32 [B,h,w,d] -> boxes fp32 [B,6] on device (model/Unet_3Dblock.py:821-873)."""
+    dev = _chk(fg)
+    B, h, w, d = fg.shape
+    L = _native.lib()
+    nbytes = L.ltu_roi_bbox_scratch(B, h, w)
+    scratch = torch.empty(nbytes // 4, dtype=torch.int32, device=dev)
+    box = torch.empty(B, 6, dtype=torch.float32, device=dev)
+    with _Guard(dev) as st:
+        check(L.ltu_roi_bbox(_p(fg), _p(box), _p(scratch), nbytes, B, h, w, d, min_h, min_w, thr, st), "ltu_roi_bbox")
+    return box
+
+
+def roi_resample(x: torch.Tensor, box: torch.Tensor, full_hw: Tuple[int, int], roi_h: int, roi_w: int,
+                 eval_h: int, eval_w: int, direction: int) -> torch.Tensor:
+    """Fisheye resample: direction 0 map->roi ([B,h,w,d,C] -> [B,eval_h,eval_w,d,C]), 1 back."""
+    dev = _chk(x, box)
+    B, _, _, d, C = x.shape
+    h, w = full_hw
+    oh, ow = (eval_h, eval_w) if direction == 0 else (h, w)
+    y = torch.empty(B, oh, ow, d, C, dtype=x.dtype, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_roi_resample(_p(x), _p(box), _p(y), B, h, w, d, C, roi_h, roi_w, eval_h, eval_w,
+                                             direction, _dt(x), st), "ltu_roi_resample")
+    return y
+
+
+def head_d2s_softmax(logits: torch.Tensor, cout: int, want_probs: bool, want_onehot: bool, want_labels: bool):
+    """logits fp32 [B,H2,W2,D,4*cout] -> (probs, onehot, labels) in the reference layout."""
+    dev = _chk(logits)
+    B, H2, W2, D, C4 = logits.shape
+    assert C4 == 4 * cout
+    shp = (B, cout, 2 * H2, 2 * W2, D)
+    probs = torch.empty(shp, dtype=torch.float32, device=dev) if want_probs else None
+    onehot = torch.empty(shp, dtype=torch.float32, device=dev) if want_onehot else None
+    labels = torch.empty((B, 2 * H2, 2 * W2, D), dtype=torch.uint8, device=dev) if want_labels else None
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_head_d2s_softmax(_p(logits), _p(probs), _p(onehot), _p(labels), B, H2, W2, D, cout, st),
+              "ltu_head_d2s_softmax")
+    return probs, onehot, labels
+
+
+def vote_accumulate(labels: torch.Tensor, starts: torch.Tensor, votes: torch.Tensor) -> None:
+    """labels uint8 [n,rh,rw,rd], starts int32 [n,3], votes uint8 [C,H,W,D] (+= one-hot)."""
+    dev = _chk(labels, starts, votes)
+    n, rh, rw, rd = labels.shape
+    C, H, W, D = votes.shape
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_vote_accumulate(_p(labels), _p(starts), _p(votes), n, rh, rw, rd, C, H, W, D, st),
+              "ltu_vote_accumulate")
+
+
+def vote_argmax(votes: torch.Tensor) -> torch.Tensor:
+    dev = _chk(votes)
+    C, H, W, D = votes.shape
+    out = torch.empty(H, W, D, dtype=torch.uint8, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_vote_argmax(_p(votes), _p(out), C, H * W * D, st), "ltu_vote_argmax")
+    return out

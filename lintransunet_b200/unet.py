@@ -1,0 +1,478 @@
+"""Drop-in ``MaskTransUnet`` (reference model/trans_3DUnet.py:150-204) for B200.
+
+The module tree below exists to reproduce the reference's constructor signature, submodule
+names and ``state_dict`` layout (614 tensors for the default config): parameters live
+in ordinary ``nn.Conv3d`` / ``nn.Linear`` / ``nn.LayerNorm`` containers whose own ``forward`` is
+never called.  ``MaskTransUnet.forward`` runs the whole network through the sm_100a kernels of
+``libltu_b200.so`` in a channels-last ``[B,H,W,D,C]`` layout; the only PyTorch compute calls are
+the plain cuBLAS GEMMs of the ``nn.Linear`` layers.  There is no CPU path.
+
+Precision: inside ``torch.autocast`` (any dtype; the reference scripts use
+``torch.cuda.amp.autocast()``) activations are stored in bf16 with fp32 arithmetic and the
+3x3x3 convolutions run on tcgen05 tensor cores; otherwise everything is fp32.  ``precision``
+can force either.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+__all__ = ["MaskTransUnet", "Encoder", "ROIDecoder", "Model_Dict", "get_model_dict"]
+
+
+# ----------------------------------------------------------------------------- containers
+class _Holder(nn.Module):
+    """Parameter container: mirrors a reference submodule by name, never executed."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container: the computation runs in MaskTransUnet.forward")
+
+
+class DownBlock(_Holder):
+    """model/Unet_3Dblock.py:290-341."""
+
+    def __init__(self, cin: int, cout: int, k: int, stride):
+        super().__init__()
+        self.conv1 = nn.Conv3d(cin, cin, k, stride=1, padding=k // 2)
+        self.conv2 = nn.Conv3d(cin, cout, k, stride=stride, padding=k // 2)
+        self.stride = tuple(stride)
+
+
+class UpBlock(_Holder):
+    """model/Unet_3Dblock.py:504-557."""
+
+    def __init__(self, cin: int, cout: int, k: int):
+        super().__init__()
+        self.conv1 = nn.Conv3d(cin, cout, k, stride=1, padding=k // 2)
+        self.conv2 = nn.Conv3d(2 * cout, cout, k, stride=1, padding=k // 2)
+
+
+class Conv3dPosEmbedding(_Holder):
+    """model/trans_block.py:70-96."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.proj = nn.Conv3d(dim, dim, 3, stride=1, padding=1, groups=dim)
+
+
+class MultihAttention(_Holder):
+    """model/trans_block.py:127-166."""
+
+    def __init__(self, d_model: int, nhead: int):
+        super().__init__()
+        assert d_model % nhead == 0
+        self.nhead = nhead
+        self.linears = nn.ModuleList([nn.Linear(d_model, d_model) for _ in range(4)])
+
+
+class SelfAttentionLayer(_Holder):
+    """model/trans_block.py:169-211."""
+
+    def __init__(self, d_model: int, nhead: int):
+        super().__init__()
+        self.self_attn = MultihAttention(d_model, nhead)
+        self.linear1 = nn.Linear(d_model, 2 * d_model)
+        self.linear2 = nn.Linear(2 * d_model, d_model)
+        self.layer_norm1 = nn.LayerNorm(d_model, eps=1e-6)
+        self.layer_norm2 = nn.LayerNorm(d_model, eps=1e-6)
+
+
+class _EmbedConv(_Holder):
+    """DownEmbedBlock / UpEmbedBlock (model/Unet_3Dblock.py:343-432): module_list.0.<idx> is the conv."""
+
+    def __init__(self, cin: int, cout: int, conv_index: int, stride: int):
+        super().__init__()
+        inner = [nn.Identity() for _ in range(conv_index)]
+        inner.append(nn.Conv3d(cin, cout, 3, stride=stride, padding=1))
+        self.module_list = nn.Sequential(nn.Sequential(*inner))
+
+    @property
+    def conv(self) -> nn.Conv3d:
+        return self.module_list[0][-1]
+
+
+class EmbedAttention3DBlock(_Holder):
+    """model/Unet_3Dblock.py:435-501."""
+
+    def __init__(self, in_dim: int, d_model: int, nhead: int, N: int):
+        super().__init__()
+        self.in_dim, self.d_model, self.nhead, self.N = in_dim, d_model, nhead, N
+        self.down_embed = _EmbedConv(in_dim, d_model, conv_index=0, stride=2)
+        self.up_embed = _EmbedConv(d_model, in_dim, conv_index=1, stride=1)
+        self.pos_encoder = Conv3dPosEmbedding(d_model)
+        self.layers = nn.ModuleList([SelfAttentionLayer(d_model, nhead) for _ in range(N)])
+
+
+class PosAttention3DBlock(_Holder):
+    """model/Unet_3Dblock.py:224-274 (only pos_encoders[0] is used, :267-270; 1..N-1 are dead
+    parameters that stay in the state_dict)."""
+
+    def __init__(self, d_model: int, nhead: int, N: int):
+        super().__init__()
+        self.d_model, self.nhead, self.N = d_model, nhead, N
+        self.pos_encoders = nn.ModuleList([Conv3dPosEmbedding(d_model) for _ in range(N)])
+        self.layers = nn.ModuleList([SelfAttentionLayer(d_model, nhead) for _ in range(N)])
+
+
+class ConnectBridge(_Holder):
+    """model/Unet_3Dblock.py:647-670."""
+
+    def __init__(self, d_model: int, nhead: int, N: int):
+        super().__init__()
+        self.transformer = PosAttention3DBlock(d_model, nhead, N)
+
+
+class ROIBridge(_Holder):
+    """model/Unet_3Dblock.py:673-755; ROI constants :697-714."""
+
+    def __init__(self, in_dim: int, d_model: int, nhead: int, N: int, roi_size: int, mask_threshold: float = 0.5):
+        super().__init__()
+        self.transformer = EmbedAttention3DBlock(in_dim, d_model, nhead, N)
+        self.roi_size = roi_size
+        self.h_roi_size = roi_size
+        self.w_roi_size = int(roi_size * 0.6)
+        self.eval_roi_size = int(1.2 * roi_size)
+        self.eval_h_roi_size = self.eval_roi_size
+        self.eval_w_roi_size = int(self.eval_h_roi_size * 0.6)
+        self.min_h_roi = self.eval_roi_size // 2
+        self.min_w_roi = self.eval_w_roi_size // 2
+        self.mask_threshold = mask_threshold
+
+
+class InitialBridge(_Holder):
+    """model/Unet_3Dblock.py:1180-1199: identity, no parameters."""
+
+
+class SpatialAttention3DBlock(_Holder):
+    """model/Unet_3Dblock.py:194-221: three 1x1x1 convs."""
+
+    def __init__(self, c_skip: int, c_up: int, c_inter: int):
+        super().__init__()
+        self.W_x = nn.Sequential(nn.Conv3d(c_skip, c_inter, 1))
+        self.W_g = nn.Sequential(nn.Conv3d(c_up, c_inter, 1))
+        self.psi = nn.Sequential(nn.Conv3d(c_inter, 1, 1))
+
+
+class Encoder(_Holder):
+    """model/Unet_3Dblock.py:560-607."""
+
+    def __init__(self, num_layers: Sequence[int], dim_input: int, kernel_size: int = 3, dropout=None):
+        super().__init__()
+        self.num_layers = list(num_layers)
+        self.block_list = nn.ModuleList([
+            DownBlock(num_layers[i - 1], num_layers[i], kernel_size, (2, 2, (i - 1) % 2 + 1))
+            for i in range(1, len(num_layers))])
+        self.input_block = nn.Conv3d(dim_input * 4, num_layers[0], kernel_size, stride=1, padding=kernel_size // 2)
+
+
+class ROIDecoder(_Holder):
+    """model/Unet_3Dblock.py:1277-1396."""
+
+    def __init__(self, num_layers: Sequence[int], roi_size_list: Sequence[int], is_roi_list: Sequence[bool],
+                 dim_output: int, kernel_size: int = 3, nhead_lens: int = 32, dropout: float = 0.2, N: int = 8):
+        super().__init__()
+        L = list(num_layers)
+        self.num_layers = L
+        bridges: List[nn.Module] = []
+        for i in range(len(L) - 1):
+            if is_roi_list[i]:
+                dm = min(4 * L[i], 256)
+                bridges.append(ROIBridge(L[i], dm, dm // 32, N, roi_size_list[i]))
+            else:
+                bridges.append(InitialBridge())
+        bridges.append(ConnectBridge(L[-1], L[-1] // nhead_lens, N))
+        self.bridge_list = nn.ModuleList(bridges)
+        self.mask_conv_list = nn.ModuleList([nn.Conv3d(L[i], dim_output, kernel_size, padding=kernel_size // 2)
+                                             for i in range(1, len(L))])
+        self.att_conv_list = nn.ModuleList([SpatialAttention3DBlock(L[i - 1], L[i], L[i - 1])
+                                            for i in range(1, len(L))])
+        self.block_list = nn.ModuleList([UpBlock(L[-i], L[-i - 1], kernel_size) for i in range(1, len(L))])
+        self.final_block = nn.Conv3d(L[0], dim_output * 4, kernel_size, stride=1, padding=kernel_size // 2)
+
+
+# ----------------------------------------------------------------------------- packed weights
+class _ConvW:
+    """Derived cache of one conv: fp32 [taps][Cin][Cout] for the CUDA-core kernel, bf16
+    [taps][Cout][Cin] for the tcgen05 kernel."""
+
+    def __init__(self, conv: nn.Conv3d, want_tc: bool):
+        w = conv.weight.detach()
+        cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+        self.k, self.cin, self.cout = k, cin, cout
+        self.w = w.permute(2, 3, 4, 1, 0).reshape(k * k * k, cin, cout).contiguous().float()
+        self.b = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+        self.w_tc = (w.permute(2, 3, 4, 0, 1).reshape(k * k * k, cout, cin).contiguous().to(torch.bfloat16)
+                     if want_tc else None)
+
+
+class _LayerW:
+    def __init__(self, layer: SelfAttentionLayer, dtype: torch.dtype):
+        lin = layer.self_attn.linears
+        c = lambda t: t.detach().to(dtype).contiguous()
+        self.w_qkv = c(torch.cat([lin[0].weight, lin[1].weight, lin[2].weight], 0))
+        self.b_qkv = c(torch.cat([lin[0].bias, lin[1].bias, lin[2].bias], 0))
+        self.w_o, self.b_o = c(lin[3].weight), c(lin[3].bias)
+        self.w_1, self.b_1 = c(layer.linear1.weight), c(layer.linear1.bias)
+        self.w_2, self.b_2 = c(layer.linear2.weight), c(layer.linear2.bias)
+        f = lambda t: t.detach().float().contiguous()
+        self.g1, self.be1 = f(layer.layer_norm1.weight), f(layer.layer_norm1.bias)
+        self.g2, self.be2 = f(layer.layer_norm2.weight), f(layer.layer_norm2.bias)
+        self.nhead = layer.self_attn.nhead
+
+
+def _pos_w(pe: Conv3dPosEmbedding):
+    # reference applies the depthwise conv on the (D,H,W)-permuted view: kernel axes = (kd,kh,kw);
+    # native [kh,kw,kd][C] packing
+    w = pe.proj.weight.detach()[:, 0]                      # [C, kd, kh, kw]
+    return (w.permute(2, 3, 1, 0).reshape(27, -1).contiguous().float(),
+            pe.proj.bias.detach().float().contiguous())
+
+
+class _Plan:
+    """All derived weights for one (device, precision).  Rebuilt when any parameter changes
+    (load_state_dict / .to() / optimizer step bump the version or the storage)."""
+
+    def __init__(self, model: "MaskTransUnet", dtype: torch.dtype):
+        tc = dtype == torch.bfloat16
+        enc, dec = model.encode, model.decode
+        self.dtype = dtype
+        self.stem = _ConvW(enc.input_block, tc)
+        self.down = [(_ConvW(b.conv1, tc), _ConvW(b.conv2, tc), b.stride) for b in enc.block_list]
+        self.mask = [_ConvW(c, False) for c in dec.mask_conv_list]
+        self.gate = []
+        for a in dec.att_conv_list:
+            psi = a.psi[0]
+            self.gate.append((_ConvW(a.W_x[0], False), _ConvW(a.W_g[0], False),
+                              psi.weight.detach().reshape(-1).float().contiguous(),
+                              psi.bias.detach().float().contiguous()))
+        self.up = [(_ConvW(b.conv1, tc), _ConvW(b.conv2, tc)) for b in dec.block_list]
+        self.final = _ConvW(dec.final_block, False)
+        self.bridges: List[Optional[dict]] = []
+        for br in dec.bridge_list:
+            if isinstance(br, ROIBridge):
+                t = br.transformer
+                self.bridges.append(dict(kind="roi", down=_ConvW(t.down_embed.conv, tc), up=_ConvW(t.up_embed.conv, tc),
+                                         pos=_pos_w(t.pos_encoder), layers=[_LayerW(l, dtype) for l in t.layers],
+                                         mod=br))
+            elif isinstance(br, ConnectBridge):
+                t = br.transformer
+                self.bridges.append(dict(kind="bottle", pos=_pos_w(t.pos_encoders[0]),
+                                         layers=[_LayerW(l, dtype) for l in t.layers]))
+            else:
+                self.bridges.append(None)
+
+
+def _signature(model: nn.Module):
+    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+
+
+# ----------------------------------------------------------------------------- the model
+class MaskTransUnet(nn.Module):
+    """Same constructor, forward contract and state_dict as the reference
+    (model/trans_3DUnet.py:161-204): train mode returns ``(probs, mask_list)``, eval mode the
+    one-hot argmax."""
+
+    def __init__(self, num_layers: list, roi_size_list: list, is_roi_list: list, dim_input: int, dim_output: int,
+                 kernel_size: int = 3, dropout: float = 0.3):
+        super().__init__()
+        if kernel_size != 3:
+            raise ValueError("only kernel_size=3 (the reference default) is supported")
+        if dim_input != 1:
+            raise ValueError("windows_embedding requires dim_input == 1 (model/Unet_3Dblock.py:132)")
+        self.num_layers = list(num_layers)
+        self.kernel_size = kernel_size
+        self.dropout = dropout
+        self.dim_input = dim_input
+        self.dim_output = dim_output
+        self.roi_size_list = list(roi_size_list)
+        self.is_roi_list = list(is_roi_list)
+        self.encode = Encoder(self.num_layers, dim_input, kernel_size, dropout)
+        self.decode = ROIDecoder(self.num_layers, self.roi_size_list, self.is_roi_list, dim_output,
+                                 dropout=dropout)
+        # runtime knobs (not part of the reference API)
+        self.precision: Optional[str] = None          # None = follow autocast, or "fp32" / "bf16"
+        self.use_tensor_cores = os.environ.get("LTU_DISABLE_TC", "0") != "1"
+        self.forced_boxes: Optional[Dict[int, torch.Tensor]] = None   # tests: teacher-forced ROI boxes
+        self.record: Optional[dict] = None            # tests: set to {} to capture taps (channels-last)
+        self._plans: Dict[tuple, tuple] = {}
+
+    # -- derived-weight cache ------------------------------------------------------------
+    def _plan(self, device: torch.device, dtype: torch.dtype) -> _Plan:
+        key = (device.index, dtype)
+        sig = _signature(self)
+        hit = self._plans.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        plan = _Plan(self, dtype)
+        self._plans[key] = (sig, plan)
+        return plan
+
+    def _compute_dtype(self) -> torch.dtype:
+        if self.precision is not None:
+            if self.precision not in ("fp32", "bf16"):
+                raise ValueError("precision must be None, 'fp32' or 'bf16'")
+            return torch.float32 if self.precision == "fp32" else torch.bfloat16
+        return torch.bfloat16 if torch.is_autocast_enabled() else torch.float32
+
+    # -- building blocks -----------------------------------------------------------------
+    def _tap(self, name: str, t: torch.Tensor):
+        if self.record is not None:
+            self.record[name] = t
+
+    def _conv(self, x, cw: _ConvW, **kw):
+        return ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, w_tc=cw.w_tc if self.use_tensor_cores else None, **kw)
+
+    def _conv_in_act(self, x, cw: _ConvW, stride=(1, 1, 1), residual=None, x1=None, up2=False):
+        """Conv3d -> InstanceNorm3d -> LeakyReLU (+ residual)."""
+        y, partials, _ = self._conv(x, cw, stride=stride, pad=cw.k // 2, x1=x1, up2=up2, want_stats=True)
+        V = y.shape[1] * y.shape[2] * y.shape[3]
+        stats = ops.instnorm_finalize(partials, V)
+        return ops.instnorm_apply(y, stats, ops.ACT_LRELU, residual=residual, inplace=True)
+
+    def _encoder_layer(self, t, lw: _LayerW):
+        """SelfAttentionLayer.forward (model/trans_block.py:203-211) on tokens [B,N,C]."""
+        B, N, C = t.shape
+        qkv = F.linear(t, lw.w_qkv, lw.b_qkv)                           # cuBLAS: plain library GEMM
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        ctx = ops.kv_reduce(k, v, lw.nhead)
+        att = ops.q_readout(q, ctx, lw.nhead)
+        o = F.linear(att, lw.w_o, lw.b_o)
+        t = ops.add_layernorm(t, o, lw.g1, lw.be1, 1e-6)
+        f = ops.gelu_(F.linear(t, lw.w_1, lw.b_1))
+        f = F.linear(f, lw.w_2, lw.b_2)
+        return ops.add_layernorm(t, f, lw.g2, lw.be2, 1e-6)
+
+    def _transformer(self, x, br: dict, name: str):
+        """The 8-layer stack of PosAttention3DBlock / EmbedAttention3DBlock
+        (model/Unet_3Dblock.py:265-270, :484-490) on a channels-last volume."""
+        B, H, W, D, C = x.shape
+        t = x.reshape(B, H * W * D, C)
+        for i, lw in enumerate(br["layers"]):
+            t = self._encoder_layer(t, lw)
+            if i == 0:
+                t = ops.posenc_dwconv3(t.reshape(B, H, W, D, C), br["pos"][0], br["pos"][1]).reshape(B, H * W * D, C)
+        return t.reshape(B, H, W, D, C)
+
+    def _roi_bridge(self, skip, fg, br: dict, idx: int):
+        """ROIBridge.forward (model/Unet_3Dblock.py:717-755)."""
+        m: ROIBridge = br["mod"]
+        B, h, w, d, C = skip.shape
+        if self.forced_boxes is not None and idx in self.forced_boxes:
+            box = self.forced_boxes[idx].to(device=skip.device, dtype=torch.float32).contiguous()
+        else:
+            box = ops.roi_bbox(fg, m.min_h_roi, m.min_w_roi, m.mask_threshold)
+        self._tap(f"box{idx}", box)
+        geo = (m.h_roi_size, m.w_roi_size, m.eval_h_roi_size, m.eval_w_roi_size)
+        roi = ops.roi_resample(skip, box, (h, w), *geo, direction=0)
+        self._tap(f"roi_in{idx}", roi)
+        t = self._conv_in_act(roi, br["down"], stride=(2, 2, 2))
+        t = self._transformer(t, br, f"bridge{idx}")
+        t = self._conv_in_act(t, br["up"], up2=True)
+        if t.shape[1:4] != roi.shape[1:4]:
+            raise RuntimeError(f"ROI bridge {idx}: up_embed output {tuple(t.shape)} does not match the ROI "
+                               f"{tuple(roi.shape)} (depth must be even at this level)")
+        self._tap(f"roi_out{idx}", t)
+        return ops.roi_resample(t, box, (h, w), *geo, direction=1)
+
+    # -- forward -------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("lintransunet_b200.MaskTransUnet runs on CUDA (sm_100a) only; there is no CPU path")
+        if self.training:
+            if self.dropout and self.dropout > 0:
+                raise NotImplementedError("training-mode dropout is not implemented (forward hot path only); "
+                                          "construct with dropout=0.0 or call .eval()")
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                raise NotImplementedError("backward is not implemented yet (SURVEY 8f-1): wrap the call in "
+                                          "torch.no_grad()")
+        B, _, H, W, D = x.shape
+        if H % 32 or W % 32 or D % 4:
+            raise ValueError("H and W must be multiples of 32 and D a multiple of 4")
+        dtype = self._compute_dtype()
+        with torch.no_grad(), torch.autocast("cuda", enabled=False):
+            plan = self._plan(x.device, dtype)
+            out = self._forward_impl(x.contiguous().float(), plan, head="train" if self.training else "eval")
+        return out
+
+    def _forward_impl(self, x: torch.Tensor, P: _Plan, head: str):
+        n = len(self.num_layers)
+        # ---- Encoder.forward (model/Unet_3Dblock.py:596-607)
+        a = ops.s2d_input(x, P.dtype)
+        a = self._conv_in_act(a, P.stem)
+        skips = []
+        for i, (c1, c2, stride) in enumerate(P.down):
+            s = self._conv_in_act(a, c1, residual=a)                 # DownBlock :327-331
+            skips.append(s)
+            self._tap(f"skip{i}", s)
+            a = self._conv_in_act(s, c2, stride=stride)             # :335-336
+        self._tap("bottle", a)
+        # ---- ROIDecoder.forward (:1359-1396)
+        x = self._transformer(a, P.bridges[n - 1], "bridge_bottle")
+        self._tap(f"bridge{n-1}", x)
+        mask_list = []
+        for i in range(1, n):
+            x = ops.upsample_trilinear(x, 2 if (n - i) % 2 == 0 else 1)          # :1375-1378
+            lvl = n - 1 - i
+            logits, _, _ = self._conv(x, P.mask[lvl], pad=1, out_f32=True)       # :1380
+            mask, fg = ops.mask_softmax(logits, want_mask=(head == "train"))
+            if mask is not None:
+                mask_list.append(mask)
+            skip = skips[-i]
+            wx, wg, psi_w, psi_b = P.gate[lvl]
+            ga, pa, _ = self._conv(skip, wx, pad=0, want_stats=True)             # SpatialAttention3DBlock :217-221
+            gg, pg, _ = self._conv(x, wg, pad=0, want_stats=True)
+            V = skip.shape[1] * skip.shape[2] * skip.shape[3]
+            skip = ops.gate_fused(ga, ops.instnorm_finalize(pa, V), gg, ops.instnorm_finalize(pg, V),
+                                  psi_w, psi_b, skip)                            # :1384-1385
+            br = P.bridges[lvl]
+            if br is not None:
+                skip = self._roi_bridge(skip, fg, br, lvl)                       # :1387-1388
+            self._tap(f"bridge{lvl}", skip)
+            c1, c2 = P.up[i - 1]
+            x = self._conv_in_act(x, c1)                                         # UpBlock :547-550
+            x = self._conv_in_act(x, c2, x1=skip)                                # cat + conv2 :553-554
+            self._tap(f"up{i-1}", x)
+        logits, _, _ = self._conv(x, P.final, pad=1, out_f32=True)               # :1392
+        self._tap("logits", logits)
+        if head == "logits":
+            return logits
+        probs, onehot, labels = ops.head_d2s_softmax(logits, self.dim_output, want_probs=(head == "train"),
+                                                     want_onehot=(head == "eval"), want_labels=(head == "labels"))
+        if head == "train":
+            return probs, mask_list
+        return onehot if head == "eval" else labels
+
+    @torch.no_grad()
+    def predict_labels(self, x: torch.Tensor) -> torch.Tensor:
+        """Eval forward returning the argmax class per voxel as uint8 [B,H,W,D]: the information of
+        the reference's one-hot eval output (trans_3DUnet.py:199-201) without materialising it.
+        Used by the sliding-window driver."""
+        if not x.is_cuda:
+            raise RuntimeError("lintransunet_b200.MaskTransUnet runs on CUDA (sm_100a) only; there is no CPU path")
+        dtype = self._compute_dtype()
+        with torch.autocast("cuda", enabled=False):
+            return self._forward_impl(x.contiguous().float(), self._plan(x.device, dtype), head="labels")
+
+    @torch.no_grad()
+    def forward_logits(self, x: torch.Tensor) -> torch.Tensor:
+        """The `decode.final_block` tap as fp32 channels-last [B,H/2,W/2,D,4*dim_output]."""
+        dtype = self._compute_dtype()
+        with torch.autocast("cuda", enabled=False):
+            return self._forward_impl(x.contiguous().float(), self._plan(x.device, dtype), head="logits")
+
+
+Model_Dict = {"MaskTransUnet": MaskTransUnet}
+
+
+def get_model_dict(name: str):
+    """model/trans_3DUnet.py:215-222.  Only MaskTransUnet is alive in the reference."""
+    if name not in Model_Dict:
+        raise KeyError(f"{name}: only MaskTransUnet is provided (the reference's other four registry entries "
+                       "crash in the reference itself)")
+    return Model_Dict[name]

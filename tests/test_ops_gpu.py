@@ -1,0 +1,363 @@
+"""GPU parity of every C-ABI kernel against the CPU oracle (oracle/ltu_oracle.py) and the
+reference-generated golden vectors, called through lintransunet_b200.ops (ctypes -> C ABI).
+
+Tolerances (max|a-b| / max|ref|): fp32 storage 1e-4 for the transcendental kernels (ex2-based
+exp) and 2e-5 for pure FMA kernels; bf16 storage 1.2e-2 (one bf16 rounding of the output is
+2^-9 = 2e-3 relative per element, plus bf16 inputs).  Integer / index results are bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ltu_oracle as O
+from tests.helpers import load_golden, rel_err, sub
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16]
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1.2e-2}
+
+
+def _ops():
+    from lintransunet_b200 import ops
+    return ops
+
+
+def to_cl(t):       # reference [B,C,H,W,D] -> channels-last [B,H,W,D,C]
+    return t.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def from_cl(t):
+    return t.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def rnd(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def q_(t, dtype):   # round through the storage dtype so both sides see the same inputs
+    return t.to(dtype).float()
+
+
+# ------------------------------------------------------------------------------ a1
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,h,N", [(2, 4, 100), (1, 8, 333), (1, 8, 31), (3, 4, 4096), (1, 4, 57408 // 4 + 5),
+                                   (2, 8, 512), (1, 8, 1), (1, 2, 700), (1, 1, 65)])
+def test_attention_core(dtype, B, h, N):
+    ops = _ops()
+    C = 32 * h
+    qkv = q_(rnd((B, N, 3 * C), 10 + N, 2.0), dtype)
+    dev = qkv.to("cuda", dtype)
+    q, k, v = dev[..., :C], dev[..., C:2 * C], dev[..., 2 * C:]
+    ctx = ops.kv_reduce(k, v, h)
+    out = ops.q_readout(q, ctx, h)
+    split = lambda t: t.view(B, N, h, 32).transpose(1, 2)
+    rq, rk, rv = (split(qkv[..., i * C:(i + 1) * C]) for i in range(3))
+    ref_ctx = torch.softmax(rk, -2).transpose(-1, -2) @ rv
+    ref = O.efficient_attention(rq, rk, rv).transpose(1, 2).reshape(B, N, C)
+    assert rel_err(ctx, ref_ctx) < 1e-4                       # ctx is fp32 in both storage modes
+    assert rel_err(out.float(), ref) < TOL[dtype]
+    # determinism: the two-stage reduction has a fixed order
+    assert torch.equal(ctx, ops.kv_reduce(k, v, h))
+
+
+def test_attention_core_golden():
+    ops = _ops()
+    g = load_golden("ops.npz")
+    for tag in ("a", "b"):
+        q, k, v = (torch.from_numpy(g[f"attn_{tag}_{n}"]) for n in "qkv")       # [B,h,N,32]
+        B, h, N, _ = q.shape
+        merge = lambda t: t.transpose(1, 2).reshape(B, N, h * 32).contiguous().cuda()
+        out = ops.q_readout(merge(q), ops.kv_reduce(merge(k), merge(v), h), h)
+        ref = torch.from_numpy(g[f"attn_{tag}_out"]).transpose(1, 2).reshape(B, N, h * 32)
+        assert rel_err(out, ref) < 1e-4
+
+
+def test_attention_core_large_logits_are_stable():
+    """Online max-rescaling: shifted keys/queries must not overflow (softmax is shift invariant)."""
+    ops = _ops()
+    B, h, N = 1, 4, 1000
+    C = 128
+    qkv = rnd((B, N, 3 * C), 3, 3.0)
+    qkv[..., :2 * C] += 80.0
+    qkv[:, 500:, C:2 * C] += 40.0        # the running max changes in the middle of the stream
+    dev = qkv.cuda()
+    out = ops.q_readout(dev[..., :C], ops.kv_reduce(dev[..., C:2 * C], dev[..., 2 * C:], h), h)
+    split = lambda t: t.view(B, N, h, 32).transpose(1, 2).double()
+    ref = O.efficient_attention(*(split(qkv[..., i * C:(i + 1) * C]) for i in range(3)))
+    ref = ref.transpose(1, 2).reshape(B, N, C)
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 2e-4
+
+
+# ------------------------------------------------------------------------------ a3 / a4
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,C", [(77, 128), (1000, 256), (1, 256), (4097, 128)])
+def test_add_layernorm(dtype, rows, C):
+    ops = _ops()
+    x, r = q_(rnd((rows, C), 1), dtype), q_(rnd((rows, C), 2), dtype)
+    g, b = 1 + 0.1 * rnd((C,), 3), 0.1 * rnd((C,), 4)
+    y = ops.add_layernorm(x.to("cuda", dtype), r.to("cuda", dtype), g.cuda(), b.cuda(), 1e-6)
+    ref = F.layer_norm(x + r, (C,), g, b, eps=1e-6)
+    assert rel_err(y.float(), ref) < (2e-5 if dtype == torch.float32 else TOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gelu(dtype):
+    ops = _ops()
+    x = q_(rnd((333, 512), 5, 2.0), dtype)
+    y = ops.gelu_(x.to("cuda", dtype).clone())
+    assert rel_err(y.float(), F.gelu(x)) < (2e-6 if dtype == torch.float32 else TOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(1, 128, 5, 4, 6), (2, 256, 3, 3, 8), (1, 128, 1, 1, 1), (1, 256, 2, 7, 1)])
+def test_posenc(dtype, shape):
+    ops = _ops()
+    from lintransunet_b200.unet import Conv3dPosEmbedding, _pos_w
+    B, C, H, W, D = shape
+    pe = Conv3dPosEmbedding(C)
+    x = q_(rnd(shape, 6), dtype)
+    w, b = _pos_w(pe)
+    y = ops.posenc_dwconv3(to_cl(x).to("cuda", dtype), w.cuda(), b.cuda())
+    ref = O.pos_embedding(x, pe.proj.weight.detach(), pe.proj.bias.detach())
+    assert rel_err(from_cl(y.float()), ref) < (2e-5 if dtype == torch.float32 else TOL[dtype])
+
+
+def test_posenc_golden():
+    ops = _ops()
+    from lintransunet_b200.unet import Conv3dPosEmbedding, _pos_w
+    g = load_golden("ops.npz")
+    sd = O.make_state_dict(O.UnetConfig(), seed=3)
+    pe = Conv3dPosEmbedding(128)
+    p = "decode.bridge_list.1.transformer.pos_encoder.proj"
+    pe.load_state_dict({"proj.weight": sd[p + ".weight"], "proj.bias": sd[p + ".bias"]})
+    w, b = _pos_w(pe)
+    y = ops.posenc_dwconv3(to_cl(torch.from_numpy(g["pos_x"])).cuda(), w.cuda(), b.cuda())
+    assert rel_err(from_cl(y), g["pos_out"]) < 2e-5
+
+
+# ------------------------------------------------------------------------------ convolutions
+CONV_CASES = [
+    # cin, cin1, cout, k, stride, up2, spatial (H,W,D), out_f32
+    (4, 0, 16, 3, (1, 1, 1), False, (8, 6, 10), False),        # stem
+    (16, 0, 16, 3, (1, 1, 1), False, (6, 5, 9), False),
+    (16, 0, 32, 3, (2, 2, 1), False, (8, 6, 7), False),        # DownBlock conv2, stride (2,2,1)
+    (32, 0, 64, 3, (2, 2, 2), False, (6, 8, 6), False),
+    (128, 0, 256, 3, (2, 2, 2), False, (4, 4, 4), False),
+    (64, 0, 2, 3, (1, 1, 1), False, (5, 4, 6), True),          # mask head (fp32 logits)
+    (16, 0, 12, 3, (1, 1, 1), False, (7, 5, 4), True),         # final block, 3 classes
+    (32, 0, 16, 1, (1, 1, 1), False, (5, 6, 7), False),        # gate W_g 1x1x1
+    (16, 16, 16, 3, (1, 1, 1), False, (6, 6, 5), False),       # UpBlock conv2 on cat(x, skip)
+    (128, 128, 128, 3, (1, 1, 1), False, (3, 4, 4), False),
+    (128, 0, 32, 3, (1, 1, 1), True, (3, 4, 5), False),        # up_embed: nearest x2 folded in
+    (32, 0, 128, 3, (2, 2, 2), False, (10, 6, 8), False),      # down_embed
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("tc", [False, True])
+def test_conv3d(dtype, case, tc):
+    ops = _ops()
+    from lintransunet_b200.unet import _ConvW
+    cin, cin1, cout, k, stride, up2, (H, W, D), out_f32 = case
+    if tc and dtype != torch.bfloat16:
+        pytest.skip("tensor-core path is bf16 only")
+    B = 2
+    conv = torch.nn.Conv3d(cin + cin1, cout, k, stride=stride, padding=k // 2)
+    with torch.no_grad():
+        conv.weight.copy_(q_(conv.weight, dtype) if tc else conv.weight)
+    cw = _ConvW(conv, want_tc=tc)
+    x0 = q_(rnd((B, cin, H, W, D), 7), dtype)
+    x1 = q_(rnd((B, cin1, H, W, D), 8), dtype) if cin1 else None
+    xin = x0 if x1 is None else torch.cat((x0, x1), 1)
+    if up2:
+        xin = F.interpolate(xin, scale_factor=2, mode="nearest")
+    ref = F.conv3d(xin, conv.weight.detach(), conv.bias.detach(), stride=stride, padding=k // 2)
+    dev = lambda t: None if t is None else to_cl(t).to("cuda", dtype)
+    y, partials, tiles = ops.conv3d(dev(x0), cw.w.cuda(), cw.b.cuda(), cout, k, stride=stride, pad=k // 2,
+                                    x1=dev(x1), up2=up2, out_f32=out_f32, want_stats=True,
+                                    w_tc=cw.w_tc.cuda() if tc else None)
+    assert y.dtype == (torch.float32 if out_f32 else dtype)
+    tol = 2e-5 if (dtype == torch.float32 or out_f32) and not tc else TOL[torch.bfloat16]
+    if dtype == torch.bfloat16 and out_f32 and not tc:
+        tol = 2e-5                                          # bf16 inputs, fp32 math, fp32 output
+    assert rel_err(from_cl(y.float()), ref) < tol
+    # InstanceNorm statistics come from the fp32 accumulators
+    V = ref.shape[2] * ref.shape[3] * ref.shape[4]
+    stats = ops.instnorm_finalize(partials, V)
+    mean = ref.mean(dim=(2, 3, 4))
+    rstd = 1 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5)
+    assert rel_err(stats[..., 0], mean) < 5e-3 and rel_err(stats[..., 1], rstd) < 5e-3
+    if not out_f32:
+        res = q_(rnd(ref.shape, 9), dtype)
+        z = ops.instnorm_apply(y.clone(), stats, ops.ACT_LRELU, residual=to_cl(res).to("cuda", dtype), inplace=True)
+        ref_z = F.leaky_relu(F.instance_norm(from_cl(y.float()).cpu(), eps=1e-5), 0.01) + res
+        assert rel_err(from_cl(z.float()), ref_z) < (1e-4 if dtype == torch.float32 else TOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_chan_stats(dtype):
+    ops = _ops()
+    x = q_(rnd((2, 32, 9, 7, 11), 12) * 3 + 1.5, dtype)
+    stats = ops.chan_stats(to_cl(x).to("cuda", dtype))
+    assert rel_err(stats[..., 0], x.mean(dim=(2, 3, 4))) < 1e-5
+    assert rel_err(stats[..., 1], 1 / torch.sqrt(x.var(dim=(2, 3, 4), unbiased=False) + 1e-5)) < 1e-5
+
+
+# ------------------------------------------------------------------------------ plumbing
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_s2d_input(dtype):
+    ops = _ops()
+    x = rnd((2, 1, 8, 12, 5), 13)
+    y = ops.s2d_input(x.cuda(), dtype)
+    assert torch.equal(from_cl(y.float()).cpu(), O.space_to_depth(x).to(dtype).float())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("fd", [1, 2])
+@pytest.mark.parametrize("shape", [(2, 16, 3, 4, 5), (1, 256, 1, 1, 4), (1, 32, 4, 4, 16)])
+def test_upsample_trilinear(dtype, fd, shape):
+    ops = _ops()
+    x = q_(rnd(shape, 14), dtype)
+    y = ops.upsample_trilinear(to_cl(x).to("cuda", dtype), fd)
+    ref = O.trilinear_up(x, (2, 2, fd))
+    assert rel_err(from_cl(y.float()), ref) < (2e-6 if dtype == torch.float32 else TOL[dtype])
+
+
+@pytest.mark.parametrize("cout", [2, 3])
+def test_mask_softmax(cout):
+    ops = _ops()
+    l = rnd((2, cout, 5, 6, 7), 15, 2.0)
+    mask, fg = ops.mask_softmax(to_cl(l).cuda(), want_mask=True)
+    ref = torch.softmax(l, 1)
+    assert rel_err(mask, ref) < 2e-6
+    assert rel_err(fg, 1 - ref[:, 0]) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("ci,cu", [(16, 32), (128, 256), (64, 128)])
+def test_attention_gate(dtype, ci, cu):
+    ops = _ops()
+    from lintransunet_b200.unet import SpatialAttention3DBlock, _ConvW
+    blk = SpatialAttention3DBlock(ci, cu, ci)
+    skip, up = q_(rnd((2, ci, 5, 4, 6), 16), dtype), q_(rnd((2, cu, 5, 4, 6), 17), dtype)
+    sd = {"g." + k: v.detach() for k, v in blk.state_dict().items()}
+    ref = skip * O.attention_gate(skip, up, sd, "g")
+    wx, wg = _ConvW(blk.W_x[0], False), _ConvW(blk.W_g[0], False)
+    s_cl, u_cl = to_cl(skip).to("cuda", dtype), to_cl(up).to("cuda", dtype)
+    a, pa, _ = ops.conv3d(s_cl, wx.w.cuda(), wx.b.cuda(), ci, 1, pad=0, want_stats=True)
+    g, pg, _ = ops.conv3d(u_cl, wg.w.cuda(), wg.b.cuda(), ci, 1, pad=0, want_stats=True)
+    V = 5 * 4 * 6
+    out = ops.gate_fused(a, ops.instnorm_finalize(pa, V), g, ops.instnorm_finalize(pg, V),
+                         blk.psi[0].weight.detach().reshape(-1).cuda(), blk.psi[0].bias.detach().cuda(), s_cl)
+    assert rel_err(from_cl(out.float()), ref) < (1e-4 if dtype == torch.float32 else 2.5e-2)
+
+
+def _golden_masks(g):
+    shape = tuple(int(s) for s in g["box_masks_shape"])
+    bits = np.unpackbits(g["box_masks_packed"])[: int(np.prod(shape))]
+    return torch.from_numpy(bits.reshape(shape).astype(np.float32))
+
+
+def test_roi_bbox_bit_exact():
+    ops = _ops()
+    g = load_golden("ops.npz")
+    masks = _golden_masks(g)                                   # [5,1,96,96,8]
+    rc = O.UnetConfig().roi_consts(1)
+    box = ops.roi_bbox(masks[:, 0].contiguous().cuda(), rc["min_h"], rc["min_w"], 0.5)
+    assert np.array_equal(box.cpu().numpy(), g["box_out"])
+    # random soft masks at several plane sizes, including degenerate (S < min_roi) ones
+    for i, (h, w, d) in enumerate([(16, 16, 8), (32, 24, 16), (128, 96, 4), (7, 5, 3)]):
+        fg = torch.rand(3, 1, h, w, d, generator=torch.Generator().manual_seed(20 + i)) ** (i + 1)
+        fg[1] = 0
+        for lvl in (1, 2, 3):
+            rc = O.UnetConfig().roi_consts(lvl)
+            ref = O.roi_boxes(fg, rc["min_h"], rc["min_w"])
+            got = ops.roi_bbox(fg[:, 0].contiguous().cuda(), rc["min_h"], rc["min_w"], 0.5)
+            assert np.array_equal(got.cpu().numpy(), ref.numpy()), (h, w, d, lvl)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_roi_resample_golden_and_oracle(dtype):
+    ops = _ops()
+    g = load_golden("ops.npz")
+    rc = O.UnetConfig().roi_consts(1)
+    box = torch.from_numpy(g["box_out"])
+    feat = torch.randn(5, 4, 96, 96, 8, generator=torch.Generator().manual_seed(int(g["resample_feat_seed"])))
+    feat8 = q_(torch.cat([feat, feat * 0.5], 1), dtype)        # 8 channels: one bf16 vector
+    geo = (rc["h_roi"], rc["w_roi"], rc["eval_h"], rc["eval_w"])
+    roi = ops.roi_resample(to_cl(feat8).to("cuda", dtype), box.cuda(), (96, 96), *geo, direction=0)
+    back = ops.roi_resample(roi, box.cuda(), (96, 96), *geo, direction=1)
+    x0, y0, x1, y1 = box[:, 0:1], box[:, 1:2], box[:, 3:4], box[:, 4:5]
+    ref_roi = O.separable_resample(feat8, O.fisheye_forward_coords(x0, x1, 95, geo[0], geo[2]),
+                                   O.fisheye_forward_coords(y0, y1, 95, geo[1], geo[3]))
+    ref_back = O.separable_resample(from_cl(roi.float()).cpu(), O.fisheye_back_coords(x0, x1, 95, geo[0], geo[2]),
+                                    O.fisheye_back_coords(y0, y1, 95, geo[1], geo[3]))
+    tol = 1e-5 if dtype == torch.float32 else TOL[dtype]
+    assert rel_err(from_cl(roi.float()), ref_roi) < tol
+    assert rel_err(from_cl(back.float()), ref_back) < tol
+    if dtype == torch.float32:                                 # against the unmodified reference
+        assert rel_err(sub(from_cl(roi)[:, :4], 65536), g["resample_roi"]) < 1e-5
+        assert rel_err(sub(from_cl(back)[:, :4], 65536), g["resample_back"]) < 1e-5
+
+
+def test_roi_resample_degenerate_box_is_all_zero():
+    """at the BASELINE patch shapes x0 > x1 and every sample falls outside the map."""
+    ops = _ops()
+    rc = O.UnetConfig().roi_consts(3)
+    box = torch.tensor([[6.5, 3.5, 0.0, -4.5, -1.5, 7.0]])
+    x = rnd((1, 4, 4, 8, 128), 31).cuda()
+    roi = ops.roi_resample(x, box.cuda(), (4, 4), rc["h_roi"], rc["w_roi"], rc["eval_h"], rc["eval_w"], 0)
+    assert roi.shape == (1, 30, 18, 8, 128) and float(roi.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cout", [2, 3])
+def test_head(cout):
+    ops = _ops()
+    logits = rnd((2, 4 * cout, 6, 5, 7), 40, 1.5)
+    probs, _, _ = ops.head_d2s_softmax(to_cl(logits).cuda(), cout, True, False, False)
+    _, onehot, labels = ops.head_d2s_softmax(to_cl(logits).cuda(), cout, False, True, True)
+    ref = torch.softmax(O.depth_to_space(logits), 1)
+    assert rel_err(probs, ref) < 2e-6
+    idx = ref.argmax(1)
+    assert float((labels.cpu().long() != idx).float().mean()) < 1e-4
+    assert torch.equal(onehot.argmax(1).cpu(), labels.cpu().long()) and float(onehot.sum(1).min()) == 1.0
+
+
+def test_vote_accumulate_and_argmax():
+    ops = _ops()
+    g = torch.Generator().manual_seed(50)
+    C, H, W, D, r = 3, 12, 16, 8, 8
+    starts = torch.tensor([[0, 0, 0], [4, 0, 0], [4, 8, 0], [0, 8, 0], [2, 4, 0]], dtype=torch.int32)
+    labels = torch.randint(0, C, (5, r, r, r), generator=g, dtype=torch.uint8)
+    votes = torch.zeros(C, H, W, D, dtype=torch.uint8, device="cuda")
+    ops.vote_accumulate(labels.cuda(), starts.cuda(), votes)
+    ref = np.zeros((C, H, W, D), np.int64)
+    for n in range(5):
+        h0, w0, d0 = starts[n].tolist()
+        for c in range(C):
+            ref[c, h0:h0 + r, w0:w0 + r, d0:d0 + r] += (labels[n].numpy() == c)
+    assert np.array_equal(votes.cpu().numpy().astype(np.int64), ref)
+    assert np.array_equal(ops.vote_argmax(votes).cpu().numpy(), ref.argmax(0).astype(np.uint8))
+
+
+# ------------------------------------------------------------------------------ block level
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_encoder_layer_golden(dtype):
+    from lintransunet_b200 import MaskTransUnet
+    from lintransunet_b200.unet import SelfAttentionLayer, _LayerW
+    g = load_golden("ops.npz")
+    sd = O.make_state_dict(O.UnetConfig(), seed=3)
+    pre = "decode.bridge_list.1.transformer.layers.2"
+    layer = SelfAttentionLayer(128, 4)
+    layer.load_state_dict({k[len(pre) + 1:]: v for k, v in sd.items() if k.startswith(pre + ".")})
+    layer.cuda()
+    m = MaskTransUnet.__new__(MaskTransUnet)          # only _encoder_layer is exercised
+    x = torch.from_numpy(g["layer_x"])
+    y = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
+    assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2)
