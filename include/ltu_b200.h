@@ -84,11 +84,13 @@ int ltu_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int Hi, 
                float* partials, int dtype, ltu_stream_t stream);
 
 /* tcgen05 (UTCHMMA) implicit-GEMM path of the same convolution for bf16 activations:
- * weight_bf16 packed [taps][Cout][C0+C1] (K-major B operand).  Requirements: ksize 3, pad 1,
- * (C0+C1) % 16 == 0, C0 % 16 == 0, Cout % 16 == 0 and Cout <= 256.  Same partials layout with
- * tiles = ltu_conv3d_tc_tiles(out_voxels).                                                    */
+ * weight_bf16 packed [Cout][Kpad] (K-major B operand), K index = tap*(C0+C1) + c, zero padded
+ * to Kpad = ltu_conv3d_tc_kpad(C0+C1) (multiple of 64).  Requirements (ltu_conv3d_tc_supported):
+ * ksize 3, pad 1, C0+C1 a power of two >= 16, C0 % 8 == 0, Cout % 16 == 0, Cout <= 256.
+ * Output is bf16.  Same partials layout with tiles = ltu_conv3d_tc_tiles(out_voxels).          */
 int ltu_conv3d_tc_supported(int C0, int C1, int Cout, int ksize, int pad);
 int ltu_conv3d_tc_tiles(int64_t out_voxels);
+int ltu_conv3d_tc_kpad(int Cin);
 int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di,
                   int up2, int sh, int sw, int sd, const void* weight_bf16, const float* bias,
                   int Cout, void* out, int Ho, int Wo, int Do, float* partials,

@@ -159,6 +159,10 @@ conv3d_kernel(const ConvParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             o[j] = acc[i][j] + bs[j];
+            // statistics are taken from the value AS STORED (rounded to the storage type), like
+            // instance_norm on the conv output: a (near-)constant channel then normalises to ~0
+            // instead of amplifying its own rounding error by rstd
+            if (!p.out_f32) o[j] = to_f32(from_f32<T>(o[j]));
             csum[j] += o[j];
             csq[j] = fmaf(o[j], o[j], csq[j]);
         }

@@ -1,11 +1,358 @@
-// tcgen05 implicit-GEMM convolution (bf16 in, fp32 accumulate in TMEM) -- placeholder entry
-// points until the kernel lands; ltu_conv3d_tc_supported() == 0 keeps callers on conv_kernels.cu.
+// Family 2 (bf16 path): implicit-GEMM 3x3x3 convolution on the 5th-generation tensor cores.
+//
+//   D[M=128 output voxels, N=Cout] += A[M, K] * B[N, K]^T,   K = 27 taps x Cin  (bf16, fp32 accum)
+//
+// * one CTA = one tile of 128 consecutive output voxels of one sample x all Cout channels
+//   (Cout <= 256 = one UMMA N, accumulator = Cout TMEM columns);
+// * warps 0-3: im2col producers.  Thread r gathers row r of the A tile (one output voxel, 64 K
+//   values = 128 B) and its share of the weight tile with 16-byte cp.async into the canonical
+//   K-major SWIZZLE_128B shared-memory layout; zero-fill implements padding, the K tail and the
+//   ragged last tile.  Completion is tracked by mbarriers (cp.async.mbarrier.arrive.noinc);
+// * warp 4: one elected lane issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=Cout, K=16)
+//   and releases pipeline stages with tcgen05.commit;
+// * epilogue (warps 0-3 again): tcgen05.ld 32x32b, + bias, bf16 store, and the per-tile
+//   InstanceNorm partial sums (sum, sum of squares from the fp32 accumulators) reduced with a
+//   fixed-order transpose-butterfly => bit-reproducible.
+//
+// Input addressing covers stride 1/2 per axis, a second (channel-concatenated) input and the
+// on-the-fly nearest x2 upsample of up_embed (reference model/Unet_3Dblock.py:421-422, :553).
 #include "common.cuh"
+
+namespace ltu {
+
+void count_launch(int n = 1);
+
+constexpr int kTcM = 128;          // output voxels per tile
+constexpr int kTcBK = 64;          // K elements per pipeline stage (128 bytes of bf16 = one swizzle row)
+constexpr int kTcProducers = 128;
+constexpr int kTcThreads = 160;    // 4 producer/epilogue warps + 1 MMA warp
+
+struct TcParams {
+    const bf16* in0; const bf16* in1;
+    int C0, C1, log2cin;
+    int Hi, Wi, Di, up2;
+    int sh, sw, sd;
+    const bf16* weight;   // [Cout][Kpad]
+    int Kpad, Ktot;
+    const float* bias;
+    int Cout;
+    bf16* out;
+    int Ho, Wo, Do;
+    float* partials; int tiles;
+    int stages, tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (1024 B:
+//   8 rows x 128 B) | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Sum v[i] over the 32 lanes for all 32 columns with 31 shuffles: afterwards lane l holds the
+// total of column l.  Fixed butterfly order => deterministic.
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            float send = upper ? v[i] : v[i + s];
+            float keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+__global__ void __launch_bounds__(kTcThreads)
+conv3d_tc_kernel(const TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve: [stages][A 16 KB][B Cout*128 B] | barriers | tmem slot | stat staging
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = kTcM * 128;
+    const int b_bytes = p.Cout * 128;
+    const int stage_bytes = a_bytes + b_bytes;
+    unsigned char* tail = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);            // [stages]
+    uint64_t* empty_bar = full_bar + p.stages;                          // [stages]
+    uint64_t* done_bar = empty_bar + p.stages;                          // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+    float* sred = reinterpret_cast<float*>(tmem_slot + 2);              // [4][Cout][2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int64_t Vo = (int64_t)p.Ho * p.Wo * p.Do;
+    const int64_t vox0 = (int64_t)blockIdx.x * kTcM;
+    const int nkb = p.Kpad / kTcBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(full_bar + s), kTcProducers);
+            mbar_init(smem_u32(empty_bar + s), 1);
+        }
+        mbar_init(smem_u32(done_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // =========================== producers: im2col gather ===========================
+        const int r = threadIdx.x;                    // A-tile row == TMEM lane
+        int64_t id = vox0 + r;
+        const bool row_ok = id < Vo;
+        if (!row_ok) id = 0;
+        const int od = (int)(id % p.Do);
+        const int64_t t2 = id / p.Do;
+        const int ow = (int)(t2 % p.Wo), oh = (int)(t2 / p.Wo);
+        const int hb = oh * p.sh - 1, wb = ow * p.sw - 1, db = od * p.sd - 1;
+        const int He = p.up2 ? 2 * p.Hi : p.Hi, We = p.up2 ? 2 * p.Wi : p.Wi, De = p.up2 ? 2 * p.Di : p.Di;
+        const int Cin = p.C0 + p.C1;
+        const int64_t in_sample = (int64_t)p.Hi * p.Wi * p.Di;
+        const uint32_t a_row = r * 128;
+        const int sw7 = r & 7;
+        const int b_iters = p.Cout / 16;              // 8*Cout chunks over 128 threads
+
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int stage = kb % p.stages;
+            const uint32_t round = kb / p.stages;
+            mbar_wait(smem_u32(empty_bar + stage), (round & 1) ^ 1);
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t sb = sa + a_bytes;
+            // ---- A row: 8 chunks of 8 channels
+            int last_tap = -1;
+            const bf16* src_vox0 = nullptr; const bf16* src_vox1 = nullptr;
+            bool tap_ok = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int kk = kb * kTcBK + j * 8;
+                const int tap = kk >> p.log2cin;
+                const int c = kk & (Cin - 1);
+                if (tap != last_tap) {
+                    last_tap = tap;
+                    tap_ok = false;
+                    if (row_ok && kk < p.Ktot) {
+                        const int kh = tap / 9, kw = (tap / 3) % 3, kd = tap % 3;
+                        int hv = hb + kh, wv = wb + kw, dv = db + kd;
+                        if (hv >= 0 && hv < He && wv >= 0 && wv < We && dv >= 0 && dv < De) {
+                            if (p.up2) { hv >>= 1; wv >>= 1; dv >>= 1; }
+                            const int64_t vox = (int64_t)b * in_sample + ((int64_t)hv * p.Wi + wv) * p.Di + dv;
+                            src_vox0 = p.in0 + vox * p.C0;
+                            src_vox1 = p.in1 + vox * p.C1;
+                            tap_ok = true;
+                        }
+                    }
+                }
+                const bf16* src = tap_ok ? (c < p.C0 ? src_vox0 + c : src_vox1 + (c - p.C0)) : p.in0;
+                cp16(sa + a_row + ((j ^ sw7) << 4), src, tap_ok ? 16 : 0);
+            }
+            // ---- B tile: Cout rows x 8 chunks (weights are zero-padded to Kpad)
+            for (int i = 0; i < b_iters; ++i) {
+                const int q = r + i * kTcProducers;
+                const int n = q >> 3, j = q & 7;
+                cp16(sb + n * 128 + ((j ^ (n & 7)) << 4), p.weight + (int64_t)n * p.Kpad + kb * kTcBK + j * 8, 16);
+            }
+            cp_async_arrive_noinc(smem_u32(full_bar + stage));
+        }
+
+        // =========================== epilogue ===========================
+        mbar_wait(smem_u32(done_bar), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t out_row = ((int64_t)b * Vo + vox0 + r) * p.Cout;
+        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            const int ncol = (p.Cout - c0) < 32 ? (p.Cout - c0) : 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float bsv = (p.bias != nullptr && i < ncol) ? __ldg(p.bias + c0 + i) : 0.f;
+                // rounded to bf16 here so that the statistics describe the stored values
+                v[i] = (row_ok && i < ncol) ? __bfloat162float(__float2bfloat16_rn(v[i] + bsv)) : 0.f;
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g * 8 < ncol) {
+                        uint4 o;
+                        o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                        o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                        *reinterpret_cast<uint4*>(p.out + out_row + c0 + g * 8) = o;
+                    }
+                }
+            }
+            if (p.partials != nullptr) {
+                float sq[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+                float s = transpose_reduce32(v, lane);
+                float q = transpose_reduce32(sq, lane);
+                if (lane < ncol) {
+                    sred[((warp * p.Cout) + c0 + lane) * 2] = s;
+                    sred[((warp * p.Cout) + c0 + lane) * 2 + 1] = q;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (p.partials != nullptr) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int c = threadIdx.x; c < p.Cout; c += kTcProducers) {
+                float s = 0.f, q = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { s += sred[(w * p.Cout + c) * 2]; q += sred[(w * p.Cout + c) * 2 + 1]; }
+                float* dst = p.partials + (((int64_t)b * p.tiles + blockIdx.x) * p.Cout + c) * 2;
+                dst[0] = s; dst[1] = q;
+            }
+        }
+    } else {
+        // =========================== MMA issuer ===========================
+        // kind::f16 instruction descriptor: D=F32 (bit 4), A=B=BF16 (bits 7, 10), K-major A and B,
+        // N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int stage = kb % p.stages;
+            const uint32_t round = kb / p.stages;
+            mbar_wait(smem_u32(full_bar + stage), round & 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> UMMA (async proxy)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + a_bytes);
+#pragma unroll
+                for (int k = 0; k < kTcBK / 16; ++k)                        // +32 B per K=16 inside the swizzle row
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                umma_commit(smem_u32(empty_bar + stage));                   // frees the stage when the MMAs retire
+                if (kb == nkb - 1) umma_commit(smem_u32(done_bar));
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+static inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+}  // namespace ltu
+
 using namespace ltu;
-extern "C" int ltu_conv3d_tc_supported(int, int, int, int, int) { return 0; }
-extern "C" int ltu_conv3d_tc_tiles(int64_t out_voxels) { return (int)ceil_div64(out_voxels, 128); }
-extern "C" int ltu_conv3d_tc(const void*, int, const void*, int, int, int, int, int, int, int, int, int, const void*,
-                             const float*, int, void*, int, int, int, float*, ltu_stream_t) {
-    set_error("conv3d_tc: not built");
-    return LTU_ERR_ARG;
+
+extern "C" int ltu_conv3d_tc_supported(int C0, int C1, int Cout, int ksize, int pad) {
+    const int Cin = C0 + C1;
+    if (ksize != 3 || pad != 1) return 0;
+    if (!is_pow2(Cin) || Cin < 16 || Cin > 1024) return 0;
+    if (C0 % 8 != 0 || C1 % 8 != 0) return 0;
+    if (Cout % 16 != 0 || Cout < 16 || Cout > 256) return 0;
+    return 1;
+}
+
+extern "C" int ltu_conv3d_tc_tiles(int64_t out_voxels) { return (int)ceil_div64(out_voxels, kTcM); }
+
+extern "C" int ltu_conv3d_tc_kpad(int Cin) { return (int)ceil_div64((int64_t)27 * Cin, kTcBK) * kTcBK; }
+
+extern "C" int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di, int up2,
+                             int sh, int sw, int sd, const void* weight_bf16, const float* bias, int Cout, void* out,
+                             int Ho, int Wo, int Do, float* partials, ltu_stream_t stream) {
+    LTU_ARG_CHECK(in0 && weight_bf16 && out, "conv3d_tc: null pointer");
+    LTU_ARG_CHECK(ltu_conv3d_tc_supported(C0, C1, Cout, 3, 1), "conv3d_tc: unsupported channels C0=%d C1=%d Cout=%d", C0, C1, Cout);
+    LTU_ARG_CHECK((in1 != nullptr) == (C1 > 0), "conv3d_tc: in1/C1 mismatch");
+    LTU_ARG_CHECK(B > 0 && B <= 65535 && Hi > 0 && Wi > 0 && Di > 0, "conv3d_tc: bad shape");
+    LTU_ARG_CHECK(sh >= 1 && sh <= 2 && sw >= 1 && sw <= 2 && sd >= 1 && sd <= 2, "conv3d_tc: stride must be 1 or 2");
+    LTU_ARG_CHECK(!up2 || (sh == 1 && sw == 1 && sd == 1), "conv3d_tc: up2 needs stride 1");
+    const int He = up2 ? 2 * Hi : Hi, We = up2 ? 2 * Wi : Wi, De = up2 ? 2 * Di : Di;
+    LTU_ARG_CHECK(Ho == (He - 1) / sh + 1 && Wo == (We - 1) / sw + 1 && Do == (De - 1) / sd + 1,
+                  "conv3d_tc: output size does not match the geometry");
+    LTU_ARG_CHECK(((uintptr_t)in0 & 15) == 0 && ((uintptr_t)in1 & 15) == 0 && ((uintptr_t)weight_bf16 & 15) == 0 &&
+                  ((uintptr_t)out & 15) == 0, "conv3d_tc: pointers must be 16-byte aligned");
+    TcParams p;
+    p.in0 = (const bf16*)in0; p.in1 = (const bf16*)in1; p.C0 = C0; p.C1 = C1; p.log2cin = ilog2(C0 + C1);
+    p.Hi = Hi; p.Wi = Wi; p.Di = Di; p.up2 = up2; p.sh = sh; p.sw = sw; p.sd = sd;
+    p.weight = (const bf16*)weight_bf16; p.Ktot = 27 * (C0 + C1); p.Kpad = ltu_conv3d_tc_kpad(C0 + C1);
+    p.bias = bias; p.Cout = Cout; p.out = (bf16*)out; p.Ho = Ho; p.Wo = Wo; p.Do = Do;
+    p.partials = partials; p.tiles = ltu_conv3d_tc_tiles((int64_t)Ho * Wo * Do);
+    int cols = 32; while (cols < Cout) cols <<= 1;
+    p.tmem_cols = cols;
+    const int stage_bytes = kTcM * 128 + Cout * 128;
+    // aim for 2 CTAs per SM (<= ~110 KB each), at least 2 and at most 6 stages
+    int stages = (108 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)4 * Cout * 2 * 4;
+    static thread_local int configured_dev = -1;
+    int dev; cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured_dev = dev;
+    }
+    conv3d_tc_kernel<<<dim3((unsigned)p.tiles, B), kTcThreads, smem, (cudaStream_t)stream>>>(p);
+    LTU_LAUNCH_CHECK("conv3d_tc");
+    count_launch(1);
+    return LTU_OK;
 }

@@ -199,7 +199,7 @@ class ROIDecoder(_Holder):
 # ----------------------------------------------------------------------------- packed weights
 class _ConvW:
     """Derived cache of one conv: fp32 [taps][Cin][Cout] for the CUDA-core kernel, bf16
-    [taps][Cout][Cin] for the tcgen05 kernel."""
+    [Cout][Kpad] (K-major) for the tcgen05 kernel."""
 
     def __init__(self, conv: nn.Conv3d, want_tc: bool):
         w = conv.weight.detach()
@@ -207,8 +207,14 @@ class _ConvW:
         self.k, self.cin, self.cout = k, cin, cout
         self.w = w.permute(2, 3, 4, 1, 0).reshape(k * k * k, cin, cout).contiguous().float()
         self.b = conv.bias.detach().float().contiguous() if conv.bias is not None else None
-        self.w_tc = (w.permute(2, 3, 4, 0, 1).reshape(k * k * k, cout, cin).contiguous().to(torch.bfloat16)
-                     if want_tc else None)
+        self.w_tc = None
+        if want_tc and k == 3:
+            # tcgen05 B operand: [Cout][Kpad], K index = tap*Cin + c, zero padded to a multiple of 64
+            ktot = 27 * cin
+            kpad = (ktot + 63) // 64 * 64
+            wt = torch.zeros(cout, kpad, dtype=torch.bfloat16, device=w.device)
+            wt[:, :ktot] = w.permute(0, 2, 3, 4, 1).reshape(cout, ktot).to(torch.bfloat16)
+            self.w_tc = wt
 
 
 class _LayerW:
