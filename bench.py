@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Headline benchmark: BASELINE.json metric "voxels/sec fwd (128^3 patch) at 1/2/4/8 B200;
+linear-attn HBM GB/s vs peak".
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference algorithm on the host CPU
+
+A step is one sliding-window inference of the multi-class MaskTransUnet (dim_output=3, random
+init, bf16) over a synthetic 512x512x256 CT volume: 128^3 windows, 50 % overlap => 147 windows,
+sw_batch_size 8 (BASELINE config 5, which runs the config-4 forward -- batch 8 of 128^3 patches --
+19 times).  Windows are dealt round-robin to the N ranks (one process per GPU, torchrun); the only
+collective is one NCCL all-reduce of the uint8 vote volume.  Total work is fixed => strong scaling.
+
+  value : window voxels / s = 147 * 128^3 * K / t, volume resident in HBM, CUDA events, max over ranks
+  e2e   : same, through lintransunet_b200.sliding_window.sliding_window_inference with the volume in
+          pinned host memory (H2D inside the timed region) and the stitched label volume read back
+  roofline / kernels : per-kernel CUDA-event timings of the timed steps vs MEASURED_PEAKS.json
+  cpu_baseline : the oracle (CPU port of the reference algorithm) on the box's host cores, one
+          128^3 window (N=1 only)
+
+The reference arm times the same oracle port (the reference is pure Python/PyTorch and cannot
+travel to the GPU box; oracle/ltu_oracle.py is pinned to it by tests/golden) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "voxels/sec fwd (128^3 patch)"
+VOLUME = (512, 512, 256)
+ROI = (128, 128, 128)
+OVERLAP = 0.5
+SW_BATCH = 8
+DIM_OUTPUT = 3
+MODEL_CFG = dict(num_layers=[16, 32, 64, 128, 256], roi_size_list=[100, 65, 40, 25, 10],
+                 is_roi_list=[False, True, True, True, True], dim_input=1, dim_output=DIM_OUTPUT)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), tensor=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained)")
+    return dict(hbm=6650.0, tensor=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def config_dict(n_gpus):
+    return {"workload": "config5: sliding-window inference, synthetic 512x512x256 volume, 128^3 windows, "
+                        "50% overlap (147 windows), sw_batch_size 8 (= config4 forward per batch), "
+                        "multi-class MaskTransUnet dim_output=3, eval, bf16 autocast",
+            "windows": 147, "sw_batch_size": SW_BATCH, "parallelism": f"window-sharded dp{n_gpus}",
+            "l2": "inputs larger than L2 (268 MB volume, 134 MB+ activations per layer)"}
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                bits = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def visible_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------- CPU oracle timing
+def oracle_window_seconds(steps: int, warmup: int, shape=(1, 1, 128, 128, 128)):
+    from oracle import ltu_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.UnetConfig(dim_output=DIM_OUTPUT)
+    sd = O.make_state_dict(cfg, seed=0)
+    x = O.make_input(shape, seed=1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.mask_trans_unet_forward(x, sd, cfg)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times, cores = oracle_window_seconds(args.steps, args.warmup)
+    vox = 128 ** 3
+    t = sum(times) / len(times)
+    sample = "one 1x1x128^3 window forward (fp32) per step, i.e. 1/147 of the volume; oracle port of the reference"
+    line = {"impl": "reference", "metric": METRIC, "value": vox / t, "unit": "voxels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": vox / t, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": vox / t, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from lintransunet_b200 import MaskTransUnet, _native, ops
+    from lintransunet_b200.sliding_window import sliding_window_inference
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)                                    # random-init weights of the architecture
+    model = MaskTransUnet(**MODEL_CFG).to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    vol_host = torch.randn((1, 1) + VOLUME, generator=g).pin_memory()
+    vol_dev = vol_host.to(dev)
+    n_windows = 147
+    win_vox = n_windows * ROI[0] * ROI[1] * ROI[2]
+
+    def step(x):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return sliding_window_inference(x, ROI, SW_BATCH, model, overlap=OVERLAP, return_labels=True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(vol_dev)
+    sync_all()
+
+    # ---- timed region 1: volume resident in HBM -------------------------------------------
+    sampler = ClockSampler(visible_index(local_rank))
+    sampler.start()
+    prof = ops.KernelProfiler()
+    ops.set_profiler(prof)
+    l0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step(vol_dev)
+    e1.record()
+    sync_all()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = _native.launch_count() - l0
+    ops.set_profiler(None)
+    ksum = prof.summary()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms_step = ms_total / args.steps
+
+    # ---- timed region 2: end to end through the public API with host buffers ----------------
+    out_host = torch.empty(VOLUME, dtype=torch.uint8).pin_memory()
+    sync_all()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        x = vol_host.to(dev, non_blocking=True)                        # H2D of the step's input
+        _, labels = step(x)
+        if rank == 0:
+            out_host.copy_(labels[0], non_blocking=True)               # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    sync_all()
+    # wall clock between two full synchronisations (every step ends with a stream sync for the D2H)
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)) / args.steps
+    h2d = vol_host.numel() * 4 * world
+    d2h = out_host.numel()
+
+    if world > 1:
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    if rank == 0:
+        pk = peaks()
+        kernels = {}
+        for name, d in ksum.items():
+            ms = d["ms"] / args.steps
+            gbs = d["bytes"] / d["ms"] / 1e6 if d["ms"] > 0 else 0.0
+            tfs = d["flops"] / d["ms"] / 1e9 if d["ms"] > 0 else 0.0
+            kernels[name] = {"launches_per_step": d["launches"] // args.steps, "ms_per_step": round(ms, 3),
+                             "share_of_step": round(ms / ms_step, 4), "GB/s": round(gbs, 1), "TFLOP/s": round(tfs, 2)}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))
+
+        def roof(name, bound):
+            d = ksum.get(name)
+            if not d or d["ms"] <= 0:
+                return None
+            if bound == "hbm":
+                a, p, u = d["bytes"] / d["ms"] / 1e6, pk["hbm"], "GB/s"
+            else:
+                a, p, u = d["flops"] / d["ms"] / 1e9, pk["tensor"], "TFLOP/s"
+            return {"kernel": name, "bound": bound, "achieved": round(a, 2), "peak": p, "unit": u,
+                    "frac": round(a / p, 4), "traffic": (traffic or {}).get(name), "peak_source": pk["source"],
+                    "algorithmic": "kv_reduce/q_readout: 2*B*N*C*E bytes each (K,V read | Q read + out written); "
+                                   "conv3d_tc: 2*27*Cin*Cout*B*Vout flop", "launches": d["launches"]}
+
+        dominant = max(ksum.items(), key=lambda kv: kv[1]["ms"])[0] if ksum else None
+        bound_of = {"conv3d_tc": "tensor", "conv3d": "tensor"}
+        roofline = roof(dominant, bound_of.get(dominant, "hbm")) if dominant else None
+        attn = {n: roof(n, "hbm") for n in ("kv_reduce", "q_readout")}
+        line = {"metric": METRIC, "value": win_vox / (ms_step / 1e3), "unit": "voxels/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": config_dict(args.gpus),
+                "volume_voxels_per_s": VOLUME[0] * VOLUME[1] * VOLUME[2] / (ms_step / 1e3),
+                "clocks": sampler.result(),
+                "e2e": {"value": win_vox / (ms_e2e / 1e3), "unit": "voxels/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "lintransunet_b200.sliding_window.sliding_window_inference"},
+                "gpu_launches": launches, "roofline": roofline, "linear_attn_roofline": attn, "kernels": kernels}
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            times, cores = oracle_window_seconds(1, 0)
+            line["cpu_baseline"] = {"value": 128 ** 3 / times[0], "unit": "voxels/s", "cores": cores, "kind": "port",
+                                    "sample": "one 1x1x128^3 window forward (fp32), 1/147 of the step; oracle port "
+                                              "of the reference on the host cores"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

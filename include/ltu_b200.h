@@ -162,6 +162,14 @@ int ltu_vote_accumulate(const uint8_t* labels, const int32_t* starts, uint8_t* v
  * torch.argmax over vote fractions with a common denominator)                                */
 int ltu_vote_argmax(const uint8_t* votes, uint8_t* labels, int C, int64_t voxels,
                     ltu_stream_t stream);
+/* votes uint8 [C,V] -> frac fp32 [C,V] = votes / sum_c votes: the stitched output_image/count_map
+ * of the constant-blend sliding window when every window prediction is one-hot                */
+int ltu_vote_fractions(const uint8_t* votes, float* frac, int C, int64_t voxels,
+                       ltu_stream_t stream);
+/* out fp32 [nwin,1,rh,rw,rd] = windows of volume fp32 [H,W,D] at starts int32 [nwin,3]
+ * (MONAI: torch.cat([inputs[win_slice] ...]))                                                  */
+int ltu_gather_windows(const float* volume, const int32_t* starts, float* out, int nwin, int rh,
+                       int rw, int rd, int H, int W, int D, ltu_stream_t stream);
 
 #ifdef __cplusplus
 }

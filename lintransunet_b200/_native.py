@@ -49,6 +49,8 @@ SIGNATURES = {
     "ltu_head_d2s_softmax": (I, [P, P, P, P, I, I, I, I, I, P]),
     "ltu_vote_accumulate": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
     "ltu_vote_argmax": (I, [P, P, I, L, P]),
+    "ltu_vote_fractions": (I, [P, P, I, L, P]),
+    "ltu_gather_windows": (I, [P, P, P, I, I, I, I, I, I, I, P]),
 }
 
 

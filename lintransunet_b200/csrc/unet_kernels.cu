@@ -240,6 +240,34 @@ vote_argmax_kernel(const uint8_t* __restrict__ votes, uint8_t* __restrict__ labe
     }
 }
 
+// votes uint8 [C,V] -> frac fp32 [C,V] = votes / sum_c votes  (MONAI: output_image / count_map with a
+// constant importance map and one-hot window predictions)
+__global__ void __launch_bounds__(256)
+vote_fractions_kernel(const uint8_t* __restrict__ votes, float* __restrict__ frac, int C, int64_t V) {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+        int tot = 0;
+        for (int c = 0; c < C; ++c) tot += votes[(int64_t)c * V + v];
+        float inv = 1.f / (float)tot;           // tot == 0 cannot happen: every voxel is covered by >= 1 window
+        for (int c = 0; c < C; ++c) frac[(int64_t)c * V + v] = (float)votes[(int64_t)c * V + v] * inv;
+    }
+}
+
+// out[n,0,h,w,d] = vol[sh+h, sw+w, sd+d]: batches sliding windows for the predictor
+__global__ void __launch_bounds__(256)
+gather_windows_kernel(const float* __restrict__ vol, const int32_t* __restrict__ starts, float* __restrict__ out,
+                      int rh, int rw, int rd, int H, int W, int D) {
+    const int win = blockIdx.y;
+    const int64_t wv = (int64_t)rh * rw * rd;
+    const int sh = starts[win * 3], sw = starts[win * 3 + 1], sd = starts[win * 3 + 2];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < wv; i += (int64_t)gridDim.x * blockDim.x) {
+        int d = (int)(i % rd);
+        int64_t t = i / rd;
+        int w = (int)(t % rw);
+        int h = (int)(t / rw);
+        out[(int64_t)win * wv + i] = vol[((int64_t)(sh + h) * W + (sw + w)) * D + (sd + d)];
+    }
+}
+
 static inline unsigned grid_for(int64_t items, int per_block, int waves) {
     int64_t b = ceil_div64(items, per_block);
     int64_t cap = (int64_t)sm_count() * waves;
@@ -363,6 +391,31 @@ extern "C" int ltu_vote_argmax(const uint8_t* votes, uint8_t* labels, int C, int
     unsigned g = grid_for(voxels, 256, 16);
     vote_argmax_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(votes, labels, C, voxels);
     LTU_LAUNCH_CHECK("vote_argmax");
+    count_launch(1);
+    return LTU_OK;
+}
+
+extern "C" int ltu_vote_fractions(const uint8_t* votes, float* frac, int C, int64_t voxels, ltu_stream_t stream) {
+    LTU_ARG_CHECK(votes && frac && C > 0 && voxels > 0, "vote_fractions: bad arguments");
+    unsigned g = grid_for(voxels, 256, 16);
+    vote_fractions_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(votes, frac, C, voxels);
+    LTU_LAUNCH_CHECK("vote_fractions");
+    count_launch(1);
+    return LTU_OK;
+}
+
+extern "C" int ltu_gather_windows(const float* volume, const int32_t* starts, float* out, int nwin, int rh, int rw,
+                                  int rd, int H, int W, int D, ltu_stream_t stream) {
+    LTU_ARG_CHECK(volume && starts && out, "gather_windows: null pointer");
+    LTU_ARG_CHECK(nwin > 0 && nwin <= 65535 && rh > 0 && rw > 0 && rd > 0 && rh <= H && rw <= W && rd <= D,
+                  "gather_windows: bad shape");
+    int64_t wv = (int64_t)rh * rw * rd;
+    int64_t bx = ceil_div64(wv, 256);
+    int64_t cap = ceil_div64((int64_t)sm_count() * 16, nwin);
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    gather_windows_kernel<<<dim3((unsigned)bx, nwin), 256, 0, (cudaStream_t)stream>>>(volume, starts, out, rh, rw, rd, H, W, D);
+    LTU_LAUNCH_CHECK("gather_windows");
     count_launch(1);
     return LTU_OK;
 }

@@ -47,22 +47,59 @@ def _chk(*ts: Optional[torch.Tensor]) -> torch.device:
     return dev
 
 
-class _Guard:
-    """Make `dev` current for the launch (DataParallel replicas run on foreign devices)."""
-    __slots__ = ("dev", "prev")
+class KernelProfiler:
+    """Per-kernel device timing with CUDA events on the launching stream (bench.py roofline):
+    every profiled launch records (name, start, end, algorithmic bytes, algorithmic flops)."""
 
-    def __init__(self, dev: torch.device):
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        """name -> dict(launches, ms, bytes, flops); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, e0, e1, nbytes, flops in self.records:
+            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0, flops=0))
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += nbytes
+            d["flops"] += flops
+        return out
+
+
+_profiler: Optional[KernelProfiler] = None
+
+
+def set_profiler(p: Optional[KernelProfiler]) -> None:
+    global _profiler
+    _profiler = p
+
+
+class _Guard:
+    """Make `dev` current for the launch (DataParallel replicas run on foreign devices) and, when a
+    KernelProfiler is installed, bracket the launch with CUDA events."""
+    __slots__ = ("dev", "prev", "prof", "e0")
+
+    def __init__(self, dev: torch.device, prof=None):
         self.dev = dev
         self.prev = None
+        self.prof = prof if _profiler is not None else None
+        self.e0 = None
 
     def __enter__(self):
         cur = torch.cuda.current_device()
         if self.dev.index is not None and self.dev.index != cur:
             self.prev = cur
             torch.cuda.set_device(self.dev)
+        if self.prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
         return c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def __exit__(self, *exc):
+        if self.prof is not None and _profiler is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profiler.records.append((self.prof[0], self.e0, e1, self.prof[1], self.prof[2]))
         if self.prev is not None:
             torch.cuda.set_device(self.prev)
         return False
@@ -79,7 +116,7 @@ def kv_reduce(k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
     if not (k.is_cuda and v.is_cuda):
         raise RuntimeError("lintransunet_b200 ops need CUDA tensors: there is no CPU fallback")
     L = _native.lib()
-    with _Guard(k.device) as st:
+    with _Guard(k.device, ("kv_reduce", 2 * B * N * C * k.element_size(), 2 * B * N * C * 32)) as st:
         ws_bytes = L.ltu_kv_reduce_workspace(B, N, heads)
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=k.device)
         ctx = torch.empty(B, heads, 32, 32, dtype=torch.float32, device=k.device)
@@ -97,7 +134,7 @@ def q_readout(q: torch.Tensor, ctx: torch.Tensor, heads: int) -> torch.Tensor:
     if not q.is_cuda:
         raise RuntimeError("lintransunet_b200 ops need CUDA tensors: there is no CPU fallback")
     out = torch.empty(B, N, C, dtype=q.dtype, device=q.device)
-    with _Guard(q.device) as st:
+    with _Guard(q.device, ("q_readout", 2 * B * N * C * q.element_size(), 2 * B * N * C * 32)) as st:
         check(_native.lib().ltu_q_readout(_p(q), q.stride(1), _p(ctx), _p(out), C, B, N, heads, _dt(q), st),
               "ltu_q_readout")
     return out
@@ -110,7 +147,7 @@ def add_layernorm(x: torch.Tensor, res: torch.Tensor, gamma: torch.Tensor, beta:
     C = x.shape[-1]
     rows = x.numel() // C
     y = torch.empty_like(x)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("add_layernorm", 3 * x.numel() * x.element_size(), 0)) as st:
         check(_native.lib().ltu_add_layernorm(_p(x), _p(res), _p(gamma), _p(beta), _p(y), rows, C, eps, _dt(x), st),
               "ltu_add_layernorm")
     return y
@@ -119,7 +156,7 @@ def add_layernorm(x: torch.Tensor, res: torch.Tensor, gamma: torch.Tensor, beta:
 def gelu_(x: torch.Tensor) -> torch.Tensor:
     """In-place exact-erf GELU (model/trans_block.py:201,:208)."""
     dev = _chk(x)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("gelu", 2 * x.numel() * x.element_size(), 0)) as st:
         check(_native.lib().ltu_gelu(_p(x), x.numel(), _dt(x), st), "ltu_gelu")
     return x
 
@@ -162,7 +199,10 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     out = torch.empty(B, Ho, Wo, Do, cout, dtype=torch.float32 if out_f32 else x0.dtype, device=dev)
     tiles = L.ltu_conv3d_tc_tiles(V) if use_tc else L.ltu_conv3d_tiles(V, cout)
     partials = torch.empty(B, tiles, cout, 2, dtype=torch.float32, device=dev) if want_stats else None
-    with _Guard(dev) as st:
+    cin = C0 + C1
+    nbytes = (x0.numel() + (0 if x1 is None else x1.numel())) * x0.element_size() + out.numel() * out.element_size()
+    prof = ("conv3d_tc" if use_tc else "conv3d", nbytes, 2 * ksize ** 3 * cin * cout * B * V)
+    with _Guard(dev, prof) as st:
         if use_tc:
             check(L.ltu_conv3d_tc(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), stride[0], stride[1],
                                   stride[2], _p(w_tc), _p(bias), cout, _p(out), Ho, Wo, Do, _p(partials), st),
@@ -204,7 +244,8 @@ def instnorm_apply(x: torch.Tensor, stats: torch.Tensor, act: int = ACT_LRELU,
     B, C = x.shape[0], x.shape[-1]
     V = x.numel() // (B * C)
     y = x if inplace else torch.empty_like(x)
-    with _Guard(dev) as st:
+    nb = (2 + (residual is not None)) * x.numel() * x.element_size()
+    with _Guard(dev, ("instnorm_apply", nb, 0)) as st:
         check(_native.lib().ltu_instnorm_apply(_p(x), _p(stats), _p(residual), _p(y), B, V, C, act, _dt(x), st),
               "ltu_instnorm_apply")
     return y
@@ -317,4 +358,29 @@ def vote_argmax(votes: torch.Tensor) -> torch.Tensor:
     out = torch.empty(H, W, D, dtype=torch.uint8, device=dev)
     with _Guard(dev) as st:
         check(_native.lib().ltu_vote_argmax(_p(votes), _p(out), C, H * W * D, st), "ltu_vote_argmax")
+    return out
+
+
+def vote_fractions(votes: torch.Tensor) -> torch.Tensor:
+    """votes uint8 [C,H,W,D] -> fp32 [C,H,W,D] vote fractions (votes / number of covering windows)."""
+    dev = _chk(votes)
+    C, H, W, D = votes.shape
+    out = torch.empty(C, H, W, D, dtype=torch.float32, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_vote_fractions(_p(votes), _p(out), C, H * W * D, st), "ltu_vote_fractions")
+    return out
+
+
+def gather_windows(volume: torch.Tensor, starts: torch.Tensor, roi) -> torch.Tensor:
+    """volume fp32 [H,W,D], starts int32 [n,3] -> windows fp32 [n,1,rh,rw,rd]."""
+    dev = _chk(volume, starts)
+    if volume.dtype != torch.float32 or starts.dtype != torch.int32:
+        raise TypeError("gather_windows: volume must be float32 and starts int32")
+    H, W, D = volume.shape
+    n = starts.shape[0]
+    rh, rw, rd = roi
+    out = torch.empty(n, 1, rh, rw, rd, dtype=torch.float32, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_gather_windows(_p(volume), _p(starts), _p(out), n, rh, rw, rd, H, W, D, st),
+              "ltu_gather_windows")
     return out

@@ -1,0 +1,135 @@
+"""Patch-sharded sliding-window inference over a full CT volume (BASELINE config 5).
+
+Drop-in for the way the reference calls MONAI 0.7.0
+``sliding_window_inference(images, roi, sw_batch_size, model, overlap=..., sigma_scale=0)``
+(inference_multi_classes.py:143, inference_embed_attn.py:141, utils/utils_3D_embed_full.py:148)
+with the default ``mode="constant"``: same tiling, same stitched result
+``sum_w pred_w / count`` -- but
+
+* the predictor is the B200 ``MaskTransUnet`` in eval mode, whose output is a one-hot argmax
+  (model/trans_3DUnet.py:196-202), so the stitched volume is a vote fraction k/n and is
+  accumulated EXACTLY as uint8 vote counts on the device (``ltu_vote_accumulate``);
+* windows are independent units: with ``torch.distributed`` initialised they are dealt
+  round-robin to the ranks (one process per GPU, weights resident) and the only collective is
+  one NCCL sum all-reduce of the uint8 vote volume over NVLink.  Integer votes make the N-GPU
+  result bit-identical to the 1-GPU result.
+
+MONAI is not installed in this image; its tiling rules are restated in ``scan_plan`` (the same
+restatement lives in oracle/sliding_window.py, which is the checker -- "parity unpinned").
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .unet import MaskTransUnet
+
+__all__ = ["scan_plan", "shard_windows", "reduce_votes", "sliding_window_inference"]
+
+
+def scan_plan(image_size: Sequence[int], roi_size: Sequence[int], overlap: float):
+    """MONAI 0.7.0 inferers/utils.py::_get_scan_interval + data/utils.py::dense_patch_slices.
+
+    Returns (padded_size, pad_before, starts) where starts is the list of window origins in C order
+    of (H, W, D)."""
+    if not 0 <= overlap < 1:
+        raise ValueError("overlap must be in [0, 1)")
+    nd = len(image_size)
+    roi = tuple(int(r) if r and r > 0 else int(image_size[i]) for i, r in enumerate(roi_size))   # fall_back_tuple
+    padded = tuple(max(int(image_size[i]), roi[i]) for i in range(nd))
+    pad_before = tuple((padded[i] - int(image_size[i])) // 2 for i in range(nd))
+    interval = []
+    for i in range(nd):
+        if roi[i] == padded[i]:
+            interval.append(roi[i])
+        else:
+            iv = int(roi[i] * (1 - overlap))
+            interval.append(iv if iv > 0 else 1)
+    per_dim: List[List[int]] = []
+    for i in range(nd):
+        num = int(math.ceil(float(padded[i]) / interval[i]))
+        scan_dim = next((d for d in range(num) if d * interval[i] + roi[i] >= padded[i]), None)
+        n = scan_dim + 1 if scan_dim is not None else 1
+        s = []
+        for idx in range(n):
+            st = idx * interval[i]
+            st -= max(st + roi[i] - padded[i], 0)
+            s.append(st)
+        per_dim.append(s)
+    starts = [(h, w, d) for h in per_dim[0] for w in per_dim[1] for d in per_dim[2]]
+    return padded, pad_before, roi, starts
+
+
+def shard_windows(n_windows: int, rank: int, world: int) -> List[int]:
+    """Round-robin deal of window indices: rank r owns r, r+world, ..."""
+    return list(range(rank, n_windows, world))
+
+
+def reduce_votes(votes: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the per-rank uint8 vote volumes (the path's single exchange step)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(votes, op=dist.ReduceOp.SUM, group=group)
+    return votes
+
+
+@torch.no_grad()
+def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_batch_size: int,
+                             predictor: MaskTransUnet, overlap: float = 0.25, mode: str = "constant",
+                             sigma_scale: float = 0.125, padding_mode: str = "constant", cval: float = 0.0,
+                             sw_device=None, device=None, *, group=None, distributed: Optional[bool] = None,
+                             return_labels: bool = False):
+    """Same positional signature as monai.inferers.sliding_window_inference (0.7.0).
+
+    inputs: fp32 [B, 1, H, W, D] on the GPU.  Returns fp32 [B, C, H, W, D] vote fractions (what MONAI's
+    ``output_image / count_map`` yields for a one-hot predictor) or, with ``return_labels``, the
+    uint8 argmax [B, H, W, D] as well."""
+    if str(mode).lower().endswith("gaussian"):
+        raise NotImplementedError("only the constant blend mode used by the reference scripts is implemented")
+    if not isinstance(predictor, MaskTransUnet):
+        raise TypeError("predictor must be a lintransunet_b200.MaskTransUnet (eval-mode one-hot votes)")
+    if not inputs.is_cuda:
+        raise RuntimeError("sliding_window_inference runs on CUDA tensors only (no CPU fallback)")
+    if inputs.dim() != 5 or inputs.shape[1] != 1:
+        raise ValueError("inputs must be [B, 1, H, W, D]")
+    B = inputs.shape[0]
+    image_size = tuple(int(s) for s in inputs.shape[2:])
+    padded, pad_before, roi, starts = scan_plan(image_size, roi_size, overlap)
+    if padded != image_size:           # volume smaller than the window: symmetric constant pad (MONAI)
+        pad = []
+        for k in (2, 1, 0):
+            diff = padded[k] - image_size[k]
+            pad.extend([diff // 2, diff - diff // 2])
+        inputs = torch.nn.functional.pad(inputs, pad, mode=padding_mode, value=cval)
+    inputs = inputs.contiguous().float()
+    if distributed is None:
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if distributed else (0, 1)
+    mine = shard_windows(len(starts), rank, world)
+    C = predictor.dim_output
+    dev = inputs.device
+    starts_dev = torch.tensor([starts[i] for i in mine], dtype=torch.int32, device=dev).reshape(-1, 3)
+    fracs, labels_out = [], []
+    for b in range(B):
+        votes = torch.zeros((C,) + padded, dtype=torch.uint8, device=dev)
+        vol = inputs[b, 0]
+        for g0 in range(0, len(mine), sw_batch_size):
+            st = starts_dev[g0:g0 + sw_batch_size].contiguous()
+            win = ops.gather_windows(vol, st, roi)
+            lab = predictor.predict_labels(win)
+            ops.vote_accumulate(lab, st, votes)
+        if distributed:
+            reduce_votes(votes, group)
+        if padded != image_size:
+            sl = tuple(slice(pad_before[i], pad_before[i] + image_size[i]) for i in range(3))
+            votes = votes[(slice(None),) + sl].contiguous()
+        fracs.append(ops.vote_fractions(votes))
+        if return_labels:
+            labels_out.append(ops.vote_argmax(votes))
+    out = torch.stack(fracs, 0) if B > 1 else fracs[0].unsqueeze(0)
+    if return_labels:
+        return out, (torch.stack(labels_out, 0) if B > 1 else labels_out[0].unsqueeze(0))
+    return out

@@ -111,7 +111,9 @@ def test_bf16_with_teacher_forced_boxes_and_tensor_cores_toggle():
         outs[tc] = from_cl(m.forward_logits(x.cuda())).cpu()
     print(f"\n[bf16 tc vs cuda-core] rel diff {rel_err(outs[True], outs[False]):.3e}; "
           f"vs golden {rel_err(sub(outs[True]), g['logits']):.3e}")
-    assert rel_err(outs[True], outs[False]) < 3e-2
+    # the tcgen05 path also rounds the conv WEIGHTS to bf16 (the CUDA-core path keeps them fp32), so the
+    # two bf16 pipelines differ by about as much as either differs from fp32
+    assert rel_err(outs[True], outs[False]) < 8e-2
     assert rel_err(sub(outs[True]), g["logits"]) < 6e-2
 
 

@@ -1,0 +1,37 @@
+"""GPU: the sharded sliding-window driver (gather -> forward -> uint8 votes -> fractions) against
+the restated MONAI algorithm (oracle/sliding_window.py) driving the CPU oracle model."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ltu_oracle as O
+from oracle import sliding_window as OSW
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sliding_window_matches_restated_monai_with_oracle_model():
+    from lintransunet_b200 import MaskTransUnet
+    from lintransunet_b200.sliding_window import sliding_window_inference
+    cfg = O.UnetConfig(dim_output=3)
+    sd = O.make_state_dict(cfg, seed=2)
+    m = MaskTransUnet(list(cfg.num_layers), list(cfg.roi_size_list), list(cfg.is_roi_list), 1, 3, dropout=0.0)
+    m.load_state_dict(sd)
+    m.cuda().eval()
+    m.precision = "fp32"
+    vol = O.make_input((1, 1, 96, 96, 24), seed=4, blob=True)
+    roi, ov = (64, 64, 16), 0.5                                     # 2 x 2 x 2 = 8 windows, ragged batches of 3
+    frac, labels = sliding_window_inference(vol.cuda(), roi, 3, m, overlap=ov, return_labels=True)
+    ref = OSW.sliding_window_inference(vol, roi, 3, lambda x: O.mask_trans_unet_forward(x, sd, cfg)["onehot"], overlap=ov)
+    assert frac.shape == ref.shape == (1, 3, 96, 96, 24)
+    mism = float((frac.cpu() != ref).any(1).float().mean())
+    print(f"\n[sliding window fp32] voxels with a differing vote fraction: {mism:.3e}")
+    assert mism <= 1e-3                                             # integer votes: equal unless an argmax tie flips
+    assert float((frac.sum(1) - 1).abs().max()) < 1e-6
+    assert torch.equal(labels[0].long().cpu(), frac[0].argmax(0).cpu())
+    # a volume smaller than the window is padded symmetrically and cropped back
+    small = O.make_input((1, 1, 64, 32, 16), seed=5)
+    f2 = sliding_window_inference(small.cuda(), roi, 2, m, overlap=ov)
+    r2 = OSW.sliding_window_inference(small, roi, 2, lambda x: O.mask_trans_unet_forward(x, sd, cfg)["onehot"], overlap=ov)
+    assert f2.shape == r2.shape == (1, 3, 64, 32, 16)
+    assert float((f2.cpu() != r2).any(1).float().mean()) <= 1e-3
