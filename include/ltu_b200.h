@@ -84,17 +84,18 @@ int ltu_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int Hi, 
                float* partials, int dtype, ltu_stream_t stream);
 
 /* tcgen05 (UTCHMMA) implicit-GEMM path of the same convolution for bf16 activations:
- * weight_bf16 packed [Cout][Kpad] (K-major B operand), K index = tap*(C0+C1) + c, zero padded
- * to Kpad = ltu_conv3d_tc_kpad(C0+C1) (multiple of 64).  Requirements (ltu_conv3d_tc_supported):
- * ksize 3, pad 1, C0+C1 a power of two >= 16, C0 % 8 == 0, Cout % 16 == 0, Cout <= 256.
- * Output is bf16.  Same partials layout with tiles = ltu_conv3d_tc_tiles(out_voxels).          */
+ * weight_bf16 packed [Cout16][Kpad] (K-major B operand), K index = tap*(C0+C1) + c, zero padded to
+ * Kpad = ltu_conv3d_tc_kpad(C0+C1, ksize) (multiple of 64) and to Cout16 = Cout rounded up to 16 rows.
+ * Requirements (ltu_conv3d_tc_supported): (ksize,pad) in {(3,1),(1,0)}, C0+C1 a power of two >= 8,
+ * C0 % 8 == 0, Cout <= 256 (and Cout % 8 == 0 for bf16 output).  Output bf16, or fp32 when out_f32.
+ * Same partials layout with tiles = ltu_conv3d_tc_tiles(out_voxels).                            */
 int ltu_conv3d_tc_supported(int C0, int C1, int Cout, int ksize, int pad);
 int ltu_conv3d_tc_tiles(int64_t out_voxels);
-int ltu_conv3d_tc_kpad(int Cin);
+int ltu_conv3d_tc_kpad(int Cin, int ksize);
 int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di,
-                  int up2, int sh, int sw, int sd, const void* weight_bf16, const float* bias,
-                  int Cout, void* out, int Ho, int Wo, int Do, float* partials,
-                  ltu_stream_t stream);
+                  int up2, int ksize, int sh, int sw, int sd, int pad, const void* weight_bf16,
+                  const float* bias, int Cout, void* out, int out_f32, int Ho, int Wo, int Do,
+                  float* partials, ltu_stream_t stream);
 
 /* InstanceNorm3d (no affine, eps 1e-5, biased variance):
  * finalize : partials [B][tiles][C][2] -> stats [B][C][2] = (mean, rstd), fixed summation order
@@ -108,8 +109,9 @@ int ltu_instnorm_apply(const void* x, const float* stats, const void* residual, 
                        int64_t voxels, int C, int act, int dtype, ltu_stream_t stream);
 
 /* ---- a10: windows_embedding, model/Unet_3Dblock.py:123-136 --------------------------------
- * x fp32 [B,1,H,W,D] -> y [B,H/2,W/2,D,4] channels-last, channel = kh*2+kw                    */
-int ltu_s2d_input(const float* x, void* y, int B, int H, int W, int D, int dtype,
+ * x fp32 [B,1,H,W,D] -> y [B,H/2,W/2,D,cpad] channels-last, channel = kh*2+kw; cpad in {4,8}:
+ * with cpad = 8 channels 4..7 are zero (pads the stem input to one 16-byte bf16 vector)        */
+int ltu_s2d_input(const float* x, void* y, int B, int H, int W, int D, int cpad, int dtype,
                   ltu_stream_t stream);
 
 /* ---- a12: nn.Upsample(trilinear, align_corners=True), model/Unet_3Dblock.py:1341-1345 ------

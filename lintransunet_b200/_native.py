@@ -34,12 +34,12 @@ SIGNATURES = {
     "ltu_conv3d": (I, [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, I, P, I, P]),
     "ltu_conv3d_tc_supported": (I, [I, I, I, I, I]),
     "ltu_conv3d_tc_tiles": (I, [L]),
-    "ltu_conv3d_tc_kpad": (I, [I]),
-    "ltu_conv3d_tc": (I, [P, I, P, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, P, P]),
+    "ltu_conv3d_tc_kpad": (I, [I, I]),
+    "ltu_conv3d_tc": (I, [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, I, P, P]),
     "ltu_instnorm_finalize": (I, [P, P, I, I, I, L, F, P]),
     "ltu_chan_partials": (I, [P, P, I, L, I, I, I, P]),
     "ltu_instnorm_apply": (I, [P, P, P, P, I, L, I, I, I, P]),
-    "ltu_s2d_input": (I, [P, P, I, I, I, I, I, P]),
+    "ltu_s2d_input": (I, [P, P, I, I, I, I, I, I, P]),
     "ltu_upsample_trilinear": (I, [P, P, I, I, I, I, I, I, I, P]),
     "ltu_mask_softmax": (I, [P, P, P, I, L, I, P]),
     "ltu_gate_fused": (I, [P, P, P, P, P, P, P, P, I, L, I, I, P]),

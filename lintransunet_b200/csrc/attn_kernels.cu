@@ -9,6 +9,8 @@
 //              (lane e owns column e).  Partial states are merged by kv_combine in a fixed order
 //              => bit-reproducible.
 // q_readout  : one pass over Q, writes out.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ltu {
@@ -341,6 +343,22 @@ posenc_kernel(const T* __restrict__ x, const float* __restrict__ w, const float*
 
 void count_launch(int n = 1);
 
+// bf16 tensor-pipe variants (attn_tc.cu)
+int kv_reduce_bf16_mma(const void* k, const void* v, int64_t ld, float* ctx, void* ws, int B, int64_t N, int heads,
+                       cudaStream_t st);
+int q_readout_bf16_mma(const void* q, int64_t ldq, const float* ctx, void* out, int64_t ldo, int B, int64_t N,
+                       int heads, cudaStream_t st);
+int kv_chunks_per_batch_host(int B, int64_t N) { return kv_chunks_per_batch(B, N); }
+int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st) {
+    kv_combine_kernel<<<dim3(heads, B), 1024, 0, st>>>(ws, ctx, heads, nparts);
+    LTU_LAUNCH_CHECK("kv_combine");
+    return LTU_OK;
+}
+static bool use_mma_attention() {
+    static const bool v = [] { const char* e = getenv("LTU_ATTN_FMA"); return !(e && e[0] == '1'); }();
+    return v;
+}
+
 template <typename T>
 static int kv_reduce_impl(const void* k, const void* v, int64_t ld, float* ctx, void* ws, size_t ws_bytes,
                           int B, int64_t N, int heads, cudaStream_t st) {
@@ -418,6 +436,10 @@ extern "C" int ltu_kv_reduce(const void* k, const void* v, int64_t ld, float* ct
     LTU_ARG_CHECK(ld >= heads * 32 && ld % vn == 0, "kv_reduce: row stride %lld not a multiple of %d", (long long)ld, vn);
     LTU_ARG_CHECK(aligned16(k) && aligned16(v) && aligned16(ws), "kv_reduce: pointers must be 16-byte aligned");
     if (dtype == LTU_F32) return kv_reduce_impl<float>(k, v, ld, ctx, ws, ws_bytes, B, N, heads, (cudaStream_t)stream);
+    if (heads >= 2 && use_mma_attention()) {
+        LTU_ARG_CHECK(ws_bytes >= ltu_kv_reduce_workspace(B, N, heads), "kv_reduce: workspace too small");
+        return kv_reduce_bf16_mma(k, v, ld, ctx, ws, B, N, heads, (cudaStream_t)stream);
+    }
     return kv_reduce_impl<bf16>(k, v, ld, ctx, ws, ws_bytes, B, N, heads, (cudaStream_t)stream);
 }
 
@@ -431,6 +453,8 @@ extern "C" int ltu_q_readout(const void* q, int64_t ldq, const float* ctx, void*
     LTU_ARG_CHECK(ldq >= heads * 32 && ldq % vn == 0 && ldo >= heads * 32, "q_readout: bad row strides");
     LTU_ARG_CHECK(aligned16(q), "q_readout: q must be 16-byte aligned");
     if (dtype == LTU_F32) return q_readout_impl<float>(q, ldq, ctx, out, ldo, B, N, heads, (cudaStream_t)stream);
+    if (heads >= 2 && ldo % 8 == 0 && aligned16(out) && use_mma_attention())
+        return q_readout_bf16_mma(q, ldq, ctx, out, ldo, B, N, heads, (cudaStream_t)stream);
     return q_readout_impl<bf16>(q, ldq, ctx, out, ldo, B, N, heads, (cudaStream_t)stream);
 }
 

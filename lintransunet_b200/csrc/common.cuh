@@ -106,6 +106,8 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t smem_u32_generic(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));

@@ -31,12 +31,13 @@ struct TcParams {
     const bf16* in0; const bf16* in1;
     int C0, C1, log2cin;
     int Hi, Wi, Di, up2;
-    int sh, sw, sd;
+    int ks, pad, sh, sw, sd;
     const bf16* weight;   // [Cout][Kpad]
     int Kpad, Ktot;
     const float* bias;
-    int Cout;
-    bf16* out;
+    int Cout;             // UMMA N (multiple of 16, zero-padded weight rows)
+    int Cstore;           // channels actually written (<= Cout)
+    void* out; int out_f32;
     int Ho, Wo, Do;
     float* partials; int tiles;
     int stages, tmem_cols;
@@ -168,7 +169,7 @@ conv3d_tc_kernel(const TcParams p) {
         const int od = (int)(id % p.Do);
         const int64_t t2 = id / p.Do;
         const int ow = (int)(t2 % p.Wo), oh = (int)(t2 / p.Wo);
-        const int hb = oh * p.sh - 1, wb = ow * p.sw - 1, db = od * p.sd - 1;
+        const int hb = oh * p.sh - p.pad, wb = ow * p.sw - p.pad, db = od * p.sd - p.pad;
         const int He = p.up2 ? 2 * p.Hi : p.Hi, We = p.up2 ? 2 * p.Wi : p.Wi, De = p.up2 ? 2 * p.Di : p.Di;
         const int Cin = p.C0 + p.C1;
         const int64_t in_sample = (int64_t)p.Hi * p.Wi * p.Di;
@@ -195,7 +196,7 @@ conv3d_tc_kernel(const TcParams p) {
                     last_tap = tap;
                     tap_ok = false;
                     if (row_ok && kk < p.Ktot) {
-                        const int kh = tap / 9, kw = (tap / 3) % 3, kd = tap % 3;
+                        const int kh = p.ks == 3 ? tap / 9 : 0, kw = p.ks == 3 ? (tap / 3) % 3 : 0, kd = p.ks == 3 ? tap % 3 : 0;
                         int hv = hb + kh, wv = wb + kw, dv = db + kd;
                         if (hv >= 0 && hv < He && wv >= 0 && wv < We && dv >= 0 && dv < De) {
                             if (p.up2) { hv >>= 1; wv >>= 1; dv >>= 1; }
@@ -221,25 +222,41 @@ conv3d_tc_kernel(const TcParams p) {
         // =========================== epilogue ===========================
         mbar_wait(smem_u32(done_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t out_row = ((int64_t)b * Vo + vox0 + r) * p.Cout;
-        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+        const int64_t out_row = ((int64_t)b * Vo + vox0 + r) * p.Cstore;
+        for (int c0 = 0; c0 < p.Cstore; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-            const int ncol = (p.Cout - c0) < 32 ? (p.Cout - c0) : 32;
+            const int ncol = (p.Cstore - c0) < 32 ? (p.Cstore - c0) : 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 float bsv = (p.bias != nullptr && i < ncol) ? __ldg(p.bias + c0 + i) : 0.f;
-                // rounded to bf16 here so that the statistics describe the stored values
-                v[i] = (row_ok && i < ncol) ? __bfloat162float(__float2bfloat16_rn(v[i] + bsv)) : 0.f;
+                float o = v[i] + bsv;
+                // bf16 output: round here so that the statistics describe the stored values
+                if (!p.out_f32) o = __bfloat162float(__float2bfloat16_rn(o));
+                v[i] = (row_ok && i < ncol) ? o : 0.f;
             }
             if (row_ok) {
+                if (p.out_f32) {
+                    float* dst = reinterpret_cast<float*>(p.out) + out_row + c0;
+                    if (ncol == 32 && (p.Cstore & 3) == 0) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (g * 8 < ncol) {
-                        uint4 o;
-                        o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-                        o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-                        *reinterpret_cast<uint4*>(p.out + out_row + c0 + g * 8) = o;
+                        for (int g = 0; g < 8; ++g)
+                            *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < ncol) dst[i] = v[i];
+                    }
+                } else {
+                    bf16* dst = reinterpret_cast<bf16*>(p.out) + out_row + c0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (g * 8 < ncol) {
+                            uint4 o;
+                            o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                            o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                            *reinterpret_cast<uint4*>(dst + g * 8) = o;
+                        }
                     }
                 }
             }
@@ -250,19 +267,19 @@ conv3d_tc_kernel(const TcParams p) {
                 float s = transpose_reduce32(v, lane);
                 float q = transpose_reduce32(sq, lane);
                 if (lane < ncol) {
-                    sred[((warp * p.Cout) + c0 + lane) * 2] = s;
-                    sred[((warp * p.Cout) + c0 + lane) * 2 + 1] = q;
+                    sred[((warp * p.Cstore) + c0 + lane) * 2] = s;
+                    sred[((warp * p.Cstore) + c0 + lane) * 2 + 1] = q;
                 }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (p.partials != nullptr) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int c = threadIdx.x; c < p.Cout; c += kTcProducers) {
+            for (int c = threadIdx.x; c < p.Cstore; c += kTcProducers) {
                 float s = 0.f, q = 0.f;
 #pragma unroll
-                for (int w = 0; w < 4; ++w) { s += sred[(w * p.Cout + c) * 2]; q += sred[(w * p.Cout + c) * 2 + 1]; }
-                float* dst = p.partials + (((int64_t)b * p.tiles + blockIdx.x) * p.Cout + c) * 2;
+                for (int w = 0; w < 4; ++w) { s += sred[(w * p.Cstore + c) * 2]; q += sred[(w * p.Cstore + c) * 2 + 1]; }
+                float* dst = p.partials + (((int64_t)b * p.tiles + blockIdx.x) * p.Cstore + c) * 2;
                 dst[0] = s; dst[1] = q;
             }
         }
@@ -305,46 +322,51 @@ using namespace ltu;
 
 extern "C" int ltu_conv3d_tc_supported(int C0, int C1, int Cout, int ksize, int pad) {
     const int Cin = C0 + C1;
-    if (ksize != 3 || pad != 1) return 0;
-    if (!is_pow2(Cin) || Cin < 16 || Cin > 1024) return 0;
+    if (!((ksize == 3 && pad == 1) || (ksize == 1 && pad == 0))) return 0;
+    if (!is_pow2(Cin) || Cin < 8 || Cin > 1024) return 0;
     if (C0 % 8 != 0 || C1 % 8 != 0) return 0;
-    if (Cout % 16 != 0 || Cout < 16 || Cout > 256) return 0;
+    if (Cout < 1 || Cout > 256) return 0;
     return 1;
 }
 
 extern "C" int ltu_conv3d_tc_tiles(int64_t out_voxels) { return (int)ceil_div64(out_voxels, kTcM); }
 
-extern "C" int ltu_conv3d_tc_kpad(int Cin) { return (int)ceil_div64((int64_t)27 * Cin, kTcBK) * kTcBK; }
+extern "C" int ltu_conv3d_tc_kpad(int Cin, int ksize) {
+    return (int)ceil_div64((int64_t)ksize * ksize * ksize * Cin, kTcBK) * kTcBK;
+}
 
 extern "C" int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di, int up2,
-                             int sh, int sw, int sd, const void* weight_bf16, const float* bias, int Cout, void* out,
-                             int Ho, int Wo, int Do, float* partials, ltu_stream_t stream) {
+                             int ksize, int sh, int sw, int sd, int pad, const void* weight_bf16, const float* bias,
+                             int Cout, void* out, int out_f32, int Ho, int Wo, int Do, float* partials,
+                             ltu_stream_t stream) {
     LTU_ARG_CHECK(in0 && weight_bf16 && out, "conv3d_tc: null pointer");
-    LTU_ARG_CHECK(ltu_conv3d_tc_supported(C0, C1, Cout, 3, 1), "conv3d_tc: unsupported channels C0=%d C1=%d Cout=%d", C0, C1, Cout);
+    LTU_ARG_CHECK(ltu_conv3d_tc_supported(C0, C1, Cout, ksize, pad), "conv3d_tc: unsupported C0=%d C1=%d Cout=%d k=%d pad=%d", C0, C1, Cout, ksize, pad);
     LTU_ARG_CHECK((in1 != nullptr) == (C1 > 0), "conv3d_tc: in1/C1 mismatch");
     LTU_ARG_CHECK(B > 0 && B <= 65535 && Hi > 0 && Wi > 0 && Di > 0, "conv3d_tc: bad shape");
     LTU_ARG_CHECK(sh >= 1 && sh <= 2 && sw >= 1 && sw <= 2 && sd >= 1 && sd <= 2, "conv3d_tc: stride must be 1 or 2");
-    LTU_ARG_CHECK(!up2 || (sh == 1 && sw == 1 && sd == 1), "conv3d_tc: up2 needs stride 1");
+    LTU_ARG_CHECK(!up2 || (sh == 1 && sw == 1 && sd == 1 && ksize == 3), "conv3d_tc: up2 needs a stride-1 3x3x3 conv");
     const int He = up2 ? 2 * Hi : Hi, We = up2 ? 2 * Wi : Wi, De = up2 ? 2 * Di : Di;
-    LTU_ARG_CHECK(Ho == (He - 1) / sh + 1 && Wo == (We - 1) / sw + 1 && Do == (De - 1) / sd + 1,
-                  "conv3d_tc: output size does not match the geometry");
+    LTU_ARG_CHECK(Ho == (He + 2 * pad - ksize) / sh + 1 && Wo == (We + 2 * pad - ksize) / sw + 1 &&
+                  Do == (De + 2 * pad - ksize) / sd + 1, "conv3d_tc: output size does not match the geometry");
     LTU_ARG_CHECK(((uintptr_t)in0 & 15) == 0 && ((uintptr_t)in1 & 15) == 0 && ((uintptr_t)weight_bf16 & 15) == 0 &&
                   ((uintptr_t)out & 15) == 0, "conv3d_tc: pointers must be 16-byte aligned");
+    LTU_ARG_CHECK(out_f32 || Cout % 8 == 0, "conv3d_tc: bf16 output needs Cout %% 8 == 0");
     TcParams p;
     p.in0 = (const bf16*)in0; p.in1 = (const bf16*)in1; p.C0 = C0; p.C1 = C1; p.log2cin = ilog2(C0 + C1);
-    p.Hi = Hi; p.Wi = Wi; p.Di = Di; p.up2 = up2; p.sh = sh; p.sw = sw; p.sd = sd;
-    p.weight = (const bf16*)weight_bf16; p.Ktot = 27 * (C0 + C1); p.Kpad = ltu_conv3d_tc_kpad(C0 + C1);
-    p.bias = bias; p.Cout = Cout; p.out = (bf16*)out; p.Ho = Ho; p.Wo = Wo; p.Do = Do;
+    p.Hi = Hi; p.Wi = Wi; p.Di = Di; p.up2 = up2; p.ks = ksize; p.pad = pad; p.sh = sh; p.sw = sw; p.sd = sd;
+    p.weight = (const bf16*)weight_bf16; p.Ktot = ksize * ksize * ksize * (C0 + C1); p.Kpad = ltu_conv3d_tc_kpad(C0 + C1, ksize);
+    p.bias = bias; p.Cstore = Cout; p.Cout = (Cout + 15) / 16 * 16; p.out = out; p.out_f32 = out_f32;
+    p.Ho = Ho; p.Wo = Wo; p.Do = Do;
     p.partials = partials; p.tiles = ltu_conv3d_tc_tiles((int64_t)Ho * Wo * Do);
-    int cols = 32; while (cols < Cout) cols <<= 1;
+    int cols = 32; while (cols < p.Cout) cols <<= 1;
     p.tmem_cols = cols;
-    const int stage_bytes = kTcM * 128 + Cout * 128;
+    const int stage_bytes = kTcM * 128 + p.Cout * 128;
     // aim for 2 CTAs per SM (<= ~110 KB each), at least 2 and at most 6 stages
     int stages = (108 * 1024) / stage_bytes;
     if (stages > 6) stages = 6;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)4 * Cout * 2 * 4;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)4 * p.Cout * 2 * 4;
     static thread_local int configured_dev = -1;
     int dev; cudaGetDevice(&dev);
     if (configured_dev != dev) {

@@ -12,7 +12,7 @@ void count_launch(int n = 1);
 // ---------------------------------------------------------------- a10: space-to-depth of the input
 template <typename T>
 __global__ void __launch_bounds__(256)
-s2d_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int H, int W, int D) {
+s2d_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int H, int W, int D, int cpad) {
     const int H2 = H / 2, W2 = W / 2;
     const int64_t total = (int64_t)B * H2 * W2 * D;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -29,7 +29,11 @@ s2d_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int H, int W, 
         v[1] = src[D];                       // kh=0,kw=1
         v[2] = src[(int64_t)W * D];          // kh=1,kw=0
         v[3] = src[(int64_t)W * D + D];      // kh=1,kw=1
-        store4(y + idx * 4, v);
+        store4(y + idx * cpad, v);
+        if (cpad == 8) {
+            const float z[4] = {0.f, 0.f, 0.f, 0.f};
+            store4(y + idx * 8 + 4, z);
+        }
     }
 }
 
@@ -283,15 +287,17 @@ using namespace ltu;
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 #define LTU_DTYPE_CHECK(name) LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, name ": bad dtype %d", dtype)
 
-extern "C" int ltu_s2d_input(const float* x, void* y, int B, int H, int W, int D, int dtype, ltu_stream_t stream) {
+extern "C" int ltu_s2d_input(const float* x, void* y, int B, int H, int W, int D, int cpad, int dtype,
+                             ltu_stream_t stream) {
+    LTU_ARG_CHECK(cpad == 4 || cpad == 8, "s2d_input: cpad must be 4 or 8");
     LTU_ARG_CHECK(x && y, "s2d_input: null pointer");
     LTU_DTYPE_CHECK("s2d_input");
     LTU_ARG_CHECK(B > 0 && H > 0 && W > 0 && D > 0 && H % 2 == 0 && W % 2 == 0, "s2d_input: H and W must be even");
     LTU_ARG_CHECK(aligned16(y), "s2d_input: output must be 16-byte aligned");
     int64_t total = (int64_t)B * (H / 2) * (W / 2) * D;
     unsigned g = grid_for(total, 256, 16);
-    if (dtype == LTU_F32) s2d_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(x, (float*)y, B, H, W, D);
-    else s2d_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, B, H, W, D);
+    if (dtype == LTU_F32) s2d_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(x, (float*)y, B, H, W, D, cpad);
+    else s2d_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, B, H, W, D, cpad);
     LTU_LAUNCH_CHECK("s2d_input");
     count_launch(1);
     return LTU_OK;

@@ -182,8 +182,8 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
            up2: bool = False, out_f32: bool = False, want_stats: bool = False,
            w_tc: Optional[torch.Tensor] = None):
     """nn.Conv3d on channels-last input(s).  Returns (out, partials, tiles); partials is None
-    unless want_stats.  When `w_tc` (bf16 [taps][Cout][Cin]) is given and the shape qualifies the
-    tcgen05 implicit-GEMM kernel is used, otherwise the CUDA-core kernel."""
+    unless want_stats.  When `w_tc` (bf16 [Cout16][Kpad], see ltu_conv3d_tc) is given and the shape
+    qualifies the tcgen05 implicit-GEMM kernel is used, otherwise the CUDA-core kernel."""
     dev = _chk(x0, x1, w_packed, bias, w_tc)
     L = _native.lib()
     B, Hi, Wi, Di, C0 = x0.shape
@@ -194,7 +194,7 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     Ho, Wo, Do = (conv_out_size(He, ksize, stride[0], pad), conv_out_size(We, ksize, stride[1], pad),
                   conv_out_size(De, ksize, stride[2], pad))
     V = Ho * Wo * Do
-    use_tc = (w_tc is not None and x0.dtype == torch.bfloat16 and not out_f32
+    use_tc = (w_tc is not None and x0.dtype == torch.bfloat16 and (out_f32 or cout % 8 == 0)
               and L.ltu_conv3d_tc_supported(C0, C1, cout, ksize, pad) == 1)
     out = torch.empty(B, Ho, Wo, Do, cout, dtype=torch.float32 if out_f32 else x0.dtype, device=dev)
     tiles = L.ltu_conv3d_tc_tiles(V) if use_tc else L.ltu_conv3d_tiles(V, cout)
@@ -204,9 +204,9 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     prof = ("conv3d_tc" if use_tc else "conv3d", nbytes, 2 * ksize ** 3 * cin * cout * B * V)
     with _Guard(dev, prof) as st:
         if use_tc:
-            check(L.ltu_conv3d_tc(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), stride[0], stride[1],
-                                  stride[2], _p(w_tc), _p(bias), cout, _p(out), Ho, Wo, Do, _p(partials), st),
-                  "ltu_conv3d_tc")
+            check(L.ltu_conv3d_tc(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), ksize, stride[0], stride[1],
+                                  stride[2], pad, _p(w_tc), _p(bias), cout, _p(out), int(out_f32), Ho, Wo, Do,
+                                  _p(partials), st), "ltu_conv3d_tc")
         else:
             check(L.ltu_conv3d(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), ksize, stride[0], stride[1],
                                stride[2], pad, _p(w_packed), _p(bias), cout, _p(out), int(out_f32), Ho, Wo, Do,
@@ -252,17 +252,18 @@ def instnorm_apply(x: torch.Tensor, stats: torch.Tensor, act: int = ACT_LRELU,
 
 
 # ------------------------------------------------------------------ U-Net plumbing
-def s2d_input(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """[B,1,H,W,D] fp32 -> [B,H/2,W/2,D,4] (windows_embedding, model/Unet_3Dblock.py:123-136)."""
+def s2d_input(x: torch.Tensor, dtype: torch.dtype, cpad: int = 4) -> torch.Tensor:
+    """[B,1,H,W,D] fp32 -> [B,H/2,W/2,D,cpad] (windows_embedding, model/Unet_3Dblock.py:123-136);
+    cpad=8 appends four zero channels (one 16-byte bf16 vector per voxel for the tensor-core stem)."""
     dev = _chk(x)
     if x.dtype != torch.float32:
         raise TypeError("model input must be float32")
     B, cin, H, W, D = x.shape
     if cin != 1:
         raise ValueError("windows_embedding requires dim_input == 1 (model/Unet_3Dblock.py:132)")
-    y = torch.empty(B, H // 2, W // 2, D, 4, dtype=dtype, device=dev)
+    y = torch.empty(B, H // 2, W // 2, D, cpad, dtype=dtype, device=dev)
     with _Guard(dev) as st:
-        check(_native.lib().ltu_s2d_input(_p(x), _p(y), B, H, W, D, _dt(y), st), "ltu_s2d_input")
+        check(_native.lib().ltu_s2d_input(_p(x), _p(y), B, H, W, D, cpad, _dt(y), st), "ltu_s2d_input")
     return y
 
 

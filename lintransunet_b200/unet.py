@@ -199,21 +199,23 @@ class ROIDecoder(_Holder):
 # ----------------------------------------------------------------------------- packed weights
 class _ConvW:
     """Derived cache of one conv: fp32 [taps][Cin][Cout] for the CUDA-core kernel, bf16
-    [Cout][Kpad] (K-major) for the tcgen05 kernel."""
+    [Cout16][Kpad] (K-major, K = tap*Cin + c) for the tcgen05 kernel.  `cin_pad` appends zero input
+    channels (the stem's 4 channels are padded to 8 = one 16-byte bf16 vector)."""
 
-    def __init__(self, conv: nn.Conv3d, want_tc: bool):
+    def __init__(self, conv: nn.Conv3d, want_tc: bool, cin_pad: int = 0):
         w = conv.weight.detach()
+        if cin_pad and cin_pad > w.shape[1]:
+            w = torch.cat([w, w.new_zeros(w.shape[0], cin_pad - w.shape[1], *w.shape[2:])], 1)
         cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
         self.k, self.cin, self.cout = k, cin, cout
         self.w = w.permute(2, 3, 4, 1, 0).reshape(k * k * k, cin, cout).contiguous().float()
         self.b = conv.bias.detach().float().contiguous() if conv.bias is not None else None
         self.w_tc = None
-        if want_tc and k == 3:
-            # tcgen05 B operand: [Cout][Kpad], K index = tap*Cin + c, zero padded to a multiple of 64
-            ktot = 27 * cin
+        if want_tc and (cin & (cin - 1)) == 0 and cin >= 8 and cout <= 256:
+            ktot = k * k * k * cin
             kpad = (ktot + 63) // 64 * 64
-            wt = torch.zeros(cout, kpad, dtype=torch.bfloat16, device=w.device)
-            wt[:, :ktot] = w.permute(0, 2, 3, 4, 1).reshape(cout, ktot).to(torch.bfloat16)
+            wt = torch.zeros((cout + 15) // 16 * 16, kpad, dtype=torch.bfloat16, device=w.device)
+            wt[:cout, :ktot] = w.permute(0, 2, 3, 4, 1).reshape(cout, ktot).to(torch.bfloat16)
             self.w_tc = wt
 
 
@@ -248,17 +250,17 @@ class _Plan:
         tc = dtype == torch.bfloat16
         enc, dec = model.encode, model.decode
         self.dtype = dtype
-        self.stem = _ConvW(enc.input_block, tc)
+        self.stem = _ConvW(enc.input_block, tc, cin_pad=8 if tc else 0)
         self.down = [(_ConvW(b.conv1, tc), _ConvW(b.conv2, tc), b.stride) for b in enc.block_list]
-        self.mask = [_ConvW(c, False) for c in dec.mask_conv_list]
+        self.mask = [_ConvW(c, tc) for c in dec.mask_conv_list]
         self.gate = []
         for a in dec.att_conv_list:
             psi = a.psi[0]
-            self.gate.append((_ConvW(a.W_x[0], False), _ConvW(a.W_g[0], False),
+            self.gate.append((_ConvW(a.W_x[0], tc), _ConvW(a.W_g[0], tc),
                               psi.weight.detach().reshape(-1).float().contiguous(),
                               psi.bias.detach().float().contiguous()))
         self.up = [(_ConvW(b.conv1, tc), _ConvW(b.conv2, tc)) for b in dec.block_list]
-        self.final = _ConvW(dec.final_block, False)
+        self.final = _ConvW(dec.final_block, tc)
         self.bridges: List[Optional[dict]] = []
         for br in dec.bridge_list:
             if isinstance(br, ROIBridge):
@@ -409,7 +411,7 @@ class MaskTransUnet(nn.Module):
     def _forward_impl(self, x: torch.Tensor, P: _Plan, head: str):
         n = len(self.num_layers)
         # ---- Encoder.forward (model/Unet_3Dblock.py:596-607)
-        a = ops.s2d_input(x, P.dtype)
+        a = ops.s2d_input(x, P.dtype, cpad=P.stem.cin)          # 8 (zero-padded) on the tensor-core path
         a = self._conv_in_act(a, P.stem)
         skips = []
         for i, (c1, c2, stride) in enumerate(P.down):

@@ -13,9 +13,9 @@ from lintransunet_b200 import ops  # noqa: E402
 from lintransunet_b200.unet import _ConvW  # noqa: E402
 
 
-def run(cin, cin1, cout, stride, up2, shape, mode, B=1):
+def run(cin, cin1, cout, stride, up2, shape, mode, B=1, k=3, out_f32=False):
     H, W, D = shape
-    conv = torch.nn.Conv3d(cin + cin1, cout, 3, stride=stride, padding=1)
+    conv = torch.nn.Conv3d(cin + cin1, cout, k, stride=stride, padding=k // 2)
     with torch.no_grad():
         if mode == "identity":
             conv.weight.zero_()
@@ -31,10 +31,10 @@ def run(cin, cin1, cout, stride, up2, shape, mode, B=1):
     xin = x0 if x1 is None else torch.cat((x0, x1), 1)
     if up2:
         xin = F.interpolate(xin, scale_factor=2, mode="nearest")
-    ref = F.conv3d(xin, conv.weight.detach(), conv.bias.detach(), stride=stride, padding=1)
+    ref = F.conv3d(xin, conv.weight.detach(), conv.bias.detach(), stride=stride, padding=k // 2)
     cl = lambda t: None if t is None else t.permute(0, 2, 3, 4, 1).contiguous().cuda().to(torch.bfloat16)
-    y, partials, tiles = ops.conv3d(cl(x0), cw.w.cuda(), cw.b.cuda(), cout, 3, stride=stride, pad=1, x1=cl(x1), up2=up2,
-                                    want_stats=True, w_tc=cw.w_tc.cuda())
+    y, partials, tiles = ops.conv3d(cl(x0), cw.w.cuda(), cw.b.cuda(), cout, k, stride=stride, pad=k // 2, x1=cl(x1),
+                                    up2=up2, want_stats=True, out_f32=out_f32, w_tc=cw.w_tc.cuda())
     torch.cuda.synchronize()
     got = y.float().permute(0, 4, 1, 2, 3).cpu()
     err = float((got - ref).abs().max() / ref.abs().max())
@@ -68,16 +68,20 @@ def main():
     run(128, 0, 32, (1, 1, 1), True, (3, 4, 5), "random")
     run(256, 0, 64, (1, 1, 1), True, (6, 7, 8), "random", B=2)
     run(16, 0, 32, (2, 2, 1), False, (16, 16, 32), "random", B=2)
+    run(64, 0, 3, (1, 1, 1), False, (5, 4, 6), "random", B=2, out_f32=True)      # mask head
+    run(16, 0, 12, (1, 1, 1), False, (7, 5, 4), "random", B=2, out_f32=True)     # final block
+    run(32, 0, 16, (1, 1, 1), False, (5, 6, 7), "random", B=2, k=1)              # gate 1x1x1
+    run(8, 0, 16, (1, 1, 1), False, (8, 6, 10), "random", B=2)                   # stem (padded to 8)
     # timing at model shapes (bf16, B=8, 128^3 patch): flops = 2*27*Cin*Cout*Vout
     import time
-    def bench(cin, cin1, cout, stride, up2, shape, B=8):
+    def bench(cin, cin1, cout, stride, up2, shape, B=8, k=3, out_f32=False):
         H, W, D = shape
-        conv = torch.nn.Conv3d(cin + cin1, cout, 3, stride=stride, padding=1)
+        conv = torch.nn.Conv3d(cin + cin1, cout, k, stride=stride, padding=k // 2)
         cw = _ConvW(conv, want_tc=True)
         x0 = torch.randn(B, H, W, D, cin, device="cuda").to(torch.bfloat16)
         x1 = torch.randn(B, H, W, D, cin1, device="cuda").to(torch.bfloat16) if cin1 else None
-        args = (x0, cw.w.cuda(), cw.b.cuda(), cout, 3)
-        kw = dict(stride=stride, pad=1, x1=x1, up2=up2, want_stats=True)
+        args = (x0, cw.w.cuda(), cw.b.cuda(), cout, k)
+        kw = dict(stride=stride, pad=k // 2, x1=x1, up2=up2, want_stats=True, out_f32=out_f32)
         wtc = cw.w_tc.cuda()
         res = {}
         for name, w in (("tc", wtc), ("cuda-core", None)):
@@ -92,9 +96,10 @@ def main():
             torch.cuda.synchronize()
             res[name] = e0.elapsed_time(e1) / 5
         V = y.shape[1] * y.shape[2] * y.shape[3]
-        fl = 2 * 27 * (cin + cin1) * cout * B * V
+        fl = 2 * k ** 3 * (cin + cin1) * cout * B * V
+        by = (x0.numel() + (0 if x1 is None else x1.numel())) * 2 + y.numel() * y.element_size()
         print(f"time cin={cin}+{cin1} cout={cout} stride={stride} up2={up2} in={shape}: tc {res['tc']:.3f} ms "
-              f"({fl/res['tc']/1e9:.1f} TFLOP/s), cuda-core {res['cuda-core']:.3f} ms ({fl/res['cuda-core']/1e9:.1f} TFLOP/s)",
+              f"({fl/res['tc']/1e9:.1f} TFLOP/s, {by/res['tc']/1e6:.0f} GB/s), cuda-core {res['cuda-core']:.3f} ms ({fl/res['cuda-core']/1e9:.1f} TFLOP/s)",
               flush=True)
     bench(128, 0, 32, (1, 1, 1), True, (39, 23, 64))      # b1.up_embed
     bench(256, 0, 64, (1, 1, 1), True, (24, 14, 32))      # b2.up_embed
@@ -106,6 +111,11 @@ def main():
     bench(64, 0, 64, (1, 1, 1), False, (16, 16, 64))      # enc.block2.conv1
     bench(128, 0, 256, (2, 2, 2), False, (8, 8, 64))      # enc.block3.conv2
     bench(256, 0, 128, (1, 1, 1), False, (8, 8, 64))      # dec.block0.conv1
+    bench(32, 0, 3, (1, 1, 1), False, (64, 64, 128), out_f32=True)     # mask head, finest level
+    bench(16, 0, 12, (1, 1, 1), False, (64, 64, 128), out_f32=True)    # final block
+    bench(8, 0, 16, (1, 1, 1), False, (64, 64, 128))                   # stem
+    bench(32, 0, 16, (1, 1, 1), False, (64, 64, 128), k=1)             # gate W_g
+    bench(16, 0, 16, (1, 1, 1), False, (64, 64, 128), k=1)             # gate W_x
 
 
 if __name__ == "__main__":
