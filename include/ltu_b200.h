@@ -86,11 +86,15 @@ int ltu_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int Hi, 
 /* tcgen05 (UTCHMMA) implicit-GEMM path of the same convolution for bf16 activations:
  * weight_bf16 packed [Cout16][Kpad] (K-major B operand), K index = tap*(C0+C1) + c, zero padded to
  * Kpad = ltu_conv3d_tc_kpad(C0+C1, ksize) (multiple of 64) and to Cout16 = Cout rounded up to 16 rows.
+ * up2 = 1 (nearest x2 upsample before a 3x3x3 conv): the weight is the FOLDED tensor
+ * [8 parity classes][Cout16][ltu_conv3d_tc_kpad(Cin, 2)], class q = pa*4+pb*2+pc, tap t = th*4+tw*2+td
+ * reading source voxel (a+th-1+pa, ...), with per-axis folded weights  parity 0: {w0, w1+w2},
+ * parity 1: {w0+w1, w2}.
  * Requirements (ltu_conv3d_tc_supported): (ksize,pad) in {(3,1),(1,0)}, C0+C1 a power of two >= 8,
  * C0 % 8 == 0, Cout <= 256 (and Cout % 8 == 0 for bf16 output).  Output bf16, or fp32 when out_f32.
- * Same partials layout with tiles = ltu_conv3d_tc_tiles(out_voxels).                            */
+ * Same partials layout with tiles = ltu_conv3d_tc_tiles(out_voxels, up2).                       */
 int ltu_conv3d_tc_supported(int C0, int C1, int Cout, int ksize, int pad);
-int ltu_conv3d_tc_tiles(int64_t out_voxels);
+int ltu_conv3d_tc_tiles(int64_t out_voxels, int up2);
 int ltu_conv3d_tc_kpad(int Cin, int ksize);
 int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di,
                   int up2, int ksize, int sh, int sw, int sd, int pad, const void* weight_bf16,

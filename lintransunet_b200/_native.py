@@ -33,7 +33,7 @@ SIGNATURES = {
     "ltu_conv3d_tiles": (I, [L, I]),
     "ltu_conv3d": (I, [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, I, P, I, P]),
     "ltu_conv3d_tc_supported": (I, [I, I, I, I, I]),
-    "ltu_conv3d_tc_tiles": (I, [L]),
+    "ltu_conv3d_tc_tiles": (I, [L, I]),
     "ltu_conv3d_tc_kpad": (I, [I, I]),
     "ltu_conv3d_tc": (I, [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, I, P, P]),
     "ltu_instnorm_finalize": (I, [P, P, I, I, I, L, F, P]),

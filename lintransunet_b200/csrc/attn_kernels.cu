@@ -26,6 +26,7 @@ static inline int kv_chunks_per_batch(int B, int64_t N) {
     int64_t want = ceil_div64(2 * (int64_t)sm_count(), B);
     if (want < 1) want = 1;
     int64_t chunks = tiles < want ? tiles : want;
+    if (chunks > 96) chunks = 96;      // bounds the serial merge in kv_combine (small B, long N)
     int64_t tiles_per_chunk = ceil_div64(tiles, chunks);
     return (int)ceil_div64(tiles, tiles_per_chunk);
 }
@@ -143,22 +144,40 @@ kv_reduce_kernel(const T* __restrict__ K, const T* __restrict__ V, int64_t ld, f
     out[1056 + lane] = s_run;
 }
 
-// grid (heads, B), 1024 threads: thread (j,e).  Merges the partial states in index order.
+// grid (heads, B), 1024 threads: thread (j,e).  Merges the partial states in a fixed order (four
+// interleaved accumulation chains keep several loads in flight; the order is still deterministic).
 __global__ void __launch_bounds__(1024)
 kv_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx, int heads, int nparts) {
     const int hd = blockIdx.x, b = blockIdx.y;
     const int j = threadIdx.x >> 5, e = threadIdx.x & 31;
     const float* base = part + ((int64_t)b * nparts * heads + hd) * kPartialFloats;
     const int64_t stride = (int64_t)heads * kPartialFloats;
-    float M = -INFINITY;
-    for (int p = 0; p < nparts; ++p) M = fmaxf(M, base[p * stride + 1024 + j]);
-    float S = 0.f, A = 0.f;
-    for (int p = 0; p < nparts; ++p) {
-        float mp = base[p * stride + 1024 + j];
-        float w = (mp == -INFINITY) ? 0.f : __expf(mp - M);
-        S = fmaf(base[p * stride + 1056 + j], w, S);
-        A = fmaf(base[p * stride + j * kHeadDim + e], w, A);
+    float M4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int p = 0;
+    for (; p + 4 <= nparts; p += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) M4[u] = fmaxf(M4[u], base[(p + u) * stride + 1024 + j]);
     }
+    for (; p < nparts; ++p) M4[0] = fmaxf(M4[0], base[p * stride + 1024 + j]);
+    const float M = fmaxf(fmaxf(M4[0], M4[1]), fmaxf(M4[2], M4[3]));
+    float S4[4] = {0.f, 0.f, 0.f, 0.f}, A4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (p = 0; p + 4 <= nparts; p += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float mp = base[(p + u) * stride + 1024 + j];
+            const float w = (mp == -INFINITY) ? 0.f : __expf(mp - M);
+            S4[u] = fmaf(base[(p + u) * stride + 1056 + j], w, S4[u]);
+            A4[u] = fmaf(base[(p + u) * stride + j * kHeadDim + e], w, A4[u]);
+        }
+    }
+    for (; p < nparts; ++p) {
+        const float mp = base[p * stride + 1024 + j];
+        const float w = (mp == -INFINITY) ? 0.f : __expf(mp - M);
+        S4[0] = fmaf(base[p * stride + 1056 + j], w, S4[0]);
+        A4[0] = fmaf(base[p * stride + j * kHeadDim + e], w, A4[0]);
+    }
+    const float S = (S4[0] + S4[1]) + (S4[2] + S4[3]);
+    const float A = (A4[0] + A4[1]) + (A4[2] + A4[3]);
     ctx[(((int64_t)b * heads + hd) * kHeadDim + j) * kHeadDim + e] = A / S;
 }
 

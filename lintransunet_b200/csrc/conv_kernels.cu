@@ -199,23 +199,30 @@ conv3d_kernel(const ConvParams p) {
     }
 }
 
-// one warp per (b, c): fp64 accumulation over tiles in a fixed order
-__global__ void __launch_bounds__(256)
+// grid (ceil(C/32), B), 1024 threads: lane <-> channel, the 32 warps stride over the tiles (coalesced
+// float2 rows of the partials), fp64 accumulation, fixed-order cross-warp merge => deterministic
+__global__ void __launch_bounds__(1024)
 instnorm_finalize_kernel(const float* __restrict__ partials, float* __restrict__ stats, int B, int tiles, int C,
                          double inv_vox, float eps) {
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B * C) return;
-    int b = warp / C, c = warp % C;
-    const float* base = partials + ((int64_t)b * tiles * C + c) * 2;
+    __shared__ double red[32][32][2];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 32 + lane;
     double s = 0.0, q = 0.0;
-    for (int t = lane; t < tiles; t += 32) {
-        s += (double)base[(int64_t)t * C * 2];
-        q += (double)base[(int64_t)t * C * 2 + 1];
+    if (c < C) {
+        const float2* base = reinterpret_cast<const float2*>(partials) + (int64_t)b * tiles * C + c;
+        for (int t = warp; t < tiles; t += 32) {
+            const float2 v = base[(int64_t)t * C];
+            s += (double)v.x;
+            q += (double)v.y;
+        }
     }
-    s = warp_sum_d(s);
-    q = warp_sum_d(q);
-    if (lane == 0) {
-        double mean = s * inv_vox;
+    red[warp][lane][0] = s;
+    red[warp][lane][1] = q;
+    __syncthreads();
+    if (warp == 0 && c < C) {
+        s = 0.0; q = 0.0;
+        for (int w = 0; w < 32; ++w) { s += red[w][lane][0]; q += red[w][lane][1]; }
+        const double mean = s * inv_vox;
         double var = q * inv_vox - mean * mean;
         if (var < 0.0) var = 0.0;
         stats[((int64_t)b * C + c) * 2] = (float)mean;
@@ -350,9 +357,8 @@ extern "C" int ltu_conv3d(const void* in0, int C0, const void* in1, int C1, int 
 extern "C" int ltu_instnorm_finalize(const float* partials, float* stats, int B, int tiles, int C, int64_t voxels,
                                      float eps, ltu_stream_t stream) {
     LTU_ARG_CHECK(partials && stats && B > 0 && tiles > 0 && C > 0 && voxels > 0, "instnorm_finalize: bad arguments");
-    int warps = B * C;
-    int blocks = (warps * 32 + 255) / 256;
-    instnorm_finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(partials, stats, B, tiles, C, 1.0 / (double)voxels, eps);
+    LTU_ARG_CHECK(B <= 65535, "instnorm_finalize: B too large");
+    instnorm_finalize_kernel<<<dim3((C + 31) / 32, B), 1024, 0, (cudaStream_t)stream>>>(partials, stats, B, tiles, C, 1.0 / (double)voxels, eps);
     LTU_LAUNCH_CHECK("instnorm_finalize");
     count_launch(1);
     return LTU_OK;

@@ -14,8 +14,10 @@
 //   InstanceNorm partial sums (sum, sum of squares from the fp32 accumulators) reduced with a
 //   fixed-order transpose-butterfly => bit-reproducible.
 //
-// Input addressing covers stride 1/2 per axis, a second (channel-concatenated) input and the
-// on-the-fly nearest x2 upsample of up_embed (reference model/Unet_3Dblock.py:421-422, :553).
+// Input addressing covers stride 1/2 per axis and a second (channel-concatenated) input (reference
+// model/Unet_3Dblock.py:553).  nn.Upsample(nearest x2) + 3x3x3 conv of up_embed (:421-422) is FOLDED:
+// output voxels of parity class (pa,pb,pc) see only 2x2x2 distinct source voxels, so each class is a
+// 2x2x2 convolution of the low-resolution input with pre-summed weights (8/27 of the flops and loads).
 #include "common.cuh"
 
 namespace ltu {
@@ -41,6 +43,9 @@ struct TcParams {
     int Ho, Wo, Do;
     float* partials; int tiles;
     int stages, tmem_cols;
+    int fold;             // 1: nearest-x2 upsample folded into 8 parity classes of 2x2x2 taps (blockIdx.z)
+    int ntaps;            // 27, 1 or 8 (fold)
+    int64_t w_class_stride;   // elements between the weight slabs of two parity classes (fold)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,10 +140,12 @@ conv3d_tc_kernel(const TcParams p) {
     uint64_t* done_bar = empty_bar + p.stages;                          // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
     float* sred = reinterpret_cast<float*>(tmem_slot + 2);              // [4][Cout][2]
+    int* toff = reinterpret_cast<int*>(sred + 4 * p.Cout * 2);          // [32] voxel offset of every tap
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-    const int64_t Vo = (int64_t)p.Ho * p.Wo * p.Do;
+    // rows of the implicit GEMM: output voxels, or (fold) low-resolution voxels of one parity class
+    const int64_t Vo = p.fold ? (int64_t)p.Hi * p.Wi * p.Di : (int64_t)p.Ho * p.Wo * p.Do;
     const int64_t vox0 = (int64_t)blockIdx.x * kTcM;
     const int nkb = p.Kpad / kTcBK;
 
@@ -149,6 +156,20 @@ conv3d_tc_kernel(const TcParams p) {
         }
         mbar_init(smem_u32(done_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // parity class of this CTA in fold mode: output voxel (2a+pa, 2b+pb, 2c+pc)
+    const int pa = p.fold ? (blockIdx.z >> 2) & 1 : 0, pb = p.fold ? (blockIdx.z >> 1) & 1 : 0, pc = p.fold ? blockIdx.z & 1 : 0;
+    if (threadIdx.x < 32) {
+        const int t = threadIdx.x;
+        int off = 0;
+        if (t < p.ntaps) {
+            int dh, dw, dd;
+            if (p.fold) { dh = ((t >> 2) & 1) - 1 + pa; dw = ((t >> 1) & 1) - 1 + pb; dd = (t & 1) - 1 + pc; }
+            else if (p.ks == 3) { dh = t / 9 - 1; dw = (t / 3) % 3 - 1; dd = t % 3 - 1; }
+            else { dh = dw = dd = 0; }
+            off = (dh * p.Wi + dw) * p.Di + dd;
+        }
+        toff[t] = off;
     }
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -166,16 +187,44 @@ conv3d_tc_kernel(const TcParams p) {
         int64_t id = vox0 + r;
         const bool row_ok = id < Vo;
         if (!row_ok) id = 0;
-        const int od = (int)(id % p.Do);
-        const int64_t t2 = id / p.Do;
-        const int ow = (int)(t2 % p.Wo), oh = (int)(t2 / p.Wo);
-        const int hb = oh * p.sh - p.pad, wb = ow * p.sw - p.pad, db = od * p.sd - p.pad;
-        const int He = p.up2 ? 2 * p.Hi : p.Hi, We = p.up2 ? 2 * p.Wi : p.Wi, De = p.up2 ? 2 * p.Di : p.Di;
+        // (ch, cw, cd): source voxel under the centre tap; valid-tap bit mask for this row
+        int ch, cw, cd;
+        int64_t out_vox;
+        uint32_t mask = 0;
+        if (p.fold) {
+            const int c_ = (int)(id % p.Di);
+            const int64_t t2 = id / p.Di;
+            const int b_ = (int)(t2 % p.Wi), a_ = (int)(t2 / p.Wi);
+            ch = a_; cw = b_; cd = c_;
+            out_vox = ((int64_t)(2 * a_ + pa) * p.Wo + (2 * b_ + pb)) * p.Do + (2 * c_ + pc);
+            for (int t = 0; t < 8; ++t) {
+                const int hv = a_ + ((t >> 2) & 1) - 1 + pa, wv = b_ + ((t >> 1) & 1) - 1 + pb, dv = c_ + (t & 1) - 1 + pc;
+                if (hv >= 0 && hv < p.Hi && wv >= 0 && wv < p.Wi && dv >= 0 && dv < p.Di) mask |= 1u << t;
+            }
+        } else {
+            const int od = (int)(id % p.Do);
+            const int64_t t2 = id / p.Do;
+            const int ow = (int)(t2 % p.Wo), oh = (int)(t2 / p.Wo);
+            ch = oh * p.sh; cw = ow * p.sw; cd = od * p.sd;
+            out_vox = id;
+            if (p.ks == 3) {
+                for (int t = 0; t < 27; ++t) {
+                    const int hv = ch + t / 9 - 1, wv = cw + (t / 3) % 3 - 1, dv = cd + t % 3 - 1;
+                    if (hv >= 0 && hv < p.Hi && wv >= 0 && wv < p.Wi && dv >= 0 && dv < p.Di) mask |= 1u << t;
+                }
+            } else {
+                mask = 1u;
+            }
+        }
+        if (!row_ok) mask = 0;
         const int Cin = p.C0 + p.C1;
-        const int64_t in_sample = (int64_t)p.Hi * p.Wi * p.Di;
+        const int64_t ctr = (int64_t)b * p.Hi * p.Wi * p.Di + ((int64_t)ch * p.Wi + cw) * p.Di + cd;
+        const bf16* ctr0 = p.in0 + ctr * p.C0;
+        const bf16* ctr1 = p.in1 + ctr * p.C1;          // unused when C1 == 0
         const uint32_t a_row = r * 128;
         const int sw7 = r & 7;
         const int b_iters = p.Cout / 16;              // 8*Cout chunks over 128 threads
+        const bf16* wbase = p.weight + (p.fold ? (int64_t)blockIdx.z * p.w_class_stride : 0);
 
         for (int kb = 0; kb < nkb; ++kb) {
             const int stage = kb % p.stages;
@@ -183,38 +232,22 @@ conv3d_tc_kernel(const TcParams p) {
             mbar_wait(smem_u32(empty_bar + stage), (round & 1) ^ 1);
             const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t sb = sa + a_bytes;
-            // ---- A row: 8 chunks of 8 channels
-            int last_tap = -1;
-            const bf16* src_vox0 = nullptr; const bf16* src_vox1 = nullptr;
-            bool tap_ok = false;
+            // ---- A row: 8 chunks of 8 channels; tap index >= ntaps (K padding) has a zero mask bit
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int kk = kb * kTcBK + j * 8;
                 const int tap = kk >> p.log2cin;
                 const int c = kk & (Cin - 1);
-                if (tap != last_tap) {
-                    last_tap = tap;
-                    tap_ok = false;
-                    if (row_ok && kk < p.Ktot) {
-                        const int kh = p.ks == 3 ? tap / 9 : 0, kw = p.ks == 3 ? (tap / 3) % 3 : 0, kd = p.ks == 3 ? tap % 3 : 0;
-                        int hv = hb + kh, wv = wb + kw, dv = db + kd;
-                        if (hv >= 0 && hv < He && wv >= 0 && wv < We && dv >= 0 && dv < De) {
-                            if (p.up2) { hv >>= 1; wv >>= 1; dv >>= 1; }
-                            const int64_t vox = (int64_t)b * in_sample + ((int64_t)hv * p.Wi + wv) * p.Di + dv;
-                            src_vox0 = p.in0 + vox * p.C0;
-                            src_vox1 = p.in1 + vox * p.C1;
-                            tap_ok = true;
-                        }
-                    }
-                }
-                const bf16* src = tap_ok ? (c < p.C0 ? src_vox0 + c : src_vox1 + (c - p.C0)) : p.in0;
-                cp16(sa + a_row + ((j ^ sw7) << 4), src, tap_ok ? 16 : 0);
+                const bool ok = (mask >> tap) & 1u;
+                const int64_t vo = (int64_t)toff[tap & 31];
+                const bf16* src = c < p.C0 ? ctr0 + vo * p.C0 + c : ctr1 + vo * p.C1 + (c - p.C0);
+                cp16(sa + a_row + ((j ^ sw7) << 4), ok ? src : p.in0, ok ? 16 : 0);
             }
             // ---- B tile: Cout rows x 8 chunks (weights are zero-padded to Kpad)
             for (int i = 0; i < b_iters; ++i) {
                 const int q = r + i * kTcProducers;
                 const int n = q >> 3, j = q & 7;
-                cp16(sb + n * 128 + ((j ^ (n & 7)) << 4), p.weight + (int64_t)n * p.Kpad + kb * kTcBK + j * 8, 16);
+                cp16(sb + n * 128 + ((j ^ (n & 7)) << 4), wbase + (int64_t)n * p.Kpad + kb * kTcBK + j * 8, 16);
             }
             cp_async_arrive_noinc(smem_u32(full_bar + stage));
         }
@@ -222,7 +255,7 @@ conv3d_tc_kernel(const TcParams p) {
         // =========================== epilogue ===========================
         mbar_wait(smem_u32(done_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t out_row = ((int64_t)b * Vo + vox0 + r) * p.Cstore;
+        const int64_t out_row = ((int64_t)b * (int64_t)p.Ho * p.Wo * p.Do + out_vox) * p.Cstore;
         for (int c0 = 0; c0 < p.Cstore; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
@@ -279,7 +312,7 @@ conv3d_tc_kernel(const TcParams p) {
                 float s = 0.f, q = 0.f;
 #pragma unroll
                 for (int w = 0; w < 4; ++w) { s += sred[(w * p.Cstore + c) * 2]; q += sred[(w * p.Cstore + c) * 2 + 1]; }
-                float* dst = p.partials + (((int64_t)b * p.tiles + blockIdx.x) * p.Cstore + c) * 2;
+                float* dst = p.partials + (((int64_t)b * p.tiles + (int64_t)blockIdx.z * gridDim.x + blockIdx.x) * p.Cstore + c) * 2;
                 dst[0] = s; dst[1] = q;
             }
         }
@@ -329,8 +362,12 @@ extern "C" int ltu_conv3d_tc_supported(int C0, int C1, int Cout, int ksize, int 
     return 1;
 }
 
-extern "C" int ltu_conv3d_tc_tiles(int64_t out_voxels) { return (int)ceil_div64(out_voxels, kTcM); }
+extern "C" int ltu_conv3d_tc_tiles(int64_t out_voxels, int up2) {
+    if (up2) return 8 * (int)ceil_div64(out_voxels / 8, kTcM);     // 8 parity classes of the low-res grid
+    return (int)ceil_div64(out_voxels, kTcM);
+}
 
+// ksize 3 -> 27 taps, 1 -> 1 tap, 2 -> the 8 folded taps of (nearest x2 upsample o 3x3x3 conv)
 extern "C" int ltu_conv3d_tc_kpad(int Cin, int ksize) {
     return (int)ceil_div64((int64_t)ksize * ksize * ksize * Cin, kTcBK) * kTcBK;
 }
@@ -351,29 +388,41 @@ extern "C" int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, i
     LTU_ARG_CHECK(((uintptr_t)in0 & 15) == 0 && ((uintptr_t)in1 & 15) == 0 && ((uintptr_t)weight_bf16 & 15) == 0 &&
                   ((uintptr_t)out & 15) == 0, "conv3d_tc: pointers must be 16-byte aligned");
     LTU_ARG_CHECK(out_f32 || Cout % 8 == 0, "conv3d_tc: bf16 output needs Cout %% 8 == 0");
+    LTU_ARG_CHECK((int64_t)Hi * Wi * Di * B < (int64_t)1 << 31, "conv3d_tc: input too large for 32-bit voxel offsets");
     TcParams p;
-    p.in0 = (const bf16*)in0; p.in1 = (const bf16*)in1; p.C0 = C0; p.C1 = C1; p.log2cin = ilog2(C0 + C1);
+    const int Cin = C0 + C1;
+    p.in0 = (const bf16*)in0; p.in1 = (const bf16*)in1; p.C0 = C0; p.C1 = C1; p.log2cin = ilog2(Cin);
     p.Hi = Hi; p.Wi = Wi; p.Di = Di; p.up2 = up2; p.ks = ksize; p.pad = pad; p.sh = sh; p.sw = sw; p.sd = sd;
-    p.weight = (const bf16*)weight_bf16; p.Ktot = ksize * ksize * ksize * (C0 + C1); p.Kpad = ltu_conv3d_tc_kpad(C0 + C1, ksize);
+    p.weight = (const bf16*)weight_bf16;
+    p.fold = up2 ? 1 : 0;
+    p.ntaps = up2 ? 8 : ksize * ksize * ksize;
+    p.Ktot = p.ntaps * Cin;
+    p.Kpad = ltu_conv3d_tc_kpad(Cin, up2 ? 2 : ksize);
     p.bias = bias; p.Cstore = Cout; p.Cout = (Cout + 15) / 16 * 16; p.out = out; p.out_f32 = out_f32;
+    p.w_class_stride = (int64_t)p.Cout * p.Kpad;
     p.Ho = Ho; p.Wo = Wo; p.Do = Do;
-    p.partials = partials; p.tiles = ltu_conv3d_tc_tiles((int64_t)Ho * Wo * Do);
+    p.partials = partials; p.tiles = ltu_conv3d_tc_tiles((int64_t)Ho * Wo * Do, up2);
     int cols = 32; while (cols < p.Cout) cols <<= 1;
     p.tmem_cols = cols;
     const int stage_bytes = kTcM * 128 + p.Cout * 128;
-    // aim for 2 CTAs per SM (<= ~110 KB each), at least 2 and at most 6 stages
-    int stages = (108 * 1024) / stage_bytes;
+    const int nkb = p.Kpad / kTcBK;
+    // 2 CTAs per SM (<= ~108 KB each) for deep-K layers; short-K layers (few k-blocks per tile) get
+    // shallower pipelines so that more CTAs are resident and hide the fill/drain latency of a tile
+    int budget = nkb <= 8 ? 52 * 1024 : 108 * 1024;
+    int stages = budget / stage_bytes;
     if (stages > 6) stages = 6;
+    if (stages > nkb) stages = nkb;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)4 * p.Cout * 2 * 4;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)4 * p.Cout * 2 * 4 + 32 * 4;
     static thread_local int configured_dev = -1;
     int dev; cudaGetDevice(&dev);
     if (configured_dev != dev) {
         cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured_dev = dev;
     }
-    conv3d_tc_kernel<<<dim3((unsigned)p.tiles, B), kTcThreads, smem, (cudaStream_t)stream>>>(p);
+    const unsigned gx = (unsigned)(up2 ? p.tiles / 8 : p.tiles);
+    conv3d_tc_kernel<<<dim3(gx, B, up2 ? 8 : 1), kTcThreads, smem, (cudaStream_t)stream>>>(p);
     LTU_LAUNCH_CHECK("conv3d_tc");
     count_launch(1);
     return LTU_OK;

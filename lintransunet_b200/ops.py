@@ -180,10 +180,12 @@ def conv_out_size(n: int, k: int, s: int, pad: int) -> int:
 def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ksize: int,
            stride: Tuple[int, int, int] = (1, 1, 1), pad: int = 1, x1: Optional[torch.Tensor] = None,
            up2: bool = False, out_f32: bool = False, want_stats: bool = False,
-           w_tc: Optional[torch.Tensor] = None):
+           w_tc: Optional[torch.Tensor] = None, w_tc_fold: Optional[torch.Tensor] = None):
     """nn.Conv3d on channels-last input(s).  Returns (out, partials, tiles); partials is None
     unless want_stats.  When `w_tc` (bf16 [Cout16][Kpad], see ltu_conv3d_tc) is given and the shape
     qualifies the tcgen05 implicit-GEMM kernel is used, otherwise the CUDA-core kernel."""
+    if up2:
+        w_tc = w_tc_fold                      # the tensor-core path of an up2 conv needs the folded weights
     dev = _chk(x0, x1, w_packed, bias, w_tc)
     L = _native.lib()
     B, Hi, Wi, Di, C0 = x0.shape
@@ -197,10 +199,11 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     use_tc = (w_tc is not None and x0.dtype == torch.bfloat16 and (out_f32 or cout % 8 == 0)
               and L.ltu_conv3d_tc_supported(C0, C1, cout, ksize, pad) == 1)
     out = torch.empty(B, Ho, Wo, Do, cout, dtype=torch.float32 if out_f32 else x0.dtype, device=dev)
-    tiles = L.ltu_conv3d_tc_tiles(V) if use_tc else L.ltu_conv3d_tiles(V, cout)
+    tiles = L.ltu_conv3d_tc_tiles(V, int(up2)) if use_tc else L.ltu_conv3d_tiles(V, cout)
     partials = torch.empty(B, tiles, cout, 2, dtype=torch.float32, device=dev) if want_stats else None
     cin = C0 + C1
     nbytes = (x0.numel() + (0 if x1 is None else x1.numel())) * x0.element_size() + out.numel() * out.element_size()
+    # algorithmic flops: the un-folded count 2*k^3*Cin*Cout*B*V (the folded up2 path executes 8/27 of it)
     prof = ("conv3d_tc" if use_tc else "conv3d", nbytes, 2 * ksize ** 3 * cin * cout * B * V)
     with _Guard(dev, prof) as st:
         if use_tc:

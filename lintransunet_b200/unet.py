@@ -202,7 +202,7 @@ class _ConvW:
     [Cout16][Kpad] (K-major, K = tap*Cin + c) for the tcgen05 kernel.  `cin_pad` appends zero input
     channels (the stem's 4 channels are padded to 8 = one 16-byte bf16 vector)."""
 
-    def __init__(self, conv: nn.Conv3d, want_tc: bool, cin_pad: int = 0):
+    def __init__(self, conv: nn.Conv3d, want_tc: bool, cin_pad: int = 0, fold_up2: bool = False):
         w = conv.weight.detach()
         if cin_pad and cin_pad > w.shape[1]:
             w = torch.cat([w, w.new_zeros(w.shape[0], cin_pad - w.shape[1], *w.shape[2:])], 1)
@@ -217,6 +217,26 @@ class _ConvW:
             wt = torch.zeros((cout + 15) // 16 * 16, kpad, dtype=torch.bfloat16, device=w.device)
             wt[:cout, :ktot] = w.permute(0, 2, 3, 4, 1).reshape(cout, ktot).to(torch.bfloat16)
             self.w_tc = wt
+        self.w_tc_fold = None
+        if want_tc and fold_up2 and self.w_tc is not None and k == 3:
+            self.w_tc_fold = _fold_up2_weights(w.float(), cout, cin)
+
+
+def _fold_up2_weights(w: torch.Tensor, cout: int, cin: int) -> torch.Tensor:
+    """nn.Upsample(nearest, x2) followed by a 3x3x3 conv == 8 parity-class 2x2x2 convs on the
+    low-resolution input.  Per axis, output parity 0 reads source offsets (-1, 0) with weights
+    (w0, w1+w2), parity 1 reads (0, +1) with (w0+w1, w2).  Returns bf16 [8][Cout16][Kpad],
+    K index = (th*4+tw*2+td)*Cin + c (see ltu_conv3d_tc)."""
+    f = w.new_zeros(2, 2, 3)                      # [parity][folded tap][original tap]
+    f[0, 0, 0] = 1; f[0, 1, 1] = 1; f[0, 1, 2] = 1
+    f[1, 0, 0] = 1; f[1, 0, 1] = 1; f[1, 1, 2] = 1
+    # w: [Cout, Cin, kh, kw, kd] -> wf[pa,pb,pc, Cout, th,tw,td, Cin]
+    wf = torch.einsum("oixyz,atx,buy,gvz->abgotuvi", w, f, f, f)
+    ktot = 8 * cin
+    kpad = (ktot + 63) // 64 * 64
+    out = torch.zeros(8, (cout + 15) // 16 * 16, kpad, dtype=torch.bfloat16, device=w.device)
+    out[:, :cout, :ktot] = wf.reshape(8, cout, ktot).to(torch.bfloat16)
+    return out
 
 
 class _LayerW:
@@ -265,7 +285,7 @@ class _Plan:
         for br in dec.bridge_list:
             if isinstance(br, ROIBridge):
                 t = br.transformer
-                self.bridges.append(dict(kind="roi", down=_ConvW(t.down_embed.conv, tc), up=_ConvW(t.up_embed.conv, tc),
+                self.bridges.append(dict(kind="roi", down=_ConvW(t.down_embed.conv, tc), up=_ConvW(t.up_embed.conv, tc, fold_up2=True),
                                          pos=_pos_w(t.pos_encoder), layers=[_LayerW(l, dtype) for l in t.layers],
                                          mod=br))
             elif isinstance(br, ConnectBridge):
@@ -334,7 +354,9 @@ class MaskTransUnet(nn.Module):
             self.record[name] = t
 
     def _conv(self, x, cw: _ConvW, **kw):
-        return ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, w_tc=cw.w_tc if self.use_tensor_cores else None, **kw)
+        tc = self.use_tensor_cores
+        return ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, w_tc=cw.w_tc if tc else None,
+                          w_tc_fold=cw.w_tc_fold if tc else None, **kw)
 
     def _conv_in_act(self, x, cw: _ConvW, stride=(1, 1, 1), residual=None, x1=None, up2=False):
         """Conv3d -> InstanceNorm3d -> LeakyReLU (+ residual)."""

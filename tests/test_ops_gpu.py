@@ -194,7 +194,7 @@ def test_conv3d(dtype, case, tc):
     conv = torch.nn.Conv3d(cin + cin1, cout, k, stride=stride, padding=k // 2)
     with torch.no_grad():
         conv.weight.copy_(q_(conv.weight, dtype) if tc else conv.weight)
-    cw = _ConvW(conv, want_tc=tc, cin_pad=8 if (tc and cin == 4) else 0)
+    cw = _ConvW(conv, want_tc=tc, cin_pad=8 if (tc and cin == 4) else 0, fold_up2=up2)
     x0 = q_(rnd((B, cin, H, W, D), 7), dtype)
     x1 = q_(rnd((B, cin1, H, W, D), 8), dtype) if cin1 else None
     xin = x0 if x1 is None else torch.cat((x0, x1), 1)
@@ -206,7 +206,8 @@ def test_conv3d(dtype, case, tc):
         x0 = torch.cat([x0, torch.zeros_like(x0)], 1)
     y, partials, tiles = ops.conv3d(dev(x0), cw.w.cuda(), cw.b.cuda(), cout, k, stride=stride, pad=k // 2,
                                     x1=dev(x1), up2=up2, out_f32=out_f32, want_stats=True,
-                                    w_tc=cw.w_tc.cuda() if tc else None)
+                                    w_tc=cw.w_tc.cuda() if tc else None,
+                                    w_tc_fold=cw.w_tc_fold.cuda() if (tc and up2) else None)
     assert y.dtype == (torch.float32 if out_f32 else dtype)
     tol = 2e-5 if (dtype == torch.float32 or out_f32) else TOL[torch.bfloat16]   # fp32 output: fp32 math on exact inputs
     assert rel_err(from_cl(y.float()), ref) < tol

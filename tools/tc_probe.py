@@ -24,7 +24,7 @@ def run(cin, cin1, cout, stride, up2, shape, mode, B=1, k=3, out_f32=False):
                 conv.weight[n, n, 1, 1, 1] = 1.0
         else:
             conv.weight.copy_(conv.weight.to(torch.bfloat16).float())
-    cw = _ConvW(conv, want_tc=True)
+    cw = _ConvW(conv, want_tc=True, fold_up2=up2)
     g = torch.Generator().manual_seed(1)
     x0 = torch.randn(B, cin, H, W, D, generator=g).to(torch.bfloat16).float()
     x1 = torch.randn(B, cin1, H, W, D, generator=g).to(torch.bfloat16).float() if cin1 else None
@@ -34,7 +34,8 @@ def run(cin, cin1, cout, stride, up2, shape, mode, B=1, k=3, out_f32=False):
     ref = F.conv3d(xin, conv.weight.detach(), conv.bias.detach(), stride=stride, padding=k // 2)
     cl = lambda t: None if t is None else t.permute(0, 2, 3, 4, 1).contiguous().cuda().to(torch.bfloat16)
     y, partials, tiles = ops.conv3d(cl(x0), cw.w.cuda(), cw.b.cuda(), cout, k, stride=stride, pad=k // 2, x1=cl(x1),
-                                    up2=up2, want_stats=True, out_f32=out_f32, w_tc=cw.w_tc.cuda())
+                                    up2=up2, want_stats=True, out_f32=out_f32, w_tc=cw.w_tc.cuda(),
+                                    w_tc_fold=cw.w_tc_fold.cuda() if up2 else None)
     torch.cuda.synchronize()
     got = y.float().permute(0, 4, 1, 2, 3).cpu()
     err = float((got - ref).abs().max() / ref.abs().max())
@@ -77,14 +78,16 @@ def main():
     def bench(cin, cin1, cout, stride, up2, shape, B=8, k=3, out_f32=False):
         H, W, D = shape
         conv = torch.nn.Conv3d(cin + cin1, cout, k, stride=stride, padding=k // 2)
-        cw = _ConvW(conv, want_tc=True)
+        cw = _ConvW(conv, want_tc=True, fold_up2=up2)
         x0 = torch.randn(B, H, W, D, cin, device="cuda").to(torch.bfloat16)
         x1 = torch.randn(B, H, W, D, cin1, device="cuda").to(torch.bfloat16) if cin1 else None
         args = (x0, cw.w.cuda(), cw.b.cuda(), cout, k)
         kw = dict(stride=stride, pad=k // 2, x1=x1, up2=up2, want_stats=True, out_f32=out_f32)
         wtc = cw.w_tc.cuda()
+        wfold = cw.w_tc_fold.cuda() if up2 else None
         res = {}
         for name, w in (("tc", wtc), ("cuda-core", None)):
+            kw["w_tc_fold"] = wfold if name == "tc" else None
             for _ in range(2):
                 y, _, _ = ops.conv3d(*args, w_tc=w, **kw)
             torch.cuda.synchronize()
