@@ -183,46 +183,65 @@ conv3d_tc_kernel(const TcParams p) {
 
     if (warp < 4) {
         // =========================== producers: im2col gather ===========================
-        const int r = threadIdx.x;                    // A-tile row == TMEM lane
-        int64_t id = vox0 + r;
-        const bool row_ok = id < Vo;
-        if (!row_ok) id = 0;
-        // (ch, cw, cd): source voxel under the centre tap; valid-tap bit mask for this row
-        int ch, cw, cd;
-        int64_t out_vox;
-        uint32_t mask = 0;
-        if (p.fold) {
-            const int c_ = (int)(id % p.Di);
-            const int64_t t2 = id / p.Di;
-            const int b_ = (int)(t2 % p.Wi), a_ = (int)(t2 / p.Wi);
-            ch = a_; cw = b_; cd = c_;
-            out_vox = ((int64_t)(2 * a_ + pa) * p.Wo + (2 * b_ + pb)) * p.Do + (2 * c_ + pc);
-            for (int t = 0; t < 8; ++t) {
-                const int hv = a_ + ((t >> 2) & 1) - 1 + pa, wv = b_ + ((t >> 1) & 1) - 1 + pb, dv = c_ + (t & 1) - 1 + pc;
-                if (hv >= 0 && hv < p.Hi && wv >= 0 && wv < p.Wi && dv >= 0 && dv < p.Di) mask |= 1u << t;
-            }
-        } else {
-            const int od = (int)(id % p.Do);
-            const int64_t t2 = id / p.Do;
-            const int ow = (int)(t2 % p.Wo), oh = (int)(t2 / p.Wo);
-            ch = oh * p.sh; cw = ow * p.sw; cd = od * p.sd;
-            out_vox = id;
-            if (p.ks == 3) {
-                for (int t = 0; t < 27; ++t) {
-                    const int hv = ch + t / 9 - 1, wv = cw + (t / 3) % 3 - 1, dv = cd + t % 3 - 1;
-                    if (hv >= 0 && hv < p.Hi && wv >= 0 && wv < p.Wi && dv >= 0 && dv < p.Di) mask |= 1u << t;
-                }
-            } else {
-                mask = 1u;
-            }
-        }
-        if (!row_ok) mask = 0;
+        // Thread t owns 16-byte chunk column j = t & 7 of rows (t >> 3) + 16*i, i < 8: the eight lanes
+        // of a row fetch its 128 contiguous bytes (full 32-byte sectors), and the tap / channel decode
+        // of (k-block, j) is shared by the thread's eight rows.
+        const int jc = threadIdx.x & 7, rbase = threadIdx.x >> 3;
         const int Cin = p.C0 + p.C1;
-        const int64_t ctr = (int64_t)b * p.Hi * p.Wi * p.Di + ((int64_t)ch * p.Wi + cw) * p.Di + cd;
-        const bf16* ctr0 = p.in0 + ctr * p.C0;
-        const bf16* ctr1 = p.in1 + ctr * p.C1;          // unused when C1 == 0
-        const uint32_t a_row = r * 128;
-        const int sw7 = r & 7;
+        int ctrv[8];                                   // source voxel under the centre tap (whole batch index)
+        uint32_t vmask[8];                             // valid-tap bits of the row
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = rbase + 16 * i;
+            int64_t rid = vox0 + rr;
+            const bool ok = rid < Vo;
+            if (!ok) rid = 0;
+            int ch, cw, cd;
+            uint32_t m = 0;
+            if (p.fold) {
+                cd = (int)(rid % p.Di);
+                const int64_t t2 = rid / p.Di;
+                cw = (int)(t2 % p.Wi); ch = (int)(t2 / p.Wi);
+                // per-axis validity of source offsets (th-1+pa), th in {0,1}
+                uint32_t hm = 0, wm = 0, dm = 0;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int hv = ch + t - 1 + pa, wv = cw + t - 1 + pb, dv = cd + t - 1 + pc;
+                    hm |= (hv >= 0 && hv < p.Hi) ? 1u << t : 0u;
+                    wm |= (wv >= 0 && wv < p.Wi) ? 1u << t : 0u;
+                    dm |= (dv >= 0 && dv < p.Di) ? 1u << t : 0u;
+                }
+#pragma unroll
+                for (int th = 0; th < 2; ++th)
+#pragma unroll
+                    for (int tw = 0; tw < 2; ++tw)
+                        if (((hm >> th) & 1u) && ((wm >> tw) & 1u)) m |= dm << (th * 4 + tw * 2);
+            } else {
+                const int od = (int)(rid % p.Do);
+                const int64_t t2 = rid / p.Do;
+                const int ow = (int)(t2 % p.Wo), oh = (int)(t2 / p.Wo);
+                ch = oh * p.sh; cw = ow * p.sw; cd = od * p.sd;
+                if (p.ks == 3) {
+                    uint32_t hm = 0, wm = 0, dm = 0;
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const int hv = ch + t - 1, wv = cw + t - 1, dv = cd + t - 1;
+                        hm |= (hv >= 0 && hv < p.Hi) ? 1u << t : 0u;
+                        wm |= (wv >= 0 && wv < p.Wi) ? 1u << t : 0u;
+                        dm |= (dv >= 0 && dv < p.Di) ? 1u << t : 0u;
+                    }
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw)
+                            if (((hm >> kh) & 1u) && ((wm >> kw) & 1u)) m |= dm << (kh * 9 + kw * 3);
+                } else {
+                    m = 1u;
+                }
+            }
+            vmask[i] = ok ? m : 0u;
+            ctrv[i] = (int)((int64_t)b * p.Hi * p.Wi * p.Di + ((int64_t)ch * p.Wi + cw) * p.Di + cd);
+        }
         const int b_iters = p.Cout / 16;              // 8*Cout chunks over 128 threads
         const bf16* wbase = p.weight + (p.fold ? (int64_t)blockIdx.z * p.w_class_stride : 0);
 
@@ -232,24 +251,41 @@ conv3d_tc_kernel(const TcParams p) {
             mbar_wait(smem_u32(empty_bar + stage), (round & 1) ^ 1);
             const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t sb = sa + a_bytes;
-            // ---- A row: 8 chunks of 8 channels; tap index >= ntaps (K padding) has a zero mask bit
+            // ---- A tile: this thread's chunk column of 8 rows; tap >= ntaps (K padding) has a zero mask bit
+            const int kk = kb * kTcBK + jc * 8;
+            const int tap = kk >> p.log2cin;
+            const int c = kk & (Cin - 1);
+            const int tvo = toff[tap & 31];
+            const bool first = c < p.C0;
+            const bf16* cbase = first ? p.in0 + c : p.in1 + (c - p.C0);
+            const int cstride = first ? p.C0 : p.C1;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int kk = kb * kTcBK + j * 8;
-                const int tap = kk >> p.log2cin;
-                const int c = kk & (Cin - 1);
-                const bool ok = (mask >> tap) & 1u;
-                const int64_t vo = (int64_t)toff[tap & 31];
-                const bf16* src = c < p.C0 ? ctr0 + vo * p.C0 + c : ctr1 + vo * p.C1 + (c - p.C0);
-                cp16(sa + a_row + ((j ^ sw7) << 4), ok ? src : p.in0, ok ? 16 : 0);
+            for (int i = 0; i < 8; ++i) {
+                const int rr = rbase + 16 * i;
+                const bool ok = (vmask[i] >> tap) & 1u;
+                const bf16* src = cbase + (int64_t)(ctrv[i] + tvo) * cstride;
+                cp16(sa + rr * 128 + ((jc ^ (rr & 7)) << 4), ok ? src : p.in0, ok ? 16 : 0);
             }
             // ---- B tile: Cout rows x 8 chunks (weights are zero-padded to Kpad)
             for (int i = 0; i < b_iters; ++i) {
-                const int q = r + i * kTcProducers;
+                const int q = threadIdx.x + i * kTcProducers;
                 const int n = q >> 3, j = q & 7;
                 cp16(sb + n * 128 + ((j ^ (n & 7)) << 4), wbase + (int64_t)n * p.Kpad + kb * kTcBK + j * 8, 16);
             }
             cp_async_arrive_noinc(smem_u32(full_bar + stage));
+        }
+
+        // epilogue row of this thread (TMEM lane = threadIdx.x)
+        const int r = threadIdx.x;
+        int64_t id = vox0 + r;
+        const bool row_ok = id < Vo;
+        if (!row_ok) id = 0;
+        int64_t out_vox = id;
+        if (p.fold) {
+            const int c_ = (int)(id % p.Di);
+            const int64_t t2 = id / p.Di;
+            const int b_ = (int)(t2 % p.Wi), a_ = (int)(t2 / p.Wi);
+            out_vox = ((int64_t)(2 * a_ + pa) * p.Wo + (2 * b_ + pb)) * p.Do + (2 * c_ + pc);
         }
 
         // =========================== epilogue ===========================

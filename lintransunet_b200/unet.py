@@ -328,7 +328,11 @@ class MaskTransUnet(nn.Module):
         self.use_tensor_cores = os.environ.get("LTU_DISABLE_TC", "0") != "1"
         self.forced_boxes: Optional[Dict[int, torch.Tensor]] = None   # tests: teacher-forced ROI boxes
         self.record: Optional[dict] = None            # tests: set to {} to capture taps (channels-last)
+        # the forward has no host sync (the ROI boxes stay on the device), so an inference forward of
+        # a fixed input shape is captured once into a CUDA graph and replayed (~600 launches -> 1)
+        self.use_cuda_graphs = os.environ.get("LTU_CUDA_GRAPHS", "1") != "0"
         self._plans: Dict[tuple, tuple] = {}
+        self._graphs: Dict[tuple, dict] = {}
 
     # -- derived-weight cache ------------------------------------------------------------
     def _plan(self, device: torch.device, dtype: torch.dtype) -> _Plan:
@@ -347,6 +351,40 @@ class MaskTransUnet(nn.Module):
                 raise ValueError("precision must be None, 'fp32' or 'bf16'")
             return torch.float32 if self.precision == "fp32" else torch.bfloat16
         return torch.bfloat16 if torch.is_autocast_enabled() else torch.float32
+
+    # -- CUDA graph replay of the inference heads ----------------------------------------------
+    def _run(self, x: torch.Tensor, head: str):
+        """Run `_forward_impl` eagerly or through a captured CUDA graph (eval / labels / logits)."""
+        dtype = self._compute_dtype()
+        x = x.contiguous().float()
+        with torch.autocast("cuda", enabled=False):
+            plan = self._plan(x.device, dtype)
+            graphable = (self.use_cuda_graphs and head != "train" and self.record is None
+                         and self.forced_boxes is None and not getattr(self, "_is_replica", False)
+                         and not torch.cuda.is_current_stream_capturing())
+            if not graphable:
+                return self._forward_impl(x, plan, head)
+            key = (x.device.index, dtype, head, tuple(x.shape), self.use_tensor_cores)
+            ent = self._graphs.get(key)
+            if ent is None or ent["plan"] is not plan:
+                ent = self._capture(x, plan, head)
+                self._graphs[key] = ent
+            ent["x"].copy_(x)
+            ent["graph"].replay()
+            return ent["out"]
+
+    def _capture(self, x: torch.Tensor, plan: "_Plan", head: str) -> dict:
+        static_x = x.clone()
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):                 # warm-up outside the capture (lazy inits, cuBLAS workspaces)
+            self._forward_impl(static_x, plan, head)
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        torch.cuda.synchronize(x.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._forward_impl(static_x, plan, head)
+        return dict(graph=graph, x=static_x, out=out, plan=plan)
 
     # -- building blocks -----------------------------------------------------------------
     def _tap(self, name: str, t: torch.Tensor):
@@ -424,10 +462,10 @@ class MaskTransUnet(nn.Module):
         B, _, H, W, D = x.shape
         if H % 32 or W % 32 or D % 4:
             raise ValueError("H and W must be multiples of 32 and D a multiple of 4")
-        dtype = self._compute_dtype()
-        with torch.no_grad(), torch.autocast("cuda", enabled=False):
-            plan = self._plan(x.device, dtype)
-            out = self._forward_impl(x.contiguous().float(), plan, head="train" if self.training else "eval")
+        with torch.no_grad():
+            out = self._run(x, "train" if self.training else "eval")
+            if not self.training and self.use_cuda_graphs:
+                out = out.clone()          # the graph's output buffer is reused by the next call
         return out
 
     def _forward_impl(self, x: torch.Tensor, P: _Plan, head: str):
@@ -482,19 +520,17 @@ class MaskTransUnet(nn.Module):
     def predict_labels(self, x: torch.Tensor) -> torch.Tensor:
         """Eval forward returning the argmax class per voxel as uint8 [B,H,W,D]: the information of
         the reference's one-hot eval output (trans_3DUnet.py:199-201) without materialising it.
-        Used by the sliding-window driver."""
+        Used by the sliding-window driver.  With CUDA graphs enabled the returned tensor is the
+        graph's static output buffer: consume it before the next call with the same input shape."""
         if not x.is_cuda:
             raise RuntimeError("lintransunet_b200.MaskTransUnet runs on CUDA (sm_100a) only; there is no CPU path")
-        dtype = self._compute_dtype()
-        with torch.autocast("cuda", enabled=False):
-            return self._forward_impl(x.contiguous().float(), self._plan(x.device, dtype), head="labels")
+        return self._run(x, "labels")
 
     @torch.no_grad()
     def forward_logits(self, x: torch.Tensor) -> torch.Tensor:
         """The `decode.final_block` tap as fp32 channels-last [B,H/2,W/2,D,4*dim_output]."""
-        dtype = self._compute_dtype()
-        with torch.autocast("cuda", enabled=False):
-            return self._forward_impl(x.contiguous().float(), self._plan(x.device, dtype), head="logits")
+        out = self._run(x, "logits")
+        return out.clone() if self.use_cuda_graphs else out
 
 
 Model_Dict = {"MaskTransUnet": MaskTransUnet}

@@ -145,3 +145,22 @@ def test_module_api_contract():
         m.eval()(x.cpu())                      # no CPU fallback
     with pytest.raises(ValueError):
         m(torch.zeros(1, 1, 48, 64, 8, device="cuda"))
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager():
+    """The captured forward (no host syncs: boxes stay on the device) must equal the eager launch sequence,
+    for new inputs of the same shape, for both precisions."""
+    g = load_golden("model_c3_64x96x32_b2.npz")
+    m, cfg, sd, x = build(g, "bf16")
+    m.eval()
+    x1 = x.cuda()
+    x2 = O.make_input(tuple(x.shape), seed=77, blob=True).cuda()
+    for prec in ("bf16", "fp32"):
+        m.precision = prec
+        m.use_cuda_graphs = False
+        e1, e2, l2 = m(x1), m(x2), m.predict_labels(x2).clone()
+        m.use_cuda_graphs = True
+        g1, g2, g1b = m(x1), m(x2), m(x1)            # capture on x1, replay on x2, replay on x1 again
+        assert torch.equal(e1, g1) and torch.equal(e2, g2) and torch.equal(g1, g1b), prec
+        assert torch.equal(m.predict_labels(x2), l2)
+        assert not torch.equal(e1, e2)
