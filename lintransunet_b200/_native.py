@@ -36,6 +36,9 @@ SIGNATURES = {
     "ltu_conv3d_tc_tiles": (I, [L, I]),
     "ltu_conv3d_tc_kpad": (I, [I, I]),
     "ltu_conv3d_tc": (I, [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, I, P, P]),
+    "ltu_conv3d_halo_supported": (I, [I, I, I, I, I, I, I, I, I]),
+    "ltu_conv3d_halo_tiles": (I, [I, I, I, I]),
+    "ltu_conv3d_halo": (I, [P, I, P, I, I, I, I, I, P, I, P, I, P, I, P, P]),
     "ltu_instnorm_finalize": (I, [P, P, I, I, I, L, F, P]),
     "ltu_chan_partials": (I, [P, P, I, L, I, I, I, P]),
     "ltu_instnorm_apply": (I, [P, P, P, P, I, L, I, I, I, P]),
@@ -84,5 +87,16 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
 
 
+_replayed = 0
+
+
+def note_replayed(n: int) -> None:
+    """Account for native kernels executed through CUDA-graph replays (the C counter only sees
+    direct launches and capture-time recording)."""
+    global _replayed
+    _replayed += n
+
+
 def launch_count() -> int:
-    return int(lib().ltu_launch_count())
+    """Native (libltu_b200) kernels executed by this process: direct launches + graph replays."""
+    return int(lib().ltu_launch_count()) + _replayed

@@ -1,0 +1,289 @@
+// Family 2, bf16 path, small-channel layers: stride-1 3x3x3 convolution with Cin in {8,16,32} and
+// Cout <= 32 at (near) full resolution -- stem, enc.block0/1 conv1, dec.block3, the finest mask head
+// and final_block.  These layers are bandwidth-bound (AI 86-216 flop/B): an im2col
+// pipeline re-reads every input voxel 27 times from L2 and drowns in address generation.  Here the
+// input halo of a 3-D output tile is staged ONCE in shared memory (16-byte cp.async, zero fill =
+// padding, XOR-swizzled rows) together with all weights, and im2col happens for free in the
+// per-lane row addresses of ldmatrix: A fragments of mma.sync.m16n8k16 (bf16, fp32 accumulate) are
+// 16 consecutive voxels along D x 16 channels of one tap.  B fragments (weights) are shared by four
+// m-tiles per warp.  Epilogue: bias, bf16/fp32 store, per-CTA InstanceNorm partial sums (fixed order).
+//
+// tcgen05 is deliberately not used for these layers: UMMA wants the A operand as 128-byte K-major
+// rows in shared memory, i.e. an explicit im2col copy (27x the smem traffic); ldmatrix gathers rows.
+#include "common.cuh"
+
+namespace ltu {
+
+void count_launch(int n = 1);
+
+struct HaloParams {
+    const bf16* in0; const bf16* in1;
+    int C0, C1;
+    int H, W, D;                 // input == output spatial size (stride 1, pad 1)
+    const bf16* weight;          // [>=16 rows][wld] bf16, K index = tap*Cin + c (the ltu_conv3d_tc packing)
+    int wld;
+    const float* bias;
+    int Cout;                    // channels stored
+    void* out; int out_f32;
+    float* partials; int tiles;  // CTAs per sample
+    int tiles_w, tiles_d;
+};
+
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// CIN: input channels; NT: n-tiles of 8 output channels (2 or 4); TH x TW x 32 output tile
+template <int CIN, int NT, int TH, int TW>
+__global__ void __launch_bounds__(256, (NT == 2 ? 2 : 1))
+conv3d_halo_kernel(const HaloParams p) {
+    constexpr int TD = 32, HH = TH + 2, HW = TW + 2, HD = TD + 2;
+    constexpr int VB = CIN * 2;                               // bytes per halo voxel (no padding: swizzled)
+    constexpr int CPV = CIN / 8;                              // 16-byte chunks per voxel
+    constexpr int NVOX = HH * HW * HD;
+    constexpr int KTOT = 27 * CIN, KSTEPS = (KTOT + 15) / 16;
+    constexpr int WROW = KSTEPS * 16 * 2 + 16;                // weight row pitch in smem (odd multiple of 16 B)
+    constexpr int NROWS = NT * 8;
+    constexpr int MT = TH * TW * 2;                           // m-tiles (16 voxels along D) per CTA tile
+    constexpr int MG = 4;                                     // m-tiles per warp pass (share B fragments)
+    static_assert(MT % (8 * MG) == 0, "tile must split into passes of 4 m-tiles per warp");
+    static_assert((WROW / 16) % 2 == 1, "weight rows must have an odd 16-byte pitch (ldmatrix bank spread)");
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sH = smem;                                 // halo  [NVOX][VB]
+    unsigned char* sW = smem + ((NVOX * VB + 127) / 128) * 128;   // weights [NROWS][WROW]
+    float* sred = reinterpret_cast<float*>(sW + NROWS * WROW);    // [8 warps][NROWS][2]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int td_i = blockIdx.x % p.tiles_d;
+    const int tw_i = (blockIdx.x / p.tiles_d) % p.tiles_w;
+    const int th_i = blockIdx.x / (p.tiles_d * p.tiles_w);
+    const int h0 = th_i * TH, w0 = tw_i * TW, d0 = td_i * TD;
+    const int Cin = p.C0 + p.C1;
+    const int64_t sample = (int64_t)b * p.H * p.W * p.D;
+
+    // ---- stage the halo (zero fill outside the volume) and the weights
+    for (int i = tid; i < NVOX * CPV; i += 256) {
+        const int v = i / CPV, cc = i - v * CPV;
+        const int hd = v % HD, hw = (v / HD) % HW, hh = v / (HD * HW);
+        const int gh = h0 - 1 + hh, gw = w0 - 1 + hw, gd = d0 - 1 + hd;
+        const bool ok = gh >= 0 && gh < p.H && gw >= 0 && gw < p.W && gd >= 0 && gd < p.D;
+        const int c = cc * 8;
+        const int64_t vox = sample + ((int64_t)gh * p.W + gw) * p.D + gd;
+        const bf16* src = c < p.C0 ? p.in0 + vox * p.C0 + c : p.in1 + vox * p.C1 + (c - p.C0);
+        const int sw = CIN == 32 ? ((v >> 1) & 3) : (CIN == 16 ? ((v >> 2) & 1) : 0);
+        cp_async16_zfill(sH + v * VB + ((cc ^ sw) << 4), ok ? src : p.in0, ok ? 16 : 0);
+    }
+    {
+        constexpr int WCH = KSTEPS * 2;                       // 16-byte chunks per weight row
+        for (int i = tid; i < NROWS * WCH; i += 256) {
+            const int n = i / WCH, c = i - n * WCH;
+            cp_async16(sW + n * WROW + c * 16, p.weight + (int64_t)n * p.wld + c * 8);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const uint32_t sH_u = smem_u32_generic(sH), sW_u = smem_u32_generic(sW);
+    const int g = lane >> 2, tq = lane & 3;
+    const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1);      // A: row inside the m-tile addressed by this lane
+    const int lhi = lane >> 4;                                // A: upper 8 of the 16 K values
+    // B: ldmatrix.x4 = (n 0-7,k lo) (n 0-7,k hi) (n 8-15,k lo) (n 8-15,k hi)
+    const uint32_t b_lane = (uint32_t)(((lane & 7) + 8 * (lane >> 4)) * WROW + 16 * ((lane >> 3) & 1));
+
+    float csum[NT][2], csq[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { csum[nt][0] = csum[nt][1] = csq[nt][0] = csq[nt][1] = 0.f; }
+    float bias_r[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = nt * 8 + 2 * tq + j;
+            bias_r[nt][j] = (p.bias != nullptr && c < p.Cout) ? p.bias[c] : 0.f;
+        }
+
+    for (int pass = 0; pass < MT / (8 * MG); ++pass) {
+        // the warp's four m-tiles: index -> (h, w, d-half)
+        int vbase[MG];
+#pragma unroll
+        for (int m = 0; m < MG; ++m) {
+            const int mt = (pass * 8 + warp) * MG + m;
+            const int dh = mt & 1, w = (mt >> 1) % TW, h = (mt >> 1) / TW;
+            vbase[m] = (h * HW + w) * HD + dh * 16 + lrow;   // halo voxel of tap (0,0,0) for this lane's row
+        }
+        float acc[MG][NT][4];
+#pragma unroll
+        for (int m = 0; m < MG; ++m)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[m][nt][i] = 0.f;
+
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            uint32_t bfr[NT / 2][4];
+#pragma unroll
+            for (int np = 0; np < NT / 2; ++np) ldsm4(sW_u + b_lane + np * 16 * WROW + ks * 32, bfr[np]);
+            // tap / channel chunk of this k-step
+            int tapoff, chunk;
+            if (CIN >= 16) {
+                constexpr int SPT = CIN / 16;                 // k-steps per tap
+                const int tap = ks / SPT;
+                tapoff = ((tap / 9) * HW + (tap / 3) % 3) * HD + tap % 3;
+                chunk = (ks % SPT) * 2 + lhi;
+            } else {                                          // CIN == 8: two taps per k-step (tap 27 = zero weights)
+                int tap = 2 * ks + lhi;
+                if (tap > 26) tap = 26;
+                tapoff = ((tap / 9) * HW + (tap / 3) % 3) * HD + tap % 3;
+                chunk = 0;
+            }
+#pragma unroll
+            for (int m = 0; m < MG; ++m) {
+                const int v = vbase[m] + tapoff;
+                const int sw = CIN == 32 ? ((v >> 1) & 3) : (CIN == 16 ? ((v >> 2) & 1) : 0);
+                uint32_t a[4];
+                ldsm4(sH_u + v * VB + ((chunk ^ sw) << 4), a);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    mma_bf16_16816(acc[m][nt], a, bfr[nt >> 1][(nt & 1) * 2], bfr[nt >> 1][(nt & 1) * 2 + 1]);
+            }
+        }
+
+        // ---- epilogue of these m-tiles: rows g and g+8 of each, columns nt*8 + 2*tq (+1)
+#pragma unroll
+        for (int m = 0; m < MG; ++m) {
+            const int mt = (pass * 8 + warp) * MG + m;
+            const int dh = mt & 1, w = (mt >> 1) % TW, h = (mt >> 1) / TW;
+            const int gh = h0 + h, gw = w0 + w;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int gd = d0 + dh * 16 + g + 8 * half;
+                const bool ok = gh < p.H && gw < p.W && gd < p.D;
+                const int64_t row = (sample + ((int64_t)gh * p.W + gw) * p.D + gd) * p.Cout;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int c = nt * 8 + 2 * tq;
+                    float o0 = acc[m][nt][half * 2] + bias_r[nt][0], o1 = acc[m][nt][half * 2 + 1] + bias_r[nt][1];
+                    if (!p.out_f32) {                          // statistics describe the stored (rounded) values
+                        o0 = __bfloat162float(__float2bfloat16_rn(o0));
+                        o1 = __bfloat162float(__float2bfloat16_rn(o1));
+                    }
+                    if (ok) {
+                        if (c < p.Cout) { csum[nt][0] += o0; csq[nt][0] = fmaf(o0, o0, csq[nt][0]); }
+                        if (c + 1 < p.Cout) { csum[nt][1] += o1; csq[nt][1] = fmaf(o1, o1, csq[nt][1]); }
+                        if (p.out_f32) {
+                            float* dst = reinterpret_cast<float*>(p.out) + row + c;
+                            if (c < p.Cout) dst[0] = o0;
+                            if (c + 1 < p.Cout) dst[1] = o1;
+                        } else {
+                            bf16* dst = reinterpret_cast<bf16*>(p.out) + row + c;
+                            if (c + 1 < p.Cout) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(o0, o1);
+                            else if (c < p.Cout) dst[0] = __float2bfloat16_rn(o0);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    if (p.partials != nullptr) {
+        // reduce over the 8 row groups g (lanes 4g+tq), then over the 8 warps in a fixed order
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int o = 4; o <= 16; o <<= 1) {
+                    csum[nt][j] += __shfl_xor_sync(0xffffffffu, csum[nt][j], o);
+                    csq[nt][j] += __shfl_xor_sync(0xffffffffu, csq[nt][j], o);
+                }
+                if (g == 0) {
+                    const int c = nt * 8 + 2 * tq + j;
+                    sred[(warp * NROWS + c) * 2] = csum[nt][j];
+                    sred[(warp * NROWS + c) * 2 + 1] = csq[nt][j];
+                }
+            }
+        __syncthreads();
+        if (tid < p.Cout) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { s += sred[(w * NROWS + tid) * 2]; q += sred[(w * NROWS + tid) * 2 + 1]; }
+            float* dst = p.partials + (((int64_t)b * p.tiles + blockIdx.x) * p.Cout + tid) * 2;
+            dst[0] = s; dst[1] = q;
+        }
+    }
+}
+
+template <int CIN, int NT, int TH, int TW>
+static int halo_launch(HaloParams& p, int B, cudaStream_t st) {
+    constexpr int TD = 32, NVOX = (TH + 2) * (TW + 2) * (TD + 2), KSTEPS = (27 * CIN + 15) / 16;
+    constexpr int WROW = KSTEPS * 32 + 16, NROWS = NT * 8;
+    const size_t smem = ((NVOX * CIN * 2 + 127) / 128) * 128 + (size_t)NROWS * WROW + (size_t)8 * NROWS * 2 * 4;
+    const int tiles_h = (p.H + TH - 1) / TH;
+    p.tiles_w = (p.W + TW - 1) / TW;
+    p.tiles_d = (p.D + TD - 1) / TD;
+    p.tiles = tiles_h * p.tiles_w * p.tiles_d;
+    static thread_local int conf = -1;
+    int dev; cudaGetDevice(&dev);
+    if (conf != dev) {
+        cudaFuncSetAttribute(conv3d_halo_kernel<CIN, NT, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        conf = dev;
+    }
+    conv3d_halo_kernel<CIN, NT, TH, TW><<<dim3(p.tiles, B), 256, smem, st>>>(p);
+    LTU_LAUNCH_CHECK("conv3d_halo");
+    count_launch(1);
+    return LTU_OK;
+}
+
+static void halo_tile(int Cin, int& th, int& tw) {
+    if (Cin == 32) { th = 4; tw = 4; } else { th = 4; tw = 8; }
+}
+
+}  // namespace ltu
+
+using namespace ltu;
+
+extern "C" int ltu_conv3d_halo_supported(int C0, int C1, int Cout, int ksize, int sh, int sw, int sd, int pad, int up2) {
+    const int Cin = C0 + C1;
+    if (ksize != 3 || pad != 1 || sh != 1 || sw != 1 || sd != 1 || up2) return 0;
+    if (!(Cin == 8 || Cin == 16 || Cin == 32) || C0 % 8 != 0 || C1 % 8 != 0) return 0;
+    if (Cout < 1 || Cout > 32) return 0;
+    return 1;
+}
+
+extern "C" int ltu_conv3d_halo_tiles(int H, int W, int D, int Cin) {
+    int th, tw;
+    halo_tile(Cin, th, tw);
+    return ((H + th - 1) / th) * ((W + tw - 1) / tw) * ((D + 31) / 32);
+}
+
+extern "C" int ltu_conv3d_halo(const void* in0, int C0, const void* in1, int C1, int B, int H, int W, int D,
+                               const void* weight_bf16, int weight_ld, const float* bias, int Cout, void* out,
+                               int out_f32, float* partials, ltu_stream_t stream) {
+    LTU_ARG_CHECK(in0 && weight_bf16 && out, "conv3d_halo: null pointer");
+    LTU_ARG_CHECK(ltu_conv3d_halo_supported(C0, C1, Cout, 3, 1, 1, 1, 1, 0), "conv3d_halo: unsupported C0=%d C1=%d Cout=%d", C0, C1, Cout);
+    LTU_ARG_CHECK((in1 != nullptr) == (C1 > 0), "conv3d_halo: in1/C1 mismatch");
+    LTU_ARG_CHECK(B > 0 && B <= 65535 && H > 0 && W > 0 && D > 0, "conv3d_halo: bad shape");
+    const int Cin = C0 + C1;
+    LTU_ARG_CHECK(weight_ld >= ((27 * Cin + 15) / 16) * 16 && weight_ld % 8 == 0, "conv3d_halo: weight row stride too small");
+    LTU_ARG_CHECK(((uintptr_t)in0 & 15) == 0 && ((uintptr_t)in1 & 15) == 0 && ((uintptr_t)weight_bf16 & 15) == 0 &&
+                  ((uintptr_t)out & 3) == 0, "conv3d_halo: misaligned pointer");
+    LTU_ARG_CHECK(out_f32 || Cout % 2 == 0, "conv3d_halo: bf16 output needs an even Cout");
+    HaloParams p;
+    p.in0 = (const bf16*)in0; p.in1 = (const bf16*)in1; p.C0 = C0; p.C1 = C1; p.H = H; p.W = W; p.D = D;
+    p.weight = (const bf16*)weight_bf16; p.wld = weight_ld; p.bias = bias; p.Cout = Cout; p.out = out; p.out_f32 = out_f32;
+    p.partials = partials;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool wide = Cout > 16;
+    if (Cin == 8)  return wide ? halo_launch<8, 4, 4, 8>(p, B, st) : halo_launch<8, 2, 4, 8>(p, B, st);
+    if (Cin == 16) return wide ? halo_launch<16, 4, 4, 8>(p, B, st) : halo_launch<16, 2, 4, 8>(p, B, st);
+    return wide ? halo_launch<32, 4, 4, 4>(p, B, st) : halo_launch<32, 2, 4, 4>(p, B, st);
+}

@@ -7,6 +7,7 @@ nothing falls back to PyTorch kernels: a CPU tensor raises.
 """
 from __future__ import annotations
 
+import os
 from ctypes import c_void_p
 from typing import Optional, Tuple
 
@@ -17,6 +18,7 @@ from ._native import check
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_LRELU = 0, 1
+USE_HALO_CONV = os.environ.get("LTU_DISABLE_HALO", "0") != "1"     # A/B switch for the small-channel conv kernel
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -198,15 +200,26 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     V = Ho * Wo * Do
     use_tc = (w_tc is not None and x0.dtype == torch.bfloat16 and (out_f32 or cout % 8 == 0)
               and L.ltu_conv3d_tc_supported(C0, C1, cout, ksize, pad) == 1)
+    # small-channel stride-1 layers: shared-memory halo + mma.sync kernel (needs the same bf16 packing)
+    use_halo = (USE_HALO_CONV and w_tc is not None and not up2 and x0.dtype == torch.bfloat16
+                and (out_f32 or cout % 2 == 0) and w_tc.shape[0] >= (32 if cout > 16 else 16)
+                and L.ltu_conv3d_halo_supported(C0, C1, cout, ksize, stride[0], stride[1], stride[2], pad, 0) == 1)
     out = torch.empty(B, Ho, Wo, Do, cout, dtype=torch.float32 if out_f32 else x0.dtype, device=dev)
-    tiles = L.ltu_conv3d_tc_tiles(V, int(up2)) if use_tc else L.ltu_conv3d_tiles(V, cout)
+    if use_halo:
+        tiles = L.ltu_conv3d_halo_tiles(Ho, Wo, Do, C0 + C1)
+    else:
+        tiles = L.ltu_conv3d_tc_tiles(V, int(up2)) if use_tc else L.ltu_conv3d_tiles(V, cout)
     partials = torch.empty(B, tiles, cout, 2, dtype=torch.float32, device=dev) if want_stats else None
     cin = C0 + C1
     nbytes = (x0.numel() + (0 if x1 is None else x1.numel())) * x0.element_size() + out.numel() * out.element_size()
     # algorithmic flops: the un-folded count 2*k^3*Cin*Cout*B*V (the folded up2 path executes 8/27 of it)
-    prof = ("conv3d_tc" if use_tc else "conv3d", nbytes, 2 * ksize ** 3 * cin * cout * B * V)
+    prof = ("conv3d_halo" if use_halo else ("conv3d_tc" if use_tc else "conv3d"), nbytes,
+            2 * ksize ** 3 * cin * cout * B * V)
     with _Guard(dev, prof) as st:
-        if use_tc:
+        if use_halo:
+            check(L.ltu_conv3d_halo(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, _p(w_tc), w_tc.shape[1], _p(bias), cout,
+                                    _p(out), int(out_f32), _p(partials), st), "ltu_conv3d_halo")
+        elif use_tc:
             check(L.ltu_conv3d_tc(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), ksize, stride[0], stride[1],
                                   stride[2], pad, _p(w_tc), _p(bias), cout, _p(out), int(out_f32), Ho, Wo, Do,
                                   _p(partials), st), "ltu_conv3d_tc")

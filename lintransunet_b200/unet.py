@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import _native, ops
 
 __all__ = ["MaskTransUnet", "Encoder", "ROIDecoder", "Model_Dict", "get_model_dict"]
 
@@ -371,6 +371,7 @@ class MaskTransUnet(nn.Module):
                 self._graphs[key] = ent
             ent["x"].copy_(x)
             ent["graph"].replay()
+            _native.note_replayed(ent["launches"])       # kernels executed by the replay (bench gpu_launches)
             return ent["out"]
 
     def _capture(self, x: torch.Tensor, plan: "_Plan", head: str) -> dict:
@@ -382,9 +383,12 @@ class MaskTransUnet(nn.Module):
         torch.cuda.current_stream(x.device).wait_stream(side)
         torch.cuda.synchronize(x.device)
         graph = torch.cuda.CUDAGraph()
+        n0 = _native.lib().ltu_launch_count()
         with torch.cuda.graph(graph):
             out = self._forward_impl(static_x, plan, head)
-        return dict(graph=graph, x=static_x, out=out, plan=plan)
+        captured = int(_native.lib().ltu_launch_count() - n0)      # native kernels recorded in the graph
+        _native.note_replayed(-captured)                          # capture itself executed nothing
+        return dict(graph=graph, x=static_x, out=out, plan=plan, launches=captured)
 
     # -- building blocks -----------------------------------------------------------------
     def _tap(self, name: str, t: torch.Tensor):

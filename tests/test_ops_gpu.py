@@ -224,6 +224,51 @@ def test_conv3d(dtype, case, tc):
         assert rel_err(from_cl(z.float()), ref_z) < (1e-4 if dtype == torch.float32 else TOL[dtype])
 
 
+HALO_CASES = [
+    # cin, cin1, cout, spatial (H,W,D), out_f32        (stride 1, k3: the shared-memory halo / mma.sync kernel)
+    (8, 0, 16, (8, 8, 32), False),          # stem (4 real + 4 zero channels)
+    (16, 0, 16, (5, 9, 40), False),         # ragged tiles in every axis
+    (16, 0, 32, (4, 8, 32), False),
+    (32, 0, 16, (4, 4, 32), False),
+    (16, 16, 16, (6, 5, 7), False),         # cat(x, skip), tiny depth
+    (8, 8, 16, (4, 9, 33), False),
+    (32, 0, 32, (7, 3, 35), False),
+    (32, 0, 3, (5, 6, 34), True),           # finest mask head, fp32 logits
+    (16, 0, 12, (4, 8, 16), True),          # final block, 3 classes
+    (16, 0, 2, (3, 3, 3), True),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv3d_halo_matches_reference_and_tc_path(case):
+    ops = _ops()
+    from lintransunet_b200.unet import _ConvW
+    cin, cin1, cout, (H, W, D), out_f32 = case
+    B = 2
+    conv = torch.nn.Conv3d(cin + cin1, cout, 3, padding=1)
+    with torch.no_grad():
+        conv.weight.copy_(q_(conv.weight, torch.bfloat16))
+    cw = _ConvW(conv, want_tc=True)
+    x0 = q_(rnd((B, cin, H, W, D), 70), torch.bfloat16)
+    x1 = q_(rnd((B, cin1, H, W, D), 71), torch.bfloat16) if cin1 else None
+    ref = F.conv3d(x0 if x1 is None else torch.cat((x0, x1), 1), conv.weight.detach(), conv.bias.detach(), padding=1)
+    dev = lambda t: None if t is None else to_cl(t).to("cuda", torch.bfloat16)
+    outs = {}
+    for halo in (True, False):
+        ops.USE_HALO_CONV = halo
+        try:
+            y, partials, tiles = ops.conv3d(dev(x0), cw.w.cuda(), cw.b.cuda(), cout, 3, pad=1, x1=dev(x1), out_f32=out_f32,
+                                            want_stats=True, w_tc=cw.w_tc.cuda())
+        finally:
+            ops.USE_HALO_CONV = True
+        assert rel_err(from_cl(y.float()), ref) < (2e-5 if out_f32 else TOL[torch.bfloat16]), halo
+        stats = ops.instnorm_finalize(partials, H * W * D)
+        assert rel_err(stats[..., 0], ref.mean(dim=(2, 3, 4))) < 5e-3
+        assert rel_err(stats[..., 1], 1 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5)) < 5e-3
+        outs[halo] = y.float()
+    assert rel_err(outs[True], outs[False]) < (2e-5 if out_f32 else 8e-3)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_chan_stats(dtype):
     ops = _ops()
