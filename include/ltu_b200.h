@@ -104,16 +104,16 @@ int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int H
 /* Small-channel stride-1 3x3x3 convolution for bf16 activations (stem, enc.block0/1 conv1,
  * dec.block3, finest mask head, final_block): the input halo of a 3-D output tile and all weights are
  * staged once in shared memory and im2col happens in the ldmatrix row addresses of mma.sync
- * (bandwidth-bound layers).  Supported: ksize 3, pad 1, stride 1, no up2, C0+C1 in
- * {8,16,32}, C0 % 8 == 0, Cout <= 32 (even for bf16 output).  weight_bf16 is the ltu_conv3d_tc packing
+ * (bandwidth-bound layers).  Supported: (ksize,pad) = (3,1) or (1,0: the 1x1x1 gate convs,
+ * Cin >= 16), stride 1, no up2, C0+C1 in {8,16,32}, C0 % 8 == 0, Cout <= 32 (even for bf16 output).  weight_bf16 is the ltu_conv3d_tc packing
  * ([>=16 rows][weight_ld], K index = tap*Cin + c).  partials: [B][tiles][Cout][2] with
  * tiles = ltu_conv3d_halo_tiles(H, W, D, Cin).                                                  */
 int ltu_conv3d_halo_supported(int C0, int C1, int Cout, int ksize, int sh, int sw, int sd, int pad,
                               int up2);
 int ltu_conv3d_halo_tiles(int H, int W, int D, int Cin);
 int ltu_conv3d_halo(const void* in0, int C0, const void* in1, int C1, int B, int H, int W, int D,
-                    const void* weight_bf16, int weight_ld, const float* bias, int Cout, void* out,
-                    int out_f32, float* partials, ltu_stream_t stream);
+                    int ksize, const void* weight_bf16, int weight_ld, const float* bias, int Cout,
+                    void* out, int out_f32, float* partials, ltu_stream_t stream);
 
 /* InstanceNorm3d (no affine, eps 1e-5, biased variance):
  * finalize : partials [B][tiles][C][2] -> stats [B][C][2] = (mean, rstd), fixed summation order

@@ -39,15 +39,17 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// CIN: input channels; NT: n-tiles of 8 output channels (2 or 4); TH x TW x 32 output tile
-template <int CIN, int NT, int TH, int TW>
+// CIN: input channels; NT: n-tiles of 8 output channels (2 or 4); TH x TW x 32 output tile;
+// KS: kernel size 3 (pad 1) or 1 (pad 0: the 1x1x1 gate convolutions, no halo)
+template <int CIN, int NT, int TH, int TW, int KS>
 __global__ void __launch_bounds__(256, (NT == 2 ? 2 : 1))
 conv3d_halo_kernel(const HaloParams p) {
-    constexpr int TD = 32, HH = TH + 2, HW = TW + 2, HD = TD + 2;
+    constexpr int TD = 32, PAD = KS / 2, HH = TH + 2 * PAD, HW = TW + 2 * PAD, HD = TD + 2 * PAD;
+    constexpr int TAPS = KS * KS * KS;
     constexpr int VB = CIN * 2;                               // bytes per halo voxel (no padding: swizzled)
     constexpr int CPV = CIN / 8;                              // 16-byte chunks per voxel
     constexpr int NVOX = HH * HW * HD;
-    constexpr int KTOT = 27 * CIN, KSTEPS = (KTOT + 15) / 16;
+    constexpr int KTOT = TAPS * CIN, KSTEPS = (KTOT + 15) / 16;
     constexpr int WROW = KSTEPS * 16 * 2 + 16;                // weight row pitch in smem (odd multiple of 16 B)
     constexpr int NROWS = NT * 8;
     constexpr int MT = TH * TW * 2;                           // m-tiles (16 voxels along D) per CTA tile
@@ -72,7 +74,7 @@ conv3d_halo_kernel(const HaloParams p) {
     for (int i = tid; i < NVOX * CPV; i += 256) {
         const int v = i / CPV, cc = i - v * CPV;
         const int hd = v % HD, hw = (v / HD) % HW, hh = v / (HD * HW);
-        const int gh = h0 - 1 + hh, gw = w0 - 1 + hw, gd = d0 - 1 + hd;
+        const int gh = h0 - PAD + hh, gw = w0 - PAD + hw, gd = d0 - PAD + hd;
         const bool ok = gh >= 0 && gh < p.H && gw >= 0 && gw < p.W && gd >= 0 && gd < p.D;
         const int c = cc * 8;
         const int64_t vox = sample + ((int64_t)gh * p.W + gw) * p.D + gd;
@@ -137,12 +139,12 @@ conv3d_halo_kernel(const HaloParams p) {
             if (CIN >= 16) {
                 constexpr int SPT = CIN / 16;                 // k-steps per tap
                 const int tap = ks / SPT;
-                tapoff = ((tap / 9) * HW + (tap / 3) % 3) * HD + tap % 3;
+                tapoff = KS == 3 ? ((tap / 9) * HW + (tap / 3) % 3) * HD + tap % 3 : 0;
                 chunk = (ks % SPT) * 2 + lhi;
             } else {                                          // CIN == 8: two taps per k-step (tap 27 = zero weights)
                 int tap = 2 * ks + lhi;
-                if (tap > 26) tap = 26;
-                tapoff = ((tap / 9) * HW + (tap / 3) % 3) * HD + tap % 3;
+                if (tap > TAPS - 1) tap = TAPS - 1;
+                tapoff = KS == 3 ? ((tap / 9) * HW + (tap / 3) % 3) * HD + tap % 3 : 0;
                 chunk = 0;
             }
 #pragma unroll
@@ -222,9 +224,10 @@ conv3d_halo_kernel(const HaloParams p) {
     }
 }
 
-template <int CIN, int NT, int TH, int TW>
+template <int CIN, int NT, int TH, int TW, int KS>
 static int halo_launch(HaloParams& p, int B, cudaStream_t st) {
-    constexpr int TD = 32, NVOX = (TH + 2) * (TW + 2) * (TD + 2), KSTEPS = (27 * CIN + 15) / 16;
+    constexpr int TD = 32, PAD = KS / 2, NVOX = (TH + 2 * PAD) * (TW + 2 * PAD) * (TD + 2 * PAD);
+    constexpr int KSTEPS = (KS * KS * KS * CIN + 15) / 16;
     constexpr int WROW = KSTEPS * 32 + 16, NROWS = NT * 8;
     const size_t smem = ((NVOX * CIN * 2 + 127) / 128) * 128 + (size_t)NROWS * WROW + (size_t)8 * NROWS * 2 * 4;
     const int tiles_h = (p.H + TH - 1) / TH;
@@ -234,10 +237,10 @@ static int halo_launch(HaloParams& p, int B, cudaStream_t st) {
     static thread_local int conf = -1;
     int dev; cudaGetDevice(&dev);
     if (conf != dev) {
-        cudaFuncSetAttribute(conv3d_halo_kernel<CIN, NT, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv3d_halo_kernel<CIN, NT, TH, TW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         conf = dev;
     }
-    conv3d_halo_kernel<CIN, NT, TH, TW><<<dim3(p.tiles, B), 256, smem, st>>>(p);
+    conv3d_halo_kernel<CIN, NT, TH, TW, KS><<<dim3(p.tiles, B), 256, smem, st>>>(p);
     LTU_LAUNCH_CHECK("conv3d_halo");
     count_launch(1);
     return LTU_OK;
@@ -253,8 +256,9 @@ using namespace ltu;
 
 extern "C" int ltu_conv3d_halo_supported(int C0, int C1, int Cout, int ksize, int sh, int sw, int sd, int pad, int up2) {
     const int Cin = C0 + C1;
-    if (ksize != 3 || pad != 1 || sh != 1 || sw != 1 || sd != 1 || up2) return 0;
+    if (!((ksize == 3 && pad == 1) || (ksize == 1 && pad == 0)) || sh != 1 || sw != 1 || sd != 1 || up2) return 0;
     if (!(Cin == 8 || Cin == 16 || Cin == 32) || C0 % 8 != 0 || C1 % 8 != 0) return 0;
+    if (ksize == 1 && Cin == 8) return 0;
     if (Cout < 1 || Cout > 32) return 0;
     return 1;
 }
@@ -265,15 +269,15 @@ extern "C" int ltu_conv3d_halo_tiles(int H, int W, int D, int Cin) {
     return ((H + th - 1) / th) * ((W + tw - 1) / tw) * ((D + 31) / 32);
 }
 
-extern "C" int ltu_conv3d_halo(const void* in0, int C0, const void* in1, int C1, int B, int H, int W, int D,
+extern "C" int ltu_conv3d_halo(const void* in0, int C0, const void* in1, int C1, int B, int H, int W, int D, int ksize,
                                const void* weight_bf16, int weight_ld, const float* bias, int Cout, void* out,
                                int out_f32, float* partials, ltu_stream_t stream) {
     LTU_ARG_CHECK(in0 && weight_bf16 && out, "conv3d_halo: null pointer");
-    LTU_ARG_CHECK(ltu_conv3d_halo_supported(C0, C1, Cout, 3, 1, 1, 1, 1, 0), "conv3d_halo: unsupported C0=%d C1=%d Cout=%d", C0, C1, Cout);
+    LTU_ARG_CHECK(ltu_conv3d_halo_supported(C0, C1, Cout, ksize, 1, 1, 1, ksize / 2, 0), "conv3d_halo: unsupported C0=%d C1=%d Cout=%d k=%d", C0, C1, Cout, ksize);
     LTU_ARG_CHECK((in1 != nullptr) == (C1 > 0), "conv3d_halo: in1/C1 mismatch");
     LTU_ARG_CHECK(B > 0 && B <= 65535 && H > 0 && W > 0 && D > 0, "conv3d_halo: bad shape");
     const int Cin = C0 + C1;
-    LTU_ARG_CHECK(weight_ld >= ((27 * Cin + 15) / 16) * 16 && weight_ld % 8 == 0, "conv3d_halo: weight row stride too small");
+    LTU_ARG_CHECK(weight_ld >= ((ksize * ksize * ksize * Cin + 15) / 16) * 16 && weight_ld % 8 == 0, "conv3d_halo: weight row stride too small");
     LTU_ARG_CHECK(((uintptr_t)in0 & 15) == 0 && ((uintptr_t)in1 & 15) == 0 && ((uintptr_t)weight_bf16 & 15) == 0 &&
                   ((uintptr_t)out & 3) == 0, "conv3d_halo: misaligned pointer");
     LTU_ARG_CHECK(out_f32 || Cout % 2 == 0, "conv3d_halo: bf16 output needs an even Cout");
@@ -283,7 +287,11 @@ extern "C" int ltu_conv3d_halo(const void* in0, int C0, const void* in1, int C1,
     p.partials = partials;
     cudaStream_t st = (cudaStream_t)stream;
     const bool wide = Cout > 16;
-    if (Cin == 8)  return wide ? halo_launch<8, 4, 4, 8>(p, B, st) : halo_launch<8, 2, 4, 8>(p, B, st);
-    if (Cin == 16) return wide ? halo_launch<16, 4, 4, 8>(p, B, st) : halo_launch<16, 2, 4, 8>(p, B, st);
-    return wide ? halo_launch<32, 4, 4, 4>(p, B, st) : halo_launch<32, 2, 4, 4>(p, B, st);
+    if (ksize == 1) {
+        if (Cin == 16) return wide ? halo_launch<16, 4, 4, 8, 1>(p, B, st) : halo_launch<16, 2, 4, 8, 1>(p, B, st);
+        return wide ? halo_launch<32, 4, 4, 4, 1>(p, B, st) : halo_launch<32, 2, 4, 4, 1>(p, B, st);
+    }
+    if (Cin == 8)  return wide ? halo_launch<8, 4, 4, 8, 3>(p, B, st) : halo_launch<8, 2, 4, 8, 3>(p, B, st);
+    if (Cin == 16) return wide ? halo_launch<16, 4, 4, 8, 3>(p, B, st) : halo_launch<16, 2, 4, 8, 3>(p, B, st);
+    return wide ? halo_launch<32, 4, 4, 4, 3>(p, B, st) : halo_launch<32, 2, 4, 4, 3>(p, B, st);
 }

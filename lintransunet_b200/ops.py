@@ -217,8 +217,8 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
             2 * ksize ** 3 * cin * cout * B * V)
     with _Guard(dev, prof) as st:
         if use_halo:
-            check(L.ltu_conv3d_halo(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, _p(w_tc), w_tc.shape[1], _p(bias), cout,
-                                    _p(out), int(out_f32), _p(partials), st), "ltu_conv3d_halo")
+            check(L.ltu_conv3d_halo(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, ksize, _p(w_tc), w_tc.shape[1], _p(bias),
+                                    cout, _p(out), int(out_f32), _p(partials), st), "ltu_conv3d_halo")
         elif use_tc:
             check(L.ltu_conv3d_tc(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), ksize, stride[0], stride[1],
                                   stride[2], pad, _p(w_tc), _p(bias), cout, _p(out), int(out_f32), Ho, Wo, Do,

@@ -236,6 +236,9 @@ HALO_CASES = [
     (32, 0, 3, (5, 6, 34), True),           # finest mask head, fp32 logits
     (16, 0, 12, (4, 8, 16), True),          # final block, 3 classes
     (16, 0, 2, (3, 3, 3), True),
+    (16, 0, 16, (5, 9, 40), False, 1),      # gate W_x, 1x1x1
+    (32, 0, 16, (4, 5, 33), False, 1),      # gate W_g, 1x1x1
+    (32, 0, 32, (3, 8, 32), False, 1),
 ]
 
 
@@ -243,22 +246,23 @@ HALO_CASES = [
 def test_conv3d_halo_matches_reference_and_tc_path(case):
     ops = _ops()
     from lintransunet_b200.unet import _ConvW
-    cin, cin1, cout, (H, W, D), out_f32 = case
+    cin, cin1, cout, (H, W, D), out_f32 = case[:5]
+    k = case[5] if len(case) > 5 else 3
     B = 2
-    conv = torch.nn.Conv3d(cin + cin1, cout, 3, padding=1)
+    conv = torch.nn.Conv3d(cin + cin1, cout, k, padding=k // 2)
     with torch.no_grad():
         conv.weight.copy_(q_(conv.weight, torch.bfloat16))
     cw = _ConvW(conv, want_tc=True)
     x0 = q_(rnd((B, cin, H, W, D), 70), torch.bfloat16)
     x1 = q_(rnd((B, cin1, H, W, D), 71), torch.bfloat16) if cin1 else None
-    ref = F.conv3d(x0 if x1 is None else torch.cat((x0, x1), 1), conv.weight.detach(), conv.bias.detach(), padding=1)
+    ref = F.conv3d(x0 if x1 is None else torch.cat((x0, x1), 1), conv.weight.detach(), conv.bias.detach(), padding=k // 2)
     dev = lambda t: None if t is None else to_cl(t).to("cuda", torch.bfloat16)
     outs = {}
     for halo in (True, False):
         ops.USE_HALO_CONV = halo
         try:
-            y, partials, tiles = ops.conv3d(dev(x0), cw.w.cuda(), cw.b.cuda(), cout, 3, pad=1, x1=dev(x1), out_f32=out_f32,
-                                            want_stats=True, w_tc=cw.w_tc.cuda())
+            y, partials, tiles = ops.conv3d(dev(x0), cw.w.cuda(), cw.b.cuda(), cout, k, pad=k // 2, x1=dev(x1),
+                                            out_f32=out_f32, want_stats=True, w_tc=cw.w_tc.cuda())
         finally:
             ops.USE_HALO_CONV = True
         assert rel_err(from_cl(y.float()), ref) < (2e-5 if out_f32 else TOL[torch.bfloat16]), halo
