@@ -63,16 +63,16 @@ __device__ __forceinline__ void stage_rows(bf16* smem, const bf16* src, int64_t 
     }
 }
 
-template <int HEADS>
-__global__ void __launch_bounds__(256)
+template <int HEADS, int NSTAGE>
+__global__ void __launch_bounds__(256, 2)
 kv_reduce_mma_kernel(const bf16* __restrict__ K, const bf16* __restrict__ V, int64_t ld, float* __restrict__ part,
                      int64_t N, int chunks, int tiles_per_chunk) {
     constexpr int C = HEADS * 32, CPR = C / 8, RPP = 256 / CPR, NCH = kTT / RPP, LDS = C + 8, WPH = 8 / HEADS;
     static_assert(NCH >= 1, "tile must give every thread at least one 16-byte chunk");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    bf16* sK = reinterpret_cast<bf16*>(smem_raw);                 // [2][kTT][LDS]  (K, then P in place)
-    bf16* sV = sK + 2 * kTT * LDS;                                // [2][kTT][LDS]
-    float* sRed = reinterpret_cast<float*>(sV + 2 * kTT * LDS);   // [RPP][C]
+    bf16* sK = reinterpret_cast<bf16*>(smem_raw);                 // [NSTAGE][kTT][LDS]  (K, then P in place)
+    bf16* sV = sK + NSTAGE * kTT * LDS;                           // [NSTAGE][kTT][LDS]
+    float* sRed = reinterpret_cast<float*>(sV + NSTAGE * kTT * LDS);   // [RPP][C]
     float* sRef = sRed + RPP * C;                                 // [C] reference r_j * log2e
     float* sScale = sRef + C;                                     // [C] rescale factors (slow path)
 
@@ -109,18 +109,25 @@ kv_reduce_mma_kernel(const bf16* __restrict__ K, const bf16* __restrict__ V, int
     for (int c = 0; c < 8; ++c) rj[c] = 0.f;
     const uint32_t ones = (lane >> 2) == 0 ? 0x3F803F80u : 0u;     // B tile with column 0 = 1.0 (bf16 pairs)
 
-    stage_rows<C, LDS>(sK, Kb, ld, tile0 * kTT, N);
-    stage_rows<C, LDS>(sV, Vb, ld, tile0 * kTT, N);
-    cp_async_commit();
-
-    for (int64_t t = 0; t < ntiles; ++t) {
-        const int buf = (int)(t & 1);
-        if (t + 1 < ntiles) {
-            stage_rows<C, LDS>(sK + (buf ^ 1) * kTT * LDS, Kb, ld, (tile0 + t + 1) * kTT, N);
-            stage_rows<C, LDS>(sV + (buf ^ 1) * kTT * LDS, Vb, ld, (tile0 + t + 1) * kTT, N);
+    // NSTAGE-deep cp.async ring: NSTAGE-1 tiles are in flight while one is processed
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+        if (s < ntiles) {
+            stage_rows<C, LDS>(sK + s * kTT * LDS, Kb, ld, (tile0 + s) * kTT, N);
+            stage_rows<C, LDS>(sV + s * kTT * LDS, Vb, ld, (tile0 + s) * kTT, N);
         }
         cp_async_commit();
-        cp_async_wait<1>();
+    }
+
+    for (int64_t t = 0; t < ntiles; ++t) {
+        const int buf = (int)(t % NSTAGE);
+        if (t + NSTAGE - 1 < ntiles) {
+            const int nb = (int)((t + NSTAGE - 1) % NSTAGE);
+            stage_rows<C, LDS>(sK + nb * kTT * LDS, Kb, ld, (tile0 + t + NSTAGE - 1) * kTT, N);
+            stage_rows<C, LDS>(sV + nb * kTT * LDS, Vb, ld, (tile0 + t + NSTAGE - 1) * kTT, N);
+        }
+        cp_async_commit();
+        cp_async_wait<NSTAGE - 1>();
         __syncthreads();                                          // tile t landed
         bf16* tK = sK + buf * kTT * LDS;
         const bf16* tV = sV + buf * kTT * LDS;
@@ -269,13 +276,13 @@ kv_reduce_mma_kernel(const bf16* __restrict__ K, const bf16* __restrict__ V, int
     }
 }
 
-template <int HEADS>
-__global__ void __launch_bounds__(256)
+template <int HEADS, int NSTAGE>
+__global__ void __launch_bounds__(256, 2)
 q_readout_mma_kernel(const bf16* __restrict__ Q, int64_t ldq, const float* __restrict__ ctx, bf16* __restrict__ O,
                      int64_t ldo, int64_t N, int tiles_per_cta) {
     constexpr int C = HEADS * 32, CPR = C / 8, LDS = C + 8, WPH = 8 / HEADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    bf16* sQ = reinterpret_cast<bf16*>(smem_raw);                 // [2][kTT][LDS]
+    bf16* sQ = reinterpret_cast<bf16*>(smem_raw);                 // [NSTAGE][kTT][LDS]
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -304,13 +311,17 @@ q_readout_mma_kernel(const bf16* __restrict__ Q, int64_t ldq, const float* __res
     if (ntiles > tiles_per_cta) ntiles = tiles_per_cta;
     if (ntiles < 0) ntiles = 0;
 
-    if (ntiles > 0) stage_rows<C, LDS>(sQ, Qb, ldq, tile0 * kTT, N);
-    cp_async_commit();
-    for (int64_t t = 0; t < ntiles; ++t) {
-        const int buf = (int)(t & 1);
-        if (t + 1 < ntiles) stage_rows<C, LDS>(sQ + (buf ^ 1) * kTT * LDS, Qb, ldq, (tile0 + t + 1) * kTT, N);
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+        if (s < ntiles) stage_rows<C, LDS>(sQ + s * kTT * LDS, Qb, ldq, (tile0 + s) * kTT, N);
         cp_async_commit();
-        cp_async_wait<1>();
+    }
+    for (int64_t t = 0; t < ntiles; ++t) {
+        const int buf = (int)(t % NSTAGE);
+        if (t + NSTAGE - 1 < ntiles)
+            stage_rows<C, LDS>(sQ + (int)((t + NSTAGE - 1) % NSTAGE) * kTT * LDS, Qb, ldq, (tile0 + t + NSTAGE - 1) * kTT, N);
+        cp_async_commit();
+        cp_async_wait<NSTAGE - 1>();
         __syncthreads();
         bf16* tQ = sQ + buf * kTT * LDS;
         const int64_t row0 = (tile0 + t) * kTT;
@@ -386,11 +397,12 @@ template <int HEADS>
 static int kv_mma_launch(const bf16* k, const bf16* v, int64_t ld, float* ws, int B, int64_t N, int chunks,
                          int tiles_per_chunk, cudaStream_t st) {
     constexpr int C = HEADS * 32, LDS = C + 8, RPP = 256 / (C / 8);
-    const size_t smem = (size_t)4 * kTT * LDS * 2 + (size_t)(RPP * C + 2 * C) * 4;
+    constexpr int NSTAGE = HEADS == 8 ? 3 : 4;                    // ~100 KB / ~70 KB / ~37 KB of tiles per CTA
+    const size_t smem = (size_t)2 * NSTAGE * kTT * LDS * 2 + (size_t)(RPP * C + 2 * C) * 4;
     static thread_local int conf = -1;
     int dev; cudaGetDevice(&dev);
-    if (conf != dev) { cudaFuncSetAttribute(kv_reduce_mma_kernel<HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); conf = dev; }
-    kv_reduce_mma_kernel<HEADS><<<dim3(chunks, B), 256, smem, st>>>(k, v, ld, ws, N, chunks, tiles_per_chunk);
+    if (conf != dev) { cudaFuncSetAttribute(kv_reduce_mma_kernel<HEADS, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); conf = dev; }
+    kv_reduce_mma_kernel<HEADS, NSTAGE><<<dim3(chunks, B), 256, smem, st>>>(k, v, ld, ws, N, chunks, tiles_per_chunk);
     LTU_LAUNCH_CHECK("kv_reduce_mma");
     return LTU_OK;
 }
@@ -399,17 +411,18 @@ template <int HEADS>
 static int q_mma_launch(const bf16* q, int64_t ldq, const float* ctx, bf16* out, int64_t ldo, int B, int64_t N,
                         cudaStream_t st) {
     constexpr int C = HEADS * 32, LDS = C + 8;
+    constexpr int NSTAGE = 4;
     const int64_t tiles = ceil_div64(N, kTT);
-    int64_t want = ceil_div64(6 * (int64_t)sm_count(), B);
+    int64_t want = ceil_div64(4 * (int64_t)sm_count(), B);
     int64_t ctas = tiles < want ? tiles : want;
     if (ctas < 1) ctas = 1;
     const int tiles_per_cta = (int)ceil_div64(tiles, ctas);
     ctas = ceil_div64(tiles, tiles_per_cta);
-    const size_t smem = (size_t)2 * kTT * LDS * 2;
+    const size_t smem = (size_t)NSTAGE * kTT * LDS * 2;
     static thread_local int conf = -1;
     int dev; cudaGetDevice(&dev);
-    if (conf != dev) { cudaFuncSetAttribute(q_readout_mma_kernel<HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); conf = dev; }
-    q_readout_mma_kernel<HEADS><<<dim3((unsigned)ctas, B), 256, smem, st>>>(q, ldq, ctx, out, ldo, N, tiles_per_cta);
+    if (conf != dev) { cudaFuncSetAttribute(q_readout_mma_kernel<HEADS, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); conf = dev; }
+    q_readout_mma_kernel<HEADS, NSTAGE><<<dim3((unsigned)ctas, B), 256, smem, st>>>(q, ldq, ctx, out, ldo, N, tiles_per_cta);
     LTU_LAUNCH_CHECK("q_readout_mma");
     count_launch(1);
     return LTU_OK;

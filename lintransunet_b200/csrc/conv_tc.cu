@@ -18,113 +18,11 @@
 // model/Unet_3Dblock.py:553).  nn.Upsample(nearest x2) + 3x3x3 conv of up_embed (:421-422) is FOLDED:
 // output voxels of parity class (pa,pb,pc) see only 2x2x2 distinct source voxels, so each class is a
 // 2x2x2 convolution of the low-resolution input with pre-summed weights (8/27 of the flops and loads).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ltu {
 
 void count_launch(int n = 1);
-
-constexpr int kTcM = 128;          // output voxels per tile
-constexpr int kTcBK = 64;          // K elements per pipeline stage (128 bytes of bf16 = one swizzle row)
-constexpr int kTcProducers = 128;
-constexpr int kTcThreads = 160;    // 4 producer/epilogue warps + 1 MMA warp
-
-struct TcParams {
-    const bf16* in0; const bf16* in1;
-    int C0, C1, log2cin;
-    int Hi, Wi, Di, up2;
-    int ks, pad, sh, sw, sd;
-    const bf16* weight;   // [Cout][Kpad]
-    int Kpad, Ktot;
-    const float* bias;
-    int Cout;             // UMMA N (multiple of 16, zero-padded weight rows)
-    int Cstore;           // channels actually written (<= Cout)
-    void* out; int out_f32;
-    int Ho, Wo, Do;
-    float* partials; int tiles;
-    int stages, tmem_cols;
-    int fold;             // 1: nearest-x2 upsample folded into 8 parity classes of 2x2x2 taps (blockIdx.z)
-    int ntaps;            // 27, 1 or 8 (fold)
-    int64_t w_class_stride;   // elements between the weight slabs of two parity classes (fold)
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void cp16(uint32_t dst, const void* src, int bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (1024 B:
-//   8 rows x 128 B) | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Sum v[i] over the 32 lanes for all 32 columns with 31 shuffles: afterwards lane l holds the
-// total of column l.  Fixed butterfly order => deterministic.
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const bool upper = (lane & s) != 0;
-#pragma unroll
-        for (int i = 0; i < s; ++i) {
-            float send = upper ? v[i] : v[i + s];
-            float keep = upper ? v[i + s] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-    return v[0];
-}
 
 __global__ void __launch_bounds__(kTcThreads)
 conv3d_tc_kernel(const TcParams p) {

@@ -1,0 +1,27 @@
+#!/bin/bash
+# Runs on the GPU box (under gpurun): per-launch time lists and a few `ncu --set full` captures of the
+# dominant kernels, exported to CSV so that only small files travel back (gpurun_out/ <= 64 MiB).
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+T="python tools/ncu_target.py"
+NCU="ncu --clock-control none"
+$T > $OUT/ncu_plain.log 2>&1 || { echo "plain run failed"; exit 1; }
+# (1) every launch of two eager forwards (batch 8 x 128^3, bf16) with its device time
+$NCU --metrics gpu__time_duration.sum -c 4000 --csv --log-file $OUT/launches_forward.csv $T > $OUT/ncu_l1.log 2>&1
+# (2) full captures, a few launches each (second forward: skip the first forward's instances)
+cap() {  # name regex skip count
+  $T > /dev/null 2>&1 && $NCU --set full --import-source on -k "regex:$2" -s $3 -c $4 -o $OUT/prof_$1 $T > $OUT/ncu_$1.log 2>&1
+  if [ -f $OUT/prof_$1.ncu-rep ]; then
+    ncu -i $OUT/prof_$1.ncu-rep --page raw --csv > $OUT/prof_$1_raw.csv 2>/dev/null
+    ncu -i $OUT/prof_$1.ncu-rep --page details --csv > $OUT/prof_$1_details.csv 2>/dev/null
+    ncu -i $OUT/prof_$1.ncu-rep --page source --csv > $OUT/prof_$1_source.csv 2>/dev/null
+    sz=$(stat -c %s $OUT/prof_$1.ncu-rep); if [ $sz -gt 12000000 ]; then rm -f $OUT/prof_$1.ncu-rep; fi
+  fi
+}
+cap kv "kv_reduce_mma_kernel<4" 8 2          # bridge 1: N=57408 tokens, C=128
+cap q "q_readout_mma_kernel<4" 8 2
+cap kv8 "kv_reduce_mma_kernel<8" 40 1        # bridge 2: N=10752, C=256
+cap tc "conv3d_tc_kernel" 30 6               # six tensor-core conv launches of the second forward
+cap halo "conv3d_halo_kernel" 9 3
+ls -la $OUT | tail -30
