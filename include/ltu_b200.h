@@ -101,6 +101,17 @@ int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int H
                   const float* bias, int Cout, void* out, int out_f32, int Ho, int Wo, int Do,
                   float* partials, ltu_stream_t stream);
 
+/* nn.Linear on a bf16 token matrix with a fused epilogue (model/trans_block.py:166,:187-189,:205-210),
+ * run by the persistent tcgen05 kernel (a 1x1x1 "convolution"):  y = epi(x W^T + b)
+ *   x bf16 [rows][Cin], Cin a power of two in [8,1024]; weight_bf16 = the ltu_conv3d_tc packing of the
+ *   [Cout][Cin] matrix ([Cout16][ltu_conv3d_tc_kpad(Cin,1)]); Cout <= 256, % 8 == 0;
+ *   y bf16 [rows][ld_y], columns [0,Cout) of every row written (wide layers = column slices);
+ *   epi 0: bias | 1: bias + exact-erf GELU | 2: LayerNorm(x W^T + b + residual) * gamma + beta
+ *   (residual bf16 [rows][Cout], Cout % 32 == 0: one thread owns one complete output row).        */
+int ltu_linear_tc(const void* x, int Cin, int64_t rows, const void* weight_bf16, const float* bias,
+                  int Cout, void* y, int ld_y, int epi, const void* residual, const float* gamma,
+                  const float* beta, float eps, ltu_stream_t stream);
+
 /* Small-channel stride-1 3x3x3 convolution for bf16 activations (stem, enc.block0/1 conv1,
  * dec.block3, finest mask head, final_block): the input halo of a 3-D output tile and all weights are
  * staged once in shared memory and im2col happens in the ldmatrix row addresses of mma.sync

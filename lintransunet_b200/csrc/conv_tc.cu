@@ -18,11 +18,19 @@
 // model/Unet_3Dblock.py:553).  nn.Upsample(nearest x2) + 3x3x3 conv of up_embed (:421-422) is FOLDED:
 // output voxels of parity class (pa,pb,pc) see only 2x2x2 distinct source voxels, so each class is a
 // 2x2x2 convolution of the low-resolution input with pre-summed weights (8/27 of the flops and loads).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace ltu {
 
 void count_launch(int n = 1);
+int conv3d_tc2_launch(const TcParams& c, int B, int epi, const void* residual, const float* gamma, const float* beta,
+                      float eps, int ld_out, cudaStream_t st);       // conv_tc2.cu: persistent variant
+static bool use_persistent_tc() {
+    static const bool v = [] { const char* e = getenv("LTU_TC_V1"); return !(e && e[0] == '1'); }();
+    return v;
+}
 
 __global__ void __launch_bounds__(kTcThreads)
 conv3d_tc_kernel(const TcParams p) {
@@ -336,6 +344,7 @@ extern "C" int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, i
     p.w_class_stride = (int64_t)p.Cout * p.Kpad;
     p.Ho = Ho; p.Wo = Wo; p.Do = Do;
     p.partials = partials; p.tiles = ltu_conv3d_tc_tiles((int64_t)Ho * Wo * Do, up2);
+    if (use_persistent_tc()) { p.stages = 0; p.tmem_cols = 0; return conv3d_tc2_launch(p, B, 0, nullptr, nullptr, nullptr, 0.f, 0, (cudaStream_t)stream); }
     int cols = 32; while (cols < p.Cout) cols <<= 1;
     p.tmem_cols = cols;
     const int stage_bytes = kTcM * 128 + p.Cout * 128;

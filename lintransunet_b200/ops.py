@@ -401,3 +401,39 @@ def gather_windows(volume: torch.Tensor, starts: torch.Tensor, roi) -> torch.Ten
         check(_native.lib().ltu_gather_windows(_p(volume), _p(starts), _p(out), n, rh, rw, rd, H, W, D, st),
               "ltu_gather_windows")
     return out
+
+
+EPI_BIAS, EPI_GELU, EPI_RES_LN = 0, 1, 2
+
+
+def pack_linear_tc(weight: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin] -> bf16 [Cout16, Kpad64] K-major operand of ltu_linear_tc."""
+    cout, cin = weight.shape
+    out = torch.zeros((cout + 15) // 16 * 16, (cin + 63) // 64 * 64, dtype=torch.bfloat16, device=weight.device)
+    out[:cout, :cin] = weight.detach().to(torch.bfloat16)
+    return out
+
+
+def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout: int, epi: int = EPI_BIAS,
+              residual: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
+              beta: Optional[torch.Tensor] = None, eps: float = 1e-6) -> torch.Tensor:
+    """y = epi(x @ W^T + b) on bf16 tokens [..., Cin] with the persistent tcgen05 kernel.  Layers wider
+    than 256 outputs are computed as column slices of one output buffer."""
+    dev = _chk(x, w_packed, bias, residual, gamma, beta)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("linear_tc needs bf16 activations")
+    cin = x.shape[-1]
+    rows = x.numel() // cin
+    y = torch.empty(*x.shape[:-1], cout, dtype=torch.bfloat16, device=dev)
+    kpad = w_packed.shape[1]
+    L = _native.lib()
+    with _Guard(dev, ("linear_tc", (x.numel() + y.numel() + (0 if residual is None else residual.numel())) * 2,
+                      2 * rows * cin * cout)) as st:
+        for n0 in range(0, cout, 256):
+            n = min(256, cout - n0)
+            if epi == EPI_RES_LN and cout > 256:
+                raise ValueError("the LayerNorm epilogue needs the whole row in one tile (Cout <= 256)")
+            check(L.ltu_linear_tc(_p(x), cin, rows, c_void_p(w_packed.data_ptr() + n0 * kpad * 2),
+                                  c_void_p(bias.data_ptr() + n0 * 4), n, c_void_p(y.data_ptr() + n0 * 2), cout, epi,
+                                  _p(residual), _p(gamma), _p(beta), eps, st), "ltu_linear_tc")
+    return y

@@ -249,6 +249,11 @@ class _LayerW:
         self.w_1, self.b_1 = c(layer.linear1.weight), c(layer.linear1.bias)
         self.w_2, self.b_2 = c(layer.linear2.weight), c(layer.linear2.bias)
         f = lambda t: t.detach().float().contiguous()
+        self.fused = dtype == torch.bfloat16
+        if self.fused:                                 # operands of the fused tcgen05 Linear layers
+            self.wt_o, self.bf_o = ops.pack_linear_tc(lin[3].weight), f(lin[3].bias)
+            self.wt_1, self.bf_1 = ops.pack_linear_tc(layer.linear1.weight), f(layer.linear1.bias)
+            self.wt_2, self.bf_2 = ops.pack_linear_tc(layer.linear2.weight), f(layer.linear2.bias)
         self.g1, self.be1 = f(layer.layer_norm1.weight), f(layer.layer_norm1.bias)
         self.g2, self.be2 = f(layer.layer_norm2.weight), f(layer.layer_norm2.bias)
         self.nhead = layer.self_attn.nhead
@@ -331,6 +336,8 @@ class MaskTransUnet(nn.Module):
         # the forward has no host sync (the ROI boxes stay on the device), so an inference forward of
         # a fixed input shape is captured once into a CUDA graph and replayed (~600 launches -> 1)
         self.use_cuda_graphs = os.environ.get("LTU_CUDA_GRAPHS", "1") != "0"
+        # bf16 path: nn.Linear + bias + GELU / residual + LayerNorm in one tcgen05 launch each (else cuBLAS + 3 kernels)
+        self.use_fused_linear = os.environ.get("LTU_FUSED_LINEAR", "1") != "0"
         self._plans: Dict[tuple, tuple] = {}
         self._graphs: Dict[tuple, dict] = {}
 
@@ -364,7 +371,7 @@ class MaskTransUnet(nn.Module):
                          and not torch.cuda.is_current_stream_capturing())
             if not graphable:
                 return self._forward_impl(x, plan, head)
-            key = (x.device.index, dtype, head, tuple(x.shape), self.use_tensor_cores)
+            key = (x.device.index, dtype, head, tuple(x.shape), self.use_tensor_cores, self.use_fused_linear)
             ent = self._graphs.get(key)
             if ent is None or ent["plan"] is not plan:
                 ent = self._capture(x, plan, head)
@@ -414,6 +421,11 @@ class MaskTransUnet(nn.Module):
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         ctx = ops.kv_reduce(k, v, lw.nhead)
         att = ops.q_readout(q, ctx, lw.nhead)
+        if lw.fused and self.use_fused_linear:
+            # O-projection + residual + LayerNorm1, FFN1 + GELU, FFN2 + residual + LayerNorm2: three launches
+            t = ops.linear_tc(att, lw.wt_o, lw.bf_o, C, ops.EPI_RES_LN, residual=t, gamma=lw.g1, beta=lw.be1)
+            f = ops.linear_tc(t, lw.wt_1, lw.bf_1, 2 * C, ops.EPI_GELU)
+            return ops.linear_tc(f, lw.wt_2, lw.bf_2, C, ops.EPI_RES_LN, residual=t, gamma=lw.g2, beta=lw.be2)
         o = F.linear(att, lw.w_o, lw.b_o)
         t = ops.add_layernorm(t, o, lw.g1, lw.be1, 1e-6)
         f = ops.gelu_(F.linear(t, lw.w_1, lw.b_1))

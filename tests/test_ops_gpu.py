@@ -432,7 +432,36 @@ def test_encoder_layer_golden(dtype):
     layer = SelfAttentionLayer(128, 4)
     layer.load_state_dict({k[len(pre) + 1:]: v for k, v in sd.items() if k.startswith(pre + ".")})
     layer.cuda()
-    m = MaskTransUnet.__new__(MaskTransUnet)          # only _encoder_layer is exercised
     x = torch.from_numpy(g["layer_x"])
-    y = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
-    assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2)
+    for fused in (True, False):
+        m = MaskTransUnet.__new__(MaskTransUnet)      # only _encoder_layer is exercised
+        torch.nn.Module.__init__(m)
+        m.use_fused_linear = fused
+        y = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
+        assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2), fused
+
+
+@pytest.mark.parametrize("epi", [0, 1, 2])
+@pytest.mark.parametrize("rows,cin,cout", [(1000, 128, 128), (777, 256, 512), (300, 512, 256), (129, 128, 256),
+                                           (40000, 256, 256), (1, 256, 768), (5000, 64, 32)])
+def test_linear_tc_fused_epilogues(epi, rows, cin, cout):
+    """Persistent tcgen05 Linear layer: bias | bias+GELU(erf) | residual+LayerNorm epilogues vs fp32 torch."""
+    ops = _ops()
+    if epi == 2 and (cout > 256 or cout % 32):
+        pytest.skip("the LayerNorm epilogue needs the whole row in one tile")
+    lin = torch.nn.Linear(cin, cout)
+    with torch.no_grad():
+        lin.weight.copy_(q_(lin.weight, torch.bfloat16))
+    x = q_(rnd((rows, cin), 80), torch.bfloat16)
+    res = q_(rnd((rows, cout), 81), torch.bfloat16)
+    g, b = 1 + 0.1 * rnd((cout,), 82), 0.1 * rnd((cout,), 83)
+    ref = F.linear(x, lin.weight.detach(), lin.bias.detach())
+    if epi == 1:
+        ref = F.gelu(ref)
+    elif epi == 2:
+        ref = F.layer_norm(ref + res, (cout,), g, b, eps=1e-6)
+    y = ops.linear_tc(x.to("cuda", torch.bfloat16), ops.pack_linear_tc(lin.weight).cuda(), lin.bias.detach().float().cuda(),
+                      cout, epi, residual=res.to("cuda", torch.bfloat16) if epi == 2 else None,
+                      gamma=g.cuda() if epi == 2 else None, beta=b.cuda() if epi == 2 else None)
+    assert y.shape == (rows, cout)
+    assert rel_err(y.float(), ref) < TOL[torch.bfloat16]

@@ -38,6 +38,31 @@ def main():
         wall = (time.perf_counter() - t0) / 7 * 1e3
         print(f"forward {prec} B={B} {S}^3: {ms:.2f} ms/iter (wall {wall:.2f}) -> {B*S**3/ms*1e3:.3e} voxels/s; "
               f"{n1-n0} native launches/forward", flush=True)
+    for fused in (True, False):
+        m.precision, m.use_fused_linear = "bf16", fused
+        x = torch.randn(8, 1, 128, 128, 128, device="cuda")
+        ms = timeit(lambda: m.predict_labels(x), warm=2, it=5)
+        print(f"forward bf16 B=8 128^3 fused_linear={fused}: {ms:.2f} ms/iter", flush=True)
+    m.use_fused_linear = True
+    import torch.nn.functional as F
+    for (M, C) in ((8 * 57408, 128), (8 * 10752, 256)):
+        t = torch.randn(M, C, device="cuda").to(torch.bfloat16)
+        lin1, lin2 = torch.nn.Linear(C, 2 * C).cuda(), torch.nn.Linear(2 * C, C).cuda()
+        w1, b1 = lin1.weight.detach().to(torch.bfloat16), lin1.bias.detach().to(torch.bfloat16)
+        w2, b2 = lin2.weight.detach().to(torch.bfloat16), lin2.bias.detach().to(torch.bfloat16)
+        p1, p2 = ops.pack_linear_tc(lin1.weight), ops.pack_linear_tc(lin2.weight)
+        f1, f2 = lin1.bias.detach().float(), lin2.bias.detach().float()
+        g, be = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+
+        def unfused():
+            f = ops.gelu_(F.linear(t, w1, b1))
+            return ops.add_layernorm(t, F.linear(f, w2, b2), g, be)
+
+        def fused():
+            f = ops.linear_tc(t, p1, f1, 2 * C, ops.EPI_GELU)
+            return ops.linear_tc(f, p2, f2, C, ops.EPI_RES_LN, residual=t, gamma=g, beta=be)
+
+        print(f"FFN M={M} C={C}: cuBLAS+gelu+LN {timeit(unfused)*1e3:.1f} us, fused tcgen05 {timeit(fused)*1e3:.1f} us", flush=True)
     # attention core at the model's token counts
     for dt in (torch.bfloat16, torch.float32):
         for (B, N, h) in ((8, 57408, 4), (8, 10752, 8), (8, 4320, 8), (8, 512, 8), (1, 57408, 4), (1, 32768, 8)):

@@ -19,9 +19,12 @@ cap() {  # name regex skip count
     sz=$(stat -c %s $OUT/prof_$1.ncu-rep); if [ $sz -gt 12000000 ]; then rm -f $OUT/prof_$1.ncu-rep; fi
   fi
 }
-cap kv "kv_reduce_mma_kernel<4" 8 2          # bridge 1: N=57408 tokens, C=128
-cap q "q_readout_mma_kernel<4" 8 2
-cap kv8 "kv_reduce_mma_kernel<8" 40 1        # bridge 2: N=10752, C=256
-cap tc "conv3d_tc_kernel" 30 6               # six tensor-core conv launches of the second forward
+# per forward the attention kernels run 32 times: bottleneck (8), bridge 3 (8), bridge 2 (8), bridge 1 (8)
+cap kv "kv_reduce_mma_kernel" 56 2           # second forward, bridge 1: N=57408 tokens, C=128
+cap q "q_readout_mma_kernel" 56 2
+cap kv8 "kv_reduce_mma_kernel" 48 1          # bridge 2: N=10752, C=256
+if [ "${NCU_SKIP_CONV:-0}" != "1" ]; then
+cap tc "conv3d_tc2_kernel|conv3d_tc_kernel" 30 6   # six tensor-core conv launches of the second forward
 cap halo "conv3d_halo_kernel" 9 3
+fi
 ls -la $OUT | tail -30
