@@ -344,7 +344,10 @@ extern "C" int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, i
     p.w_class_stride = (int64_t)p.Cout * p.Kpad;
     p.Ho = Ho; p.Wo = Wo; p.Do = Do;
     p.partials = partials; p.tiles = ltu_conv3d_tc_tiles((int64_t)Ho * Wo * Do, up2);
-    if (use_persistent_tc()) { p.stages = 0; p.tmem_cols = 0; return conv3d_tc2_launch(p, B, 0, nullptr, nullptr, nullptr, 0.f, 0, (cudaStream_t)stream); }
+    // The persistent kernel wins where a tile has very little K (1x1x1 convs: one k-block per tile, the
+    // per-CTA set-up dominated); deep-K layers are gather-bound and prefer two resident CTAs of this
+    // kernel (2 x 128 producer threads per SM).  Measured on B200: profiles/r1_conv_variants.md
+    if (use_persistent_tc() && ksize == 1) { p.stages = 0; p.tmem_cols = 0; return conv3d_tc2_launch(p, B, 0, nullptr, nullptr, nullptr, 0.f, 0, (cudaStream_t)stream); }
     int cols = 32; while (cols < p.Cout) cols <<= 1;
     p.tmem_cols = cols;
     const int stage_bytes = kTcM * 128 + p.Cout * 128;

@@ -336,8 +336,11 @@ class MaskTransUnet(nn.Module):
         # the forward has no host sync (the ROI boxes stay on the device), so an inference forward of
         # a fixed input shape is captured once into a CUDA graph and replayed (~600 launches -> 1)
         self.use_cuda_graphs = os.environ.get("LTU_CUDA_GRAPHS", "1") != "0"
-        # bf16 path: nn.Linear + bias + GELU / residual + LayerNorm in one tcgen05 launch each (else cuBLAS + 3 kernels)
-        self.use_fused_linear = os.environ.get("LTU_FUSED_LINEAR", "1") != "0"
+        # bf16 path, EXPERIMENTAL (off): nn.Linear + bias + GELU / residual + LayerNorm in one tcgen05 launch each.
+        # Correct (tests/test_ops_gpu.py::test_linear_tc_fused_epilogues) but 4.4x slower than cuBLAS + the separate
+        # bandwidth-bound kernels at the model's shapes (profiles/r1_conv_variants.md) until the GEMM keeps its
+        # weights resident and widens the epilogue.
+        self.use_fused_linear = os.environ.get("LTU_FUSED_LINEAR", "0") == "1"
         self._plans: Dict[tuple, tuple] = {}
         self._graphs: Dict[tuple, dict] = {}
 
