@@ -51,52 +51,6 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     }
 }
 
-// ---- bulk-copy (TMA, 1-D) staging: one lane per token row, completion on an mbarrier --------------
-__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-// Called by ONE warp: lane r fetches token row row0+r (C bf16 = C*2 contiguous bytes) of up to `nsrc` row-strided
-// matrices into padded smem rows; rows past the end of the sequence are zero-filled with plain stores.
-template <int C, int LDS>
-__device__ __forceinline__ void bulk_stage(int lane, uint32_t bar, bf16* s0, const bf16* g0, bf16* s1, const bf16* g1,
-                                           int64_t ld, int64_t row0, int64_t nrows) {
-    const int64_t left = nrows - row0;
-    const int valid = left < kTT ? (int)left : kTT;
-    const uint32_t per_row = (uint32_t)C * 2u;
-    if (lane == 0) bar_expect_tx(bar, (uint32_t)valid * per_row * (s1 != nullptr ? 2u : 1u));
-    __syncwarp();
-    if (lane < valid) {
-        bulk_g2s(smem_u32_generic(s0 + lane * LDS), g0 + (row0 + lane) * ld, per_row, bar);
-        if (s1 != nullptr) bulk_g2s(smem_u32_generic(s1 + lane * LDS), g1 + (row0 + lane) * ld, per_row, bar);
-    } else {
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int c = 0; c < C / 8; ++c) {
-            *reinterpret_cast<uint4*>(s0 + lane * LDS + c * 8) = z;
-            if (s1 != nullptr) *reinterpret_cast<uint4*>(s1 + lane * LDS + c * 8) = z;
-        }
-    }
-}
-
 // stage kTT rows x C bf16 into padded smem rows (row stride LDS elements); rows >= nrows are zero
 template <int C, int LDS>
 __device__ __forceinline__ void stage_rows(bf16* smem, const bf16* src, int64_t ld, int64_t row0, int64_t nrows) {
@@ -121,7 +75,6 @@ kv_reduce_mma_kernel(const bf16* __restrict__ K, const bf16* __restrict__ V, int
     float* sRed = reinterpret_cast<float*>(sV + NSTAGE * kTT * LDS);   // [RPP][C]
     float* sRef = sRed + RPP * C;                                 // [C] reference r_j * log2e
     float* sScale = sRef + C;                                     // [C] rescale factors (slow path)
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sScale + C);     // [NSTAGE] "tile landed" mbarriers
 
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -156,31 +109,26 @@ kv_reduce_mma_kernel(const bf16* __restrict__ K, const bf16* __restrict__ V, int
     for (int c = 0; c < 8; ++c) rj[c] = 0.f;
     const uint32_t ones = (lane >> 2) == 0 ? 0x3F803F80u : 0u;     // B tile with column 0 = 1.0 (bf16 pairs)
 
-    // NSTAGE-deep ring filled by 1-D bulk copies (one lane of warp 0 per token row, mbarrier completion):
-    // NSTAGE-1 tiles are in flight while one is processed
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) bar_init(smem_u32_generic(sBar + s), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp == 0) {
+    // NSTAGE-deep cp.async ring: NSTAGE-1 tiles are in flight while one is processed
 #pragma unroll
-        for (int s = 0; s < NSTAGE - 1; ++s)
-            if (s < ntiles)
-                bulk_stage<C, LDS>(lane, smem_u32_generic(sBar + s), sK + s * kTT * LDS, Kb, sV + s * kTT * LDS, Vb, ld,
-                                   (tile0 + s) * kTT, N);
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+        if (s < ntiles) {
+            stage_rows<C, LDS>(sK + s * kTT * LDS, Kb, ld, (tile0 + s) * kTT, N);
+            stage_rows<C, LDS>(sV + s * kTT * LDS, Vb, ld, (tile0 + s) * kTT, N);
+        }
+        cp_async_commit();
     }
-    __syncthreads();
 
     for (int64_t t = 0; t < ntiles; ++t) {
         const int buf = (int)(t % NSTAGE);
-        if (warp == 0 && t + NSTAGE - 1 < ntiles) {
+        if (t + NSTAGE - 1 < ntiles) {
             const int nb = (int)((t + NSTAGE - 1) % NSTAGE);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses of that buffer are done
-            bulk_stage<C, LDS>(lane, smem_u32_generic(sBar + nb), sK + nb * kTT * LDS, Kb, sV + nb * kTT * LDS, Vb, ld,
-                               (tile0 + t + NSTAGE - 1) * kTT, N);
+            stage_rows<C, LDS>(sK + nb * kTT * LDS, Kb, ld, (tile0 + t + NSTAGE - 1) * kTT, N);
+            stage_rows<C, LDS>(sV + nb * kTT * LDS, Vb, ld, (tile0 + t + NSTAGE - 1) * kTT, N);
         }
-        bar_wait(smem_u32_generic(sBar + buf), (uint32_t)((t / NSTAGE) & 1));   // tile t landed
+        cp_async_commit();
+        cp_async_wait<NSTAGE - 1>();
+        __syncthreads();                                          // tile t landed
         bf16* tK = sK + buf * kTT * LDS;
         const bf16* tV = sV + buf * kTT * LDS;
         const int64_t row0 = (tile0 + t) * kTT;
@@ -306,6 +254,7 @@ kv_reduce_mma_kernel(const bf16* __restrict__ K, const bf16* __restrict__ V, int
         }
         __syncthreads();                                          // buffers of tile t are free again
     }
+    cp_async_wait<0>();
 
     // ---- partial state: ctx[j][e], m[j] (natural-log units), s[j]
     const int g = lane >> 2, tq = lane & 3;
@@ -334,7 +283,6 @@ q_readout_mma_kernel(const bf16* __restrict__ Q, int64_t ldq, const float* __res
     constexpr int C = HEADS * 32, CPR = C / 8, LDS = C + 8, WPH = 8 / HEADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     bf16* sQ = reinterpret_cast<bf16*>(smem_raw);                 // [NSTAGE][kTT][LDS]
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sQ + NSTAGE * kTT * LDS);   // [NSTAGE]
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -363,30 +311,18 @@ q_readout_mma_kernel(const bf16* __restrict__ Q, int64_t ldq, const float* __res
     if (ntiles > tiles_per_cta) ntiles = tiles_per_cta;
     if (ntiles < 0) ntiles = 0;
 
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) bar_init(smem_u32_generic(sBar + s), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE - 1; ++s)
-            if (s < ntiles)
-                bulk_stage<C, LDS>(lane, smem_u32_generic(sBar + s), sQ + s * kTT * LDS, Qb, nullptr, nullptr, ldq,
-                                   (tile0 + s) * kTT, N);
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+        if (s < ntiles) stage_rows<C, LDS>(sQ + s * kTT * LDS, Qb, ldq, (tile0 + s) * kTT, N);
+        cp_async_commit();
     }
-    __syncthreads();
     for (int64_t t = 0; t < ntiles; ++t) {
         const int buf = (int)(t % NSTAGE);
-        if (warp == 0 && t + NSTAGE - 1 < ntiles) {
-            const int nb = (int)((t + NSTAGE - 1) % NSTAGE);
-            // the bulk store issued from that buffer one iteration ago must have finished reading it
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bulk_stage<C, LDS>(lane, smem_u32_generic(sBar + nb), sQ + nb * kTT * LDS, Qb, nullptr, nullptr, ldq,
-                               (tile0 + t + NSTAGE - 1) * kTT, N);
-        }
-        bar_wait(smem_u32_generic(sBar + buf), (uint32_t)((t / NSTAGE) & 1));
+        if (t + NSTAGE - 1 < ntiles)
+            stage_rows<C, LDS>(sQ + (int)((t + NSTAGE - 1) % NSTAGE) * kTT * LDS, Qb, ldq, (tile0 + t + NSTAGE - 1) * kTT, N);
+        cp_async_commit();
+        cp_async_wait<NSTAGE - 1>();
+        __syncthreads();
         bf16* tQ = sQ + buf * kTT * LDS;
         const int64_t row0 = (tile0 + t) * kTT;
         const int valid = (int)((N - row0) < kTT ? (N - row0) : kTT);
@@ -442,14 +378,15 @@ q_readout_mma_kernel(const bf16* __restrict__ Q, int64_t ldq, const float* __res
                 *reinterpret_cast<uint32_t*>(p0 + 8 * LDS) = pack_bf16x2(d[nt][2] * i1, d[nt][3] * i1);
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my smem writes -> visible to the bulk store
         __syncthreads();                                          // output tile complete in smem
-        if (warp == 0) {                                          // one 1-D bulk store per token row
-            if (lane < valid) bulk_s2g(Ob + (row0 + lane) * ldo, smem_u32_generic(tQ + lane * LDS), (uint32_t)C * 2u);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        for (int i = tid; i < kTT * CPR; i += 256) {
+            const int r = i / CPR, c = i - r * CPR;
+            if (r < valid)
+                *reinterpret_cast<uint4*>(Ob + (row0 + r) * ldo + c * 8) = *reinterpret_cast<const uint4*>(tQ + r * LDS + c * 8);
         }
+        __syncthreads();                                          // before the buffer is refilled
     }
-    if (warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA exits
+    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -461,7 +398,7 @@ static int kv_mma_launch(const bf16* k, const bf16* v, int64_t ld, float* ws, in
                          int tiles_per_chunk, cudaStream_t st) {
     constexpr int C = HEADS * 32, LDS = C + 8, RPP = 256 / (C / 8);
     constexpr int NSTAGE = HEADS == 8 ? 3 : 4;                    // ~100 KB / ~70 KB / ~37 KB of tiles per CTA
-    const size_t smem = (size_t)2 * NSTAGE * kTT * LDS * 2 + (size_t)(RPP * C + 2 * C) * 4 + NSTAGE * 8;
+    const size_t smem = (size_t)2 * NSTAGE * kTT * LDS * 2 + (size_t)(RPP * C + 2 * C) * 4;
     static thread_local int conf = -1;
     int dev; cudaGetDevice(&dev);
     if (conf != dev) { cudaFuncSetAttribute(kv_reduce_mma_kernel<HEADS, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); conf = dev; }
@@ -481,7 +418,7 @@ static int q_mma_launch(const bf16* q, int64_t ldq, const float* ctx, bf16* out,
     if (ctas < 1) ctas = 1;
     const int tiles_per_cta = (int)ceil_div64(tiles, ctas);
     ctas = ceil_div64(tiles, tiles_per_cta);
-    const size_t smem = (size_t)NSTAGE * kTT * LDS * 2 + NSTAGE * 8;
+    const size_t smem = (size_t)NSTAGE * kTT * LDS * 2;
     static thread_local int conf = -1;
     int dev; cudaGetDevice(&dev);
     if (conf != dev) { cudaFuncSetAttribute(q_readout_mma_kernel<HEADS, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); conf = dev; }
