@@ -23,11 +23,11 @@ constexpr int kPartialFloats = 32 * 32 + 64;   // ctx[32][32], m[32], s[32]
 
 // How a sample's N tokens are split into chunks (one CTA each, one partial state per chunk).  The split
 // depends on N ONLY -- never on the batch size -- so that a sample's result is bit-identical whatever
-// batch it is processed in (the N-GPU sliding window must equal the 1-GPU one exactly): about 64 chunks
-// per sample, at least 4 tiles (128 tokens) each.
+// batch it is processed in (the N-GPU sliding window must equal the 1-GPU one exactly): up to 74 chunks
+// per sample (74 * B CTAs = whole waves of 2 CTAs x 148 SMs for B = 4, 8), at least 4 tiles (128 tokens) each.
 static inline int kv_chunks_per_batch(int /*B*/, int64_t N) {
     const int64_t tiles = ceil_div64(N, kTileTokens);
-    int64_t tiles_per_chunk = ceil_div64(tiles, 64);
+    int64_t tiles_per_chunk = ceil_div64(tiles, 74);
     if (tiles_per_chunk < 4) tiles_per_chunk = 4;
     return (int)ceil_div64(tiles, tiles_per_chunk);
 }
