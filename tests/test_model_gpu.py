@@ -164,3 +164,19 @@ def test_cuda_graph_replay_is_bit_identical_to_eager():
         assert torch.equal(e1, g1) and torch.equal(e2, g2) and torch.equal(g1, g1b), prec
         assert torch.equal(m.predict_labels(x2), l2)
         assert not torch.equal(e1, e2)
+
+
+def test_result_does_not_depend_on_batch_composition():
+    """Every reduction is split by per-sample rules only (never by the batch size), so a patch gives the
+    same bits alone, in a batch of 3 or in a batch of 5 -- the property that makes the N-GPU sliding window
+    bit-identical to the 1-GPU one (tools/mgpu_check.py checks it across ranks)."""
+    g = load_golden("model_c3_64x96x32_b2.npz")
+    m, cfg, sd, x = build(g, "bf16")
+    m.eval()
+    xs = torch.cat([O.make_input((1, 1, 64, 96, 32), seed=90 + i, blob=bool(i % 2)) for i in range(5)]).cuda()
+    for prec in ("bf16", "fp32"):
+        m.precision = prec
+        full = m.forward_logits(xs)
+        for lo, hi in ((0, 1), (1, 4), (4, 5), (2, 3)):
+            part = m.forward_logits(xs[lo:hi].contiguous())
+            assert torch.equal(part, full[lo:hi]), (prec, lo, hi)
