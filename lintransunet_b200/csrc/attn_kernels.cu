@@ -361,6 +361,71 @@ posenc_kernel(const T* __restrict__ x, const float* __restrict__ w, const float*
     }
 }
 
+// v2: one thread = one (b,h,w) column segment of LD outputs along D x 2 channels.  The 27x2 weights live in
+// registers; every input value is loaded once per (kh,kw) neighbour and scattered to the three outputs it
+// feeds (kd = 0,1,2), so an output costs ~10 loads instead of 27 + 27 weight loads.
+__device__ __forceinline__ void load2(const float* p, float& a, float& b) { float2 v = *reinterpret_cast<const float2*>(p); a = v.x; b = v.y; }
+__device__ __forceinline__ void load2(const bf16* p, float& a, float& b) {
+    uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+    a = __uint_as_float(v << 16); b = __uint_as_float(v & 0xffff0000u);
+}
+__device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store2(bf16* p, float a, float b) { *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(a, b); }
+
+template <typename T, int LD>
+__global__ void __launch_bounds__(256)
+posenc2_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+               T* __restrict__ y, int B, int H, int W, int D, int C) {
+    const int cp = C / 2, nd = (D + LD - 1) / LD;
+    const int64_t total = (int64_t)B * H * W * nd * cp;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % cp) * 2;
+    int64_t t = idx / cp;
+    const int dc = (int)(t % nd); t /= nd;
+    const int ww = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    float wr[27][2];
+#pragma unroll
+    for (int tp = 0; tp < 27; ++tp) load2(w + tp * C + c0, wr[tp][0], wr[tp][1]);
+    float b0, b1;
+    load2(bias + c0, b0, b1);
+    const int d0 = dc * LD;
+    const int dend = (d0 + LD < D) ? d0 + LD : D;                 // outputs d0 .. dend-1
+    const T* xb = x + (int64_t)b * H * W * D * C + c0;
+    T* yb = y + (int64_t)b * H * W * D * C + c0;
+    float aP0 = 0.f, aP1 = 0.f, aC0 = 0.f, aC1 = 0.f, aN0 = 0.f, aN1 = 0.f;
+    for (int dd = d0 - 1; dd <= dend; ++dd) {
+        if (dd >= 0 && dd < D) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int hh = h + kh - 1;
+                if (hh < 0 || hh >= H) continue;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int w2 = ww + kw - 1;
+                    if (w2 < 0 || w2 >= W) continue;
+                    float v0, v1;
+                    load2(xb + (((int64_t)hh * W + w2) * D + dd) * C, v0, v1);
+                    const int t0 = kh * 9 + kw * 3;
+                    aN0 = fmaf(wr[t0][0], v0, aN0);     aN1 = fmaf(wr[t0][1], v1, aN1);        // kd = 0 -> out dd+1
+                    aC0 = fmaf(wr[t0 + 1][0], v0, aC0); aC1 = fmaf(wr[t0 + 1][1], v1, aC1);    // kd = 1 -> out dd
+                    aP0 = fmaf(wr[t0 + 2][0], v0, aP0); aP1 = fmaf(wr[t0 + 2][1], v1, aP1);    // kd = 2 -> out dd-1
+                }
+            }
+        }
+        const int o = dd - 1;                                      // complete: planes o-1, o, o+1 were scattered
+        if (o >= d0 && o < dend) {
+            const int64_t off = (((int64_t)h * W + ww) * D + o) * C;
+            float x0, x1;
+            load2(xb + off, x0, x1);
+            store2(yb + off, aP0 + b0 + x0, aP1 + b1 + x1);
+        }
+        aP0 = aC0; aP1 = aC1; aC0 = aN0; aC1 = aN1; aN0 = 0.f; aN1 = 0.f;
+    }
+}
+
 void count_launch(int n = 1);
 
 // bf16 tensor-pipe variants (attn_tc.cu)
@@ -521,12 +586,21 @@ extern "C" int ltu_posenc_dwconv3(const void* x, const float* w, const float* bi
     LTU_ARG_CHECK(B > 0 && H > 0 && W > 0 && D > 0 && C > 0 && C % 4 == 0, "posenc_dwconv3: bad shape");
     LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "posenc_dwconv3: bad dtype %d", dtype);
     LTU_ARG_CHECK(x != y, "posenc_dwconv3: in-place is not supported");
-    int64_t total = (int64_t)B * H * W * D * (C / 4);
-    int64_t blocks = ceil_div64(total, 256);
-    int64_t cap = (int64_t)sm_count() * 32;
-    if (blocks > cap) blocks = cap;
-    if (dtype == LTU_F32) posenc_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, w, bias, (float*)y, B, H, W, D, C);
-    else posenc_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, (bf16*)y, B, H, W, D, C);
+    if (D >= 8) {       // long enough D runs: the register-sliding kernel
+        constexpr int LD = 16;
+        int64_t total = (int64_t)B * H * W * ((D + LD - 1) / LD) * (C / 2);
+        int64_t blocks = ceil_div64(total, 256);
+        LTU_ARG_CHECK(blocks < ((int64_t)1 << 31), "posenc_dwconv3: tensor too large");
+        if (dtype == LTU_F32) posenc2_kernel<float, LD><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, w, bias, (float*)y, B, H, W, D, C);
+        else posenc2_kernel<bf16, LD><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, (bf16*)y, B, H, W, D, C);
+    } else {
+        int64_t total = (int64_t)B * H * W * D * (C / 4);
+        int64_t blocks = ceil_div64(total, 256);
+        int64_t cap = (int64_t)sm_count() * 32;
+        if (blocks > cap) blocks = cap;
+        if (dtype == LTU_F32) posenc_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, w, bias, (float*)y, B, H, W, D, C);
+        else posenc_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, (bf16*)y, B, H, W, D, C);
+    }
     LTU_LAUNCH_CHECK("posenc_dwconv3");
     count_launch(1);
     return LTU_OK;

@@ -109,23 +109,33 @@ kv_reduce_mma_kernel(const bf16* __restrict__ K, const bf16* __restrict__ V, int
     for (int c = 0; c < 8; ++c) rj[c] = 0.f;
     const uint32_t ones = (lane >> 2) == 0 ? 0x3F803F80u : 0u;     // B tile with column 0 = 1.0 (bf16 pairs)
 
-    // NSTAGE-deep cp.async ring: NSTAGE-1 tiles are in flight while one is processed
+    // NSTAGE-deep cp.async ring: NSTAGE-1 tiles are in flight while one is processed.  A thread stages
+    // exactly the chunks it later transforms: rows r0 + i*RPP, 16-byte column cc (offsets are loop invariant).
+    const int64_t goff0 = (int64_t)r0 * ld + cc * 8;
+    const int64_t gstep = (int64_t)RPP * ld;
+    const int soff0 = r0 * LDS + cc * 8;
+    auto stage = [&](int nb, int64_t trow0) {
+        const bf16* gk = Kb + trow0 * ld + goff0;
+        const bf16* gv = Vb + trow0 * ld + goff0;
+        bf16* dk = sK + nb * kTT * LDS + soff0;
+        bf16* dv = sV + nb * kTT * LDS + soff0;
+        const int64_t left = N - trow0 - r0;                   // rows r0 + i*RPP with i*RPP < left exist
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const bool ok = (int64_t)i * RPP < left;
+            cp_async16_zfill(dk + i * RPP * LDS, ok ? gk + i * gstep : Kb, ok ? 16 : 0);
+            cp_async16_zfill(dv + i * RPP * LDS, ok ? gv + i * gstep : Vb, ok ? 16 : 0);
+        }
+    };
 #pragma unroll
     for (int s = 0; s < NSTAGE - 1; ++s) {
-        if (s < ntiles) {
-            stage_rows<C, LDS>(sK + s * kTT * LDS, Kb, ld, (tile0 + s) * kTT, N);
-            stage_rows<C, LDS>(sV + s * kTT * LDS, Vb, ld, (tile0 + s) * kTT, N);
-        }
+        if (s < ntiles) stage(s, (tile0 + s) * kTT);
         cp_async_commit();
     }
 
     for (int64_t t = 0; t < ntiles; ++t) {
         const int buf = (int)(t % NSTAGE);
-        if (t + NSTAGE - 1 < ntiles) {
-            const int nb = (int)((t + NSTAGE - 1) % NSTAGE);
-            stage_rows<C, LDS>(sK + nb * kTT * LDS, Kb, ld, (tile0 + t + NSTAGE - 1) * kTT, N);
-            stage_rows<C, LDS>(sV + nb * kTT * LDS, Vb, ld, (tile0 + t + NSTAGE - 1) * kTT, N);
-        }
+        if (t + NSTAGE - 1 < ntiles) stage((int)((t + NSTAGE - 1) % NSTAGE), (tile0 + t + NSTAGE - 1) * kTT);
         cp_async_commit();
         cp_async_wait<NSTAGE - 1>();
         __syncthreads();                                          // tile t landed
@@ -162,23 +172,42 @@ kv_reduce_mma_kernel(const bf16* __restrict__ K, const bf16* __restrict__ V, int
 
         // ---- K -> P in place
         float dmax = -INFINITY;
+        if (valid == kTT) {                                       // every tile but the last one of the sequence
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-            const int row = r0 + i * RPP;
-            uint4* ptr = reinterpret_cast<uint4*>(tK + row * LDS + cc * 8);
-            float k[8];
-            unpack8(*ptr, k);
-            const bool ok = row < valid;
+            for (int i = 0; i < NCH; ++i) {
+                uint4* ptr = reinterpret_cast<uint4*>(tK + (r0 + i * RPP) * LDS + cc * 8);
+                float k[8];
+                unpack8(*ptr, k);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float d = fmaf(k[c], kLog2e, -rj[c]);
-                if (ok) dmax = fmaxf(dmax, d);
-                k[c] = ok ? ex2f(d) : 0.f;
+                for (int c = 0; c < 8; ++c) {
+                    const float d = fmaf(k[c], kLog2e, -rj[c]);
+                    dmax = fmaxf(dmax, d);
+                    k[c] = ex2f(d);
+                }
+                uint4 o;
+                o.x = pack_bf16x2(k[0], k[1]); o.y = pack_bf16x2(k[2], k[3]);
+                o.z = pack_bf16x2(k[4], k[5]); o.w = pack_bf16x2(k[6], k[7]);
+                *ptr = o;
             }
-            uint4 o;
-            o.x = pack_bf16x2(k[0], k[1]); o.y = pack_bf16x2(k[2], k[3]);
-            o.z = pack_bf16x2(k[4], k[5]); o.w = pack_bf16x2(k[6], k[7]);
-            *ptr = o;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                const int row = r0 + i * RPP;
+                uint4* ptr = reinterpret_cast<uint4*>(tK + row * LDS + cc * 8);
+                float k[8];
+                unpack8(*ptr, k);
+                const bool ok = row < valid;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float d = fmaf(k[c], kLog2e, -rj[c]);
+                    if (ok) dmax = fmaxf(dmax, d);
+                    k[c] = ok ? ex2f(d) : 0.f;
+                }
+                uint4 o;
+                o.x = pack_bf16x2(k[0], k[1]); o.y = pack_bf16x2(k[2], k[3]);
+                o.z = pack_bf16x2(k[4], k[5]); o.w = pack_bf16x2(k[6], k[7]);
+                *ptr = o;
+            }
         }
         if (__syncthreads_or(dmax > 64.f)) {
             // ---- rare: the data ran away from the reference.  Raise r_j to the tile's column max,
@@ -311,15 +340,30 @@ q_readout_mma_kernel(const bf16* __restrict__ Q, int64_t ldq, const float* __res
     if (ntiles > tiles_per_cta) ntiles = tiles_per_cta;
     if (ntiles < 0) ntiles = 0;
 
+    // a thread stages / copies out the same chunks every tile: rows r0 + i*RPP, 16-byte column cc
+    constexpr int RPP = 256 / CPR, NCH = kTT / RPP;
+    const int cc = tid % CPR, r0 = tid / CPR;
+    const int64_t goff0 = (int64_t)r0 * ldq + cc * 8, gstep = (int64_t)RPP * ldq;
+    const int64_t ooff0 = (int64_t)r0 * ldo + cc * 8, ostep = (int64_t)RPP * ldo;
+    const int soff0 = r0 * LDS + cc * 8;
+    auto stage = [&](int nb, int64_t trow0) {
+        const bf16* gq = Qb + trow0 * ldq + goff0;
+        bf16* dq = sQ + nb * kTT * LDS + soff0;
+        const int64_t left = N - trow0 - r0;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const bool ok = (int64_t)i * RPP < left;
+            cp_async16_zfill(dq + i * RPP * LDS, ok ? gq + i * gstep : Qb, ok ? 16 : 0);
+        }
+    };
 #pragma unroll
     for (int s = 0; s < NSTAGE - 1; ++s) {
-        if (s < ntiles) stage_rows<C, LDS>(sQ + s * kTT * LDS, Qb, ldq, (tile0 + s) * kTT, N);
+        if (s < ntiles) stage(s, (tile0 + s) * kTT);
         cp_async_commit();
     }
     for (int64_t t = 0; t < ntiles; ++t) {
         const int buf = (int)(t % NSTAGE);
-        if (t + NSTAGE - 1 < ntiles)
-            stage_rows<C, LDS>(sQ + (int)((t + NSTAGE - 1) % NSTAGE) * kTT * LDS, Qb, ldq, (tile0 + t + NSTAGE - 1) * kTT, N);
+        if (t + NSTAGE - 1 < ntiles) stage((int)((t + NSTAGE - 1) % NSTAGE), (tile0 + t + NSTAGE - 1) * kTT);
         cp_async_commit();
         cp_async_wait<NSTAGE - 1>();
         __syncthreads();
@@ -379,10 +423,13 @@ q_readout_mma_kernel(const bf16* __restrict__ Q, int64_t ldq, const float* __res
             }
         }
         __syncthreads();                                          // output tile complete in smem
-        for (int i = tid; i < kTT * CPR; i += 256) {
-            const int r = i / CPR, c = i - r * CPR;
-            if (r < valid)
-                *reinterpret_cast<uint4*>(Ob + (row0 + r) * ldo + c * 8) = *reinterpret_cast<const uint4*>(tQ + r * LDS + c * 8);
+        {
+            bf16* go = Ob + row0 * ldo + ooff0;
+            const bf16* so = tQ + soff0;
+#pragma unroll
+            for (int i = 0; i < NCH; ++i)
+                if (r0 + i * RPP < valid)
+                    *reinterpret_cast<uint4*>(go + i * ostep) = *reinterpret_cast<const uint4*>(so + i * RPP * LDS);
         }
         __syncthreads();                                          // before the buffer is refilled
     }

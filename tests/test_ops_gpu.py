@@ -137,7 +137,8 @@ def test_gelu(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(1, 128, 5, 4, 6), (2, 256, 3, 3, 8), (1, 128, 1, 1, 1), (1, 256, 2, 7, 1)])
+@pytest.mark.parametrize("shape", [(1, 128, 5, 4, 6), (2, 256, 3, 3, 8), (1, 128, 1, 1, 1), (1, 256, 2, 7, 1),
+                                   (1, 128, 5, 4, 37), (2, 256, 3, 4, 16), (1, 128, 2, 2, 64)])
 def test_posenc(dtype, shape):
     ops = _ops()
     from lintransunet_b200.unet import Conv3dPosEmbedding, _pos_w
