@@ -23,11 +23,12 @@ constexpr int kPartialFloats = 32 * 32 + 64;   // ctx[32][32], m[32], s[32]
 
 // How a sample's N tokens are split into chunks (one CTA each, one partial state per chunk).  The split
 // depends on N ONLY -- never on the batch size -- so that a sample's result is bit-identical whatever
-// batch it is processed in (the N-GPU sliding window must equal the 1-GPU one exactly): up to 74 chunks
-// per sample (74 * B CTAs = whole waves of 2 CTAs x 148 SMs for B = 4, 8), at least 4 tiles (128 tokens) each.
+// batch it is processed in (the N-GPU sliding window must equal the 1-GPU one exactly): up to 37 chunks
+// per sample (37 * 8 CTAs = one wave of 2 CTAs x 148 SMs at the benchmark's batch of 8; measured: 74 chunks
+// cost 25 % more through extra partial states and pipeline fills), at least 4 tiles (128 tokens) each.
 static inline int kv_chunks_per_batch(int /*B*/, int64_t N) {
     const int64_t tiles = ceil_div64(N, kTileTokens);
-    int64_t tiles_per_chunk = ceil_div64(tiles, 74);
+    int64_t tiles_per_chunk = ceil_div64(tiles, 37);
     if (tiles_per_chunk < 4) tiles_per_chunk = 4;
     return (int)ceil_div64(tiles, tiles_per_chunk);
 }
@@ -586,7 +587,10 @@ extern "C" int ltu_posenc_dwconv3(const void* x, const float* w, const float* bi
     LTU_ARG_CHECK(B > 0 && H > 0 && W > 0 && D > 0 && C > 0 && C % 4 == 0, "posenc_dwconv3: bad shape");
     LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "posenc_dwconv3: bad dtype %d", dtype);
     LTU_ARG_CHECK(x != y, "posenc_dwconv3: in-place is not supported");
-    if (D >= 8) {       // long enough D runs: the register-sliding kernel
+    // posenc2_kernel (register-sliding along D) measured 2x SLOWER than the plain 27-tap kernel on B200
+    // (404 vs 219 us on [8,39,23,64,128]: a serial chain of dependent loads per thread at 114 registers);
+    // kept for reference, not dispatched.
+    if (false && D >= 8) {
         constexpr int LD = 16;
         int64_t total = (int64_t)B * H * W * ((D + LD - 1) / LD) * (C / 2);
         int64_t blocks = ceil_div64(total, 256);
