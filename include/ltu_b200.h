@@ -96,10 +96,14 @@ int ltu_conv3d(const void* in0, int C0, const void* in1, int C1, int B, int Hi, 
 int ltu_conv3d_tc_supported(int C0, int C1, int Cout, int ksize, int pad);
 int ltu_conv3d_tc_tiles(int64_t out_voxels, int up2);
 int ltu_conv3d_tc_kpad(int Cin, int ksize);
+/* Fused head (n_aux > 0, 3x3x3 only): the weight/bias carry n_aux extra output rows after the Cout
+ * main ones (e.g. the 3-class mask head of ROIDecoder, Unet_3Dblock.py:1380, which reads the same
+ * input as UpBlock.conv1); their unrounded fp32 results go to aux_out [B][V][n_aux] and are not part of
+ * the statistics.  supported() is then asked with Cout + n_aux.                                     */
 int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di,
                   int up2, int ksize, int sh, int sw, int sd, int pad, const void* weight_bf16,
                   const float* bias, int Cout, void* out, int out_f32, int Ho, int Wo, int Do,
-                  float* partials, ltu_stream_t stream);
+                  float* partials, int n_aux, float* aux_out, ltu_stream_t stream);
 
 /* nn.Linear on a bf16 token matrix with a fused epilogue (model/trans_block.py:166,:187-189,:205-210),
  * run by the persistent tcgen05 kernel (a 1x1x1 "convolution"):  y = epi(x W^T + b)
@@ -116,7 +120,7 @@ int ltu_linear_tc(const void* x, int Cin, int64_t rows, const void* weight_bf16,
  * dec.block3, finest mask head, final_block): the input halo of a 3-D output tile and all weights are
  * staged once in shared memory and im2col happens in the ldmatrix row addresses of mma.sync
  * (bandwidth-bound layers).  Supported: (ksize,pad) = (3,1) or (1,0: the 1x1x1 gate convs,
- * Cin >= 16), stride 1, no up2, C0+C1 in {8,16,32}, C0 % 8 == 0, Cout <= 32 (even for bf16 output).  weight_bf16 is the ltu_conv3d_tc packing
+ * Cin in {16,32,64}), stride 1, no up2, C0+C1 in {8,16,32} for 3x3x3, C0 % 8 == 0, Cout <= 32 (even for bf16 output).  weight_bf16 is the ltu_conv3d_tc packing
  * ([>=16 rows][weight_ld], K index = tap*Cin + c).  partials: [B][tiles][Cout][2] with
  * tiles = ltu_conv3d_halo_tiles(H, W, D, Cin).                                                  */
 int ltu_conv3d_halo_supported(int C0, int C1, int Cout, int ksize, int sh, int sw, int sd, int pad,
@@ -124,7 +128,8 @@ int ltu_conv3d_halo_supported(int C0, int C1, int Cout, int ksize, int sh, int s
 int ltu_conv3d_halo_tiles(int H, int W, int D, int Cin);
 int ltu_conv3d_halo(const void* in0, int C0, const void* in1, int C1, int B, int H, int W, int D,
                     int ksize, const void* weight_bf16, int weight_ld, const float* bias, int Cout,
-                    void* out, int out_f32, float* partials, ltu_stream_t stream);
+                    void* out, int out_f32, float* partials, int n_aux, float* aux_out,
+                    ltu_stream_t stream);
 
 /* InstanceNorm3d (no affine, eps 1e-5, biased variance):
  * finalize : partials [B][tiles][C][2] -> stats [B][C][2] = (mean, rstd), fixed summation order

@@ -35,11 +35,11 @@ SIGNATURES = {
     "ltu_conv3d_tc_supported": (I, [I, I, I, I, I]),
     "ltu_conv3d_tc_tiles": (I, [L, I]),
     "ltu_conv3d_tc_kpad": (I, [I, I]),
-    "ltu_conv3d_tc": (I, [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, I, P, P]),
+    "ltu_conv3d_tc": (I, [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, I, P, I, P, P]),
     "ltu_linear_tc": (I, [P, I, L, P, P, I, P, I, I, P, P, P, F, P]),
     "ltu_conv3d_halo_supported": (I, [I, I, I, I, I, I, I, I, I]),
     "ltu_conv3d_halo_tiles": (I, [I, I, I, I]),
-    "ltu_conv3d_halo": (I, [P, I, P, I, I, I, I, I, I, P, I, P, I, P, I, P, P]),
+    "ltu_conv3d_halo": (I, [P, I, P, I, I, I, I, I, I, P, I, P, I, P, I, P, I, P, P]),
     "ltu_instnorm_finalize": (I, [P, P, I, I, I, L, F, P]),
     "ltu_chan_partials": (I, [P, P, I, L, I, I, I, P]),
     "ltu_instnorm_apply": (I, [P, P, P, P, I, L, I, I, I, P]),

@@ -23,7 +23,8 @@ struct HaloParams {
     const bf16* weight;          // [>=16 rows][wld] bf16, K index = tap*Cin + c (the ltu_conv3d_tc packing)
     int wld;
     const float* bias;
-    int Cout;                    // channels stored
+    int Cout;                    // main channels stored in `out` (and covered by the statistics)
+    int naux; float* aux;        // fused fp32 head: channels [Cout, Cout+naux) go to aux [B][V][naux]
     void* out; int out_f32;
     float* partials; int tiles;  // CTAs per sample
     int tiles_w, tiles_d;
@@ -79,7 +80,7 @@ conv3d_halo_kernel(const HaloParams p) {
         const int c = cc * 8;
         const int64_t vox = sample + ((int64_t)gh * p.W + gw) * p.D + gd;
         const bf16* src = c < p.C0 ? p.in0 + vox * p.C0 + c : p.in1 + vox * p.C1 + (c - p.C0);
-        const int sw = CIN == 32 ? ((v >> 1) & 3) : (CIN == 16 ? ((v >> 2) & 1) : 0);
+        const int sw = CIN >= 64 ? (v & 7) : (CIN == 32 ? ((v >> 1) & 3) : (CIN == 16 ? ((v >> 2) & 1) : 0));
         cp_async16_zfill(sH + v * VB + ((cc ^ sw) << 4), ok ? src : p.in0, ok ? 16 : 0);
     }
     {
@@ -109,7 +110,7 @@ conv3d_halo_kernel(const HaloParams p) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int c = nt * 8 + 2 * tq + j;
-            bias_r[nt][j] = (p.bias != nullptr && c < p.Cout) ? p.bias[c] : 0.f;
+            bias_r[nt][j] = (p.bias != nullptr && c < p.Cout + p.naux) ? p.bias[c] : 0.f;
         }
 
     for (int pass = 0; pass < MT / (8 * MG); ++pass) {
@@ -150,7 +151,7 @@ conv3d_halo_kernel(const HaloParams p) {
 #pragma unroll
             for (int m = 0; m < MG; ++m) {
                 const int v = vbase[m] + tapoff;
-                const int sw = CIN == 32 ? ((v >> 1) & 3) : (CIN == 16 ? ((v >> 2) & 1) : 0);
+                const int sw = CIN >= 64 ? (v & 7) : (CIN == 32 ? ((v >> 1) & 3) : (CIN == 16 ? ((v >> 2) & 1) : 0));
                 uint32_t a[4];
                 ldsm4(sH_u + v * VB + ((chunk ^ sw) << 4), a);
 #pragma unroll
@@ -169,11 +170,17 @@ conv3d_halo_kernel(const HaloParams p) {
             for (int half = 0; half < 2; ++half) {
                 const int gd = d0 + dh * 16 + g + 8 * half;
                 const bool ok = gh < p.H && gw < p.W && gd < p.D;
-                const int64_t row = (sample + ((int64_t)gh * p.W + gw) * p.D + gd) * p.Cout;
+                const int64_t vrow = sample + ((int64_t)gh * p.W + gw) * p.D + gd;
+                const int64_t row = vrow * p.Cout;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const int c = nt * 8 + 2 * tq;
                     float o0 = acc[m][nt][half * 2] + bias_r[nt][0], o1 = acc[m][nt][half * 2 + 1] + bias_r[nt][1];
+                    if (p.naux > 0 && ok) {                        // fused head: unrounded fp32 logits
+                        const int ca = c - p.Cout;
+                        if (ca >= 0 && ca < p.naux) p.aux[vrow * p.naux + ca] = o0;
+                        if (ca + 1 >= 0 && ca + 1 < p.naux) p.aux[vrow * p.naux + ca + 1] = o1;
+                    }
                     if (!p.out_f32) {                          // statistics describe the stored (rounded) values
                         o0 = __bfloat162float(__float2bfloat16_rn(o0));
                         o1 = __bfloat162float(__float2bfloat16_rn(o1));
@@ -247,7 +254,7 @@ static int halo_launch(HaloParams& p, int B, cudaStream_t st) {
 }
 
 static void halo_tile(int Cin, int& th, int& tw) {
-    if (Cin == 32) { th = 4; tw = 4; } else { th = 4; tw = 8; }
+    if (Cin >= 32) { th = 4; tw = 4; } else { th = 4; tw = 8; }
 }
 
 }  // namespace ltu
@@ -257,7 +264,7 @@ using namespace ltu;
 extern "C" int ltu_conv3d_halo_supported(int C0, int C1, int Cout, int ksize, int sh, int sw, int sd, int pad, int up2) {
     const int Cin = C0 + C1;
     if (!((ksize == 3 && pad == 1) || (ksize == 1 && pad == 0)) || sh != 1 || sw != 1 || sd != 1 || up2) return 0;
-    if (!(Cin == 8 || Cin == 16 || Cin == 32) || C0 % 8 != 0 || C1 % 8 != 0) return 0;
+    if (!(Cin == 8 || Cin == 16 || Cin == 32 || (Cin == 64 && ksize == 1)) || C0 % 8 != 0 || C1 % 8 != 0) return 0;
     if (ksize == 1 && Cin == 8) return 0;
     if (Cout < 1 || Cout > 32) return 0;
     return 1;
@@ -271,9 +278,10 @@ extern "C" int ltu_conv3d_halo_tiles(int H, int W, int D, int Cin) {
 
 extern "C" int ltu_conv3d_halo(const void* in0, int C0, const void* in1, int C1, int B, int H, int W, int D, int ksize,
                                const void* weight_bf16, int weight_ld, const float* bias, int Cout, void* out,
-                               int out_f32, float* partials, ltu_stream_t stream) {
+                               int out_f32, float* partials, int n_aux, float* aux_out, ltu_stream_t stream) {
     LTU_ARG_CHECK(in0 && weight_bf16 && out, "conv3d_halo: null pointer");
-    LTU_ARG_CHECK(ltu_conv3d_halo_supported(C0, C1, Cout, ksize, 1, 1, 1, ksize / 2, 0), "conv3d_halo: unsupported C0=%d C1=%d Cout=%d k=%d", C0, C1, Cout, ksize);
+    LTU_ARG_CHECK(n_aux >= 0 && (n_aux == 0 || (aux_out && !out_f32)), "conv3d_halo: bad auxiliary head");
+    LTU_ARG_CHECK(ltu_conv3d_halo_supported(C0, C1, Cout + n_aux, ksize, 1, 1, 1, ksize / 2, 0), "conv3d_halo: unsupported C0=%d C1=%d Cout=%d k=%d", C0, C1, Cout + n_aux, ksize);
     LTU_ARG_CHECK((in1 != nullptr) == (C1 > 0), "conv3d_halo: in1/C1 mismatch");
     LTU_ARG_CHECK(B > 0 && B <= 65535 && H > 0 && W > 0 && D > 0, "conv3d_halo: bad shape");
     const int Cin = C0 + C1;
@@ -284,10 +292,12 @@ extern "C" int ltu_conv3d_halo(const void* in0, int C0, const void* in1, int C1,
     HaloParams p;
     p.in0 = (const bf16*)in0; p.in1 = (const bf16*)in1; p.C0 = C0; p.C1 = C1; p.H = H; p.W = W; p.D = D;
     p.weight = (const bf16*)weight_bf16; p.wld = weight_ld; p.bias = bias; p.Cout = Cout; p.out = out; p.out_f32 = out_f32;
+    p.naux = n_aux; p.aux = aux_out;
     p.partials = partials;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool wide = Cout > 16;
+    const bool wide = Cout + n_aux > 16;
     if (ksize == 1) {
+        if (Cin == 64) return wide ? halo_launch<64, 4, 4, 4, 1>(p, B, st) : halo_launch<64, 2, 4, 4, 1>(p, B, st);
         if (Cin == 16) return wide ? halo_launch<16, 4, 4, 8, 1>(p, B, st) : halo_launch<16, 2, 4, 8, 1>(p, B, st);
         return wide ? halo_launch<32, 4, 4, 4, 1>(p, B, st) : halo_launch<32, 2, 4, 4, 1>(p, B, st);
     }

@@ -197,19 +197,34 @@ conv3d_tc_kernel(const TcParams p) {
         // =========================== epilogue ===========================
         mbar_wait(smem_u32(done_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t out_row = ((int64_t)b * (int64_t)p.Ho * p.Wo * p.Do + out_vox) * p.Cstore;
-        for (int c0 = 0; c0 < p.Cstore; c0 += 32) {
+        const int64_t vrow = (int64_t)b * (int64_t)p.Ho * p.Wo * p.Do + out_vox;
+        const int64_t out_row = vrow * p.Cstore;
+        const int ctot = p.Cstore + p.naux;                       // main channels, then the fused fp32 head
+        for (int c0 = 0; c0 < ctot; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-            const int ncol = (p.Cstore - c0) < 32 ? (p.Cstore - c0) : 32;
+            int ncol = p.Cstore - c0;                              // main columns of this chunk
+            ncol = ncol < 0 ? 0 : (ncol > 32 ? 32 : ncol);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                float bsv = (p.bias != nullptr && i < ncol) ? __ldg(p.bias + c0 + i) : 0.f;
-                float o = v[i] + bsv;
+                float bsv = (p.bias != nullptr && c0 + i < ctot) ? __ldg(p.bias + c0 + i) : 0.f;
+                v[i] += bsv;
+            }
+            if (p.naux > 0 && row_ok) {                            // auxiliary head: unrounded fp32 logits
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int ca = c0 + i - p.Cstore;
+                    if (ca >= 0 && ca < p.naux) p.aux[vrow * p.naux + ca] = v[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float o = v[i];
                 // bf16 output: round here so that the statistics describe the stored values
                 if (!p.out_f32) o = __bfloat162float(__float2bfloat16_rn(o));
                 v[i] = (row_ok && i < ncol) ? o : 0.f;
             }
+            if (ncol == 0) continue;
             if (row_ok) {
                 if (p.out_f32) {
                     float* dst = reinterpret_cast<float*>(p.out) + out_row + c0;
@@ -316,10 +331,11 @@ extern "C" int ltu_conv3d_tc_kpad(int Cin, int ksize) {
 
 extern "C" int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di, int up2,
                              int ksize, int sh, int sw, int sd, int pad, const void* weight_bf16, const float* bias,
-                             int Cout, void* out, int out_f32, int Ho, int Wo, int Do, float* partials,
-                             ltu_stream_t stream) {
+                             int Cout, void* out, int out_f32, int Ho, int Wo, int Do, float* partials, int n_aux,
+                             float* aux_out, ltu_stream_t stream) {
     LTU_ARG_CHECK(in0 && weight_bf16 && out, "conv3d_tc: null pointer");
-    LTU_ARG_CHECK(ltu_conv3d_tc_supported(C0, C1, Cout, ksize, pad), "conv3d_tc: unsupported C0=%d C1=%d Cout=%d k=%d pad=%d", C0, C1, Cout, ksize, pad);
+    LTU_ARG_CHECK(n_aux >= 0 && n_aux <= 16 && (n_aux == 0 || (aux_out && ksize == 3 && !out_f32)), "conv3d_tc: bad auxiliary head");
+    LTU_ARG_CHECK(ltu_conv3d_tc_supported(C0, C1, Cout + n_aux, ksize, pad), "conv3d_tc: unsupported C0=%d C1=%d Cout=%d k=%d pad=%d", C0, C1, Cout + n_aux, ksize, pad);
     LTU_ARG_CHECK((in1 != nullptr) == (C1 > 0), "conv3d_tc: in1/C1 mismatch");
     LTU_ARG_CHECK(B > 0 && B <= 65535 && Hi > 0 && Wi > 0 && Di > 0, "conv3d_tc: bad shape");
     LTU_ARG_CHECK(sh >= 1 && sh <= 2 && sw >= 1 && sw <= 2 && sd >= 1 && sd <= 2, "conv3d_tc: stride must be 1 or 2");
@@ -340,7 +356,8 @@ extern "C" int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, i
     p.ntaps = up2 ? 8 : ksize * ksize * ksize;
     p.Ktot = p.ntaps * Cin;
     p.Kpad = ltu_conv3d_tc_kpad(Cin, up2 ? 2 : ksize);
-    p.bias = bias; p.Cstore = Cout; p.Cout = (Cout + 15) / 16 * 16; p.out = out; p.out_f32 = out_f32;
+    p.bias = bias; p.Cstore = Cout; p.naux = n_aux; p.aux = aux_out;
+    p.Cout = (Cout + n_aux + 15) / 16 * 16; p.out = out; p.out_f32 = out_f32;
     p.w_class_stride = (int64_t)p.Cout * p.Kpad;
     p.Ho = Ho; p.Wo = Wo; p.Do = Do;
     p.partials = partials; p.tiles = ltu_conv3d_tc_tiles((int64_t)Ho * Wo * Do, up2);

@@ -441,7 +441,7 @@ extern "C" int ltu_linear_tc(const void* x, int Cin, int64_t rows, const void* w
     c.in0 = (const bf16*)x; c.in1 = nullptr; c.C0 = Cin; c.C1 = 0; c.log2cin = ilog2i(Cin);
     c.Hi = 1; c.Wi = 1; c.Di = (int)rows; c.up2 = 0; c.ks = 1; c.pad = 0; c.sh = c.sw = c.sd = 1;
     c.weight = (const bf16*)weight_bf16; c.ntaps = 1; c.Ktot = Cin; c.Kpad = (Cin + kTcBK - 1) / kTcBK * kTcBK;
-    c.bias = bias; c.Cstore = Cout; c.Cout = (Cout + 15) / 16 * 16; c.out = y; c.out_f32 = 0;
+    c.bias = bias; c.Cstore = Cout; c.naux = 0; c.aux = nullptr; c.Cout = (Cout + 15) / 16 * 16; c.out = y; c.out_f32 = 0;
     c.Ho = 1; c.Wo = 1; c.Do = (int)rows; c.partials = nullptr; c.tiles = 0; c.stages = 0; c.tmem_cols = 0;
     c.fold = 0; c.w_class_stride = 0;
     return conv3d_tc2_launch(c, 1, epi, residual, gamma, beta, eps, ld_y, (cudaStream_t)stream);

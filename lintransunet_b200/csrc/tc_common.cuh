@@ -19,7 +19,9 @@ struct TcParams {
     int Kpad, Ktot;
     const float* bias;
     int Cout;             // UMMA N (multiple of 16, zero-padded weight rows)
-    int Cstore;           // channels actually written (<= Cout)
+    int Cstore;           // main output channels (row stride of `out`, channels with statistics)
+    int naux;             // extra fp32 output channels right after the main ones (fused mask head), 0 = none
+    float* aux;           // [B][V][naux] fp32
     void* out; int out_f32;
     int Ho, Wo, Do;
     float* partials; int tiles;

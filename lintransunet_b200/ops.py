@@ -182,7 +182,7 @@ def conv_out_size(n: int, k: int, s: int, pad: int) -> int:
 def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ksize: int,
            stride: Tuple[int, int, int] = (1, 1, 1), pad: int = 1, x1: Optional[torch.Tensor] = None,
            up2: bool = False, out_f32: bool = False, want_stats: bool = False,
-           w_tc: Optional[torch.Tensor] = None, w_tc_fold: Optional[torch.Tensor] = None):
+           w_tc: Optional[torch.Tensor] = None, w_tc_fold: Optional[torch.Tensor] = None, n_aux: int = 0):
     """nn.Conv3d on channels-last input(s).  Returns (out, partials, tiles); partials is None
     unless want_stats.  When `w_tc` (bf16 [Cout16][Kpad], see ltu_conv3d_tc) is given and the shape
     qualifies the tcgen05 implicit-GEMM kernel is used, otherwise the CUDA-core kernel."""
@@ -198,12 +198,16 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     Ho, Wo, Do = (conv_out_size(He, ksize, stride[0], pad), conv_out_size(We, ksize, stride[1], pad),
                   conv_out_size(De, ksize, stride[2], pad))
     V = Ho * Wo * Do
+    ctot = cout + n_aux        # with a fused fp32 head the packed weight/bias carry n_aux extra output rows
     use_tc = (w_tc is not None and x0.dtype == torch.bfloat16 and (out_f32 or cout % 8 == 0)
-              and L.ltu_conv3d_tc_supported(C0, C1, cout, ksize, pad) == 1)
+              and L.ltu_conv3d_tc_supported(C0, C1, ctot, ksize, pad) == 1)
     # small-channel stride-1 layers: shared-memory halo + mma.sync kernel (needs the same bf16 packing)
     use_halo = (USE_HALO_CONV and w_tc is not None and not up2 and x0.dtype == torch.bfloat16
-                and (out_f32 or cout % 2 == 0) and w_tc.shape[0] >= (32 if cout > 16 else 16)
-                and L.ltu_conv3d_halo_supported(C0, C1, cout, ksize, stride[0], stride[1], stride[2], pad, 0) == 1)
+                and (out_f32 or cout % 2 == 0) and w_tc.shape[0] >= (32 if ctot > 16 else 16)
+                and L.ltu_conv3d_halo_supported(C0, C1, ctot, ksize, stride[0], stride[1], stride[2], pad, 0) == 1)
+    if n_aux and not (use_tc or use_halo):
+        raise RuntimeError("a fused auxiliary head needs the bf16 tensor-core path (tcgen05 or halo kernel)")
+    aux = torch.empty(B, Ho, Wo, Do, n_aux, dtype=torch.float32, device=dev) if n_aux else None
     out = torch.empty(B, Ho, Wo, Do, cout, dtype=torch.float32 if out_f32 else x0.dtype, device=dev)
     if use_halo:
         tiles = L.ltu_conv3d_halo_tiles(Ho, Wo, Do, C0 + C1)
@@ -218,15 +222,17 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     with _Guard(dev, prof) as st:
         if use_halo:
             check(L.ltu_conv3d_halo(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, ksize, _p(w_tc), w_tc.shape[1], _p(bias),
-                                    cout, _p(out), int(out_f32), _p(partials), st), "ltu_conv3d_halo")
+                                    cout, _p(out), int(out_f32), _p(partials), n_aux, _p(aux), st), "ltu_conv3d_halo")
         elif use_tc:
             check(L.ltu_conv3d_tc(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), ksize, stride[0], stride[1],
                                   stride[2], pad, _p(w_tc), _p(bias), cout, _p(out), int(out_f32), Ho, Wo, Do,
-                                  _p(partials), st), "ltu_conv3d_tc")
+                                  _p(partials), n_aux, _p(aux), st), "ltu_conv3d_tc")
         else:
             check(L.ltu_conv3d(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), ksize, stride[0], stride[1],
                                stride[2], pad, _p(w_packed), _p(bias), cout, _p(out), int(out_f32), Ho, Wo, Do,
                                _p(partials), _dt(x0), st), "ltu_conv3d")
+    if n_aux:
+        return out, partials, tiles, aux
     return out, partials, tiles
 
 

@@ -202,14 +202,21 @@ class _ConvW:
     [Cout16][Kpad] (K-major, K = tap*Cin + c) for the tcgen05 kernel.  `cin_pad` appends zero input
     channels (the stem's 4 channels are padded to 8 = one 16-byte bf16 vector)."""
 
-    def __init__(self, conv: nn.Conv3d, want_tc: bool, cin_pad: int = 0, fold_up2: bool = False):
+    def __init__(self, conv: nn.Conv3d, want_tc: bool, cin_pad: int = 0, fold_up2: bool = False,
+                 aux: Optional[nn.Conv3d] = None):
         w = conv.weight.detach()
+        bias = conv.bias.detach() if conv.bias is not None else None
+        self.n_aux = 0
+        if aux is not None:          # fused head: extra output rows after the main ones (same input, same geometry)
+            self.n_aux = aux.weight.shape[0]
+            w = torch.cat([w, aux.weight.detach()], 0)
+            bias = torch.cat([bias, aux.bias.detach()], 0)
         if cin_pad and cin_pad > w.shape[1]:
             w = torch.cat([w, w.new_zeros(w.shape[0], cin_pad - w.shape[1], *w.shape[2:])], 1)
         cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
-        self.k, self.cin, self.cout = k, cin, cout
+        self.k, self.cin, self.cout = k, cin, cout - self.n_aux        # cout = MAIN output channels
         self.w = w.permute(2, 3, 4, 1, 0).reshape(k * k * k, cin, cout).contiguous().float()
-        self.b = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+        self.b = bias.float().contiguous() if bias is not None else None
         self.w_tc = None
         if want_tc and (cin & (cin - 1)) == 0 and cin >= 8 and cout <= 256:
             ktot = k * k * k * cin
@@ -285,6 +292,9 @@ class _Plan:
                               psi.weight.detach().reshape(-1).float().contiguous(),
                               psi.bias.detach().float().contiguous()))
         self.up = [(_ConvW(b.conv1, tc), _ConvW(b.conv2, tc)) for b in dec.block_list]
+        # bf16 path: the mask head of level i reads the same upsampled x as UpBlock.conv1 -> one fused launch
+        n = len(dec.block_list)
+        self.up_dual = [_ConvW(dec.block_list[i].conv1, True, aux=dec.mask_conv_list[n - 1 - i]) for i in range(n)] if tc else None
         self.final = _ConvW(dec.final_block, tc)
         self.bridges: List[Optional[dict]] = []
         for br in dec.bridge_list:
@@ -341,6 +351,8 @@ class MaskTransUnet(nn.Module):
         # bandwidth-bound kernels at the model's shapes (profiles/r1_conv_variants.md) until the GEMM keeps its
         # weights resident and widens the epilogue.
         self.use_fused_linear = os.environ.get("LTU_FUSED_LINEAR", "0") == "1"
+        # bf16 path: compute the mask head inside UpBlock.conv1's launch (same input), fp32 logits as a second output
+        self.fuse_mask_head = os.environ.get("LTU_FUSE_MASK_HEAD", "1") != "0"
         self._plans: Dict[tuple, tuple] = {}
         self._graphs: Dict[tuple, dict] = {}
 
@@ -374,7 +386,8 @@ class MaskTransUnet(nn.Module):
                          and not torch.cuda.is_current_stream_capturing())
             if not graphable:
                 return self._forward_impl(x, plan, head)
-            key = (x.device.index, dtype, head, tuple(x.shape), self.use_tensor_cores, self.use_fused_linear)
+            key = (x.device.index, dtype, head, tuple(x.shape), self.use_tensor_cores, self.use_fused_linear,
+                   self.fuse_mask_head)
             ent = self._graphs.get(key)
             if ent is None or ent["plan"] is not plan:
                 ent = self._capture(x, plan, head)
@@ -506,7 +519,13 @@ class MaskTransUnet(nn.Module):
         for i in range(1, n):
             x = ops.upsample_trilinear(x, 2 if (n - i) % 2 == 0 else 1)          # :1375-1378
             lvl = n - 1 - i
-            logits, _, _ = self._conv(x, P.mask[lvl], pad=1, out_f32=True)       # :1380
+            fused = P.up_dual is not None and self.use_tensor_cores and self.fuse_mask_head
+            if fused:    # mask head (:1380) + UpBlock.conv1 (:547) share their input: one conv, two outputs
+                cw = P.up_dual[i - 1]
+                raw1, part1, _, logits = ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, pad=1, want_stats=True, w_tc=cw.w_tc,
+                                                    n_aux=cw.n_aux)
+            else:
+                logits, _, _ = self._conv(x, P.mask[lvl], pad=1, out_f32=True)   # :1380
             mask, fg = ops.mask_softmax(logits, want_mask=(head == "train"))
             if mask is not None:
                 mask_list.append(mask)
@@ -522,7 +541,11 @@ class MaskTransUnet(nn.Module):
                 skip = self._roi_bridge(skip, fg, br, lvl)                       # :1387-1388
             self._tap(f"bridge{lvl}", skip)
             c1, c2 = P.up[i - 1]
-            x = self._conv_in_act(x, c1)                                         # UpBlock :547-550
+            if fused:
+                V1 = raw1.shape[1] * raw1.shape[2] * raw1.shape[3]
+                x = ops.instnorm_apply(raw1, ops.instnorm_finalize(part1, V1), ops.ACT_LRELU, inplace=True)
+            else:
+                x = self._conv_in_act(x, c1)                                     # UpBlock :547-550
             x = self._conv_in_act(x, c2, x1=skip)                                # cat + conv2 :553-554
             self._tap(f"up{i-1}", x)
         logits, _, _ = self._conv(x, P.final, pad=1, out_f32=True)               # :1392

@@ -240,6 +240,8 @@ HALO_CASES = [
     (16, 0, 16, (5, 9, 40), False, 1),      # gate W_x, 1x1x1
     (32, 0, 16, (4, 5, 33), False, 1),      # gate W_g, 1x1x1
     (32, 0, 32, (3, 8, 32), False, 1),
+    (64, 0, 32, (5, 4, 35), False, 1),      # gate W_g of level 3
+    (64, 0, 16, (4, 4, 32), False, 1),
 ]
 
 
@@ -272,6 +274,33 @@ def test_conv3d_halo_matches_reference_and_tc_path(case):
         assert rel_err(stats[..., 1], 1 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5)) < 5e-3
         outs[halo] = y.float()
     assert rel_err(outs[True], outs[False]) < (2e-5 if out_f32 else 8e-3)
+
+
+@pytest.mark.parametrize("cin,cmain,naux,shape", [(32, 16, 3, (5, 6, 34)), (64, 32, 3, (4, 5, 9)), (256, 128, 2, (3, 4, 4)),
+                                                   (128, 64, 3, (4, 4, 6)), (16, 16, 3, (4, 8, 32))])
+def test_conv3d_fused_mask_head(cin, cmain, naux, shape):
+    """UpBlock.conv1 and the mask head read the same input: one launch, bf16 main output (+ IN statistics)
+    and unrounded fp32 logits as the auxiliary output (halo kernel for Cin<=32, tcgen05 otherwise)."""
+    ops = _ops()
+    from lintransunet_b200.unet import _ConvW
+    H, W, D = shape
+    B = 2
+    main, head = torch.nn.Conv3d(cin, cmain, 3, padding=1), torch.nn.Conv3d(cin, naux, 3, padding=1)
+    with torch.no_grad():
+        main.weight.copy_(q_(main.weight, torch.bfloat16))
+        head.weight.copy_(q_(head.weight, torch.bfloat16))
+    cw = _ConvW(main, True, aux=head)
+    assert cw.cout == cmain and cw.n_aux == naux
+    x = q_(rnd((B, cin, H, W, D), 60), torch.bfloat16)
+    ref_main = F.conv3d(x, main.weight.detach(), main.bias.detach(), padding=1)
+    ref_head = F.conv3d(x, head.weight.detach(), head.bias.detach(), padding=1)
+    y, partials, tiles, aux = ops.conv3d(to_cl(x).to("cuda", torch.bfloat16), cw.w.cuda(), cw.b.cuda(), cmain, 3, pad=1,
+                                         want_stats=True, w_tc=cw.w_tc.cuda(), n_aux=naux)
+    assert y.shape[-1] == cmain and aux.shape[-1] == naux and aux.dtype == torch.float32
+    assert rel_err(from_cl(y.float()), ref_main) < TOL[torch.bfloat16]
+    assert rel_err(from_cl(aux), ref_head) < 2e-5
+    stats = ops.instnorm_finalize(partials, H * W * D)
+    assert rel_err(stats[..., 0], ref_main.mean(dim=(2, 3, 4))) < 5e-3
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
