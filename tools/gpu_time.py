@@ -43,7 +43,7 @@ def main():
         x = torch.randn(8, 1, 128, 128, 128, device="cuda")
         ms = timeit(lambda: m.predict_labels(x), warm=2, it=5)
         print(f"forward bf16 B=8 128^3 fused_linear={fused}: {ms:.2f} ms/iter", flush=True)
-    m.use_fused_linear = True
+    m.use_fused_linear = False
     import torch.nn.functional as F
     for (M, C) in ((8 * 57408, 128), (8 * 10752, 256)):
         t = torch.randn(M, C, device="cuda").to(torch.bfloat16)
