@@ -32,7 +32,7 @@ static bool use_persistent_tc() {
     return v;
 }
 
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 4)
 conv3d_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve: [stages][A 16 KB][B Cout*128 B] | barriers | tmem slot | stat staging
@@ -369,9 +369,14 @@ extern "C" int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, i
     p.tmem_cols = cols;
     const int stage_bytes = kTcM * 128 + p.Cout * 128;
     const int nkb = p.Kpad / kTcBK;
-    // 2 CTAs per SM (<= ~108 KB each) for deep-K layers; short-K layers (few k-blocks per tile) get
-    // shallower pipelines so that more CTAs are resident and hide the fill/drain latency of a tile
-    int budget = nkb <= 8 ? 52 * 1024 : 108 * 1024;
+    // The kernel is bound by the im2col gather (address generation + L2 latency), i.e. by the number of
+    // resident producer threads: measured on B200, 4 CTAs/SM (<= 54 KB of pipeline each, 96 registers)
+    // beats 2 CTAs/SM with deeper pipelines by 1.2-1.5x on every layer (profiles/r1_conv_variants.md).
+    int budget = 54 * 1024;
+    {   // tuning knob (KB of pipeline smem per CTA => CTAs per SM); unset in production
+        static const int knob = [] { const char* e = getenv("LTU_TC_SMEM_KB"); return e ? atoi(e) : 0; }();
+        if (knob > 0) budget = knob * 1024;
+    }
     int stages = budget / stage_bytes;
     if (stages > 6) stages = 6;
     if (stages > nkb) stages = nkb;
