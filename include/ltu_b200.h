@@ -116,6 +116,18 @@ int ltu_linear_tc(const void* x, int Cin, int64_t rows, const void* weight_bf16,
                   int Cout, void* y, int ld_y, int epi, const void* residual, const float* gamma,
                   const float* beta, float eps, ltu_stream_t stream);
 
+/* Fused feed-forward half of SelfAttentionLayer (model/trans_block.py:207-210: linear1 -> erf GELU ->
+ * linear2 -> residual -> layer_norm2, dropouts are identity in eval) as ONE persistent tcgen05 kernel:
+ *     y = LayerNorm(x + W2 gelu(W1 x + b1) + b2) * gamma + beta
+ *   x, y bf16 [rows][C] (y may alias x); w1_bf16 [2C][C] and w2_bf16 [C][2C] are the nn.Linear weights
+ *   rounded to bf16 (row-major, K innermost: the K-major UMMA operand, fetched by TMA); biases, gamma,
+ *   beta fp32.  The 2C-wide hidden activation stays in tensor memory; HBM traffic is one read of x and
+ *   one write of y.  supported(C): 1 for C == 128 (the weights of wider layers do not fit in smem). */
+int ltu_ffn_fused_supported(int C);
+int ltu_ffn_fused(const void* x, int64_t rows, int C, const void* w1_bf16, const float* b1,
+                  const void* w2_bf16, const float* b2, const float* gamma, const float* beta,
+                  float eps, void* y, ltu_stream_t stream);
+
 /* Small-channel stride-1 3x3x3 convolution for bf16 activations (stem, enc.block0/1 conv1,
  * dec.block3, finest mask head, final_block): the input halo of a 3-D output tile and all weights are
  * staged once in shared memory and im2col happens in the ldmatrix row addresses of mma.sync

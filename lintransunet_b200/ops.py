@@ -443,3 +443,25 @@ def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
                                   c_void_p(bias.data_ptr() + n0 * 4), n, c_void_p(y.data_ptr() + n0 * 2), cout, epi,
                                   _p(residual), _p(gamma), _p(beta), eps, st), "ltu_linear_tc")
     return y
+
+
+def ffn_fused_supported(c: int) -> bool:
+    return bool(_native.lib().ltu_ffn_fused_supported(c))
+
+
+def ffn_fused(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+              gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm(x + W2 gelu(W1 x + b1) + b2) on bf16 tokens [..., C] in one persistent tcgen05 kernel
+    (model/trans_block.py:207-210).  w1 [2C, C] / w2 [C, 2C] bf16, the rest fp32."""
+    dev = _chk(x, w1, b1, w2, b2, gamma, beta, out)
+    c = x.shape[-1]
+    if x.dtype != torch.bfloat16 or w1.dtype != torch.bfloat16 or w2.dtype != torch.bfloat16:
+        raise TypeError("ffn_fused needs bf16 activations and bf16 weights")
+    if tuple(w1.shape) != (2 * c, c) or tuple(w2.shape) != (c, 2 * c):
+        raise ValueError(f"ffn_fused: weight shapes {tuple(w1.shape)} / {tuple(w2.shape)} do not match d_model {c}")
+    rows = x.numel() // c
+    y = torch.empty_like(x) if out is None else out
+    with _Guard(dev, ("ffn_fused", 2 * x.numel() * 2, 2 * rows * c * 2 * c * 2)) as st:
+        check(_native.lib().ltu_ffn_fused(_p(x), rows, c, _p(w1), _p(b1), _p(w2), _p(b2), _p(gamma), _p(beta), eps,
+                                          _p(y), st), "ltu_ffn_fused")
+    return y

@@ -495,3 +495,28 @@ def test_linear_tc_fused_epilogues(epi, rows, cin, cout):
                       gamma=g.cuda() if epi == 2 else None, beta=b.cuda() if epi == 2 else None)
     assert y.shape == (rows, cout)
     assert rel_err(y.float(), ref) < TOL[torch.bfloat16]
+
+
+@pytest.mark.parametrize("rows", [1, 127, 128, 129, 1000, 148 * 128 * 2 + 77, 57408])
+def test_ffn_fused(rows):
+    """Fused FFN half of the encoder layer (trans_block.py:207-210) vs fp32 torch on the same bf16-rounded operands."""
+    ops = _ops()
+    C = 128
+    l1, l2 = torch.nn.Linear(C, 2 * C), torch.nn.Linear(2 * C, C)
+    with torch.no_grad():
+        l1.weight.copy_(q_(l1.weight * 2, torch.bfloat16))
+        l2.weight.copy_(q_(l2.weight * 2, torch.bfloat16))
+    x = q_(rnd((rows, C), 90 + rows % 7, 1.5), torch.bfloat16)
+    g, b = 1 + 0.1 * rnd((C,), 91), 0.1 * rnd((C,), 92)
+    h = F.gelu(F.linear(x, l1.weight.detach(), l1.bias.detach()))
+    ref = F.layer_norm(x + F.linear(q_(h, torch.bfloat16), l2.weight.detach(), l2.bias.detach()), (C,), g, b, eps=1e-6)
+    cu = lambda t: t.detach().to("cuda")
+    xd = x.to("cuda", torch.bfloat16)
+    y = ops.ffn_fused(xd, cu(l1.weight).to(torch.bfloat16), cu(l1.bias), cu(l2.weight).to(torch.bfloat16), cu(l2.bias),
+                      cu(g), cu(b), 1e-6)
+    assert y.shape == (rows, C)
+    assert rel_err(y.float(), ref) < TOL[torch.bfloat16]
+    # in place, and bit-identical to the out-of-place result
+    y2 = ops.ffn_fused(xd, cu(l1.weight).to(torch.bfloat16), cu(l1.bias), cu(l2.weight).to(torch.bfloat16), cu(l2.bias),
+                       cu(g), cu(b), 1e-6, out=xd)
+    assert torch.equal(y2, y)
