@@ -127,6 +127,11 @@ int ltu_ffn_fused_supported(int C);
 int ltu_ffn_fused(const void* x, int64_t rows, int C, const void* w1_bf16, const float* b1,
                   const void* w2_bf16, const float* b2, const float* gamma, const float* beta,
                   float eps, void* y, ltu_stream_t stream);
+/* debugging aid: same launch, CTA 0 also records clock64() stamps of its pipeline events into
+ * trace[2 roles][64 tiles][8 events] (int64, device memory, zero it first)                      */
+int ltu_ffn_fused_trace(const void* x, int64_t rows, int C, const void* w1_bf16, const float* b1,
+                        const void* w2_bf16, const float* b2, const float* gamma, const float* beta,
+                        float eps, void* y, long long* trace, ltu_stream_t stream);
 
 /* Small-channel stride-1 3x3x3 convolution for bf16 activations (stem, enc.block0/1 conv1,
  * dec.block3, finest mask head, final_block): the input halo of a 3-D output tile and all weights are

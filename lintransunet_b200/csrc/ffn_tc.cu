@@ -6,21 +6,29 @@
 // traffic per token row (GEMM1 r1+w2, gelu r2+w2, GEMM2 r2+w1, add+LayerNorm r2+w1); this kernel
 // moves 2 (read t once, write y once): the 256-wide hidden activation never leaves the SM.
 //
-//   grid = min(#row tiles, #SMs), 384 threads, one 128-row tile at a time per CTA
-//   warp 0      TMA: W1 (64 KB) and W2 (64 KB) once per CTA, then the t tiles (2 x [128 x 64] boxes,
-//               SWIZZLE_128B) into a 2-slot ring; it also TMA-stores the finished y tile from the same
-//               slot (the epilogue overwrites its own residual rows in place)
-//   warp 1      one lane issues tcgen05.mma:  acc1[128x256] = T . W1^T           (A, B from smem)
-//                                             acc2[128x128] = H . W2^T           (A from TENSOR MEMORY)
-//   warps 4-11  epilogue (2 warps per TMEM lane quarter, splitting the columns):
-//               epi1: acc1 -> +b1 -> erf-GELU -> bf16 pairs -> tcgen05.st into the H region of TMEM
-//                     (64-column chunks, each with its own mbarrier so GEMM2 starts on chunk 0
-//                     while the later chunks are still being activated)
-//               epi2: acc2 -> +b2 + residual (read back from the swizzled t tile in smem) ->
-//                     two-pass LayerNorm (row halves exchanged through smem) -> bf16 -> same smem slot
-//   TMEM: acc1 cols [0,256) | H (packed bf16) cols [256,384) | acc2 cols [384,512)
-//
-// GEMM1 of tile i+1 is issued as soon as epi1 of tile i has drained acc1, so it runs under epi2(i).
+//   grid = min(#row tiles, #SMs), 512 threads; a CTA walks its 128-row tiles T, T+grid, ... (tile t of
+//   the CTA uses smem slot / TMEM buffer t & 1).  Two specialised groups of 8 warps, two warps per TMEM
+//   lane quarter, one row per thread:
+//     warps 0-7   e1: acc1 -> +b1 -> erf-GELU -> bf16 pairs -> tcgen05.st over the thread's OWN acc1
+//                 columns (128 hidden columns per thread)
+//     warps 8-15  e2: acc2 -> +b2 + residual (re-read from L2) -> LayerNorm (per-thread mean/M2 merged
+//                 with the row partner by Chan's formula, one smem exchange) -> bf16 -> global
+//                 (64 output columns per thread)
+//   The GELU warps carry ~75 % of the instructions and never wait for the tensor pipe: acc1 of tile t+1
+//   is complete long before e1(t) ends.  There are no dedicated producer / MMA warps (they would only
+//   spin on barriers and cost issue slots); lane 0 of the first warp of each group is its leader:
+//     warp 0 lane 0 : TMA load of tile t+2 (2 x [128 x 64] boxes, SWIZZLE_128B) once acc1(t) is complete
+//                     (GEMM1 has consumed the slot) -- two instructions, no waiting
+//     warp 8 lane 0 : GEMM2(t)  acc2[128x128] = H . W2^T  (A from TENSOR MEMORY) once H is published; a
+//                     tcgen05.mma issue blocks for about the duration of the MMA, so this must not sit in
+//                     a GELU warp (measured: +2300 cycles per tile on the critical path)
+//     warp 12 lane 0: GEMM1(t+2)  acc1[128x256] = T . W1^T  (A, B from smem) once the e2 group has pulled
+//                     acc2(t) into registers
+//   W1 / W2 (64 KB each) are loaded once per CTA.
+//   TMEM: two 256-column buffers.  acc1 fills a buffer; a thread turns 16 of its accumulator columns at a
+//   time into 8 packed bf16 columns and writes them back over columns it has already consumed, so
+//   H = [0,64) u [128,192) with no cross-warp hazard, and acc2 lands in the columns in between:
+//   [64,128) (outputs 0-63) and [192,256) (outputs 64-127), as two N=64 GEMMs.
 #include <cuda.h>
 
 #include "tc_common.cuh"
@@ -29,53 +37,58 @@ namespace ltu {
 
 void count_launch(int n = 1);
 
-constexpr int kFfnThreads = 384;
-constexpr int kFfnSlots = 2;
-constexpr int kFfnEpiThreads = 256;
+constexpr int kFfnThreads = 512;
+constexpr int kFfnGroupThreads = 256;
 constexpr uint32_t kFfnW1Bytes = 256 * 128 * 2;     // [256 out][128 in] bf16
 constexpr uint32_t kFfnW2Bytes = 128 * 256 * 2;     // [128 out][256 in] bf16
 constexpr uint32_t kFfnXBytes = 128 * 128 * 2;      // one 128-row tile
 constexpr uint32_t kFfnOffW1 = 0;
 constexpr uint32_t kFfnOffW2 = kFfnOffW1 + kFfnW1Bytes;
 constexpr uint32_t kFfnOffX = kFfnOffW2 + kFfnW2Bytes;
-constexpr uint32_t kFfnOffTail = kFfnOffX + kFfnSlots * kFfnXBytes;
-constexpr uint32_t kTmemAcc1 = 0, kTmemH = 256, kTmemAcc2 = 384;
+constexpr uint32_t kFfnOffTail = kFfnOffX + 2 * kFfnXBytes;
 
 struct FfnTail {
-    uint64_t w_full, x_full[kFfnSlots], out_ready[kFfnSlots], acc1_full, acc1_empty, h_full[4], acc2_full;
+    uint64_t w_full, x_full[2], acc1_full[2], h_full[2], acc2_full[2], buf_free[2];
     uint32_t tmem_slot, pad_;
     float b1[256], b2[128], gamma[128], beta[128];
-    float xs[2][128], xq[2][128];
+    float2 xs[2][2][128];           // [tile parity][column half][row] = (mean, M2)
 };
 
 struct FfnParams {
+    const bf16* x; bf16* y;
     const float* b1; const float* b2; const float* gamma; const float* beta;
     float eps;
     int tiles;
+    int64_t rows;
+    int mode;               // debug ablations: bit 0 = skip GELU math, bit 1 = skip LayerNorm math + stores
+    long long* trace;       // debug: [2 roles][64 tiles][8 events] clock64 stamps of CTA 0 (nullptr = off)
 };
 
 // erf-based GELU, x * Phi(x), with erfc from Abramowitz & Stegun 7.1.28
-//   erfc(z) = (1 + a1 z + ... + a6 z^6)^-16,  |error| <= 3e-7   (z = |x| / sqrt(2))
-// gelu(x) = max(x,0) - |x| erfc(z) / 2.  One MUFU (rcp) per element, no branches.
+//   erfc(z) = (1 + a1 z + ... + a6 z^6)^-16,  |error| <= 3e-7   (z = |x| / sqrt(2), folded into the a_k)
+// gelu(x) = max(x,0) - |x| erfc(z) / 2.  The epilogue is bound by the fp32 FMA pipe, so the 16th power goes
+// to the (idle) MUFU pipe, p^-16 = ex2(-16 lg2 p), and every multiply-add has an immediate operand:
+// 6 FFMA + 2 FMUL + 1 FFMA on the FMA pipe, 2 MUFU, 1 FMNMX per element, no branches.
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    float p = fmaf(z, 0.0000430638f, 0.0002765672f);
-    p = fmaf(p, z, 0.0001520143f);
-    p = fmaf(p, z, 0.0092705272f);
-    p = fmaf(p, z, 0.0422820123f);
-    p = fmaf(p, z, 0.0705230784f);
+    const float z = fabsf(x);
+    float p = fmaf(z, 0.0000430638f * 0.125f, 0.0002765672f * 0.17677669529663687f);
+    p = fmaf(p, z, 0.0001520143f * 0.25f);
+    p = fmaf(p, z, 0.0092705272f * 0.35355339059327373f);
+    p = fmaf(p, z, 0.0422820123f * 0.5f);
+    p = fmaf(p, z, 0.0705230784f * 0.70710678118654752f);
     p = fmaf(p, z, 1.0f);
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
-    r *= r; r *= r; r *= r; r *= r;
-    return fmaxf(x, 0.f) - fabsf(0.5f * x * r);
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(p));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -16.f));
+    return fmaf(-0.5f * z, r, fmaxf(x, 0.f));
 }
 
 __global__ void __launch_bounds__(kFfnThreads, 1)
-ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
-              const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2, const FfnParams p) {
+ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
+              const __grid_constant__ CUtensorMap tm_w2, const FfnParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // keep the shared address space visible to the compiler (LDS/STS instead of generic accesses)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     FfnTail* tail = reinterpret_cast<FfnTail*>(smem + kFfnOffTail);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,21 +96,20 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&tail->w_full), 1);
-        for (int s = 0; s < kFfnSlots; ++s) {
+        for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tail->x_full[s]), 1);
-            mbar_init(smem_u32(&tail->out_ready[s]), kFfnEpiThreads);
+            mbar_init(smem_u32(&tail->acc1_full[s]), 1);
+            mbar_init(smem_u32(&tail->h_full[s]), kFfnGroupThreads);
+            mbar_init(smem_u32(&tail->acc2_full[s]), 1);
+            mbar_init(smem_u32(&tail->buf_free[s]), kFfnGroupThreads);
         }
-        mbar_init(smem_u32(&tail->acc1_full), 1);
-        mbar_init(smem_u32(&tail->acc1_empty), kFfnEpiThreads);
-        for (int c = 0; c < 4; ++c) mbar_init(smem_u32(&tail->h_full[c]), kFfnEpiThreads / 2);
-        mbar_init(smem_u32(&tail->acc2_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 256; i += kFfnThreads) tail->b1[i] = p.b1[i];
     for (int i = threadIdx.x; i < 128; i += kFfnThreads) {
         tail->b2[i] = p.b2[i]; tail->gamma[i] = p.gamma[i]; tail->beta[i] = p.beta[i];
     }
-    if (warp == 1) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(&tail->tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -107,169 +119,215 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = tail->tmem_slot;
 
-    if (warp == 0) {
-        // =========================== TMA producer / store issuer ===========================
-        if (lane == 0) {
+    const int role = warp >> 3;                // 0: e1 (GELU) warps, 1: e2 (LayerNorm) warps
+    const int e = warp & 7;
+    const int q = e & 3;                       // TMEM lane quarter (== warp % 4)
+    const int hh = e >> 2;                     // column half: hidden [128hh, +128) / output [64hh, +64)
+    const int row = q * 32 + lane;             // tile row == TMEM lane
+    const bool leader = (e == 0) && (lane == 0);
+    auto stamp = [&](int t, int ev) {
+        if (p.trace != nullptr && lane == 0 && (e == 0 || (role == 1 && e == 4 && (ev == 2 || ev == 3))) && blockIdx.x == 0 && t < 64)
+            p.trace[(role * 64 + t) * 8 + ev] = clock64();
+    };
+    constexpr uint32_t idesc1 = umma_idesc_bf16(128, 256), idesc2 = umma_idesc_bf16(128, 64);
+    auto load_tile = [&](int t) {
+        const int b = t & 1;
+        const int row0 = ((int)blockIdx.x + t * (int)gridDim.x) * 128;
+        const uint32_t xb = smem_u32(&tail->x_full[b]), dst = sbase + kFfnOffX + b * kFfnXBytes;
+        mbar_expect_tx(xb, kFfnXBytes);
+        tma_load_2d(dst, &tm_x, 0, row0, xb);
+        tma_load_2d(dst + 16384, &tm_x, 64, row0, xb);
+    };
+    auto gemm1 = [&](int b) {
+        const uint32_t xslot = sbase + kFfnOffX + b * kFfnXBytes;
+        if (!(p.mode & 8))
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t adesc = make_desc(xslot + kb * 16384), bdesc = make_desc(sbase + kFfnOffW1 + kb * 32768);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + (uint32_t)(b * 256), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
+        }
+        umma_commit(smem_u32(&tail->acc1_full[b]));
+    };
+
+    if (role == 0) {
+        // =========================== e1: GELU warps ===========================
+        if (leader) {
             const uint32_t wbar = smem_u32(&tail->w_full);
             mbar_expect_tx(wbar, kFfnW1Bytes + kFfnW2Bytes);
             for (int kb = 0; kb < 2; ++kb) tma_load_2d(sbase + kFfnOffW1 + kb * 32768, &tm_w1, kb * 64, 0, wbar);
             for (int kb = 0; kb < 4; ++kb) tma_load_2d(sbase + kFfnOffW2 + kb * 16384, &tm_w2, kb * 64, 0, wbar);
-            for (int i = 0; i < kFfnSlots && i < n_my; ++i) {
-                const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * 128;
-                const uint32_t xb = smem_u32(&tail->x_full[i]), dst = sbase + kFfnOffX + i * kFfnXBytes;
-                mbar_expect_tx(xb, kFfnXBytes);
-                tma_load_2d(dst, &tm_x, 0, row0, xb);
-                tma_load_2d(dst + 16384, &tm_x, 64, row0, xb);
-            }
-            for (int i = 0; i < n_my; ++i) {
-                const int s = i % kFfnSlots;
-                const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * 128;
-                const uint32_t slot = sbase + kFfnOffX + s * kFfnXBytes;
-                mbar_wait(smem_u32(&tail->out_ready[s]), (i / kFfnSlots) & 1);
-                tma_store_2d(&tm_y, slot, 0, row0);
-                tma_store_2d(&tm_y, slot + 16384, 64, row0);
-                tma_store_commit();
-                tma_store_wait_read();                           // the slot may be overwritten now
-                if (i + kFfnSlots < n_my) {
-                    const int nrow0 = ((int)blockIdx.x + (i + kFfnSlots) * (int)gridDim.x) * 128;
-                    const uint32_t xb = smem_u32(&tail->x_full[s]);
-                    mbar_expect_tx(xb, kFfnXBytes);
-                    tma_load_2d(slot, &tm_x, 0, nrow0, xb);
-                    tma_load_2d(slot + 16384, &tm_x, 64, nrow0, xb);
-                }
-            }
-            tma_store_wait_all();
+            load_tile(0);
+            if (n_my > 1) load_tile(1);
         }
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
-        constexpr uint32_t idesc1 = umma_idesc_bf16(128, 256), idesc2 = umma_idesc_bf16(128, 128);
-        mbar_wait(smem_u32(&tail->w_full), 0);
-        for (int i = 0; i < n_my; ++i) {
-            const int s = i % kFfnSlots;
-            mbar_wait(smem_u32(&tail->x_full[s]), (i / kFfnSlots) & 1);
-            mbar_wait(smem_u32(&tail->acc1_empty), (i & 1) ^ 1);           // epi1 of the previous tile drained acc1
+        __syncwarp();
+        for (int t = 0; t < n_my; ++t) {
+            const int b = t & 1;
+            const uint32_t ph = (t >> 1) & 1;
+            const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256);
+            stamp(t, 0);
+            mbar_wait(smem_u32(&tail->acc1_full[b]), ph);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t xa = sbase + kFfnOffX + s * kFfnXBytes;
+            stamp(t, 1);
+            if (leader && t + 2 < n_my) load_tile(t + 2);       // GEMM1(t) is complete: the slot is free
+            __syncwarp();
+            // 16 accumulator columns per step (few live registers -> the 16 independent GELU chains of a step
+            // interleave); the 8 packed result columns go back over columns this thread has already consumed
+            {
+                const uint32_t abase = tb + (uint32_t)(hh * 128);
+                uint32_t cur[16], nxt[16];
+                tmem_ld16_nowait(abase, cur);
+                tmem_ld_wait();
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
-                    const uint64_t adesc = make_desc(xa + kb * 16384), bdesc = make_desc(sbase + kFfnOffW1 + kb * 32768);
+                for (int s8 = 0; s8 < 8; ++s8) {
+                    if (s8 < 7) tmem_ld16_nowait(abase + (uint32_t)(16 * (s8 + 1)), nxt);
+                    const float4* b1v = reinterpret_cast<const float4*>(tail->b1 + hh * 128 + s8 * 16);
+                    float4 bb[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + kTmemAcc1, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
+                    for (int j = 0; j < 4; ++j) bb[j] = b1v[j];
+                    uint32_t pk[8];
+                    if (p.mode & 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pk[j] = cur[2 * j] ^ cur[2 * j + 1];
+                    } else
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        pk[2 * j] = pack_bf16x2(gelu_erf(__uint_as_float(cur[4 * j]) + bb[j].x), gelu_erf(__uint_as_float(cur[4 * j + 1]) + bb[j].y));
+                        pk[2 * j + 1] = pack_bf16x2(gelu_erf(__uint_as_float(cur[4 * j + 2]) + bb[j].z), gelu_erf(__uint_as_float(cur[4 * j + 3]) + bb[j].w));
+                    }
+                    tmem_st8(abase + (uint32_t)(8 * s8), pk);
+                    if (s8 < 7) {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+                    }
                 }
-                umma_commit(smem_u32(&tail->acc1_full));
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            stamp(t, 2);
+            mbar_arrive(smem_u32(&tail->h_full[b]));
+        }
+    } else {
+        // =========================== e2: residual + LayerNorm warps ===========================
+        if (leader) {
+            mbar_wait(smem_u32(&tail->w_full), 0);
+            mbar_wait(smem_u32(&tail->x_full[0]), 0);
+            gemm1(0);
+            if (n_my > 1) { mbar_wait(smem_u32(&tail->x_full[1]), 0); gemm1(1); }
+        }
+        __syncwarp();
+        for (int t = 0; t < n_my; ++t) {
+            const int b = t & 1;
+            const uint32_t ph = (t >> 1) & 1;
+            const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256);
+            const int64_t grow = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * 128 + row;
+            const bool row_ok = grow < p.rows;
+            uint4 res[8];
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(p.x + (row_ok ? grow : 0) * 128 + hh * 64);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) res[j] = (p.mode & 16) ? make_uint4(0, 0, 0, 0) : __ldg(src + j);
+            }
+            if (leader) {                                       // GEMM2 as soon as the GELU group has published H
+                const uint32_t tacc = tmem_base + (uint32_t)(b * 256);
+                mbar_wait_sleep(smem_u32(&tail->h_full[b]), ph, 32);
+                tc_fence_after();
+                stamp(t, 7);
+                if (!(p.mode & 4))
+#pragma unroll
+                for (int nh = 0; nh < 2; ++nh) {                // output columns [64nh, 64nh+64) -> TMEM [64+128nh, +64)
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {              // hidden [16k, 16k+16): packed at TMEM (k>>3)*128 + (k&7)*8
+                        const uint64_t bdesc = make_desc(sbase + kFfnOffW2 + (k >> 2) * 16384 + nh * 8192) + (uint64_t)((k & 3) * 2);
+                        umma_bf16_ts(tacc + (uint32_t)(64 + 128 * nh), tacc + (uint32_t)((k >> 3) * 128 + (k & 7) * 8),
+                                     bdesc, idesc2, k != 0);
+                    }
+                }
+                umma_commit(smem_u32(&tail->acc2_full[b]));
             }
             __syncwarp();
-            // GEMM2 over the hidden chunks in the order the two epilogue halves finish them: 0,2,1,3
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                const int c = ((o & 1) << 1) | (o >> 1);
-                mbar_wait(smem_u32(&tail->h_full[c]), i & 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint64_t bdesc = make_desc(sbase + kFfnOffW2 + c * 16384);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_ts(tmem_base + kTmemAcc2, tmem_base + kTmemH + (uint32_t)(c * 32 + k * 8),
-                                     bdesc + (uint64_t)(k * 2), idesc2, (o | k) != 0);
-                    if (o == 3) umma_commit(smem_u32(&tail->acc2_full));
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp >= 4) {
-        // =========================== epilogue ===========================
-        const int e = warp - 4;
-        const int q = e & 3;                       // TMEM lane quarter (== warp % 4)
-        const int hh = e >> 2;                     // column half
-        const int row = q * 32 + lane;             // tile row == TMEM lane
-        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const int swz = row & 7;
-        for (int i = 0; i < n_my; ++i) {
-            const int s = i % kFfnSlots;
-            // ---- epi1: hidden activation into TMEM
-            mbar_wait(smem_u32(&tail->acc1_full), i & 1);
+            stamp(t, 0);
+            mbar_wait_sleep(smem_u32(&tail->acc2_full[b]), ph);
             tc_fence_after();
-#pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c = hh * 2 + cc;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int col0 = c * 64 + half * 32;
-                    float v[32];
-                    tmem_ld32(tmem_base + lane_off + kTmemAcc1 + (uint32_t)col0, v);
-                    if (cc == 1 && half == 1) {                  // last read of acc1 by this thread
-                        tc_fence_before();
-                        mbar_arrive(smem_u32(&tail->acc1_empty));
-                    }
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float a = gelu_erf(v[2 * j] + tail->b1[col0 + 2 * j]);
-                        const float b = gelu_erf(v[2 * j + 1] + tail->b1[col0 + 2 * j + 1]);
-                        pk[j] = pack_bf16x2(a, b);
-                    }
-                    tmem_st16(tmem_base + lane_off + kTmemH + (uint32_t)(col0 >> 1), pk);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(smem_u32(&tail->h_full[c]));
-            }
-            // ---- epi2: + b2 + residual -> LayerNorm -> bf16, in place in the t tile
-            mbar_wait(smem_u32(&tail->x_full[s]), (i / kFfnSlots) & 1);     // acquire the TMA-written tile
-            mbar_wait(smem_u32(&tail->acc2_full), i & 1);
-            tc_fence_after();
+            stamp(t, 1);
             float y[64];
             {
-                float v[32];
-                tmem_ld32(tmem_base + lane_off + kTmemAcc2 + (uint32_t)(hh * 64), v);
+                uint32_t v0[32], v1[32];
+                tmem_ld32_nowait(tb + (uint32_t)(64 + 128 * hh), v0);
+                tmem_ld32_nowait(tb + (uint32_t)(64 + 128 * hh + 32), v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&tail->buf_free[b]));
+                if (e == 4 && lane == 0 && t + 2 < n_my) {      // GEMM1 of tile t+2 into the drained buffer
+                    mbar_wait(smem_u32(&tail->buf_free[b]), ph);
+                    stamp(t, 2);
+                    mbar_wait(smem_u32(&tail->x_full[b]), ph ^ 1);
+                    tc_fence_after();
+                    stamp(t, 3);
+                    gemm1(b);
+                }
+                __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) y[j] = v[j];
-                tmem_ld32(tmem_base + lane_off + kTmemAcc2 + (uint32_t)(hh * 64 + 32), v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) y[32 + j] = v[j];
+                for (int j = 0; j < 32; ++j) { y[j] = __uint_as_float(v0[j]); y[32 + j] = __uint_as_float(v1[j]); }
             }
-            tc_fence_before();
-            unsigned char* xrow = smem + kFfnOffX + s * kFfnXBytes + hh * 16384 + row * 128;
+            if (p.mode & 2) {
+                if (y[0] == 123.456f && row_ok) p.y[grow * 128 + hh * 64] = __float2bfloat16_rn(y[1] + __uint_as_float(res[0].x));
+                continue;
+            }
             float s1 = 0.f;
+            const float4* b2v = reinterpret_cast<const float4*>(tail->b2 + hh * 64);
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                float r8[8];
-                load_vec(reinterpret_cast<const bf16*>(xrow + ((jj ^ swz) << 4)), r8);
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t w[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+                const float4 ba = b2v[2 * j], bb = b2v[2 * j + 1];
+                const float bs[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const float val = y[jj * 8 + t] + tail->b2[hh * 64 + jj * 8 + t] + r8[t];
-                    y[jj * 8 + t] = val;
-                    s1 += val;
+                for (int u = 0; u < 4; ++u) {
+                    const float lo = __uint_as_float(w[u] << 16), hi = __uint_as_float(w[u] & 0xffff0000u);
+                    y[j * 8 + 2 * u] += bs[2 * u] + lo;
+                    y[j * 8 + 2 * u + 1] += bs[2 * u + 1] + hi;
+                    s1 += y[j * 8 + 2 * u] + y[j * 8 + 2 * u + 1];
                 }
             }
-            tail->xs[hh][row] = s1;
+            const float m_loc = s1 * (1.f / 64.f);
+            float m2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) { const float d = y[j] - m_loc; m2 = fmaf(d, d, m2); }
+            tail->xs[b][hh][row] = make_float2(m_loc, m2);
+            stamp(t, 4);
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float mean = (s1 + tail->xs[hh ^ 1][row]) * (1.f / 128.f);
-            float s2 = 0.f;
+            stamp(t, 5);
+            const float2 other = tail->xs[b][hh ^ 1][row];
+            const float mean = 0.5f * (m_loc + other.x);
+            const float dm = m_loc - other.x;
+            const float var = (m2 + other.y + dm * dm * 32.f) * (1.f / 128.f);      // Chan: n_a n_b / (n_a + n_b) = 32
+            const float rstd = rsqrtf(var + p.eps);
+            if (row_ok) {
+                uint4* dst = reinterpret_cast<uint4*>(p.y + grow * 128 + hh * 64);
+                const float4* gv = reinterpret_cast<const float4*>(tail->gamma + hh * 64);
+                const float4* bv = reinterpret_cast<const float4*>(tail->beta + hh * 64);
 #pragma unroll
-            for (int j = 0; j < 64; ++j) { const float d = y[j] - mean; s2 = fmaf(d, d, s2); }
-            tail->xq[hh][row] = s2;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float rstd = rsqrtf((s2 + tail->xq[hh ^ 1][row]) * (1.f / 128.f) + p.eps);
+                for (int j = 0; j < 8; ++j) {
+                    const float4 g0 = gv[2 * j], g1 = gv[2 * j + 1], e0 = bv[2 * j], e1 = bv[2 * j + 1];
+                    const float gs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                    const float es[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                    float o[8];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                float o8[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const int col = hh * 64 + jj * 8 + t;
-                    o8[t] = fmaf((y[jj * 8 + t] - mean) * rstd, tail->gamma[col], tail->beta[col]);
+                    for (int u = 0; u < 8; ++u) o[u] = fmaf((y[j * 8 + u] - mean) * rstd, gs[u], es[u]);
+                    uint4 ov;
+                    ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
+                    ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+                    dst[j] = ov;
                 }
-                store_vec(reinterpret_cast<bf16*>(xrow + ((jj ^ swz) << 4)), o8);
             }
-            fence_async_smem();                                  // generic-proxy writes -> visible to the TMA store
-            mbar_arrive(smem_u32(&tail->out_ready[s]));
+            stamp(t, 6);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -314,23 +372,25 @@ using namespace ltu;
 
 extern "C" int ltu_ffn_fused_supported(int C) { return C == 128 ? 1 : 0; }
 
-extern "C" int ltu_ffn_fused(const void* x, int64_t rows, int C, const void* w1_bf16, const float* b1, const void* w2_bf16,
-                             const float* b2, const float* gamma, const float* beta, float eps, void* y,
-                             ltu_stream_t stream) {
+static int ffn_launch(const void* x, int64_t rows, int C, const void* w1_bf16, const float* b1, const void* w2_bf16,
+                      const float* b2, const float* gamma, const float* beta, float eps, void* y, long long* trace,
+                      ltu_stream_t stream, int mode = 0) {
     LTU_ARG_CHECK(C == 128, "ffn_fused: d_model %d not supported (128)", C);
     LTU_ARG_CHECK(x && y && w1_bf16 && w2_bf16 && b1 && b2 && gamma && beta, "ffn_fused: null pointer");
     LTU_ARG_CHECK(rows > 0 && rows < ((int64_t)1 << 31) - 256, "ffn_fused: bad row count");
     LTU_ARG_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w1_bf16 & 15) == 0 &&
                   ((uintptr_t)w2_bf16 & 15) == 0, "ffn_fused: pointers must be 16-byte aligned");
-    CUtensorMap tx, ty, tw1, tw2;
+    CUtensorMap tx, tw1, tw2;
     int rc;
     if ((rc = make_tmap_bf16_2d(&tx, x, (uint64_t)rows, 128, 128)) != LTU_OK) return rc;
-    if ((rc = make_tmap_bf16_2d(&ty, y, (uint64_t)rows, 128, 128)) != LTU_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&tw1, w1_bf16, 256, 128, 256)) != LTU_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&tw2, w2_bf16, 128, 256, 128)) != LTU_OK) return rc;
     FfnParams p;
+    p.x = (const bf16*)x; p.y = (bf16*)y; p.rows = rows;
     p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps;
     p.tiles = (int)((rows + 127) / 128);
+    p.trace = trace;
+    p.mode = mode;
     const size_t smem = 1024 + kFfnOffTail + sizeof(FfnTail);
     static thread_local int configured_dev = -1;
     int dev; cudaGetDevice(&dev);
@@ -340,8 +400,25 @@ extern "C" int ltu_ffn_fused(const void* x, int64_t rows, int C, const void* w1_
     }
     int grid = sm_count();
     if (grid > p.tiles) grid = p.tiles;
-    ffn128_kernel<<<grid, kFfnThreads, smem, (cudaStream_t)stream>>>(tx, ty, tw1, tw2, p);
+    ffn128_kernel<<<grid, kFfnThreads, smem, (cudaStream_t)stream>>>(tx, tw1, tw2, p);
     LTU_LAUNCH_CHECK("ffn_fused");
     count_launch(1);
     return LTU_OK;
+}
+
+extern "C" int ltu_ffn_fused(const void* x, int64_t rows, int C, const void* w1_bf16, const float* b1, const void* w2_bf16,
+                             const float* b2, const float* gamma, const float* beta, float eps, void* y,
+                             ltu_stream_t stream) {
+    return ffn_launch(x, rows, C, w1_bf16, b1, w2_bf16, b2, gamma, beta, eps, y, nullptr, stream);
+}
+
+// Same launch with a pipeline trace: CTA 0 writes clock64() stamps into trace[2][64][8] (int64, device memory;
+// role 0 = GELU group leader: wait acc1 | acc1 ready | GELU done | GEMM2 issued; role 1 = LayerNorm group leader:
+// wait acc2 | acc2 ready | buffer drained | tile t+2 landed (GEMM1 issued) | stats ready | exchanged | stored).
+extern "C" int ltu_ffn_fused_trace(const void* x, int64_t rows, int C, const void* w1_bf16, const float* b1,
+                                   const void* w2_bf16, const float* b2, const float* gamma, const float* beta, float eps,
+                                   void* y, long long* trace, ltu_stream_t stream) {
+    // a trace pointer below 16 is not a pointer but an ablation mode (1: no GELU math, 2: no LayerNorm/stores, 3: both)
+    if ((uintptr_t)trace < 64) return ffn_launch(x, rows, C, w1_bf16, b1, w2_bf16, b2, gamma, beta, eps, y, nullptr, stream, (int)(uintptr_t)trace);
+    return ffn_launch(x, rows, C, w1_bf16, b1, w2_bf16, b2, gamma, beta, eps, y, trace, stream);
 }

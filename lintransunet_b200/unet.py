@@ -261,6 +261,10 @@ class _LayerW:
             self.wt_o, self.bf_o = ops.pack_linear_tc(lin[3].weight), f(lin[3].bias)
             self.wt_1, self.bf_1 = ops.pack_linear_tc(layer.linear1.weight), f(layer.linear1.bias)
             self.wt_2, self.bf_2 = ops.pack_linear_tc(layer.linear2.weight), f(layer.linear2.bias)
+        # fused FFN kernel (ltu_ffn_fused): bf16 weights in the nn.Linear layout, fp32 biases
+        self.ffn = self.fused and ops.ffn_fused_supported(layer.linear1.in_features)
+        if self.ffn:
+            self.b1_f32, self.b2_f32 = f(layer.linear1.bias), f(layer.linear2.bias)
         self.g1, self.be1 = f(layer.layer_norm1.weight), f(layer.layer_norm1.bias)
         self.g2, self.be2 = f(layer.layer_norm2.weight), f(layer.layer_norm2.bias)
         self.nhead = layer.self_attn.nhead
@@ -351,6 +355,9 @@ class MaskTransUnet(nn.Module):
         # bandwidth-bound kernels at the model's shapes (profiles/r1_conv_variants.md) until the GEMM keeps its
         # weights resident and widens the epilogue.
         self.use_fused_linear = os.environ.get("LTU_FUSED_LINEAR", "0") == "1"
+        # Fused FFN half of the encoder layers with d_model = 128 (bridge 1: 57 408 tokens per sample at 128^3):
+        # 155 us vs 306 us for cuBLAS + gelu + cuBLAS + add_layernorm at batch 8.  LTU_FUSED_FFN=0 is the A/B switch.
+        self.use_fused_ffn = os.environ.get("LTU_FUSED_FFN", "1") == "1"
         # bf16 path: compute the mask head inside UpBlock.conv1's launch (same input), fp32 logits as a second output
         self.fuse_mask_head = os.environ.get("LTU_FUSE_MASK_HEAD", "1") != "0"
         self._plans: Dict[tuple, tuple] = {}
@@ -444,6 +451,9 @@ class MaskTransUnet(nn.Module):
             return ops.linear_tc(f, lw.wt_2, lw.bf_2, C, ops.EPI_RES_LN, residual=t, gamma=lw.g2, beta=lw.be2)
         o = F.linear(att, lw.w_o, lw.b_o)
         t = ops.add_layernorm(t, o, lw.g1, lw.be1, 1e-6)
+        if lw.ffn and self.use_fused_ffn:
+            # linear1 + GELU + linear2 + residual + LayerNorm2 in one launch; the hidden activation stays on the SM
+            return ops.ffn_fused(t, lw.w_1, lw.b1_f32, lw.w_2, lw.b2_f32, lw.g2, lw.be2, 1e-6)
         f = ops.gelu_(F.linear(t, lw.w_1, lw.b_1))
         f = F.linear(f, lw.w_2, lw.b_2)
         return ops.add_layernorm(t, f, lw.g2, lw.be2, 1e-6)

@@ -467,6 +467,7 @@ def test_encoder_layer_golden(dtype):
         m = MaskTransUnet.__new__(MaskTransUnet)      # only _encoder_layer is exercised
         torch.nn.Module.__init__(m)
         m.use_fused_linear = fused
+        m.use_fused_ffn = not fused
         y = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
         assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2), fused
 
