@@ -146,40 +146,35 @@ kv_reduce_kernel(const T* __restrict__ K, const T* __restrict__ V, int64_t ld, f
     out[1056 + lane] = s_run;
 }
 
-// grid (heads, B), 1024 threads: thread (j,e).  Merges the partial states in a fixed order (four
-// interleaved accumulation chains keep several loads in flight; the order is still deterministic).
+// grid (heads, B), 1024 threads: warp j, lane e own ctx[j][e].  Merges the partial states in a fixed order.
+// The merge is latency bound (every part is one dependent L2 round trip per thread), so the lanes of a warp
+// split the parts for the running-max / key-sum columns (exact max; butterfly sums) and the 32 weighted
+// accumulator loads of a block of parts are all issued before the first one is consumed.
 __global__ void __launch_bounds__(1024)
 kv_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx, int heads, int nparts) {
     const int hd = blockIdx.x, b = blockIdx.y;
     const int j = threadIdx.x >> 5, e = threadIdx.x & 31;
     const float* base = part + ((int64_t)b * nparts * heads + hd) * kPartialFloats;
     const int64_t stride = (int64_t)heads * kPartialFloats;
-    float M4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    int p = 0;
-    for (; p + 4 <= nparts; p += 4) {
+    float M = -INFINITY;
+    for (int p = e; p < nparts; p += 32) M = fmaxf(M, base[p * stride + 1024 + j]);
+    M = warp_max(M);
+    float S = 0.f;
+    float A8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p0 = 0; p0 < nparts; p0 += 32) {
+        const int p = p0 + e;
+        const float mp = p < nparts ? base[p * stride + 1024 + j] : -INFINITY;
+        const float sp = p < nparts ? base[p * stride + 1056 + j] : 0.f;
+        const float wl = (mp == -INFINITY) ? 0.f : __expf(mp - M);
+        S += warp_sum(sp * wl);
+        const int cnt = nparts - p0 < 32 ? nparts - p0 : 32;
+        float a[32];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) M4[u] = fmaxf(M4[u], base[(p + u) * stride + 1024 + j]);
-    }
-    for (; p < nparts; ++p) M4[0] = fmaxf(M4[0], base[p * stride + 1024 + j]);
-    const float M = fmaxf(fmaxf(M4[0], M4[1]), fmaxf(M4[2], M4[3]));
-    float S4[4] = {0.f, 0.f, 0.f, 0.f}, A4[4] = {0.f, 0.f, 0.f, 0.f};
-    for (p = 0; p + 4 <= nparts; p += 4) {
+        for (int u = 0; u < 32; ++u) a[u] = u < cnt ? base[(p0 + u) * stride + j * kHeadDim + e] : 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float mp = base[(p + u) * stride + 1024 + j];
-            const float w = (mp == -INFINITY) ? 0.f : __expf(mp - M);
-            S4[u] = fmaf(base[(p + u) * stride + 1056 + j], w, S4[u]);
-            A4[u] = fmaf(base[(p + u) * stride + j * kHeadDim + e], w, A4[u]);
-        }
+        for (int u = 0; u < 32; ++u) A8[u & 7] = fmaf(a[u], __shfl_sync(0xffffffffu, wl, u), A8[u & 7]);
     }
-    for (; p < nparts; ++p) {
-        const float mp = base[p * stride + 1024 + j];
-        const float w = (mp == -INFINITY) ? 0.f : __expf(mp - M);
-        S4[0] = fmaf(base[p * stride + 1056 + j], w, S4[0]);
-        A4[0] = fmaf(base[p * stride + j * kHeadDim + e], w, A4[0]);
-    }
-    const float S = (S4[0] + S4[1]) + (S4[2] + S4[3]);
-    const float A = (A4[0] + A4[1]) + (A4[2] + A4[3]);
+    const float A = ((A8[0] + A8[1]) + (A8[2] + A8[3])) + ((A8[4] + A8[5]) + (A8[6] + A8[7]));
     ctx[(((int64_t)b * heads + hd) * kHeadDim + j) * kHeadDim + e] = A / S;
 }
 
@@ -581,6 +576,88 @@ extern "C" int ltu_gelu(void* x, int64_t n, int dtype, ltu_stream_t stream) {
     return LTU_OK;
 }
 
+// bf16 storage: one thread = 8 channels x 4 consecutive outputs along D.  For each of the 9 (kh,kw) neighbours
+// the six input planes d0-1 .. d0+4 are loaded once (16-byte loads) and feed the 3 taps of the 4 outputs, so an
+// output costs 13.5 data + 13.5 weight loads per 8 channels instead of 54 + 54 (the plain kernel is LSU-issue
+// bound: 219 us on [8,39,23,64,128]); the residual term reuses the centre planes.
+__global__ void __launch_bounds__(256)
+posenc_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   bf16* __restrict__ y, int B, int H, int W, int D, int C) {
+    const int c8n = C >> 3;
+    const int dgn = (D + 3) >> 2;
+    const int64_t total = (int64_t)B * H * W * dgn * c8n;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(idx % c8n) * 8;
+        int64_t t = idx / c8n;
+        const int d0 = (int)(t % dgn) * 4;
+        t /= dgn;
+        const int ww = (int)(t % W);
+        t /= W;
+        const int h = (int)(t % H);
+        const int b = (int)(t / H);
+        float acc[4][8];
+        {
+            float b8[8];
+            load_vec(bias + c0, *reinterpret_cast<float(*)[4]>(b8));
+            load_vec(bias + c0 + 4, *reinterpret_cast<float(*)[4]>(b8 + 4));
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[o][i] = b8[i];
+        }
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hh = h + kh - 1;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int w2 = ww + kw - 1;
+                if (w2 < 0 || w2 >= W) continue;
+                const bf16* col = x + ((((int64_t)b * H + hh) * W + w2) * D) * C + c0;
+                uint4 raw[6];
+#pragma unroll
+                for (int pl = 0; pl < 6; ++pl) {
+                    const int dd = d0 + pl - 1;
+                    raw[pl] = (dd >= 0 && dd < D) ? *reinterpret_cast<const uint4*>(col + (int64_t)dd * C) : make_uint4(0, 0, 0, 0);
+                }
+                float wt[3][8];
+#pragma unroll
+                for (int kd = 0; kd < 3; ++kd) {
+                    const float* wp = w + (kh * 9 + kw * 3 + kd) * C + c0;
+                    load_vec(wp, *reinterpret_cast<float(*)[4]>(wt[kd]));
+                    load_vec(wp + 4, *reinterpret_cast<float(*)[4]>(wt[kd] + 4));
+                }
+#pragma unroll
+                for (int pl = 0; pl < 6; ++pl) {
+                    const uint32_t u[4] = {raw[pl].x, raw[pl].y, raw[pl].z, raw[pl].w};
+                    float xv[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        xv[2 * i] = __uint_as_float(u[i] << 16);
+                        xv[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+                    }
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const int o = pl - kd;                  // output d0+o reads plane d0+o+kd-1 = d0+pl-1
+                        if (o < 0 || o > 3) continue;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[o][i] = fmaf(xv[i], wt[kd][i], acc[o][i]);
+                    }
+                    if (kh == 1 && kw == 1 && pl >= 1 && pl <= 4) {     // residual: x itself
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[pl - 1][i] += xv[i];
+                    }
+                }
+            }
+        }
+        bf16* out = y + ((((int64_t)b * H + h) * W + ww) * D + d0) * C + c0;
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (d0 + o < D) store_vec(out + (int64_t)o * C, acc[o]);
+    }
+}
+
 extern "C" int ltu_posenc_dwconv3(const void* x, const float* w, const float* bias, void* y, int B, int H, int W,
                                   int D, int C, int dtype, ltu_stream_t stream) {
     LTU_ARG_CHECK(x && w && bias && y, "posenc_dwconv3: null pointer");
@@ -590,7 +667,12 @@ extern "C" int ltu_posenc_dwconv3(const void* x, const float* w, const float* bi
     // posenc2_kernel (register-sliding along D) measured 2x SLOWER than the plain 27-tap kernel on B200
     // (404 vs 219 us on [8,39,23,64,128]: a serial chain of dependent loads per thread at 114 registers);
     // kept for reference, not dispatched.
-    if (false && D >= 8) {
+    if (dtype == LTU_BF16 && C % 8 == 0 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)bias) & 15) == 0) {
+        int64_t total = (int64_t)B * H * W * ((D + 3) / 4) * (C / 8);
+        int64_t blocks = ceil_div64(total, 256);
+        LTU_ARG_CHECK(blocks < ((int64_t)1 << 31), "posenc_dwconv3: tensor too large");
+        posenc_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, (bf16*)y, B, H, W, D, C);
+    } else if (false && D >= 8) {
         constexpr int LD = 16;
         int64_t total = (int64_t)B * H * W * ((D + LD - 1) / LD) * (C / 2);
         int64_t blocks = ceil_div64(total, 256);

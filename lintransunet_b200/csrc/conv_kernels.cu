@@ -210,11 +210,23 @@ instnorm_finalize_kernel(const float* __restrict__ partials, float* __restrict__
     double s = 0.0, q = 0.0;
     if (c < C) {
         const float2* base = reinterpret_cast<const float2*>(partials) + (int64_t)b * tiles * C + c;
-        for (int t = warp; t < tiles; t += 32) {
-            const float2 v = base[(int64_t)t * C];
-            s += (double)v.x;
-            q += (double)v.y;
+        // eight independent loads in flight per thread (the loop is a chain of L2 round trips otherwise)
+        double s8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int t = warp;
+        for (; t + 7 * 32 < tiles; t += 8 * 32) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = base[(int64_t)(t + 32 * u) * C];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s8[u] += (double)v[u].x; q8[u] += (double)v[u].y; }
         }
+        for (; t < tiles; t += 32) {
+            const float2 v = base[(int64_t)t * C];
+            s8[0] += (double)v.x;
+            q8[0] += (double)v.y;
+        }
+        s = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
+        q = ((q8[0] + q8[1]) + (q8[2] + q8[3])) + ((q8[4] + q8[5]) + (q8[6] + q8[7]));
     }
     red[warp][lane][0] = s;
     red[warp][lane][1] = q;
