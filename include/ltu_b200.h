@@ -133,6 +133,20 @@ int ltu_ffn_fused_trace(const void* x, int64_t rows, int C, const void* w1_bf16,
                         const void* w2_bf16, const float* b2, const float* gamma, const float* beta,
                         float eps, void* y, long long* trace, ltu_stream_t stream);
 
+/* Query half of the encoder layer (model/trans_block.py:50,:65 readout, :155-166 projections, :205-206
+ * residual + layer_norm1) for d_model 128 / 4 heads as ONE persistent tcgen05 kernel:
+ *     y = LayerNorm(x + (softmax_d(x Wq^T + bq)/sqrt(32) . ctx_b) Wo^T + bo) * gamma + beta
+ *   x, y bf16 [B][N][128]; wq_bf16, wo_bf16 the nn.Linear weights [128][128] rounded to bf16; biases, gamma,
+ *   beta fp32; ctx_bf16 = ltu_ctx_pack_bf16 of the fp32 ctx [B][heads][32][32] produced by ltu_kv_reduce:
+ *   bf16 [B*heads*32 rows (h*32+e)][64] with row[j] = ctx[b][h][j][e] for j < 32 and zeros above (the K-major
+ *   tensor-core operand of the readout, fetched by TMA).  Q, the softmax and the attention output never leave
+ *   tensor memory: HBM traffic is one read of x and one write of y.                                     */
+int ltu_attn_out_fused_supported(int C, int heads);
+int ltu_ctx_pack_bf16(const float* ctx, void* out, int B, int heads, ltu_stream_t stream);
+int ltu_attn_out_fused(const void* x, int B, int64_t N, int C, int heads, const void* wq_bf16,
+                       const float* bq, const void* ctx_bf16, const void* wo_bf16, const float* bo,
+                       const float* gamma, const float* beta, float eps, void* y, ltu_stream_t stream);
+
 /* Small-channel stride-1 3x3x3 convolution for bf16 activations (stem, enc.block0/1 conv1,
  * dec.block3, finest mask head, final_block): the input halo of a 3-D output tile and all weights are
  * staged once in shared memory and im2col happens in the ldmatrix row addresses of mma.sync

@@ -465,3 +465,34 @@ def ffn_fused(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Ten
         check(_native.lib().ltu_ffn_fused(_p(x), rows, c, _p(w1), _p(b1), _p(w2), _p(b2), _p(gamma), _p(beta), eps,
                                           _p(y), st), "ltu_ffn_fused")
     return y
+
+
+def attn_out_fused_supported(c: int, heads: int) -> bool:
+    return bool(_native.lib().ltu_attn_out_fused_supported(c, heads))
+
+
+def ctx_pack(ctx: torch.Tensor) -> torch.Tensor:
+    """fp32 ctx [B, heads, 32, 32] (kv_reduce) -> bf16 [B*heads*32, 64] tensor-core operand of attn_out_fused."""
+    dev = _chk(ctx)
+    B, heads = ctx.shape[0], ctx.shape[1]
+    out = torch.empty(B * heads * 32, 64, dtype=torch.bfloat16, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_ctx_pack_bf16(_p(ctx), _p(out), B, heads, st), "ltu_ctx_pack_bf16")
+    return out
+
+
+def attn_out_fused(x: torch.Tensor, wq: torch.Tensor, bq: torch.Tensor, ctx16: torch.Tensor, wo: torch.Tensor,
+                   bo: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, heads: int, eps: float = 1e-6) -> torch.Tensor:
+    """LayerNorm(x + readout(x Wq^T + bq, ctx) Wo^T + bo) on bf16 tokens [B, N, C] in one persistent tcgen05 kernel
+    (model/trans_block.py:50,:65,:155-166,:205-206)."""
+    dev = _chk(x, wq, bq, ctx16, wo, bo, gamma, beta)
+    B, N, C = x.shape
+    if x.dtype != torch.bfloat16 or wq.dtype != torch.bfloat16 or wo.dtype != torch.bfloat16 or ctx16.dtype != torch.bfloat16:
+        raise TypeError("attn_out_fused needs bf16 activations, weights and packed ctx")
+    if tuple(wq.shape) != (C, C) or tuple(wo.shape) != (C, C) or tuple(ctx16.shape) != (B * heads * 32, 64):
+        raise ValueError("attn_out_fused: operand shapes do not match")
+    y = torch.empty_like(x)
+    with _Guard(dev, ("attn_out_fused", 2 * x.numel() * 2, 2 * B * N * C * (2 * C + 32))) as st:
+        check(_native.lib().ltu_attn_out_fused(_p(x), B, N, C, heads, _p(wq), _p(bq), _p(ctx16), _p(wo), _p(bo),
+                                               _p(gamma), _p(beta), eps, _p(y), st), "ltu_attn_out_fused")
+    return y

@@ -265,6 +265,12 @@ class _LayerW:
         self.ffn = self.fused and ops.ffn_fused_supported(layer.linear1.in_features)
         if self.ffn:
             self.b1_f32, self.b2_f32 = f(layer.linear1.bias), f(layer.linear2.bias)
+        # fused query half (ltu_attn_out_fused): K/V projection stays a cuBLAS GEMM feeding kv_reduce
+        self.attn_fused = self.fused and ops.attn_out_fused_supported(layer.linear1.in_features, layer.self_attn.nhead)
+        if self.attn_fused:
+            self.w_kv = c(torch.cat([lin[1].weight, lin[2].weight], 0))
+            self.b_kv = c(torch.cat([lin[1].bias, lin[2].bias], 0))
+            self.w_q, self.bq_f32, self.bo_f32 = c(lin[0].weight), f(lin[0].bias), f(lin[3].bias)
         self.g1, self.be1 = f(layer.layer_norm1.weight), f(layer.layer_norm1.bias)
         self.g2, self.be2 = f(layer.layer_norm2.weight), f(layer.layer_norm2.bias)
         self.nhead = layer.self_attn.nhead
@@ -358,6 +364,9 @@ class MaskTransUnet(nn.Module):
         # Fused FFN half of the encoder layers with d_model = 128 (bridge 1: 57 408 tokens per sample at 128^3):
         # 155 us vs 306 us for cuBLAS + gelu + cuBLAS + add_layernorm at batch 8.  LTU_FUSED_FFN=0 is the A/B switch.
         self.use_fused_ffn = os.environ.get("LTU_FUSED_FFN", "1") == "1"
+        # Fused query half of the same layers (Q projection + readout + output projection + residual + LayerNorm1):
+        # 253 us vs 318 us for the attention half at batch 8.  LTU_FUSED_ATTN=0 is the A/B switch.
+        self.use_fused_attn = os.environ.get("LTU_FUSED_ATTN", "1") == "1"
         # bf16 path: compute the mask head inside UpBlock.conv1's launch (same input), fp32 logits as a second output
         self.fuse_mask_head = os.environ.get("LTU_FUSE_MASK_HEAD", "1") != "0"
         self._plans: Dict[tuple, tuple] = {}
@@ -440,6 +449,17 @@ class MaskTransUnet(nn.Module):
     def _encoder_layer(self, t, lw: _LayerW):
         """SelfAttentionLayer.forward (model/trans_block.py:203-211) on tokens [B,N,C]."""
         B, N, C = t.shape
+        if lw.attn_fused and self.use_fused_attn and not (lw.fused and self.use_fused_linear):
+            # K/V projection (cuBLAS) -> kv_reduce -> ONE kernel for Q projection, readout, output projection,
+            # residual and LayerNorm1; then ONE kernel for the feed-forward half
+            kv = F.linear(t, lw.w_kv, lw.b_kv)
+            ctx = ops.kv_reduce(kv[..., :C], kv[..., C:], lw.nhead)
+            t = ops.attn_out_fused(t, lw.w_q, lw.bq_f32, ops.ctx_pack(ctx), lw.w_o, lw.bo_f32, lw.g1, lw.be1, lw.nhead)
+            if lw.ffn and self.use_fused_ffn:
+                return ops.ffn_fused(t, lw.w_1, lw.b1_f32, lw.w_2, lw.b2_f32, lw.g2, lw.be2, 1e-6)
+            f = ops.gelu_(F.linear(t, lw.w_1, lw.b_1))
+            f = F.linear(f, lw.w_2, lw.b_2)
+            return ops.add_layernorm(t, f, lw.g2, lw.be2, 1e-6)
         qkv = F.linear(t, lw.w_qkv, lw.b_qkv)                           # cuBLAS: plain library GEMM
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         ctx = ops.kv_reduce(k, v, lw.nhead)

@@ -463,13 +463,13 @@ def test_encoder_layer_golden(dtype):
     layer.load_state_dict({k[len(pre) + 1:]: v for k, v in sd.items() if k.startswith(pre + ".")})
     layer.cuda()
     x = torch.from_numpy(g["layer_x"])
-    for fused in (True, False):
+    for fused_linear, fused_ffn, fused_attn in ((True, False, False), (False, True, False), (False, True, True),
+                                                (False, False, True), (False, False, False)):
         m = MaskTransUnet.__new__(MaskTransUnet)      # only _encoder_layer is exercised
         torch.nn.Module.__init__(m)
-        m.use_fused_linear = fused
-        m.use_fused_ffn = not fused
+        m.use_fused_linear, m.use_fused_ffn, m.use_fused_attn = fused_linear, fused_ffn, fused_attn
         y = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
-        assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2), fused
+        assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2), (fused_linear, fused_ffn, fused_attn)
 
 
 @pytest.mark.parametrize("epi", [0, 1, 2])
@@ -521,3 +521,31 @@ def test_ffn_fused(rows):
     y2 = ops.ffn_fused(xd, cu(l1.weight).to(torch.bfloat16), cu(l1.bias), cu(l2.weight).to(torch.bfloat16), cu(l2.bias),
                        cu(g), cu(b), 1e-6, out=xd)
     assert torch.equal(y2, y)
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (1, 128), (2, 129), (2, 300), (3, 7176), (8, 57408 // 16)])
+def test_attn_out_fused(B, N):
+    """Fused Q-projection + readout + output projection + residual + LayerNorm1 (trans_block.py:50,:65,:155-166,
+    :205-206) vs fp32 torch on the same bf16-rounded operands."""
+    ops = _ops()
+    C, h = 128, 4
+    lq, lo = torch.nn.Linear(C, C), torch.nn.Linear(C, C)
+    with torch.no_grad():
+        lq.weight.copy_(q_(lq.weight * 3, torch.bfloat16))
+        lo.weight.copy_(q_(lo.weight * 3, torch.bfloat16))
+    x = q_(rnd((B, N, C), 70 + N % 5, 1.5), torch.bfloat16)
+    ctx = rnd((B, h, 32, 32), 71, 0.5)
+    g, b = 1 + 0.1 * rnd((C,), 72), 0.1 * rnd((C,), 73)
+    qh = F.linear(x, lq.weight.detach(), lq.bias.detach()).view(B, N, h, 32)
+    pr = q_(torch.softmax(qh, -1) / math.sqrt(32.0), torch.bfloat16)
+    att = torch.einsum("bnhj,bhje->bnhe", pr, q_(ctx, torch.bfloat16)).reshape(B, N, C)
+    ref = F.layer_norm(x + F.linear(q_(att, torch.bfloat16), lo.weight.detach(), lo.bias.detach()), (C,), g, b, eps=1e-6)
+    cu = lambda t: t.detach().to("cuda")
+    ctx16 = ops.ctx_pack(cu(ctx).contiguous())
+    ref16 = torch.zeros(B * h * 32, 64)
+    ref16[:, :32] = q_(ctx, torch.bfloat16).permute(0, 1, 3, 2).reshape(B * h * 32, 32)
+    assert torch.equal(ctx16.float().cpu(), ref16)
+    y = ops.attn_out_fused(x.to("cuda", torch.bfloat16), cu(lq.weight).to(torch.bfloat16), cu(lq.bias), ctx16,
+                           cu(lo.weight).to(torch.bfloat16), cu(lo.bias), cu(g), cu(b), h)
+    assert y.shape == (B, N, C)
+    assert rel_err(y.float(), ref) < TOL[torch.bfloat16]
