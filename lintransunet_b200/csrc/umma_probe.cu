@@ -1,0 +1,94 @@
+// Hardware probe (not on the product path): does a K-major SWIZZLE_128B UMMA operand descriptor accept a start
+// address that is not 1024-byte aligned and a stride between 8-row groups (SBO) that is not a multiple of
+// 1024 bytes?  This is what a shared-memory HALO needs: the A rows of filter tap (kh,kw,kd) are the halo rows
+// shifted by a constant, and consecutive 8-row groups of the 4x4x8 output tile are (8+2) halo rows apart.
+//
+//   halo  : R rows x 128 B (64 bf16), written by ONE TMA box load with SWIZZLE_128B
+//   A     : rows r = 8g + i  <->  halo row  off + g * sbo_rows + i      (M = 128)
+//   B     : [64][64] bf16, TMA SWIZZLE_128B
+//   out   : fp32 [128][64] = A . B^T
+#include <cuda.h>
+
+#include "tc_common.cuh"
+
+namespace ltu {
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_w, float* out,
+                  int R, int off_rows, int sbo_rows, int use_base_offset) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t bar_full, bar_done;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t sa = smem_u32(smem), sb = sa + 256 * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bar_full), 1);
+        mbar_init(smem_u32(&bar_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(smem_u32(&bar_full), (uint32_t)(R * 128 + 64 * 128));
+        tma_load_2d(sa, &tm_g, 0, 0, smem_u32(&bar_full));
+        tma_load_2d(sb, &tm_w, 0, 0, smem_u32(&bar_full));
+        mbar_wait(smem_u32(&bar_full), 0);
+        tc_fence_after();
+        const uint32_t start = sa + (uint32_t)off_rows * 128u;
+        uint64_t adesc = 0;
+        adesc |= (uint64_t)((start & 0x3FFFF) >> 4);
+        adesc |= (uint64_t)1 << 16;
+        adesc |= (uint64_t)(((uint32_t)sbo_rows * 128u) >> 4) << 32;
+        adesc |= (uint64_t)1 << 46;
+        if (use_base_offset) adesc |= (uint64_t)((start >> 7) & 7) << 49;
+        adesc |= (uint64_t)2 << 61;
+        const uint64_t bdesc = make_desc(sb);
+        const uint32_t idesc = umma_idesc_bf16(128, 64);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k != 0);
+        umma_commit(smem_u32(&bar_done));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bar_done), 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        for (int i = 0; i < 32; ++i) out[row * 64 + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+    }
+}
+
+}  // namespace ltu
+
+using namespace ltu;
+
+// g bf16 [R][64] (R <= 256), w bf16 [64][64], out fp32 [128][64]
+extern "C" int ltu_debug_umma_probe(const void* g, int R, const void* w, float* out, int off_rows, int sbo_rows,
+                                    int use_base_offset, ltu_stream_t stream) {
+    LTU_ARG_CHECK(g && w && out && R > 0 && R <= 256, "umma_probe: bad arguments");
+    LTU_ARG_CHECK(off_rows >= 0 && sbo_rows > 0 && off_rows + 15 * sbo_rows + 8 <= R, "umma_probe: rows out of the halo");
+    CUtensorMap tg, tw;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(&tg, g, (uint64_t)R, 64, (uint32_t)R)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&tw, w, 64, 64, 64)) != LTU_OK) return rc;
+    const size_t smem = 1024 + 256 * 128 + 64 * 128;
+    cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tg, tw, out, R, off_rows, sbo_rows, use_base_offset);
+    LTU_LAUNCH_CHECK("umma_probe");
+    return LTU_OK;
+}

@@ -1,0 +1,27 @@
+"""Which shared-memory HALO addressing does a SWIZZLE_128B UMMA operand descriptor accept on B200?
+Prints, per (start row offset, rows between 8-row groups, base_offset field), whether A . B^T is exact."""
+import sys
+from ctypes import c_void_p
+
+import torch
+
+sys.path.insert(0, ".")
+from lintransunet_b200 import _native  # noqa: E402
+
+torch.manual_seed(0)
+R = 256
+g = torch.randint(-4, 5, (R, 64), device="cuda").to(torch.bfloat16)
+w = torch.randint(-2, 3, (64, 64), device="cuda").to(torch.bfloat16)
+out = torch.empty(128, 64, device="cuda")
+P = lambda t: c_void_p(t.data_ptr())
+for off, sbo in ((0, 8), (8, 8), (1, 8), (3, 8), (0, 10), (2, 10), (5, 10), (11, 10), (0, 16), (7, 12)):
+    rows = torch.tensor([off + (r // 8) * sbo + r % 8 for r in range(128)], device="cuda")
+    ref = g[rows].float() @ w.float().t()
+    res = []
+    for ubo in (0, 1):
+        out.zero_()
+        rc = _native.lib().ltu_debug_umma_probe(P(g), R, P(w), P(out), off, sbo, ubo, c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        bad = (out != ref).any(dim=1)
+        res.append("exact" if rc == 0 and not bad.any() else f"rc={rc} wrong rows {int(bad.sum())}/128 (first {int(bad.nonzero()[0]) if bad.any() else -1})")
+    print(f"start row {off:2d}, group stride {sbo:2d} rows: base_offset=0 -> {res[0]}; base_offset=(addr>>7)&7 -> {res[1]}", flush=True)
