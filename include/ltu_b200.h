@@ -105,6 +105,22 @@ int ltu_conv3d_tc(const void* in0, int C0, const void* in1, int C1, int B, int H
                   const float* bias, int Cout, void* out, int out_f32, int Ho, int Wo, int Do,
                   float* partials, int n_aux, float* aux_out, ltu_stream_t stream);
 
+/* Third-generation tensor-core convolution: TMA-loaded shared-memory halo + tcgen05 (conv_tc3.cu).  Same
+ * results contract as ltu_conv3d_tc for stride-1 3x3x3 convolutions (pad 1) of bf16 activations with C0 >= 64,
+ * C0 % 64 == 0, C1 % 64 == 0, Cout % 8 == 0, Cout <= 128, bf16 output, optional fp32 auxiliary head (n_aux extra
+ * weight rows, as in ltu_conv3d_tc); up2 = the folded nearest-x2 upsample (Cout <= 32 only: wider folded layers
+ * measured faster on the im2col kernel).  A CTA owns TH x 16 x 8 output voxels (TH = 1, 2 or 4); one 5-D TMA box brings the
+ * (TH+2) x 18 x 10 halo of a 64-channel slice (each input voxel is fetched 2-4x instead of 27x) and every
+ * filter tap reads it through a shifted UMMA descriptor.  weight_bf16 = the ltu_conv3d_tc packing with weight_rows = Cout + n_aux rounded up to 32
+ * ([rows][Kpad], folded: [8][rows][Kpad]).  partials: [B][ltu_conv3d_tc3_tiles(B,Hi,Wi,Di,Cout,n_aux,up2)][Cout][2].   */
+int ltu_conv3d_tc3_supported(int C0, int C1, int Cout, int ksize, int sh, int sw, int sd, int pad,
+                             int up2, int out_f32, int n_aux);
+int ltu_conv3d_tc3_tiles(int B, int Hi, int Wi, int Di, int Cout, int n_aux, int up2);
+int ltu_conv3d_tc3(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di,
+                   int up2, const void* weight_bf16, int weight_rows, int Kpad, const float* bias,
+                   int Cout, void* out, float* partials, int n_aux, float* aux_out,
+                   ltu_stream_t stream);
+
 /* nn.Linear on a bf16 token matrix with a fused epilogue (model/trans_block.py:166,:187-189,:205-210),
  * run by the persistent tcgen05 kernel (a 1x1x1 "convolution"):  y = epi(x W^T + b)
  *   x bf16 [rows][Cin], Cin a power of two in [8,1024]; weight_bf16 = the ltu_conv3d_tc packing of the

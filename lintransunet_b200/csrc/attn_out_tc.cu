@@ -131,9 +131,9 @@ attn_out128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const uint64_t adesc = make_desc(xs + kb * 16384), bdesc = make_desc(sbase + kAoOffWq + kb * 16384);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_base + (uint32_t)(b * 256), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idescQ, (kb | k) != 0);
+                umma_bf16_elect(tmem_base + (uint32_t)(b * 256), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idescQ, (kb | k) != 0);
         }
-        umma_commit(smem_u32(&tail->q_full[b]));
+        umma_commit_elect(smem_u32(&tail->q_full[b]));
     };
 
     if (role == 0) {
@@ -220,7 +220,7 @@ attn_out128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         }
     } else {
         // =========================== group B: MMA issue + residual + LayerNorm ===========================
-        if (e == 4 && lane == 0) {
+        if (e == 4) {                                          // whole warp: warp-uniform MMA issue, one elected lane
             mbar_wait(smem_u32(&tail->w_full), 0);
             mbar_wait(smem_u32(&tail->x_full[0]), 0);
             gemm_q(0);
@@ -229,7 +229,7 @@ attn_out128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         __syncwarp();
         for (int a = 0; a < n_my; a += 2) {
             // ---- issue duties of this pair, spread over single lanes of different warps
-            if (e == 0 && lane == 0) {                          // GATT(a), GATT(b): one N=32 GEMM per head
+            if (e == 0) {                                       // GATT(a), GATT(b): one N=32 GEMM per head
                 for (int t = a; t < a + 2 && t < n_my; ++t) {
                     const int b = t & 1;
                     const uint32_t ph = (t >> 1) & 1;
@@ -242,13 +242,13 @@ attn_out128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         const uint64_t bdesc = make_desc(sbase + kAoOffC + b * kAoCBytes + h * 4096);
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks)
-                            umma_bf16_ts(tacc + (uint32_t)(128 + 32 * h), tacc + (uint32_t)(32 * h + 8 * ks),
-                                         bdesc + (uint64_t)(ks * 2), idescA, ks != 0);
+                            umma_bf16_ts_elect(tacc + (uint32_t)(128 + 32 * h), tacc + (uint32_t)(32 * h + 8 * ks),
+                                               bdesc + (uint64_t)(ks * 2), idescA, ks != 0);
                     }
-                    umma_commit(smem_u32(&tail->att_full[b]));
+                    umma_commit_elect(smem_u32(&tail->att_full[b]));
                 }
             }
-            if ((e == 1 || e == 2) && lane == 0) {              // GO(a) by warp 9, GO(b) by warp 10
+            if (e == 1 || e == 2) {                             // GO(a) by warp 9, GO(b) by warp 10
                 const int t = a + (e - 1);
                 if (t < n_my) {
                     const int b = t & 1;
@@ -259,9 +259,9 @@ attn_out128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const uint64_t bdesc = make_desc(sbase + kAoOffWo + (k >> 2) * 16384) + (uint64_t)((k & 3) * 2);
-                        umma_bf16_ts(tacc, tacc + 128 + (uint32_t)(k < 4 ? 8 * k : 64 + 8 * (k - 4)), bdesc, idescQ, k != 0);
+                        umma_bf16_ts_elect(tacc, tacc + 128 + (uint32_t)(k < 4 ? 8 * k : 64 + 8 * (k - 4)), bdesc, idescQ, k != 0);
                     }
-                    umma_commit(smem_u32(&tail->o_full[b]));
+                    umma_commit_elect(smem_u32(&tail->o_full[b]));
                 }
             }
             __syncwarp();
@@ -289,7 +289,7 @@ attn_out128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     tmem_ld_wait();
                     tc_fence_before();
                     mbar_arrive(smem_u32(&tail->r1_free[b]));
-                    if (e == 4 && lane == 0 && t + 2 < n_my) {  // GQ of tile t+2 into the drained R1
+                    if (e == 4 && t + 2 < n_my) {               // GQ of tile t+2 into the drained R1 (whole warp, elected issue)
                         mbar_wait(smem_u32(&tail->r1_free[b]), ph);
                         mbar_wait(smem_u32(&tail->x_full[b]), ph ^ 1);
                         tc_fence_after();

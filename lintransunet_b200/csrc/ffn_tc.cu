@@ -146,9 +146,9 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
             const uint64_t adesc = make_desc(xslot + kb * 16384), bdesc = make_desc(sbase + kFfnOffW1 + kb * 32768);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_base + (uint32_t)(b * 256), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
+                umma_bf16_elect(tmem_base + (uint32_t)(b * 256), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
         }
-        umma_commit(smem_u32(&tail->acc1_full[b]));
+        umma_commit_elect(smem_u32(&tail->acc1_full[b]));
     };
 
     if (role == 0) {
@@ -211,7 +211,7 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
         }
     } else {
         // =========================== e2: residual + LayerNorm warps ===========================
-        if (leader) {
+        if (e == 0) {                                          // whole warp: the MMA issue is warp-uniform, one elected lane issues
             mbar_wait(smem_u32(&tail->w_full), 0);
             mbar_wait(smem_u32(&tail->x_full[0]), 0);
             gemm1(0);
@@ -230,7 +230,7 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) res[j] = (p.mode & 16) ? make_uint4(0, 0, 0, 0) : __ldg(src + j);
             }
-            if (leader) {                                       // GEMM2 as soon as the GELU group has published H
+            if (e == 0) {                                       // GEMM2 as soon as the GELU group has published H
                 const uint32_t tacc = tmem_base + (uint32_t)(b * 256);
                 mbar_wait_sleep(smem_u32(&tail->h_full[b]), ph, 32);
                 tc_fence_after();
@@ -241,11 +241,11 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {              // hidden [16k, 16k+16): packed at TMEM (k>>3)*128 + (k&7)*8
                         const uint64_t bdesc = make_desc(sbase + kFfnOffW2 + (k >> 2) * 16384 + nh * 8192) + (uint64_t)((k & 3) * 2);
-                        umma_bf16_ts(tacc + (uint32_t)(64 + 128 * nh), tacc + (uint32_t)((k >> 3) * 128 + (k & 7) * 8),
-                                     bdesc, idesc2, k != 0);
+                        umma_bf16_ts_elect(tacc + (uint32_t)(64 + 128 * nh), tacc + (uint32_t)((k >> 3) * 128 + (k & 7) * 8),
+                                           bdesc, idesc2, k != 0);
                     }
                 }
-                umma_commit(smem_u32(&tail->acc2_full[b]));
+                umma_commit_elect(smem_u32(&tail->acc2_full[b]));
             }
             __syncwarp();
             stamp(t, 0);
@@ -260,7 +260,7 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&tail->buf_free[b]));
-                if (e == 4 && lane == 0 && t + 2 < n_my) {      // GEMM1 of tile t+2 into the drained buffer
+                if (e == 4 && t + 2 < n_my) {                   // GEMM1 of tile t+2 into the drained buffer (whole warp, elected issue)
                     mbar_wait(smem_u32(&tail->buf_free[b]), ph);
                     stamp(t, 2);
                     mbar_wait(smem_u32(&tail->x_full[b]), ph ^ 1);

@@ -19,6 +19,7 @@ from ._native import check
 F32, BF16 = 0, 1
 ACT_NONE, ACT_LRELU = 0, 1
 USE_HALO_CONV = os.environ.get("LTU_DISABLE_HALO", "0") != "1"     # A/B switch for the small-channel conv kernel
+USE_TC3_CONV = os.environ.get("LTU_DISABLE_TC3", "0") != "1"       # A/B switch for the TMA-halo tcgen05 conv kernel
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -205,12 +206,18 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     use_halo = (USE_HALO_CONV and w_tc is not None and not up2 and x0.dtype == torch.bfloat16
                 and (out_f32 or cout % 2 == 0) and w_tc.shape[0] >= (32 if ctot > 16 else 16)
                 and L.ltu_conv3d_halo_supported(C0, C1, ctot, ksize, stride[0], stride[1], stride[2], pad, 0) == 1)
+    # stride-1 3x3x3 with >= 64 channels per input: TMA halo + tcgen05 (conv_tc3.cu)
+    use_tc3 = (use_tc and not use_halo and USE_TC3_CONV and w_tc.shape[-2] % 32 == 0
+               and L.ltu_conv3d_tc3_supported(C0, C1, cout, ksize, stride[0], stride[1], stride[2], pad, int(up2),
+                                              int(out_f32), n_aux) == 1)
     if n_aux and not (use_tc or use_halo):
         raise RuntimeError("a fused auxiliary head needs the bf16 tensor-core path (tcgen05 or halo kernel)")
     aux = torch.empty(B, Ho, Wo, Do, n_aux, dtype=torch.float32, device=dev) if n_aux else None
     out = torch.empty(B, Ho, Wo, Do, cout, dtype=torch.float32 if out_f32 else x0.dtype, device=dev)
     if use_halo:
         tiles = L.ltu_conv3d_halo_tiles(Ho, Wo, Do, C0 + C1)
+    elif use_tc3:
+        tiles = L.ltu_conv3d_tc3_tiles(B, Hi, Wi, Di, cout, n_aux, int(up2))
     else:
         tiles = L.ltu_conv3d_tc_tiles(V, int(up2)) if use_tc else L.ltu_conv3d_tiles(V, cout)
     partials = torch.empty(B, tiles, cout, 2, dtype=torch.float32, device=dev) if want_stats else None
@@ -223,6 +230,9 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
         if use_halo:
             check(L.ltu_conv3d_halo(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, ksize, _p(w_tc), w_tc.shape[1], _p(bias),
                                     cout, _p(out), int(out_f32), _p(partials), n_aux, _p(aux), st), "ltu_conv3d_halo")
+        elif use_tc3:
+            check(L.ltu_conv3d_tc3(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), _p(w_tc), w_tc.shape[-2], w_tc.shape[-1],
+                                   _p(bias), cout, _p(out), _p(partials), n_aux, _p(aux), st), "ltu_conv3d_tc3")
         elif use_tc:
             check(L.ltu_conv3d_tc(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, int(up2), ksize, stride[0], stride[1],
                                   stride[2], pad, _p(w_tc), _p(bias), cout, _p(out), int(out_f32), Ho, Wo, Do,

@@ -179,6 +179,15 @@ CONV_CASES = [
     (128, 128, 128, 3, (1, 1, 1), False, (3, 4, 4), False),
     (128, 0, 32, 3, (1, 1, 1), True, (3, 4, 5), False),        # up_embed: nearest x2 folded in
     (32, 0, 128, 3, (2, 2, 2), False, (10, 6, 8), False),      # down_embed
+    # TMA halo + tcgen05 kernel (conv_tc3.cu): stride-1 3x3x3, >= 64 channels per input, ragged tiles in every axis
+    (64, 0, 64, 3, (1, 1, 1), False, (9, 17, 5), False),
+    (256, 0, 128, 3, (1, 1, 1), False, (8, 8, 20), False),      # decoder level 0: D is the 16-axis
+    (128, 0, 64, 3, (1, 1, 1), False, (5, 33, 9), False),
+    (64, 64, 64, 3, (1, 1, 1), False, (6, 7, 18), False),       # cat(x, skip)
+    (64, 0, 32, 3, (1, 1, 1), False, (4, 4, 8), False),         # exactly one tile
+    (256, 0, 64, 3, (1, 1, 1), True, (5, 3, 9), False),         # folded up_embed, 2 classes per pass
+    (256, 0, 128, 3, (1, 1, 1), True, (3, 5, 4), False),        # folded up_embed, 1 class per pass
+    (128, 0, 32, 3, (1, 1, 1), True, (6, 18, 10), False),       # folded up_embed, 4 classes per pass, several tiles
 ]
 
 

@@ -21,10 +21,13 @@ cap() {  # name regex skip count
 }
 # per forward the attention kernels run 32 times: bottleneck (8), bridge 3 (8), bridge 2 (8), bridge 1 (8)
 cap kv "kv_reduce_mma_kernel" 56 2           # second forward, bridge 1: N=57408 tokens, C=128
-cap q "q_readout_mma_kernel" 56 2
+cap q "q_readout_mma_kernel" 40 2            # bridge 2 (bridge 1's readout lives in attn_out128_kernel): N=10752, C=256
 cap kv8 "kv_reduce_mma_kernel" 48 1          # bridge 2: N=10752, C=256
+cap ffn "ffn128_kernel" 8 1                  # fused FFN half, bridge 1 (8 launches per forward)
+cap attnout "attn_out128_kernel" 8 1         # fused query half, bridge 1
 if [ "${NCU_SKIP_CONV:-0}" != "1" ]; then
-cap tc "conv3d_tc2_kernel|conv3d_tc_kernel" 30 6   # six tensor-core conv launches of the second forward
+cap tc "conv3d_tc2_kernel|conv3d_tc_kernel" 20 6   # six im2col tensor-core conv launches of the second forward
+cap tc3 "conv3d_tc3_kernel" 12 6             # six TMA-halo tensor-core conv launches of the second forward
 cap halo "conv3d_halo_kernel" 9 3
 fi
 ls -la $OUT | tail -30

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GP = os.path.join(ROOT, "gpurun_out")
 PR = os.path.join(ROOT, "profiles")
 
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+KEYS = ["gpu__time_duration.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
@@ -81,7 +81,11 @@ def main():
                 "Target: tools/ncu_target.py (second eager forward, batch 8 x 128^3, bf16).  Raw exports: "
                 f"`{a.round}_prof_*_raw.csv`.\n")
     for name, title in (("kv", "kv_reduce (bridge 1: B=8, N=57408, C=128, 4 heads)"), ("kv8", "kv_reduce (bridge 2: N=10752, C=256, 8 heads)"),
-                        ("q", "q_readout (bridge 1)"), ("tc", "conv3d_tc (tcgen05 implicit GEMM)"), ("halo", "conv3d_halo (smem halo + mma.sync)")):
+                        ("q", "q_readout (bridge 2: N=10752, C=256; bridge 1 runs inside attn_out128_kernel)"),
+                        ("ffn", "ffn128_kernel (fused FFN half, bridge 1: 459264 rows, d_model 128)"),
+                        ("attnout", "attn_out128_kernel (fused query half, bridge 1)"),
+                        ("tc3", "conv3d_tc3 (TMA halo + tcgen05)"),
+                        ("tc", "conv3d_tc (tcgen05 implicit GEMM, im2col per tap)"), ("halo", "conv3d_halo (smem halo + mma.sync)")):
         raw = os.path.join(GP, f"prof_{name}_raw.csv")
         if os.path.exists(raw):
             shutil.copy(raw, os.path.join(PR, f"{a.round}_prof_{name}_raw.csv"))
