@@ -352,15 +352,21 @@ static EncodeTiledFn encode_fn() {
 
 // Row-major bf16 matrix [rows][cols] -> map with a [box_rows x 64-column] box, SWIZZLE_128B (the K-major UMMA
 // operand layout); out-of-range rows read as zeros and are not written.
+int make_tmap_bf16_2d_w(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    return make_tmap_bf16_2d_w(map, base, rows, cols, box_rows, 64);
+}
+// box_cols in {16, 32, 64}: 32- / 64- / 128-byte rows with the matching TMA swizzle
+int make_tmap_bf16_2d_w(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LTU_ERR_ARG; }
     const cuuint64_t gdim[2] = {cols, rows};
     const cuuint64_t gstride[1] = {cols * 2};
-    const cuuint32_t box[2] = {64, box_rows};
+    const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return LTU_ERR_ARG; }
     return LTU_OK;

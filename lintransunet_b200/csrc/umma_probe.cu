@@ -13,16 +13,18 @@
 
 namespace ltu {
 
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+int make_tmap_bf16_2d_w(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 
 __global__ void __launch_bounds__(128, 1)
 umma_probe_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_w, float* out,
-                  int R, int off_rows, int sbo_rows, int use_base_offset) {
+                  int R, int off_rows, int sbo_rows, int use_base_offset, int CW) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t bar_full, bar_done;
     __shared__ uint32_t tmem_slot;
     const uint32_t sa = smem_u32(smem), sb = sa + 256 * 128;
+    const uint32_t RB = (uint32_t)CW * 2u;                         // row bytes: 128 / 64 / 32 <-> SWIZZLE_128B / 64B / 32B
+    const uint64_t layout = CW == 64 ? 2 : (CW == 32 ? 4 : 6);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&bar_full), 1);
@@ -38,22 +40,22 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     if (threadIdx.x == 0) {
-        mbar_expect_tx(smem_u32(&bar_full), (uint32_t)(R * 128 + 64 * 128));
+        mbar_expect_tx(smem_u32(&bar_full), (uint32_t)(R + 64) * RB);
         tma_load_2d(sa, &tm_g, 0, 0, smem_u32(&bar_full));
         tma_load_2d(sb, &tm_w, 0, 0, smem_u32(&bar_full));
         mbar_wait(smem_u32(&bar_full), 0);
         tc_fence_after();
-        const uint32_t start = sa + (uint32_t)off_rows * 128u;
+        const uint32_t start = sa + (uint32_t)off_rows * RB;
         uint64_t adesc = 0;
         adesc |= (uint64_t)((start & 0x3FFFF) >> 4);
         adesc |= (uint64_t)1 << 16;
-        adesc |= (uint64_t)(((uint32_t)sbo_rows * 128u) >> 4) << 32;
+        adesc |= (uint64_t)(((uint32_t)sbo_rows * RB) >> 4) << 32;
         adesc |= (uint64_t)1 << 46;
         if (use_base_offset) adesc |= (uint64_t)((start >> 7) & 7) << 49;
-        adesc |= (uint64_t)2 << 61;
-        const uint64_t bdesc = make_desc(sb);
+        adesc |= layout << 61;
+        uint64_t bdesc = (uint64_t)((sb & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((8u * RB) >> 4) << 32) | ((uint64_t)1 << 46) | (layout << 61);
         const uint32_t idesc = umma_idesc_bf16(128, 64);
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k != 0);
+        for (int k = 0; k < CW / 16; ++k) umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k != 0);
         umma_commit(smem_u32(&bar_done));
     }
     __syncwarp();
@@ -77,18 +79,18 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constan
 
 using namespace ltu;
 
-// g bf16 [R][64] (R <= 256), w bf16 [64][64], out fp32 [128][64]
+// g bf16 [R][CW] (R <= 256), w bf16 [64][CW], out fp32 [128][64]; CW = 64, 32 or 16 channels per row
 extern "C" int ltu_debug_umma_probe(const void* g, int R, const void* w, float* out, int off_rows, int sbo_rows,
-                                    int use_base_offset, ltu_stream_t stream) {
-    LTU_ARG_CHECK(g && w && out && R > 0 && R <= 256, "umma_probe: bad arguments");
+                                    int use_base_offset, int CW, ltu_stream_t stream) {
+    LTU_ARG_CHECK(g && w && out && R > 0 && R <= 256 && (CW == 64 || CW == 32 || CW == 16), "umma_probe: bad arguments");
     LTU_ARG_CHECK(off_rows >= 0 && sbo_rows > 0 && off_rows + 15 * sbo_rows + 8 <= R, "umma_probe: rows out of the halo");
     CUtensorMap tg, tw;
     int rc;
-    if ((rc = make_tmap_bf16_2d(&tg, g, (uint64_t)R, 64, (uint32_t)R)) != LTU_OK) return rc;
-    if ((rc = make_tmap_bf16_2d(&tw, w, 64, 64, 64)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_2d_w(&tg, g, (uint64_t)R, (uint64_t)CW, (uint32_t)R, (uint32_t)CW)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_2d_w(&tw, w, 64, (uint64_t)CW, 64, (uint32_t)CW)) != LTU_OK) return rc;
     const size_t smem = 1024 + 256 * 128 + 64 * 128;
     cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tg, tw, out, R, off_rows, sbo_rows, use_base_offset);
+    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tg, tw, out, R, off_rows, sbo_rows, use_base_offset, CW);
     LTU_LAUNCH_CHECK("umma_probe");
     return LTU_OK;
 }

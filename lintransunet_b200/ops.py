@@ -207,9 +207,11 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
                 and (out_f32 or cout % 2 == 0) and w_tc.shape[0] >= (32 if ctot > 16 else 16)
                 and L.ltu_conv3d_halo_supported(C0, C1, ctot, ksize, stride[0], stride[1], stride[2], pad, 0) == 1)
     # stride-1 3x3x3 with >= 64 channels per input: TMA halo + tcgen05 (conv_tc3.cu)
-    use_tc3 = (use_tc and not use_halo and USE_TC3_CONV and w_tc.shape[-2] % 32 == 0
+    use_tc3 = (use_tc and USE_TC3_CONV and w_tc.shape[-2] % 32 == 0
                and L.ltu_conv3d_tc3_supported(C0, C1, cout, ksize, stride[0], stride[1], stride[2], pad, int(up2),
                                               int(out_f32), n_aux) == 1)
+    if use_tc3:
+        use_halo = False
     if n_aux and not (use_tc or use_halo):
         raise RuntimeError("a fused auxiliary head needs the bf16 tensor-core path (tcgen05 or halo kernel)")
     aux = torch.empty(B, Ho, Wo, Do, n_aux, dtype=torch.float32, device=dev) if n_aux else None
@@ -224,7 +226,7 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     cin = C0 + C1
     nbytes = (x0.numel() + (0 if x1 is None else x1.numel())) * x0.element_size() + out.numel() * out.element_size()
     # algorithmic flops: the un-folded count 2*k^3*Cin*Cout*B*V (the folded up2 path executes 8/27 of it)
-    prof = ("conv3d_halo" if use_halo else ("conv3d_tc" if use_tc else "conv3d"), nbytes,
+    prof = ("conv3d_halo" if use_halo else ("conv3d_tc3" if use_tc3 else ("conv3d_tc" if use_tc else "conv3d")), nbytes,
             2 * ksize ** 3 * cin * cout * B * V)
     with _Guard(dev, prof) as st:
         if use_halo:

@@ -221,8 +221,8 @@ class _ConvW:
         if want_tc and (cin & (cin - 1)) == 0 and cin >= 8 and cout <= 256:
             ktot = k * k * k * cin
             kpad = (ktot + 63) // 64 * 64
-            # rows padded to 16 (32 for the >= 64-channel layers the TMA-halo kernel takes; the other kernels read Cout16 rows)
-            rpad = 32 if (k == 3 and cin >= 64) else 16
+            # rows padded to 16 (32 for the 3x3x3 layers the TMA-halo kernel can take; the other kernels read Cout16 rows)
+            rpad = 32 if (k == 3 and cin >= 16) else 16
             wt = torch.zeros((cout + rpad - 1) // rpad * rpad, kpad, dtype=torch.bfloat16, device=w.device)
             wt[:cout, :ktot] = w.permute(0, 2, 3, 4, 1).reshape(cout, ktot).to(torch.bfloat16)
             self.w_tc = wt

@@ -270,19 +270,24 @@ def test_conv3d_halo_matches_reference_and_tc_path(case):
     ref = F.conv3d(x0 if x1 is None else torch.cat((x0, x1), 1), conv.weight.detach(), conv.bias.detach(), padding=k // 2)
     dev = lambda t: None if t is None else to_cl(t).to("cuda", torch.bfloat16)
     outs = {}
-    for halo in (True, False):
-        ops.USE_HALO_CONV = halo
+    # the three bf16 kernels that can run this layer: TMA-halo tcgen05 (default when it applies), smem-halo mma.sync, im2col tcgen05
+    import os
+    for name, halo, tc3 in (("tc3", True, True), ("halo", True, False), ("im2col", False, False)):
+        ops.USE_HALO_CONV, ops.USE_TC3_CONV = halo, tc3
+        os.environ["LTU_TC3_SMALL"] = "1" if tc3 else "0"       # let the TMA-halo kernel take 16- / 32-channel K slices
         try:
             y, partials, tiles = ops.conv3d(dev(x0), cw.w.cuda(), cw.b.cuda(), cout, k, pad=k // 2, x1=dev(x1),
                                             out_f32=out_f32, want_stats=True, w_tc=cw.w_tc.cuda())
         finally:
-            ops.USE_HALO_CONV = True
-        assert rel_err(from_cl(y.float()), ref) < (2e-5 if out_f32 else TOL[torch.bfloat16]), halo
+            ops.USE_HALO_CONV, ops.USE_TC3_CONV = True, True
+            os.environ["LTU_TC3_SMALL"] = "0"
+        assert rel_err(from_cl(y.float()), ref) < (2e-5 if out_f32 else TOL[torch.bfloat16]), name
         stats = ops.instnorm_finalize(partials, H * W * D)
-        assert rel_err(stats[..., 0], ref.mean(dim=(2, 3, 4))) < 5e-3
-        assert rel_err(stats[..., 1], 1 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5)) < 5e-3
-        outs[halo] = y.float()
-    assert rel_err(outs[True], outs[False]) < (2e-5 if out_f32 else 8e-3)
+        assert rel_err(stats[..., 0], ref.mean(dim=(2, 3, 4))) < 5e-3, name
+        assert rel_err(stats[..., 1], 1 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5)) < 5e-3, name
+        outs[name] = y.float()
+    assert rel_err(outs["halo"], outs["im2col"]) < (2e-5 if out_f32 else 8e-3)
+    assert rel_err(outs["tc3"], outs["im2col"]) < (2e-5 if out_f32 else 8e-3)
 
 
 @pytest.mark.parametrize("cin,cmain,naux,shape", [(32, 16, 3, (5, 6, 34)), (64, 32, 3, (4, 5, 9)), (256, 128, 2, (3, 4, 4)),

@@ -8,6 +8,13 @@ from lintransunet_b200 import ops  # noqa: E402
 from lintransunet_b200.unet import _ConvW  # noqa: E402
 from tools.ffn_probe import timeit  # noqa: E402
 
+SMALL = [  # the small-channel stride-1 layers (so far: smem-halo mma.sync kernel); (H, W, D) of the conv input
+    ("enc.block0.conv1 16->16", 16, 0, 16, False, (64, 64, 128)),
+    ("enc.block1.conv1 32->32", 32, 0, 32, False, (32, 32, 128)),
+    ("dec.block2.conv2 32+32->32", 32, 32, 32, False, (32, 32, 128)),
+    ("dec.block3.conv1 32->16", 32, 0, 16, False, (64, 64, 128)),
+    ("dec.block3.conv2 16+16->16", 16, 16, 16, False, (64, 64, 128)),
+]
 LAYERS = [  # name, cin, cin1, cout, up2, (H, W, D) of the conv INPUT
     ("b1.up_embed 128->32 x2", 128, 0, 32, True, (39, 23, 64)),
     ("b2.up_embed 256->64 x2", 256, 0, 64, True, (24, 14, 32)),
@@ -22,7 +29,7 @@ LAYERS = [  # name, cin, cin1, cout, up2, (H, W, D) of the conv INPUT
 ]
 B = 8
 torch.manual_seed(0)
-for name, cin, cin1, cout, up2, (H, W, D) in LAYERS:
+for name, cin, cin1, cout, up2, (H, W, D) in (SMALL + LAYERS if "--all" in sys.argv else (SMALL if "--small" in sys.argv else LAYERS)):
     conv = torch.nn.Conv3d(cin + cin1, cout, 3, padding=1)
     cw = _ConvW(conv, want_tc=True, fold_up2=up2)
     x0 = torch.randn(B, H, W, D, cin, device="cuda").to(torch.bfloat16)
@@ -40,5 +47,5 @@ for name, cin, cin1, cout, up2, (H, W, D) in LAYERS:
     ds = (res[True][2] - res[False][2]).abs().max().item()
     V = B * H * W * D * (8 if up2 else 1)
     fl = 2 * 27 * (cin + cin1) * cout * V
-    print(f"{name:32s} im2col {res[False][0]:8.1f} us | halo {res[True][0]:8.1f} us ({fl / res[True][0] / 1e6:7.0f} TFLOP/s alg.)"
+    print(f"{name:32s} before {res[False][0]:8.1f} us | tma-halo {res[True][0]:8.1f} us ({fl / res[True][0] / 1e6:7.0f} TFLOP/s alg.)"
           f" | max|dy| {dy:.4f} max|dstats| {ds:.2e}", flush=True)

@@ -10,17 +10,20 @@ from lintransunet_b200 import _native  # noqa: E402
 
 torch.manual_seed(0)
 R = 256
-g = torch.randint(-4, 5, (R, 64), device="cuda").to(torch.bfloat16)
-w = torch.randint(-2, 3, (64, 64), device="cuda").to(torch.bfloat16)
 out = torch.empty(128, 64, device="cuda")
 P = lambda t: c_void_p(t.data_ptr())
-for off, sbo in ((0, 8), (8, 8), (1, 8), (3, 8), (0, 10), (2, 10), (5, 10), (11, 10), (0, 16), (7, 12)):
+for CW in (64, 32, 16):
+  print(f"--- {CW} channels per row ({2 * CW}-byte rows, SWIZZLE_{2 * CW}B)")
+  g = torch.randint(-4, 5, (R, CW), device="cuda").to(torch.bfloat16)
+  w = torch.randint(-2, 3, (64, CW), device="cuda").to(torch.bfloat16)
+  for off, sbo in ((0, 8), (8, 8), (1, 8), (3, 8), (0, 10), (2, 10), (5, 10), (11, 10), (0, 16), (7, 12)):
+   for _ in (0,):
     rows = torch.tensor([off + (r // 8) * sbo + r % 8 for r in range(128)], device="cuda")
     ref = g[rows].float() @ w.float().t()
     res = []
     for ubo in (0, 1):
         out.zero_()
-        rc = _native.lib().ltu_debug_umma_probe(P(g), R, P(w), P(out), off, sbo, ubo, c_void_p(torch.cuda.current_stream().cuda_stream))
+        rc = _native.lib().ltu_debug_umma_probe(P(g), R, P(w), P(out), off, sbo, ubo, CW, c_void_p(torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         bad = (out != ref).any(dim=1)
         res.append("exact" if rc == 0 and not bad.any() else f"rc={rc} wrong rows {int(bad.sum())}/128 (first {int(bad.nonzero()[0]) if bad.any() else -1})")
