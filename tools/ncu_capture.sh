@@ -26,8 +26,8 @@ cap kv8 "kv_reduce_mma_kernel" 48 1          # bridge 2: N=10752, C=256
 cap ffn "ffn128_kernel" 8 1                  # fused FFN half, bridge 1 (8 launches per forward)
 cap attnout "attn_out128_kernel" 8 1         # fused query half, bridge 1
 if [ "${NCU_SKIP_CONV:-0}" != "1" ]; then
-cap tc "conv3d_tc2_kernel|conv3d_tc_kernel" 20 6   # six im2col tensor-core conv launches of the second forward
-cap tc3 "conv3d_tc3_kernel" 12 6             # six TMA-halo tensor-core conv launches of the second forward
+cap tc "conv3d_tc2_kernel|conv3d_tc_kernel" 16 6   # six im2col tensor-core conv launches of the second forward
+cap tc3 "conv3d_tc3_kernel" 8 6              # six TMA-halo tensor-core conv launches of the second forward
 cap halo "conv3d_halo_kernel" 9 3
 fi
 ls -la $OUT | tail -30
