@@ -278,6 +278,9 @@ chan_partials_kernel(const T* __restrict__ x, float* __restrict__ partials, int6
     }
 }
 
+// The grid stride (gridDim.x * 256 vectors) is a multiple of the vectors per voxel (C / VN in {1,2,4,...,32}), so a thread
+// always handles the same channel group: (mean, rstd) live in registers and the loop body is two 16-byte loads, the
+// arithmetic and one 16-byte store, two independent iterations in flight.
 template <typename T>
 __global__ void __launch_bounds__(256)
 instnorm_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const T* __restrict__ res,
@@ -287,26 +290,57 @@ instnorm_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, 
     const int cv = C / VN;
     const int64_t total = V * cv;
     const float* st = stats + (int64_t)b * C * 2;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        int c0 = (int)(idx % cv) * VN;
-        int64_t off = ((int64_t)b * V) * C + idx * VN;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool fixed = (stride % cv) == 0;                    // true for every launch of the wrapper (256 % cv == 0)
+    float mean[VN], rstd[VN];
+    {
+        const int c0 = (int)(first % cv) * VN;
+#pragma unroll
+        for (int i = 0; i < VN; ++i) { mean[i] = __ldg(st + (c0 + i) * 2); rstd[i] = __ldg(st + (c0 + i) * 2 + 1); }
+    }
+    const T* xb = x + (int64_t)b * V * C;
+    const T* rb = res != nullptr ? res + (int64_t)b * V * C : nullptr;
+    T* yb = y + (int64_t)b * V * C;
+    auto body = [&](int64_t idx, const float (&v_in)[VN], const float (&r_in)[VN]) {
         float v[VN];
-        load_vec(x + off, v);
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
-            float mean = __ldg(st + (c0 + i) * 2), rstd = __ldg(st + (c0 + i) * 2 + 1);
-            float t = (v[i] - mean) * rstd;
+            float t = (v_in[i] - mean[i]) * rstd[i];
             if (act == LTU_ACT_LRELU) t = t > 0.f ? t : 0.01f * t;
-            v[i] = t;
+            v[i] = t + r_in[i];
         }
-        if (res != nullptr) {
-            float r[VN];
-            load_vec(res + off, r);
+        store_vec(yb + idx * VN, v);
+    };
+    int64_t idx = first;
+    if (fixed) {
+        for (; idx + stride < total; idx += 2 * stride) {
+            float v0[VN], v1[VN], r0[VN], r1[VN];
+            load_vec(xb + idx * VN, v0);
+            load_vec(xb + (idx + stride) * VN, v1);
+            if (rb != nullptr) { load_vec(rb + idx * VN, r0); load_vec(rb + (idx + stride) * VN, r1); }
+            else {
 #pragma unroll
-            for (int i = 0; i < VN; ++i) v[i] += r[i];
+                for (int i = 0; i < VN; ++i) { r0[i] = 0.f; r1[i] = 0.f; }
+            }
+            body(idx, v0, r0);
+            body(idx + stride, v1, r1);
         }
-        store_vec(y + off, v);
+    }
+    for (; idx < total; idx += stride) {
+        if (!fixed) {
+            const int c0 = (int)(idx % cv) * VN;
+#pragma unroll
+            for (int i = 0; i < VN; ++i) { mean[i] = __ldg(st + (c0 + i) * 2); rstd[i] = __ldg(st + (c0 + i) * 2 + 1); }
+        }
+        float v0[VN], r0[VN];
+        load_vec(xb + idx * VN, v0);
+        if (rb != nullptr) load_vec(rb + idx * VN, r0);
+        else {
+#pragma unroll
+            for (int i = 0; i < VN; ++i) r0[i] = 0.f;
+        }
+        body(idx, v0, r0);
     }
 }
 
