@@ -294,15 +294,29 @@ add_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ r, const flo
     }
 }
 
+template <typename T> __device__ __forceinline__ float gelu_of(float v);
+template <> __device__ __forceinline__ float gelu_of<float>(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+template <> __device__ __forceinline__ float gelu_of<bf16>(float v) { return gelu_erf(v); }   // |error| 3e-7, then rounded to bf16
+
 template <typename T>
 __global__ void __launch_bounds__(256) gelu_kernel(T* __restrict__ x, int64_t nvec) {
     constexpr int VN = Vec<T>::N;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < nvec; i += 2 * stride) {              // two independent 16-byte vectors in flight
+        float a[VN], b[VN];
+        load_vec(x + i * VN, a);
+        load_vec(x + (i + stride) * VN, b);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) { a[k] = gelu_of<T>(a[k]); b[k] = gelu_of<T>(b[k]); }
+        store_vec(x + i * VN, a);
+        store_vec(x + (i + stride) * VN, b);
+    }
+    for (; i < nvec; i += stride) {
         float v[VN];
         load_vec(x + i * VN, v);
 #pragma unroll
-        for (int k = 0; k < VN; ++k) v[k] = 0.5f * v[k] * (1.f + erff(v[k] * 0.70710678118654752f));
+        for (int k = 0; k < VN; ++k) v[k] = gelu_of<T>(v[k]);
         store_vec(x + i * VN, v);
     }
 }

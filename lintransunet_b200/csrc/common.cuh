@@ -89,6 +89,25 @@ __device__ __forceinline__ void store4(bf16* p, const float (&r)[4]) {
     *reinterpret_cast<uint2*>(p) = v;
 }
 
+// erf-based GELU, x * Phi(x), with erfc from Abramowitz & Stegun 7.1.28
+//   erfc(z) = (1 + a1 z + ... + a6 z^6)^-16,  |error| <= 3e-7   (z = |x| / sqrt(2), folded into the a_k)
+// gelu(x) = max(x,0) - |x| erfc(z) / 2.  The 16th power goes to the MUFU pipe, p^-16 = ex2(-16 lg2 p), and every
+// multiply-add has an immediate operand: 6 FFMA + 2 FMUL + 1 FFMA on the FMA pipe, 2 MUFU, 1 FMNMX, no branches.
+// Used where the result is rounded to bf16 (the fp32 path keeps erff).
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x);
+    float p = fmaf(z, 0.0000430638f * 0.125f, 0.0002765672f * 0.17677669529663687f);
+    p = fmaf(p, z, 0.0001520143f * 0.25f);
+    p = fmaf(p, z, 0.0092705272f * 0.35355339059327373f);
+    p = fmaf(p, z, 0.0422820123f * 0.5f);
+    p = fmaf(p, z, 0.0705230784f * 0.70710678118654752f);
+    p = fmaf(p, z, 1.0f);
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(p));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -16.f));
+    return fmaf(-0.5f * z, r, fmaxf(x, 0.f));
+}
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -64,25 +64,7 @@ struct FfnParams {
     long long* trace;       // debug: [2 roles][64 tiles][8 events] clock64 stamps of CTA 0 (nullptr = off)
 };
 
-// erf-based GELU, x * Phi(x), with erfc from Abramowitz & Stegun 7.1.28
-//   erfc(z) = (1 + a1 z + ... + a6 z^6)^-16,  |error| <= 3e-7   (z = |x| / sqrt(2), folded into the a_k)
-// gelu(x) = max(x,0) - |x| erfc(z) / 2.  The epilogue is bound by the fp32 FMA pipe, so the 16th power goes
-// to the (idle) MUFU pipe, p^-16 = ex2(-16 lg2 p), and every multiply-add has an immediate operand:
-// 6 FFMA + 2 FMUL + 1 FFMA on the FMA pipe, 2 MUFU, 1 FMNMX per element, no branches.
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x);
-    float p = fmaf(z, 0.0000430638f * 0.125f, 0.0002765672f * 0.17677669529663687f);
-    p = fmaf(p, z, 0.0001520143f * 0.25f);
-    p = fmaf(p, z, 0.0092705272f * 0.35355339059327373f);
-    p = fmaf(p, z, 0.0422820123f * 0.5f);
-    p = fmaf(p, z, 0.0705230784f * 0.70710678118654752f);
-    p = fmaf(p, z, 1.0f);
-    float l, r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(p));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -16.f));
-    return fmaf(-0.5f * z, r, fmaxf(x, 0.f));
-}
-
+// gelu_erf(): common.cuh (A&S 7.1.28 erfc, |error| 3e-7, 16th power on the MUFU pipe)
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
               const __grid_constant__ CUtensorMap tm_w2, const FfnParams p) {
