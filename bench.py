@@ -232,8 +232,9 @@ def run_ours(args):
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        x = vol_host.to(dev, non_blocking=True)                        # H2D of the step's input
-        _, labels = step(x)
+        # the public API takes the pinned HOST volume: it streams the rows this rank's windows touch to the device on a
+        # copy stream (H2D inside the timed region, overlapped with the first windows)
+        _, labels = step(vol_host)
         if rank == 0:
             out_host.copy_(labels[0], non_blocking=True)               # D2H of the step's result
         torch.cuda.current_stream().synchronize()
@@ -241,7 +242,12 @@ def run_ours(args):
     sync_all()
     # wall clock between two full synchronisations (every step ends with a stream sync for the D2H)
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)) / args.steps
-    h2d = vol_host.numel() * 4 * world
+    from lintransunet_b200 import sliding_window as _sw
+    h2d = _sw.last_h2d_bytes                                           # bytes this rank uploaded per step
+    if world > 1:
+        ht = torch.tensor([h2d], dtype=torch.int64, device=dev)
+        dist.all_reduce(ht)
+        h2d = int(ht.item())
     d2h = out_host.numel()
 
     if world > 1:

@@ -69,6 +69,17 @@ def shard_windows(n_windows: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_windows, world))
 
 
+def shard_windows_contiguous(n_windows: int, rank: int, world: int) -> List[int]:
+    """Contiguous blocks in C order of (H, W, D): rank r owns a slab of the volume along H, so a rank that streams
+    the volume from host memory uploads only the rows its windows touch.  Block sizes differ by at most one."""
+    base, extra = divmod(n_windows, world)
+    lo = rank * base + min(rank, extra)
+    return list(range(lo, lo + base + (1 if rank < extra else 0)))
+
+
+last_h2d_bytes = 0      # bytes uploaded by this process in the most recent call with a host-memory input (bench.py e2e)
+
+
 def reduce_votes(votes: torch.Tensor, group=None) -> torch.Tensor:
     """Sum the per-rank uint8 vote volumes (the path's single exchange step)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -84,40 +95,80 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
                              return_labels: bool = False):
     """Same positional signature as monai.inferers.sliding_window_inference (0.7.0).
 
-    inputs: fp32 [B, 1, H, W, D] on the GPU.  Returns fp32 [B, C, H, W, D] vote fractions (what MONAI's
-    ``output_image / count_map`` yields for a one-hot predictor) or, with ``return_labels``, the
-    uint8 argmax [B, H, W, D] as well."""
+    inputs: fp32 [B, 1, H, W, D] on the GPU, or in (pinned) HOST memory: the volume is then streamed to the device in
+    slabs along H on a copy stream while the first windows are already being computed, and under torch.distributed
+    each rank owns a contiguous block of windows and uploads only the rows they touch.  Every computation runs on the
+    GPU either way.  Returns fp32 [B, C, H, W, D] vote fractions (what MONAI's ``output_image / count_map`` yields for a
+    one-hot predictor) or, with ``return_labels``, the uint8 argmax [B, H, W, D] as well."""
+    global last_h2d_bytes
     if str(mode).lower().endswith("gaussian"):
         raise NotImplementedError("only the constant blend mode used by the reference scripts is implemented")
     if not isinstance(predictor, MaskTransUnet):
         raise TypeError("predictor must be a lintransunet_b200.MaskTransUnet (eval-mode one-hot votes)")
-    if not inputs.is_cuda:
-        raise RuntimeError("sliding_window_inference runs on CUDA tensors only (no CPU fallback)")
     if inputs.dim() != 5 or inputs.shape[1] != 1:
         raise ValueError("inputs must be [B, 1, H, W, D]")
+    host_input = not inputs.is_cuda
+    if host_input:
+        if not torch.cuda.is_available():
+            raise RuntimeError("sliding_window_inference needs a CUDA device (no CPU fallback)")
+        dev = torch.device(device) if device is not None else next(predictor.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("sliding_window_inference runs on the GPU only: move the predictor to a CUDA device")
     B = inputs.shape[0]
     image_size = tuple(int(s) for s in inputs.shape[2:])
     padded, pad_before, roi, starts = scan_plan(image_size, roi_size, overlap)
+    if host_input and (padded != image_size or inputs.dtype != torch.float32):
+        inputs = inputs.to(dev, non_blocking=True)      # small / odd volumes: plain upload, then the device path
+        last_h2d_bytes = inputs.numel() * inputs.element_size()
+        host_input = False
     if padded != image_size:           # volume smaller than the window: symmetric constant pad (MONAI)
         pad = []
         for k in (2, 1, 0):
             diff = padded[k] - image_size[k]
             pad.extend([diff // 2, diff - diff // 2])
         inputs = torch.nn.functional.pad(inputs, pad, mode=padding_mode, value=cval)
-    inputs = inputs.contiguous().float()
+    if not host_input:
+        inputs = inputs.contiguous().float()
+        dev = inputs.device
     if distributed is None:
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if distributed else (0, 1)
-    mine = shard_windows(len(starts), rank, world)
+    mine = (shard_windows_contiguous if host_input else shard_windows)(len(starts), rank, world)
     C = predictor.dim_output
-    dev = inputs.device
     starts_dev = torch.tensor([starts[i] for i in mine], dtype=torch.int32, device=dev).reshape(-1, 3)
     fracs, labels_out = [], []
+    if host_input:
+        last_h2d_bytes = 0
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream(dev)
+        slab = roi[0] // 2 if roi[0] >= 2 else 1                      # rows per upload: half a window
+        src = inputs.contiguous()
     for b in range(B):
         votes = torch.zeros((C,) + padded, dtype=torch.uint8, device=dev)
-        vol = inputs[b, 0]
+        if host_input:
+            # rows [h_lo, h_hi) this rank's windows touch; uploaded in `slab`-row pieces in window order
+            h_lo = min(starts[i][0] for i in mine) if mine else 0
+            h_hi = max(starts[i][0] for i in mine) + roi[0] if mine else 0
+            vol = torch.empty(padded, dtype=torch.float32, device=dev)
+            ready = {}                                                    # last row of a piece -> event
+            copy_stream.wait_stream(main_stream)
+            with torch.cuda.stream(copy_stream):
+                for r0 in range(h_lo, h_hi, slab):
+                    r1 = min(r0 + slab, h_hi)
+                    vol[r0:r1].copy_(src[b, 0, r0:r1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    ready[r1] = ev
+                    last_h2d_bytes += (r1 - r0) * padded[1] * padded[2] * 4
+            vol.record_stream(copy_stream)
+            piece_ends = sorted(ready)
+        else:
+            vol = inputs[b, 0]
         for g0 in range(0, len(mine), sw_batch_size):
             st = starts_dev[g0:g0 + sw_batch_size].contiguous()
+            if host_input:                                                # wait for the last row this batch reads
+                need = max(starts[i][0] for i in mine[g0:g0 + sw_batch_size]) + roi[0]
+                main_stream.wait_event(ready[next(e for e in piece_ends if e >= need)])
             win = ops.gather_windows(vol, st, roi)
             lab = predictor.predict_labels(win)
             ops.vote_accumulate(lab, st, votes)

@@ -87,3 +87,12 @@ def test_two_rank_vote_reduce_equals_single_rank_and_oracle():
     frac = single.astype(np.float32) / single.sum(0, keepdims=True).astype(np.float32)
     ref = OSW.sliding_window_inference(vol[None, None], (16, 16, 16), 4, _fake_predictor, overlap=0.5)[0].numpy()
     assert np.allclose(frac, ref, atol=1e-6)
+
+
+def test_contiguous_sharding_partitions_the_windows():
+    from lintransunet_b200.sliding_window import shard_windows_contiguous
+    for n, world in [(147, 1), (147, 2), (147, 4), (147, 8), (5, 8), (0, 3)]:
+        parts = [shard_windows_contiguous(n, r, world) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+        assert all(p == list(range(p[0], p[0] + len(p))) for p in parts if p)

@@ -35,3 +35,17 @@ def test_sliding_window_matches_restated_monai_with_oracle_model():
     r2 = OSW.sliding_window_inference(small, roi, 2, lambda x: O.mask_trans_unet_forward(x, sd, cfg)["onehot"], overlap=ov)
     assert f2.shape == r2.shape == (1, 3, 64, 32, 16)
     assert float((f2.cpu() != r2).any(1).float().mean()) <= 1e-3
+
+
+def test_host_memory_input_is_streamed_and_bit_identical():
+    """A pinned host volume is uploaded slab by slab on a copy stream; votes and labels equal the device-input result."""
+    from lintransunet_b200 import MaskTransUnet, sliding_window as sw
+    torch.manual_seed(0)
+    m = MaskTransUnet([16, 32, 64, 128, 256], [100, 65, 40, 25, 10], [False, True, True, True, True], 1, 3).cuda().eval()
+    vol = torch.randn(1, 1, 160, 96, 32, generator=torch.Generator().manual_seed(2)).pin_memory()
+    roi = (64, 64, 16)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        f_dev, l_dev = sw.sliding_window_inference(vol.cuda(), roi, 4, m, overlap=0.5, return_labels=True)
+        f_host, l_host = sw.sliding_window_inference(vol, roi, 4, m, overlap=0.5, return_labels=True)
+    assert sw.last_h2d_bytes == vol.numel() * 4
+    assert torch.equal(f_dev, f_host) and torch.equal(l_dev, l_host)
