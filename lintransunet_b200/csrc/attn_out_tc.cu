@@ -48,7 +48,7 @@ constexpr uint32_t kAoOffTail = kAoOffC + 2 * kAoCBytes;
 struct AoTail {
     uint64_t w_full, x_full[2], c_full[2], q_full[2], p_full[2], att_full[2], a_full[2], o_full[2], r1_free[2];
     uint32_t tmem_slot, pad_;
-    float bq[128], bo[128], gamma[128], beta[128];
+    alignas(16) float bq[128], bo[128], gamma[128], beta[128];       // read as float4
     float2 xs[2][2][128];           // [tile parity][column half][row] = (mean, M2)
 };
 

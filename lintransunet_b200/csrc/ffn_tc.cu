@@ -50,7 +50,7 @@ constexpr uint32_t kFfnOffTail = kFfnOffX + 2 * kFfnXBytes;
 struct FfnTail {
     uint64_t w_full, x_full[2], acc1_full[2], h_full[2], acc2_full[2], buf_free[2];
     uint32_t tmem_slot, pad_;
-    float b1[256], b2[128], gamma[128], beta[128];
+    alignas(16) float b1[256], b2[128], gamma[128], beta[128];       // read as float4
     float2 xs[2][2][128];           // [tile parity][column half][row] = (mean, M2)
 };
 
@@ -358,16 +358,25 @@ int make_tmap_bf16_2d_w(CUtensorMap* map, const void* base, uint64_t rows, uint6
 
 using namespace ltu;
 
-extern "C" int ltu_ffn_fused_supported(int C) { return C == 128 ? 1 : 0; }
+namespace ltu {
+int ffn256_launch(const void* x, int64_t rows, const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
+                  const float* gamma, const float* beta, float eps, void* y, cudaStream_t stream);      // ffn256_tc.cu
+}
+
+extern "C" int ltu_ffn_fused_supported(int C) { return (C == 128 || C == 256) ? 1 : 0; }
 
 static int ffn_launch(const void* x, int64_t rows, int C, const void* w1_bf16, const float* b1, const void* w2_bf16,
                       const float* b2, const float* gamma, const float* beta, float eps, void* y, long long* trace,
                       ltu_stream_t stream, int mode = 0) {
-    LTU_ARG_CHECK(C == 128, "ffn_fused: d_model %d not supported (128)", C);
+    LTU_ARG_CHECK(C == 128 || C == 256, "ffn_fused: d_model %d not supported (128, 256)", C);
     LTU_ARG_CHECK(x && y && w1_bf16 && w2_bf16 && b1 && b2 && gamma && beta, "ffn_fused: null pointer");
     LTU_ARG_CHECK(rows > 0 && rows < ((int64_t)1 << 31) - 256, "ffn_fused: bad row count");
     LTU_ARG_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w1_bf16 & 15) == 0 &&
                   ((uintptr_t)w2_bf16 & 15) == 0, "ffn_fused: pointers must be 16-byte aligned");
+    if (C == 256) {
+        LTU_ARG_CHECK(trace == nullptr && mode == 0, "ffn_fused: the trace / ablation hooks exist for d_model 128 only");
+        return ffn256_launch(x, rows, w1_bf16, b1, w2_bf16, b2, gamma, beta, eps, y, (cudaStream_t)stream);
+    }
     CUtensorMap tx, tw1, tw2;
     int rc;
     if ((rc = make_tmap_bf16_2d(&tx, x, (uint64_t)rows, 128, 128)) != LTU_OK) return rc;

@@ -512,11 +512,11 @@ def test_linear_tc_fused_epilogues(epi, rows, cin, cout):
     assert rel_err(y.float(), ref) < TOL[torch.bfloat16]
 
 
+@pytest.mark.parametrize("C", [128, 256])
 @pytest.mark.parametrize("rows", [1, 127, 128, 129, 1000, 148 * 128 * 2 + 77, 57408])
-def test_ffn_fused(rows):
+def test_ffn_fused(rows, C):
     """Fused FFN half of the encoder layer (trans_block.py:207-210) vs fp32 torch on the same bf16-rounded operands."""
     ops = _ops()
-    C = 128
     l1, l2 = torch.nn.Linear(C, 2 * C), torch.nn.Linear(2 * C, C)
     with torch.no_grad():
         l1.weight.copy_(q_(l1.weight * 2, torch.bfloat16))

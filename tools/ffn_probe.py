@@ -21,9 +21,8 @@ def timeit(fn, n=10, warm=3):
 
 
 def main():
-    C = 128
     torch.manual_seed(0)
-    for rows in (8 * 57408, 57408, 8 * 4320):
+    for C, rows in ((128, 8 * 57408), (128, 57408), (256, 8 * 10752), (256, 8 * 4320), (256, 8 * 512)):
         x = torch.randn(rows, C, device="cuda").to(torch.bfloat16)
         w1 = (torch.randn(2 * C, C, device="cuda") * 0.1).to(torch.bfloat16)
         w2 = (torch.randn(C, 2 * C, device="cuda") * 0.1).to(torch.bfloat16)
@@ -44,7 +43,7 @@ def main():
         err = (ya.float() - yb.float()).abs().max().item()
         ts, tf = timeit(separate), timeit(fused)
         gbs = 2 * rows * C * 2 / tf / 1e3
-        print(f"rows={rows}: separate {ts:.1f} us, fused {tf:.1f} us ({gbs:.0f} GB/s of x+y, "
+        print(f"C={C} rows={rows}: separate {ts:.1f} us, fused {tf:.1f} us ({gbs:.0f} GB/s of x+y, "
               f"{2 * rows * C * 2 * C * 2 / tf / 1e6:.0f} TFLOP/s), max|diff| {err:.4f}", flush=True)
 
 
