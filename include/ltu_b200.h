@@ -138,8 +138,9 @@ int ltu_linear_tc(const void* x, int Cin, int64_t rows, const void* weight_bf16,
  *   x, y bf16 [rows][C] (y may alias x); w1_bf16 [2C][C] and w2_bf16 [C][2C] are the nn.Linear weights
  *   rounded to bf16 (row-major, K innermost: the K-major UMMA operand, fetched by TMA); biases, gamma,
  *   beta fp32.  The 2C-wide hidden activation stays in tensor memory; HBM traffic is one read of x and
- *   one write of y.  supported(C): 1 for C == 128 (W1, W2 resident in shared memory) and C == 256 (W1, W2
- *   streamed from L2 through a TMA ring once per 128-row tile, hidden dimension in four quarters).  */
+ *   one write of y.  C == 128: W1, W2 resident in shared memory.  C == 256: W1, W2 streamed from L2 through a TMA ring
+ *   once per 128-row tile (optionally once per 2-CTA cluster, multicast), hidden dimension in four quarters.
+ *   supported(C) is the dispatch hint of the model: 1 for 128; for 256 only with LTU_FFN256=1 (no faster yet).   */
 int ltu_ffn_fused_supported(int C);
 int ltu_ffn_fused(const void* x, int64_t rows, int C, const void* w1_bf16, const float* b1,
                   const void* w2_bf16, const float* b2, const float* gamma, const float* beta,

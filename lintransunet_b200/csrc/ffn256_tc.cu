@@ -18,6 +18,7 @@
 //   warp 16     TMA producer (t tile: 4 boxes [128 x 64]; ring: W1 stages = 2 boxes [128 x 64], W2 stages = 1 box [256 x 64])
 //   warp 17     tcgen05.mma issue (warp-uniform, one elected lane), TMEM allocation
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -47,22 +48,30 @@ struct F2Params {
     float eps;
     int tiles;
     int64_t rows;
+    int cl;                 // CTAs per cluster: 1, or 2 = every weight stage is fetched once per CTA pair (TMA multicast)
 };
 
 __global__ void __launch_bounds__(kF2Threads, 1)
 ffn256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
-              const __grid_constant__ CUtensorMap tm_w2, const F2Params p) {
+              const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w2h, const F2Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     F2Tail* tail = reinterpret_cast<F2Tail*>(smem + kF2OffTail);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_my = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // Cluster mode: the two CTAs of a pair walk tile PAIRS in lock step (same trip count; a tile past the end computes on
+    // zero rows and stores nothing) because both must take part in every weight stage.
+    const int crank = p.cl == 2 ? (int)cluster_ctarank() : 0;
+    const int ngroups = (int)gridDim.x / p.cl, group = (int)blockIdx.x / p.cl;
+    const int gtiles = (p.tiles + p.cl - 1) / p.cl;                       // tile groups (pairs)
+    const int n_my = (gtiles - group + ngroups - 1) / ngroups;
+    auto tile_of = [&](int t) { return (group + t * ngroups) * p.cl + crank; };
+    const uint16_t cmask = (uint16_t)((1u << p.cl) - 1);
 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&tail->x_full), 1);
         mbar_init(smem_u32(&tail->x_empty), 1);
-        for (int s = 0; s < kF2Stages; ++s) { mbar_init(smem_u32(&tail->b_full[s]), 1); mbar_init(smem_u32(&tail->b_empty[s]), 1); }
+        for (int s = 0; s < kF2Stages; ++s) { mbar_init(smem_u32(&tail->b_full[s]), 1); mbar_init(smem_u32(&tail->b_empty[s]), (uint32_t)p.cl); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tail->a1_full[s]), 1);
             mbar_init(smem_u32(&tail->a1_free[s]), 1);
@@ -82,6 +91,7 @@ ffn256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.cl == 2) cluster_sync_all();                  // the peer's barriers exist before anything is multicast to them
     const uint32_t tmem_base = tail->tmem_slot;
 
     // order of the eight GEMM phases of a tile: (kind, quarter); kind 0 = G1, 1 = G2
@@ -93,7 +103,7 @@ ffn256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
         if (lane == 0) {
             uint32_t n = 0;
             for (int t = 0; t < n_my; ++t) {
-                const int row0 = ((int)blockIdx.x + t * (int)gridDim.x) * 128;
+                const int row0 = tile_of(t) * 128;
                 mbar_wait(smem_u32(&tail->x_empty), (t & 1) ^ 1);            // every G1 of the previous tile has read the t tile
                 mbar_expect_tx(smem_u32(&tail->x_full), 65536);
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(sbase + kF2OffX + kb * 16384, &tm_x, kb * 64, row0, smem_u32(&tail->x_full));
@@ -106,7 +116,10 @@ ffn256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                         const uint32_t dst = sbase + kF2OffRing + s * kF2StageBytes, bar = smem_u32(&tail->b_full[s]);
                         mbar_wait(smem_u32(&tail->b_empty[s]), ((n / kF2Stages) & 1) ^ 1);
                         mbar_expect_tx(bar, kF2StageBytes);
-                        if (kind == 0) {        // W1 rows [128q, +128), K-blocks 2*s2 and 2*s2 + 1
+                        if (p.cl == 2) {        // each CTA fetches one 16 KB half of the stage and multicasts it to both
+                            if (kind == 0) tma_load_2d_mc(dst + crank * 16384, &tm_w1, (2 * s2 + crank) * 64, q * 128, bar, cmask);
+                            else tma_load_2d_mc(dst + crank * 16384, &tm_w2h, q * 128 + s2 * 64, crank * 128, bar, cmask);
+                        } else if (kind == 0) { // W1 rows [128q, +128), K-blocks 2*s2 and 2*s2 + 1
                             tma_load_2d(dst, &tm_w1, (2 * s2) * 64, q * 128, bar);
                             tma_load_2d(dst + 16384, &tm_w1, (2 * s2 + 1) * 64, q * 128, bar);
                         } else {                // W2 all 256 rows, hidden columns [128q + 64*s2, +64)
@@ -145,7 +158,8 @@ ffn256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                             for (int k = 0; k < 4; ++k)
                                 umma_bf16_elect(a1, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc1, (s2 | kb | k) != 0);
                         }
-                        umma_commit_elect(smem_u32(&tail->b_empty[s]));
+                        if (p.cl == 2) umma_commit_mc_elect(smem_u32(&tail->b_empty[s]), cmask);     // the stage is free when BOTH CTAs have consumed it
+                        else umma_commit_elect(smem_u32(&tail->b_empty[s]));
                     }
                     umma_commit_elect(smem_u32(&tail->a1_full[b]));
                     ++use[b];
@@ -166,7 +180,8 @@ ffn256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                             umma_bf16_ts_elect(tmem_base + 256, a1 + (uint32_t)(32 * (kk >> 1) + 8 * (kk & 1)),
                                                bdesc + (uint64_t)(k * 2), idesc2, (q | kk) != 0);
                         }
-                        umma_commit_elect(smem_u32(&tail->b_empty[s]));
+                        if (p.cl == 2) umma_commit_mc_elect(smem_u32(&tail->b_empty[s]), cmask);     // the stage is free when BOTH CTAs have consumed it
+                        else umma_commit_elect(smem_u32(&tail->b_empty[s]));
                     }
                     umma_commit_elect(smem_u32(&tail->a1_free[b]));
                     ++g2use[b];
@@ -207,7 +222,7 @@ ffn256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                 mbar_arrive(smem_u32(&tail->h_full[b]));
             }
             // ---- e2: + b2 + residual -> LayerNorm over 256 columns -> bf16 rows (this thread: columns [64cg, 64cg+64))
-            const int64_t grow = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * 128 + row;
+            const int64_t grow = (int64_t)tile_of(t) * 128 + row;
             const bool row_ok = grow < p.rows;
             const uint4* rsrc = reinterpret_cast<const uint4*>(p.x + (row_ok ? grow : 0) * 256 + cg * 64);
             mbar_wait_sleep(smem_u32(&tail->acc2_full), t & 1, 64);
@@ -275,6 +290,7 @@ ffn256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cl == 2) cluster_sync_all();                  // no CTA leaves while its peer may still multicast into it
     if (warp == 17) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -284,11 +300,12 @@ ffn256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
 // launcher used by ltu_ffn_fused (ffn_tc.cu) for C == 256
 int ffn256_launch(const void* x, int64_t rows, const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
                   const float* gamma, const float* beta, float eps, void* y, cudaStream_t stream) {
-    CUtensorMap tx, tw1, tw2;
+    CUtensorMap tx, tw1, tw2, tw2h;
     int rc;
     if ((rc = make_tmap_bf16_2d(&tx, x, (uint64_t)rows, 256, 128)) != LTU_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&tw1, w1_bf16, 512, 256, 128)) != LTU_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&tw2, w2_bf16, 256, 512, 256)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&tw2h, w2_bf16, 256, 512, 128)) != LTU_OK) return rc;     // half-stage boxes (cluster mode)
     F2Params p;
     p.x = (const bf16*)x; p.y = (bf16*)y; p.rows = rows;
     p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps;
@@ -300,9 +317,19 @@ int ffn256_launch(const void* x, int64_t rows, const void* w1_bf16, const float*
         cudaFuncSetAttribute(ffn256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured_dev = dev;
     }
-    int grid = sm_count();
-    if (grid > p.tiles) grid = p.tiles;
-    ffn256_kernel<<<grid, kF2Threads, smem, stream>>>(tx, tw1, tw2, p);
+    static const int want_cl = [] { const char* e = getenv("LTU_FFN256_CLUSTER"); return (e && e[0] == '0') ? 1 : 2; }();
+    p.cl = (want_cl == 2 && p.tiles >= 2) ? 2 : 1;
+    int grid = sm_count() / p.cl * p.cl;
+    const int need = (p.tiles + p.cl - 1) / p.cl * p.cl;
+    if (grid > need) grid = need;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kF2Threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, ffn256_kernel, tx, tw1, tw2, tw2h, p);
+    if (le != cudaSuccess) { set_error("ffn_fused (d_model 256): launch failed: %s", cudaGetErrorString(le)); return (int)le; }
     LTU_LAUNCH_CHECK("ffn_fused (d_model 256)");
     count_launch(1);
     return LTU_OK;

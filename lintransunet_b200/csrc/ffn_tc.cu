@@ -30,6 +30,7 @@
 //   H = [0,64) u [128,192) with no cross-warp hazard, and acc2 lands in the columns in between:
 //   [64,128) (outputs 0-63) and [192,256) (outputs 64-127), as two N=64 GEMMs.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -363,7 +364,14 @@ int ffn256_launch(const void* x, int64_t rows, const void* w1_bf16, const float*
                   const float* gamma, const float* beta, float eps, void* y, cudaStream_t stream);      // ffn256_tc.cu
 }
 
-extern "C" int ltu_ffn_fused_supported(int C) { return (C == 128 || C == 256) ? 1 : 0; }
+// Dispatch hint for the model: d_model 128 always; d_model 256 only with LTU_FFN256=1 -- ffn256_kernel is correct (tests call
+// it directly) but bound by the latency of its 128 KB weight ring (tensor pipe 21 % busy) and only matches cuBLAS + gelu +
+// add_layernorm inside the step (profiles/r1_conv_variants.md).
+extern "C" int ltu_ffn_fused_supported(int C) {
+    if (C == 128) return 1;
+    const char* e = getenv("LTU_FFN256");
+    return (C == 256 && e && e[0] == '1') ? 1 : 0;
+}
 
 static int ffn_launch(const void* x, int64_t rows, int C, const void* w1_bf16, const float* b1, const void* w2_bf16,
                       const float* b2, const float* gamma, const float* beta, float eps, void* y, long long* trace,
