@@ -16,13 +16,14 @@
 //                 (64 output columns per thread)
 //   The GELU warps carry ~75 % of the instructions and never wait for the tensor pipe: acc1 of tile t+1
 //   is complete long before e1(t) ends.  There are no dedicated producer / MMA warps (they would only
-//   spin on barriers and cost issue slots); lane 0 of the first warp of each group is its leader:
+//   spin on barriers and cost issue slots).  MMA issue is warp-uniform (the whole warp runs the descriptor
+//   arithmetic, one elected lane issues):
 //     warp 0 lane 0 : TMA load of tile t+2 (2 x [128 x 64] boxes, SWIZZLE_128B) once acc1(t) is complete
 //                     (GEMM1 has consumed the slot) -- two instructions, no waiting
-//     warp 8 lane 0 : GEMM2(t)  acc2[128x128] = H . W2^T  (A from TENSOR MEMORY) once H is published; a
+//     warp 8        : GEMM2(t)  acc2[128x128] = H . W2^T  (A from TENSOR MEMORY) once H is published; a
 //                     tcgen05.mma issue blocks for about the duration of the MMA, so this must not sit in
 //                     a GELU warp (measured: +2300 cycles per tile on the critical path)
-//     warp 12 lane 0: GEMM1(t+2)  acc1[128x256] = T . W1^T  (A, B from smem) once the e2 group has pulled
+//     warp 12       : GEMM1(t+2)  acc1[128x256] = T . W1^T  (A, B from smem) once the e2 group has pulled
 //                     acc2(t) into registers
 //   W1 / W2 (64 KB each) are loaded once per CTA.
 //   TMEM: two 256-column buffers.  acc1 fills a buffer; a thread turns 16 of its accumulator columns at a

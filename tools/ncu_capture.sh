@@ -16,7 +16,7 @@ cap() {  # name regex skip count
     ncu -i $OUT/prof_$1.ncu-rep --page raw --csv > $OUT/prof_$1_raw.csv 2>/dev/null
     ncu -i $OUT/prof_$1.ncu-rep --page details --csv > $OUT/prof_$1_details.csv 2>/dev/null
     ncu -i $OUT/prof_$1.ncu-rep --page source --csv > $OUT/prof_$1_source.csv 2>/dev/null
-    sz=$(stat -c %s $OUT/prof_$1.ncu-rep); if [ $sz -gt 12000000 ]; then rm -f $OUT/prof_$1.ncu-rep; fi
+    rm -f $OUT/prof_$1.ncu-rep $OUT/prof_$1_details.csv
   fi
 }
 # per forward the attention kernels run 32 times: bottleneck (8), bridge 3 (8), bridge 2 (8), bridge 1 (8)
