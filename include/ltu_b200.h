@@ -263,6 +263,36 @@ int ltu_vote_fractions(const uint8_t* votes, float* frac, int C, int64_t voxels,
 int ltu_gather_windows(const float* volume, const int32_t* starts, float* out, int nwin, int rh,
                        int rw, int rd, int H, int W, int D, ltu_stream_t stream);
 
+/* ---- 8f-2: decisions on the stitched volume, inference_embed_attn.py:147 `(predict >= threshold)`
+ * and inference_multi_classes.py:148 `torch.round(predict)` (half to even: 0.5 -> 0) ------------
+ * votes uint8 [C,V] -> onehot uint8 [C,V] (0/1); the fraction votes / sum_c votes is formed in fp32
+ * with an IEEE division exactly as ltu_vote_fractions does, without materialising it.           */
+#define LTU_DECIDE_THRESHOLD 0
+#define LTU_DECIDE_ROUND 1
+int ltu_vote_decide(const uint8_t* votes, uint8_t* onehot, int C, int64_t voxels, int mode,
+                    float thr, ltu_stream_t stream);
+
+/* ---- 8f-4: monai.transforms.KeepLargestConnectedComponent(applied_labels, independent=False,
+ * connectivity) as constructed at inference_multi_classes.py:104 and applied at :150 (MONAI 0.7.0,
+ * one-hot branch: foreground = any applied channel; its largest connected component -- skimage
+ * label order, first maximum wins -- is kept, every other foreground voxel is zeroed in the
+ * applied channels).  onehot uint8 [C,H,W,D] is edited in place; applied_mask bit i = label i;
+ * connectivity 1/2/3 = 6/18/26 neighbours.  independent=True is one call per label with a
+ * single-bit mask.  workspace: ltu_keep_largest_component_workspace(H*W*D) bytes, 16-byte aligned. */
+size_t ltu_keep_largest_component_workspace(int64_t voxels);
+int ltu_keep_largest_component(uint8_t* onehot, int C, unsigned applied_mask, int H, int W, int D,
+                               int connectivity, void* workspace, size_t ws_bytes,
+                               ltu_stream_t stream);
+
+/* ---- 8f-2/-4: the integer statistics behind the evaluation metrics of the inference scripts
+ * (loss/criterions.py DiceClassLoss :46-69, Recall :291-311, Precision :359-379, LocalizationLoss
+ * :192-241; loss/multi_criterions.py :41-55,:69-83,:232-281,:359-374) ---------------------------
+ * pred_onehot uint8 [C,H,W,D] (0/1), target uint8 [H,W,D] (class index) ->
+ * counts int64 [C+1][H][3] = (sum pred*target, sum pred, sum target) per class and H-row;
+ * row C is the foreground pseudo-class (1 - pred[0]) vs (target != 0).                         */
+int ltu_overlap_counts(const uint8_t* pred_onehot, const uint8_t* target, int C, int H, int W,
+                       int D, int64_t* counts, ltu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

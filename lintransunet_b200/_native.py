@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libltu_b200.so")
@@ -65,6 +65,10 @@ SIGNATURES = {
     "ltu_vote_argmax": (I, [P, P, I, L, P]),
     "ltu_vote_fractions": (I, [P, P, I, L, P]),
     "ltu_gather_windows": (I, [P, P, P, I, I, I, I, I, I, I, P]),
+    "ltu_vote_decide": (I, [P, P, I, L, I, F, P]),
+    "ltu_keep_largest_component_workspace": (Z, [L]),
+    "ltu_keep_largest_component": (I, [P, I, c_uint, I, I, I, I, P, Z, P]),
+    "ltu_overlap_counts": (I, [P, P, I, I, I, I, P, P]),
 }
 
 

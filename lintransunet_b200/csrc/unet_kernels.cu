@@ -251,8 +251,9 @@ vote_fractions_kernel(const uint8_t* __restrict__ votes, float* __restrict__ fra
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
         int tot = 0;
         for (int c = 0; c < C; ++c) tot += votes[(int64_t)c * V + v];
-        float inv = 1.f / (float)tot;           // tot == 0 cannot happen: every voxel is covered by >= 1 window
-        for (int c = 0; c < C; ++c) frac[(int64_t)c * V + v] = (float)votes[(int64_t)c * V + v] * inv;
+        // IEEE division like MONAI's `output_image / count_map` (k * (1/n) can differ in the last bit when n is not a
+        // power of two: overlap 0.6 gives n = 3, 6, ...); tot == 0 cannot happen: every voxel is covered by >= 1 window
+        for (int c = 0; c < C; ++c) frac[(int64_t)c * V + v] = __fdiv_rn((float)votes[(int64_t)c * V + v], (float)tot);
     }
 }
 

@@ -406,6 +406,59 @@ def vote_fractions(votes: torch.Tensor) -> torch.Tensor:
     return out
 
 
+DECIDE_THRESHOLD, DECIDE_ROUND = 0, 1
+
+
+def vote_decide(votes: torch.Tensor, mode: int, thr: float = 0.5) -> torch.Tensor:
+    """votes uint8 [C,H,W,D] -> uint8 one-hot [C,H,W,D]: `(fractions >= thr)` (inference_embed_attn.py:147) or
+    `torch.round(fractions)` (inference_multi_classes.py:148) without materialising the fp32 fractions."""
+    dev = _chk(votes)
+    if votes.dtype != torch.uint8:
+        raise TypeError("vote_decide: votes must be uint8")
+    C = votes.shape[0]
+    out = torch.empty_like(votes)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_vote_decide(_p(votes), _p(out), C, votes.numel() // C, mode, thr, st), "ltu_vote_decide")
+    return out
+
+
+def keep_largest_component_(onehot: torch.Tensor, applied_labels, connectivity: int = 3,
+                            independent: bool = False) -> torch.Tensor:
+    """In-place monai.transforms.KeepLargestConnectedComponent (0.7.0) on a uint8 one-hot volume [C,H,W,D]
+    (inference_multi_classes.py:104,:150).  The labelling runs on the GPU (union-find), nothing goes to the host."""
+    dev = _chk(onehot)
+    if onehot.dtype != torch.uint8 or onehot.dim() != 4:
+        raise TypeError("keep_largest_component_: onehot must be uint8 [C,H,W,D]")
+    C, H, W, D = onehot.shape
+    labels = [int(a) for a in applied_labels]
+    if not labels or min(labels) < 0 or max(labels) >= C:
+        raise ValueError("keep_largest_component_: applied_labels must be channel indices")
+    L = _native.lib()
+    nbytes = L.ltu_keep_largest_component_workspace(H * W * D)
+    ws = torch.empty(nbytes // 8, dtype=torch.int64, device=dev)
+    masks = [1 << a for a in labels] if independent else [sum(1 << a for a in set(labels))]
+    with _Guard(dev) as st:
+        for m in masks:
+            check(L.ltu_keep_largest_component(_p(onehot), C, m, H, W, D, connectivity, _p(ws), nbytes, st),
+                  "ltu_keep_largest_component")
+    return onehot
+
+
+def overlap_counts(pred_onehot: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """pred uint8 one-hot [C,H,W,D], target uint8 class indices [H,W,D] -> int64 [C+1,H,3] = (TP, predicted, target)
+    per class and H-row; row C is the foreground pseudo-class (1 - pred[0]) vs (target != 0)."""
+    dev = _chk(pred_onehot, target)
+    if pred_onehot.dtype != torch.uint8 or target.dtype != torch.uint8:
+        raise TypeError("overlap_counts: uint8 tensors expected")
+    C, H, W, D = pred_onehot.shape
+    if tuple(target.shape) != (H, W, D):
+        raise ValueError("overlap_counts: target must be [H,W,D]")
+    out = torch.empty(C + 1, H, 3, dtype=torch.int64, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_overlap_counts(_p(pred_onehot), _p(target), C, H, W, D, _p(out), st), "ltu_overlap_counts")
+    return out
+
+
 def gather_windows(volume: torch.Tensor, starts: torch.Tensor, roi) -> torch.Tensor:
     """volume fp32 [H,W,D], starts int32 [n,3] -> windows fp32 [n,1,rh,rw,rd]."""
     dev = _chk(volume, starts)

@@ -92,14 +92,16 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
                              predictor: MaskTransUnet, overlap: float = 0.25, mode: str = "constant",
                              sigma_scale: float = 0.125, padding_mode: str = "constant", cval: float = 0.0,
                              sw_device=None, device=None, *, group=None, distributed: Optional[bool] = None,
-                             return_labels: bool = False):
+                             return_labels: bool = False, return_votes: bool = False):
     """Same positional signature as monai.inferers.sliding_window_inference (0.7.0).
 
     inputs: fp32 [B, 1, H, W, D] on the GPU, or in (pinned) HOST memory: the volume is then streamed to the device in
     slabs along H on a copy stream while the first windows are already being computed, and under torch.distributed
     each rank owns a contiguous block of windows and uploads only the rows they touch.  Every computation runs on the
     GPU either way.  Returns fp32 [B, C, H, W, D] vote fractions (what MONAI's ``output_image / count_map`` yields for a
-    one-hot predictor) or, with ``return_labels``, the uint8 argmax [B, H, W, D] as well."""
+    one-hot predictor) or, with ``return_labels``, the uint8 argmax [B, H, W, D] as well.  ``return_votes`` returns the
+    exact uint8 vote counts [B, C, H, W, D] INSTEAD of the fractions (the decisions of the inference scripts --
+    threshold, round, argmax -- are taken on them directly, see lintransunet_b200/inference.py)."""
     global last_h2d_bytes
     if str(mode).lower().endswith("gaussian"):
         raise NotImplementedError("only the constant blend mode used by the reference scripts is implemented")
@@ -177,7 +179,7 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
         if padded != image_size:
             sl = tuple(slice(pad_before[i], pad_before[i] + image_size[i]) for i in range(3))
             votes = votes[(slice(None),) + sl].contiguous()
-        fracs.append(ops.vote_fractions(votes))
+        fracs.append(votes if return_votes else ops.vote_fractions(votes))
         if return_labels:
             labels_out.append(ops.vote_argmax(votes))
     out = torch.stack(fracs, 0) if B > 1 else fracs[0].unsqueeze(0)

@@ -50,6 +50,14 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert lib.ltu_conv3d(p, 16, None, 0, 1, 4, 4, 4, 0, 5, 1, 1, 1, 2, p, None, 16, p, 0, 4, 4, 4, None, 0, None) == -1
     assert lib.ltu_head_d2s_softmax(p, p, None, None, 1, 2, 2, 2, 9, None) == -1   # dim_output > 8
     assert lib.ltu_kv_reduce_workspace(0, 0, 4) == 0
+    assert lib.ltu_vote_decide(p, p, 3, 64, 2, 0.5, None) == -1                    # mode not in {0,1}
+    assert b"vote_decide" in lib.ltu_last_error()
+    assert lib.ltu_keep_largest_component_workspace(1000) == 16 + 8000
+    assert lib.ltu_keep_largest_component(p, 3, 0b110, 2, 2, 2, 4, p, 1 << 20, None) == -1      # connectivity 4
+    assert lib.ltu_keep_largest_component(p, 3, 0b1000, 2, 2, 2, 3, p, 1 << 20, None) == -1     # label 3 of 3 channels
+    assert lib.ltu_keep_largest_component(p, 3, 0b110, 2, 2, 2, 3, p, 8, None) == -1            # workspace too small
+    assert b"workspace" in lib.ltu_last_error()
+    assert lib.ltu_overlap_counts(p, None, 3, 2, 2, 2, p, None) == -1
 
 
 def test_product_refuses_cpu_tensors(lib):
