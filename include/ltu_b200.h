@@ -293,6 +293,19 @@ int ltu_keep_largest_component(uint8_t* onehot, int C, unsigned applied_mask, in
 int ltu_overlap_counts(const uint8_t* pred_onehot, const uint8_t* target, int C, int H, int W,
                        int D, int64_t* counts, ltu_stream_t stream);
 
+/* ---- 8f-1 (first slice): backward of linear_attention, model/trans_block.py:41-67 (what autograd
+ * does for `F.softmax(query,-1)/sqrt(d)`, `F.softmax(key,-2)`, and the two einsums) ------------
+ * q,k,v,dout: [B,N,heads*32] views with row strides ldq / ldkv (k and v) / ldo; ctx fp32
+ * [B,heads,32,32] from ltu_kv_reduce.  Writes dq,dk,dv (row stride ldd, activation dtype) and,
+ * as by-products, dctx fp32 [B,heads,32,32] and kstats fp32 [B,heads,3,32] = (column max of K,
+ * column sum of exp(K-max), sum_e dctx*ctx).  Nothing else has to be saved by the forward.
+ * workspace: ltu_attn_bwd_workspace(B,N,heads) bytes; fixed-order merges (bit-reproducible).    */
+size_t ltu_attn_bwd_workspace(int B, int64_t N, int heads);
+int ltu_attn_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                 const void* dout, int64_t ldo, const float* ctx, void* dq, void* dk, void* dv,
+                 int64_t ldd, float* dctx, float* kstats, void* workspace, size_t ws_bytes, int B,
+                 int64_t N, int heads, int dtype, ltu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

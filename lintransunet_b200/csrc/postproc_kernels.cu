@@ -55,6 +55,43 @@ vote_decide_kernel(const uint8_t* __restrict__ votes, uint8_t* __restrict__ oneh
     }
 }
 
+// Exact integer form of the two decisions the scripts use: with k votes of n, fp32(k/n) > 0.5 <=> 2k > n and
+// fp32(k/n) >= 0.5 <=> 2k >= n (k/n differs from 0.5 by at least 1/(2n) >= 1/510 unless it IS 0.5, which fp32 holds
+// exactly), and rintf(x) == 1 on [0,1] <=> x > 0.5 (half to even).  16 voxels per thread, packed-byte SIMD:
+// k > n-k  (no overflow: n <= 255), masked by n != 0.
+__device__ __forceinline__ uint32_t decide_word(uint32_t k, uint32_t n, bool ge) {
+    const uint32_t rest = __vsub4(n, k);
+    const uint32_t hit = ge ? __vcmpgeu4(k, rest) : __vcmpgtu4(k, rest);
+    return hit & __vcmpne4(n, 0u) & 0x01010101u;
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+vote_decide_half_kernel(const uint8_t* __restrict__ votes, uint8_t* __restrict__ onehot, int C, int64_t V, int ge) {
+    const int64_t n16 = V / 16;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 w[CMAX];
+        uint4 tot = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            if (c < C) {
+                w[c] = __ldg(reinterpret_cast<const uint4*>(votes + (int64_t)c * V) + i);
+                tot.x = __vadd4(tot.x, w[c].x); tot.y = __vadd4(tot.y, w[c].y);
+                tot.z = __vadd4(tot.z, w[c].z); tot.w = __vadd4(tot.w, w[c].w);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            if (c < C) {
+                uint4 o;
+                o.x = decide_word(w[c].x, tot.x, ge); o.y = decide_word(w[c].y, tot.y, ge);
+                o.z = decide_word(w[c].z, tot.z, ge); o.w = decide_word(w[c].w, tot.w, ge);
+                reinterpret_cast<uint4*>(onehot + (int64_t)c * V)[i] = o;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- connected components (union-find)
 // Labels live in an int32 volume: L[v] = parent voxel index (a root has L[v] == v), -1 = background.  Links only
 // ever point to a SMALLER index of the same component (atomicMin), so the structure is a forest at every moment,
@@ -80,21 +117,70 @@ __device__ __forceinline__ void cc_union(int* L, int a, int b) {
     }
 }
 
+// Foreground test + run linking without atomics: the 32 voxels of a warp are consecutive in memory (along D);
+// every foreground voxel points straight at the first voxel of its run inside the warp's segment (a run also ends at
+// a row boundary, d == 0).  Runs that continue across a segment boundary are joined by one union in cc_merge.
 __global__ void __launch_bounds__(256)
-cc_init_kernel(const uint8_t* __restrict__ onehot, int C, unsigned applied, int64_t V, int* __restrict__ L,
+cc_init_kernel(const uint8_t* __restrict__ onehot, int C, unsigned applied, int64_t V, int D, int* __restrict__ L,
                int* __restrict__ cnt, unsigned long long* __restrict__ best) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *best = 0ull;
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    // block-uniform trip count: every lane reaches the ballots
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < V; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = base + threadIdx.x;
         bool fg = false;
-        for (int c = 0; c < C; ++c)
-            if ((applied >> c) & 1u) fg |= onehot[(int64_t)c * V + v] != 0;
-        L[v] = fg ? (int)v : -1;
-        cnt[v] = 0;
+        if (v < V)
+            for (int c = 0; c < C; ++c)
+                if ((applied >> c) & 1u) fg |= onehot[(int64_t)c * V + v] != 0;
+        const unsigned fgbits = __ballot_sync(0xffffffffu, fg);
+        const unsigned d0bits = __ballot_sync(0xffffffffu, v < V && (v % D) == 0);
+        // bit s set: lane s begins a run segment (first lane, or its predecessor is background, or a new row starts)
+        const unsigned breaks = 1u | (~fgbits << 1) | d0bits;
+        if (v < V) {
+            const int start = 31 - __clz(breaks & ((2u << lane) - 1u));
+            L[v] = fg ? (int)(v - (lane - start)) : -1;
+            cnt[v] = 0;
+        }
     }
 }
 
-// every foreground voxel links itself to its foreground neighbours that precede it in raster order
-// (13 of 26 for connectivity 3, 9 of 18 for 2, 3 of 6 for 1: |dh|+|dw|+|dd| <= connectivity)
+// 26-connectivity (the reference's setting), run based: between a run R of this row and a run U of one of the four
+// rows that precede it in raster order, ONE union is enough, and it is issued by
+//   * R's first voxel a, if U covers a-1, or starts at a or a+1;
+//   * otherwise by the voxel of R that sits just before U's first voxel (U starts at c >= a+2: voxel c-1).
+// A voxel with a foreground predecessor therefore only looks at column d+1 of the neighbouring rows, and only when
+// a run starts there; the interior of a solid object issues no union at all.
+__global__ void __launch_bounds__(256)
+cc_merge26_kernel(int* __restrict__ L, int H, int W, int D) {
+    const int64_t V = (int64_t)H * W * D;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+        const int lv = __ldcg(L + v);
+        if (lv < 0) continue;
+        const int d = (int)(v % D);
+        const int64_t t = v / D;
+        const int w = (int)(t % W), h = (int)(t / W);
+        const bool prev = d > 0 && __ldcg(L + v - 1) >= 0;
+        if (prev && (v & 31) == 0) cc_union(L, (int)v, (int)v - 1);     // first lane of a segment (cc_init): the run continues
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int dh = r < 3 ? -1 : 0, dw = r < 3 ? r - 1 : -1;
+            const int hh = h + dh, ww = w + dw;
+            if (hh < 0 || ww < 0 || ww >= W) continue;
+            const int* row = L + ((int64_t)hh * W + ww) * D;
+            const bool um = d > 0 && __ldcg(row + d - 1) >= 0;           // U covers d-1 / d / d+1
+            const bool u0 = __ldcg(row + d) >= 0;
+            const bool up = d + 1 < D && __ldcg(row + d + 1) >= 0;
+            if (!prev) {
+                if (um) cc_union(L, (int)v, (int)(row - L) + d - 1);
+                else if (u0) cc_union(L, (int)v, (int)(row - L) + d);
+            }
+            if (up && !u0) cc_union(L, (int)v, (int)(row - L) + d + 1);
+        }
+    }
+}
+
+// connectivity 1 and 2 (6 / 18 neighbours): every foreground voxel links itself to its foreground neighbours that
+// precede it in raster order (3 of 6, 9 of 18: at most `connectivity` non-zero offsets)
 __global__ void __launch_bounds__(256)
 cc_merge_kernel(int* __restrict__ L, int H, int W, int D, int connectivity) {
     const int64_t V = (int64_t)H * W * D;
@@ -170,13 +256,30 @@ cc_apply_kernel(uint8_t* __restrict__ onehot, int C, unsigned applied, int64_t V
 // (1 - pred[0]) vs (target != 0) of loss/multi_criterions.py:49-50,:239-240.  out int64 [C+1][H][3] = TP, P, T.
 __global__ void __launch_bounds__(256)
 overlap_counts_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ target, int C, int H, int64_t row,
-                      long long* __restrict__ out) {
+                      int vec_ok, long long* __restrict__ out) {
     const int h = blockIdx.x, c = blockIdx.y;
     const bool fgclass = c == C;
     const uint8_t* p = pred + ((int64_t)(fgclass ? 0 : c) * H + h) * row;
     const uint8_t* t = target + (int64_t)h * row;
     int tp = 0, np = 0, nt = 0;
-    for (int64_t i = threadIdx.x; i < row; i += 256) {
+    int64_t done = 0;
+    if (vec_ok) {                                            // 16 voxels per load, packed-byte compares, popcounts
+        const uint32_t cls = 0x01010101u * (uint32_t)(c & 0xFF);
+        const int64_t n16 = row / 16;
+        for (int64_t i = threadIdx.x; i < n16; i += 256) {
+            const uint4 pw = __ldg(reinterpret_cast<const uint4*>(p) + i);
+            const uint4 tw = __ldg(reinterpret_cast<const uint4*>(t) + i);
+            const uint32_t pa[4] = {pw.x, pw.y, pw.z, pw.w}, ta[4] = {tw.x, tw.y, tw.z, tw.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t pv = (fgclass ? __vcmpeq4(pa[k], 0u) : __vcmpne4(pa[k], 0u)) & 0x01010101u;
+                const uint32_t tv = (fgclass ? __vcmpne4(ta[k], 0u) : __vcmpeq4(ta[k], cls)) & 0x01010101u;
+                tp += __popc(pv & tv); np += __popc(pv); nt += __popc(tv);
+            }
+        }
+        done = n16 * 16;
+    }
+    for (int64_t i = done + threadIdx.x; i < row; i += 256) {
         const int pv = fgclass ? (p[i] == 0) : (p[i] != 0);
         const int tv = fgclass ? (t[i] != 0) : (t[i] == c);
         tp += pv & tv; np += pv; nt += tv;
@@ -205,6 +308,17 @@ extern "C" int ltu_vote_decide(const uint8_t* votes, uint8_t* onehot, int C, int
                                ltu_stream_t stream) {
     LTU_ARG_CHECK(votes && onehot && C > 0 && C <= 255 && voxels > 0, "vote_decide: bad arguments");
     LTU_ARG_CHECK(mode == LTU_DECIDE_THRESHOLD || mode == LTU_DECIDE_ROUND, "vote_decide: mode must be 0 (threshold) or 1 (round)");
+    // the decisions of the reference scripts (round, threshold 0.5) in exact integer form, 16 voxels per thread
+    const bool half = mode == LTU_DECIDE_ROUND || thr == 0.5f;
+    if (half && C <= 8 && voxels % 16 == 0 && ((reinterpret_cast<uintptr_t>(votes) | reinterpret_cast<uintptr_t>(onehot)) & 15) == 0) {
+        const int ge = mode == LTU_DECIDE_THRESHOLD;
+        const unsigned g = pp_grid(voxels / 16, 256, 8);
+        if (C <= 4) vote_decide_half_kernel<4><<<g, 256, 0, (cudaStream_t)stream>>>(votes, onehot, C, voxels, ge);
+        else vote_decide_half_kernel<8><<<g, 256, 0, (cudaStream_t)stream>>>(votes, onehot, C, voxels, ge);
+        LTU_LAUNCH_CHECK("vote_decide");
+        count_launch(1);
+        return LTU_OK;
+    }
     const bool vec = voxels % 4 == 0 && ((reinterpret_cast<uintptr_t>(votes) | reinterpret_cast<uintptr_t>(onehot)) & 3) == 0;
     if (vec) vote_decide_kernel<4><<<pp_grid(voxels / 4, 256, 16), 256, 0, (cudaStream_t)stream>>>(votes, onehot, C, voxels, mode, thr);
     else vote_decide_kernel<1><<<pp_grid(voxels, 256, 16), 256, 0, (cudaStream_t)stream>>>(votes, onehot, C, voxels, mode, thr);
@@ -231,9 +345,10 @@ extern "C" int ltu_keep_largest_component(uint8_t* onehot, int C, unsigned appli
     int* cnt = L + V;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned g = pp_grid(V, 256, 16);
-    cc_init_kernel<<<g, 256, 0, st>>>(onehot, C, applied_mask, V, L, cnt, best);
+    cc_init_kernel<<<g, 256, 0, st>>>(onehot, C, applied_mask, V, D, L, cnt, best);
     LTU_LAUNCH_CHECK("cc_init");
-    cc_merge_kernel<<<g, 256, 0, st>>>(L, H, W, D, connectivity);
+    if (connectivity == 3) cc_merge26_kernel<<<g, 256, 0, st>>>(L, H, W, D);
+    else cc_merge_kernel<<<g, 256, 0, st>>>(L, H, W, D, connectivity);
     LTU_LAUNCH_CHECK("cc_merge");
     cc_count_kernel<<<g, 256, 0, st>>>(L, cnt, V);
     LTU_LAUNCH_CHECK("cc_count");
@@ -248,9 +363,12 @@ extern "C" int ltu_keep_largest_component(uint8_t* onehot, int C, unsigned appli
 extern "C" int ltu_overlap_counts(const uint8_t* pred_onehot, const uint8_t* target, int C, int H, int W, int D,
                                   int64_t* counts, ltu_stream_t stream) {
     LTU_ARG_CHECK(pred_onehot && target && counts, "overlap_counts: null pointer");
-    LTU_ARG_CHECK(C > 0 && C < 65535 && H > 0 && W > 0 && D > 0 && (int64_t)W * D < 0x7FFFFFFFll, "overlap_counts: bad shape");
+    LTU_ARG_CHECK(C > 0 && C <= 255 && H > 0 && W > 0 && D > 0 && (int64_t)W * D < 0x7FFFFFFFll, "overlap_counts: bad shape");
+    const int64_t row = (int64_t)W * D;
+    // rows start 16-byte aligned when the bases are and the row length is a multiple of 16
+    const int vec_ok = row % 16 == 0 && ((reinterpret_cast<uintptr_t>(pred_onehot) | reinterpret_cast<uintptr_t>(target)) & 15) == 0;
     overlap_counts_kernel<<<dim3((unsigned)H, (unsigned)(C + 1)), 256, 0, (cudaStream_t)stream>>>(
-        pred_onehot, target, C, H, (int64_t)W * D, reinterpret_cast<long long*>(counts));
+        pred_onehot, target, C, H, row, vec_ok, reinterpret_cast<long long*>(counts));
     LTU_LAUNCH_CHECK("overlap_counts");
     count_launch(1);
     return LTU_OK;

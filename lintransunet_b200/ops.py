@@ -143,6 +143,34 @@ def q_readout(q: torch.Tensor, ctx: torch.Tensor, heads: int) -> torch.Tensor:
     return out
 
 
+def linear_attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, ctx: torch.Tensor, dout: torch.Tensor,
+                         heads: int):
+    """Backward of the attention core (model/trans_block.py:41-67): q, k, v, dout [B, N, C] views (k and v with a common
+    row stride), ctx fp32 [B,heads,32,32] from kv_reduce -> dqkv [B, N, 3C] (dq | dk | dv, activation dtype): one
+    buffer, so the backward of a fused QKV projection is a single GEMM."""
+    B, N, C = q.shape
+    assert C == heads * 32 and k.shape == q.shape and v.shape == q.shape and dout.shape == q.shape
+    for t in (q, k, v, dout):
+        if not t.is_cuda:
+            raise RuntimeError("lintransunet_b200 ops need CUDA tensors: there is no CPU fallback")
+        assert t.stride(2) == 1 and t.stride(0) == N * t.stride(1) and t.dtype == q.dtype
+    assert k.stride(1) == v.stride(1)
+    dev = _chk(ctx)
+    L = _native.lib()
+    ws_bytes = L.ltu_attn_bwd_workspace(B, N, heads)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+    dqkv = torch.empty(B, N, 3 * C, dtype=q.dtype, device=dev)
+    dctx = torch.empty(B, heads, 32, 32, dtype=torch.float32, device=dev)
+    kst = torch.empty(B, heads, 3, 32, dtype=torch.float32, device=dev)
+    es = q.element_size()
+    with _Guard(dev, ("attn_bwd", 10 * B * N * C * es, 10 * B * N * C * 32)) as st:
+        check(L.ltu_attn_bwd(_p(q), q.stride(1), _p(k), _p(v), k.stride(1), _p(dout), dout.stride(1), _p(ctx),
+                             c_void_p(dqkv.data_ptr()), c_void_p(dqkv.data_ptr() + C * es),
+                             c_void_p(dqkv.data_ptr() + 2 * C * es), 3 * C, _p(dctx), _p(kst), _p(ws), ws_bytes,
+                             B, N, heads, _dt(q), st), "ltu_attn_bwd")
+    return dqkv
+
+
 def add_layernorm(x: torch.Tensor, res: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
                   eps: float = 1e-6) -> torch.Tensor:
     """LayerNorm(x + res) over the last dim (model/trans_block.py:205-206, :209-210)."""
