@@ -306,6 +306,18 @@ int ltu_attn_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64
                  int64_t ldd, float* dctx, float* kstats, void* workspace, size_t ws_bytes, int B,
                  int64_t N, int heads, int dtype, ltu_stream_t stream);
 
+/* backward of `layer_norm(x + dropout(res))`, model/trans_block.py:205-206,:209-210: z = x + res is
+ * rebuilt from the forward's inputs; dz [rows,C] is the gradient of BOTH x and res; dgamma, dbeta
+ * fp32 [C] by per-CTA partials summed in a fixed order.  C in {128, 256}.
+ * workspace: ltu_add_layernorm_bwd_workspace(rows, C) bytes.                                      */
+size_t ltu_add_layernorm_bwd_workspace(int64_t rows, int C);
+int ltu_add_layernorm_bwd(const void* x, const void* res, const void* dy, const float* gamma,
+                          void* dz, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes,
+                          int64_t rows, int C, float eps, int dtype, ltu_stream_t stream);
+/* backward of the exact-erf F.gelu, model/trans_block.py:201,:208: dx = dy (Phi(x) + x phi(x)),
+ * x = the pre-activation                                                                          */
+int ltu_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, ltu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,9 @@ SIGNATURES = {
     "ltu_keep_largest_component_workspace": (Z, [L]),
     "ltu_keep_largest_component": (I, [P, I, c_uint, I, I, I, I, P, Z, P]),
     "ltu_overlap_counts": (I, [P, P, I, I, I, I, P, P]),
+    "ltu_add_layernorm_bwd_workspace": (Z, [L, I]),
+    "ltu_add_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, Z, L, I, F, I, P]),
+    "ltu_gelu_bwd": (I, [P, P, P, L, I, P]),
     "ltu_attn_bwd_workspace": (Z, [I, L, I]),
     "ltu_attn_bwd": (I, [P, L, P, P, L, P, L, P, P, P, P, L, P, P, P, Z, I, L, I, I, P]),
 }

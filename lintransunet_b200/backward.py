@@ -1,0 +1,91 @@
+"""Training-mode forward and backward of one SelfAttentionLayer (model/trans_block.py:169-211) on the
+sm_100a kernels -- the first complete slice of SURVEY 8f-1 (backward / train step).
+
+Not wired into ``MaskTransUnet.forward`` yet (the convolution, InstanceNorm, resampling and head backward kernels
+do not exist): ``encoder_layer_train`` / ``encoder_layer_backward`` are the building block an
+``autograd.Function`` around the transformer stack will call.  Dropout-free (``dropout=0.0``), like every parity
+test of this repo.
+
+Per layer the native launches are: forward ``kv_reduce`` + ``kv_combine`` + ``q_readout`` + 2 x ``add_layernorm`` +
+``gelu``; backward 2 x ``add_layernorm_bwd`` (+ finalize) + ``gelu_bwd`` + ``attn_bwd`` (reduce, combine, apply).
+The Linear layers and their weight gradients are plain cuBLAS GEMMs (``F.linear`` / ``torch.mm`` / ``torch.addmm``),
+as in the forward.  Activations may be fp32 or bf16; parameter gradients are returned in fp32.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+__all__ = ["encoder_layer_train", "encoder_layer_backward"]
+
+
+def _params(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
+    lin = layer.self_attn.linears
+    c = lambda t: t.detach().to(dtype).contiguous()
+    f = lambda t: t.detach().float().contiguous()
+    return dict(w_qkv=c(torch.cat([lin[0].weight, lin[1].weight, lin[2].weight], 0)),
+                b_qkv=c(torch.cat([lin[0].bias, lin[1].bias, lin[2].bias], 0)),
+                w_o=c(lin[3].weight), b_o=c(lin[3].bias), w_1=c(layer.linear1.weight), b_1=c(layer.linear1.bias),
+                w_2=c(layer.linear2.weight), b_2=c(layer.linear2.bias),
+                g1=f(layer.layer_norm1.weight), be1=f(layer.layer_norm1.bias),
+                g2=f(layer.layer_norm2.weight), be2=f(layer.layer_norm2.bias), nhead=layer.self_attn.nhead)
+
+
+@torch.no_grad()
+def encoder_layer_train(t: torch.Tensor, layer) -> Tuple[torch.Tensor, dict]:
+    """SelfAttentionLayer.forward on tokens [B,N,C] (fp32 or bf16, CUDA), keeping what the backward needs.
+    `layer` is the parameter container lintransunet_b200.unet.SelfAttentionLayer."""
+    p = _params(layer, t.dtype)
+    B, N, C = t.shape
+    h = p["nhead"]
+    qkv = F.linear(t, p["w_qkv"], p["b_qkv"])
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    ctx = ops.kv_reduce(k, v, h)
+    att = ops.q_readout(q, ctx, h)
+    o = F.linear(att, p["w_o"], p["b_o"])
+    t1 = ops.add_layernorm(t, o, p["g1"], p["be1"], 1e-6)
+    f1 = F.linear(t1, p["w_1"], p["b_1"])
+    fa = ops.gelu(f1)
+    f2 = F.linear(fa, p["w_2"], p["b_2"])
+    t2 = ops.add_layernorm(t1, f2, p["g2"], p["be2"], 1e-6)
+    return t2, dict(p=p, t=t, qkv=qkv, ctx=ctx, att=att, o=o, t1=t1, f1=f1, fa=fa, f2=f2)
+
+
+def _wgrad(dy2: torch.Tensor, x2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """y = x W^T + b  ->  dW = dy^T x, db = sum_rows dy (fp32)."""
+    return torch.mm(dy2.t(), x2).float(), torch.sum(dy2, 0, dtype=torch.float32)
+
+
+@torch.no_grad()
+def encoder_layer_backward(dout: torch.Tensor, saved: dict) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """Gradient of the layer input and of the 16 parameters, keyed like the reference's state_dict entries
+    relative to the layer (``self_attn.linears.0.weight`` ... ``layer_norm2.bias``)."""
+    p, t, t1 = saved["p"], saved["t"], saved["t1"]
+    B, N, C = t.shape
+    h = p["nhead"]
+    rows = B * N
+    g: Dict[str, torch.Tensor] = {}
+    two = lambda a: a.reshape(rows, a.shape[-1])
+    # y = LN2(t1 + f2)
+    dz2, g["layer_norm2.weight"], g["layer_norm2.bias"] = ops.add_layernorm_bwd(t1, saved["f2"], dout.contiguous(), p["g2"], 1e-6)
+    g["linear2.weight"], g["linear2.bias"] = _wgrad(two(dz2), two(saved["fa"]))
+    dfa = torch.mm(two(dz2), p["w_2"]).reshape(B, N, 2 * C)
+    df1 = ops.gelu_bwd(saved["f1"], dfa)
+    g["linear1.weight"], g["linear1.bias"] = _wgrad(two(df1), two(t1))
+    dt1 = torch.addmm(two(dz2), two(df1), p["w_1"]).reshape(B, N, C)            # residual + through linear1
+    # t1 = LN1(t + o)
+    dz1, g["layer_norm1.weight"], g["layer_norm1.bias"] = ops.add_layernorm_bwd(t, saved["o"], dt1, p["g1"], 1e-6)
+    g["self_attn.linears.3.weight"], g["self_attn.linears.3.bias"] = _wgrad(two(dz1), two(saved["att"]))
+    datt = torch.mm(two(dz1), p["w_o"]).reshape(B, N, C)
+    qkv = saved["qkv"]
+    dqkv = ops.linear_attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], saved["ctx"], datt, h)
+    dw, db = _wgrad(two(dqkv), two(t))
+    for i in range(3):
+        g[f"self_attn.linears.{i}.weight"] = dw[i * C:(i + 1) * C]
+        g[f"self_attn.linears.{i}.bias"] = db[i * C:(i + 1) * C]
+    dt = torch.addmm(two(dz1), two(dqkv), p["w_qkv"]).reshape(B, N, C)          # residual + through the QKV projection
+    return dt, g

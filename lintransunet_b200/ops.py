@@ -184,6 +184,37 @@ def add_layernorm(x: torch.Tensor, res: torch.Tensor, gamma: torch.Tensor, beta:
     return y
 
 
+def add_layernorm_bwd(x: torch.Tensor, res: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-6):
+    """Backward of LayerNorm(x + res): returns (dz, dgamma, dbeta); dz is the gradient of x AND of res."""
+    dev = _chk(x, res, dy, gamma)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    L = _native.lib()
+    nbytes = L.ltu_add_layernorm_bwd_workspace(rows, C)
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+    dz = torch.empty_like(x)
+    dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+    with _Guard(dev, ("add_layernorm_bwd", 4 * x.numel() * x.element_size(), 0)) as st:
+        check(L.ltu_add_layernorm_bwd(_p(x), _p(res), _p(dy), _p(gamma), _p(dz), _p(dgamma), _p(dbeta), _p(ws), nbytes,
+                                      rows, C, eps, _dt(x), st), "ltu_add_layernorm_bwd")
+    return dz, dgamma, dbeta
+
+
+def gelu_bwd(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """dx = dy * gelu'(x) for the exact-erf GELU; x is the pre-activation."""
+    dev = _chk(x, dy)
+    dx = torch.empty_like(x)
+    with _Guard(dev, ("gelu_bwd", 3 * x.numel() * x.element_size(), 0)) as st:
+        check(_native.lib().ltu_gelu_bwd(_p(x), _p(dy), _p(dx), x.numel(), _dt(x), st), "ltu_gelu_bwd")
+    return dx
+
+
+def gelu(x: torch.Tensor) -> torch.Tensor:
+    """Out-of-place exact-erf GELU (the training forward keeps the pre-activation for gelu_bwd)."""
+    return gelu_(x.clone())
+
+
 def gelu_(x: torch.Tensor) -> torch.Tensor:
     """In-place exact-erf GELU (model/trans_block.py:201,:208)."""
     dev = _chk(x)
