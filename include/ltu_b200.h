@@ -318,6 +318,14 @@ int ltu_add_layernorm_bwd(const void* x, const void* res, const void* dy, const 
  * x = the pre-activation                                                                          */
 int ltu_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, ltu_stream_t stream);
 
+/* backward of Conv3dPosEmbedding, model/trans_block.py:86-96, parameters: dw fp32 [27][C] in the
+ * packing of ltu_posenc_dwconv3 (tap = (kh*3+kw)*3+kd), dbias fp32 [C].  The input gradient is
+ * ltu_posenc_dwconv3 itself on dy with the 27 taps reversed and a zero bias.
+ * workspace: ltu_posenc_wgrad_workspace(...) bytes; fixed-order sums.                              */
+size_t ltu_posenc_wgrad_workspace(int B, int H, int W, int D, int C);
+int ltu_posenc_wgrad(const void* x, const void* dy, float* dw, float* dbias, void* workspace,
+                     size_t ws_bytes, int B, int H, int W, int D, int C, int dtype, ltu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,8 @@ SIGNATURES = {
     "ltu_add_layernorm_bwd_workspace": (Z, [L, I]),
     "ltu_add_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, Z, L, I, F, I, P]),
     "ltu_gelu_bwd": (I, [P, P, P, L, I, P]),
+    "ltu_posenc_wgrad_workspace": (Z, [I, I, I, I, I]),
+    "ltu_posenc_wgrad": (I, [P, P, P, P, P, Z, I, I, I, I, I, I, P]),
     "ltu_attn_bwd_workspace": (Z, [I, L, I]),
     "ltu_attn_bwd": (I, [P, L, P, P, L, P, L, P, P, P, P, L, P, P, P, Z, I, L, I, I, P]),
 }

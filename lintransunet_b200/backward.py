@@ -20,7 +20,7 @@ import torch.nn.functional as F
 
 from . import ops
 
-__all__ = ["encoder_layer_train", "encoder_layer_backward"]
+__all__ = ["encoder_layer_train", "encoder_layer_backward", "transformer_stack_train", "transformer_stack_backward"]
 
 
 def _params(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
@@ -89,3 +89,42 @@ def encoder_layer_backward(dout: torch.Tensor, saved: dict) -> Tuple[torch.Tenso
         g[f"self_attn.linears.{i}.bias"] = db[i * C:(i + 1) * C]
     dt = torch.addmm(two(dz1), two(dqkv), p["w_qkv"]).reshape(B, N, C)          # residual + through the QKV projection
     return dt, g
+
+
+@torch.no_grad()
+def transformer_stack_train(x: torch.Tensor, layers, pos_encoder) -> Tuple[torch.Tensor, dict]:
+    """The 8-layer stack of PosAttention3DBlock / EmbedAttention3DBlock (model/Unet_3Dblock.py:265-270, :484-490) on
+    a channels-last volume [B,H,W,D,C]: positional depthwise conv once, after layer 0.  `layers` = the ModuleList of
+    SelfAttentionLayer containers, `pos_encoder` = the Conv3dPosEmbedding container that is actually used."""
+    from .unet import _pos_w
+    B, H, W, D, C = x.shape
+    w27, pb = _pos_w(pos_encoder)
+    t = x.reshape(B, H * W * D, C)
+    saved_layers, pos_in = [], None
+    for i, layer in enumerate(layers):
+        t, sv = encoder_layer_train(t, layer)
+        saved_layers.append(sv)
+        if i == 0:
+            pos_in = t.reshape(B, H, W, D, C)
+            t = ops.posenc_dwconv3(pos_in, w27, pb).reshape(B, H * W * D, C)
+    return t.reshape(B, H, W, D, C), dict(layers=saved_layers, pos_in=pos_in, w27=w27, shape=(B, H, W, D, C))
+
+
+@torch.no_grad()
+def transformer_stack_backward(dout: torch.Tensor, saved: dict) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """Gradients of the stack input [B,H,W,D,C] and of its parameters, keyed ``layers.<i>.<name>`` and
+    ``pos.proj.weight`` [C,1,3,3,3] / ``pos.proj.bias`` (the reference's parameter layout: kernel axes (kd,kh,kw))."""
+    B, H, W, D, C = saved["shape"]
+    grads: Dict[str, torch.Tensor] = {}
+    dt = dout.reshape(B, H * W * D, C).contiguous()
+    for i in range(len(saved["layers"]) - 1, -1, -1):
+        if i == 0:
+            dvol, dw27, db = ops.posenc_dwconv3_bwd(saved["pos_in"], dt.reshape(B, H, W, D, C), saved["w27"])
+            # packed [kh,kw,kd][c] = weight[c,0,kd,kh,kw] (unet._pos_w)
+            grads["pos.proj.weight"] = dw27.reshape(3, 3, 3, C).permute(3, 2, 0, 1).unsqueeze(1).contiguous()
+            grads["pos.proj.bias"] = db
+            dt = dvol.reshape(B, H * W * D, C)
+        dt, g = encoder_layer_backward(dt, saved["layers"][i])
+        for k, v in g.items():
+            grads[f"layers.{i}.{k}"] = v
+    return dt.reshape(B, H, W, D, C), grads

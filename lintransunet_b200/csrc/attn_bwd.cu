@@ -11,8 +11,10 @@
 // The column statistics of K (max m_j, sum s_j) are rebuilt in pass 1 from K itself (online max), so the op
 // needs nothing saved from the forward beyond ctx.
 //
-// First correct version: fp32 arithmetic on CUDA cores, one warp per (token, head) with lane = column, the 32x32
-// contractions as shuffle-broadcast FMAs; fixed-order merges => bit-reproducible.  Bytes: pass 1 reads Q, G, K,
+// First version: fp32 arithmetic on CUDA cores, one warp per (token, head) with lane = column, the 32x32
+// contractions as FMAs against shared-memory broadcasts (16-byte broadcast loads; the shuffle-broadcast variant ran
+// at 637 GB/s, bound by the shuffle pipe); fixed-order merges => bit-reproducible.  The tensor-pipe (mma) form
+// of the forward kernels is the next step.  Bytes: pass 1 reads Q, G, K,
 // pass 2 reads Q, K, V, G and writes dQ, dK, dV: 10 N C E against a floor of 7 N C E.
 #include "common.cuh"
 
@@ -23,6 +25,7 @@ int kv_chunks_per_batch_host(int B, int64_t N);              // attn_kernels.cu:
 
 constexpr int kBwdPartF = 32 * 32 + 64;                      // dctx[32][32], m[32], s[32]
 constexpr float kInvSqrtD = 0.17677669529663687f;            // 1/sqrt(32)
+constexpr int kPD = 4;                                       // tokens in flight per warp (register prefetch ring)
 
 template <typename T> __device__ __forceinline__ float ld1(const T* p) { return to_f32(*p); }
 
@@ -45,18 +48,49 @@ attn_bwd_reduce_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict
     const T* k = K + (int64_t)b * N * ldk + col;
     const T* g = G + (int64_t)b * N * ldg + col;
 
+    // The 32-wide broadcasts go through shared memory (one 16-byte broadcast load feeds 4 FMAs); with shuffles the
+    // kernel was bound by the shuffle pipe (one warp shuffle per clock per SM).
+    __shared__ __align__(16) float sp[8][32];
+    float* myp = sp[warp];
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 0.f;
     float m_run = -INFINITY, s_run = 0.f;
-    for (int64_t n = n0 + sub; n < n1; n += wph) {
-        const float qv = ld1(q + n * ldq), kv = ld1(k + n * ldk), gv = ld1(g + n * ldg);
-        const float ex = __expf(qv - warp_max(qv));
-        const float p = ex / warp_sum(ex) * kInvSqrtD;       // Qs[n][lane]
+    // kPD tokens of this warp are always in flight: slot u is reloaded (kPD tokens ahead) right after it is consumed,
+    // so the global-load latency of a token overlaps the arithmetic of the kPD - 1 tokens before it.
+    float rq[kPD], rk[kPD], rg[kPD];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = fmaf(__shfl_sync(0xffffffffu, p, j), gv, acc[j]);
-        if (kv > m_run) { s_run = s_run * __expf(m_run - kv) + 1.f; m_run = kv; }
-        else s_run += __expf(kv - m_run);
+    for (int u = 0; u < kPD; ++u) {
+        const int64_t n = n0 + sub + (int64_t)u * wph;
+        const bool ok = n < n1;
+        rq[u] = ok ? ld1(q + n * ldq) : 0.f;
+        rk[u] = ok ? ld1(k + n * ldk) : 0.f;
+        rg[u] = ok ? ld1(g + n * ldg) : 0.f;
+    }
+    for (int64_t nb = n0 + sub; nb < n1; nb += (int64_t)kPD * wph) {
+#pragma unroll
+        for (int u = 0; u < kPD; ++u) {
+            const int64_t n = nb + (int64_t)u * wph;
+            if (n >= n1) break;                              // warp-uniform
+            const float qv = rq[u], kv = rk[u], gv = rg[u];
+            const int64_t nn = n + (int64_t)kPD * wph;
+            if (nn < n1) { rq[u] = ld1(q + nn * ldq); rk[u] = ld1(k + nn * ldk); rg[u] = ld1(g + nn * ldg); }
+            const float ex = __expf(qv - warp_max(qv));
+            const float p = ex / warp_sum(ex) * kInvSqrtD;   // Qs[n][lane]
+            __syncwarp();                                    // the previous token's reads are done
+            myp[lane] = p;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 pj = *reinterpret_cast<const float4*>(myp + j);
+                acc[j] = fmaf(pj.x, gv, acc[j]);
+                acc[j + 1] = fmaf(pj.y, gv, acc[j + 1]);
+                acc[j + 2] = fmaf(pj.z, gv, acc[j + 2]);
+                acc[j + 3] = fmaf(pj.w, gv, acc[j + 3]);
+            }
+            if (kv > m_run) { s_run = s_run * __expf(m_run - kv) + 1.f; m_run = kv; }
+            else s_run += __expf(kv - m_run);
+        }
     }
     float* out = part + ((((int64_t)b * chunks + chunk) * wph + sub) * heads + hd) * kBwdPartF;
 #pragma unroll
@@ -98,7 +132,7 @@ attn_bwd_combine_kernel(const float* __restrict__ part, const float* __restrict_
 // ---------------------------------------------------------------- pass 2: dQ, dK, dV
 // grid (ctas, B), 256 threads; every CTA owns a contiguous token range, warp w: head w % heads, phase w / heads.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 attn_bwd_apply_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ K, const T* __restrict__ V, int64_t ldkv,
                       const T* __restrict__ G, int64_t ldg, const float* __restrict__ ctx, const float* __restrict__ dctx,
                       const float* __restrict__ kst, T* __restrict__ dQ, T* __restrict__ dK, T* __restrict__ dV,
@@ -121,6 +155,10 @@ attn_bwd_apply_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict_
         dc[i] = db[i * 32 + lane];
     }
     const float M = ks[lane], invS = 1.f / ks[32 + lane], t = ks[64 + lane];
+    __shared__ __align__(16) float sb[8][3][32];             // per-warp broadcast staging of G, V, Ks of one token
+    float* sg = sb[warp][0];
+    float* sv = sb[warp][1];
+    float* sk = sb[warp][2];
     const T* q = Q + (int64_t)b * N * ldq + col;
     const T* k = K + (int64_t)b * N * ldkv + col;
     const T* v = V + (int64_t)b * N * ldkv + col;
@@ -128,23 +166,48 @@ attn_bwd_apply_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict_
     T* dq = dQ + (int64_t)b * N * ldd + col;
     T* dk = dK + (int64_t)b * N * ldd + col;
     T* dv = dV + (int64_t)b * N * ldd + col;
-    for (int64_t n = n0 + sub; n < n1; n += wph) {
-        const float qv = ld1(q + n * ldq), kv = ld1(k + n * ldkv), vv = ld1(v + n * ldkv), gv = ld1(g + n * ldg);
-        const float ex = __expf(qv - warp_max(qv));
-        const float P = ex / warp_sum(ex);
-        const float Ks = __expf(kv - M) * invS;
-        float dqs = 0.f, dks = 0.f, dvv = 0.f;
+    float rq[kPD], rk[kPD], rv[kPD], rg[kPD];                // kPD tokens in flight (see attn_bwd_reduce_kernel)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            dqs = fmaf(__shfl_sync(0xffffffffu, gv, i), cr[i], dqs);     // sum_e G[e]  ctx[lane][e]
-            dks = fmaf(__shfl_sync(0xffffffffu, vv, i), dr[i], dks);     // sum_e V[e]  dctx[lane][e]
-            dvv = fmaf(__shfl_sync(0xffffffffu, Ks, i), dc[i], dvv);     // sum_j Ks[j] dctx[j][lane]
+    for (int u = 0; u < kPD; ++u) {
+        const int64_t n = n0 + sub + (int64_t)u * wph;
+        const bool ok = n < n1;
+        rq[u] = ok ? ld1(q + n * ldq) : 0.f;
+        rk[u] = ok ? ld1(k + n * ldkv) : 0.f;
+        rv[u] = ok ? ld1(v + n * ldkv) : 0.f;
+        rg[u] = ok ? ld1(g + n * ldg) : 0.f;
+    }
+    for (int64_t nb = n0 + sub; nb < n1; nb += (int64_t)kPD * wph) {
+#pragma unroll
+        for (int u = 0; u < kPD; ++u) {
+            const int64_t n = nb + (int64_t)u * wph;
+            if (n >= n1) break;                              // warp-uniform
+            const float qv = rq[u], kv = rk[u], vv = rv[u], gv = rg[u];
+            const int64_t nn = n + (int64_t)kPD * wph;
+            if (nn < n1) {
+                rq[u] = ld1(q + nn * ldq); rk[u] = ld1(k + nn * ldkv); rv[u] = ld1(v + nn * ldkv); rg[u] = ld1(g + nn * ldg);
+            }
+            const float ex = __expf(qv - warp_max(qv));
+            const float P = ex / warp_sum(ex);
+            const float Ks = __expf(kv - M) * invS;
+            __syncwarp();                                    // the previous token's reads are done
+            sg[lane] = gv; sv[lane] = vv; sk[lane] = Ks;
+            __syncwarp();
+            float dqs = 0.f, dks = 0.f, dvv = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(sg + i);   // sum_e G[e]  ctx[lane][e]
+                const float4 b4 = *reinterpret_cast<const float4*>(sv + i);  // sum_e V[e]  dctx[lane][e]
+                const float4 c = *reinterpret_cast<const float4*>(sk + i);   // sum_j Ks[j] dctx[j][lane]
+                dqs = fmaf(a.x, cr[i], dqs); dqs = fmaf(a.y, cr[i + 1], dqs); dqs = fmaf(a.z, cr[i + 2], dqs); dqs = fmaf(a.w, cr[i + 3], dqs);
+                dks = fmaf(b4.x, dr[i], dks); dks = fmaf(b4.y, dr[i + 1], dks); dks = fmaf(b4.z, dr[i + 2], dks); dks = fmaf(b4.w, dr[i + 3], dks);
+                dvv = fmaf(c.x, dc[i], dvv); dvv = fmaf(c.y, dc[i + 1], dvv); dvv = fmaf(c.z, dc[i + 2], dvv); dvv = fmaf(c.w, dc[i + 3], dvv);
+            }
+            const float dP = dqs * kInvSqrtD;
+            const float dot = warp_sum(P * dP);
+            dq[n * ldd] = from_f32<T>(P * (dP - dot));
+            dk[n * ldd] = from_f32<T>(Ks * (dks - t));
+            dv[n * ldd] = from_f32<T>(dvv);
         }
-        const float dP = dqs * kInvSqrtD;
-        const float dot = warp_sum(P * dP);
-        dq[n * ldd] = from_f32<T>(P * (dP - dot));
-        dk[n * ldd] = from_f32<T>(Ks * (dks - t));
-        dv[n * ldd] = from_f32<T>(dvv);
     }
 }
 
@@ -161,7 +224,7 @@ static int attn_bwd_impl(const void* q, int64_t ldq, const void* k, const void* 
     attn_bwd_combine_kernel<<<dim3(heads, B), 1024, 0, st>>>(ws, ctx, dctx, kst, heads, chunks * wph);
     LTU_LAUNCH_CHECK("attn_bwd_combine");
     int64_t ctas = ceil_div64(4 * (int64_t)sm_count(), B);
-    const int64_t max_ctas = ceil_div64(N, 64);              // at least 64 tokens per CTA
+    const int64_t max_ctas = ceil_div64(N, 32);              // at least 32 tokens per CTA
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
     const int64_t tokens_per_cta = ceil_div64(N, ctas);

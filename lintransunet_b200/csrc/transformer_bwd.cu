@@ -117,6 +117,95 @@ gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict
     }
 }
 
+// ---------------------------------------------------------------- Conv3dPosEmbedding weight / bias gradient
+// y = x + bias + sum_tap w[tap][c] x[vox + off(tap)][c]  (model/trans_block.py:86-96 in native axes):
+//   dw[tap][c] = sum_vox dy[vox][c] x[vox + off(tap)][c],  dbias[c] = sum_vox dy[vox][c]
+// (dx needs no kernel of its own: it is the forward kernel applied to dy with the taps reversed and a zero bias).
+// A thread owns 4 channels and every `phases`-th voxel of its CTA's slice; 28 x 4 accumulators in registers; the
+// voxel phases are folded into shared memory one after the other (fixed order), then one partial row per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256)
+posenc_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int B, int H, int W,
+                    int D, int C, int64_t vox_per_cta) {
+    extern __shared__ float sacc[];                          // [28][C]
+    const int cv = C / 4, phases = 256 / cv;
+    const int cg = threadIdx.x % cv, ph = threadIdx.x / cv;
+    const int c4 = cg * 4;
+    const int64_t total = (int64_t)B * H * W * D;
+    const int64_t v0 = (int64_t)blockIdx.x * vox_per_cta;
+    int64_t v1 = v0 + vox_per_cta;
+    if (v1 > total) v1 = total;
+    float acc[28][4];
+#pragma unroll
+    for (int t = 0; t < 28; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
+    for (int64_t vox = v0 + ph; vox < v1; vox += phases) {
+        const int d = (int)(vox % D);
+        int64_t t = vox / D;
+        const int ww = (int)(t % W);
+        t /= W;
+        const int h = (int)(t % H);
+        const int b = (int)(t / H);
+        float g[4];
+        load4(dy + vox * C + c4, g);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[27][i] += g[i];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hh = h + kh - 1;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int w2 = ww + kw - 1;
+                if (w2 < 0 || w2 >= W) continue;
+#pragma unroll
+                for (int kd = 0; kd < 3; ++kd) {
+                    const int dd = d + kd - 1;
+                    if (dd < 0 || dd >= D) continue;
+                    float xv[4];
+                    const int64_t nv = (((int64_t)b * H + hh) * W + w2) * D + dd;
+                    load4(x + nv * C + c4, xv);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[kh * 9 + kw * 3 + kd][i] = fmaf(g[i], xv[i], acc[kh * 9 + kw * 3 + kd][i]);
+                }
+            }
+        }
+    }
+    for (int p = 0; p < phases; ++p) {                       // ordered fold of the voxel phases
+        if (ph == p) {
+#pragma unroll
+            for (int t = 0; t < 28; ++t)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float* s = sacc + t * C + c4 + i;
+                    *s = p == 0 ? acc[t][i] : *s + acc[t][i];
+                }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < 28 * C; i += 256) part[(int64_t)blockIdx.x * 28 * C + i] = sacc[i];
+}
+
+// out[i] = sum over CTAs (in order) of part[cta][i], i < 28*C: rows 0..26 = dw[tap][c], row 27 = dbias[c]
+__global__ void __launch_bounds__(256)
+posenc_wgrad_finalize_kernel(const float* __restrict__ part, int nblocks, int n, float* __restrict__ dw,
+                             float* __restrict__ dbias, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * n + i];
+    if (i < 27 * C) dw[i] = s;
+    else dbias[i - 27 * C] = s;
+}
+
+static inline int posenc_wgrad_blocks(int64_t voxels) {
+    int64_t blocks = ceil_div64(voxels, 64);                 // at least 64 voxels per CTA
+    const int64_t cap = (int64_t)sm_count() * 2;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
 static inline int ln_bwd_blocks(int64_t rows) {
     int64_t blocks = ceil_div64(rows, 8);
     const int64_t cap = (int64_t)sm_count() * 6;             // 6 CTAs / SM of loads in flight; the ordered finalize stays short
@@ -171,5 +260,32 @@ extern "C" int ltu_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, 
     else gelu_bwd_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, nvec);
     LTU_LAUNCH_CHECK("gelu_bwd");
     count_launch(1);
+    return LTU_OK;
+}
+
+extern "C" size_t ltu_posenc_wgrad_workspace(int B, int H, int W, int D, int C) {
+    if (B <= 0 || H <= 0 || W <= 0 || D <= 0 || C <= 0) return 0;
+    return (size_t)posenc_wgrad_blocks((int64_t)B * H * W * D) * 28 * C * sizeof(float);
+}
+
+extern "C" int ltu_posenc_wgrad(const void* x, const void* dy, float* dw, float* dbias, void* ws, size_t ws_bytes, int B,
+                                int H, int W, int D, int C, int dtype, ltu_stream_t stream) {
+    LTU_ARG_CHECK(x && dy && dw && dbias && ws, "posenc_wgrad: null pointer");
+    LTU_ARG_CHECK(B > 0 && H > 0 && W > 0 && D > 0, "posenc_wgrad: bad shape");
+    LTU_ARG_CHECK(C == 128 || C == 256 || C == 64 || C == 32, "posenc_wgrad: C must be 32, 64, 128 or 256 (got %d)", C);
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "posenc_wgrad: bad dtype %d", dtype);
+    LTU_ARG_CHECK(al16(x) && al16(dy), "posenc_wgrad: pointers must be 16-byte aligned");
+    LTU_ARG_CHECK(ws_bytes >= ltu_posenc_wgrad_workspace(B, H, W, D, C), "posenc_wgrad: workspace too small");
+    const int64_t voxels = (int64_t)B * H * W * D;
+    const int blocks = posenc_wgrad_blocks(voxels);
+    const int64_t vox_per_cta = ceil_div64(voxels, blocks);
+    const size_t smem = (size_t)28 * C * sizeof(float);      // <= 28 KB
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LTU_F32) posenc_wgrad_kernel<float><<<blocks, 256, smem, st>>>((const float*)x, (const float*)dy, (float*)ws, B, H, W, D, C, vox_per_cta);
+    else posenc_wgrad_kernel<bf16><<<blocks, 256, smem, st>>>((const bf16*)x, (const bf16*)dy, (float*)ws, B, H, W, D, C, vox_per_cta);
+    LTU_LAUNCH_CHECK("posenc_wgrad");
+    posenc_wgrad_finalize_kernel<<<(28 * C + 255) / 256, 256, 0, st>>>((const float*)ws, blocks, 28 * C, dw, dbias, C);
+    LTU_LAUNCH_CHECK("posenc_wgrad_finalize");
+    count_launch(2);
     return LTU_OK;
 }

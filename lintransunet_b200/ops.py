@@ -234,6 +234,23 @@ def posenc_dwconv3(x: torch.Tensor, w27c: torch.Tensor, bias: torch.Tensor) -> t
     return y
 
 
+def posenc_dwconv3_bwd(x: torch.Tensor, dy: torch.Tensor, w27c: torch.Tensor):
+    """Backward of posenc_dwconv3: returns (dx, dw27c fp32 [27,C], dbias fp32 [C]).  dx is the forward kernel applied
+    to dy with the taps reversed (a stride-1 'same' depthwise correlation is its own transpose up to the flip)."""
+    dev = _chk(x, dy, w27c)
+    B, H, W, D, C = x.shape
+    dx = posenc_dwconv3(dy, w27c.flip(0).contiguous(), torch.zeros(C, dtype=torch.float32, device=dev))
+    L = _native.lib()
+    nbytes = L.ltu_posenc_wgrad_workspace(B, H, W, D, C)
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+    dw = torch.empty(27, C, dtype=torch.float32, device=dev)
+    db = torch.empty(C, dtype=torch.float32, device=dev)
+    with _Guard(dev) as st:
+        check(L.ltu_posenc_wgrad(_p(x), _p(dy), _p(dw), _p(db), _p(ws), nbytes, B, H, W, D, C, _dt(x), st),
+              "ltu_posenc_wgrad")
+    return dx, dw, db
+
+
 # ------------------------------------------------------------------ convolution + InstanceNorm
 def conv_out_size(n: int, k: int, s: int, pad: int) -> int:
     return (n + 2 * pad - k) // s + 1

@@ -80,3 +80,61 @@ def test_encoder_layer_backward_matches_oracle_autograd(d_model, nhead, B, N, dt
     print(f"\n[encoder layer bwd {dtype} C={d_model} B={B} N={N}] dx rel err {e_in:.2e}, worst parameter gradient "
           f"{worst:.2e} ({worst_name})")
     assert e_in <= tol and worst <= tol
+
+
+@pytest.mark.parametrize("shape,C", [((2, 5, 4, 6), 128), ((1, 9, 7, 8), 256), ((2, 3, 3, 3), 128)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1e-2)])
+def test_posenc_backward(shape, C, dtype, tol):
+    """Conv3dPosEmbedding backward: dx through the forward kernel with reversed taps, dw / dbias by ltu_posenc_wgrad."""
+    from lintransunet_b200 import ops
+    from lintransunet_b200.unet import Conv3dPosEmbedding, _pos_w
+    B, H, W, D = shape
+    torch.manual_seed(H * W + C)
+    pe = Conv3dPosEmbedding(C).cuda()
+    w27, pb = _pos_w(pe)
+    x = torch.randn(B, H, W, D, C, device="cuda").to(dtype)
+    dy = torch.randn(B, H, W, D, C, device="cuda").to(dtype)
+    xd = x.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)           # oracle layout [B,C,H,W,D]
+    wd = pe.proj.weight.detach().double().clone().requires_grad_(True)
+    bd = pe.proj.bias.detach().double().clone().requires_grad_(True)
+    O.pos_embedding(xd, wd, bd).backward(dy.double().permute(0, 4, 1, 2, 3))
+    dx, dw27, db = ops.posenc_dwconv3_bwd(x, dy, w27)
+    dw = dw27.reshape(3, 3, 3, C).permute(3, 2, 0, 1).unsqueeze(1)               # -> [C,1,kd,kh,kw]
+    assert rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1)) <= tol
+    assert rel_err(dw, wd.grad) <= 2e-5 and rel_err(db, bd.grad) <= 2e-5
+    dx2, dw2, db2 = ops.posenc_dwconv3_bwd(x, dy, w27)
+    assert torch.equal(dw27, dw2) and torch.equal(db, db2)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 8e-2)])
+def test_transformer_stack_backward_matches_oracle_autograd(dtype, tol):
+    """Eight layers + the positional conv (PosAttention3DBlock / EmbedAttention3DBlock stack) end to end."""
+    from lintransunet_b200.backward import transformer_stack_backward, transformer_stack_train
+    from lintransunet_b200.unet import EmbedAttention3DBlock
+    torch.manual_seed(11)
+    C, nhead, n_layers = 128, 4, 8
+    blk = EmbedAttention3DBlock(32, C, nhead, n_layers).cuda()
+    B, H, W, D = 2, 6, 5, 8
+    x = torch.randn(B, H, W, D, C, device="cuda").to(dtype)
+    dout = torch.randn(B, H, W, D, C, device="cuda").to(dtype)
+    sd = {f"T.{k}": v.detach().double().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+    xd = x.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    yd = O.transformer_stack(xd, sd, "T", nhead, sd["T.pos_encoder.proj.weight"], sd["T.pos_encoder.proj.bias"], n_layers)
+    yd.backward(dout.double().permute(0, 4, 1, 2, 3))
+    y, saved = transformer_stack_train(x, blk.layers, blk.pos_encoder)
+    dx, grads = transformer_stack_backward(dout, saved)
+    assert rel_err(y, yd.detach().permute(0, 2, 3, 4, 1)) <= tol
+    e_in = rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1))
+    worst, worst_name = 0.0, ""
+    for name, gr in grads.items():
+        ref = sd["T." + name.replace("pos.", "pos_encoder.")].grad
+        assert gr.shape == ref.shape, name
+        if name.endswith("self_attn.linears.1.bias"):                             # mathematically zero: noise only
+            assert float(gr.abs().max()) <= tol * float(grads[name[:-4] + "weight"].abs().max())
+            continue
+        e = rel_err(gr, ref)
+        if e > worst:
+            worst, worst_name = e, name
+    assert len(grads) == n_layers * 16 + 2
+    print(f"\n[transformer stack bwd {dtype}] dx rel err {e_in:.2e}, worst parameter gradient {worst:.2e} ({worst_name})")
+    assert e_in <= tol and worst <= tol
