@@ -326,6 +326,15 @@ size_t ltu_posenc_wgrad_workspace(int B, int H, int W, int D, int C);
 int ltu_posenc_wgrad(const void* x, const void* dy, float* dw, float* dbias, void* workspace,
                      size_t ws_bytes, int B, int H, int W, int D, int C, int dtype, ltu_stream_t stream);
 
+/* backward of nn.InstanceNorm3d (+ LeakyReLU), model/Unet_3Dblock.py:325-336,:547-554: x = the RAW
+ * convolution output [B,V,C] the forward normalised, stats fp32 [B,C,2] = (mean, rstd) of the
+ * forward, dy the gradient of act(norm(x)); writes dx.  A residual added after the activation
+ * simply receives dy.  workspace: ltu_instnorm_bwd_workspace(B, voxels, C) bytes; ordered sums.  */
+size_t ltu_instnorm_bwd_workspace(int B, int64_t voxels, int C);
+int ltu_instnorm_bwd(const void* x, const float* stats, const void* dy, void* dx, void* workspace,
+                     size_t ws_bytes, int B, int64_t voxels, int C, int act, int dtype,
+                     ltu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

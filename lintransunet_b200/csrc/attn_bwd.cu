@@ -16,6 +16,8 @@
 // at 637 GB/s, bound by the shuffle pipe); fixed-order merges => bit-reproducible.  The tensor-pipe (mma) form
 // of the forward kernels is the next step.  Bytes: pass 1 reads Q, G, K,
 // pass 2 reads Q, K, V, G and writes dQ, dK, dV: 10 N C E against a floor of 7 N C E.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ltu {
@@ -211,6 +213,22 @@ attn_bwd_apply_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict_
     }
 }
 
+int attn_bwd_combine_launch(const float* ws, const float* ctx, float* dctx, float* kst, int heads, int B, int nparts,
+                            cudaStream_t st) {
+    attn_bwd_combine_kernel<<<dim3(heads, B), 1024, 0, st>>>(ws, ctx, dctx, kst, heads, nparts);
+    LTU_LAUNCH_CHECK("attn_bwd_combine");
+    return LTU_OK;
+}
+
+// bf16 tensor-pipe variant (attn_bwd_tc.cu)
+int attn_bwd_bf16_mma(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* g, int64_t ldg,
+                      const float* ctx, void* dq, void* dk, void* dv, int64_t ldd, float* dctx, float* kst, float* ws,
+                      int B, int64_t N, int heads, cudaStream_t st);
+static bool use_mma_attn_bwd() {
+    static const bool v = [] { const char* e = getenv("LTU_ATTN_BWD_FMA"); return !(e && e[0] == '1'); }();
+    return v;
+}
+
 template <typename T>
 static int attn_bwd_impl(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* g, int64_t ldg,
                          const float* ctx, void* dq, void* dk, void* dv, int64_t ldd, float* dctx, float* kst, float* ws,
@@ -260,5 +278,11 @@ extern "C" int ltu_attn_bwd(const void* q, int64_t ldq, const void* k, const voi
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == LTU_F32)
         return attn_bwd_impl<float>(q, ldq, k, v, ldkv, dout, ldo, ctx, dq, dk, dv, ldd, dctx, kstats, (float*)ws, B, N, heads, st);
+    const bool vec_ok = ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && ldd % 2 == 0 &&
+                        ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                          reinterpret_cast<uintptr_t>(dout)) & 15) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 3) == 0;
+    if (vec_ok && use_mma_attn_bwd())
+        return attn_bwd_bf16_mma(q, ldq, k, v, ldkv, dout, ldo, ctx, dq, dk, dv, ldd, dctx, kstats, (float*)ws, B, N, heads, st);
     return attn_bwd_impl<bf16>(q, ldq, k, v, ldkv, dout, ldo, ctx, dq, dk, dv, ldd, dctx, kstats, (float*)ws, B, N, heads, st);
 }

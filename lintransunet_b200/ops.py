@@ -361,6 +361,22 @@ def instnorm_apply(x: torch.Tensor, stats: torch.Tensor, act: int = ACT_LRELU,
     return y
 
 
+def instnorm_bwd(x_raw: torch.Tensor, stats: torch.Tensor, dy: torch.Tensor, act: int = ACT_LRELU) -> torch.Tensor:
+    """Backward of act(InstanceNorm(x_raw)): x_raw [B,...,C] is the raw conv output, stats [B,C,2] the forward's
+    (mean, rstd).  Returns dx; a residual added after the activation receives dy unchanged."""
+    dev = _chk(x_raw, stats, dy)
+    B, C = x_raw.shape[0], x_raw.shape[-1]
+    V = x_raw.numel() // (B * C)
+    L = _native.lib()
+    nbytes = L.ltu_instnorm_bwd_workspace(B, V, C)
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+    dx = torch.empty_like(x_raw)
+    with _Guard(dev, ("instnorm_bwd", 5 * x_raw.numel() * x_raw.element_size(), 0)) as st:
+        check(L.ltu_instnorm_bwd(_p(x_raw), _p(stats), _p(dy), _p(dx), _p(ws), nbytes, B, V, C, act, _dt(x_raw), st),
+              "ltu_instnorm_bwd")
+    return dx
+
+
 # ------------------------------------------------------------------ U-Net plumbing
 def s2d_input(x: torch.Tensor, dtype: torch.dtype, cpad: int = 4) -> torch.Tensor:
     """[B,1,H,W,D] fp32 -> [B,H/2,W/2,D,cpad] (windows_embedding, model/Unet_3Dblock.py:123-136);

@@ -138,3 +138,23 @@ def test_transformer_stack_backward_matches_oracle_autograd(dtype, tol):
     assert len(grads) == n_layers * 16 + 2
     print(f"\n[transformer stack bwd {dtype}] dx rel err {e_in:.2e}, worst parameter gradient {worst:.2e} ({worst_name})")
     assert e_in <= tol and worst <= tol
+
+
+@pytest.mark.parametrize("shape,C,act", [((2, 6, 5, 7), 16, 1), ((1, 9, 8, 10), 64, 1), ((3, 4, 4, 4), 256, 1), ((2, 12, 10, 9), 32, 0)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-5), (torch.bfloat16, 1.5e-2)])
+def test_instnorm_lrelu_backward(shape, C, act, dtype, tol):
+    """Backward of LeakyReLU(InstanceNorm3d(x)) (model/Unet_3Dblock.py:325-336) on the raw conv output."""
+    from lintransunet_b200 import ops
+    B, H, W, D = shape
+    g = torch.Generator(device="cuda").manual_seed(H * W * D + C)
+    x = (torch.randn(B, H, W, D, C, device="cuda", generator=g) * 1.7 + 0.3).to(dtype)
+    dy = torch.randn(B, H, W, D, C, device="cuda", generator=g).to(dtype)
+    xd = x.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    y = F.instance_norm(xd, eps=1e-5)
+    if act:
+        y = F.leaky_relu(y, 0.01)
+    y.backward(dy.double().permute(0, 4, 1, 2, 3))
+    stats = ops.chan_stats(x, 1e-5)                                   # the forward's (mean, rstd)
+    dx = ops.instnorm_bwd(x, stats, dy, ops.ACT_LRELU if act else ops.ACT_NONE)
+    assert dx.dtype == dtype and rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1)) <= tol
+    assert torch.equal(dx, ops.instnorm_bwd(x, stats, dy, ops.ACT_LRELU if act else ops.ACT_NONE))
