@@ -111,18 +111,22 @@ attn_bwd_combine_kernel(const float* __restrict__ part, const float* __restrict_
     const float* base = part + ((int64_t)b * nparts * heads + hd) * kBwdPartF;
     const int64_t stride = (int64_t)heads * kBwdPartF;
     float a = 0.f;
-    for (int p = 0; p < nparts; ++p) a += base[p * stride + j * 32 + e];
+#pragma unroll 8
+    for (int p = 0; p < nparts; ++p) a += base[p * stride + j * 32 + e];     // fixed order; 8 loads in flight
     const int64_t o = (((int64_t)b * heads + hd) * 32 + j) * 32 + e;
     dctx[o] = a;
     const float t = warp_sum(a * ctx[o]);
-    // column statistics of K for column j (every lane computes the same value from the same data in the same order)
+    // column statistics of K for column j: the lanes split the parts (exact max; per-lane sums in part order, then a
+    // butterfly: the same order every run)
     float M = -INFINITY;
-    for (int p = 0; p < nparts; ++p) M = fmaxf(M, base[p * stride + 1024 + j]);
+    for (int p = e; p < nparts; p += 32) M = fmaxf(M, base[p * stride + 1024 + j]);
+    M = warp_max(M);
     float S = 0.f;
-    for (int p = 0; p < nparts; ++p) {
+    for (int p = e; p < nparts; p += 32) {
         const float mp = base[p * stride + 1024 + j];
         if (mp != -INFINITY) S += base[p * stride + 1056 + j] * __expf(mp - M);
     }
+    S = warp_sum(S);
     if (e == 0) {
         float* ks = kst + ((int64_t)b * heads + hd) * 96;
         ks[j] = M;

@@ -199,22 +199,34 @@ attn_bwd_apply_mma_kernel(const bf16* __restrict__ Q, int64_t ldq, const bf16* _
     const int64_t base_g = (int64_t)b * N * ldg + hd * 32 + 2 * tq;
     const int64_t base_d = (int64_t)b * N * ldd + hd * 32 + 2 * tq;
 
-    for (int64_t t0 = n0 + (int64_t)sub * 16; t0 < n1; t0 += (int64_t)wph * 16) {
-        const int64_t row[2] = {t0 + gq, t0 + gq + 8};
-        const bool ok[2] = {row[0] < n1, row[1] < n1};
-        // ---- A fragments straight from global memory: register (s, x) = row x&1, columns 16 s + 8 (x>>1) + 2t, +1
-        uint32_t aq[2][4], ak[2][4], av[2][4], ag[2][4];
+    // A fragments straight from global memory: register (s, x) = row x&1, columns 16 s + 8 (x>>1) + 2t, +1.
+    // The NEXT tile's fragments are requested before the current tile is processed (one tile of loads always in flight).
+    uint32_t nq[2][4], nk[2][4], nv[2][4], ng[2][4];
+    auto fetch = [&](int64_t t0) {
 #pragma unroll
         for (int s = 0; s < 2; ++s)
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                const int rr = x & 1, co = 16 * s + 8 * (x >> 1);
-                const bool o = ok[rr];
-                aq[s][x] = o ? *reinterpret_cast<const uint32_t*>(Q + base_q + row[rr] * ldq + co) : 0u;
-                ak[s][x] = o ? *reinterpret_cast<const uint32_t*>(K + base_kv + row[rr] * ldkv + co) : 0u;
-                av[s][x] = o ? *reinterpret_cast<const uint32_t*>(V + base_kv + row[rr] * ldkv + co) : 0u;
-                ag[s][x] = o ? *reinterpret_cast<const uint32_t*>(G + base_g + row[rr] * ldg + co) : 0u;
+                const int64_t r = t0 + gq + 8 * (x & 1);
+                const int co = 16 * s + 8 * (x >> 1);
+                const bool o = r < n1;
+                nq[s][x] = o ? *reinterpret_cast<const uint32_t*>(Q + base_q + r * ldq + co) : 0u;
+                nk[s][x] = o ? *reinterpret_cast<const uint32_t*>(K + base_kv + r * ldkv + co) : 0u;
+                nv[s][x] = o ? *reinterpret_cast<const uint32_t*>(V + base_kv + r * ldkv + co) : 0u;
+                ng[s][x] = o ? *reinterpret_cast<const uint32_t*>(G + base_g + r * ldg + co) : 0u;
             }
+    };
+    const int64_t first = n0 + (int64_t)sub * 16;
+    if (first < n1) fetch(first);
+    for (int64_t t0 = first; t0 < n1; t0 += (int64_t)wph * 16) {
+        const int64_t row[2] = {t0 + gq, t0 + gq + 8};
+        const bool ok[2] = {row[0] < n1, row[1] < n1};
+        uint32_t aq[2][4], ak[2][4], av[2][4], ag[2][4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) { aq[s][x] = nq[s][x]; ak[s][x] = nk[s][x]; av[s][x] = nv[s][x]; ag[s][x] = ng[s][x]; }
+        if (t0 + (int64_t)wph * 16 < n1) fetch(t0 + (int64_t)wph * 16);
         // ---- P = softmax_d(Q) per row (quad reduction), Ks = exp(K - M)/S; element [row][n'][i]
         float p[2][4][2], kf[2][4][2];
         float mx[2] = {-INFINITY, -INFINITY};

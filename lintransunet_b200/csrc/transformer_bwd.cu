@@ -86,16 +86,18 @@ add_layernorm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ r, const
     }
 }
 
-// dgamma[c] = sum over CTAs (in order) of part[cta][0][c]; dbeta likewise
+// dgamma[c] = sum over the CTAs of part[cta][0][c]; dbeta likewise.  One warp per output: the lanes take the CTAs
+// cta = lane, lane + 32, ... in order, then a butterfly -- the same summation tree every run.
 __global__ void __launch_bounds__(256)
 ln_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int C, float* __restrict__ dgamma,
                        float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= 2 * C) return;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= 2 * C) return;                                  // warp-uniform
     const int which = c / C, col = c - which * C;
     float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += part[((int64_t)b * 2 + which) * C + col];
-    (which == 0 ? dgamma : dbeta)[col] = s;
+    for (int b = lane; b < nblocks; b += 32) s += part[((int64_t)b * 2 + which) * C + col];
+    s = warp_sum(s);
+    if (lane == 0) (which == 0 ? dgamma : dbeta)[col] = s;
 }
 
 // d/dx [x Phi(x)] = Phi(x) + x phi(x)
@@ -151,23 +153,29 @@ posenc_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __
         load4(dy + vox * C + c4, g);
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[27][i] += g[i];
+        // clamped coordinates + a 0/1 mask instead of branches: the 27 neighbour loads are independent and issued together
+        // (guarded by `continue`s they were serialised, one L2 round trip each)
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
             const int hh = h + kh - 1;
-            if (hh < 0 || hh >= H) continue;
+            const bool vh = hh >= 0 && hh < H;
+            const int hc = vh ? hh : h;
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
                 const int w2 = ww + kw - 1;
-                if (w2 < 0 || w2 >= W) continue;
+                const bool vw = w2 >= 0 && w2 < W;
+                const int wc = vw ? w2 : ww;
 #pragma unroll
                 for (int kd = 0; kd < 3; ++kd) {
                     const int dd = d + kd - 1;
-                    if (dd < 0 || dd >= D) continue;
+                    const bool vd = dd >= 0 && dd < D;
+                    const int dc = vd ? dd : d;
+                    const float m = (vh && vw && vd) ? 1.f : 0.f;
                     float xv[4];
-                    const int64_t nv = (((int64_t)b * H + hh) * W + w2) * D + dd;
+                    const int64_t nv = (((int64_t)b * H + hc) * W + wc) * D + dc;
                     load4(x + nv * C + c4, xv);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[kh * 9 + kw * 3 + kd][i] = fmaf(g[i], xv[i], acc[kh * 9 + kw * 3 + kd][i]);
+                    for (int i = 0; i < 4; ++i) acc[kh * 9 + kw * 3 + kd][i] = fmaf(g[i] * m, xv[i], acc[kh * 9 + kw * 3 + kd][i]);
                 }
             }
         }
@@ -208,7 +216,7 @@ static inline int posenc_wgrad_blocks(int64_t voxels) {
 
 static inline int ln_bwd_blocks(int64_t rows) {
     int64_t blocks = ceil_div64(rows, 8);
-    const int64_t cap = (int64_t)sm_count() * 6;             // 6 CTAs / SM of loads in flight; the ordered finalize stays short
+    const int64_t cap = (int64_t)sm_count() * 8;             // 8 CTAs / SM of loads in flight
     if (blocks > cap) blocks = cap;
     return (int)(blocks < 1 ? 1 : blocks);
 }
@@ -241,7 +249,7 @@ extern "C" int ltu_add_layernorm_bwd(const void* x, const void* res, const void*
     else                  { if (C == 128) LNB(bf16, 128);  else LNB(bf16, 256); }
 #undef LNB
     LTU_LAUNCH_CHECK("add_layernorm_bwd");
-    ln_bwd_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(part, blocks, C, dgamma, dbeta);
+    ln_bwd_finalize_kernel<<<(2 * C + 7) / 8, 256, 0, st>>>(part, blocks, C, dgamma, dbeta);
     LTU_LAUNCH_CHECK("ln_bwd_finalize");
     count_launch(2);
     return LTU_OK;
