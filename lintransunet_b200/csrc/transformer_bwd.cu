@@ -216,7 +216,8 @@ static inline int posenc_wgrad_blocks(int64_t voxels) {
 
 static inline int ln_bwd_blocks(int64_t rows) {
     int64_t blocks = ceil_div64(rows, 8);
-    const int64_t cap = (int64_t)sm_count() * 8;             // 8 CTAs / SM of loads in flight
+    const int64_t cap = (int64_t)sm_count() * 4;             // ONE resident wave (48-64 registers, 9-17 KB: >= 4 CTAs / SM): the rows are
+                                                             // grid-strided, a second partial wave only adds a tail
     if (blocks > cap) blocks = cap;
     return (int)(blocks < 1 ? 1 : blocks);
 }
