@@ -335,6 +335,18 @@ int ltu_instnorm_bwd(const void* x, const float* stats, const void* dy, void* dx
                      size_t ws_bytes, int B, int64_t voxels, int C, int act, int dtype,
                      ltu_stream_t stream);
 
+/* weight gradient of nn.Conv3d (what autograd computes for the convolutions of DownBlock / UpBlock /
+ * the embed blocks / the gates, model/Unet_3Dblock.py:304-323,:519-538,:343-432,:195-215):
+ * x bf16 [B,Hi,Wi,Di,Cin], dy bf16 [B,Ho,Wo,Do,Cout] -> dw fp32 [k^3][Cout][Cin] (tap = (kh*3+kw)*3+kd),
+ * fp32 accumulation on the tensor pipe, ordered finalize.  k in {1,3}, any stride / padding, Cin and
+ * Cout multiples of 8.  The INPUT gradient of a stride-1 convolution is the forward kernel applied
+ * to dy with the filter reversed and its channel axes swapped (lintransunet_b200/backward.py).
+ * workspace: ltu_conv3d_wgrad_workspace(...) bytes.                                               */
+size_t ltu_conv3d_wgrad_workspace(int B, int Ho, int Wo, int Do, int Cin, int Cout, int ksize);
+int ltu_conv3d_wgrad(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, int B,
+                     int Hi, int Wi, int Di, int Cin, int Ho, int Wo, int Do, int Cout, int ksize, int sh,
+                     int sw, int sd, int pad, ltu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

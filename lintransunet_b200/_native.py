@@ -76,6 +76,8 @@ SIGNATURES = {
     "ltu_posenc_wgrad": (I, [P, P, P, P, P, Z, I, I, I, I, I, I, P]),
     "ltu_instnorm_bwd_workspace": (Z, [I, L, I]),
     "ltu_instnorm_bwd": (I, [P, P, P, P, P, Z, I, L, I, I, I, P]),
+    "ltu_conv3d_wgrad_workspace": (Z, [I, I, I, I, I, I, I]),
+    "ltu_conv3d_wgrad": (I, [P, P, P, P, Z, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "ltu_attn_bwd_workspace": (Z, [I, L, I]),
     "ltu_attn_bwd": (I, [P, L, P, P, L, P, L, P, P, P, P, L, P, P, P, Z, I, L, I, I, P]),
 }

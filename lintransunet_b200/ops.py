@@ -361,6 +361,26 @@ def instnorm_apply(x: torch.Tensor, stats: torch.Tensor, act: int = ACT_LRELU,
     return y
 
 
+def conv3d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, stride: Tuple[int, int, int] = (1, 1, 1),
+                 pad: int = 1) -> torch.Tensor:
+    """Weight gradient of nn.Conv3d: x bf16 [B,Hi,Wi,Di,Cin], dy bf16 [B,Ho,Wo,Do,Cout] -> fp32 [k^3, Cout, Cin]
+    (tap = (kh*3+kw)*3+kd).  As a parameter gradient: dw.view(k,k,k,Cout,Cin).permute(3,4,0,1,2)."""
+    dev = _chk(x, dy)
+    if x.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16:
+        raise TypeError("conv3d_wgrad runs on the bf16 path (fp32 accumulation)")
+    B, Hi, Wi, Di, Cin = x.shape
+    _, Ho, Wo, Do, Cout = dy.shape
+    L = _native.lib()
+    nbytes = L.ltu_conv3d_wgrad_workspace(B, Ho, Wo, Do, Cin, Cout, ksize)
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+    dw = torch.empty(ksize ** 3, Cout, Cin, dtype=torch.float32, device=dev)
+    flops = 2 * ksize ** 3 * Cin * Cout * B * Ho * Wo * Do
+    with _Guard(dev, ("conv3d_wgrad", (x.numel() + dy.numel()) * 2, flops)) as st:
+        check(L.ltu_conv3d_wgrad(_p(x), _p(dy), _p(dw), _p(ws), nbytes, B, Hi, Wi, Di, Cin, Ho, Wo, Do, Cout, ksize,
+                                 stride[0], stride[1], stride[2], pad, st), "ltu_conv3d_wgrad")
+    return dw
+
+
 def instnorm_bwd(x_raw: torch.Tensor, stats: torch.Tensor, dy: torch.Tensor, act: int = ACT_LRELU) -> torch.Tensor:
     """Backward of act(InstanceNorm(x_raw)): x_raw [B,...,C] is the raw conv output, stats [B,C,2] the forward's
     (mean, rstd).  Returns dx; a residual added after the activation receives dy unchanged."""

@@ -1,0 +1,59 @@
+"""GPU: backward of nn.Conv3d on the bf16 path (ltu_conv3d_wgrad on the tensor pipe; input gradient through the forward
+kernels with the reversed, transposed filter) against fp64 autograd of F.conv3d on the same bf16-rounded operands.
+SURVEY 8f-1."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # cin, cout, k, stride, (H, W, D), B
+    (16, 16, 3, (1, 1, 1), (6, 5, 9), 2),
+    (8, 16, 3, (1, 1, 1), (8, 6, 10), 1),          # stem (4 input channels padded to 8)
+    (16, 32, 3, (2, 2, 1), (8, 6, 7), 2),          # DownBlock conv2, stride (2,2,1)
+    (32, 64, 3, (2, 2, 2), (6, 8, 6), 2),
+    (64, 64, 3, (1, 1, 1), (5, 4, 6), 3),
+    (128, 128, 3, (1, 1, 1), (3, 4, 4), 2),
+    (256, 128, 3, (1, 1, 1), (3, 3, 4), 1),        # several 64x64 channel blocks
+    (32, 16, 1, (1, 1, 1), (5, 6, 7), 2),          # gate W_g 1x1x1
+    (64, 24, 3, (1, 1, 1), (9, 7, 12), 2),         # Cout not a multiple of 16, ragged voxel tiles
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,shape,B", CASES)
+def test_conv3d_backward_matches_autograd(cin, cout, k, stride, shape, B):
+    from lintransunet_b200.backward import conv3d_backward
+    H, W, D = shape
+    torch.manual_seed(cin * 7 + cout + k)
+    conv = torch.nn.Conv3d(cin, cout, k, stride=stride, padding=k // 2).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.to(torch.bfloat16).float())                 # bf16-representable filter
+    x = torch.randn(B, H, W, D, cin, device="cuda").to(torch.bfloat16)
+    xd = x.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    wd = conv.weight.detach().double().clone().requires_grad_(True)
+    bd = conv.bias.detach().double().clone().requires_grad_(True)
+    yd = F.conv3d(xd, wd, bd, stride=stride, padding=k // 2)
+    dy = torch.randn(B, yd.shape[2], yd.shape[3], yd.shape[4], cout, device="cuda").to(torch.bfloat16)
+    yd.backward(dy.double().permute(0, 4, 1, 2, 3))
+    need_dx = stride == (1, 1, 1)
+    dx, dw, db = conv3d_backward(x, dy, conv, need_dx=need_dx)
+    assert dw.shape == conv.weight.shape and dw.dtype == torch.float32
+    e_w, e_b = rel_err(dw, wd.grad), rel_err(db, bd.grad)
+    e_x = rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1)) if need_dx else 0.0
+    print(f"\n[conv bwd {cin}->{cout} k{k} s{stride}] dW {e_w:.2e} db {e_b:.2e} dx {e_x:.2e}")
+    assert e_w <= 1e-4 and e_b <= 1e-5                     # exact bf16 products, fp32 accumulation
+    assert e_x <= 1e-2                                      # dx is stored in bf16
+    dw2 = conv3d_backward(x, dy, conv, need_dx=False)[1]
+    assert torch.equal(dw, dw2)
+
+
+def test_strided_input_gradient_is_refused():
+    from lintransunet_b200.backward import conv3d_backward
+    conv = torch.nn.Conv3d(16, 16, 3, stride=2, padding=1).cuda()
+    x = torch.zeros(1, 4, 4, 4, 16, device="cuda", dtype=torch.bfloat16)
+    dy = torch.zeros(1, 2, 2, 2, 16, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(NotImplementedError):
+        conv3d_backward(x, dy, conv)
