@@ -345,7 +345,16 @@ int ltu_instnorm_bwd(const void* x, const float* stats, const void* dy, void* dx
 size_t ltu_conv3d_wgrad_workspace(int B, int Ho, int Wo, int Do, int Cin, int Cout, int ksize);
 int ltu_conv3d_wgrad(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, int B,
                      int Hi, int Wi, int Di, int Cin, int Ho, int Wo, int Do, int Cout, int ksize, int sh,
-                     int sw, int sd, int pad, ltu_stream_t stream);
+                     int sw, int sd, int pad, int up2, ltu_stream_t stream);
+/* up2 = 1: the convolution read nn.Upsample(nearest, x2) of x (UpEmbedBlock, Unet_3Dblock.py:419-429);
+ * Ho/Wo/Do then refer to the upsampled extent.
+ * Helpers for the INPUT gradients (both channels-last, C % 4 == 0):
+ *  ltu_zero_insert: z[b, h*sh, w*sw, d*sd, :] = y[b,h,w,d,:], zero elsewhere -- the gradient of a strided
+ *    convolution is the stride-1 forward kernel on z with the reversed, transposed filter;
+ *  ltu_sumpool2: y = sum over 2x2x2 blocks of x -- backward of the nearest x2 upsample.               */
+int ltu_zero_insert(const void* y, void* z, int B, int H, int W, int D, int C, int Hz, int Wz, int Dz,
+                    int sh, int sw, int sd, int dtype, ltu_stream_t stream);
+int ltu_sumpool2(const void* x, void* y, int B, int H, int W, int D, int C, int dtype, ltu_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -132,23 +132,28 @@ def transformer_stack_backward(dout: torch.Tensor, saved: dict) -> Tuple[torch.T
 
 
 @torch.no_grad()
-def conv3d_backward(x: torch.Tensor, dy: torch.Tensor, conv: torch.nn.Conv3d, need_dx: bool = True):
+def conv3d_backward(x: torch.Tensor, dy: torch.Tensor, conv: torch.nn.Conv3d, need_dx: bool = True, up2: bool = False):
     """Backward of a 3x3x3 (pad 1) or 1x1x1 (pad 0) nn.Conv3d on channels-last bf16 tensors: returns (dx | None, dW in
-    the parameter layout [Cout,Cin,k,k,k] fp32, dbias fp32).  dW is ltu_conv3d_wgrad (any stride); dx exists for stride
-    1: the FORWARD convolution kernels applied to dy with the filter reversed and its channel axes swapped."""
+    the parameter layout [Cout,Cin,k,k,k] fp32, dbias fp32).  `up2`: the convolution read nn.Upsample(nearest, x2)(x)
+    (UpEmbedBlock).  dW is ltu_conv3d_wgrad.  dx is the FORWARD convolution kernel applied to the output gradient with
+    the filter reversed and its channel axes swapped -- after zero insertion for a strided convolution, followed by
+    2x2x2 block sums for up2."""
     from .unet import _ConvW
     k = conv.kernel_size[0]
     stride = tuple(conv.stride)
     pad = k // 2
     cout, cin = conv.weight.shape[0], conv.weight.shape[1]
-    dw = ops.conv3d_wgrad(x, dy, k, stride, pad).reshape(k, k, k, cout, cin).permute(3, 4, 0, 1, 2).contiguous()
+    dw = ops.conv3d_wgrad(x, dy, k, stride, pad, up2=up2).reshape(k, k, k, cout, cin).permute(3, 4, 0, 1, 2).contiguous()
     db = torch.sum(dy.reshape(-1, cout), 0, dtype=torch.float32)
     dx = None
     if need_dx:
-        if stride != (1, 1, 1):
-            raise NotImplementedError("input gradient of a strided convolution (transposed convolution) is not built yet")
         t = torch.nn.Conv3d(cout, cin, k, padding=pad, bias=False).to(conv.weight.device)
         t.weight.copy_(conv.weight.detach().flip(2, 3, 4).transpose(0, 1))
         cw = _ConvW(t, True)
-        dx = ops.conv3d(dy, cw.w, None, cw.cout, k, pad=pad, w_tc=cw.w_tc)[0]
+        e = 2 if up2 else 1
+        full = (e * x.shape[1], e * x.shape[2], e * x.shape[3])          # extent the convolution actually read
+        z = dy if stride == (1, 1, 1) else ops.zero_insert(dy, full, stride)
+        dx = ops.conv3d(z, cw.w, None, cw.cout, k, pad=pad, w_tc=cw.w_tc)[0]
+        if up2:
+            dx = ops.sumpool2(dx)
     return dx, dw, db

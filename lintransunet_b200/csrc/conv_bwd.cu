@@ -101,6 +101,53 @@ instnorm_bwd_apply_kernel(const T* __restrict__ x, const float* __restrict__ sta
     }
 }
 
+// z [B, Hz, Wz, Dz, C] = 0 except z[b, h*sh, w*sw, d*sd, :] = y[b, h, w, d, :]: the zero-insertion that turns the input
+// gradient of a strided convolution into a stride-1 convolution of z with the reversed, transposed filter
+template <typename T>
+__global__ void __launch_bounds__(256)
+zero_insert_kernel(const T* __restrict__ y, T* __restrict__ z, int B, int H, int W, int D, int C, int Hz, int Wz, int Dz,
+                   int sh, int sw, int sd) {
+    const int cg = C / 4;
+    const int64_t total = (int64_t)B * Hz * Wz * Dz * cg;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % cg) * 4;
+        int64_t t = idx / cg;
+        const int d = (int)(t % Dz); t /= Dz;
+        const int w = (int)(t % Wz); t /= Wz;
+        const int h = (int)(t % Hz);
+        const int b = (int)(t / Hz);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (h % sh == 0 && w % sw == 0 && d % sd == 0 && h / sh < H && w / sw < W && d / sd < D)
+            load4(y + ((((int64_t)b * H + h / sh) * W + w / sw) * D + d / sd) * C + c4, v);
+        store4(z + (idx / cg) * C + c4, v);
+    }
+}
+
+// y [B, H, W, D, C] = sum of the 2x2x2 block of x [B, 2H, 2W, 2D, C]: backward of nn.Upsample(nearest, x2)
+template <typename T>
+__global__ void __launch_bounds__(256)
+sumpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int D, int C) {
+    const int cg = C / 4;
+    const int64_t total = (int64_t)B * H * W * D * cg;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % cg) * 4;
+        int64_t t = idx / cg;
+        const int d = (int)(t % D); t /= D;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const int b = (int)(t / H);
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v[4];
+            load4(x + ((((int64_t)b * 2 * H + 2 * h + (k >> 2)) * 2 * W + 2 * w + ((k >> 1) & 1)) * 2 * D + 2 * d + (k & 1)) * C + c4, v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[i] += v[i];
+        }
+        store4(y + (idx / cg) * C + c4, s);
+    }
+}
+
 static inline int in_bwd_chunks(int64_t V) {
     int64_t c = V / 512;
     if (c > 256) c = 256;
@@ -144,5 +191,39 @@ extern "C" int ltu_instnorm_bwd(const void* x, const float* stats, const void* d
     else instnorm_bwd_apply_kernel<bf16><<<dim3((unsigned)bx, B), 256, 0, st>>>((const bf16*)x, stats, msum, (const bf16*)dy, (bf16*)dx, voxels, C, act);
     LTU_LAUNCH_CHECK("instnorm_bwd_apply");
     count_launch(3);
+    return LTU_OK;
+}
+
+static unsigned ew_grid(int64_t items) {
+    int64_t b = ceil_div64(items, 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (b > cap) b = cap;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+extern "C" int ltu_zero_insert(const void* y, void* z, int B, int H, int W, int D, int C, int Hz, int Wz, int Dz, int sh,
+                               int sw, int sd, int dtype, ltu_stream_t stream) {
+    LTU_ARG_CHECK(y && z && B > 0 && H > 0 && W > 0 && D > 0 && C > 0 && C % 4 == 0, "zero_insert: bad arguments");
+    LTU_ARG_CHECK(sh >= 1 && sw >= 1 && sd >= 1 && Hz >= (H - 1) * sh + 1 && Wz >= (W - 1) * sw + 1 && Dz >= (D - 1) * sd + 1,
+                  "zero_insert: the target volume is too small for the stride");
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "zero_insert: bad dtype %d", dtype);
+    LTU_ARG_CHECK(a16(y) && a16(z), "zero_insert: pointers must be 16-byte aligned");
+    const unsigned g = ew_grid((int64_t)B * Hz * Wz * Dz * (C / 4));
+    if (dtype == LTU_F32) zero_insert_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)y, (float*)z, B, H, W, D, C, Hz, Wz, Dz, sh, sw, sd);
+    else zero_insert_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)y, (bf16*)z, B, H, W, D, C, Hz, Wz, Dz, sh, sw, sd);
+    LTU_LAUNCH_CHECK("zero_insert");
+    count_launch(1);
+    return LTU_OK;
+}
+
+extern "C" int ltu_sumpool2(const void* x, void* y, int B, int H, int W, int D, int C, int dtype, ltu_stream_t stream) {
+    LTU_ARG_CHECK(x && y && B > 0 && H > 0 && W > 0 && D > 0 && C > 0 && C % 4 == 0, "sumpool2: bad arguments");
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "sumpool2: bad dtype %d", dtype);
+    LTU_ARG_CHECK(a16(x) && a16(y), "sumpool2: pointers must be 16-byte aligned");
+    const unsigned g = ew_grid((int64_t)B * H * W * D * (C / 4));
+    if (dtype == LTU_F32) sumpool2_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, B, H, W, D, C);
+    else sumpool2_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, D, C);
+    LTU_LAUNCH_CHECK("sumpool2");
+    count_launch(1);
     return LTU_OK;
 }

@@ -32,7 +32,7 @@ __device__ __forceinline__ void mma_w(float (&d)[4], const uint32_t (&a)[4], uin
 
 struct WgradParams {
     const bf16* x; const bf16* dy; float* part;
-    int B, Hi, Wi, Di, Cin, Ho, Wo, Do, Cout, k, sh, sw, sd, pad;
+    int B, Hi, Wi, Di, Cin, Ho, Wo, Do, Cout, k, sh, sw, sd, pad, up2;   // up2: the conv reads nearest-x2-upsampled x
     int64_t vout;                                            // B*Ho*Wo*Do
     int64_t vox_per_cta;                                     // multiple of kTile
     int cin_blocks, CoP, CiP;                                // channel counts padded to 64
@@ -73,8 +73,9 @@ conv_wgrad_mma_kernel(const WgradParams p) {
             const int b = (int)(t / p.Ho);
             gd = p.dy + v * p.Cout + co0 + c * 8;
             const int hi = hO * p.sh + kh - p.pad, wi = wO * p.sw + kw - p.pad, di = dO * p.sd + kd - p.pad;
-            xok = hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi && di >= 0 && di < p.Di;
-            if (xok) gx = p.x + ((((int64_t)b * p.Hi + hi) * p.Wi + wi) * p.Di + di) * p.Cin + ci0 + c * 8;
+            const int e = p.up2 ? 2 : 1;                     // bounds in the (virtually upsampled) input, then the source voxel
+            xok = hi >= 0 && hi < e * p.Hi && wi >= 0 && wi < e * p.Wi && di >= 0 && di < e * p.Di;
+            if (xok) gx = p.x + ((((int64_t)b * p.Hi + hi / e) * p.Wi + wi / e) * p.Di + di / e) * p.Cin + ci0 + c * 8;
         }
         cp_async16_zfill(sD[buf] + r * kRow + c * 8, (vok && co_ok) ? gd : p.dy, (vok && co_ok) ? 16 : 0);
         cp_async16_zfill(sX[buf] + r * kRow + c * 8, (xok && ci_ok) ? gx : p.x, (xok && ci_ok) ? 16 : 0);
@@ -159,20 +160,22 @@ extern "C" size_t ltu_conv3d_wgrad_workspace(int B, int Ho, int Wo, int Do, int 
 
 extern "C" int ltu_conv3d_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes, int B, int Hi, int Wi,
                                 int Di, int Cin, int Ho, int Wo, int Do, int Cout, int ksize, int sh, int sw, int sd, int pad,
-                                ltu_stream_t stream) {
+                                int up2, ltu_stream_t stream) {
     LTU_ARG_CHECK(x && dy && dw && ws, "conv3d_wgrad: null pointer");
     LTU_ARG_CHECK(B > 0 && Hi > 0 && Wi > 0 && Di > 0 && Ho > 0 && Wo > 0 && Do > 0, "conv3d_wgrad: bad shape");
     LTU_ARG_CHECK(ksize == 1 || ksize == 3, "conv3d_wgrad: kernel size must be 1 or 3");
     LTU_ARG_CHECK(Cin % 8 == 0 && Cout % 8 == 0 && Cin <= 1024 && Cout <= 1024, "conv3d_wgrad: Cin=%d and Cout=%d must be multiples of 8", Cin, Cout);
     LTU_ARG_CHECK(sh >= 1 && sw >= 1 && sd >= 1 && pad >= 0, "conv3d_wgrad: bad stride / padding");
-    LTU_ARG_CHECK(Ho == (Hi + 2 * pad - ksize) / sh + 1 && Wo == (Wi + 2 * pad - ksize) / sw + 1 && Do == (Di + 2 * pad - ksize) / sd + 1,
+    const int ue = up2 ? 2 : 1;
+    LTU_ARG_CHECK(Ho == (ue * Hi + 2 * pad - ksize) / sh + 1 && Wo == (ue * Wi + 2 * pad - ksize) / sw + 1 &&
+                  Do == (ue * Di + 2 * pad - ksize) / sd + 1,
                   "conv3d_wgrad: output size does not match input size, kernel, stride and padding");
     LTU_ARG_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0, "conv3d_wgrad: pointers must be 16-byte aligned");
     LTU_ARG_CHECK(ws_bytes >= ltu_conv3d_wgrad_workspace(B, Ho, Wo, Do, Cin, Cout, ksize), "conv3d_wgrad: workspace too small");
     WgradParams p;
     p.x = (const bf16*)x; p.dy = (const bf16*)dy; p.part = (float*)ws;
     p.B = B; p.Hi = Hi; p.Wi = Wi; p.Di = Di; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Do = Do; p.Cout = Cout;
-    p.k = ksize; p.sh = sh; p.sw = sw; p.sd = sd; p.pad = pad;
+    p.k = ksize; p.sh = sh; p.sw = sw; p.sd = sd; p.pad = pad; p.up2 = up2 ? 1 : 0;
     p.vout = (int64_t)B * Ho * Wo * Do;
     const int taps = ksize * ksize * ksize, cob = (Cout + 63) / 64, cib = (Cin + 63) / 64;
     const int chunks = wgrad_chunks(p.vout, taps, cob * cib);

@@ -361,10 +361,32 @@ def instnorm_apply(x: torch.Tensor, stats: torch.Tensor, act: int = ACT_LRELU,
     return y
 
 
+def zero_insert(y: torch.Tensor, size: Tuple[int, int, int], stride: Tuple[int, int, int]) -> torch.Tensor:
+    """z [B,*size,C] with z[:, ::sh, ::sw, ::sd] = y and zeros elsewhere (input gradient of a strided convolution)."""
+    dev = _chk(y)
+    B, H, W, D, C = y.shape
+    z = torch.empty(B, size[0], size[1], size[2], C, dtype=y.dtype, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_zero_insert(_p(y), _p(z), B, H, W, D, C, size[0], size[1], size[2], stride[0], stride[1],
+                                            stride[2], _dt(y), st), "ltu_zero_insert")
+    return z
+
+
+def sumpool2(x: torch.Tensor) -> torch.Tensor:
+    """[B,2H,2W,2D,C] -> [B,H,W,D,C]: sums of 2x2x2 blocks (backward of the nearest x2 upsample)."""
+    dev = _chk(x)
+    B, H2, W2, D2, C = x.shape
+    y = torch.empty(B, H2 // 2, W2 // 2, D2 // 2, C, dtype=x.dtype, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_sumpool2(_p(x), _p(y), B, H2 // 2, W2 // 2, D2 // 2, C, _dt(x), st), "ltu_sumpool2")
+    return y
+
+
 def conv3d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, stride: Tuple[int, int, int] = (1, 1, 1),
-                 pad: int = 1) -> torch.Tensor:
+                 pad: int = 1, up2: bool = False) -> torch.Tensor:
     """Weight gradient of nn.Conv3d: x bf16 [B,Hi,Wi,Di,Cin], dy bf16 [B,Ho,Wo,Do,Cout] -> fp32 [k^3, Cout, Cin]
-    (tap = (kh*3+kw)*3+kd).  As a parameter gradient: dw.view(k,k,k,Cout,Cin).permute(3,4,0,1,2)."""
+    (tap = (kh*3+kw)*3+kd).  As a parameter gradient: dw.view(k,k,k,Cout,Cin).permute(3,4,0,1,2).  `up2`: the
+    convolution read the nearest-x2 upsampling of x."""
     dev = _chk(x, dy)
     if x.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16:
         raise TypeError("conv3d_wgrad runs on the bf16 path (fp32 accumulation)")
@@ -377,7 +399,7 @@ def conv3d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, stride: Tuple[in
     flops = 2 * ksize ** 3 * Cin * Cout * B * Ho * Wo * Do
     with _Guard(dev, ("conv3d_wgrad", (x.numel() + dy.numel()) * 2, flops)) as st:
         check(L.ltu_conv3d_wgrad(_p(x), _p(dy), _p(dw), _p(ws), nbytes, B, Hi, Wi, Di, Cin, Ho, Wo, Do, Cout, ksize,
-                                 stride[0], stride[1], stride[2], pad, st), "ltu_conv3d_wgrad")
+                                 stride[0], stride[1], stride[2], pad, int(up2), st), "ltu_conv3d_wgrad")
     return dw
 
 

@@ -38,11 +38,10 @@ def test_conv3d_backward_matches_autograd(cin, cout, k, stride, shape, B):
     yd = F.conv3d(xd, wd, bd, stride=stride, padding=k // 2)
     dy = torch.randn(B, yd.shape[2], yd.shape[3], yd.shape[4], cout, device="cuda").to(torch.bfloat16)
     yd.backward(dy.double().permute(0, 4, 1, 2, 3))
-    need_dx = stride == (1, 1, 1)
-    dx, dw, db = conv3d_backward(x, dy, conv, need_dx=need_dx)
+    dx, dw, db = conv3d_backward(x, dy, conv)
     assert dw.shape == conv.weight.shape and dw.dtype == torch.float32
     e_w, e_b = rel_err(dw, wd.grad), rel_err(db, bd.grad)
-    e_x = rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1)) if need_dx else 0.0
+    e_x = rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1))
     print(f"\n[conv bwd {cin}->{cout} k{k} s{stride}] dW {e_w:.2e} db {e_b:.2e} dx {e_x:.2e}")
     assert e_w <= 1e-4 and e_b <= 1e-5                     # exact bf16 products, fp32 accumulation
     assert e_x <= 1e-2                                      # dx is stored in bf16
@@ -50,10 +49,22 @@ def test_conv3d_backward_matches_autograd(cin, cout, k, stride, shape, B):
     assert torch.equal(dw, dw2)
 
 
-def test_strided_input_gradient_is_refused():
+@pytest.mark.parametrize("cin,cout,shape", [(128, 32, (5, 4, 6)), (256, 64, (3, 4, 4))])
+def test_upsampled_conv3d_backward_matches_autograd(cin, cout, shape):
+    """UpEmbedBlock: nn.Upsample(nearest, x2) -> Conv3d (model/Unet_3Dblock.py:419-429)."""
     from lintransunet_b200.backward import conv3d_backward
-    conv = torch.nn.Conv3d(16, 16, 3, stride=2, padding=1).cuda()
-    x = torch.zeros(1, 4, 4, 4, 16, device="cuda", dtype=torch.bfloat16)
-    dy = torch.zeros(1, 2, 2, 2, 16, device="cuda", dtype=torch.bfloat16)
-    with pytest.raises(NotImplementedError):
-        conv3d_backward(x, dy, conv)
+    H, W, D = shape
+    torch.manual_seed(cin + cout)
+    conv = torch.nn.Conv3d(cin, cout, 3, padding=1).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.to(torch.bfloat16).float())
+    x = torch.randn(2, H, W, D, cin, device="cuda").to(torch.bfloat16)
+    xd = x.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    wd = conv.weight.detach().double().clone().requires_grad_(True)
+    yd = F.conv3d(F.interpolate(xd, scale_factor=2, mode="nearest"), wd, None, padding=1)
+    dy = torch.randn(2, 2 * H, 2 * W, 2 * D, cout, device="cuda").to(torch.bfloat16)
+    yd.backward(dy.double().permute(0, 4, 1, 2, 3))
+    dx, dw, _ = conv3d_backward(x, dy, conv, up2=True)
+    e_w, e_x = rel_err(dw, wd.grad), rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1))
+    print(f"\n[up2 conv bwd {cin}->{cout}] dW {e_w:.2e} dx {e_x:.2e}")
+    assert e_w <= 1e-4 and e_x <= 2e-2                      # dx: bf16 full-resolution gradient, then 8-term bf16 sums
