@@ -21,7 +21,7 @@ import torch.nn.functional as F
 from . import ops
 
 __all__ = ["encoder_layer_train", "encoder_layer_backward", "transformer_stack_train", "transformer_stack_backward",
-           "conv3d_backward"]
+           "conv3d_backward", "conv_in_act_train", "conv_in_act_backward", "encoder_train", "encoder_backward"]
 
 
 def _params(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
@@ -143,7 +143,8 @@ def conv3d_backward(x: torch.Tensor, dy: torch.Tensor, conv: torch.nn.Conv3d, ne
     stride = tuple(conv.stride)
     pad = k // 2
     cout, cin = conv.weight.shape[0], conv.weight.shape[1]
-    dw = ops.conv3d_wgrad(x, dy, k, stride, pad, up2=up2).reshape(k, k, k, cout, cin).permute(3, 4, 0, 1, 2).contiguous()
+    cin_x = x.shape[-1]                                    # > cin for the zero-padded stem input
+    dw = ops.conv3d_wgrad(x, dy, k, stride, pad, up2=up2).reshape(k, k, k, cout, cin_x).permute(3, 4, 0, 1, 2).contiguous()
     db = torch.sum(dy.reshape(-1, cout), 0, dtype=torch.float32)
     dx = None
     if need_dx:
@@ -157,3 +158,59 @@ def conv3d_backward(x: torch.Tensor, dy: torch.Tensor, conv: torch.nn.Conv3d, ne
         if up2:
             dx = ops.sumpool2(dx)
     return dx, dw, db
+
+
+# ----------------------------------------------------------------------------- conv blocks (bf16 path)
+@torch.no_grad()
+def conv_in_act_train(x: torch.Tensor, conv: torch.nn.Conv3d, residual=None, cin_pad: int = 0):
+    """Conv3d -> InstanceNorm3d -> LeakyReLU (+ residual) keeping the raw convolution output and the statistics
+    (DownBlock / UpBlock / Encoder stem, model/Unet_3Dblock.py:325-336,:547-554,:596-600).  bf16, channels-last."""
+    from .unet import _ConvW
+    cw = _ConvW(conv, True, cin_pad=cin_pad)
+    stride = tuple(conv.stride)
+    raw, partials, _ = ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, stride=stride, pad=cw.k // 2, want_stats=True, w_tc=cw.w_tc)
+    V = raw.shape[1] * raw.shape[2] * raw.shape[3]
+    stats = ops.instnorm_finalize(partials, V)
+    y = ops.instnorm_apply(raw, stats, ops.ACT_LRELU, residual=residual, inplace=False)
+    return y, dict(x=x, raw=raw, stats=stats, conv=conv, residual=residual is not None)
+
+
+@torch.no_grad()
+def conv_in_act_backward(dy: torch.Tensor, saved: dict, need_dx: bool = True):
+    """Returns (dx | None, dW, dbias); a residual added after the activation receives dy itself (the caller adds it)."""
+    draw = ops.instnorm_bwd(saved["raw"], saved["stats"], dy.contiguous(), ops.ACT_LRELU)
+    return conv3d_backward(saved["x"], draw, saved["conv"], need_dx=need_dx)
+
+
+@torch.no_grad()
+def encoder_train(x: torch.Tensor, enc):
+    """Encoder.forward (model/Unet_3Dblock.py:596-607) on the bf16 path with everything the backward needs.
+    x fp32 [B,1,H,W,D]; `enc` = the lintransunet_b200.unet.Encoder container.  Returns (bottleneck, skips, saved)."""
+    a = ops.s2d_input(x.contiguous().float(), torch.bfloat16, cpad=8)          # 4 channels + 4 zero channels
+    a, sv_stem = conv_in_act_train(a, enc.input_block, cin_pad=8)
+    blocks, skips = [], []
+    for blk in enc.block_list:
+        s, sv1 = conv_in_act_train(a, blk.conv1, residual=a)                  # DownBlock :327-331
+        skips.append(s)
+        a, sv2 = conv_in_act_train(s, blk.conv2)                              # :335-336 (strided)
+        blocks.append((sv1, sv2))
+    return a, skips, dict(stem=sv_stem, blocks=blocks)
+
+
+@torch.no_grad()
+def encoder_backward(d_bottle: torch.Tensor, d_skips, saved: dict) -> Dict[str, torch.Tensor]:
+    """Parameter gradients of the Encoder, keyed like its state_dict (``input_block.weight`` ...,
+    ``block_list.<i>.conv{1,2}.{weight,bias}``), given the gradients of the bottleneck and of the four skips
+    (None = no gradient flows into that skip)."""
+    grads: Dict[str, torch.Tensor] = {}
+    da = d_bottle
+    for i in range(len(saved["blocks"]) - 1, -1, -1):
+        sv1, sv2 = saved["blocks"][i]
+        ds, grads[f"block_list.{i}.conv2.weight"], grads[f"block_list.{i}.conv2.bias"] = conv_in_act_backward(da, sv2)
+        if d_skips is not None and d_skips[i] is not None:
+            ds = ds + d_skips[i]
+        dx1, grads[f"block_list.{i}.conv1.weight"], grads[f"block_list.{i}.conv1.bias"] = conv_in_act_backward(ds, sv1)
+        da = dx1 + ds                                                          # s = act(norm(conv1(a))) + a
+    _, dw, grads["input_block.bias"] = conv_in_act_backward(da, saved["stem"], need_dx=False)
+    grads["input_block.weight"] = dw[:, :4].contiguous()                       # drop the four zero-padded input channels
+    return grads
