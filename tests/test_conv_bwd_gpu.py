@@ -70,11 +70,18 @@ def test_upsampled_conv3d_backward_matches_autograd(cin, cout, shape):
     assert e_w <= 1e-4 and e_x <= 2e-2                      # dx: bf16 full-resolution gradient, then 8-term bf16 sums
 
 
+def _stored(cd: torch.Tensor, raw_cl: torch.Tensor) -> torch.Tensor:
+    """Straight-through substitution: the reference continues from the convolution output AS THE FORWARD STORED IT (bf16),
+    gradients flow to the fp64 convolution unchanged.  Without it the comparison measures how many LeakyReLU signs of
+    near-zero activations a bf16 rounding flips (dozens per layer, each worth |dy| in the max norm), not the kernels."""
+    return cd + (raw_cl.double().permute(0, 4, 1, 2, 3) - cd).detach()
+
+
 @pytest.mark.parametrize("cin,cout,stride,shape,residual", [(16, 16, (1, 1, 1), (12, 10, 8), True), (32, 64, (2, 2, 2), (8, 8, 8), False),
                                                             (128, 256, (2, 2, 2), (4, 4, 8), False), (128, 128, (1, 1, 1), (4, 4, 8), True)])
 def test_conv_instnorm_lrelu_block_backward(cin, cout, stride, shape, residual):
     """One Conv3d -> InstanceNorm3d -> LeakyReLU (+ residual) stage of DownBlock (model/Unet_3Dblock.py:325-336): input and
-    parameter gradients against fp64 autograd on the same bf16 input."""
+    parameter gradients against fp64 autograd on the same bf16 input and the same stored convolution output."""
     from lintransunet_b200.backward import conv_in_act_backward, conv_in_act_train
     H, W, D = shape
     torch.manual_seed(cin + cout)
@@ -82,13 +89,15 @@ def test_conv_instnorm_lrelu_block_backward(cin, cout, stride, shape, residual):
     with torch.no_grad():
         conv.weight.copy_(conv.weight.to(torch.bfloat16).float())
     x = torch.randn(2, H, W, D, cin, device="cuda").to(torch.bfloat16)
+    y, saved = conv_in_act_train(x, conv, residual=x if residual else None)
     xd = x.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
     wd = conv.weight.detach().double().clone().requires_grad_(True)
     bd = conv.bias.detach().double().clone().requires_grad_(True)
-    yd = F.leaky_relu(F.instance_norm(F.conv3d(xd, wd, bd, stride=stride, padding=1), eps=1e-5), 0.01)
+    cd = F.conv3d(xd, wd, bd, stride=stride, padding=1)
+    assert rel_err(saved["raw"], cd.detach().permute(0, 2, 3, 4, 1)) <= 1e-2
+    yd = F.leaky_relu(F.instance_norm(_stored(cd, saved["raw"]), eps=1e-5), 0.01)
     if residual:
         yd = yd + xd
-    y, saved = conv_in_act_train(x, conv, residual=x if residual else None)
     assert rel_err(y, yd.detach().permute(0, 2, 3, 4, 1)) <= 1e-2
     dy = torch.randn(y.shape, device="cuda").to(torch.bfloat16)
     yd.backward(dy.double().permute(0, 4, 1, 2, 3))
@@ -97,43 +106,54 @@ def test_conv_instnorm_lrelu_block_backward(cin, cout, stride, shape, residual):
         dx = dx + dy
     e_x, e_w = rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1)), rel_err(dw, wd.grad)
     print(f"\n[conv+IN+LReLU bwd {cin}->{cout} s{stride}] dx {e_x:.2e} dW {e_w:.2e}")
-    assert e_x <= 3e-2 and e_w <= 3e-2            # the raw conv output is stored in bf16: xhat (and a few LeakyReLU signs) move
+    assert e_x <= 1.5e-2 and e_w <= 1e-2          # the gradient of the raw output is stored in bf16 before it is contracted
 
 
-def test_encoder_backward_matches_oracle_autograd():
-    """All 18 parameter gradients of Encoder (stem + 4 DownBlocks, model/Unet_3Dblock.py:596-607) from the native
-    kernels (bf16 storage, fp32 accumulation) against fp64 autograd through oracle.encoder_forward."""
+def test_encoder_backward_matches_autograd_on_the_stored_activations():
+    """All 18 parameter gradients of Encoder (stem + 4 DownBlocks, model/Unet_3Dblock.py:596-607: restated here like
+    oracle.encoder_forward, plus the straight-through substitution of every stored convolution output)."""
     from oracle import ltu_oracle as O
     from lintransunet_b200.backward import encoder_backward, encoder_train
     from lintransunet_b200.unet import Encoder
     torch.manual_seed(5)
     cfg = O.UnetConfig(dim_output=2)
     enc = Encoder(list(cfg.num_layers), 1).cuda()
-    x = torch.randn(1, 1, 128, 128, 32, device="cuda")
-    sd = {f"encode.{k}": v.detach().double().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
-    bottle_d, skips_d = O.encoder_forward(x.double(), sd, cfg)
+    with torch.no_grad():
+        for p_ in enc.parameters():
+            p_.copy_(p_.to(torch.bfloat16).float())
+    x = torch.randn(2, 1, 64, 64, 16, device="cuda")
     bottle, skips, saved = encoder_train(x, enc)
+    sd = {k: v.detach().double().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
+    cia = lambda cd, sv, res=None: O.lrelu(O.inorm(_stored(cd, sv["raw"]))) + (0 if res is None else res)
+    a = O.space_to_depth(x.to(torch.bfloat16).double(), 2)                      # the kernels read the bf16 input
+    a = cia(F.conv3d(a, sd["input_block.weight"], sd["input_block.bias"], padding=1), saved["stem"])
+    skips_d = []
+    for i, (sv1, sv2) in enumerate(saved["blocks"]):
+        p_ = f"block_list.{i}"
+        s_ = cia(F.conv3d(a, sd[p_ + ".conv1.weight"], sd[p_ + ".conv1.bias"], padding=1), sv1, a)
+        skips_d.append(s_)
+        a = cia(F.conv3d(s_, sd[p_ + ".conv2.weight"], sd[p_ + ".conv2.bias"], stride=(2, 2, i % 2 + 1), padding=1), sv2)
     to_cl = lambda t: t.permute(0, 2, 3, 4, 1)
-    print(f"\n[encoder fwd bf16] bottleneck rel err {rel_err(bottle, to_cl(bottle_d.detach())):.2e}")
+    assert rel_err(bottle, to_cl(a.detach())) <= 2e-2
     g = torch.Generator(device="cuda").manual_seed(9)
     d_bottle = torch.randn(bottle.shape, device="cuda", generator=g).to(torch.bfloat16)
     d_skips = [torch.randn(s.shape, device="cuda", generator=g).to(torch.bfloat16) for s in skips]
-    loss = (bottle_d * d_bottle.double().permute(0, 4, 1, 2, 3)).sum()
+    loss = (a * d_bottle.double().permute(0, 4, 1, 2, 3)).sum()
     for s_d, ds in zip(skips_d, d_skips):
         loss = loss + (s_d * ds.double().permute(0, 4, 1, 2, 3)).sum()
     loss.backward()
     grads = encoder_backward(d_bottle, d_skips, saved)
-    assert sorted(grads) == sorted(k[7:] for k in sd)
-    worst = 0.0
+    assert sorted(grads) == sorted(sd)
+    worst, worst_name = 0.0, ""
     for name, gr in sorted(grads.items()):
-        ref = sd["encode." + name].grad
+        ref = sd[name].grad
         assert gr.shape == ref.shape, name
         if name.endswith(".bias"):
             # a bias in front of an InstanceNorm has a mathematically zero gradient: noise on both sides
             assert float(gr.abs().max()) <= 5e-2 * float(grads[name[:-4] + "weight"].abs().max()), name
             continue
-        # relative L2 error: the layers are deep in a bf16 network, single elements carry the accumulated rounding
-        e = float((gr.double() - ref).norm() / ref.norm())
-        print(f"[encoder bwd bf16] {name}: relative L2 error {e:.2e}, max-norm error {rel_err(gr, ref):.2e}")
-        worst = max(worst, e)
-    assert worst <= 1e-1
+        e = rel_err(gr, ref)
+        if e > worst:
+            worst, worst_name = e, name
+    print(f"\n[encoder bwd bf16] worst weight-gradient error {worst:.2e} ({worst_name})")
+    assert worst <= 5e-2                           # nine stages of bf16 gradients
