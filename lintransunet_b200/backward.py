@@ -21,7 +21,8 @@ import torch.nn.functional as F
 from . import ops
 
 __all__ = ["encoder_layer_train", "encoder_layer_backward", "transformer_stack_train", "transformer_stack_backward",
-           "conv3d_backward", "conv_in_act_train", "conv_in_act_backward", "encoder_train", "encoder_backward"]
+           "conv3d_backward", "conv_in_act_train", "conv_in_act_backward", "encoder_train", "encoder_backward",
+           "embed_block_train", "embed_block_backward"]
 
 
 def _params(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
@@ -162,24 +163,26 @@ def conv3d_backward(x: torch.Tensor, dy: torch.Tensor, conv: torch.nn.Conv3d, ne
 
 # ----------------------------------------------------------------------------- conv blocks (bf16 path)
 @torch.no_grad()
-def conv_in_act_train(x: torch.Tensor, conv: torch.nn.Conv3d, residual=None, cin_pad: int = 0):
+def conv_in_act_train(x: torch.Tensor, conv: torch.nn.Conv3d, residual=None, cin_pad: int = 0, up2: bool = False):
     """Conv3d -> InstanceNorm3d -> LeakyReLU (+ residual) keeping the raw convolution output and the statistics
-    (DownBlock / UpBlock / Encoder stem, model/Unet_3Dblock.py:325-336,:547-554,:596-600).  bf16, channels-last."""
+    (DownBlock / UpBlock / Encoder stem / embed blocks, model/Unet_3Dblock.py:325-336,:547-554,:596-600,:373-382,
+    :419-429).  `up2`: nn.Upsample(nearest, x2) in front of the convolution (UpEmbedBlock).  bf16, channels-last."""
     from .unet import _ConvW
-    cw = _ConvW(conv, True, cin_pad=cin_pad)
+    cw = _ConvW(conv, True, cin_pad=cin_pad, fold_up2=up2)
     stride = tuple(conv.stride)
-    raw, partials, _ = ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, stride=stride, pad=cw.k // 2, want_stats=True, w_tc=cw.w_tc)
+    raw, partials, _ = ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, stride=stride, pad=cw.k // 2, up2=up2, want_stats=True,
+                                  w_tc=cw.w_tc, w_tc_fold=cw.w_tc_fold)
     V = raw.shape[1] * raw.shape[2] * raw.shape[3]
     stats = ops.instnorm_finalize(partials, V)
     y = ops.instnorm_apply(raw, stats, ops.ACT_LRELU, residual=residual, inplace=False)
-    return y, dict(x=x, raw=raw, stats=stats, conv=conv, residual=residual is not None)
+    return y, dict(x=x, raw=raw, stats=stats, conv=conv, residual=residual is not None, up2=up2)
 
 
 @torch.no_grad()
 def conv_in_act_backward(dy: torch.Tensor, saved: dict, need_dx: bool = True):
     """Returns (dx | None, dW, dbias); a residual added after the activation receives dy itself (the caller adds it)."""
     draw = ops.instnorm_bwd(saved["raw"], saved["stats"], dy.contiguous(), ops.ACT_LRELU)
-    return conv3d_backward(saved["x"], draw, saved["conv"], need_dx=need_dx)
+    return conv3d_backward(saved["x"], draw, saved["conv"], need_dx=need_dx, up2=saved.get("up2", False))
 
 
 @torch.no_grad()
@@ -214,3 +217,26 @@ def encoder_backward(d_bottle: torch.Tensor, d_skips, saved: dict) -> Dict[str, 
     _, dw, grads["input_block.bias"] = conv_in_act_backward(da, saved["stem"], need_dx=False)
     grads["input_block.weight"] = dw[:, :4].contiguous()                       # drop the four zero-padded input channels
     return grads
+
+
+@torch.no_grad()
+def embed_block_train(x: torch.Tensor, blk):
+    """EmbedAttention3DBlock.forward (model/Unet_3Dblock.py:469-501), the inside of a ROI bridge: stride-2 down_embed
+    conv + IN + LeakyReLU -> 8 encoder layers with the positional conv -> nearest x2 + up_embed conv + IN + LeakyReLU.
+    x bf16 [B,h,w,d,in_dim]; `blk` = lintransunet_b200.unet.EmbedAttention3DBlock."""
+    t, sv_down = conv_in_act_train(x, blk.down_embed.conv)
+    t, sv_stack = transformer_stack_train(t, blk.layers, blk.pos_encoder)
+    y, sv_up = conv_in_act_train(t, blk.up_embed.conv, up2=True)
+    return y, dict(down=sv_down, stack=sv_stack, up=sv_up)
+
+
+@torch.no_grad()
+def embed_block_backward(dy: torch.Tensor, saved: dict):
+    """Gradients of the block input and of all its parameters, keyed like the block's state_dict."""
+    grads: Dict[str, torch.Tensor] = {}
+    dt, grads["up_embed.module_list.0.1.weight"], grads["up_embed.module_list.0.1.bias"] = conv_in_act_backward(dy, saved["up"])
+    dt, g = transformer_stack_backward(dt, saved["stack"])
+    for k, v in g.items():
+        grads[k.replace("pos.", "pos_encoder.")] = v
+    dx, grads["down_embed.module_list.0.0.weight"], grads["down_embed.module_list.0.0.bias"] = conv_in_act_backward(dt, saved["down"])
+    return dx, grads

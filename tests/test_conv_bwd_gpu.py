@@ -157,3 +157,45 @@ def test_encoder_backward_matches_autograd_on_the_stored_activations():
             worst, worst_name = e, name
     print(f"\n[encoder bwd bf16] worst weight-gradient error {worst:.2e} ({worst_name})")
     assert worst <= 5e-2                           # nine stages of bf16 gradients
+
+
+def test_embed_attention_block_backward():
+    """EmbedAttention3DBlock (the inside of a ROI bridge, model/Unet_3Dblock.py:469-501): down_embed conv -> 8 encoder
+    layers + positional conv -> upsample + up_embed conv.  Reference: fp64 autograd through the oracle's transformer
+    stack, continuing from the two convolution outputs as stored."""
+    from oracle import ltu_oracle as O
+    from lintransunet_b200.backward import embed_block_backward, embed_block_train
+    from lintransunet_b200.unet import EmbedAttention3DBlock
+    torch.manual_seed(21)
+    in_dim, C, nhead, n_layers = 32, 128, 4, 8
+    blk = EmbedAttention3DBlock(in_dim, C, nhead, n_layers).cuda()
+    with torch.no_grad():
+        for p_ in blk.parameters():
+            p_.copy_(p_.to(torch.bfloat16).float())
+    x = torch.randn(2, 16, 12, 8, in_dim, device="cuda").to(torch.bfloat16)
+    y, saved = embed_block_train(x, blk)
+    sd = {f"T.{k}": v.detach().double().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+    xd = x.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    act = lambda cd, sv: O.lrelu(O.inorm(_stored(cd, sv["raw"])))
+    t = act(F.conv3d(xd, sd["T.down_embed.module_list.0.0.weight"], sd["T.down_embed.module_list.0.0.bias"], stride=2, padding=1),
+            saved["down"])
+    t = O.transformer_stack(t, sd, "T", nhead, sd["T.pos_encoder.proj.weight"], sd["T.pos_encoder.proj.bias"], n_layers)
+    t = F.interpolate(t, scale_factor=2, mode="nearest")
+    yd = act(F.conv3d(t, sd["T.up_embed.module_list.0.1.weight"], sd["T.up_embed.module_list.0.1.bias"], padding=1), saved["up"])
+    assert y.shape == x.shape and rel_err(y, yd.detach().permute(0, 2, 3, 4, 1)) <= 2e-2
+    dy = torch.randn(y.shape, device="cuda").to(torch.bfloat16)
+    yd.backward(dy.double().permute(0, 4, 1, 2, 3))
+    dx, grads = embed_block_backward(dy, saved)
+    assert sorted(grads) == sorted(k[2:] for k in sd)
+    e_x = rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1))
+    worst, worst_name = 0.0, ""
+    for name, gr in grads.items():
+        ref = sd["T." + name].grad
+        assert gr.shape == ref.shape, name
+        if name.endswith("self_attn.linears.1.bias") or (name.endswith(".bias") and "embed" in name):
+            continue                                        # mathematically zero gradients (softmax over tokens / InstanceNorm)
+        e = rel_err(gr, ref)
+        if e > worst:
+            worst, worst_name = e, name
+    print(f"\n[embed block bwd bf16] dx rel err {e_x:.2e}, worst parameter gradient {worst:.2e} ({worst_name})")
+    assert e_x <= 8e-2 and worst <= 8e-2
