@@ -356,6 +356,20 @@ int ltu_zero_insert(const void* y, void* z, int B, int H, int W, int D, int C, i
                     int sh, int sw, int sd, int dtype, ltu_stream_t stream);
 int ltu_sumpool2(const void* x, void* y, int B, int H, int W, int D, int C, int dtype, ltu_stream_t stream);
 
+/* backward of the decoder glue (all gathers: bit-reproducible):
+ *  ltu_upsample_trilinear_bwd: dy [B,2H,2W,fd*D,C] -> dx [B,H,W,D,C], the exact transpose of
+ *    ltu_upsample_trilinear (nn.Upsample(trilinear, align_corners=True), Unet_3Dblock.py:1341-1345);
+ *  ltu_mask_softmax_bwd: logits fp32 [B,V,Cout], dmask fp32 [B,Cout,V] -> dlogits fp32 [B,V,Cout]
+ *    (torch.softmax(mask_conv(x), 1), :1380);
+ *  ltu_head_d2s_softmax_bwd: logits fp32 [B,H2,W2,D,4*Cout], dprobs fp32 [B,Cout,2*H2,2*W2,D] ->
+ *    dlogits like logits (windows_unembedding + F.softmax, :138-152,:1392-1394).                  */
+int ltu_upsample_trilinear_bwd(const void* dy, void* dx, int B, int H, int W, int D, int C, int fd,
+                               int dtype, ltu_stream_t stream);
+int ltu_mask_softmax_bwd(const float* logits, const float* dmask, float* dlogits, int B,
+                         int64_t voxels, int Cout, ltu_stream_t stream);
+int ltu_head_d2s_softmax_bwd(const float* logits, const float* dprobs, float* dlogits, int B, int H2,
+                             int W2, int D, int Cout, ltu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

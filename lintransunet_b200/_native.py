@@ -80,6 +80,9 @@ SIGNATURES = {
     "ltu_conv3d_wgrad": (I, [P, P, P, P, Z, I, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "ltu_zero_insert": (I, [P, P, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "ltu_sumpool2": (I, [P, P, I, I, I, I, I, I, P]),
+    "ltu_upsample_trilinear_bwd": (I, [P, P, I, I, I, I, I, I, I, P]),
+    "ltu_mask_softmax_bwd": (I, [P, P, P, I, L, I, P]),
+    "ltu_head_d2s_softmax_bwd": (I, [P, P, P, I, I, I, I, I, P]),
     "ltu_attn_bwd_workspace": (Z, [I, L, I]),
     "ltu_attn_bwd": (I, [P, L, P, P, L, P, L, P, P, P, P, L, P, P, P, Z, I, L, I, I, P]),
 }

@@ -22,7 +22,7 @@ from . import ops
 
 __all__ = ["encoder_layer_train", "encoder_layer_backward", "transformer_stack_train", "transformer_stack_backward",
            "conv3d_backward", "conv_in_act_train", "conv_in_act_backward", "encoder_train", "encoder_backward",
-           "embed_block_train", "embed_block_backward"]
+           "embed_block_train", "embed_block_backward", "upblock_train", "upblock_backward"]
 
 
 def _params(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
@@ -240,3 +240,23 @@ def embed_block_backward(dy: torch.Tensor, saved: dict):
         grads[k.replace("pos.", "pos_encoder.")] = v
     dx, grads["down_embed.module_list.0.0.weight"], grads["down_embed.module_list.0.0.bias"] = conv_in_act_backward(dt, saved["down"])
     return dx, grads
+
+
+@torch.no_grad()
+def upblock_train(x: torch.Tensor, skip: torch.Tensor, blk):
+    """UpBlock.forward (model/Unet_3Dblock.py:540-557): conv1 + IN + LeakyReLU, concatenation with the (gated, bridged)
+    skip, conv2 + IN + LeakyReLU.  The training path materialises the concatenation (its gradient is a split)."""
+    x1, sv1 = conv_in_act_train(x, blk.conv1)
+    cat = torch.cat([x1, skip], -1)
+    y, sv2 = conv_in_act_train(cat, blk.conv2)
+    return y, dict(c1=sv1, c2=sv2, split=x1.shape[-1])
+
+
+@torch.no_grad()
+def upblock_backward(dy: torch.Tensor, saved: dict):
+    """Returns (dx, dskip, parameter gradients keyed conv{1,2}.{weight,bias})."""
+    g: Dict[str, torch.Tensor] = {}
+    dcat, g["conv2.weight"], g["conv2.bias"] = conv_in_act_backward(dy, saved["c2"])
+    c = saved["split"]
+    dx, g["conv1.weight"], g["conv1.bias"] = conv_in_act_backward(dcat[..., :c].contiguous(), saved["c1"])
+    return dx, dcat[..., c:].contiguous(), g

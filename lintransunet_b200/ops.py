@@ -446,6 +446,40 @@ def upsample_trilinear(x: torch.Tensor, fd: int) -> torch.Tensor:
     return y
 
 
+def upsample_trilinear_bwd(dy: torch.Tensor, fd: int) -> torch.Tensor:
+    """Transpose of upsample_trilinear: dy [B,2H,2W,fd*D,C] -> dx [B,H,W,D,C]."""
+    dev = _chk(dy)
+    B, Ho, Wo, Do, C = dy.shape
+    H, W, D = Ho // 2, Wo // 2, Do // fd
+    dx = torch.empty(B, H, W, D, C, dtype=dy.dtype, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_upsample_trilinear_bwd(_p(dy), _p(dx), B, H, W, D, C, fd, _dt(dy), st),
+              "ltu_upsample_trilinear_bwd")
+    return dx
+
+
+def mask_softmax_bwd(logits: torch.Tensor, dmask: torch.Tensor) -> torch.Tensor:
+    """logits fp32 [B,h,w,d,Cout], dmask fp32 [B,Cout,h,w,d] -> dlogits fp32 like logits."""
+    dev = _chk(logits, dmask)
+    B, h, w, d, C = logits.shape
+    out = torch.empty_like(logits)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_mask_softmax_bwd(_p(logits), _p(dmask), _p(out), B, h * w * d, C, st), "ltu_mask_softmax_bwd")
+    return out
+
+
+def head_d2s_softmax_bwd(logits: torch.Tensor, dprobs: torch.Tensor, cout: int) -> torch.Tensor:
+    """logits fp32 [B,H2,W2,D,4*cout], dprobs fp32 [B,cout,2*H2,2*W2,D] -> dlogits fp32 like logits."""
+    dev = _chk(logits, dprobs)
+    B, H2, W2, D, C4 = logits.shape
+    assert C4 == 4 * cout
+    out = torch.empty_like(logits)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_head_d2s_softmax_bwd(_p(logits), _p(dprobs), _p(out), B, H2, W2, D, cout, st),
+              "ltu_head_d2s_softmax_bwd")
+    return out
+
+
 def mask_softmax(logits: torch.Tensor, want_mask: bool):
     """logits fp32 [B,h,w,d,Cout] -> (mask fp32 [B,Cout,h,w,d] | None, fg fp32 [B,h,w,d])."""
     dev = _chk(logits)

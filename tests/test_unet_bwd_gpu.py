@@ -1,0 +1,84 @@
+"""GPU: backward of the decoder glue (ltu_upsample_trilinear_bwd, ltu_mask_softmax_bwd, ltu_head_d2s_softmax_bwd) and of
+UpBlock (composition of existing kernels) against fp64 autograd.  SURVEY 8f-1."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ltu_oracle as O
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape,C,fd", [((3, 4, 5), 16, 2), ((6, 5, 8), 32, 1), ((1, 1, 4), 8, 2), ((8, 8, 16), 64, 2), ((2, 7, 1), 16, 1)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 6e-3)])
+def test_upsample_trilinear_backward(shape, C, fd, dtype, tol):
+    from lintransunet_b200 import ops
+    H, W, D = shape
+    g = torch.Generator(device="cuda").manual_seed(H * W + D + C)
+    x = torch.randn(2, H, W, D, C, device="cuda", generator=g).to(dtype)
+    dy = torch.randn(2, 2 * H, 2 * W, fd * D, C, device="cuda", generator=g).to(dtype)
+    xd = x.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    yd = F.interpolate(xd, scale_factor=(2, 2, fd), mode="trilinear", align_corners=True)
+    assert rel_err(ops.upsample_trilinear(x, fd), yd.detach().permute(0, 2, 3, 4, 1)) <= max(tol, 1e-5)
+    yd.backward(dy.double().permute(0, 4, 1, 2, 3))
+    dx = ops.upsample_trilinear_bwd(dy, fd)
+    assert dx.shape == x.shape and rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1)) <= tol
+    # exact adjoint: <up(x), dy> == <x, up^T(dy)> in fp32
+    if dtype == torch.float32:
+        lhs = float((ops.upsample_trilinear(x, fd).double() * dy.double()).sum())
+        rhs = float((x.double() * dx.double()).sum())
+        assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs))
+
+
+@pytest.mark.parametrize("cout", [2, 3])
+def test_mask_and_head_softmax_backward(cout):
+    from lintransunet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(cout)
+    logits = torch.randn(2, 5, 4, 6, cout, device="cuda", generator=g) * 2
+    dmask = torch.randn(2, cout, 5, 4, 6, device="cuda", generator=g)
+    ld = logits.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    torch.softmax(ld, 1).backward(dmask.double())
+    assert rel_err(ops.mask_softmax_bwd(logits, dmask), ld.grad.permute(0, 2, 3, 4, 1)) <= 1e-5
+    # output head: depth-to-space (in-channel = c*4 + kh*2 + kw) + softmax over classes
+    hl = torch.randn(2, 4, 3, 5, 4 * cout, device="cuda", generator=g) * 2
+    dprobs = torch.randn(2, cout, 8, 6, 5, device="cuda", generator=g)
+    hd = hl.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    probs = torch.softmax(O.depth_to_space(hd, 2), 1)
+    got_probs = ops.head_d2s_softmax(hl, cout, want_probs=True, want_onehot=False, want_labels=False)[0]
+    assert rel_err(got_probs, probs.detach()) <= 1e-5
+    probs.backward(dprobs.double())
+    assert rel_err(ops.head_d2s_softmax_bwd(hl, dprobs, cout), hd.grad.permute(0, 2, 3, 4, 1)) <= 1e-5
+
+
+def _stored(cd, raw_cl):
+    """Continue the reference from the convolution output as the forward stored it (see tests/test_conv_bwd_gpu.py)."""
+    return cd + (raw_cl.double().permute(0, 4, 1, 2, 3) - cd).detach()
+
+
+def test_upblock_backward():
+    """UpBlock (model/Unet_3Dblock.py:540-557): conv1 -> IN -> LReLU, cat with the skip, conv2 -> IN -> LReLU."""
+    from lintransunet_b200.backward import upblock_backward, upblock_train
+    from lintransunet_b200.unet import UpBlock
+    torch.manual_seed(3)
+    blk = UpBlock(128, 64, 3).cuda()
+    with torch.no_grad():
+        for p_ in blk.parameters():
+            p_.copy_(p_.to(torch.bfloat16).float())
+    x = torch.randn(2, 6, 5, 8, 128, device="cuda").to(torch.bfloat16)
+    skip = torch.randn(2, 6, 5, 8, 64, device="cuda").to(torch.bfloat16)
+    y, saved = upblock_train(x, skip, blk)
+    sd = {k: v.detach().double().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+    xd = x.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    kd = skip.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    act = lambda cd, sv: O.lrelu(O.inorm(_stored(cd, sv["raw"])))
+    x1 = act(F.conv3d(xd, sd["conv1.weight"], sd["conv1.bias"], padding=1), saved["c1"])
+    yd = act(F.conv3d(torch.cat((x1, kd), dim=1), sd["conv2.weight"], sd["conv2.bias"], padding=1), saved["c2"])
+    assert rel_err(y, yd.detach().permute(0, 2, 3, 4, 1)) <= 2e-2
+    dy = torch.randn(y.shape, device="cuda").to(torch.bfloat16)
+    yd.backward(dy.double().permute(0, 4, 1, 2, 3))
+    dx, dskip, grads = upblock_backward(dy, saved)
+    errs = dict(dx=rel_err(dx, xd.grad.permute(0, 2, 3, 4, 1)), dskip=rel_err(dskip, kd.grad.permute(0, 2, 3, 4, 1)),
+                w1=rel_err(grads["conv1.weight"], sd["conv1.weight"].grad), w2=rel_err(grads["conv2.weight"], sd["conv2.weight"].grad))
+    print("\n[upblock bwd bf16]", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) <= 2e-2
