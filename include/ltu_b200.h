@@ -370,6 +370,16 @@ int ltu_mask_softmax_bwd(const float* logits, const float* dmask, float* dlogits
 int ltu_head_d2s_softmax_bwd(const float* logits, const float* dprobs, float* dlogits, int B, int H2,
                              int W2, int D, int Cout, ltu_stream_t stream);
 
+/* backward of ltu_gate_fused (SpatialAttention3DBlock + `encoded * attn`, Unet_3Dblock.py:217-221,:1385):
+ * writes dskip = dout * gate (direct path), dh = the gradient of norm(W_x skip) AND of norm(W_g up)
+ * (feed it to ltu_instnorm_bwd with LTU_ACT_NONE for each), dpsi_w fp32 [Ci], dpsi_b fp32 [1].
+ * workspace: ltu_gate_bwd_workspace(B, voxels, Ci) bytes; ordered sums.                           */
+size_t ltu_gate_bwd_workspace(int B, int64_t voxels, int Ci);
+int ltu_gate_bwd(const void* a, const float* stats_a, const void* g, const float* stats_g,
+                 const float* psi_w, const float* psi_b, const void* skip, const void* dout, void* dskip,
+                 void* dh, float* dpsi_w, float* dpsi_b, void* workspace, size_t ws_bytes, int B,
+                 int64_t voxels, int Ci, int dtype, ltu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

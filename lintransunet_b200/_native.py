@@ -83,6 +83,8 @@ SIGNATURES = {
     "ltu_upsample_trilinear_bwd": (I, [P, P, I, I, I, I, I, I, I, P]),
     "ltu_mask_softmax_bwd": (I, [P, P, P, I, L, I, P]),
     "ltu_head_d2s_softmax_bwd": (I, [P, P, P, I, I, I, I, I, P]),
+    "ltu_gate_bwd_workspace": (Z, [I, L, I]),
+    "ltu_gate_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, P, Z, I, L, I, I, P]),
     "ltu_attn_bwd_workspace": (Z, [I, L, I]),
     "ltu_attn_bwd": (I, [P, L, P, P, L, P, L, P, P, P, P, L, P, P, P, Z, I, L, I, I, P]),
 }

@@ -22,7 +22,7 @@ from . import ops
 
 __all__ = ["encoder_layer_train", "encoder_layer_backward", "transformer_stack_train", "transformer_stack_backward",
            "conv3d_backward", "conv_in_act_train", "conv_in_act_backward", "encoder_train", "encoder_backward",
-           "embed_block_train", "embed_block_backward", "upblock_train", "upblock_backward"]
+           "embed_block_train", "embed_block_backward", "upblock_train", "upblock_backward", "gate_train", "gate_backward"]
 
 
 def _params(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
@@ -260,3 +260,35 @@ def upblock_backward(dy: torch.Tensor, saved: dict):
     c = saved["split"]
     dx, g["conv1.weight"], g["conv1.bias"] = conv_in_act_backward(dcat[..., :c].contiguous(), saved["c1"])
     return dx, dcat[..., c:].contiguous(), g
+
+
+@torch.no_grad()
+def gate_train(skip: torch.Tensor, up: torch.Tensor, att):
+    """SpatialAttention3DBlock + `encoded * attn` (model/Unet_3Dblock.py:217-221,:1385): skip [B,h,w,d,C],
+    up [B,h,w,d,Cg] (the upsampled decoder state), `att` = lintransunet_b200.unet.SpatialAttention3DBlock."""
+    from .unet import _ConvW
+    wx, wg = _ConvW(att.W_x[0], True), _ConvW(att.W_g[0], True)
+    ga, pa, _ = ops.conv3d(skip, wx.w, wx.b, wx.cout, 1, pad=0, want_stats=True, w_tc=wx.w_tc)
+    gg, pg, _ = ops.conv3d(up, wg.w, wg.b, wg.cout, 1, pad=0, want_stats=True, w_tc=wg.w_tc)
+    V = skip.shape[1] * skip.shape[2] * skip.shape[3]
+    sa, sg = ops.instnorm_finalize(pa, V), ops.instnorm_finalize(pg, V)
+    psi_w = att.psi[0].weight.detach().reshape(-1).float().contiguous()
+    psi_b = att.psi[0].bias.detach().float().contiguous()
+    out = ops.gate_fused(ga, sa, gg, sg, psi_w, psi_b, skip)
+    return out, dict(skip=skip, up=up, ga=ga, gg=gg, sa=sa, sg=sg, psi_w=psi_w, psi_b=psi_b, att=att)
+
+
+@torch.no_grad()
+def gate_backward(dout: torch.Tensor, saved: dict):
+    """Returns (dskip, dup, gradients keyed like the block's state_dict: W_x.0.*, W_g.0.*, psi.0.*)."""
+    att = saved["att"]
+    g: Dict[str, torch.Tensor] = {}
+    dskip, dh, dpw, dpb = ops.gate_bwd(saved["ga"], saved["sa"], saved["gg"], saved["sg"], saved["psi_w"], saved["psi_b"],
+                                       saved["skip"], dout.contiguous())
+    g["psi.0.weight"] = dpw.reshape(att.psi[0].weight.shape)
+    g["psi.0.bias"] = dpb
+    da = ops.instnorm_bwd(saved["ga"], saved["sa"], dh, ops.ACT_NONE)
+    dg = ops.instnorm_bwd(saved["gg"], saved["sg"], dh, ops.ACT_NONE)
+    dsk2, g["W_x.0.weight"], g["W_x.0.bias"] = conv3d_backward(saved["skip"], da, att.W_x[0])
+    dup, g["W_g.0.weight"], g["W_g.0.bias"] = conv3d_backward(saved["up"], dg, att.W_g[0])
+    return dskip + dsk2, dup, g

@@ -141,6 +141,106 @@ head_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ dpro
     }
 }
 
+// ---------------------------------------------------------------- attention gate (a13)
+// forward (unet_kernels.cu::gate_kernel): h = relu(norm(a) + norm(g)), z = psi.h + b, s = sigmoid(z), out = skip * s
+// backward, given dout:   dskip = dout * s            (the direct path; the W_x path is added by the caller)
+//                         dz = (sum_c dout_c skip_c) s (1 - s);  dh_c = dz psi_c [h_c > 0]   (= d norm(a) = d norm(g))
+//                         dpsi_c = sum_v dz h_c;  dpsi_b = sum_v dz        (per-CTA partials, ordered finalize)
+// G = Ci / 4 lanes share a voxel (4 channels each), the two per-voxel sums are butterflies inside the lane group.
+// part [gridDim.y * gridDim.x][Ci + 1].
+template <typename T>
+__global__ void __launch_bounds__(256)
+gate_bwd_kernel(const T* __restrict__ a, const float* __restrict__ sa, const T* __restrict__ g, const float* __restrict__ sg,
+                const float* __restrict__ psi_w, const float* __restrict__ psi_b, const T* __restrict__ skip,
+                const T* __restrict__ dout, T* __restrict__ dskip, T* __restrict__ dh, float* __restrict__ part, int64_t V,
+                int Ci) {
+    __shared__ float red[256][5];
+    const int G = Ci / 4;
+    const int b = blockIdx.y;
+    const int64_t total = V * G;
+    const int64_t total_pad = (total + 31) / 32 * 32;
+    const float bias = psi_b[0];
+    const float* st_a = sa + (int64_t)b * Ci * 2;
+    const float* st_g = sg + (int64_t)b * Ci * 2;
+    // the grid stride (gridDim.x * 256) is a multiple of G: a thread always owns the same 4 channels
+    const int c0 = (int)(threadIdx.x % G) * 4;
+    float ma[4], ra[4], mg[4], rg[4], pw[4], acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ma[i] = st_a[(c0 + i) * 2]; ra[i] = st_a[(c0 + i) * 2 + 1];
+        mg[i] = st_g[(c0 + i) * 2]; rg[i] = st_g[(c0 + i) * 2 + 1];
+        pw[i] = psi_w[c0 + i];
+    }
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total_pad; idx += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = idx < total;
+        const int64_t cidx = live ? idx : total - 1;
+        const int64_t off = (int64_t)b * V * Ci + (cidx / G) * Ci + c0;
+        float va[4], vg[4], vs[4], vd[4], h[4];
+        load4(a + off, va);
+        load4(g + off, vg);
+        load4(skip + off, vs);
+        load4(dout + off, vd);
+        float dot = 0.f, ds = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            h[i] = fmaxf((va[i] - ma[i]) * ra[i] + (vg[i] - mg[i]) * rg[i], 0.f);
+            dot = fmaf(h[i], pw[i], dot);
+            ds = fmaf(vd[i], vs[i], ds);
+        }
+        for (int o = G >> 1; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        }
+        const float s = 1.f / (1.f + __expf(-(dot + bias)));
+        const float dz = ds * s * (1.f - s);
+        if (live) {
+            float o1[4], o2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                o1[i] = vd[i] * s;
+                o2[i] = h[i] > 0.f ? dz * pw[i] : 0.f;
+                acc[i] = fmaf(dz, h[i], acc[i]);
+            }
+            if (c0 == 0) acc[4] += dz;
+            store4(dskip + off, o1);
+            store4(dh + off, o2);
+        }
+    }
+    // ordered fold over the threads that own the same channels: t, t + G, t + 2G, ...
+#pragma unroll
+    for (int i = 0; i < 5; ++i) red[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    float* out = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (Ci + 1);
+    if (threadIdx.x < G) {
+        float sum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = threadIdx.x; t < 256; t += G)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) sum[i] += red[t][i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[threadIdx.x * 4 + i] = sum[i];
+        if (threadIdx.x == 0) out[Ci] = sum[4];
+    }
+}
+
+// dpsi [Ci] and dpsi_b [1]: one warp per output, lanes take the partial rows in order, then a butterfly
+__global__ void __launch_bounds__(256)
+gate_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int Ci, float* __restrict__ dpsi_w, float* __restrict__ dpsi_b) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c > Ci) return;
+    float s = 0.f;
+    for (int p = lane; p < nparts; p += 32) s += part[(int64_t)p * (Ci + 1) + c];
+    s = warp_sum(s);
+    if (lane == 0) { if (c < Ci) dpsi_w[c] = s; else dpsi_b[0] = s; }
+}
+
+static inline int gate_bwd_blocks(int B, int64_t V, int Ci) {
+    const int G = Ci / 4;
+    int64_t bx = ceil_div64(V * G, 256);
+    const int64_t cap = ceil_div64((int64_t)sm_count() * 8, B);
+    if (bx > cap) bx = cap;
+    return (int)(bx < 1 ? 1 : bx);
+}
+
 static unsigned ub_grid(int64_t items, int waves) {
     int64_t b = ceil_div64(items, 256);
     const int64_t cap = (int64_t)sm_count() * waves;
@@ -192,5 +292,33 @@ extern "C" int ltu_head_d2s_softmax_bwd(const float* logits, const float* dprobs
     }
     LTU_LAUNCH_CHECK("head_d2s_softmax_bwd");
     count_launch(1);
+    return LTU_OK;
+}
+
+extern "C" size_t ltu_gate_bwd_workspace(int B, int64_t voxels, int Ci) {
+    if (B <= 0 || voxels <= 0 || Ci <= 0 || Ci % 4) return 0;
+    return (size_t)B * gate_bwd_blocks(B, voxels, Ci) * (Ci + 1) * sizeof(float);
+}
+
+extern "C" int ltu_gate_bwd(const void* a, const float* stats_a, const void* g, const float* stats_g, const float* psi_w,
+                            const float* psi_b, const void* skip, const void* dout, void* dskip, void* dh, float* dpsi_w,
+                            float* dpsi_b, void* ws, size_t ws_bytes, int B, int64_t voxels, int Ci, int dtype,
+                            ltu_stream_t stream) {
+    LTU_ARG_CHECK(a && stats_a && g && stats_g && psi_w && psi_b && skip && dout && dskip && dh && dpsi_w && dpsi_b && ws,
+                  "gate_bwd: null pointer");
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "gate_bwd: bad dtype %d", dtype);
+    const int G = Ci / 4;
+    LTU_ARG_CHECK(Ci % 4 == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "gate_bwd: Ci=%d unsupported (Ci/4 must be a power of two <= 32)", Ci);
+    LTU_ARG_CHECK(B > 0 && B <= 65535 && voxels > 0, "gate_bwd: bad shape");
+    LTU_ARG_CHECK(ws_bytes >= ltu_gate_bwd_workspace(B, voxels, Ci), "gate_bwd: workspace too small");
+    const int bx = gate_bwd_blocks(B, voxels, Ci);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* part = (float*)ws;
+    if (dtype == LTU_F32) gate_bwd_kernel<float><<<dim3(bx, B), 256, 0, st>>>((const float*)a, stats_a, (const float*)g, stats_g, psi_w, psi_b, (const float*)skip, (const float*)dout, (float*)dskip, (float*)dh, part, voxels, Ci);
+    else gate_bwd_kernel<bf16><<<dim3(bx, B), 256, 0, st>>>((const bf16*)a, stats_a, (const bf16*)g, stats_g, psi_w, psi_b, (const bf16*)skip, (const bf16*)dout, (bf16*)dskip, (bf16*)dh, part, voxels, Ci);
+    LTU_LAUNCH_CHECK("gate_bwd");
+    gate_bwd_finalize_kernel<<<(Ci + 1 + 7) / 8, 256, 0, st>>>(part, bx * B, Ci, dpsi_w, dpsi_b);
+    LTU_LAUNCH_CHECK("gate_bwd_finalize");
+    count_launch(2);
     return LTU_OK;
 }

@@ -503,6 +503,25 @@ def gate_fused(a: torch.Tensor, stats_a: torch.Tensor, g: torch.Tensor, stats_g:
     return out
 
 
+def gate_bwd(a: torch.Tensor, stats_a: torch.Tensor, g: torch.Tensor, stats_g: torch.Tensor, psi_w: torch.Tensor,
+             psi_b: torch.Tensor, skip: torch.Tensor, dout: torch.Tensor):
+    """Backward of gate_fused: returns (dskip_direct, dh, dpsi_w fp32 [Ci], dpsi_b fp32 [1]); dh is the gradient of
+    BOTH normalised 1x1x1 conv outputs (pass it through instnorm_bwd(..., ACT_NONE) for each)."""
+    dev = _chk(a, stats_a, g, stats_g, psi_w, psi_b, skip, dout)
+    B, Ci = a.shape[0], a.shape[-1]
+    V = a.numel() // (B * Ci)
+    L = _native.lib()
+    nbytes = L.ltu_gate_bwd_workspace(B, V, Ci)
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+    dskip, dh = torch.empty_like(skip), torch.empty_like(a)
+    dpw = torch.empty(Ci, dtype=torch.float32, device=dev)
+    dpb = torch.empty(1, dtype=torch.float32, device=dev)
+    with _Guard(dev) as st:
+        check(L.ltu_gate_bwd(_p(a), _p(stats_a), _p(g), _p(stats_g), _p(psi_w), _p(psi_b), _p(skip), _p(dout), _p(dskip),
+                             _p(dh), _p(dpw), _p(dpb), _p(ws), nbytes, B, V, Ci, _dt(a), st), "ltu_gate_bwd")
+    return dskip, dh, dpw, dpb
+
+
 def roi_bbox(fg: torch.Tensor, min_h: int, min_w: int, thr: float = 0.5) -> torch.Tensor:
     """fg fp32 [B,h,w,d] -> boxes fp32 [B,6] on device (model/Unet_3Dblock.py:821-873)."""
     dev = _chk(fg)

@@ -82,3 +82,35 @@ def test_upblock_backward():
                 w1=rel_err(grads["conv1.weight"], sd["conv1.weight"].grad), w2=rel_err(grads["conv2.weight"], sd["conv2.weight"].grad))
     print("\n[upblock bwd bf16]", {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) <= 2e-2
+
+
+@pytest.mark.parametrize("c_skip,c_up,shape", [(16, 32, (8, 6, 10)), (64, 128, (5, 4, 6)), (128, 256, (3, 4, 4))])
+def test_attention_gate_backward(c_skip, c_up, shape):
+    """SpatialAttention3DBlock + `encoded * attn` (model/Unet_3Dblock.py:217-221,:1385) on the bf16 path."""
+    from lintransunet_b200.backward import gate_backward, gate_train
+    from lintransunet_b200.unet import SpatialAttention3DBlock
+    H, W, D = shape
+    torch.manual_seed(c_skip + H)
+    att = SpatialAttention3DBlock(c_skip, c_up, c_skip).cuda()
+    with torch.no_grad():
+        for p_ in att.parameters():
+            p_.copy_(p_.to(torch.bfloat16).float())
+    skip = torch.randn(2, H, W, D, c_skip, device="cuda").to(torch.bfloat16)
+    up = torch.randn(2, H, W, D, c_up, device="cuda").to(torch.bfloat16)
+    out, saved = gate_train(skip, up, att)
+    sd = {k: v.detach().double().clone().requires_grad_(True) for k, v in att.state_dict().items()}
+    kd = skip.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    ud = up.double().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    a = O.inorm(_stored(F.conv3d(kd, sd["W_x.0.weight"], sd["W_x.0.bias"]), saved["ga"]))
+    b = O.inorm(_stored(F.conv3d(ud, sd["W_g.0.weight"], sd["W_g.0.bias"]), saved["gg"]))
+    od = kd * torch.sigmoid(F.conv3d(F.relu(a + b), sd["psi.0.weight"], sd["psi.0.bias"]))
+    assert rel_err(out, od.detach().permute(0, 2, 3, 4, 1)) <= 1e-2
+    dout = torch.randn(out.shape, device="cuda").to(torch.bfloat16)
+    od.backward(dout.double().permute(0, 4, 1, 2, 3))
+    dskip, dup, grads = gate_backward(dout, saved)
+    errs = dict(dskip=rel_err(dskip, kd.grad.permute(0, 2, 3, 4, 1)), dup=rel_err(dup, ud.grad.permute(0, 2, 3, 4, 1)))
+    for k in ("W_x.0.weight", "W_g.0.weight", "psi.0.weight", "psi.0.bias"):
+        assert grads[k].shape == sd[k].shape, k
+        errs[k] = rel_err(grads[k], sd[k].grad)
+    print(f"\n[gate bwd bf16 {c_skip}/{c_up}]", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) <= 3e-2
