@@ -380,6 +380,16 @@ int ltu_gate_bwd(const void* a, const float* stats_a, const void* g, const float
                  void* dh, float* dpsi_w, float* dpsi_b, void* workspace, size_t ws_bytes, int B,
                  int64_t voxels, int Ci, int dtype, ltu_stream_t stream);
 
+/* backward of ltu_roi_resample (grid_sample of roi_alignment2 / post_processing2, Unet_3Dblock.py:
+ * 985-1039,:1080-1117; the box is not differentiated, like the reference where it comes out of
+ * searchsorted): dy has the forward's OUTPUT extent, dx its INPUT extent; same `direction`, ROI
+ * constants and box as the forward call.  A gather over tabulated forward taps: exact transpose,
+ * no atomics.  workspace: ltu_roi_resample_bwd_workspace(B, h, w, eval_h, eval_w) bytes.          */
+size_t ltu_roi_resample_bwd_workspace(int B, int h, int w, int eval_h, int eval_w);
+int ltu_roi_resample_bwd(const void* dy, const float* box, void* dx, void* workspace, size_t ws_bytes,
+                         int B, int h, int w, int d, int C, int roi_h, int roi_w, int eval_h, int eval_w,
+                         int direction, int dtype, ltu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

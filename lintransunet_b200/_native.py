@@ -85,6 +85,8 @@ SIGNATURES = {
     "ltu_head_d2s_softmax_bwd": (I, [P, P, P, I, I, I, I, I, P]),
     "ltu_gate_bwd_workspace": (Z, [I, L, I]),
     "ltu_gate_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, P, Z, I, L, I, I, P]),
+    "ltu_roi_resample_bwd_workspace": (Z, [I, I, I, I, I]),
+    "ltu_roi_resample_bwd": (I, [P, P, P, P, Z, I, I, I, I, I, I, I, I, I, I, I, P]),
     "ltu_attn_bwd_workspace": (Z, [I, L, I]),
     "ltu_attn_bwd": (I, [P, L, P, P, L, P, L, P, P, P, P, L, P, P, P, Z, I, L, I, I, P]),
 }

@@ -177,11 +177,130 @@ roi_resample_kernel(const T* __restrict__ x, const float* __restrict__ box, T* _
     }
 }
 
+// ---------------------------------------------------------------- backward of the fisheye resample
+// The forward is separable: y[o_i, o_j] = sum_{a,b} wh_a(o_i) ww_b(o_j) x[h_a(o_i), w_b(o_j)].  Its transpose is computed as a
+// GATHER: roi_taps_kernel tabulates, per sample and axis, the forward's own taps (same device functions, so the pair is the
+// exact transpose, degenerate / NaN boxes included) and, for every INPUT index, the first and last output index that reads it
+// (the piecewise-linear maps are monotone, so the readers are contiguous; entries inside the range that do not read the index
+// simply weigh 0); roi_resample_bwd_kernel then sums dy over that small rectangle.  No atomics: bit-reproducible.
+// grid B, 256 threads.  tabh [B][oh], tabw [B][ow] (Tap), rngh [B][ih], rngw [B][iw] (int2 = first, last; empty: 0, -1)
+__global__ void __launch_bounds__(256)
+roi_taps_kernel(const float* __restrict__ box, Tap* __restrict__ tabh, Tap* __restrict__ tabw, int2* __restrict__ rngh,
+                int2* __restrict__ rngw, int ih, int iw, int oh, int ow, int h_full, int w_full, int roi_h, int roi_w,
+                int eval_h, int eval_w, int direction) {
+    const int b = blockIdx.x;
+    const float x0 = box[b * 6 + 0], y0 = box[b * 6 + 1], x1 = box[b * 6 + 3], y1 = box[b * 6 + 4];
+    Tap* th = tabh + (int64_t)b * oh;
+    Tap* tw = tabw + (int64_t)b * ow;
+    for (int n = threadIdx.x; n < oh; n += blockDim.x) {
+        const float c = direction == 0 ? fisheye_fwd(x0, x1, h_full - 1, roi_h, eval_h, n) : fisheye_back(x0, x1, h_full - 1, roi_h, eval_h, n);
+        th[n] = make_tap(c, ih);
+    }
+    for (int n = threadIdx.x; n < ow; n += blockDim.x) {
+        const float c = direction == 0 ? fisheye_fwd(y0, y1, w_full - 1, roi_w, eval_w, n) : fisheye_back(y0, y1, w_full - 1, roi_w, eval_w, n);
+        tw[n] = make_tap(c, iw);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ih + iw; i += blockDim.x) {
+        const bool isw = i >= ih;
+        const int k = isw ? i - ih : i;
+        const Tap* t = isw ? tw : th;
+        const int n_out = isw ? ow : oh;
+        int lo = 0, hi = -1;
+        bool found = false;
+        for (int n = 0; n < n_out; ++n) {
+            const Tap q = t[n];
+            if ((q.i0 == k && q.w0 != 0.f) || (q.i1 == k && q.w1 != 0.f)) {
+                if (!found) { lo = n; found = true; }
+                hi = n;
+            }
+        }
+        (isw ? rngw : rngh)[(int64_t)b * (isw ? iw : ih) + k] = make_int2(lo, hi);
+    }
+}
+
+// dy [B,oh,ow,d,C] -> dx [B,ih,iw,d,C]
+template <typename T>
+__global__ void __launch_bounds__(256)
+roi_resample_bwd_kernel(const T* __restrict__ dy, const Tap* __restrict__ tabh, const Tap* __restrict__ tabw,
+                        const int2* __restrict__ rngh, const int2* __restrict__ rngw, T* __restrict__ dx, int ih, int iw,
+                        int oh, int ow, int d, int C) {
+    const int b = blockIdx.y;
+    const int cg = C / 4;
+    const int64_t total = (int64_t)ih * iw * d * cg;
+    const T* yb = dy + (int64_t)b * oh * ow * d * C;
+    T* xb = dx + (int64_t)b * ih * iw * d * C;
+    const Tap* th = tabh + (int64_t)b * oh;
+    const Tap* tw = tabw + (int64_t)b * ow;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % cg) * 4;
+        int64_t t = idx / cg;
+        const int dd = (int)(t % d); t /= d;
+        const int j = (int)(t % iw);
+        const int i = (int)(t / iw);
+        const int2 rh = rngh[(int64_t)b * ih + i], rw = rngw[(int64_t)b * iw + j];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int n = rh.x; n <= rh.y; ++n) {
+            const Tap a = th[n];
+            const float wh = (a.i0 == i ? a.w0 : 0.f) + (a.i1 == i ? a.w1 : 0.f);
+            if (wh == 0.f) continue;
+            for (int m = rw.x; m <= rw.y; ++m) {
+                const Tap q = tw[m];
+                const float ww = (q.i0 == j ? q.w0 : 0.f) + (q.i1 == j ? q.w1 : 0.f);
+                if (ww == 0.f) continue;
+                float v[4];
+                load4(yb + (((int64_t)n * ow + m) * d + dd) * C + c4, v);
+                const float wt = wh * ww;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
+            }
+        }
+        store4(xb + (idx / cg) * C + c4, acc);
+    }
+}
+
 }  // namespace ltu
 
 using namespace ltu;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" size_t ltu_roi_resample_bwd_workspace(int B, int h, int w, int eval_h, int eval_w) {
+    if (B <= 0 || h <= 0 || w <= 0 || eval_h <= 0 || eval_w <= 0) return 0;
+    // either direction: one axis pair is (h, w), the other (eval_h, eval_w)
+    return (size_t)B * ((size_t)(h + w + eval_h + eval_w) * 16);
+}
+
+extern "C" int ltu_roi_resample_bwd(const void* dy, const float* box, void* dx, void* ws, size_t ws_bytes, int B, int h, int w,
+                                    int d, int C, int roi_h, int roi_w, int eval_h, int eval_w, int direction, int dtype,
+                                    ltu_stream_t stream) {
+    LTU_ARG_CHECK(dy && box && dx && ws, "roi_resample_bwd: null pointer");
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "roi_resample_bwd: bad dtype %d", dtype);
+    LTU_ARG_CHECK(B > 0 && B <= 65535 && h > 0 && w > 0 && d > 0 && C % 4 == 0, "roi_resample_bwd: bad shape");
+    LTU_ARG_CHECK(direction == 0 || direction == 1, "roi_resample_bwd: direction must be 0 or 1");
+    LTU_ARG_CHECK(roi_h > 1 && roi_w > 1 && eval_h > roi_h && eval_w > roi_w, "roi_resample_bwd: bad ROI constants");
+    LTU_ARG_CHECK(aligned16(dy) && aligned16(dx) && aligned16(ws), "roi_resample_bwd: pointers must be 16-byte aligned");
+    LTU_ARG_CHECK(ws_bytes >= ltu_roi_resample_bwd_workspace(B, h, w, eval_h, eval_w), "roi_resample_bwd: workspace too small");
+    // forward: x [ih, iw] -> y [oh, ow]; here dy has the forward's OUTPUT extent and dx its INPUT extent
+    const int ih = direction == 0 ? h : eval_h, iw = direction == 0 ? w : eval_w;
+    const int oh = direction == 0 ? eval_h : h, ow = direction == 0 ? eval_w : w;
+    Tap* tabh = reinterpret_cast<Tap*>(ws);
+    Tap* tabw = tabh + (size_t)B * oh;
+    int2* rngh = reinterpret_cast<int2*>(tabw + (size_t)B * ow);
+    int2* rngw = rngh + (size_t)B * ih;
+    cudaStream_t st = (cudaStream_t)stream;
+    roi_taps_kernel<<<B, 256, 0, st>>>(box, tabh, tabw, rngh, rngw, ih, iw, oh, ow, h, w, roi_h, roi_w, eval_h, eval_w, direction);
+    LTU_LAUNCH_CHECK("roi_taps");
+    int64_t bx = ceil_div64((int64_t)ih * iw * d * (C / 4), 256);
+    const int64_t cap = ceil_div64((int64_t)sm_count() * 16, B);
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    if (dtype == LTU_F32) roi_resample_bwd_kernel<float><<<dim3((unsigned)bx, B), 256, 0, st>>>((const float*)dy, tabh, tabw, rngh, rngw, (float*)dx, ih, iw, oh, ow, d, C);
+    else roi_resample_bwd_kernel<bf16><<<dim3((unsigned)bx, B), 256, 0, st>>>((const bf16*)dy, tabh, tabw, rngh, rngw, (bf16*)dx, ih, iw, oh, ow, d, C);
+    LTU_LAUNCH_CHECK("roi_resample_bwd");
+    count_launch(2);
+    return LTU_OK;
+}
 
 extern "C" size_t ltu_roi_bbox_scratch(int B, int h, int w) { return (size_t)B * (h + w) * sizeof(int); }
 

@@ -549,6 +549,23 @@ def roi_resample(x: torch.Tensor, box: torch.Tensor, full_hw: Tuple[int, int], r
     return y
 
 
+def roi_resample_bwd(dy: torch.Tensor, box: torch.Tensor, full_hw: Tuple[int, int], roi_h: int, roi_w: int,
+                     eval_h: int, eval_w: int, direction: int) -> torch.Tensor:
+    """Transpose of roi_resample (same arguments): dy has the forward's output extent, the result its input extent."""
+    dev = _chk(dy, box)
+    B, _, _, d, C = dy.shape
+    h, w = full_hw
+    ih, iw = (h, w) if direction == 0 else (eval_h, eval_w)
+    L = _native.lib()
+    nbytes = L.ltu_roi_resample_bwd_workspace(B, h, w, eval_h, eval_w)
+    ws = torch.empty(max(nbytes // 16, 1), 4, dtype=torch.float32, device=dev)
+    dx = torch.empty(B, ih, iw, d, C, dtype=dy.dtype, device=dev)
+    with _Guard(dev) as st:
+        check(L.ltu_roi_resample_bwd(_p(dy), _p(box), _p(dx), _p(ws), nbytes, B, h, w, d, C, roi_h, roi_w, eval_h, eval_w,
+                                     direction, _dt(dy), st), "ltu_roi_resample_bwd")
+    return dx
+
+
 def head_d2s_softmax(logits: torch.Tensor, cout: int, want_probs: bool, want_onehot: bool, want_labels: bool):
     """logits fp32 [B,H2,W2,D,4*cout] -> (probs, onehot, labels) in the reference layout."""
     dev = _chk(logits)

@@ -114,3 +114,44 @@ def test_attention_gate_backward(c_skip, c_up, shape):
         errs[k] = rel_err(grads[k], sd[k].grad)
     print(f"\n[gate bwd bf16 {c_skip}/{c_up}]", {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) <= 3e-2
+
+
+@pytest.mark.parametrize("level,hw,d,C", [(1, (32, 32), 6, 32), (2, (16, 16), 5, 64), (3, (8, 8), 4, 128)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 8e-3)])
+def test_roi_resample_backward(level, hw, d, C, dtype, tol):
+    """Transpose of the fisheye resample (both directions) against autograd through the oracle's separable restatement,
+    for well-formed, small, edge-touching and degenerate boxes; plus the exact-adjoint identity in fp32."""
+    from lintransunet_b200 import ops
+    rc = O.UnetConfig().roi_consts(level)
+    geo = (rc["h_roi"], rc["w_roi"], rc["eval_h"], rc["eval_w"])
+    h, w = hw
+    boxes = torch.tensor([[0.25 * h, 0.2 * w, 0, 0.8 * h, 0.75 * w, d - 1],          # well formed
+                          [0.4 * h, 0.45 * w, 0, 0.6 * h, 0.55 * w, d - 1],          # small: strong magnification
+                          [0.0, 0.0, 0, 0.5 * h, 0.5 * w, d - 1],                    # touches the border
+                          [0.7 * h, 0.6 * w, 0, 0.2 * h, 0.3 * w, d - 1]],           # degenerate (x0 > x1), SURVEY 0.11
+                         dtype=torch.float32)
+    B = boxes.shape[0]
+    x0, y0, x1, y1 = boxes[:, 0:1], boxes[:, 1:2], boxes[:, 3:4], boxes[:, 4:5]
+    g = torch.Generator(device="cuda").manual_seed(level)
+    for direction in (0, 1):
+        if direction == 0:
+            ih, iw, oh, ow = h, w, geo[2], geo[3]
+            ch, cw = O.fisheye_forward_coords(x0, x1, h - 1, geo[0], geo[2]), O.fisheye_forward_coords(y0, y1, w - 1, geo[1], geo[3])
+        else:
+            ih, iw, oh, ow = geo[2], geo[3], h, w
+            ch, cw = O.fisheye_back_coords(x0, x1, h - 1, geo[0], geo[2]), O.fisheye_back_coords(y0, y1, w - 1, geo[1], geo[3])
+        x = torch.randn(B, ih, iw, d, C, device="cuda", generator=g).to(dtype)
+        dy = torch.randn(B, oh, ow, d, C, device="cuda", generator=g).to(dtype)
+        xd = x.double().cpu().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+        yd = O.separable_resample(xd, torch.nan_to_num(ch.double()), torch.nan_to_num(cw.double()))
+        yd.backward(dy.double().cpu().permute(0, 4, 1, 2, 3))
+        dx = ops.roi_resample_bwd(dy, boxes.cuda(), (h, w), *geo, direction=direction)
+        assert dx.shape == x.shape
+        ref = xd.grad.permute(0, 2, 3, 4, 1)
+        err = rel_err(dx.cpu(), ref)
+        print(f"\n[roi resample bwd {dtype} level {level} dir {direction}] rel err {err:.2e}")
+        assert err <= tol
+        if dtype == torch.float32:
+            y = ops.roi_resample(x, boxes.cuda(), (h, w), *geo, direction=direction)
+            lhs, rhs = float((y.double() * dy.double()).sum()), float((x.double() * dx.double()).sum())
+            assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs))
