@@ -22,7 +22,7 @@ from . import ops
 
 __all__ = ["encoder_layer_train", "encoder_layer_backward", "transformer_stack_train", "transformer_stack_backward",
            "conv3d_backward", "conv_in_act_train", "conv_in_act_backward", "encoder_train", "encoder_backward",
-           "embed_block_train", "embed_block_backward", "upblock_train", "upblock_backward", "gate_train", "gate_backward"]
+           "embed_block_train", "embed_block_backward", "upblock_train", "upblock_backward", "gate_train", "gate_backward", "roi_bridge_train", "roi_bridge_backward"]
 
 
 def _params(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
@@ -292,3 +292,27 @@ def gate_backward(dout: torch.Tensor, saved: dict):
     dsk2, g["W_x.0.weight"], g["W_x.0.bias"] = conv3d_backward(saved["skip"], da, att.W_x[0])
     dup, g["W_g.0.weight"], g["W_g.0.bias"] = conv3d_backward(saved["up"], dg, att.W_g[0])
     return dskip + dsk2, dup, g
+
+
+@torch.no_grad()
+def roi_bridge_train(skip: torch.Tensor, fg: torch.Tensor, bridge, box: torch.Tensor = None):
+    """ROIBridge.forward (model/Unet_3Dblock.py:717-755): box from the foreground probability (not differentiated, as in
+    the reference where it comes out of searchsorted), fisheye resample into the ROI, EmbedAttention3DBlock, resample
+    back.  skip bf16 [B,h,w,d,C], fg fp32 [B,h,w,d]; `bridge` = lintransunet_b200.unet.ROIBridge."""
+    B, h, w, d, C = skip.shape
+    if box is None:
+        box = ops.roi_bbox(fg, bridge.min_h_roi, bridge.min_w_roi, bridge.mask_threshold)
+    geo = (bridge.h_roi_size, bridge.w_roi_size, bridge.eval_h_roi_size, bridge.eval_w_roi_size)
+    roi = ops.roi_resample(skip, box, (h, w), *geo, direction=0)
+    t, sv = embed_block_train(roi, bridge.transformer)
+    out = ops.roi_resample(t, box, (h, w), *geo, direction=1)
+    return out, dict(box=box, geo=geo, hw=(h, w), block=sv)
+
+
+@torch.no_grad()
+def roi_bridge_backward(dout: torch.Tensor, saved: dict):
+    """Returns (dskip, parameter gradients keyed like the bridge's state_dict: transformer.<...>)."""
+    dt = ops.roi_resample_bwd(dout.contiguous(), saved["box"], saved["hw"], *saved["geo"], direction=1)
+    droi, g = embed_block_backward(dt, saved["block"])
+    dskip = ops.roi_resample_bwd(droi, saved["box"], saved["hw"], *saved["geo"], direction=0)
+    return dskip, {f"transformer.{k}": v for k, v in g.items()}

@@ -155,3 +155,55 @@ def test_roi_resample_backward(level, hw, d, C, dtype, tol):
             y = ops.roi_resample(x, boxes.cuda(), (h, w), *geo, direction=direction)
             lhs, rhs = float((y.double() * dy.double()).sum()), float((x.double() * dx.double()).sum())
             assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs))
+
+
+def test_roi_bridge_backward():
+    """ROIBridge (model/Unet_3Dblock.py:717-755) end to end: resample into the ROI, EmbedAttention3DBlock, resample back.
+    Reference: fp64 autograd through the oracle's resample / transformer restatements, continuing from the two stored
+    convolution outputs; the box is shared (it is not differentiated on either side)."""
+    from lintransunet_b200.backward import roi_bridge_backward, roi_bridge_train
+    from lintransunet_b200.unet import ROIBridge
+    torch.manual_seed(17)
+    cfg = O.UnetConfig(dim_output=2)
+    lvl = 1
+    cin, dm, nhead = cfg.bridge_dims(lvl)
+    br = ROIBridge(cin, dm, nhead, 8, cfg.roi_size_list[lvl]).cuda()
+    with torch.no_grad():
+        for p_ in br.parameters():
+            p_.copy_(p_.to(torch.bfloat16).float())
+    B, h, w, d = 2, 32, 32, 4
+    skip = torch.randn(B, h, w, d, cin, device="cuda").to(torch.bfloat16)
+    box = torch.tensor([[8.0, 6.0, 0, 25.0, 24.0, d - 1], [4.0, 10.0, 0, 20.0, 28.0, d - 1]], dtype=torch.float32, device="cuda")
+    out, saved = roi_bridge_train(skip, None, br, box=box)
+    sd = {k: v.detach().double().cpu().clone().requires_grad_(True) for k, v in br.state_dict().items()}
+    rc = cfg.roi_consts(lvl)
+    bx = box.cpu()
+    x0, y0, x1, y1 = bx[:, 0:1], bx[:, 1:2], bx[:, 3:4], bx[:, 4:5]
+    kd = skip.double().cpu().permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    roi = O.separable_resample(kd, O.fisheye_forward_coords(x0, x1, h - 1, rc["h_roi"], rc["eval_h"]).double(),
+                               O.fisheye_forward_coords(y0, y1, w - 1, rc["w_roi"], rc["eval_w"]).double())
+    p = "transformer"
+    stored = lambda cd, sv: cd + (sv["raw"].double().cpu().permute(0, 4, 1, 2, 3) - cd).detach()
+    t = O.lrelu(O.inorm(stored(F.conv3d(roi, sd[f"{p}.down_embed.module_list.0.0.weight"], sd[f"{p}.down_embed.module_list.0.0.bias"],
+                                        stride=2, padding=1), saved["block"]["down"])))
+    t = O.transformer_stack(t, sd, p, nhead, sd[f"{p}.pos_encoder.proj.weight"], sd[f"{p}.pos_encoder.proj.bias"], 8)
+    t = F.interpolate(t, scale_factor=2, mode="nearest")
+    t = O.lrelu(O.inorm(stored(F.conv3d(t, sd[f"{p}.up_embed.module_list.0.1.weight"], sd[f"{p}.up_embed.module_list.0.1.bias"],
+                                        padding=1), saved["block"]["up"])))
+    od = O.separable_resample(t, O.fisheye_back_coords(x0, x1, h - 1, rc["h_roi"], rc["eval_h"]).double(),
+                              O.fisheye_back_coords(y0, y1, w - 1, rc["w_roi"], rc["eval_w"]).double())
+    assert out.shape == skip.shape and rel_err(out.cpu(), od.detach().permute(0, 2, 3, 4, 1)) <= 3e-2
+    dout = torch.randn(out.shape, device="cuda").to(torch.bfloat16)
+    od.backward(dout.double().cpu().permute(0, 4, 1, 2, 3))
+    dskip, grads = roi_bridge_backward(dout, saved)
+    assert sorted(grads) == sorted(sd)
+    e_x = rel_err(dskip.cpu(), kd.grad.permute(0, 2, 3, 4, 1))
+    worst, worst_name = 0.0, ""
+    for name, gr in grads.items():
+        if name.endswith("self_attn.linears.1.bias") or (name.endswith(".bias") and "embed" in name):
+            continue                                        # mathematically zero gradients
+        e = rel_err(gr.cpu(), sd[name].grad)
+        if e > worst:
+            worst, worst_name = e, name
+    print(f"\n[roi bridge bwd bf16] dskip rel err {e_x:.2e}, worst parameter gradient {worst:.2e} ({worst_name})")
+    assert e_x <= 8e-2 and worst <= 8e-2
