@@ -58,6 +58,20 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert lib.ltu_keep_largest_component(p, 3, 0b110, 2, 2, 2, 3, p, 8, None) == -1            # workspace too small
     assert b"workspace" in lib.ltu_last_error()
     assert lib.ltu_overlap_counts(p, None, 3, 2, 2, 2, p, None) == -1
+    # backward entry points
+    assert lib.ltu_attn_bwd_workspace(1, 100, 3) == 0                              # heads = 3
+    assert lib.ltu_attn_bwd(p, 128, p, p, 128, p, 128, p, p, p, p, 384, p, p, p, 0, 1, 100, 4, 0, None) == -1   # workspace 0
+    assert b"workspace" in lib.ltu_last_error()
+    assert lib.ltu_add_layernorm_bwd(p, p, p, p, p, p, p, p, 1 << 20, 4, 100, 1e-6, 0, None) == -1              # C = 100
+    assert lib.ltu_gelu_bwd(p, p, p, 7, 0, None) == -1                             # n not a multiple of 4
+    assert lib.ltu_instnorm_bwd(p, p, p, p, p, 1 << 20, 1, 64, 24, 1, 0, None) == -1   # C = 24
+    assert lib.ltu_conv3d_wgrad(p, p, p, p, 1 << 20, 1, 4, 4, 4, 12, 4, 4, 4, 16, 3, 1, 1, 1, 1, 0, None) == -1  # Cin = 12
+    assert lib.ltu_conv3d_wgrad(p, p, p, p, 1 << 20, 1, 4, 4, 4, 16, 3, 4, 4, 16, 3, 1, 1, 1, 1, 0, None) == -1  # Ho mismatch
+    assert b"output size" in lib.ltu_last_error()
+    assert lib.ltu_upsample_trilinear_bwd(p, p, 1, 2, 2, 2, 16, 3, 0, None) == -1  # depth factor 3
+    assert lib.ltu_gate_bwd_workspace(1, 64, 24) > 0 and lib.ltu_gate_bwd_workspace(1, 64, 6) == 0
+    assert lib.ltu_roi_resample_bwd(p, p, p, p, 1 << 20, 1, 8, 8, 4, 16, 10, 6, 9, 5, 0, 0, None) == -1         # eval <= roi
+    assert lib.ltu_zero_insert(p, p, 1, 4, 4, 4, 16, 6, 7, 7, 2, 2, 2, 0, None) == -1                           # target too small
 
 
 def test_product_refuses_cpu_tensors(lib):
