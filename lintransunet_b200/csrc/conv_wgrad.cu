@@ -123,6 +123,113 @@ conv_wgrad_mma_kernel(const WgradParams p) {
     }
 }
 
+// Small layers (Cin, Cout <= CT in {16, 32}): a 64x64 channel block would leave 15/16 (3/4) of the MMAs multiplying zeros
+// and a 32-voxel tile moves 2 KB per CTA step.  Here the tile is 256 voxels x CT channels (one voxel row per thread), the
+// eight warps split the K dimension (32 voxels each) and their CT x CT accumulators are summed in a fixed order through
+// shared memory at the end.  Single-stage tiles; 4-5 CTAs per SM hide the load latency.
+template <int CT>
+__global__ void __launch_bounds__(256)
+conv_wgrad_small_kernel(const WgradParams p) {
+    constexpr int ROW = CT + 8, NCH = CT / 8, MT = CT / 16, NT = CT / 8, VT = 256;
+    __shared__ __align__(16) unsigned char smem_raw[2 * VT * ROW * 2];
+    bf16* sD = reinterpret_cast<bf16*>(smem_raw);            // dy tile [voxel][CT]
+    bf16* sX = sD + VT * ROW;                                // x tile  [voxel][CT], shifted by the tap
+    static_assert(8 * CT * CT * 4 <= 2 * VT * ROW * 2, "the reduction buffer reuses the tiles");
+    const int tap = blockIdx.y;
+    const int kh = p.k == 3 ? tap / 9 : 0, kw = p.k == 3 ? (tap / 3) % 3 : 0, kd = p.k == 3 ? tap % 3 : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mi = lane >> 3, lr = lane & 7;
+    const int64_t v0 = (int64_t)blockIdx.x * p.vox_per_cta;
+    int64_t v1 = v0 + p.vox_per_cta;
+    if (v1 > p.vout) v1 = p.vout;
+    const int ntiles = v1 > v0 ? (int)ceil_div64(v1 - v0, VT) : 0;
+    const int r = threadIdx.x;                               // this thread stages voxel row r of every tile
+
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int64_t v = v0 + (int64_t)t * VT + r;
+        const bool vok = v < v1;
+        const bf16* gd = p.dy;
+        const bf16* gx = p.x;
+        bool xok = false;
+        if (vok) {
+            int64_t q = v;
+            const int dO = (int)(q % p.Do); q /= p.Do;
+            const int wO = (int)(q % p.Wo); q /= p.Wo;
+            const int hO = (int)(q % p.Ho);
+            const int b = (int)(q / p.Ho);
+            gd = p.dy + v * p.Cout;
+            const int hi = hO * p.sh + kh - p.pad, wi = wO * p.sw + kw - p.pad, di = dO * p.sd + kd - p.pad;
+            const int e = p.up2 ? 2 : 1;
+            xok = hi >= 0 && hi < e * p.Hi && wi >= 0 && wi < e * p.Wi && di >= 0 && di < e * p.Di;
+            if (xok) gx = p.x + ((((int64_t)b * p.Hi + hi / e) * p.Wi + wi / e) * p.Di + di / e) * p.Cin;
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const bool dok = vok && c * 8 < p.Cout, iok = xok && c * 8 < p.Cin;
+            cp_async16_zfill(sD + r * ROW + c * 8, dok ? gd + c * 8 : p.dy, dok ? 16 : 0);
+            cp_async16_zfill(sX + r * ROW + c * 8, iok ? gx + c * 8 : p.x, iok ? 16 : 0);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int rr = warp * 32 + ks * 16;
+            uint32_t a[MT][4], bq[MT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+                ldsm4t_w(smem_u32_generic(sD + (rr + lr + 8 * (mi >> 1)) * ROW + mt * 16 + 8 * (mi & 1)), a[mt]);
+#pragma unroll
+            for (int np = 0; np < MT; ++np)
+                ldsm4t_w(smem_u32_generic(sX + (rr + lr + 8 * (mi & 1)) * ROW + np * 16 + 8 * (mi >> 1)), bq[np]);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    mma_w(acc[mt][nt], a[mt], bq[nt >> 1][(nt & 1) * 2], bq[nt >> 1][(nt & 1) * 2 + 1]);
+        }
+        __syncthreads();                                     // the tiles are free again
+    }
+    // ordered sum of the eight warps' accumulators
+    float* red = reinterpret_cast<float*>(smem_raw);         // [8][CT][CT]
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            float* dst = red + ((warp * CT) + mt * 16 + gq) * CT + nt * 8 + 2 * tq;
+            dst[0] = acc[mt][nt][0]; dst[1] = acc[mt][nt][1];
+            dst[8 * CT] = acc[mt][nt][2]; dst[8 * CT + 1] = acc[mt][nt][3];
+        }
+    __syncthreads();
+    float* out = p.part + ((int64_t)blockIdx.x * gridDim.y + tap) * CT * CT;
+    for (int i = threadIdx.x; i < CT * CT; i += 256) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w * CT * CT + i];
+        out[i] = sum;
+    }
+}
+
+static inline int wgrad_small_chunks(int64_t vout, int taps) {
+    int64_t want = ceil_div64((int64_t)sm_count() * 8, taps);        // about two waves of 4 CTAs / SM
+    const int64_t most = ceil_div64(vout, 4 * 256);                  // at least four 256-voxel tiles per CTA
+    if (want > most) want = most;
+    return (int)(want < 1 ? 1 : want);
+}
+static inline int wgrad_small_ct(int Cin, int Cout) {                // 0: use the 64x64 block kernel
+    const int m = Cin > Cout ? Cin : Cout;
+    return m <= 16 ? 16 : (m <= 32 ? 32 : 0);
+}
+
 // dw[tap][co][ci] = sum over the chunks (in order) of the partial tiles
 __global__ void __launch_bounds__(256)
 conv_wgrad_finalize_kernel(const float* __restrict__ part, float* __restrict__ dw, int chunks, int taps, int Cout, int Cin,
@@ -154,6 +261,8 @@ using namespace ltu;
 extern "C" size_t ltu_conv3d_wgrad_workspace(int B, int Ho, int Wo, int Do, int Cin, int Cout, int ksize) {
     if (B <= 0 || Ho <= 0 || Wo <= 0 || Do <= 0 || Cin <= 0 || Cout <= 0 || !(ksize == 1 || ksize == 3)) return 0;
     const int taps = ksize * ksize * ksize, cob = (Cout + 63) / 64, cib = (Cin + 63) / 64;
+    const int ct = wgrad_small_ct(Cin, Cout);
+    if (ct) return (size_t)wgrad_small_chunks((int64_t)B * Ho * Wo * Do, taps) * taps * ct * ct * sizeof(float);
     const int chunks = wgrad_chunks((int64_t)B * Ho * Wo * Do, taps, cob * cib);
     return (size_t)chunks * taps * cob * 64 * cib * 64 * sizeof(float);
 }
@@ -178,11 +287,21 @@ extern "C" int ltu_conv3d_wgrad(const void* x, const void* dy, float* dw, void* 
     p.k = ksize; p.sh = sh; p.sw = sw; p.sd = sd; p.pad = pad; p.up2 = up2 ? 1 : 0;
     p.vout = (int64_t)B * Ho * Wo * Do;
     const int taps = ksize * ksize * ksize, cob = (Cout + 63) / 64, cib = (Cin + 63) / 64;
-    const int chunks = wgrad_chunks(p.vout, taps, cob * cib);
-    p.vox_per_cta = ceil_div64(ceil_div64(p.vout, chunks), kTile) * kTile;
-    p.cin_blocks = cib; p.CoP = cob * 64; p.CiP = cib * 64;
     cudaStream_t st = (cudaStream_t)stream;
-    conv_wgrad_mma_kernel<<<dim3(chunks, taps, cob * cib), 256, 0, st>>>(p);
+    const int ct = wgrad_small_ct(Cin, Cout);
+    int chunks;
+    if (ct) {
+        chunks = wgrad_small_chunks(p.vout, taps);
+        p.vox_per_cta = ceil_div64(ceil_div64(p.vout, chunks), 256) * 256;
+        p.cin_blocks = 1; p.CoP = ct; p.CiP = ct;
+        if (ct == 16) conv_wgrad_small_kernel<16><<<dim3(chunks, taps), 256, 0, st>>>(p);
+        else conv_wgrad_small_kernel<32><<<dim3(chunks, taps), 256, 0, st>>>(p);
+    } else {
+        chunks = wgrad_chunks(p.vout, taps, cob * cib);
+        p.vox_per_cta = ceil_div64(ceil_div64(p.vout, chunks), kTile) * kTile;
+        p.cin_blocks = cib; p.CoP = cob * 64; p.CiP = cib * 64;
+        conv_wgrad_mma_kernel<<<dim3(chunks, taps, cob * cib), 256, 0, st>>>(p);
+    }
     LTU_LAUNCH_CHECK("conv3d_wgrad");
     const int64_t n = (int64_t)taps * Cout * Cin;
     int64_t fb = ceil_div64(n, 256);
