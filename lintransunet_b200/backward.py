@@ -1,15 +1,25 @@
-"""Training-mode forward and backward of one SelfAttentionLayer (model/trans_block.py:169-211) on the
-sm_100a kernels -- the first complete slice of SURVEY 8f-1 (backward / train step).
+"""Training-mode forward and backward of the model's building blocks on the sm_100a kernels.
 
-Not wired into ``MaskTransUnet.forward`` yet (the convolution, InstanceNorm, resampling and head backward kernels
-do not exist): ``encoder_layer_train`` / ``encoder_layer_backward`` are the building block an
-``autograd.Function`` around the transformer stack will call.  Dropout-free (``dropout=0.0``), like every parity
-test of this repo.
+Every operator of ``MaskTransUnet`` has a gradient kernel (include/ltu_b200.h: ``ltu_attn_bwd``, ``ltu_add_layernorm_bwd``,
+``ltu_gelu_bwd``, ``ltu_posenc_wgrad``, ``ltu_instnorm_bwd``, ``ltu_conv3d_wgrad`` + the forward convolution kernels for the
+input gradient, ``ltu_upsample_trilinear_bwd``, ``ltu_roi_resample_bwd``, ``ltu_gate_bwd``, ``ltu_mask_softmax_bwd``,
+``ltu_head_d2s_softmax_bwd``); this module composes them, block by block, each pair ``*_train`` / ``*_backward`` with a parity
+test against fp64 autograd through the oracle (tests/test_encoder_layer_bwd_gpu.py, test_conv_bwd_gpu.py, test_unet_bwd_gpu.py):
 
-Per layer the native launches are: forward ``kv_reduce`` + ``kv_combine`` + ``q_readout`` + 2 x ``add_layernorm`` +
-``gelu``; backward 2 x ``add_layernorm_bwd`` (+ finalize) + ``gelu_bwd`` + ``attn_bwd`` (reduce, combine, apply).
-The Linear layers and their weight gradients are plain cuBLAS GEMMs (``F.linear`` / ``torch.mm`` / ``torch.addmm``),
-as in the forward.  Activations may be fp32 or bf16; parameter gradients are returned in fp32.
+* ``encoder_layer_*``      one SelfAttentionLayer (model/trans_block.py:169-211), fp32 or bf16
+* ``transformer_stack_*``  the 8-layer stack with its positional conv (PosAttention3DBlock / EmbedAttention3DBlock)
+* ``conv3d_backward``, ``conv_in_act_*``   Conv3d (strided / upsampled) and Conv -> InstanceNorm -> LeakyReLU (+ residual), bf16
+* ``encoder_*``            the whole Encoder (stem + 4 DownBlocks)
+* ``embed_block_*``, ``roi_bridge_*``      the inside of a ROI bridge and the bridge itself (fisheye resample both ways)
+* ``upblock_*``, ``gate_*``                the decoder's UpBlock and attention gate
+
+NOT yet composed: the ROIDecoder loop (it also needs the 2/3/12-channel head convolutions padded to 8 channels for the weight
+gradient), the link to ``lintransunet_b200.losses`` and the ``autograd.Function`` wiring -- ``MaskTransUnet.forward`` therefore
+still refuses to run with autograd enabled.  Dropout-free (``dropout=0.0``), like every parity test of this repo.
+
+The ``nn.Linear`` layers and their weight gradients are plain cuBLAS GEMMs (``F.linear`` / ``torch.mm`` / ``torch.addmm``), as
+in the forward; small tensor glue (concatenation, residual adds, bias-gradient row sums) uses torch ops.  Weights are re-packed
+on every call here (no plan cache yet).  Parameter gradients are returned in fp32 under the reference's parameter names.
 """
 from __future__ import annotations
 
