@@ -121,3 +121,85 @@ def test_parser_defaults_are_the_reference_defaults():
     assert (a.roi_size, a.sw_batch_size, a.overlap, a.threshold) == (512, 4, 0.6, 0.5)
     b = get_parse(["--dir_data", "/tmp/x", "--num_layers", "8,16,32", "--is_roi_list", "[False, True, True]"])
     assert b.num_layers == [8, 16, 32] and b.is_roi_list == [False, True, True]
+
+
+def test_integer_form_of_the_half_decisions_is_exact():
+    """postproc_kernels.cu decides `fp32(k/n) >= 0.5` as 2k >= n and `rint(fp32(k/n)) == 1` as 2k > n (packed-byte SIMD):
+    exhaustive check over every vote count a uint8 volume can hold."""
+    n = np.arange(1, 256, dtype=np.int64)[None, :]
+    k = np.arange(0, 256, dtype=np.int64)[:, None]
+    ok = k <= n
+    frac = (k.astype(np.float32) / n.astype(np.float32)).astype(np.float32)
+    assert np.array_equal((frac >= np.float32(0.5))[ok], (2 * k >= n)[ok])
+    rounded = torch.round(torch.from_numpy(frac)).numpy()
+    assert np.array_equal((rounded == 1)[ok], (2 * k > n)[ok])
+
+
+def _run_based_components(fg: np.ndarray) -> np.ndarray:
+    """Sequential model of cc_init_kernel + cc_merge26_kernel (postproc_kernels.cu): 32-voxel segments linked without
+    unions, then one union per (run, neighbouring run) pair issued by the rule in the kernel's comment.  Returns the root
+    (smallest voxel index of the component) per voxel, -1 for background."""
+    H, W, D = fg.shape
+    V = H * W * D
+    f = fg.ravel()
+    L = np.full(V, -1, dtype=np.int64)
+    for base in range(0, V, 32):
+        for lane in range(min(32, V - base)):
+            v = base + lane
+            if not f[v]:
+                continue
+            s = lane
+            while s > 0 and f[base + s - 1] and (base + s) % D != 0:
+                s -= 1
+            L[v] = base + s
+
+    def find(x):
+        while L[x] != x:
+            x = L[x]
+        return x
+
+    def union(a, b):
+        a, b = find(a), find(b)
+        if a != b:
+            L[max(a, b)] = min(a, b)
+
+    for v in range(V):
+        if L[v] < 0:
+            continue
+        d, t = v % D, v // D
+        w, h = t % W, t // W
+        prev = d > 0 and f[v - 1]
+        if prev and v % 32 == 0:
+            union(v, v - 1)
+        for dh, dw in ((-1, -1), (-1, 0), (-1, 1), (0, -1)):
+            hh, ww = h + dh, w + dw
+            if hh < 0 or ww < 0 or ww >= W:
+                continue
+            row = (hh * W + ww) * D
+            um = d > 0 and f[row + d - 1]
+            u0 = f[row + d]
+            up = d + 1 < D and f[row + d + 1]
+            if not prev:
+                if um:
+                    union(v, row + d - 1)
+                elif u0:
+                    union(v, row + d)
+            if up and not u0:
+                union(v, row + d + 1)
+    return np.array([find(v) if L[v] >= 0 else -1 for v in range(V)]).reshape(fg.shape)
+
+
+@pytest.mark.parametrize("shape", [(7, 6, 5), (5, 4, 40), (6, 5, 33), (3, 3, 100)])
+def test_run_based_merge_rule_gives_the_26_connected_components(shape):
+    """The union rule of cc_merge26_kernel (at most one union per pair of adjacent runs) yields exactly the
+    26-connected components, for runs that cross the 32-voxel segments and rows that are not multiples of 32."""
+    from scipy import ndimage
+    g = np.random.default_rng(sum(shape))
+    for density in (0.05, 0.3, 0.6, 0.9):
+        fg = g.random(shape) < density
+        roots = _run_based_components(fg)
+        labels, n = ndimage.label(fg, structure=np.ones((3, 3, 3)))
+        pairs = set(zip(labels[fg].tolist(), roots[fg].tolist()))
+        assert len(pairs) == n == len(set(roots[fg].tolist()))               # same partition
+        for lab, root in pairs:                                             # root = first voxel in raster order
+            assert root == int(np.flatnonzero(labels.ravel() == lab)[0])
