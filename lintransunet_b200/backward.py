@@ -13,9 +13,10 @@ test against fp64 autograd through the oracle (tests/test_encoder_layer_bwd_gpu.
 * ``embed_block_*``, ``roi_bridge_*``      the inside of a ROI bridge and the bridge itself (fisheye resample both ways)
 * ``upblock_*``, ``gate_*``                the decoder's UpBlock and attention gate
 
-NOT yet composed: the ROIDecoder loop (it also needs the 2/3/12-channel head convolutions padded to 8 channels for the weight
-gradient), the link to ``lintransunet_b200.losses`` and the ``autograd.Function`` wiring -- ``MaskTransUnet.forward`` therefore
-still refuses to run with autograd enabled.  Dropout-free (``dropout=0.0``), like every parity test of this repo.
+WRITTEN BUT NOT YET RUN ON A GPU (the round's GPU budget was spent; tests/test_train_step_gpu.py is skipped until its first
+run): ``head_conv_*`` (the 2/3/12-channel head convolutions, output gradient padded to 8 channels), ``decoder_*`` (the ROIDecoder
+loop) and ``model_loss_and_gradients`` (encoder + decoder + ``lintransunet_b200.losses``).  The ``autograd.Function`` wiring does
+not exist -- ``MaskTransUnet.forward`` still refuses to run with autograd enabled.  Dropout-free (``dropout=0.0``), like every parity test of this repo.
 
 The ``nn.Linear`` layers and their weight gradients are plain cuBLAS GEMMs (``F.linear`` / ``torch.mm`` / ``torch.addmm``), as
 in the forward; small tensor glue (concatenation, residual adds, bias-gradient row sums) uses torch ops.  Weights are re-packed
@@ -32,7 +33,8 @@ from . import ops
 
 __all__ = ["encoder_layer_train", "encoder_layer_backward", "transformer_stack_train", "transformer_stack_backward",
            "conv3d_backward", "conv_in_act_train", "conv_in_act_backward", "encoder_train", "encoder_backward",
-           "embed_block_train", "embed_block_backward", "upblock_train", "upblock_backward", "gate_train", "gate_backward", "roi_bridge_train", "roi_bridge_backward"]
+           "embed_block_train", "embed_block_backward", "upblock_train", "upblock_backward", "gate_train", "gate_backward", "roi_bridge_train", "roi_bridge_backward",
+           "head_conv_train", "head_conv_backward", "decoder_train", "decoder_backward", "model_loss_and_gradients"]
 
 
 def _params(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
@@ -326,3 +328,113 @@ def roi_bridge_backward(dout: torch.Tensor, saved: dict):
     droi, g = embed_block_backward(dt, saved["block"])
     dskip = ops.roi_resample_bwd(droi, saved["box"], saved["hw"], *saved["geo"], direction=0)
     return dskip, {f"transformer.{k}": v for k, v in g.items()}
+
+
+# ----------------------------------------------------------------------------- decoder loop and the whole model
+# NOT YET RUN ON A GPU: composition of verified blocks, written after the round's GPU budget was spent.
+@torch.no_grad()
+def head_conv_train(x: torch.Tensor, conv: torch.nn.Conv3d):
+    """A 3x3x3 convolution with fp32 logits and few output channels (mask heads :1380, final_block :1392)."""
+    from .unet import _ConvW
+    cw = _ConvW(conv, True)
+    logits = ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, pad=1, out_f32=True, w_tc=cw.w_tc)[0]
+    return logits, dict(x=x, conv=conv)
+
+
+@torch.no_grad()
+def head_conv_backward(dlogits: torch.Tensor, saved: dict):
+    """dlogits fp32 [B,h,w,d,Cout] -> (dx bf16, dW [Cout,Cin,3,3,3] fp32, dbias fp32).  The gradient is rounded to bf16 and
+    zero-padded to a multiple of 8 channels (16-byte vectors of ltu_conv3d_wgrad); the padded filter rows are zero."""
+    conv = saved["conv"]
+    cout, cin, k = conv.weight.shape[0], conv.weight.shape[1], conv.kernel_size[0]
+    cp = (cout + 7) // 8 * 8
+    dy = torch.zeros(*dlogits.shape[:-1], cp, dtype=torch.bfloat16, device=dlogits.device)
+    dy[..., :cout] = dlogits.to(torch.bfloat16)
+    padded = torch.nn.Conv3d(cin, cp, k, padding=k // 2).to(conv.weight.device)
+    padded.weight.zero_()
+    padded.bias.zero_()
+    padded.weight[:cout].copy_(conv.weight.detach())
+    dx, dw, db = conv3d_backward(saved["x"], dy, padded)
+    return dx, dw[:cout].contiguous(), db[:cout].contiguous()
+
+
+@torch.no_grad()
+def decoder_train(bottle: torch.Tensor, skips, dec, dim_output: int):
+    """ROIDecoder.forward (model/Unet_3Dblock.py:1359-1396) in training mode: returns (probs fp32 [B,C,H,W,D], mask_list,
+    saved).  `dec` = lintransunet_b200.unet.ROIDecoder; bottle / skips from encoder_train."""
+    from .unet import ROIBridge
+    n = len(dec.num_layers)
+    tr = dec.bridge_list[n - 1].transformer
+    x, sv_bottle = transformer_stack_train(bottle, tr.layers, tr.pos_encoders[0])
+    levels, mask_list = [], []
+    for i in range(1, n):
+        fd = 2 if (n - i) % 2 == 0 else 1                                     # :1375-1378
+        xu = ops.upsample_trilinear(x, fd)
+        lvl = n - 1 - i
+        logits, sv_m = head_conv_train(xu, dec.mask_conv_list[lvl])            # :1380
+        mask, fg = ops.mask_softmax(logits, want_mask=True)
+        mask_list.append(mask)
+        skip, sv_g = gate_train(skips[-i], xu, dec.att_conv_list[lvl])         # :1384-1385
+        bridge, sv_b = dec.bridge_list[lvl], None
+        if isinstance(bridge, ROIBridge):
+            skip, sv_b = roi_bridge_train(skip, fg, bridge)                    # :1387-1388
+        x, sv_u = upblock_train(xu, skip, dec.block_list[i - 1])
+        levels.append(dict(fd=fd, lvl=lvl, logits=logits, m=sv_m, g=sv_g, b=sv_b, u=sv_u))
+    logits, sv_f = head_conv_train(x, dec.final_block)                         # :1392
+    probs = ops.head_d2s_softmax(logits, dim_output, want_probs=True, want_onehot=False, want_labels=False)[0]
+    return probs, mask_list, dict(bottle=sv_bottle, levels=levels, final=sv_f, final_logits=logits, n=n, cout=dim_output)
+
+
+@torch.no_grad()
+def decoder_backward(dprobs: torch.Tensor, dmask_list, saved: dict):
+    """Returns (d_bottle, d_skips (one per encoder block), gradients keyed like ROIDecoder's state_dict)."""
+    n = saved["n"]
+    grads: Dict[str, torch.Tensor] = {}
+    dlogits = ops.head_d2s_softmax_bwd(saved["final_logits"], dprobs.contiguous().float(), saved["cout"])
+    dx, grads["final_block.weight"], grads["final_block.bias"] = head_conv_backward(dlogits, saved["final"])
+    d_skips = [None] * (n - 1)
+    for i in range(n - 1, 0, -1):
+        lv = saved["levels"][i - 1]
+        lvl = lv["lvl"]
+        dxu, dskip, g = upblock_backward(dx, lv["u"])
+        for k, v in g.items():
+            grads[f"block_list.{i - 1}.{k}"] = v
+        if lv["b"] is not None:
+            dskip, g = roi_bridge_backward(dskip, lv["b"])
+            for k, v in g.items():
+                grads[f"bridge_list.{lvl}.{k}"] = v
+        dskip, dup, g = gate_backward(dskip, lv["g"])
+        for k, v in g.items():
+            grads[f"att_conv_list.{lvl}.{k}"] = v
+        dxu = dxu + dup
+        if dmask_list is not None and dmask_list[i - 1] is not None:            # deep supervision on this mask head
+            dlm = ops.mask_softmax_bwd(lv["logits"], dmask_list[i - 1].contiguous().float())
+            dxm, grads[f"mask_conv_list.{lvl}.weight"], grads[f"mask_conv_list.{lvl}.bias"] = head_conv_backward(dlm, lv["m"])
+            dxu = dxu + dxm
+        d_skips[n - 1 - i] = dskip                                               # skips[-i]
+        dx = ops.upsample_trilinear_bwd(dxu, lv["fd"])
+    d_bottle, g = transformer_stack_backward(dx, saved["bottle"])
+    for k, v in g.items():
+        grads[f"bridge_list.{n - 1}.transformer." + k.replace("pos.", "pos_encoders.0.")] = v
+    return d_bottle, d_skips, grads
+
+
+def model_loss_and_gradients(model, x: torch.Tensor, masks: torch.Tensor):
+    """One training step's loss and parameter gradients of a binary MaskTransUnet (dropout-free) on the bf16 path:
+    encoder_train -> decoder_train -> lintransunet_b200.losses.deep_supervision_loss (torch autograd on the outputs only)
+    -> decoder_backward -> encoder_backward.  Returns (total, terms, grads keyed like model.state_dict())."""
+    from . import losses
+    with torch.no_grad():
+        bottle, skips, sv_e = encoder_train(x, model.encode)
+        probs, mask_list, sv_d = decoder_train(bottle, skips, model.decode, model.dim_output)
+    p = probs.detach().requires_grad_(True)
+    ms = [m.detach().requires_grad_(True) for m in mask_list]
+    with torch.enable_grad():
+        total, terms = losses.deep_supervision_loss(p, ms, masks)
+        dall = torch.autograd.grad(total, [p] + ms)
+    with torch.no_grad():
+        d_bottle, d_skips, g_dec = decoder_backward(dall[0], list(dall[1:]), sv_d)
+        g_enc = encoder_backward(d_bottle, d_skips, sv_e)
+    grads = {f"encode.{k}": v for k, v in g_enc.items()}
+    grads.update({f"decode.{k}": v for k, v in g_dec.items()})
+    return total.detach(), terms, grads
