@@ -13,9 +13,11 @@ test against fp64 autograd through the oracle (tests/test_encoder_layer_bwd_gpu.
 * ``embed_block_*``, ``roi_bridge_*``      the inside of a ROI bridge and the bridge itself (fisheye resample both ways)
 * ``upblock_*``, ``gate_*``                the decoder's UpBlock and attention gate
 
-WRITTEN BUT NOT YET RUN ON A GPU (the round's GPU budget was spent; tests/test_train_step_gpu.py is skipped until its first
-run): ``head_conv_*`` (the 2/3/12-channel head convolutions, output gradient padded to 8 channels), ``decoder_*`` (the ROIDecoder
-loop) and ``model_loss_and_gradients`` (encoder + decoder + ``lintransunet_b200.losses``).  The ``autograd.Function`` wiring does
+NOT YET RUN WITH THE KERNELS (the round's GPU budget was spent; tests/test_train_step_gpu.py is skipped until its first run):
+``head_conv_*`` (the 2/3/12-channel head convolutions, output gradient padded to 8 channels), ``decoder_*`` (the ROIDecoder
+loop) and ``model_loss_and_gradients`` (encoder + decoder + ``lintransunet_b200.losses``).  Their host logic IS verified:
+tests/test_backward_composition_cpu.py replaces every kernel wrapper by a torch stand-in (fp64) and reproduces all 600 parameter
+gradients of autograd through the oracle model and loss to 3e-8.  The ``autograd.Function`` wiring does
 not exist -- ``MaskTransUnet.forward`` still refuses to run with autograd enabled.  Dropout-free (``dropout=0.0``), like every parity test of this repo.
 
 The ``nn.Linear`` layers and their weight gradients are plain cuBLAS GEMMs (``F.linear`` / ``torch.mm`` / ``torch.addmm``), as
@@ -30,6 +32,8 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
+
+_ACT = torch.bfloat16          # activation storage type of the convolutional blocks (the conv weight gradient is bf16 only)
 
 __all__ = ["encoder_layer_train", "encoder_layer_backward", "transformer_stack_train", "transformer_stack_backward",
            "conv3d_backward", "conv_in_act_train", "conv_in_act_backward", "encoder_train", "encoder_backward",
@@ -201,7 +205,7 @@ def conv_in_act_backward(dy: torch.Tensor, saved: dict, need_dx: bool = True):
 def encoder_train(x: torch.Tensor, enc):
     """Encoder.forward (model/Unet_3Dblock.py:596-607) on the bf16 path with everything the backward needs.
     x fp32 [B,1,H,W,D]; `enc` = the lintransunet_b200.unet.Encoder container.  Returns (bottleneck, skips, saved)."""
-    a = ops.s2d_input(x.contiguous().float(), torch.bfloat16, cpad=8)          # 4 channels + 4 zero channels
+    a = ops.s2d_input(x.contiguous().float(), _ACT, cpad=8)                    # 4 channels + 4 zero channels
     a, sv_stem = conv_in_act_train(a, enc.input_block, cin_pad=8)
     blocks, skips = [], []
     for blk in enc.block_list:
@@ -331,7 +335,7 @@ def roi_bridge_backward(dout: torch.Tensor, saved: dict):
 
 
 # ----------------------------------------------------------------------------- decoder loop and the whole model
-# NOT YET RUN ON A GPU: composition of verified blocks, written after the round's GPU budget was spent.
+# Host logic verified with fp64 stand-ins for the kernels (tests/test_backward_composition_cpu.py); not yet run on a GPU.
 @torch.no_grad()
 def head_conv_train(x: torch.Tensor, conv: torch.nn.Conv3d):
     """A 3x3x3 convolution with fp32 logits and few output channels (mask heads :1380, final_block :1392)."""
@@ -348,8 +352,8 @@ def head_conv_backward(dlogits: torch.Tensor, saved: dict):
     conv = saved["conv"]
     cout, cin, k = conv.weight.shape[0], conv.weight.shape[1], conv.kernel_size[0]
     cp = (cout + 7) // 8 * 8
-    dy = torch.zeros(*dlogits.shape[:-1], cp, dtype=torch.bfloat16, device=dlogits.device)
-    dy[..., :cout] = dlogits.to(torch.bfloat16)
+    dy = torch.zeros(*dlogits.shape[:-1], cp, dtype=_ACT, device=dlogits.device)
+    dy[..., :cout] = dlogits.to(_ACT)
     padded = torch.nn.Conv3d(cin, cp, k, padding=k // 2).to(conv.weight.device)
     padded.weight.zero_()
     padded.bias.zero_()
