@@ -327,6 +327,42 @@ def _signature(model: nn.Module):
     return tuple((p.data_ptr(), p._version) for p in model.parameters())
 
 
+# ----------------------------------------------------------------------------- training
+class _NativeTrainFunction(torch.autograd.Function):
+    """``(probs, *mask_list) = f(x, *parameters)`` with the native forward (training mode) and the native backward of
+    lintransunet_b200/backward.py, so that ``loss.backward()`` of the reference's train step
+    (utils/utils_3D_embed_full.py:63-91) fills ``p.grad`` of every parameter.  bf16 activations, fp32 gradients.
+    Host logic verified on the CPU with stand-in kernels (tests/test_backward_composition_cpu.py); opt-in
+    (``model.native_backward`` / LTU_NATIVE_BACKWARD=1) until it has run on a GPU."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        from . import backward as BW
+        bottle, skips, sv_e = BW.encoder_train(x, model.encode)
+        probs, mask_list, sv_d = BW.decoder_train(bottle, skips, model.decode, model.dim_output)
+        ctx.saved_state = (sv_e, sv_d)
+        ctx.names = [n for n, _ in model.named_parameters()]
+        ctx.dtypes = [p.dtype for p in params]
+        ctx.out_shapes = [tuple(probs.shape)] + [tuple(m.shape) for m in mask_list]
+        return (probs, *mask_list)
+
+    @staticmethod
+    def backward(ctx, dprobs, *dmasks):
+        from . import backward as BW
+        sv_e, sv_d = ctx.saved_state
+        if dprobs is None:
+            dprobs = torch.zeros(ctx.out_shapes[0], dtype=torch.float32, device=sv_d["final_logits"].device)
+        d_bottle, d_skips, g_dec = BW.decoder_backward(dprobs, list(dmasks), sv_d)
+        g_enc = BW.encoder_backward(d_bottle, d_skips, sv_e)
+        grads = {f"encode.{k}": v for k, v in g_enc.items()}
+        grads.update({f"decode.{k}": v for k, v in g_dec.items()})
+        out = []
+        for name, dt in zip(ctx.names, ctx.dtypes):
+            g = grads.get(name)                      # None: dead parameters (pos_encoders.1-7) and unsupervised heads
+            out.append(None if g is None else g.to(dt))
+        return (None, None, *out)
+
+
 # ----------------------------------------------------------------------------- the model
 class MaskTransUnet(nn.Module):
     """Same constructor, forward contract and state_dict as the reference
@@ -371,6 +407,8 @@ class MaskTransUnet(nn.Module):
         self.use_fused_attn = os.environ.get("LTU_FUSED_ATTN", "1") == "1"
         # bf16 path: compute the mask head inside UpBlock.conv1's launch (same input), fp32 logits as a second output
         self.fuse_mask_head = os.environ.get("LTU_FUSE_MASK_HEAD", "1") != "0"
+        # training with autograd through the native backward (bf16 path, dropout 0): opt-in until it has run on a GPU
+        self.native_backward = os.environ.get("LTU_NATIVE_BACKWARD", "0") == "1"
         self._plans: Dict[tuple, tuple] = {}
         self._graphs: Dict[tuple, dict] = {}
 
@@ -521,8 +559,19 @@ class MaskTransUnet(nn.Module):
                 raise NotImplementedError("training-mode dropout is not implemented (forward hot path only); "
                                           "construct with dropout=0.0 or call .eval()")
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-                raise NotImplementedError("backward is not implemented yet (SURVEY 8f-1): wrap the call in "
-                                          "torch.no_grad()")
+                if not self.native_backward:
+                    raise NotImplementedError("the native backward (SURVEY 8f-1) is opt-in until it has run on a GPU: set "
+                                              "model.native_backward = True (or LTU_NATIVE_BACKWARD=1), or wrap the call "
+                                              "in torch.no_grad()")
+                if self._compute_dtype() != torch.bfloat16:
+                    raise NotImplementedError("the native backward exists on the bf16 path only: call the model inside "
+                                              "torch.autocast (as the reference's train step does)")
+                B, _, H, W, D = x.shape
+                if H % 32 or W % 32 or D % 4:
+                    raise ValueError("H and W must be multiples of 32 and D a multiple of 4")
+                with torch.autocast("cuda", enabled=False):
+                    out = _NativeTrainFunction.apply(self, x.contiguous().float(), *[p for _, p in self.named_parameters()])
+                return out[0], list(out[1:])
         B, _, H, W, D = x.shape
         if H % 32 or W % 32 or D % 4:
             raise ValueError("H and W must be multiples of 32 and D a multiple of 4")

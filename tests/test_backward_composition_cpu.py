@@ -274,3 +274,35 @@ def test_whole_model_gradient_composition_matches_oracle_autograd(standins):
             worst, worst_name = e, k
     print(f"\n[backward composition, fp64 stand-ins] worst relative weight-gradient error {worst:.2e} ({worst_name})")
     assert worst <= 1e-6                                       # parameter gradients are returned in fp32
+
+
+def test_autograd_wiring_fills_parameter_gradients(standins):
+    """loss.backward() through lintransunet_b200.unet._NativeTrainFunction (what MaskTransUnet.forward returns in training
+    mode with model.native_backward) gives every live parameter the oracle-autograd gradient and leaves the dead ones None."""
+    from lintransunet_b200 import MaskTransUnet, losses
+    from lintransunet_b200.unet import _NativeTrainFunction
+    cfg = O.UnetConfig(dim_output=2)
+    sd = O.make_state_dict(cfg, seed=0)
+    model = MaskTransUnet(list(cfg.num_layers), list(cfg.roi_size_list), list(cfg.is_roi_list), 1, 2, dropout=0.0)
+    model.load_state_dict(sd)
+    model.train()
+    x = O.make_input((1, 1, 64, 64, 16), seed=1, blob=True)
+    masks = torch.zeros(1, 1, 64, 64, 16, dtype=torch.long)
+    masks[:, :, 20:44, 16:40, 4:12] = 1
+    out = _NativeTrainFunction.apply(model, x, *[p for _, p in model.named_parameters()])
+    probs, mask_list = out[0], list(out[1:])
+    assert probs.requires_grad and len(mask_list) == 4
+    total, _ = losses.deep_supervision_loss(probs, mask_list, masks)
+    total.backward()
+    sdd = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.mask_trans_unet_forward(x.double(), sdd, cfg)
+    total_ref, _ = T.train_loss(ref["probs"], ref["mask_list"], masks)
+    total_ref.backward()
+    gmax = max(float(v.grad.norm()) for v in sdd.values() if v.grad is not None)
+    for name, p in model.named_parameters():
+        r = sdd[name].grad
+        if r is None:
+            assert p.grad is None, name
+            continue
+        assert p.grad is not None and p.grad.dtype == p.dtype and p.grad.shape == p.shape, name
+        assert float((p.grad.double() - r).norm()) <= 1e-5 * float(r.norm()) + 1e-7 * gmax, name
