@@ -13,7 +13,12 @@ import torch
 from oracle import ltu_oracle as O
 from tests.helpers import load_golden
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skip(reason="decoder-loop composition not yet run on a GPU (round 1 budget spent)")]
+import os
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("LTU_RUN_TRAIN_STEP") != "1",
+                                 reason="decoder-loop composition not yet run on a GPU (round 1 budget spent); "
+                                        "LTU_RUN_TRAIN_STEP=1 runs it")]
 
 
 def test_train_step_gradients_against_the_reference():
