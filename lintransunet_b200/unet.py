@@ -332,8 +332,9 @@ class _NativeTrainFunction(torch.autograd.Function):
     """``(probs, *mask_list) = f(x, *parameters)`` with the native forward (training mode) and the native backward of
     lintransunet_b200/backward.py, so that ``loss.backward()`` of the reference's train step
     (utils/utils_3D_embed_full.py:63-91) fills ``p.grad`` of every parameter.  bf16 activations, fp32 gradients.
-    Host logic verified on the CPU with stand-in kernels (tests/test_backward_composition_cpu.py); opt-in
-    (``model.native_backward`` / LTU_NATIVE_BACKWARD=1) until it has run on a GPU."""
+    The functions it calls reproduce the reference's gradients on B200 (tests/test_train_step_gpu.py); this wrapper itself is
+    verified on the CPU with stand-in kernels only (tests/test_backward_composition_cpu.py) and therefore opt-in
+    (``model.native_backward`` / LTU_NATIVE_BACKWARD=1)."""
 
     @staticmethod
     def forward(ctx, model, x, *params):

@@ -1,11 +1,12 @@
-"""GPU: one training step's loss and gradients from the native backward (lintransunet_b200.backward.model_loss_and_gradients)
-against the gradients the unmodified reference produced on the same weights, input and labels
-(tests/golden/train_c2_64x64x16.npz, tools/make_golden_train.py).
+"""GPU: one training step's loss and gradients from the native backward (lintransunet_b200.backward.model_loss_and_gradients:
+encoder + ROIDecoder loop + deep-supervision loss, bf16 activations) against what the UNMODIFIED reference produced on the same
+weights, input and labels in fp32 (tests/golden/train_c2_64x64x16.npz, tools/make_golden_train.py).
 
-SKIPPED until its first GPU run: the decoder-loop composition was written after round 1's GPU budget was spent.  Expectation
-when enabled: loss terms within a few percent (bf16 forward); gradients are compared in the relative L2 norm with a loose bound,
-because against an exact fp32 reference a bf16 forward flips the LeakyReLU sign of near-zero activations (5-12 % per layer, see
-tests/test_conv_bwd_gpu.py) and may move a ROI box by a pixel."""
+Measured on B200 (profiles/r1_train_step_gpu.log): the ten loss terms agree to 1e-3 (0.0762/0.8506 ... vs 0.0762/0.8504 ...), the worst
+relative deviation of a parameter-gradient norm (over the gradients above 1e-3 of the largest) is 4.6e-2.  The bounds below are wide on
+purpose: against an exact fp32 reference a bf16 forward flips the LeakyReLU sign of near-zero activations (5-12 % per layer in
+the max norm, see tests/test_conv_bwd_gpu.py) and may move a ROI box by a pixel; the kernels are bit-reproducible, so the
+measured values do not fluctuate."""
 import numpy as np
 import pytest
 import torch
@@ -13,12 +14,7 @@ import torch
 from oracle import ltu_oracle as O
 from tests.helpers import load_golden
 
-import os
-
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("LTU_RUN_TRAIN_STEP") != "1",
-                                 reason="decoder-loop composition not yet run on a GPU (round 1 budget spent); "
-                                        "LTU_RUN_TRAIN_STEP=1 runs it")]
+pytestmark = pytest.mark.gpu
 
 
 def test_train_step_gradients_against_the_reference():
