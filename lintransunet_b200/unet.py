@@ -567,12 +567,8 @@ class MaskTransUnet(nn.Module):
                 if self._compute_dtype() != torch.bfloat16:
                     raise NotImplementedError("the native backward exists on the bf16 path only: call the model inside "
                                               "torch.autocast (as the reference's train step does)")
-                B, _, H, W, D = x.shape
-                if H % 32 or W % 32 or D % 4:
-                    raise ValueError("H and W must be multiples of 32 and D a multiple of 4")
                 with torch.autocast("cuda", enabled=False):
-                    out = _NativeTrainFunction.apply(self, x.contiguous().float(), *[p for _, p in self.named_parameters()])
-                return out[0], list(out[1:])
+                    return self._forward_train(x)
         B, _, H, W, D = x.shape
         if H % 32 or W % 32 or D % 4:
             raise ValueError("H and W must be multiples of 32 and D a multiple of 4")
@@ -581,6 +577,15 @@ class MaskTransUnet(nn.Module):
             if not self.training and self.use_cuda_graphs:
                 out = out.clone()          # the graph's output buffer is reused by the next call
         return out
+
+    def _forward_train(self, x: torch.Tensor):
+        """Training-mode forward with autograd through the native backward: returns (probs, mask_list) like the
+        reference's train-mode forward (model/trans_3DUnet.py:181-195)."""
+        B, _, H, W, D = x.shape
+        if H % 32 or W % 32 or D % 4:
+            raise ValueError("H and W must be multiples of 32 and D a multiple of 4")
+        out = _NativeTrainFunction.apply(self, x.contiguous().float(), *[p for _, p in self.named_parameters()])
+        return out[0], list(out[1:])
 
     def _forward_impl(self, x: torch.Tensor, P: _Plan, head: str):
         n = len(self.num_layers)

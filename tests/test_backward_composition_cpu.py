@@ -306,3 +306,29 @@ def test_autograd_wiring_fills_parameter_gradients(standins):
             continue
         assert p.grad is not None and p.grad.dtype == p.dtype and p.grad.shape == p.shape, name
         assert float((p.grad.double() - r).norm()) <= 1e-5 * float(r.norm()) + 1e-7 * gmax, name
+
+
+def test_train_step_updates_parameters_like_an_oracle_step(standins, monkeypatch):
+    """lintransunet_b200.train.train_step (forward, loss, backward through the autograd wrapper, SGD step) moves every
+    parameter exactly as an SGD step on the oracle-autograd gradients."""
+    from lintransunet_b200 import MaskTransUnet, train
+    cfg = O.UnetConfig(dim_output=2)
+    sd = O.make_state_dict(cfg, seed=0)
+    model = MaskTransUnet(list(cfg.num_layers), list(cfg.roi_size_list), list(cfg.is_roi_list), 1, 2, dropout=0.0)
+    model.load_state_dict(sd)
+    monkeypatch.setattr(MaskTransUnet, "forward", lambda self, x: self._forward_train(x))      # skip the CUDA-only guard
+    x = O.make_input((1, 1, 64, 64, 16), seed=1, blob=True)
+    masks = torch.zeros(1, 1, 64, 64, 16, dtype=torch.long)
+    masks[:, :, 20:44, 16:40, 4:12] = 1
+    lr = 0.1
+    opt = torch.optim.SGD(model.parameters(), lr=lr)
+    total, terms = train.train_step(model, opt, x, masks)
+    sdd = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.mask_trans_unet_forward(x.double(), sdd, cfg)
+    total_ref, _ = T.train_loss(ref["probs"], ref["mask_list"], masks)
+    total_ref.backward()
+    assert abs(total - float(total_ref.detach())) <= 1e-6 * abs(float(total_ref.detach())) and len(terms) == 5
+    for name, p in model.named_parameters():
+        want = sd[name].double() - (lr * sdd[name].grad if sdd[name].grad is not None else 0)
+        assert torch.allclose(p.detach().double(), want, rtol=0, atol=1e-6 * float(want.abs().max()) + 1e-9), name
+        assert p.grad is None or float(p.grad.abs().max()) == 0.0                 # zero_grad after the step
