@@ -224,6 +224,27 @@ class StandIns:
         return vjp(lambda x: StandIns._resample(x, box, full_hw, roi_h, roi_w, eval_h, eval_w, direction), [x0], dy)[0]
 
 
+def _case():
+    cfg = O.UnetConfig(dim_output=2)
+    sd = O.make_state_dict(cfg, seed=0)
+    x = O.make_input((1, 1, 64, 64, 16), seed=1, blob=True)
+    masks = torch.zeros(1, 1, 64, 64, 16, dtype=torch.long)
+    masks[:, :, 20:44, 16:40, 4:12] = 1
+    return cfg, sd, x, masks
+
+
+@pytest.fixture(scope="module")
+def oracle_step():
+    """fp64 autograd through the oracle model and the oracle loss, computed once for the module."""
+    cfg, sd, x, masks = _case()
+    sdd = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    out = O.mask_trans_unet_forward(x.double(), sdd, cfg)
+    total, terms = T.train_loss(out["probs"], out["mask_list"], masks)
+    total.backward()
+    return dict(total=float(total.detach()), terms=[[float(v.detach()) for v in row] for row in terms],
+                grads={k: v.grad for k, v in sdd.items()})
+
+
 @pytest.fixture()
 def standins(monkeypatch):
     from lintransunet_b200 import backward, ops
@@ -234,31 +255,23 @@ def standins(monkeypatch):
     return backward
 
 
-def test_whole_model_gradient_composition_matches_oracle_autograd(standins):
+def test_whole_model_gradient_composition_matches_oracle_autograd(standins, oracle_step):
     from lintransunet_b200 import MaskTransUnet
-    cfg = O.UnetConfig(dim_output=2)
-    sd = O.make_state_dict(cfg, seed=0)
+    cfg, sd, x, masks = _case()
     model = MaskTransUnet(list(cfg.num_layers), list(cfg.roi_size_list), list(cfg.is_roi_list), 1, 2, dropout=0.0)
     model.load_state_dict(sd)
-    x = O.make_input((1, 1, 64, 64, 16), seed=1, blob=True)
-    masks = torch.zeros(1, 1, 64, 64, 16, dtype=torch.long)
-    masks[:, :, 20:44, 16:40, 4:12] = 1
-    # reference: fp64 autograd through the oracle model and the oracle loss
-    sdd = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
-    out = O.mask_trans_unet_forward(x.double(), sdd, cfg)
-    total_ref, terms_ref = T.train_loss(out["probs"], out["mask_list"], masks)
-    total_ref.backward()
     total, terms, grads = standins.model_loss_and_gradients(model, x, masks)
-    assert abs(float(total) - float(total_ref.detach())) <= 1e-6 * abs(float(total_ref.detach()))
-    for row, row_ref in zip(terms, terms_ref):
+    assert abs(float(total) - oracle_step["total"]) <= 1e-6 * abs(oracle_step["total"])
+    for row, row_ref in zip(terms, oracle_step["terms"]):
         for a, b in zip(row, row_ref):
-            assert abs(float(a.detach()) - float(b.detach())) <= 1e-6 * max(1.0, abs(float(b.detach())))
-    live = sorted(k for k, v in sdd.items() if v.grad is not None)
+            assert abs(float(a.detach()) - b) <= 1e-6 * max(1.0, abs(b))
+    ref_grads = oracle_step["grads"]
+    live = sorted(k for k, v in ref_grads.items() if v is not None)
     assert sorted(grads) == live                               # same 600 parameters, same names
-    gmax = max(float(sdd[k].grad.norm()) for k in live)
+    gmax = max(float(ref_grads[k].norm()) for k in live)
     worst, worst_name = 0.0, ""
     for k in live:
-        ref = sdd[k].grad
+        ref = ref_grads[k]
         assert grads[k].shape == ref.shape, k
         err = float((grads[k].double() - ref).norm())
         if k.endswith(".bias"):
@@ -276,31 +289,24 @@ def test_whole_model_gradient_composition_matches_oracle_autograd(standins):
     assert worst <= 1e-6                                       # parameter gradients are returned in fp32
 
 
-def test_autograd_wiring_fills_parameter_gradients(standins):
+def test_autograd_wiring_fills_parameter_gradients(standins, oracle_step):
     """loss.backward() through lintransunet_b200.unet._NativeTrainFunction (what MaskTransUnet.forward returns in training
     mode with model.native_backward) gives every live parameter the oracle-autograd gradient and leaves the dead ones None."""
     from lintransunet_b200 import MaskTransUnet, losses
     from lintransunet_b200.unet import _NativeTrainFunction
-    cfg = O.UnetConfig(dim_output=2)
-    sd = O.make_state_dict(cfg, seed=0)
+    cfg, sd, x, masks = _case()
     model = MaskTransUnet(list(cfg.num_layers), list(cfg.roi_size_list), list(cfg.is_roi_list), 1, 2, dropout=0.0)
     model.load_state_dict(sd)
     model.train()
-    x = O.make_input((1, 1, 64, 64, 16), seed=1, blob=True)
-    masks = torch.zeros(1, 1, 64, 64, 16, dtype=torch.long)
-    masks[:, :, 20:44, 16:40, 4:12] = 1
     out = _NativeTrainFunction.apply(model, x, *[p for _, p in model.named_parameters()])
     probs, mask_list = out[0], list(out[1:])
     assert probs.requires_grad and len(mask_list) == 4
     total, _ = losses.deep_supervision_loss(probs, mask_list, masks)
     total.backward()
-    sdd = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
-    ref = O.mask_trans_unet_forward(x.double(), sdd, cfg)
-    total_ref, _ = T.train_loss(ref["probs"], ref["mask_list"], masks)
-    total_ref.backward()
-    gmax = max(float(v.grad.norm()) for v in sdd.values() if v.grad is not None)
+    ref_grads = oracle_step["grads"]
+    gmax = max(float(v.norm()) for v in ref_grads.values() if v is not None)
     for name, p in model.named_parameters():
-        r = sdd[name].grad
+        r = ref_grads[name]
         if r is None:
             assert p.grad is None, name
             continue
@@ -308,27 +314,20 @@ def test_autograd_wiring_fills_parameter_gradients(standins):
         assert float((p.grad.double() - r).norm()) <= 1e-5 * float(r.norm()) + 1e-7 * gmax, name
 
 
-def test_train_step_updates_parameters_like_an_oracle_step(standins, monkeypatch):
+def test_train_step_updates_parameters_like_an_oracle_step(standins, oracle_step, monkeypatch):
     """lintransunet_b200.train.train_step (forward, loss, backward through the autograd wrapper, SGD step) moves every
     parameter exactly as an SGD step on the oracle-autograd gradients."""
     from lintransunet_b200 import MaskTransUnet, train
-    cfg = O.UnetConfig(dim_output=2)
-    sd = O.make_state_dict(cfg, seed=0)
+    cfg, sd, x, masks = _case()
     model = MaskTransUnet(list(cfg.num_layers), list(cfg.roi_size_list), list(cfg.is_roi_list), 1, 2, dropout=0.0)
     model.load_state_dict(sd)
     monkeypatch.setattr(MaskTransUnet, "forward", lambda self, x: self._forward_train(x))      # skip the CUDA-only guard
-    x = O.make_input((1, 1, 64, 64, 16), seed=1, blob=True)
-    masks = torch.zeros(1, 1, 64, 64, 16, dtype=torch.long)
-    masks[:, :, 20:44, 16:40, 4:12] = 1
     lr = 0.1
     opt = torch.optim.SGD(model.parameters(), lr=lr)
     total, terms = train.train_step(model, opt, x, masks)
-    sdd = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
-    ref = O.mask_trans_unet_forward(x.double(), sdd, cfg)
-    total_ref, _ = T.train_loss(ref["probs"], ref["mask_list"], masks)
-    total_ref.backward()
-    assert abs(total - float(total_ref.detach())) <= 1e-6 * abs(float(total_ref.detach())) and len(terms) == 5
+    assert abs(total - oracle_step["total"]) <= 1e-6 * abs(oracle_step["total"]) and len(terms) == 5
     for name, p in model.named_parameters():
-        want = sd[name].double() - (lr * sdd[name].grad if sdd[name].grad is not None else 0)
+        g = oracle_step["grads"][name]
+        want = sd[name].double() - (lr * g if g is not None else 0)
         assert torch.allclose(p.detach().double(), want, rtol=0, atol=1e-6 * float(want.abs().max()) + 1e-9), name
         assert p.grad is None or float(p.grad.abs().max()) == 0.0                 # zero_grad after the step
