@@ -8,15 +8,23 @@ linear-attn HBM GB/s vs peak".
 A step is one sliding-window inference of the multi-class MaskTransUnet (dim_output=3, random
 init, bf16) over a synthetic 512x512x256 CT volume: 128^3 windows, 50 % overlap => 147 windows,
 sw_batch_size 8 (BASELINE config 5, which runs the config-4 forward -- batch 8 of 128^3 patches --
-19 times).  Windows are dealt round-robin to the N ranks (one process per GPU, torchrun); the only
-collective is one NCCL all-reduce of the uint8 vote volume.  Total work is fixed => strong scaling.
+19 times, in batches of 8 and 7).  Windows are dealt round-robin to the N ranks (one process per GPU,
+torchrun); the only exchange is a reduce-scatter of the uint8 vote volume by H-slab followed by an
+all-gather of the uint8 label slabs (NCCL).  Total work is fixed => strong scaling.
 
   value : window voxels / s = 147 * 128^3 * K / t, volume resident in HBM, CUDA events, max over ranks
   e2e   : same, through lintransunet_b200.sliding_window.sliding_window_inference with the volume in
-          pinned host memory (H2D inside the timed region) and the stitched label volume read back
+          pinned host memory (H2D inside the timed region) and every rank's slab of the stitched label
+          volume read back to its host (D2H inside the timed region)
   roofline / kernels : per-kernel CUDA-event timings of the timed steps vs MEASURED_PEAKS.json
+          (the dominant kernel by time; tensor-bound kernels report algorithmic AND executed TFLOP/s)
+  parity : UNTIMED, after the timed region: two windows of the volume through the timed model against
+          the oracle (fp32 and its own bf16-autocast floor); at N > 1 the sharded label volume must
+          equal rank 0's single-rank result bit for bit; labels_crc32 is the same number at every N
   cpu_baseline : the oracle (CPU port of the reference algorithm) on the box's host cores, 8 of the
           147 windows after one warm-up window (N=1 only, about 10 s)
+  gpu_eager_baseline : the same oracle port in eager PyTorch on the same B200 (bf16 autocast and
+          fp32, batch 8 x 128^3) -- the kernel-vs-library bar of SURVEY 8d (N=1 only)
 
 The reference arm times the same oracle port (the reference is pure Python/PyTorch and cannot
 travel to the GPU box; oracle/ltu_oracle.py is pinned to it by tests/golden) on all host threads.
@@ -147,7 +155,67 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- our arm
+def gpu_eager_baseline(dev, steps=5, warmup=2):
+    """The survey's real bar: the reference ALGORITHM in eager PyTorch on the same B200 -- the oracle
+    port (device-agnostic torch, pinned to the unmodified reference by tests/golden), one batch of 8 x 128^3 windows
+    per step, under bf16 autocast (what the reference scripts do) and in true fp32.  CUDA events, same clocks.
+    Checker-side code: it is timed as a BASELINE, never shipped."""
+    from oracle import ltu_oracle as O
+    cfg = O.UnetConfig(dim_output=DIM_OUTPUT)
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(cfg, seed=0).items()}
+    x = O.make_input((SW_BATCH, 1) + ROI, seed=1).to(dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = {}
+    for name, ac in (("bf16_autocast", True), ("fp32", False)):
+        ts = []
+        with torch.no_grad():
+            for i in range(warmup + steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                    O.mask_trans_unet_forward(x, sd, cfg)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= warmup:
+                    ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        out[name] = {"ms_per_batch_of_8": round(ms, 3), "voxels_per_s": SW_BATCH * 128 ** 3 / (ms / 1e3)}
+    out["what"] = ("oracle port of the reference forward in eager PyTorch (cuDNN / cuBLAS / ATen kernels) on the same "
+                   "B200, batch 8 x 128^3, 3 classes, median of %d after %d warm-ups; includes the reference's 18 host "
+                   "syncs per sample" % (steps, warmup))
+    return out
+
+
+def parity_check(model, vol_dev, dev, n_windows=2):
+    """Untimed: the first `n_windows` windows of the benchmark volume through the model that was just timed, against the
+    oracle (fp32 and bf16-autocast, on the GPU) -- so the timed configuration itself is parity-checked."""
+    from oracle import ltu_oracle as O
+    from lintransunet_b200.sliding_window import scan_plan
+    _, _, roi, starts = scan_plan(VOLUME, ROI, OVERLAP)
+    wins = torch.stack([vol_dev[0, :, h:h + roi[0], w:w + roi[1], d:d + roi[2]] for h, w, d in starts[:n_windows]], 0).contiguous()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    cfg = O.UnetConfig(dim_output=DIM_OUTPUT)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        ref32 = O.mask_trans_unet_forward(wins, sd, cfg)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ref16 = O.mask_trans_unet_forward(wins, sd, cfg)
+            logits = model.forward_logits(wins).permute(0, 4, 1, 2, 3).float()
+            labels = model.predict_labels(wins).clone()
+    scale = ref32["logits"].abs().max()
+    lab_ref = ref32["onehot"].argmax(1)
+    return {"windows_checked": n_windows, "checker": "oracle/ltu_oracle.py on the GPU (fp32, TF32 off; bf16 autocast for the floor)",
+            "logits_rel_err_vs_fp32": float((logits - ref32["logits"]).abs().max() / scale),
+            "reference_bf16_floor": float((ref16["logits"].float() - ref32["logits"]).abs().max() / scale),
+            "label_flips_vs_fp32": float((labels.long() != lab_ref).float().mean()),
+            "reference_bf16_label_flips": float((ref16["onehot"].argmax(1) != lab_ref).float().mean())}
+
+
 def run_ours(args):
+    import zlib
     import torch.distributed as dist
     from lintransunet_b200 import MaskTransUnet, _native, ops
     from lintransunet_b200.sliding_window import sliding_window_inference
@@ -172,9 +240,11 @@ def run_ours(args):
     n_windows = 147
     win_vox = n_windows * ROI[0] * ROI[1] * ROI[2]
 
-    def step(x):
+    def step(x, **kw):
+        # labels only: the stitched argmax volume (uint8).  Under torch.distributed the exchange is a reduce-scatter of
+        # the uint8 votes by H-slab, argmax on the owned slab, all-gather of the label slabs (every rank gets the result)
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            return sliding_window_inference(x, ROI, SW_BATCH, model, overlap=OVERLAP, return_labels=True)
+            return sliding_window_inference(x, ROI, SW_BATCH, model, overlap=OVERLAP, labels_only=True, **kw)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -201,7 +271,7 @@ def run_ours(args):
     sync_all()
     e0.record()
     for _ in range(args.steps):
-        step(vol_dev)
+        labels_timed = step(vol_dev)
     e1.record()
     sync_all()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -209,6 +279,23 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     ms_step = ms_total / args.steps
+
+    # ---- untimed checks of what was just timed ------------------------------------------------
+    # (1) N > 1: the sharded result must equal the single-rank result bit for bit (rank 0 stitches the whole volume
+    #     alone); the CRC of the label volume is the same number at every N
+    labels_crc = zlib.crc32(labels_timed.cpu().numpy().tobytes()) if rank == 0 else 0
+    sharded_ok = None
+    if world > 1:
+        same = 1
+        if rank == 0:
+            single = step(vol_dev, distributed=False)
+            same = int(torch.equal(single, labels_timed))
+        f = torch.tensor([same], device=dev)
+        dist.broadcast(f, 0)
+        sharded_ok = bool(f.item())
+    # (2) two windows of the volume against the oracle
+    parity = parity_check(model, vol_dev, dev) if rank == 0 else None
+    sync_all()
 
     # ---- per-kernel device times: the timed steps replay CUDA graphs (no place for events between
     # kernels), so the same kernels are timed in one extra EAGER step bracketed by CUDA events
@@ -241,16 +328,17 @@ def run_ours(args):
     ms_prof_step = ep0.elapsed_time(ep1)
 
     # ---- timed region 2: end to end through the public API with host buffers ----------------
-    out_host = torch.empty(VOLUME, dtype=torch.uint8).pin_memory()
+    rows = VOLUME[0] // world if VOLUME[0] % world == 0 else VOLUME[0]
+    out_host = torch.empty((rows,) + VOLUME[1:], dtype=torch.uint8).pin_memory()
     sync_all()
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        # the public API takes the pinned HOST volume: it streams the rows this rank's windows touch to the device on a
-        # copy stream (H2D inside the timed region, overlapped with the first windows)
-        _, labels = step(vol_host)
-        if rank == 0:
-            out_host.copy_(labels[0], non_blocking=True)               # D2H of the step's result
+        # the public API takes the pinned HOST volume (H2D inside the timed region: streamed under the first windows at
+        # 1-2 ranks, one disjoint slab per rank + NVLink all-gather at >= 4 ranks); every rank reads its own slab of the
+        # stitched label volume back to its host buffer (D2H inside the timed region)
+        slab, off = step(vol_host, gather_labels=False)
+        out_host[:slab.shape[1]].copy_(slab[0], non_blocking=True)
         torch.cuda.current_stream().synchronize()
     e1.record()
     sync_all()
@@ -258,16 +346,38 @@ def run_ours(args):
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)) / args.steps
     from lintransunet_b200 import sliding_window as _sw
     h2d = _sw.last_h2d_bytes                                           # bytes this rank uploaded per step
+    d2h = slab.numel()
     if world > 1:
-        ht = torch.tensor([h2d], dtype=torch.int64, device=dev)
+        ht = torch.tensor([h2d, d2h, launches], dtype=torch.int64, device=dev)
         dist.all_reduce(ht)
-        h2d = int(ht.item())
-    d2h = out_host.numel()
+        h2d, d2h, launches = (int(v) for v in ht.tolist())
 
+    # ---- the exchange alone (N > 1): 3 reduce-scatters of the uint8 class volumes + the label all-gather
+    nccl = None
     if world > 1:
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt)
-        launches = int(lt.item())
+        C = DIM_OUTPUT
+        votes = torch.zeros((C,) + VOLUME, dtype=torch.uint8, device=dev)
+        mine_v = torch.empty((C, VOLUME[0] // world) + VOLUME[1:], dtype=torch.uint8, device=dev)
+        lab = torch.empty((VOLUME[0] // world,) + VOLUME[1:], dtype=torch.uint8, device=dev)
+        full = torch.empty(VOLUME, dtype=torch.uint8, device=dev)
+
+        def exchange():
+            for c in range(C):
+                dist.reduce_scatter_tensor(mine_v[c], votes[c])
+            dist.all_gather_into_tensor(full, lab)
+        for _ in range(3):
+            exchange()
+        sync_all()
+        e0.record()
+        for _ in range(10):
+            exchange()
+        e1.record()
+        sync_all()
+        ms_x = max_over_ranks(e0.elapsed_time(e1)) / 10
+        moved = (votes.numel() + full.numel()) * (world - 1) / world       # bytes each rank sends (= receives)
+        nccl = {"exchange_ms": round(ms_x, 4), "bus_GB/s": round(moved / ms_x / 1e6, 1),
+                "what": "3 x reduce_scatter (uint8 votes, 67 MB per class) + all_gather (uint8 labels, 67 MB); "
+                        "bus bandwidth = bytes x (N-1)/N per rank / time", "share_of_step": round(ms_x / ms_step, 4)}
 
     if rank == 0:
         pk = peaks()
@@ -276,8 +386,10 @@ def run_ours(args):
             ms = d["ms"]
             gbs = d["bytes"] / d["ms"] / 1e6 if d["ms"] > 0 else 0.0
             tfs = d["flops"] / d["ms"] / 1e9 if d["ms"] > 0 else 0.0
+            tfx = d["flops_exec"] / d["ms"] / 1e9 if d["ms"] > 0 else 0.0
             kernels[name] = {"launches_per_step": d["launches"], "ms_per_step": round(ms, 3),
-                             "share_of_step": round(ms / ms_step, 4), "GB/s": round(gbs, 1), "TFLOP/s": round(tfs, 2)}
+                             "share_of_step": round(ms / ms_step, 4), "GB/s": round(gbs, 1), "TFLOP/s": round(tfs, 2),
+                             "TFLOP/s_executed": round(tfx, 2)}
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
@@ -287,37 +399,27 @@ def run_ours(args):
             d = ksum.get(name)
             if not d or d["ms"] <= 0:
                 return None
+            out = {"kernel": name, "bound": bound}
             if bound == "hbm":
-                a, p, u = d["bytes"] / d["ms"] / 1e6, pk["hbm"], "GB/s"
+                a, pkv, u = d["bytes"] / d["ms"] / 1e6, pk["hbm"], "GB/s"
             else:
-                a, p, u = d["flops"] / d["ms"] / 1e9, pk["tensor"], "TFLOP/s"
-            return {"kernel": name, "bound": bound, "achieved": round(a, 2), "peak": p, "unit": u,
-                    "frac": round(a / p, 4), "traffic": (traffic or {}).get(name.split(" ")[0].replace("conv3d_tcgen05", "conv3d_tc")),
-                    "peak_source": pk["source"],
-                    "algorithmic": "kv_reduce/q_readout: 2*B*N*C*E bytes each (K,V read | Q read + out written); "
-                                   "ffn_fused/attn_out_fused: 2*rows*C*E bytes (x read once, y written once; their "
-                                   "TFLOP/s in `kernels` counts the GEMM flops they contain); "
-                                   "conv3d_tc: 2*27*Cin*Cout*B*Vout flop", "launches": d["launches"]}
+                a, pkv, u = d["flops"] / d["ms"] / 1e9, pk["tensor"], "TFLOP/s"
+                ax = d["flops_exec"] / d["ms"] / 1e9
+                out.update({"achieved_algorithmic": round(a, 2), "achieved_executed": round(ax, 2),
+                            "frac_executed": round(ax / pkv, 4)})
+            out.update({"achieved": round(a, 2), "peak": pkv, "unit": u, "frac": round(a / pkv, 4),
+                        "traffic": (traffic or {}).get(name), "peak_source": pk["source"],
+                        "algorithmic": ALGORITHMIC.get(name, "in + out bytes"), "launches": d["launches"],
+                        "avg_launch_us": round(d["ms"] / d["launches"] * 1e3, 2)})
+            return out
 
-        # the tcgen05 implicit-GEMM convolution family = conv3d_tc (im2col per tap) + conv3d_tc3 (TMA halo): one op,
-        # one flop definition; `kernels` lists them separately, the roofline is taken over the family
-        fam = {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0}
-        for n in ("conv3d_tc", "conv3d_tc3"):
-            if n in ksum:
-                for k in fam:
-                    fam[k] += ksum[n][k]
-        if fam["launches"]:
-            ksum = dict(ksum)
-            ksum["conv3d_tcgen05 (conv3d_tc + conv3d_tc3)"] = fam
-        dominant = max((kv for kv in ksum.items() if kv[0] not in ("conv3d_tc", "conv3d_tc3")),
-                       key=lambda kv: kv[1]["ms"])[0] if ksum else None
-        bound_of = {"conv3d_tc": "tensor", "conv3d_tc3": "tensor", "conv3d": "tensor",
-                    "conv3d_tcgen05 (conv3d_tc + conv3d_tc3)": "tensor"}
+        bound_of = {"conv3d_tc": "tensor", "conv3d_tc3": "tensor", "conv3d": "tensor", "conv3d_tc4": "tensor"}
+        dominant = max(ksum.items(), key=lambda kv: kv[1]["ms"])[0] if ksum else None
         roofline = roof(dominant, bound_of.get(dominant, "hbm")) if dominant else None
-        attn = {n: roof(n, "hbm") for n in ("kv_reduce", "q_readout")}
+        attn = {n: roof(n, "hbm") for n in ("kv_reduce", "q_readout") if n in ksum}
         # d_model=128 layers: the readout, both projections, the FFN and both LayerNorms run inside two fused kernels
-        fused = {n: roof(n, "hbm") for n in ("attn_out_fused", "ffn_fused")}
-        conv_detail = {n: roof(n, "tensor") for n in ("conv3d_tc", "conv3d_tc3") if n in ksum}
+        fused = {n: roof(n, "hbm") for n in ("attn_out_fused", "ffn_fused") if n in ksum}
+        conv_detail = {n: roof(n, bound_of.get(n, "hbm")) for n in ("conv3d_tc", "conv3d_tc3", "conv3d_tc4", "conv3d_halo") if n in ksum}
         line = {"metric": METRIC, "value": win_vox / (ms_step / 1e3), "unit": "voxels/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -326,8 +428,11 @@ def run_ours(args):
                 "clocks": sampler.result(),
                 "e2e": {"value": win_vox / (ms_e2e / 1e3), "unit": "voxels/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "lintransunet_b200.sliding_window.sliding_window_inference"},
-                "gpu_launches": launches, "roofline": roofline, "linear_attn_roofline": attn, "fused_layer_roofline": fused, "conv_roofline": conv_detail,
+                        "api": "lintransunet_b200.sliding_window.sliding_window_inference(pinned host volume, "
+                               "labels_only=True, gather_labels=False) + D2H of every rank's label slab"},
+                "gpu_launches": launches, "roofline": roofline, "linear_attn_roofline": attn, "fused_layer_roofline": fused,
+                "conv_roofline": conv_detail, "parity": parity,
+                "labels_crc32": labels_crc, "sharded_equals_single_rank": sharded_ok, "nccl": nccl,
                 "kernels": kernels,
                 "kernel_timing": {"how": "one extra eager step with CUDA events around every native launch (the timed "
                                          "steps replay CUDA graphs of the same kernels); each forward starts with a "
@@ -343,10 +448,23 @@ def run_ours(args):
                                     "sample": f"{len(times)} of the step's 147 windows (1x1x128^3 forwards, fp32, mean after one "
                                               "warm-up window); oracle port of the reference on the host cores",
                                     "seconds_per_window": round(t_win, 4)}
+            line["gpu_eager_baseline"] = gpu_eager_baseline(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+ALGORITHMIC = {
+    "kv_reduce": "2*B*N*C*E bytes (K and V read once)",
+    "q_readout": "2*B*N*C*E bytes (Q read, out written)",
+    "attn_out_fused": "2*rows*C*E bytes (x read once, y written once)",
+    "ffn_fused": "2*rows*C*E bytes (x read once, y written once)",
+    "conv3d_tc": "2*27*Cin*Cout*B*Vout flop (un-folded; `executed` counts 8/27 of it for the folded up_embed layers)",
+    "conv3d_tc3": "2*27*Cin*Cout*B*Vout flop (un-folded; `executed` counts 8/27 of it for the folded up_embed layer)",
+    "conv3d_tc4": "2*27*Cin*Cout*B*Vout flop",
+    "conv3d_halo": "(B*Cin*Vin + B*Cout*Vout)*E bytes",
+}
 
 
 def main():

@@ -60,12 +60,23 @@ int ltu_q_readout(const void* q, int64_t ld_q, const float* ctx, void* out, int6
 int ltu_add_layernorm(const void* x, const void* res, const float* gamma, const float* beta,
                       void* y, int64_t rows, int C, float eps, int dtype, ltu_stream_t stream);
 int ltu_gelu(void* x, int64_t n, int dtype, ltu_stream_t stream);
+/* bf16 path, split token stream: the residual stream between encoder layers is carried as two bf16 tensors
+ * hi = bf16(y), lo = bf16(y - hi).  The Linear layers read `hi` (the bf16 cast autocast applies to a Linear's
+ * input, trans_block.py:155-157,:208) while the residual adds of :205,:209 see hi + lo, i.e. ~16 significant bits:
+ * the reference keeps that stream in fp32 under autocast (layer_norm autocasts to fp32).  x_lo may be null. */
+int ltu_add_layernorm_split(const void* x_hi, const void* x_lo, const void* res, const float* gamma,
+                            const float* beta, void* y_hi, void* y_lo, int64_t rows, int C, float eps,
+                            ltu_stream_t stream);
 
 /* ---- a4: Conv3dPosEmbedding, model/trans_block.py:86-96 -----------------------------------
  * y = x + bias + depthwise3x3x3(x), zero pad 1, channels-last; w is fp32 [27][C] with the tap
  * index kh*9+kw*3+kd in the NATIVE (H,W,D) axes (w'[c,kh,kw,kd] = w_ref[c,0,kd,kh,kw]).       */
 int ltu_posenc_dwconv3(const void* x, const float* w27c, const float* bias, void* y, int B, int H,
                        int W, int D, int C, int dtype, ltu_stream_t stream);
+/* the same on the split bf16 token stream: the 27 taps read x_hi (a conv's input is cast to bf16 under autocast),
+ * the residual term is x_hi + x_lo (x_lo may be null), the result is stored as y_hi, y_lo. */
+int ltu_posenc_dwconv3_split(const void* x_hi, const void* x_lo, const float* w27c, const float* bias,
+                             void* y_hi, void* y_lo, int B, int H, int W, int D, int C, ltu_stream_t stream);
 
 /* ---- a10-a14: nn.Conv3d (+ InstanceNorm3d statistics), model/Unet_3Dblock.py:310-316,
  * :375,:422,:523-531,:588,:1328,:1353, gates :200-214 ---------------------------------------

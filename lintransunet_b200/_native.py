@@ -28,8 +28,10 @@ SIGNATURES = {
     "ltu_kv_reduce": (I, [P, P, L, P, P, Z, I, L, I, I, P]),
     "ltu_q_readout": (I, [P, L, P, P, L, I, L, I, I, P]),
     "ltu_add_layernorm": (I, [P, P, P, P, P, L, I, F, I, P]),
+    "ltu_add_layernorm_split": (I, [P, P, P, P, P, P, P, L, I, F, P]),
     "ltu_gelu": (I, [P, L, I, P]),
     "ltu_posenc_dwconv3": (I, [P, P, P, P, I, I, I, I, I, I, P]),
+    "ltu_posenc_dwconv3_split": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "ltu_conv3d_tiles": (I, [L, I]),
     "ltu_conv3d": (I, [P, I, P, I, I, I, I, I, I, I, I, I, I, I, P, P, I, P, I, I, I, I, P, I, P]),
     "ltu_conv3d_tc_supported": (I, [I, I, I, I, I]),

@@ -252,10 +252,24 @@ q_readout_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restrict__
 }
 
 // ---------------------------------------------------------------- add + LayerNorm
+// Split-bf16 token stream (bf16 path): the residual stream between encoder layers is kept as hi + lo, two bf16 words
+// (hi = bf16(y), lo = bf16(y - hi)): the GEMMs read `hi` only -- exactly the bf16 cast autocast applies to a Linear's
+// input -- while the residual add sees 16 significant bits, like the reference, whose LayerNorm output stays fp32 under
+// autocast.  `xlo` / `ylo` may be null (plain bf16 stream).
+template <typename T> __device__ __forceinline__ void split_store4(T* yhi, T* ylo, const float (&o)[4]) { store4(yhi, o); }
+template <> __device__ __forceinline__ void split_store4<bf16>(bf16* yhi, bf16* ylo, const float (&o)[4]) {
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i] = __bfloat162float(__float2bfloat16_rn(o[i])); l[i] = o[i] - h[i]; }
+    store4(yhi, h);
+    if (ylo) store4(ylo, l);
+}
+
 template <typename T, int C>
 __global__ void __launch_bounds__(256)
-add_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, T* __restrict__ y, int64_t rows, float eps) {
+add_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ xlo, const T* __restrict__ r,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
+                     T* __restrict__ ylo, int64_t rows, float eps) {
     constexpr int Q = C / 128;   // 4-element chunks per lane
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -274,6 +288,12 @@ add_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ r, const flo
             float a[4], bb[4];
             load4(x + row * C + q * 128 + lane * 4, a);
             load4(r + row * C + q * 128 + lane * 4, bb);
+            if (xlo) {
+                float lo[4];
+                load4(xlo + row * C + q * 128 + lane * 4, lo);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] += lo[i];
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) { v[q][i] = a[i] + bb[i]; sum += v[q][i]; }
         }
@@ -289,7 +309,7 @@ add_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ r, const flo
             float o[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = (v[q][i] - mean) * rstd * g[q][i] + bt[q][i];
-            store4(y + row * C + q * 128 + lane * 4, o);
+            split_store4<T>(y + row * C + q * 128 + lane * 4, ylo ? ylo + row * C + q * 128 + lane * 4 : nullptr, o);
         }
     }
 }
@@ -553,25 +573,38 @@ extern "C" int ltu_q_readout(const void* q, int64_t ldq, const float* ctx, void*
     return q_readout_impl<bf16>(q, ldq, ctx, out, ldo, B, N, heads, (cudaStream_t)stream);
 }
 
-extern "C" int ltu_add_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* y,
-                                 int64_t rows, int C, float eps, int dtype, ltu_stream_t stream) {
+static int add_layernorm_impl(const void* x, const void* xlo, const void* res, const float* gamma, const float* beta,
+                              void* y, void* ylo, int64_t rows, int C, float eps, int dtype, ltu_stream_t stream) {
     LTU_ARG_CHECK(x && res && gamma && beta && y, "add_layernorm: null pointer");
     LTU_ARG_CHECK(rows > 0, "add_layernorm: rows=%lld", (long long)rows);
     LTU_ARG_CHECK(C == 128 || C == 256, "add_layernorm: C must be 128 or 256 (got %d)", C);
     LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "add_layernorm: bad dtype %d", dtype);
-    LTU_ARG_CHECK(aligned16(x) && aligned16(res) && aligned16(y) && aligned16(gamma) && aligned16(beta),
-                  "add_layernorm: pointers must be 16-byte aligned");
+    LTU_ARG_CHECK(dtype == LTU_BF16 || (!xlo && !ylo), "add_layernorm: the split stream exists for bf16 only");
+    LTU_ARG_CHECK(aligned16(x) && aligned16(res) && aligned16(y) && aligned16(gamma) && aligned16(beta) &&
+                  aligned16(xlo) && aligned16(ylo), "add_layernorm: pointers must be 16-byte aligned");
     int64_t blocks = ceil_div64(rows, 8);
     int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
-#define LN_LAUNCH(T, CC) add_layernorm_kernel<T, CC><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, (const T*)res, gamma, beta, (T*)y, rows, eps)
+#define LN_LAUNCH(T, CC) add_layernorm_kernel<T, CC><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, (const T*)xlo, (const T*)res, gamma, beta, (T*)y, (T*)ylo, rows, eps)
     if (dtype == LTU_F32) { if (C == 128) LN_LAUNCH(float, 128); else LN_LAUNCH(float, 256); }
     else                  { if (C == 128) LN_LAUNCH(bf16, 128);  else LN_LAUNCH(bf16, 256); }
 #undef LN_LAUNCH
     LTU_LAUNCH_CHECK("add_layernorm");
     count_launch(1);
     return LTU_OK;
+}
+
+extern "C" int ltu_add_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* y,
+                                 int64_t rows, int C, float eps, int dtype, ltu_stream_t stream) {
+    return add_layernorm_impl(x, nullptr, res, gamma, beta, y, nullptr, rows, C, eps, dtype, stream);
+}
+
+extern "C" int ltu_add_layernorm_split(const void* x_hi, const void* x_lo, const void* res, const float* gamma,
+                                       const float* beta, void* y_hi, void* y_lo, int64_t rows, int C, float eps,
+                                       ltu_stream_t stream) {
+    LTU_ARG_CHECK(y_lo, "add_layernorm_split: y_lo is null");
+    return add_layernorm_impl(x_hi, x_lo, res, gamma, beta, y_hi, y_lo, rows, C, eps, LTU_BF16, stream);
 }
 
 extern "C" int ltu_gelu(void* x, int64_t n, int dtype, ltu_stream_t stream) {
@@ -595,8 +628,9 @@ extern "C" int ltu_gelu(void* x, int64_t n, int dtype, ltu_stream_t stream) {
 // output costs 13.5 data + 13.5 weight loads per 8 channels instead of 54 + 54 (the plain kernel is LSU-issue
 // bound: 219 us on [8,39,23,64,128]); the residual term reuses the centre planes.
 __global__ void __launch_bounds__(256)
-posenc_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                   bf16* __restrict__ y, int B, int H, int W, int D, int C) {
+posenc_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ xlo, const float* __restrict__ w,
+                   const float* __restrict__ bias, bf16* __restrict__ y, bf16* __restrict__ ylo, int B, int H, int W,
+                   int D, int C) {
     const int c8n = C >> 3;
     const int dgn = (D + 3) >> 2;
     const int64_t total = (int64_t)B * H * W * dgn * c8n;
@@ -665,34 +699,51 @@ posenc_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ w, cons
                 }
             }
         }
-        bf16* out = y + ((((int64_t)b * H + h) * W + ww) * D + d0) * C + c0;
+        const int64_t off = ((((int64_t)b * H + h) * W + ww) * D + d0) * C + c0;
+        if (xlo) {                                  // split stream: the residual term is hi + lo, the taps read hi
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (d0 + o < D) {
+                    float l8[8];
+                    load_vec(xlo + off + (int64_t)o * C, l8);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[o][i] += l8[i];
+                }
+        }
 #pragma unroll
         for (int o = 0; o < 4; ++o)
-            if (d0 + o < D) store_vec(out + (int64_t)o * C, acc[o]);
+            if (d0 + o < D) {
+                if (ylo) {
+                    float h8[8], l8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { h8[i] = __bfloat162float(__float2bfloat16_rn(acc[o][i])); l8[i] = acc[o][i] - h8[i]; }
+                    store_vec(y + off + (int64_t)o * C, h8);
+                    store_vec(ylo + off + (int64_t)o * C, l8);
+                } else {
+                    store_vec(y + off + (int64_t)o * C, acc[o]);
+                }
+            }
     }
 }
 
-extern "C" int ltu_posenc_dwconv3(const void* x, const float* w, const float* bias, void* y, int B, int H, int W,
-                                  int D, int C, int dtype, ltu_stream_t stream) {
+static int posenc_impl(const void* x, const void* xlo, const float* w, const float* bias, void* y, void* ylo, int B,
+                       int H, int W, int D, int C, int dtype, ltu_stream_t stream) {
     LTU_ARG_CHECK(x && w && bias && y, "posenc_dwconv3: null pointer");
     LTU_ARG_CHECK(B > 0 && H > 0 && W > 0 && D > 0 && C > 0 && C % 4 == 0, "posenc_dwconv3: bad shape");
     LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "posenc_dwconv3: bad dtype %d", dtype);
     LTU_ARG_CHECK(x != y, "posenc_dwconv3: in-place is not supported");
+    const bool vec_ok = dtype == LTU_BF16 && C % 8 == 0 &&
+                        (((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)bias | (uintptr_t)xlo | (uintptr_t)ylo) & 15) == 0;
+    LTU_ARG_CHECK(vec_ok || (!xlo && !ylo), "posenc_dwconv3: the split stream needs bf16, C %% 8 == 0 and 16-byte aligned pointers");
     // posenc2_kernel (register-sliding along D) measured 2x SLOWER than the plain 27-tap kernel on B200
     // (404 vs 219 us on [8,39,23,64,128]: a serial chain of dependent loads per thread at 114 registers);
     // kept for reference, not dispatched.
-    if (dtype == LTU_BF16 && C % 8 == 0 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)bias) & 15) == 0) {
+    if (vec_ok) {
         int64_t total = (int64_t)B * H * W * ((D + 3) / 4) * (C / 8);
         int64_t blocks = ceil_div64(total, 256);
         LTU_ARG_CHECK(blocks < ((int64_t)1 << 31), "posenc_dwconv3: tensor too large");
-        posenc_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, (bf16*)y, B, H, W, D, C);
-    } else if (false && D >= 8) {
-        constexpr int LD = 16;
-        int64_t total = (int64_t)B * H * W * ((D + LD - 1) / LD) * (C / 2);
-        int64_t blocks = ceil_div64(total, 256);
-        LTU_ARG_CHECK(blocks < ((int64_t)1 << 31), "posenc_dwconv3: tensor too large");
-        if (dtype == LTU_F32) posenc2_kernel<float, LD><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, w, bias, (float*)y, B, H, W, D, C);
-        else posenc2_kernel<bf16, LD><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, (bf16*)y, B, H, W, D, C);
+        posenc_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)xlo, w, bias, (bf16*)y,
+                                                                              (bf16*)ylo, B, H, W, D, C);
     } else {
         int64_t total = (int64_t)B * H * W * D * (C / 4);
         int64_t blocks = ceil_div64(total, 256);
@@ -704,4 +755,15 @@ extern "C" int ltu_posenc_dwconv3(const void* x, const float* w, const float* bi
     LTU_LAUNCH_CHECK("posenc_dwconv3");
     count_launch(1);
     return LTU_OK;
+}
+
+extern "C" int ltu_posenc_dwconv3(const void* x, const float* w, const float* bias, void* y, int B, int H, int W,
+                                  int D, int C, int dtype, ltu_stream_t stream) {
+    return posenc_impl(x, nullptr, w, bias, y, nullptr, B, H, W, D, C, dtype, stream);
+}
+
+extern "C" int ltu_posenc_dwconv3_split(const void* x_hi, const void* x_lo, const float* w, const float* bias, void* y_hi,
+                                        void* y_lo, int B, int H, int W, int D, int C, ltu_stream_t stream) {
+    LTU_ARG_CHECK(y_lo, "posenc_dwconv3_split: y_lo is null");
+    return posenc_impl(x_hi, x_lo, w, bias, y_hi, y_lo, B, H, W, D, C, LTU_BF16, stream);
 }

@@ -58,14 +58,17 @@ class KernelProfiler:
         self.records = []
 
     def summary(self):
-        """name -> dict(launches, ms, bytes, flops); call after torch.cuda.synchronize()."""
+        """name -> dict(launches, ms, bytes, flops, flops_exec); call after torch.cuda.synchronize().  `flops` is the
+        algorithmic count (un-folded), `flops_exec` what the kernel executes (8/27 of it for the folded
+        nearest-x2 + 3x3x3 convolutions)."""
         out = {}
-        for name, e0, e1, nbytes, flops in self.records:
-            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0, flops=0))
+        for name, e0, e1, nbytes, flops, fexec in self.records:
+            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0, flops=0, flops_exec=0))
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
             d["bytes"] += nbytes
             d["flops"] += flops
+            d["flops_exec"] += fexec
         return out
 
 
@@ -102,7 +105,8 @@ class _Guard:
         if self.prof is not None and _profiler is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _profiler.records.append((self.prof[0], self.e0, e1, self.prof[1], self.prof[2]))
+            _profiler.records.append((self.prof[0], self.e0, e1, self.prof[1], self.prof[2],
+                                      self.prof[3] if len(self.prof) > 3 else self.prof[2]))
         if self.prev is not None:
             torch.cuda.set_device(self.prev)
         return False
@@ -184,6 +188,23 @@ def add_layernorm(x: torch.Tensor, res: torch.Tensor, gamma: torch.Tensor, beta:
     return y
 
 
+def add_layernorm_split(x_hi: torch.Tensor, x_lo: Optional[torch.Tensor], res: torch.Tensor, gamma: torch.Tensor,
+                        beta: torch.Tensor, eps: float = 1e-6):
+    """LayerNorm(x_hi + x_lo + res) -> (y_hi, y_lo), all bf16: the split token stream of the bf16 path (the Linear
+    layers read y_hi, the next residual add reads y_hi + y_lo; include/ltu_b200.h)."""
+    dev = _chk(x_hi, x_lo, res, gamma, beta)
+    if x_hi.dtype != torch.bfloat16:
+        raise TypeError("add_layernorm_split: bf16 tokens only")
+    C = x_hi.shape[-1]
+    rows = x_hi.numel() // C
+    y_hi, y_lo = torch.empty_like(x_hi), torch.empty_like(x_hi)
+    n_units = 4 + (x_lo is not None)
+    with _Guard(dev, ("add_layernorm", n_units * x_hi.numel() * 2, 0)) as st:
+        check(_native.lib().ltu_add_layernorm_split(_p(x_hi), _p(x_lo), _p(res), _p(gamma), _p(beta), _p(y_hi), _p(y_lo),
+                                                    rows, C, eps, st), "ltu_add_layernorm_split")
+    return y_hi, y_lo
+
+
 def add_layernorm_bwd(x: torch.Tensor, res: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-6):
     """Backward of LayerNorm(x + res): returns (dz, dgamma, dbeta); dz is the gradient of x AND of res."""
     dev = _chk(x, res, dy, gamma)
@@ -232,6 +253,19 @@ def posenc_dwconv3(x: torch.Tensor, w27c: torch.Tensor, bias: torch.Tensor) -> t
         check(_native.lib().ltu_posenc_dwconv3(_p(x), _p(w27c), _p(bias), _p(y), B, H, W, D, C, _dt(x), st),
               "ltu_posenc_dwconv3")
     return y
+
+
+def posenc_dwconv3_split(x_hi: torch.Tensor, x_lo: Optional[torch.Tensor], w27c: torch.Tensor, bias: torch.Tensor):
+    """posenc_dwconv3 on the split bf16 token stream: (x_hi, x_lo) [B,H,W,D,C] -> (y_hi, y_lo)."""
+    dev = _chk(x_hi, x_lo, w27c, bias)
+    if x_hi.dtype != torch.bfloat16:
+        raise TypeError("posenc_dwconv3_split: bf16 tokens only")
+    B, H, W, D, C = x_hi.shape
+    y_hi, y_lo = torch.empty_like(x_hi), torch.empty_like(x_hi)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_posenc_dwconv3_split(_p(x_hi), _p(x_lo), _p(w27c), _p(bias), _p(y_hi), _p(y_lo),
+                                                     B, H, W, D, C, st), "ltu_posenc_dwconv3_split")
+    return y_hi, y_lo
 
 
 def posenc_dwconv3_bwd(x: torch.Tensor, dy: torch.Tensor, w27c: torch.Tensor):
@@ -302,8 +336,10 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     cin = C0 + C1
     nbytes = (x0.numel() + (0 if x1 is None else x1.numel())) * x0.element_size() + out.numel() * out.element_size()
     # algorithmic flops: the un-folded count 2*k^3*Cin*Cout*B*V (the folded up2 path executes 8/27 of it)
+    flops = 2 * ksize ** 3 * cin * cout * B * V
+    folded = up2 and (use_tc or use_tc3)
     prof = ("conv3d_halo" if use_halo else ("conv3d_tc3" if use_tc3 else ("conv3d_tc" if use_tc else "conv3d")), nbytes,
-            2 * ksize ** 3 * cin * cout * B * V)
+            flops, flops * 8 // 27 if folded else flops)
     with _Guard(dev, prof) as st:
         if use_halo:
             check(L.ltu_conv3d_halo(_p(x0), C0, _p(x1), C1, B, Hi, Wi, Di, ksize, _p(w_tc), w_tc.shape[1], _p(bias),

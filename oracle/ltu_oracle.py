@@ -1,4 +1,5 @@
-"""CPU oracle for the LinTransUNet ``MaskTransUnet`` forward hot path.
+"""Oracle for the LinTransUNet ``MaskTransUnet`` forward hot path (CPU; device-agnostic, so the GPU tests can also run it
+under ``torch.autocast`` on the box to measure the reference algorithm's own bf16 noise floor).
 
 TEST INFRASTRUCTURE ONLY.  This file is a from-scratch, functional restatement
 (plain PyTorch on the CPU, fp32 or fp64) of the reference algorithm.  It is the
@@ -309,6 +310,7 @@ def _quantile_indices(profile: Tensor) -> Tuple[float, float, float]:
     if tot == 0:
         mid = S / 2
         return mid - 1, mid + 1, mid
+    profile = profile.cpu()           # the reference does this arithmetic in fp32 on whatever device; indices are exact
     r = torch.cumsum(profile, 0).to(torch.float32) / torch.tensor(float(tot), dtype=torch.float32)
     lo_t = torch.tensor(0.001, dtype=torch.float32)
     hi_t = torch.tensor(1 - 0.001, dtype=torch.float32)
@@ -343,14 +345,14 @@ def roi_boxes(fg: Tensor, min_h: int, min_w: int, thr: float = 0.5) -> Tensor:
                 hi = torch.minimum(mid + (S - mn) / 2, f32(float(S)))
             box[b, i0], box[b, i1] = lo, hi
         box[b, 2], box[b, 5] = 0.0, float(D - 1)
-    return box
+    return box.to(fg.device)
 
 
 def fisheye_forward_coords(x0: Tensor, x1: Tensor, h: int, roi: int, eroi: int) -> Tensor:
     """get_transfer_index, Unet_3Dblock.py:51-64.  x0,x1: fp32 [B,1]; returns the
     normalised grid coordinate [B, eroi].  The two fix-ups are sequential and the second
     test sees the already-updated value."""
-    i = torch.arange(0, eroi, dtype=torch.float32)
+    i = torch.arange(0, eroi, dtype=torch.float32, device=x0.device)
     k2 = (x1 - x0) / (roi - 1)
     k1 = (h - x1 + x0) / (eroi - roi)
     t = i * k2 + x0 * (1 - k2 / k1)
@@ -363,7 +365,7 @@ def fisheye_forward_coords(x0: Tensor, x1: Tensor, h: int, roi: int, eroi: int) 
 
 def fisheye_back_coords(x0: Tensor, x1: Tensor, h: int, roi: int, eroi: int) -> Tensor:
     """get_transfer_back_index, Unet_3Dblock.py:66-82; normalises by /eroi (not eroi-1, :81)."""
-    p = torch.arange(0, h + 1, dtype=torch.float32)
+    p = torch.arange(0, h + 1, dtype=torch.float32, device=x0.device)
     k2 = roi / (x1 - x0)
     k1 = (eroi - roi) / (h - x1 + x0)
     p0 = x0 * k1
@@ -418,7 +420,8 @@ def roi_bridge(x: Tensor, fg: Tensor, sd: Dict[str, Tensor], cfg: UnetConfig, i:
     rc = cfg.roi_consts(i)
     cin, dm, nhead = cfg.bridge_dims(i)
     B, C, h, w, d = x.shape
-    box = roi_boxes(fg, rc["min_h"], rc["min_w"]) if forced_box is None else forced_box.to(torch.float32)
+    box = (roi_boxes(fg, rc["min_h"], rc["min_w"]) if forced_box is None
+           else forced_box.to(device=x.device, dtype=torch.float32))
     if taps is not None:
         taps[f"box{i}"] = box
     x0, y0, x1, y1 = box[:, 0:1], box[:, 1:2], box[:, 3:4], box[:, 4:5]
@@ -497,7 +500,7 @@ def mask_trans_unet_forward(x: Tensor, sd: Dict[str, Tensor], cfg: UnetConfig,
     Returns logits (the decode.final_block tap), probs, mask_list, onehot (eval output)
     and the ROI boxes / intermediate taps."""
     assert cfg.dim_input == 1, "windows_embedding requires a single input channel (Unet_3Dblock.py:132)"
-    sd = {k: v.to(x.dtype) for k, v in sd.items()}
+    sd = {k: v.to(device=x.device, dtype=x.dtype) for k, v in sd.items()}
     taps: Optional[Dict[str, Tensor]] = {} if want_taps else None
     box_taps: Dict[str, Tensor] = {} if taps is None else taps
     bottle, skips = encoder_forward(x, sd, cfg, taps)

@@ -26,6 +26,12 @@ def main():
         frac_d, lab_d = sliding_window_inference(vol, roi, 4, m, overlap=0.5, return_labels=True)              # sharded
         frac_s, lab_s = sliding_window_inference(vol, roi, 4, m, overlap=0.5, return_labels=True, distributed=False)
         same = torch.equal(frac_d, frac_s) and torch.equal(lab_d, lab_s)
+        # label-only exchange (reduce-scatter by H-slab + all-gather of the label slabs) and the per-rank slab
+        lab_o = sliding_window_inference(vol, roi, 4, m, overlap=0.5, labels_only=True)
+        slab, off = sliding_window_inference(vol, roi, 4, m, overlap=0.5, labels_only=True, gather_labels=False)
+        lab_h = sliding_window_inference(vol.cpu().pin_memory(), roi, 4, m, overlap=0.5, labels_only=True)   # host volume
+        same = same and torch.equal(lab_o, lab_s) and torch.equal(slab, lab_s[:, off:off + slab.shape[1]])
+        same = same and torch.equal(lab_h, lab_s)
         flags = torch.tensor([int(same)], device="cuda")
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if rank == 0:
