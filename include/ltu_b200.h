@@ -176,13 +176,6 @@ int ltu_attn_out_fused(const void* x, int B, int64_t N, int C, int heads, const 
                        const float* bq, const void* ctx_bf16, const void* wo_bf16, const float* bo,
                        const float* gamma, const float* beta, float eps, void* y, ltu_stream_t stream);
 
-/* Hardware probe, not on the product path (tools/umma_probe.py): one tcgen05.mma whose SWIZZLE_128B A operand
- * starts at halo row off_rows (128-byte rows, not 1024-byte aligned) with sbo_rows rows between 8-row groups.
- * g bf16 [R][CW], w bf16 [64][CW], out fp32 [128][64] = A . w^T with A row 8g+i = g[off_rows + g*sbo_rows + i];
- * CW = 64 / 32 / 16 channels per row selects SWIZZLE_128B / 64B / 32B.                                        */
-int ltu_debug_umma_probe(const void* g, int R, const void* w, float* out, int off_rows, int sbo_rows,
-                         int use_base_offset, int CW, ltu_stream_t stream);
-
 /* Small-channel stride-1 3x3x3 convolution for bf16 activations (stem, enc.block0/1 conv1,
  * dec.block3, finest mask head, final_block): the input halo of a 3-D output tile and all weights are
  * staged once in shared memory and im2col happens in the ldmatrix row addresses of mma.sync

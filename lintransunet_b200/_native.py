@@ -48,7 +48,6 @@ SIGNATURES = {
     "ltu_attn_out_fused_supported": (I, [I, I]),
     "ltu_ctx_pack_bf16": (I, [P, P, I, I, P]),
     "ltu_attn_out_fused": (I, [P, I, L, I, I, P, P, P, P, P, P, P, F, P, P]),
-    "ltu_debug_umma_probe": (I, [P, I, P, P, I, I, I, I, P]),
     "ltu_conv3d_halo_supported": (I, [I, I, I, I, I, I, I, I, I]),
     "ltu_conv3d_halo_tiles": (I, [I, I, I, I]),
     "ltu_conv3d_halo": (I, [P, I, P, I, I, I, I, I, I, P, I, P, I, P, I, P, I, P, P]),

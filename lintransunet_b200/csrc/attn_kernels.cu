@@ -152,6 +152,7 @@ kv_reduce_kernel(const T* __restrict__ K, const T* __restrict__ V, int64_t ld, f
 // accumulator loads of a block of parts are all issued before the first one is consumed.
 __global__ void __launch_bounds__(1024)
 kv_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx, int heads, int nparts) {
+    pdl_prologue();
     const int hd = blockIdx.x, b = blockIdx.y;
     const int j = threadIdx.x >> 5, e = threadIdx.x & 31;
     const float* base = part + ((int64_t)b * nparts * heads + hd) * kPartialFloats;
@@ -465,10 +466,19 @@ int q_readout_bf16_mma(const void* q, int64_t ldq, const float* ctx, void* out, 
                        int heads, cudaStream_t st);
 int kv_chunks_per_batch_host(int B, int64_t N) { return kv_chunks_per_batch(B, N); }
 int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st) {
-    kv_combine_kernel<<<dim3(heads, B), 1024, 0, st>>>(ws, ctx, heads, nparts);
-    LTU_LAUNCH_CHECK("kv_combine");
+    cudaError_t e = launch_pdl(kv_combine_kernel, dim3(heads, B), dim3(1024), 0, st, ws, ctx, heads, nparts);
+    if (e != cudaSuccess) { set_error("kv_combine: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return LTU_OK;
 }
+// LTU_ATTN_STREAM=0 falls back to the first-generation cp.async kernels of attn_tc.cu (A/B switch, read once)
+static bool use_stream_attention() {
+    static const bool v = [] { const char* e = getenv("LTU_ATTN_STREAM"); return !(e && e[0] == '0'); }();
+    return v;
+}
+int kv_reduce_bf16_stream(const void* k, const void* v, int64_t ld, float* ctx, void* ws, int B, int64_t N, int heads,
+                          cudaStream_t st);                      // attn_stream.cu
+int q_readout_bf16_stream(const void* q, int64_t ldq, const float* ctx, void* out, int64_t ldo, int B, int64_t N, int heads,
+                          cudaStream_t st);
 static bool use_mma_attention() {
     static const bool v = [] { const char* e = getenv("LTU_ATTN_FMA"); return !(e && e[0] == '1'); }();
     return v;
@@ -553,6 +563,8 @@ extern "C" int ltu_kv_reduce(const void* k, const void* v, int64_t ld, float* ct
     if (dtype == LTU_F32) return kv_reduce_impl<float>(k, v, ld, ctx, ws, ws_bytes, B, N, heads, (cudaStream_t)stream);
     if (heads >= 2 && use_mma_attention()) {
         LTU_ARG_CHECK(ws_bytes >= ltu_kv_reduce_workspace(B, N, heads), "kv_reduce: workspace too small");
+        if ((heads == 4 || heads == 8) && ld % 8 == 0 && N < ((int64_t)1 << 31) && use_stream_attention())
+            return kv_reduce_bf16_stream(k, v, ld, ctx, ws, B, N, heads, (cudaStream_t)stream);
         return kv_reduce_bf16_mma(k, v, ld, ctx, ws, B, N, heads, (cudaStream_t)stream);
     }
     return kv_reduce_impl<bf16>(k, v, ld, ctx, ws, ws_bytes, B, N, heads, (cudaStream_t)stream);
@@ -568,6 +580,9 @@ extern "C" int ltu_q_readout(const void* q, int64_t ldq, const float* ctx, void*
     LTU_ARG_CHECK(ldq >= heads * 32 && ldq % vn == 0 && ldo >= heads * 32, "q_readout: bad row strides");
     LTU_ARG_CHECK(aligned16(q), "q_readout: q must be 16-byte aligned");
     if (dtype == LTU_F32) return q_readout_impl<float>(q, ldq, ctx, out, ldo, B, N, heads, (cudaStream_t)stream);
+    if ((heads == 4 || heads == 8) && ldq % 8 == 0 && ldo % 8 == 0 && aligned16(out) && N < ((int64_t)1 << 31) &&
+        use_mma_attention() && use_stream_attention())
+        return q_readout_bf16_stream(q, ldq, ctx, out, ldo, B, N, heads, (cudaStream_t)stream);
     if (heads >= 2 && ldo % 8 == 0 && aligned16(out) && use_mma_attention())
         return q_readout_bf16_mma(q, ldq, ctx, out, ldo, B, N, heads, (cudaStream_t)stream);
     return q_readout_impl<bf16>(q, ldq, ctx, out, ldo, B, N, heads, (cudaStream_t)stream);

@@ -141,4 +141,31 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel that starts with pdl_prologue() and is launched through launch_pdl() may be scheduled while its
+// predecessor in the stream is still draining (the predecessor must have executed griddepcontrol.launch_dependents,
+// which pdl_prologue() also does): block scheduling, barrier / tensor-map set-up and the launch latency overlap the
+// predecessor's tail, and griddepcontrol.wait returns once the predecessor has COMPLETED and its writes are visible.
+// Nothing may touch global memory before the wait.  Both instructions are no-ops in an ordinary launch; the edges
+// survive CUDA-graph stream capture.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 }  // namespace ltu

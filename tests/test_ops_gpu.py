@@ -151,6 +151,47 @@ def test_posenc(dtype, shape):
     assert rel_err(from_cl(y.float()), ref) < (2e-5 if dtype == torch.float32 else TOL[dtype])
 
 
+@pytest.mark.parametrize("rows,C", [(77, 128), (1000, 256), (4097, 256)])
+def test_add_layernorm_split_stream(rows, C):
+    """hi + lo carries the LayerNorm output to ~16 significant bits; hi alone is the plain bf16 result."""
+    ops = _ops()
+    bf = torch.bfloat16
+    x = rnd((rows, C), 1)
+    x_hi = x.to(bf)
+    x_lo = (x - x_hi.float()).to(bf)
+    r = q_(rnd((rows, C), 2), bf)
+    g, b = 1 + 0.1 * rnd((C,), 3), 0.1 * rnd((C,), 4)
+    y_hi, y_lo = ops.add_layernorm_split(x_hi.cuda(), x_lo.cuda(), r.to("cuda", bf), g.cuda(), b.cuda(), 1e-6)
+    ref = F.layer_norm(x_hi.float() + x_lo.float() + r, (C,), g, b, eps=1e-6)
+    assert rel_err(y_hi.float() + y_lo.float(), ref) < 5e-5
+    assert torch.equal(y_hi.cpu(), ref.to(bf)) or rel_err(y_hi.float(), ref) < TOL[bf]
+    # x_lo = None: the first layer of a stack starts from a plain bf16 tensor
+    y2_hi, y2_lo = ops.add_layernorm_split(x_hi.cuda(), None, r.to("cuda", bf), g.cuda(), b.cuda(), 1e-6)
+    ref2 = F.layer_norm(x_hi.float() + r, (C,), g, b, eps=1e-6)
+    assert rel_err(y2_hi.float() + y2_lo.float(), ref2) < 5e-5
+    assert torch.equal(y2_hi, ops.add_layernorm(x_hi.cuda(), r.to("cuda", bf), g.cuda(), b.cuda(), 1e-6))
+
+
+def test_posenc_split_stream():
+    ops = _ops()
+    from lintransunet_b200.unet import Conv3dPosEmbedding, _pos_w
+    bf = torch.bfloat16
+    B, C, H, W, D = 2, 256, 5, 4, 7
+    pe = Conv3dPosEmbedding(C)
+    x = rnd((B, C, H, W, D), 6)
+    x_hi = x.to(bf)
+    x_lo = (x - x_hi.float()).to(bf)
+    w, b = _pos_w(pe)
+    y_hi, y_lo = ops.posenc_dwconv3_split(to_cl(x_hi).cuda(), to_cl(x_lo).cuda(), w.cuda(), b.cuda())
+    # the taps read hi (a conv input is bf16 under autocast), the residual term is hi + lo
+    conv = O.pos_embedding(x_hi.float(), pe.proj.weight.detach(), pe.proj.bias.detach()) - x_hi.float()
+    ref = x_hi.float() + x_lo.float() + conv
+    assert rel_err(from_cl(y_hi.float() + y_lo.float()), ref) < 5e-5
+    plain = ops.posenc_dwconv3(to_cl(x_hi).cuda(), w.cuda(), b.cuda())
+    y0_hi, _ = ops.posenc_dwconv3_split(to_cl(x_hi).cuda(), None, w.cuda(), b.cuda())
+    assert torch.equal(y0_hi, plain)
+
+
 def test_posenc_golden():
     ops = _ops()
     from lintransunet_b200.unet import Conv3dPosEmbedding, _pos_w

@@ -1,4 +1,4 @@
-// Hardware probe (not on the product path): does a K-major SWIZZLE_128B UMMA operand descriptor accept a start
+// Hardware probe, a development tool built by tools/umma_probe.py into tools/libltu_probe.so (NOT part of libltu_b200.so): does a K-major SWIZZLE_128B UMMA operand descriptor accept a start
 // address that is not 1024-byte aligned and a stride between 8-row groups (SBO) that is not a multiple of
 // 1024 bytes?  This is what a shared-memory HALO needs: the A rows of filter tap (kh,kw,kd) are the halo rows
 // shifted by a constant, and consecutive 8-row groups of the 4x4x8 output tile are (8+2) halo rows apart.
