@@ -413,13 +413,13 @@ def run_ours(args):
                         "avg_launch_us": round(d["ms"] / d["launches"] * 1e3, 2)})
             return out
 
-        bound_of = {"conv3d_tc": "tensor", "conv3d_tc3": "tensor", "conv3d": "tensor", "conv3d_tc4": "tensor"}
+        bound_of = {"conv3d_tc": "tensor", "conv3d_tc3": "tensor", "conv3d": "tensor"}
         dominant = max(ksum.items(), key=lambda kv: kv[1]["ms"])[0] if ksum else None
         roofline = roof(dominant, bound_of.get(dominant, "hbm")) if dominant else None
         attn = {n: roof(n, "hbm") for n in ("kv_reduce", "q_readout") if n in ksum}
         # d_model=128 layers: the readout, both projections, the FFN and both LayerNorms run inside two fused kernels
         fused = {n: roof(n, "hbm") for n in ("attn_out_fused", "ffn_fused") if n in ksum}
-        conv_detail = {n: roof(n, bound_of.get(n, "hbm")) for n in ("conv3d_tc", "conv3d_tc3", "conv3d_tc4", "conv3d_halo") if n in ksum}
+        conv_detail = {n: roof(n, bound_of.get(n, "hbm")) for n in ("conv3d_tc", "conv3d_tc3", "conv3d_sv", "conv3d_halo") if n in ksum}
         line = {"metric": METRIC, "value": win_vox / (ms_step / 1e3), "unit": "voxels/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -462,7 +462,8 @@ ALGORITHMIC = {
     "ffn_fused": "2*rows*C*E bytes (x read once, y written once)",
     "conv3d_tc": "2*27*Cin*Cout*B*Vout flop (un-folded; `executed` counts 8/27 of it for the folded up_embed layers)",
     "conv3d_tc3": "2*27*Cin*Cout*B*Vout flop (un-folded; `executed` counts 8/27 of it for the folded up_embed layer)",
-    "conv3d_tc4": "2*27*Cin*Cout*B*Vout flop",
+    "conv3d_sv": "(B*Cin*Vin + B*Cout*Vout)*E bytes: the small-channel layers (SURVEY 8a: AI 86-216, HBM-bound) in "
+                 "super-voxel form on the TMA-halo tcgen05 kernel",
     "conv3d_halo": "(B*Cin*Vin + B*Cout*Vout)*E bytes",
 }
 

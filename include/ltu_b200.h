@@ -131,6 +131,19 @@ int ltu_conv3d_tc3(const void* in0, int C0, const void* in1, int C1, int B, int 
                    int up2, const void* weight_bf16, int weight_rows, int Kpad, const float* bias,
                    int Cout, void* out, float* partials, int n_aux, float* aux_out,
                    ltu_stream_t stream);
+/* The small-channel stride-1 3x3x3 layers (model/Unet_3Dblock.py:310,:523,:528,:588,:1353 and the finest mask head
+ * :1328: stem, enc.block0/1 conv1, dec.block2/3, final_block; 8, 16 or 32 channels per input) on the same kernel in
+ * SUPER-VOXEL form: g = 64 / Cin consecutive voxels along D are one 64-channel row (the same memory viewed as
+ * [B][H][W][D/g][64]; D % g == 0), the weights are the block-Toeplitz repacking
+ * W'[(kh,kw,kg)][(p,c)][(delta,co)] = W[kh][kw][g(kg-1)+p-delta+1][c][co] (zero outside 0..2), so UMMA N = g * Cout and
+ * the output [B][H][W][D/g][g*Cout] IS the channels-last [B][H][W][D][Cout] tensor.  The caller passes the viewed shapes
+ * (C0 = 64, C1 in {0, 64}, Di = D/g, Cout = g * Cout, n_aux = g * n_aux, aux rows ordered (delta, a) after the
+ * (delta, co) main rows; Cout = 0 with an auxiliary head only = fp32 output).  ks_mask: 27 bytes in HOST memory, bit ks
+ * of entry t = the 16-channel K block ks of tap t is not identically zero (zero blocks are not issued).             */
+int ltu_conv3d_tc3_masked(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di,
+                          const void* weight_bf16, int weight_rows, int Kpad, const float* bias, int Cout,
+                          void* out, float* partials, int n_aux, float* aux_out, const uint8_t* ks_mask,
+                          ltu_stream_t stream);
 
 /* nn.Linear on a bf16 token matrix with a fused epilogue (model/trans_block.py:166,:187-189,:205-210),
  * run by the persistent tcgen05 kernel (a 1x1x1 "convolution"):  y = epi(x W^T + b)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "ltu_conv3d_tc3_supported": (I, [I, I, I, I, I, I, I, I, I, I, I]),
     "ltu_conv3d_tc3_tiles": (I, [I, I, I, I, I, I, I]),
     "ltu_conv3d_tc3": (I, [P, I, P, I, I, I, I, I, I, P, I, I, P, I, P, P, I, P, P]),
+    "ltu_conv3d_tc3_masked": (I, [P, I, P, I, I, I, I, I, P, I, I, P, I, P, P, I, P, P, P]),
     "ltu_linear_tc": (I, [P, I, L, P, P, I, P, I, I, P, P, P, F, P]),
     "ltu_ffn_fused_supported": (I, [I]),
     "ltu_ffn_fused": (I, [P, L, I, P, P, P, P, P, P, F, P, P]),

@@ -52,6 +52,9 @@ struct T3Params {
     int nacc;                        // accumulator sets in tensor memory: 2 (256 columns each) when TH*cpp*N <= 256, else 1
     int tiles, total_tiles;          // tiles per sample, tiles over the batch
     uint32_t halo_bytes, halo_stride, off_b;   // bytes of one halo, distance between halo buffers, offset of the weight ring
+    // super-voxel mode (ltu_conv3d_tc3_masked): bit ks of ksmask[t] = the 16-channel K block ks of filter tap t holds
+    // non-zero weights (block-Toeplitz repacking, see the entry point); all-zero blocks are not issued.  0xF otherwise.
+    uint8_t ksmask[27];
 };
 
 struct T3Tail {
@@ -134,6 +137,7 @@ conv3d_tc3_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_const
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         const uint32_t idesc = umma_idesc_bf16(128, p.N);
+        const int first_ks = __ffs((int)p.ksmask[0]) - 1;                           // first issued MMA of an item overwrites
         uint32_t nb = 0, nh = 0, it = 0;
         for (int i = 0; i < n_my; ++i)
         for (int pass = 0; pass < p.npass; ++pass, ++it) {
@@ -161,6 +165,7 @@ conv3d_tc3_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_const
                             }
                             auto pick = [&](int ax) { return ax == 0 ? k[0] : (ax == 1 ? k[1] : k[2]); };
                             const int row0 = (pick(p.axT) * 18 + pick(p.ax16)) * 10 + pick(p.ax8);
+                            const uint32_t kmask = p.ksmask[t];
                             const uint64_t bdesc = make_desc(sbase + p.off_b + s * b_bytes);
 #pragma unroll
                             for (int v = 0; v < 4; ++v) {
@@ -171,8 +176,11 @@ conv3d_tc3_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_const
                                                        ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
                                 const uint32_t tacc = acc_base + (uint32_t)((zl * p.TH + v) * p.N);
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    umma_bf16_elect(tacc, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, (j | t | ks) != 0);
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    if (!((kmask >> ks) & 1u)) continue;
+                                    umma_bf16_elect(tacc, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc,
+                                                    (uint32_t)((j | t) != 0 || ks != first_ks));
+                                }
                             }
                             umma_commit_elect(smem_u32(&tail->b_empty[s]));
                         }
@@ -374,10 +382,10 @@ using namespace ltu;
 extern "C" int ltu_conv3d_tc3_supported(int C0, int C1, int Cout, int ksize, int sh, int sw, int sd, int pad, int up2,
                                         int out_f32, int n_aux) {
     if (!tc3_enabled()) return 0;
-    if (ksize != 3 || pad != 1 || sh != 1 || sw != 1 || sd != 1 || out_f32 || n_aux < 0 || n_aux > 16) return 0;
+    if (ksize != 3 || pad != 1 || sh != 1 || sw != 1 || sd != 1 || out_f32 || n_aux < 0 || n_aux > 64) return 0;
     if (C0 < 64 || C0 % 64 != 0 || C1 % 64 != 0) return 0;
     const int N = (Cout + n_aux + 31) / 32 * 32;
-    if (Cout % 8 != 0 || Cout > 128 || N > 256) return 0;
+    if (Cout < 0 || Cout % 8 != 0 || Cout > 128 || N > 256 || N < 32) return 0;
     // folded layers: measured faster than the im2col kernel only for narrow outputs (b1.up_embed, Cout 32)
     if (up2 && (N > 32 || n_aux)) return 0;
     return 1;
@@ -395,9 +403,37 @@ extern "C" int ltu_conv3d_tc3_tiles(int B, int Hi, int Wi, int Di, int Cout, int
 
 // Same contract as ltu_conv3d_tc for the shapes ltu_conv3d_tc3_supported accepts.  weight_bf16: the ltu_conv3d_tc
 // packing with rows padded to a multiple of 32 ([rows32][Kpad], or [8][rows32][Kpad] folded).
+static int conv3d_tc3_impl(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di, int up2,
+                           const void* weight_bf16, int weight_rows, int Kpad, const float* bias, int Cout, void* out,
+                           float* partials, int n_aux, float* aux_out, const uint8_t* ks_mask, ltu_stream_t stream);
+
 extern "C" int ltu_conv3d_tc3(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di, int up2,
                               const void* weight_bf16, int weight_rows, int Kpad, const float* bias, int Cout, void* out,
                               float* partials, int n_aux, float* aux_out, ltu_stream_t stream) {
+    return conv3d_tc3_impl(in0, C0, in1, C1, B, Hi, Wi, Di, up2, weight_bf16, weight_rows, Kpad, bias, Cout, out, partials,
+                           n_aux, aux_out, nullptr, stream);
+}
+
+// Super-voxel form of the small-channel layers (Cin in {8, 16, 32} per input): g = 64 / Cin consecutive voxels along D
+// are ONE row of 64 channels -- the same memory, viewed as [B][H][W][D/g][64] -- so the layer is a 3x3x3 convolution over
+// super-voxels with 64 input channels per tensor and g * Cout output channels, whose weights are the block-Toeplitz
+// repacking of the original taps (W'[(kh,kw,kg)][(p,c)][(delta,co)] = W[kh][kw][g(kg-1)+p-delta+1][c][co], zero outside
+// 0..2).  It runs on this kernel unchanged: UMMA N = g * Cout (64 .. 128) instead of 16 .. 32, the A operand is read
+// once per g output voxels, the output [B][H][W][D/g][g*Cout] IS the channels-last [B][H][W][D][Cout] tensor, and the
+// auxiliary head / InstanceNorm columns come out in (delta, channel) order.  ks_mask[27] (host memory): bit ks of entry
+// t = K block ks of tap t is not identically zero; the zero blocks (7 of 12 per (kh,kw) at g = 4) are skipped.
+extern "C" int ltu_conv3d_tc3_masked(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di,
+                                     const void* weight_bf16, int weight_rows, int Kpad, const float* bias, int Cout,
+                                     void* out, float* partials, int n_aux, float* aux_out, const uint8_t* ks_mask,
+                                     ltu_stream_t stream) {
+    LTU_ARG_CHECK(ks_mask, "conv3d_tc3_masked: null mask");
+    return conv3d_tc3_impl(in0, C0, in1, C1, B, Hi, Wi, Di, 0, weight_bf16, weight_rows, Kpad, bias, Cout, out, partials,
+                           n_aux, aux_out, ks_mask, stream);
+}
+
+static int conv3d_tc3_impl(const void* in0, int C0, const void* in1, int C1, int B, int Hi, int Wi, int Di, int up2,
+                           const void* weight_bf16, int weight_rows, int Kpad, const float* bias, int Cout, void* out,
+                           float* partials, int n_aux, float* aux_out, const uint8_t* ks_mask, ltu_stream_t stream) {
     LTU_ARG_CHECK(in0 && weight_bf16 && out, "conv3d_tc3: null pointer");
     LTU_ARG_CHECK(ltu_conv3d_tc3_supported(C0, C1, Cout, 3, 1, 1, 1, 1, up2, 0, n_aux), "conv3d_tc3: unsupported C0=%d C1=%d Cout=%d n_aux=%d", C0, C1, Cout, n_aux);
     LTU_ARG_CHECK(n_aux == 0 || aux_out, "conv3d_tc3: auxiliary head without an output buffer");
@@ -410,6 +446,10 @@ extern "C" int ltu_conv3d_tc3(const void* in0, int C0, const void* in1, int C1, 
     LTU_ARG_CHECK(((uintptr_t)in0 & 15) == 0 && ((uintptr_t)in1 & 15) == 0 && ((uintptr_t)weight_bf16 & 15) == 0 &&
                   ((uintptr_t)out & 15) == 0, "conv3d_tc3: pointers must be 16-byte aligned");
     p.out = (bf16*)out; p.bias = bias; p.partials = partials; p.Cstore = Cout;
+    for (int t = 0; t < 27; ++t) {
+        p.ksmask[t] = ks_mask ? (uint8_t)(ks_mask[t] & 0xF) : (uint8_t)0xF;
+        LTU_ARG_CHECK(p.ksmask[t] != 0, "conv3d_tc3_masked: tap %d has an empty mask", t);
+    }
     p.nchunk0 = C0 / 64; p.nchunk1 = C1 / 64; p.Cin = C0 + C1;
     p.fold = up2 ? 1 : 0; p.ntaps = up2 ? 8 : 27;
     p.dim[0] = Hi; p.dim[1] = Wi; p.dim[2] = Di;

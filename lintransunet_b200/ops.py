@@ -286,6 +286,93 @@ def posenc_dwconv3_bwd(x: torch.Tensor, dy: torch.Tensor, w27c: torch.Tensor):
 
 
 # ------------------------------------------------------------------ convolution + InstanceNorm
+class SVPack:
+    """Super-voxel form of a small-channel stride-1 3x3x3 convolution (include/ltu_b200.h, ltu_conv3d_tc3_masked):
+    g = 64 / ci consecutive voxels along D are one 64-channel row.  `w` bf16 [rows32][27 * 64 * n_inputs] is the
+    block-Toeplitz repacking, rows ordered (delta, co) for the n_main bf16 channels then (delta, a) for the n_aux fp32
+    channels; `mask` 27 bytes: which 16-channel K blocks of a tap are not identically zero."""
+    __slots__ = ("w", "bias", "mask", "g", "n_main", "n_aux", "ci", "n_inputs", "blocks")
+
+    def __init__(self, w, bias, mask, g, n_main, n_aux, ci, n_inputs):
+        self.w, self.bias, self.mask, self.g = w, bias, mask, g
+        self.n_main, self.n_aux, self.ci, self.n_inputs = n_main, n_aux, ci, n_inputs
+        self.blocks = sum(bin(b).count("1") for b in mask)          # issued K blocks per 128 rows and input
+
+
+def sv_pack(w: torch.Tensor, bias: Optional[torch.Tensor], n_main: int, n_aux: int, ci: int, n_inputs: int) -> SVPack:
+    """w fp32 [n_main + n_aux, ci * n_inputs, 3, 3, 3] (nn.Conv3d layout, kernel axes (H, W, D)) -> SVPack."""
+    g = 64 // ci
+    cout = n_main + n_aux
+    assert w.shape[0] == cout and w.shape[1] == ci * n_inputs and g * ci == 64
+    dev = w.device
+    # sel[kg, p, delta, kd] = 1 iff input voxel p of super-voxel (G + kg - 1) is tap kd of output voxel delta of super-voxel G
+    sel = torch.zeros(3, g, g, 3, device=dev)
+    for kg in range(3):
+        for p_ in range(g):
+            for d in range(g):
+                kd = g * (kg - 1) + p_ - d + 1
+                if 0 <= kd <= 2:
+                    sel[kg, p_, d, kd] = 1.0
+    w6 = w.reshape(cout, n_inputs, ci, 3, 3, 3)                                      # [o, j, c, kh, kw, kd]
+    wp = torch.einsum("gpdk,ojchwk->dohwgjpc", sel, w6)                               # [delta, o, kh, kw, kg, j, p, c]
+    K = 27 * 64 * n_inputs
+    rows = g * cout
+    rows32 = (rows + 31) // 32 * 32
+    out = torch.zeros(rows32, K, dtype=torch.bfloat16, device=dev)
+    main = wp[:, :n_main].reshape(g * n_main, K)
+    aux = wp[:, n_main:].reshape(g * n_aux, K)
+    out[:g * n_main] = main.to(torch.bfloat16)
+    out[g * n_main:rows] = aux.to(torch.bfloat16)
+    b = torch.zeros(rows32, dtype=torch.float32, device=dev)
+    if bias is not None:
+        b[:g * n_main] = bias[:n_main].float().repeat(g)
+        b[g * n_main:rows] = bias[n_main:].float().repeat(g)
+    mask = []
+    for t in range(27):
+        kg = t % 3
+        m = 0
+        for ks in range(4):
+            ps = range((16 * ks) // ci, (16 * ks + 15) // ci + 1)
+            if any(float(sel[kg, p_].sum()) > 0 for p_ in ps):
+                m |= 1 << ks
+        mask.append(m)
+    return SVPack(out.contiguous(), b, bytes(mask), g, n_main, n_aux, ci, n_inputs)
+
+
+USE_SV_CONV = os.environ.get("LTU_DISABLE_SV", "0") != "1"         # A/B switch for the super-voxel form
+
+
+def _conv3d_sv(x0, x1, sv: SVPack, want_stats: bool):
+    """Run a small-channel 3x3x3 stride-1 convolution in super-voxel form on the TMA-halo tcgen05 kernel."""
+    L = _native.lib()
+    dev = x0.device
+    B, H, W, D, ci = x0.shape
+    g = sv.g
+    Dg = D // g
+    x0v = x0.view(B, H, W, Dg, 64)
+    x1v = None if x1 is None else x1.view(B, H, W, Dg, 64)
+    cm, ca = g * sv.n_main, g * sv.n_aux
+    out = torch.empty(B, H, W, D, sv.n_main, dtype=torch.bfloat16, device=dev) if sv.n_main else None
+    aux = torch.empty(B, H, W, D, sv.n_aux, dtype=torch.float32, device=dev) if sv.n_aux else None
+    tiles = L.ltu_conv3d_tc3_tiles(B, H, W, Dg, cm, ca, 0)
+    partials = torch.empty(B, tiles, cm, 2, dtype=torch.float32, device=dev) if (want_stats and sv.n_main) else None
+    V = H * W * D
+    cin = ci * sv.n_inputs
+    nbytes = (x0.numel() + (0 if x1 is None else x1.numel())) * 2 + (0 if out is None else out.numel() * 2) + \
+        (0 if aux is None else aux.numel() * 4)
+    flops = 2 * 27 * cin * (sv.n_main + sv.n_aux) * B * V
+    rows = B * H * W * Dg
+    fexec = 2 * rows * sv.w.shape[0] * 16 * sv.blocks * sv.n_inputs
+    with _Guard(dev, ("conv3d_sv", nbytes, flops, fexec)) as st:
+        check(L.ltu_conv3d_tc3_masked(_p(x0v), 64, _p(x1v), 0 if x1 is None else 64, B, H, W, Dg, _p(sv.w), sv.w.shape[0],
+                                      sv.w.shape[1], _p(sv.bias), cm, _p(out if out is not None else aux), _p(partials), ca,
+                                      _p(aux), sv.mask, st), "ltu_conv3d_tc3_masked")
+    if partials is not None:
+        partials = partials.view(B, tiles * g, sv.n_main, 2)     # columns are (delta, co): delta joins the tile index
+        tiles = tiles * g
+    return out, partials, tiles, aux
+
+
 def conv_out_size(n: int, k: int, s: int, pad: int) -> int:
     return (n + 2 * pad - k) // s + 1
 
@@ -293,13 +380,22 @@ def conv_out_size(n: int, k: int, s: int, pad: int) -> int:
 def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ksize: int,
            stride: Tuple[int, int, int] = (1, 1, 1), pad: int = 1, x1: Optional[torch.Tensor] = None,
            up2: bool = False, out_f32: bool = False, want_stats: bool = False,
-           w_tc: Optional[torch.Tensor] = None, w_tc_fold: Optional[torch.Tensor] = None, n_aux: int = 0):
+           w_tc: Optional[torch.Tensor] = None, w_tc_fold: Optional[torch.Tensor] = None, n_aux: int = 0,
+           sv: Optional[SVPack] = None):
     """nn.Conv3d on channels-last input(s).  Returns (out, partials, tiles); partials is None
     unless want_stats.  When `w_tc` (bf16 [Cout16][Kpad], see ltu_conv3d_tc) is given and the shape
     qualifies the tcgen05 implicit-GEMM kernel is used, otherwise the CUDA-core kernel."""
     if up2:
         w_tc = w_tc_fold                      # the tensor-core path of an up2 conv needs the folded weights
     dev = _chk(x0, x1, w_packed, bias, w_tc)
+    if (sv is not None and USE_SV_CONV and USE_TC3_CONV and x0.dtype == torch.bfloat16 and not up2 and ksize == 3 and pad == 1
+            and tuple(stride) == (1, 1, 1) and x0.shape[-1] == sv.ci and x0.shape[3] % sv.g == 0
+            and (x1 is not None) == (sv.n_inputs == 2) and (x1 is None or x1.shape == x0.shape)
+            and out_f32 == (sv.n_main == 0) and n_aux == (0 if out_f32 else sv.n_aux)):
+        out, partials, tiles, aux = _conv3d_sv(x0, x1, sv, want_stats)
+        if out_f32:
+            return aux, None, tiles
+        return (out, partials, tiles, aux) if n_aux else (out, partials, tiles)
     L = _native.lib()
     B, Hi, Wi, Di, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[-1]

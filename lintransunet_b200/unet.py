@@ -203,7 +203,7 @@ class _ConvW:
     channels (the stem's 4 channels are padded to 8 = one 16-byte bf16 vector)."""
 
     def __init__(self, conv: nn.Conv3d, want_tc: bool, cin_pad: int = 0, fold_up2: bool = False,
-                 aux: Optional[nn.Conv3d] = None):
+                 aux: Optional[nn.Conv3d] = None, n_inputs: int = 1, f32_out: bool = False):
         w = conv.weight.detach()
         bias = conv.bias.detach() if conv.bias is not None else None
         self.n_aux = 0
@@ -229,6 +229,15 @@ class _ConvW:
         self.w_tc_fold = None
         if want_tc and fold_up2 and self.w_tc is not None and k == 3:
             self.w_tc_fold = _fold_up2_weights(w.float(), cout, cin)
+        # small-channel stride-1 3x3x3 layers: super-voxel repacking for the TMA-halo tcgen05 kernel (ops.SVPack)
+        self.sv = None
+        ci = cin // n_inputs
+        if want_tc and k == 3 and tuple(conv.stride) == (1, 1, 1) and ci in (8, 16, 32) and cin == ci * n_inputs and n_inputs in (1, 2):
+            n_main = 0 if f32_out else self.cout
+            n_aux = cout if f32_out else self.n_aux
+            g = 64 // ci
+            if g * n_main <= 128 and g * (n_main + n_aux) <= 256 and g * n_aux <= 64:
+                self.sv = ops.sv_pack(w.float(), self.b, n_main, n_aux, ci, n_inputs)
 
 
 def _fold_up2_weights(w: torch.Tensor, cout: int, cin: int) -> torch.Tensor:
@@ -296,18 +305,18 @@ class _Plan:
         self.dtype = dtype
         self.stem = _ConvW(enc.input_block, tc, cin_pad=8 if tc else 0)
         self.down = [(_ConvW(b.conv1, tc), _ConvW(b.conv2, tc), b.stride) for b in enc.block_list]
-        self.mask = [_ConvW(c, tc) for c in dec.mask_conv_list]
+        self.mask = [_ConvW(c, tc, f32_out=True) for c in dec.mask_conv_list]
         self.gate = []
         for a in dec.att_conv_list:
             psi = a.psi[0]
             self.gate.append((_ConvW(a.W_x[0], tc), _ConvW(a.W_g[0], tc),
                               psi.weight.detach().reshape(-1).float().contiguous(),
                               psi.bias.detach().float().contiguous()))
-        self.up = [(_ConvW(b.conv1, tc), _ConvW(b.conv2, tc)) for b in dec.block_list]
+        self.up = [(_ConvW(b.conv1, tc), _ConvW(b.conv2, tc, n_inputs=2)) for b in dec.block_list]
         # bf16 path: the mask head of level i reads the same upsampled x as UpBlock.conv1 -> one fused launch
         n = len(dec.block_list)
         self.up_dual = [_ConvW(dec.block_list[i].conv1, True, aux=dec.mask_conv_list[n - 1 - i]) for i in range(n)] if tc else None
-        self.final = _ConvW(dec.final_block, tc)
+        self.final = _ConvW(dec.final_block, tc, f32_out=True)
         self.bridges: List[Optional[dict]] = []
         for br in dec.bridge_list:
             if isinstance(br, ROIBridge):
@@ -507,7 +516,7 @@ class MaskTransUnet(nn.Module):
     def _conv(self, x, cw: _ConvW, **kw):
         tc = self.use_tensor_cores
         return ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, w_tc=cw.w_tc if tc else None,
-                          w_tc_fold=cw.w_tc_fold if tc else None, **kw)
+                          w_tc_fold=cw.w_tc_fold if tc else None, sv=cw.sv if tc else None, **kw)
 
     def _conv_in_act(self, x, cw: _ConvW, stride=(1, 1, 1), residual=None, x1=None, up2=False):
         """Conv3d -> InstanceNorm3d -> LeakyReLU (+ residual)."""
@@ -655,7 +664,7 @@ class MaskTransUnet(nn.Module):
             if fused:    # mask head (:1380) + UpBlock.conv1 (:547) share their input: one conv, two outputs
                 cw = P.up_dual[i - 1]
                 raw1, part1, _, logits = ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, pad=1, want_stats=True, w_tc=cw.w_tc,
-                                                    n_aux=cw.n_aux)
+                                                    n_aux=cw.n_aux, sv=cw.sv)
             else:
                 logits, _, _ = self._conv(x, P.mask[lvl], pad=1, out_f32=True)   # :1380
             mask, fg = ops.mask_softmax(logits, want_mask=(head == "train"))

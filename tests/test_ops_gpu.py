@@ -275,6 +275,69 @@ def test_conv3d(dtype, case, tc):
         assert rel_err(from_cl(z.float()), ref_z) < (1e-4 if dtype == torch.float32 else TOL[dtype])
 
 
+SV_CASES = [
+    # ci per input, inputs, main channels, fp32 head channels, spatial (H,W,D): super-voxel form on the TMA-halo tcgen05 kernel
+    (8, 1, 16, 0, (9, 17, 40)),         # stem (4 real + 4 zero channels): g = 8, UMMA N = 128
+    (16, 1, 16, 0, (5, 33, 16)),        # enc.block0.conv1: g = 4, N = 64; ragged tiles
+    (16, 1, 16, 0, (64, 64, 32)),       # many tiles, persistent loop wraps
+    (32, 1, 32, 0, (9, 5, 18)),         # enc.block1.conv1: g = 2
+    (32, 1, 16, 3, (7, 16, 12)),        # dec.block3.conv1 + the finest mask head (fp32 aux)
+    (32, 1, 16, 2, (4, 4, 8)),
+    (16, 2, 16, 0, (6, 9, 20)),         # dec.block3.conv2 on cat(x, skip)
+    (32, 2, 32, 0, (5, 8, 6)),          # dec.block2.conv2 on cat(x, skip)
+    (16, 1, 0, 12, (8, 8, 16)),         # final_block, 3 classes: fp32 output only
+    (16, 1, 0, 8, (3, 18, 4)),          # final_block, 2 classes
+    (32, 1, 0, 3, (6, 6, 10)),          # mask head alone
+]
+
+
+@pytest.mark.parametrize("case", SV_CASES)
+def test_conv3d_super_voxel_form(case):
+    ops = _ops()
+    from lintransunet_b200.unet import _ConvW
+    ci, n_in, n_main, n_aux, (H, W, D) = case
+    B, bf = 2, torch.bfloat16
+    f32_only = n_main == 0
+    conv = torch.nn.Conv3d(ci * n_in, n_aux if f32_only else n_main, 3, padding=1)
+    aux = None if (f32_only or n_aux == 0) else torch.nn.Conv3d(ci * n_in, n_aux, 3, padding=1)
+    with torch.no_grad():
+        conv.weight.copy_(q_(conv.weight, bf))
+        if aux is not None:
+            aux.weight.copy_(q_(aux.weight, bf))
+    conv.cuda()
+    if aux is not None:
+        aux.cuda()
+    cw = _ConvW(conv, want_tc=True, aux=aux, n_inputs=n_in, f32_out=f32_only)
+    assert cw.sv is not None and cw.sv.g == 64 // ci
+    x0 = q_(rnd((B, ci, H, W, D), 70), bf)
+    x1 = q_(rnd((B, ci, H, W, D), 71), bf) if n_in == 2 else None
+    xin = x0 if x1 is None else torch.cat((x0, x1), 1)
+    ref = F.conv3d(xin, conv.weight.detach().cpu(), conv.bias.detach().cpu(), padding=1)
+    dev = lambda t: None if t is None else to_cl(t).to("cuda", bf)
+    res = ops.conv3d(dev(x0), cw.w, cw.b, cw.cout, 3, pad=1, x1=dev(x1), out_f32=f32_only, want_stats=not f32_only,
+                     w_tc=cw.w_tc, n_aux=0 if f32_only else n_aux, sv=cw.sv)
+    if f32_only:
+        y, partials, tiles = res
+        assert y.dtype == torch.float32 and partials is None
+        assert rel_err(from_cl(y), ref) < 2e-5
+        return
+    y, partials = res[0], res[1]
+    assert y.dtype == bf and rel_err(from_cl(y.float()), ref) < TOL[bf]
+    stats = ops.instnorm_finalize(partials, H * W * D)
+    assert rel_err(stats[..., 0], ref.mean(dim=(2, 3, 4))) < 5e-3
+    assert rel_err(stats[..., 1], 1 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5)) < 5e-3
+    if n_aux:
+        ref_aux = F.conv3d(xin, aux.weight.detach().cpu(), aux.bias.detach().cpu(), padding=1)
+        assert res[3].dtype == torch.float32 and rel_err(from_cl(res[3]), ref_aux) < 2e-5
+    # the mma.sync halo kernel on the same operands: bf16 storage of the same fp32 sums
+    ops.USE_SV_CONV = False
+    try:
+        alt = ops.conv3d(dev(x0), cw.w, cw.b, cw.cout, 3, pad=1, x1=dev(x1), want_stats=True, w_tc=cw.w_tc, n_aux=n_aux)
+    finally:
+        ops.USE_SV_CONV = True
+    assert rel_err(y.float(), alt[0].float()) < 8e-3
+
+
 HALO_CASES = [
     # cin, cin1, cout, spatial (H,W,D), out_f32        (stride 1, k3: the shared-memory halo / mma.sync kernel)
     (8, 0, 16, (8, 8, 32), False),          # stem (4 real + 4 zero channels)
@@ -523,8 +586,18 @@ def test_encoder_layer_golden(dtype):
         m = MaskTransUnet.__new__(MaskTransUnet)      # only _encoder_layer is exercised
         torch.nn.Module.__init__(m)
         m.use_fused_linear, m.use_fused_ffn, m.use_fused_attn = fused_linear, fused_ffn, fused_attn
-        y = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
+        y, lo = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
+        assert lo is None
         assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2), (fused_linear, fused_ffn, fused_attn)
+    if dtype == torch.bfloat16:     # split token stream (separate-kernel path): hi + lo carries 16 significant bits
+        m.use_fused_linear = m.use_fused_ffn = m.use_fused_attn = False
+        xin = x.to("cuda", dtype)
+        hi, lo = MaskTransUnet._encoder_layer(m, xin, _LayerW(layer, dtype), None, True)
+        plain, _ = MaskTransUnet._encoder_layer(m, xin, _LayerW(layer, dtype))
+        assert lo is not None
+        e_split, e_plain = rel_err(hi.float() + lo.float(), g["layer_out"]), rel_err(plain.float(), g["layer_out"])
+        print(f"\n[encoder layer bf16] plain stream {e_plain:.2e}, split stream (hi + lo) {e_split:.2e}")
+        assert e_split <= e_plain and e_split < 3e-2
 
 
 @pytest.mark.parametrize("epi", [0, 1, 2])
