@@ -156,6 +156,20 @@ int ltu_linear_tc(const void* x, int Cin, int64_t rows, const void* weight_bf16,
                   int Cout, void* y, int ld_y, int epi, const void* residual, const float* gamma,
                   const float* beta, float eps, ltu_stream_t stream);
 
+/* nn.Linear of the encoder layers with d_model 256 (and the K/V projection of d_model 128) as ONE persistent,
+ * warp-specialised TMA + tcgen05 kernel (csrc/linear_tma.cu): replaces F.linear (model/trans_block.py:155-157 Q/K/V
+ * projections as one [3C][C] GEMM, :166 output projection, :208 linear1 / linear2) together with the bias, the exact-erf
+ * GELU (:208) or the residual add + LayerNorm (:205-206, :209-210) that follow it.
+ *     epi 0: y = x W^T + b | 1: y = gelu(x W^T + b) | 2: (y_hi, y_lo) = split(LayerNorm(x W^T + b + res_hi + res_lo))
+ *   x bf16 [rows][K], K % 64 == 0, K <= 1024; w_bf16 = the nn.Linear weight [N][K] rounded to bf16 (row-major);
+ *   bias fp32 [N]; N in {256, 512, 768}; y_hi bf16 [rows][N].  epi 2: N == 256, res_hi / res_lo bf16 [rows][256]
+ *   (the split token stream of ltu_add_layernorm_split; res_lo may be null), gamma / beta fp32 [256], y_lo may be
+ *   null.  All global traffic is TMA (x, W and the residual through one 3-stage ring, outputs through per-warp
+ *   staging tiles); the residual is added on the tensor pipe (acc += R . I_64).                                  */
+int ltu_linear_fused(const void* x, int64_t rows, int K, const void* w_bf16, const float* bias, int N,
+                     int epi, const void* res_hi, const void* res_lo, const float* gamma,
+                     const float* beta, float eps, void* y_hi, void* y_lo, ltu_stream_t stream);
+
 /* Fused feed-forward half of SelfAttentionLayer (model/trans_block.py:207-210: linear1 -> erf GELU ->
  * linear2 -> residual -> layer_norm2, dropouts are identity in eval) as ONE persistent tcgen05 kernel:
  *     y = LayerNorm(x + W2 gelu(W1 x + b1) + b2) * gamma + beta
@@ -331,6 +345,16 @@ size_t ltu_add_layernorm_bwd_workspace(int64_t rows, int C);
 int ltu_add_layernorm_bwd(const void* x, const void* res, const void* dy, const float* gamma,
                           void* dz, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes,
                           int64_t rows, int C, float eps, int dtype, ltu_stream_t stream);
+/* Training-mode dropout (p = 0.3 by default, model/trans_3DUnet.py:162): nn.Dropout of
+ * model/trans_block.py:205,:208,:209 and model/Unet_3Dblock.py:339,:382,:429,:556 (channelwise 0) and the nn.Dropout3d of
+ * Conv3dPosEmbedding, model/trans_block.py:96 (channelwise 1: one draw per (sample, channel)) on a channels-last tensor:
+ *     y = keep ? x / (1 - p) : 0,   keep(i) = Philox4x32-10(seed, offset + i / 4)[i % 4] >= p * 2^32
+ * The decision is a pure function of (seed, offset, index): the backward applies the same call to the gradient.  n elements,
+ * C channels innermost, per_sample elements per batch sample; consumes ceil(n / 4) counters (channel mode:
+ * ceil(samples * C / 4)) starting at `offset`.  y may alias x.  n, C multiples of the 16-byte vector.              */
+int ltu_dropout(const void* x, void* y, int64_t n, int C, int64_t per_sample, float p,
+                uint64_t seed, uint64_t offset, int channelwise, int dtype, ltu_stream_t stream);
+
 /* backward of the exact-erf F.gelu, model/trans_block.py:201,:208: dx = dy (Phi(x) + x phi(x)),
  * x = the pre-activation                                                                          */
 int ltu_gelu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, ltu_stream_t stream);

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libltu_b200.so")
@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libltu_b200.so")
 _lib = None
 _lock = threading.Lock()
 
-P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
+P, I, L, F, Z, U64 = c_void_p, c_int, c_int64, c_float, c_size_t, c_uint64
 
 # name -> (restype, argtypes); mirrors include/ltu_b200.h one to one
 SIGNATURES = {
@@ -30,6 +30,7 @@ SIGNATURES = {
     "ltu_add_layernorm": (I, [P, P, P, P, P, L, I, F, I, P]),
     "ltu_add_layernorm_split": (I, [P, P, P, P, P, P, P, L, I, F, P]),
     "ltu_gelu": (I, [P, L, I, P]),
+    "ltu_dropout": (I, [P, P, L, I, L, F, U64, U64, I, I, P]),
     "ltu_posenc_dwconv3": (I, [P, P, P, P, I, I, I, I, I, I, P]),
     "ltu_posenc_dwconv3_split": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "ltu_conv3d_tiles": (I, [L, I]),
@@ -43,6 +44,7 @@ SIGNATURES = {
     "ltu_conv3d_tc3": (I, [P, I, P, I, I, I, I, I, I, P, I, I, P, I, P, P, I, P, P]),
     "ltu_conv3d_tc3_masked": (I, [P, I, P, I, I, I, I, I, P, I, I, P, I, P, P, I, P, P, P]),
     "ltu_linear_tc": (I, [P, I, L, P, P, I, P, I, I, P, P, P, F, P]),
+    "ltu_linear_fused": (I, [P, L, I, P, P, I, I, P, P, P, P, F, P, P, P]),
     "ltu_ffn_fused_supported": (I, [I]),
     "ltu_ffn_fused": (I, [P, L, I, P, P, P, P, P, P, F, P, P]),
     "ltu_ffn_fused_trace": (I, [P, L, I, P, P, P, P, P, P, F, P, P, P]),

@@ -19,15 +19,18 @@ step's loss terms agree with the unmodified reference to 1e-3 and every paramete
 (tests/test_train_step_gpu.py, bf16 activations against the reference's fp32 run), and the host logic reproduces all 600
 gradients of oracle autograd to 3e-8 when every kernel wrapper is replaced by an fp64 torch stand-in
 (tests/test_backward_composition_cpu.py).  The ``autograd.Function`` wiring (``unet._NativeTrainFunction``) calls the same
-functions; it is verified with the stand-ins only and therefore still opt-in (``model.native_backward``).  Dropout-free
-(``dropout=0.0``), like every parity test of this repo.
+functions; it is verified with the stand-ins only and therefore still opt-in (``model.native_backward``).  Training-mode dropout (the reference's
+default p = 0.3) is a Philox mask re-generated in the backward (``DropoutState``, ``ltu_dropout``); the parity tests run
+dropout-free, the dropout path has its own statistical and gradient-consistency tests (tests/test_dropout_gpu.py).
 
 The ``nn.Linear`` layers and their weight gradients are plain cuBLAS GEMMs (``F.linear`` / ``torch.mm`` / ``torch.addmm``), as
-in the forward; small tensor glue (concatenation, residual adds, bias-gradient row sums) uses torch ops.  Weights are re-packed
-on every call here (no plan cache yet).  Parameter gradients are returned in fp32 under the reference's parameter names.
+in the forward; small tensor glue (concatenation, residual adds, bias-gradient row sums) uses torch ops.  Packed / transposed
+weights are cached per parameter object and version (``_memo``): an optimizer step re-packs once, nothing is built on the CPU.  Parameter gradients are returned in fp32 under the reference's parameter names.
 """
 from __future__ import annotations
 
+import weakref
+from types import SimpleNamespace
 from typing import Dict, Tuple
 
 import torch
@@ -43,7 +46,83 @@ __all__ = ["encoder_layer_train", "encoder_layer_backward", "transformer_stack_t
            "head_conv_train", "head_conv_backward", "decoder_train", "decoder_backward", "model_loss_and_gradients"]
 
 
+# Derived (packed / transposed / bf16) weights of the training path, keyed on the parameter OBJECTS and their versions: an
+# optimizer step updates a parameter in place (same object, new version -> rebuilt once), a new model is a new object.
+# One slot per (tag, parameters): stale generations are overwritten, not accumulated.
+_PACKS: Dict[tuple, tuple] = {}
+
+
+def _memo(tag, tensors, build):
+    key = (tag,) + tuple(id(t) for t in tensors)
+    ver = tuple(t._version for t in tensors) + tuple(t.data_ptr() for t in tensors)
+    hit = _PACKS.get(key)
+    if hit is not None and hit[0] == ver and all(r() is t for r, t in zip(hit[1], tensors)):
+        return hit[2]
+    val = build()
+    if len(_PACKS) > 4096:
+        _PACKS.clear()
+    _PACKS[key] = (ver, tuple(weakref.ref(t) for t in tensors), val)
+    return val
+
+
+def _conv_pack(conv, **kw):
+    """unet._ConvW of an nn.Conv3d container, cached across training steps."""
+    from .unet import _ConvW
+    ts = [conv.weight] + ([conv.bias] if conv.bias is not None else [])
+    return _memo(("conv",) + tuple(sorted(kw.items())), ts, lambda: _ConvW(conv, True, **kw))
+
+
+class DropoutState:
+    """The dropout stream of ONE training forward (p = the model's `dropout`, 0.3 in the reference): every site draws from
+    Philox4x32-10 keyed by the CUDA generator's seed at consecutive counter offsets (ops.dropout), and remembers its offset
+    in the saved state so that the backward re-applies the identical mask to the gradient.  `finish()` advances torch's
+    CUDA generator past the counters used, so the next forward (and torch's own random ops) draw fresh numbers and
+    `torch.manual_seed` makes a training run reproducible.  The CPU generator is never touched."""
+
+    def __init__(self, p: float = 0.0, device: torch.device = None, seed: int = None, offset: int = 0):
+        self.p = float(p or 0.0)
+        self._gen = None
+        self.seed, self.offset = 0, int(offset)
+        if self.p > 0.0:
+            if not 0.0 < self.p < 1.0:
+                raise ValueError(f"dropout must be in [0, 1), got {p}")
+            if seed is not None:
+                self.seed = int(seed)
+            else:
+                idx = device.index if device.index is not None else torch.cuda.current_device()
+                self._gen = torch.cuda.default_generators[idx]
+                self.seed, self.offset = self._gen.initial_seed(), self._gen.get_offset()
+
+    def apply(self, x: torch.Tensor, channelwise: bool = False):
+        """In-place dropout of a freshly produced activation; returns (x, token for `backward`)."""
+        if self.p == 0.0:
+            return x, None
+        tok = (self.offset, channelwise)
+        ops.dropout(x, self.p, self.seed, self.offset, channelwise, inplace=True)
+        self.offset += ops.dropout_counters(x, channelwise)
+        return x, tok
+
+    def backward(self, dy: torch.Tensor, tok):
+        if tok is None:
+            return dy
+        return ops.dropout(dy.contiguous(), self.p, self.seed, tok[0], tok[1], inplace=False)
+
+    def finish(self) -> None:
+        if self._gen is not None:
+            self._gen.set_offset((self.offset + 3) // 4 * 4)
+
+
+_NO_DROP = DropoutState(0.0)
+
+
 def _params(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
+    # attribute access, not .parameters(): an nn.DataParallel replica keeps its weights as plain attributes
+    mods = list(layer.self_attn.linears) + [layer.linear1, layer.linear2, layer.layer_norm1, layer.layer_norm2]
+    ts = [t for m in mods for t in (m.weight, m.bias)]
+    return _memo(("layer", dtype), ts, lambda: _params_build(layer, dtype))
+
+
+def _params_build(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
     lin = layer.self_attn.linears
     c = lambda t: t.detach().to(dtype).contiguous()
     f = lambda t: t.detach().float().contiguous()
@@ -56,9 +135,11 @@ def _params(layer, dtype: torch.dtype) -> Dict[str, torch.Tensor]:
 
 
 @torch.no_grad()
-def encoder_layer_train(t: torch.Tensor, layer) -> Tuple[torch.Tensor, dict]:
+def encoder_layer_train(t: torch.Tensor, layer, drop: DropoutState = _NO_DROP) -> Tuple[torch.Tensor, dict]:
     """SelfAttentionLayer.forward on tokens [B,N,C] (fp32 or bf16, CUDA), keeping what the backward needs.
-    `layer` is the parameter container lintransunet_b200.unet.SelfAttentionLayer."""
+    `layer` is the parameter container lintransunet_b200.unet.SelfAttentionLayer.  Training-mode dropout (`drop`):
+    dropout1 on the attention output (:205), dropout on the GELU output (:208), dropout2 on linear2's output (:209); the
+    dropout inside linear_attention (:62-63) does not reach its result in the reference and draws nothing here."""
     p = _params(layer, t.dtype)
     B, N, C = t.shape
     h = p["nhead"]
@@ -66,13 +147,14 @@ def encoder_layer_train(t: torch.Tensor, layer) -> Tuple[torch.Tensor, dict]:
     q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
     ctx = ops.kv_reduce(k, v, h)
     att = ops.q_readout(q, ctx, h)
-    o = F.linear(att, p["w_o"], p["b_o"])
+    o, tok_o = drop.apply(F.linear(att, p["w_o"], p["b_o"]))
     t1 = ops.add_layernorm(t, o, p["g1"], p["be1"], 1e-6)
     f1 = F.linear(t1, p["w_1"], p["b_1"])
-    fa = ops.gelu(f1)
-    f2 = F.linear(fa, p["w_2"], p["b_2"])
+    fa, tok_fa = drop.apply(ops.gelu(f1))
+    f2, tok_f2 = drop.apply(F.linear(fa, p["w_2"], p["b_2"]))
     t2 = ops.add_layernorm(t1, f2, p["g2"], p["be2"], 1e-6)
-    return t2, dict(p=p, t=t, qkv=qkv, ctx=ctx, att=att, o=o, t1=t1, f1=f1, fa=fa, f2=f2)
+    return t2, dict(p=p, t=t, qkv=qkv, ctx=ctx, att=att, o=o, t1=t1, f1=f1, fa=fa, f2=f2, drop=drop,
+                    toks=(tok_o, tok_fa, tok_f2))
 
 
 def _wgrad(dy2: torch.Tensor, x2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -90,17 +172,21 @@ def encoder_layer_backward(dout: torch.Tensor, saved: dict) -> Tuple[torch.Tenso
     rows = B * N
     g: Dict[str, torch.Tensor] = {}
     two = lambda a: a.reshape(rows, a.shape[-1])
-    # y = LN2(t1 + f2)
+    drop = saved.get("drop", _NO_DROP)
+    tok_o, tok_fa, tok_f2 = saved.get("toks", (None, None, None))
+    # y = LN2(t1 + dropout2(f2));  saved f2 / fa / o are the tensors AFTER their dropout
     dz2, g["layer_norm2.weight"], g["layer_norm2.bias"] = ops.add_layernorm_bwd(t1, saved["f2"], dout.contiguous(), p["g2"], 1e-6)
-    g["linear2.weight"], g["linear2.bias"] = _wgrad(two(dz2), two(saved["fa"]))
-    dfa = torch.mm(two(dz2), p["w_2"]).reshape(B, N, 2 * C)
+    df2 = drop.backward(dz2, tok_f2)
+    g["linear2.weight"], g["linear2.bias"] = _wgrad(two(df2), two(saved["fa"]))
+    dfa = drop.backward(torch.mm(two(df2), p["w_2"]).reshape(B, N, 2 * C), tok_fa)
     df1 = ops.gelu_bwd(saved["f1"], dfa)
     g["linear1.weight"], g["linear1.bias"] = _wgrad(two(df1), two(t1))
     dt1 = torch.addmm(two(dz2), two(df1), p["w_1"]).reshape(B, N, C)            # residual + through linear1
-    # t1 = LN1(t + o)
+    # t1 = LN1(t + dropout1(o))
     dz1, g["layer_norm1.weight"], g["layer_norm1.bias"] = ops.add_layernorm_bwd(t, saved["o"], dt1, p["g1"], 1e-6)
-    g["self_attn.linears.3.weight"], g["self_attn.linears.3.bias"] = _wgrad(two(dz1), two(saved["att"]))
-    datt = torch.mm(two(dz1), p["w_o"]).reshape(B, N, C)
+    do = drop.backward(dz1, tok_o)
+    g["self_attn.linears.3.weight"], g["self_attn.linears.3.bias"] = _wgrad(two(do), two(saved["att"]))
+    datt = torch.mm(two(do), p["w_o"]).reshape(B, N, C)
     qkv = saved["qkv"]
     dqkv = ops.linear_attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], saved["ctx"], datt, h)
     dw, db = _wgrad(two(dqkv), two(t))
@@ -112,7 +198,7 @@ def encoder_layer_backward(dout: torch.Tensor, saved: dict) -> Tuple[torch.Tenso
 
 
 @torch.no_grad()
-def transformer_stack_train(x: torch.Tensor, layers, pos_encoder) -> Tuple[torch.Tensor, dict]:
+def transformer_stack_train(x: torch.Tensor, layers, pos_encoder, drop: DropoutState = _NO_DROP) -> Tuple[torch.Tensor, dict]:
     """The 8-layer stack of PosAttention3DBlock / EmbedAttention3DBlock (model/Unet_3Dblock.py:265-270, :484-490) on
     a channels-last volume [B,H,W,D,C]: positional depthwise conv once, after layer 0.  `layers` = the ModuleList of
     SelfAttentionLayer containers, `pos_encoder` = the Conv3dPosEmbedding container that is actually used."""
@@ -120,14 +206,16 @@ def transformer_stack_train(x: torch.Tensor, layers, pos_encoder) -> Tuple[torch
     B, H, W, D, C = x.shape
     w27, pb = _pos_w(pos_encoder)
     t = x.reshape(B, H * W * D, C)
-    saved_layers, pos_in = [], None
+    saved_layers, pos_in, tok_pos = [], None, None
     for i, layer in enumerate(layers):
-        t, sv = encoder_layer_train(t, layer)
+        t, sv = encoder_layer_train(t, layer, drop)
         saved_layers.append(sv)
         if i == 0:
             pos_in = t.reshape(B, H, W, D, C)
-            t = ops.posenc_dwconv3(pos_in, w27, pb).reshape(B, H * W * D, C)
-    return t.reshape(B, H, W, D, C), dict(layers=saved_layers, pos_in=pos_in, w27=w27, shape=(B, H, W, D, C))
+            t, tok_pos = drop.apply(ops.posenc_dwconv3(pos_in, w27, pb), channelwise=True)     # nn.Dropout3d, trans_block.py:96
+            t = t.reshape(B, H * W * D, C)
+    return t.reshape(B, H, W, D, C), dict(layers=saved_layers, pos_in=pos_in, w27=w27, shape=(B, H, W, D, C), drop=drop,
+                                          tok_pos=tok_pos)
 
 
 @torch.no_grad()
@@ -139,6 +227,7 @@ def transformer_stack_backward(dout: torch.Tensor, saved: dict) -> Tuple[torch.T
     dt = dout.reshape(B, H * W * D, C).contiguous()
     for i in range(len(saved["layers"]) - 1, -1, -1):
         if i == 0:
+            dt = saved.get("drop", _NO_DROP).backward(dt.reshape(B, H, W, D, C), saved.get("tok_pos"))
             dvol, dw27, db = ops.posenc_dwconv3_bwd(saved["pos_in"], dt.reshape(B, H, W, D, C), saved["w27"])
             # packed [kh,kw,kd][c] = weight[c,0,kd,kh,kw] (unet._pos_w)
             grads["pos.proj.weight"] = dw27.reshape(3, 3, 3, C).permute(3, 2, 0, 1).unsqueeze(1).contiguous()
@@ -158,7 +247,7 @@ def conv3d_backward(x: torch.Tensor, dy: torch.Tensor, conv: torch.nn.Conv3d, ne
     the filter reversed and its channel axes swapped -- after zero insertion for a strided convolution, followed by
     2x2x2 block sums for up2."""
     from .unet import _ConvW
-    k = conv.kernel_size[0]
+    k = conv.weight.shape[2]
     stride = tuple(conv.stride)
     pad = k // 2
     cout, cin = conv.weight.shape[0], conv.weight.shape[1]
@@ -167,9 +256,9 @@ def conv3d_backward(x: torch.Tensor, dy: torch.Tensor, conv: torch.nn.Conv3d, ne
     db = torch.sum(dy.reshape(-1, cout), 0, dtype=torch.float32)
     dx = None
     if need_dx:
-        t = torch.nn.Conv3d(cout, cin, k, padding=pad, bias=False).to(conv.weight.device)
-        t.weight.copy_(conv.weight.detach().flip(2, 3, 4).transpose(0, 1))
-        cw = _ConvW(t, True)
+        # transposed filter built on the device from the weight itself: no module construction, no RNG, no H2D copy
+        cw = _memo(("convT",), [conv.weight], lambda: _ConvW(SimpleNamespace(
+            weight=conv.weight.detach().flip(2, 3, 4).transpose(0, 1).contiguous(), bias=None, stride=(1, 1, 1)), True))
         e = 2 if up2 else 1
         full = (e * x.shape[1], e * x.shape[2], e * x.shape[3])          # extent the convolution actually read
         z = dy if stride == (1, 1, 1) else ops.zero_insert(dy, full, stride)
@@ -181,30 +270,33 @@ def conv3d_backward(x: torch.Tensor, dy: torch.Tensor, conv: torch.nn.Conv3d, ne
 
 # ----------------------------------------------------------------------------- conv blocks (bf16 path)
 @torch.no_grad()
-def conv_in_act_train(x: torch.Tensor, conv: torch.nn.Conv3d, residual=None, cin_pad: int = 0, up2: bool = False):
+def conv_in_act_train(x: torch.Tensor, conv: torch.nn.Conv3d, residual=None, cin_pad: int = 0, up2: bool = False,
+                      drop: DropoutState = _NO_DROP):
     """Conv3d -> InstanceNorm3d -> LeakyReLU (+ residual) keeping the raw convolution output and the statistics
     (DownBlock / UpBlock / Encoder stem / embed blocks, model/Unet_3Dblock.py:325-336,:547-554,:596-600,:373-382,
-    :419-429).  `up2`: nn.Upsample(nearest, x2) in front of the convolution (UpEmbedBlock).  bf16, channels-last."""
-    from .unet import _ConvW
-    cw = _ConvW(conv, True, cin_pad=cin_pad, fold_up2=up2)
+    :419-429).  `up2`: nn.Upsample(nearest, x2) in front of the convolution (UpEmbedBlock).  `drop`: the nn.Dropout that
+    follows the activation in DownBlock.conv2 (:339), the embed blocks (:382,:429) and UpBlock.conv2 (:556).  bf16,
+    channels-last."""
+    cw = _conv_pack(conv, cin_pad=cin_pad, fold_up2=up2)
     stride = tuple(conv.stride)
     raw, partials, _ = ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, stride=stride, pad=cw.k // 2, up2=up2, want_stats=True,
                                   w_tc=cw.w_tc, w_tc_fold=cw.w_tc_fold)
     V = raw.shape[1] * raw.shape[2] * raw.shape[3]
     stats = ops.instnorm_finalize(partials, V)
-    y = ops.instnorm_apply(raw, stats, ops.ACT_LRELU, residual=residual, inplace=False)
-    return y, dict(x=x, raw=raw, stats=stats, conv=conv, residual=residual is not None, up2=up2)
+    y, tok = drop.apply(ops.instnorm_apply(raw, stats, ops.ACT_LRELU, residual=residual, inplace=False))
+    return y, dict(x=x, raw=raw, stats=stats, conv=conv, residual=residual is not None, up2=up2, drop=drop, tok=tok)
 
 
 @torch.no_grad()
 def conv_in_act_backward(dy: torch.Tensor, saved: dict, need_dx: bool = True):
     """Returns (dx | None, dW, dbias); a residual added after the activation receives dy itself (the caller adds it)."""
+    dy = saved.get("drop", _NO_DROP).backward(dy, saved.get("tok"))
     draw = ops.instnorm_bwd(saved["raw"], saved["stats"], dy.contiguous(), ops.ACT_LRELU)
     return conv3d_backward(saved["x"], draw, saved["conv"], need_dx=need_dx, up2=saved.get("up2", False))
 
 
 @torch.no_grad()
-def encoder_train(x: torch.Tensor, enc):
+def encoder_train(x: torch.Tensor, enc, drop: DropoutState = _NO_DROP):
     """Encoder.forward (model/Unet_3Dblock.py:596-607) on the bf16 path with everything the backward needs.
     x fp32 [B,1,H,W,D]; `enc` = the lintransunet_b200.unet.Encoder container.  Returns (bottleneck, skips, saved)."""
     a = ops.s2d_input(x.contiguous().float(), _ACT, cpad=8)                    # 4 channels + 4 zero channels
@@ -213,7 +305,7 @@ def encoder_train(x: torch.Tensor, enc):
     for blk in enc.block_list:
         s, sv1 = conv_in_act_train(a, blk.conv1, residual=a)                  # DownBlock :327-331
         skips.append(s)
-        a, sv2 = conv_in_act_train(s, blk.conv2)                              # :335-336 (strided)
+        a, sv2 = conv_in_act_train(s, blk.conv2, drop=drop)                   # :335-339 (strided; dropout on x, not on the skip)
         blocks.append((sv1, sv2))
     return a, skips, dict(stem=sv_stem, blocks=blocks)
 
@@ -238,13 +330,13 @@ def encoder_backward(d_bottle: torch.Tensor, d_skips, saved: dict) -> Dict[str, 
 
 
 @torch.no_grad()
-def embed_block_train(x: torch.Tensor, blk):
+def embed_block_train(x: torch.Tensor, blk, drop: DropoutState = _NO_DROP):
     """EmbedAttention3DBlock.forward (model/Unet_3Dblock.py:469-501), the inside of a ROI bridge: stride-2 down_embed
     conv + IN + LeakyReLU -> 8 encoder layers with the positional conv -> nearest x2 + up_embed conv + IN + LeakyReLU.
     x bf16 [B,h,w,d,in_dim]; `blk` = lintransunet_b200.unet.EmbedAttention3DBlock."""
-    t, sv_down = conv_in_act_train(x, blk.down_embed.conv)
-    t, sv_stack = transformer_stack_train(t, blk.layers, blk.pos_encoder)
-    y, sv_up = conv_in_act_train(t, blk.up_embed.conv, up2=True)
+    t, sv_down = conv_in_act_train(x, blk.down_embed.conv, drop=drop)
+    t, sv_stack = transformer_stack_train(t, blk.layers, blk.pos_encoder, drop)
+    y, sv_up = conv_in_act_train(t, blk.up_embed.conv, up2=True, drop=drop)
     return y, dict(down=sv_down, stack=sv_stack, up=sv_up)
 
 
@@ -261,12 +353,12 @@ def embed_block_backward(dy: torch.Tensor, saved: dict):
 
 
 @torch.no_grad()
-def upblock_train(x: torch.Tensor, skip: torch.Tensor, blk):
+def upblock_train(x: torch.Tensor, skip: torch.Tensor, blk, drop: DropoutState = _NO_DROP):
     """UpBlock.forward (model/Unet_3Dblock.py:540-557): conv1 + IN + LeakyReLU, concatenation with the (gated, bridged)
     skip, conv2 + IN + LeakyReLU.  The training path materialises the concatenation (its gradient is a split)."""
     x1, sv1 = conv_in_act_train(x, blk.conv1)
     cat = torch.cat([x1, skip], -1)
-    y, sv2 = conv_in_act_train(cat, blk.conv2)
+    y, sv2 = conv_in_act_train(cat, blk.conv2, drop=drop)                     # dropout after the second activation (:555-556)
     return y, dict(c1=sv1, c2=sv2, split=x1.shape[-1])
 
 
@@ -284,14 +376,14 @@ def upblock_backward(dy: torch.Tensor, saved: dict):
 def gate_train(skip: torch.Tensor, up: torch.Tensor, att):
     """SpatialAttention3DBlock + `encoded * attn` (model/Unet_3Dblock.py:217-221,:1385): skip [B,h,w,d,C],
     up [B,h,w,d,Cg] (the upsampled decoder state), `att` = lintransunet_b200.unet.SpatialAttention3DBlock."""
-    from .unet import _ConvW
-    wx, wg = _ConvW(att.W_x[0], True), _ConvW(att.W_g[0], True)
+    wx, wg = _conv_pack(att.W_x[0]), _conv_pack(att.W_g[0])
     ga, pa, _ = ops.conv3d(skip, wx.w, wx.b, wx.cout, 1, pad=0, want_stats=True, w_tc=wx.w_tc)
     gg, pg, _ = ops.conv3d(up, wg.w, wg.b, wg.cout, 1, pad=0, want_stats=True, w_tc=wg.w_tc)
     V = skip.shape[1] * skip.shape[2] * skip.shape[3]
     sa, sg = ops.instnorm_finalize(pa, V), ops.instnorm_finalize(pg, V)
-    psi_w = att.psi[0].weight.detach().reshape(-1).float().contiguous()
-    psi_b = att.psi[0].bias.detach().float().contiguous()
+    psi_w, psi_b = _memo(("psi",), [att.psi[0].weight, att.psi[0].bias],
+                         lambda: (att.psi[0].weight.detach().reshape(-1).float().contiguous(),
+                                  att.psi[0].bias.detach().float().contiguous()))
     out = ops.gate_fused(ga, sa, gg, sg, psi_w, psi_b, skip)
     return out, dict(skip=skip, up=up, ga=ga, gg=gg, sa=sa, sg=sg, psi_w=psi_w, psi_b=psi_b, att=att)
 
@@ -313,7 +405,7 @@ def gate_backward(dout: torch.Tensor, saved: dict):
 
 
 @torch.no_grad()
-def roi_bridge_train(skip: torch.Tensor, fg: torch.Tensor, bridge, box: torch.Tensor = None):
+def roi_bridge_train(skip: torch.Tensor, fg: torch.Tensor, bridge, box: torch.Tensor = None, drop: DropoutState = _NO_DROP):
     """ROIBridge.forward (model/Unet_3Dblock.py:717-755): box from the foreground probability (not differentiated, as in
     the reference where it comes out of searchsorted), fisheye resample into the ROI, EmbedAttention3DBlock, resample
     back.  skip bf16 [B,h,w,d,C], fg fp32 [B,h,w,d]; `bridge` = lintransunet_b200.unet.ROIBridge."""
@@ -322,7 +414,7 @@ def roi_bridge_train(skip: torch.Tensor, fg: torch.Tensor, bridge, box: torch.Te
         box = ops.roi_bbox(fg, bridge.min_h_roi, bridge.min_w_roi, bridge.mask_threshold)
     geo = (bridge.h_roi_size, bridge.w_roi_size, bridge.eval_h_roi_size, bridge.eval_w_roi_size)
     roi = ops.roi_resample(skip, box, (h, w), *geo, direction=0)
-    t, sv = embed_block_train(roi, bridge.transformer)
+    t, sv = embed_block_train(roi, bridge.transformer, drop)
     out = ops.roi_resample(t, box, (h, w), *geo, direction=1)
     return out, dict(box=box, geo=geo, hw=(h, w), block=sv)
 
@@ -341,8 +433,7 @@ def roi_bridge_backward(dout: torch.Tensor, saved: dict):
 @torch.no_grad()
 def head_conv_train(x: torch.Tensor, conv: torch.nn.Conv3d):
     """A 3x3x3 convolution with fp32 logits and few output channels (mask heads :1380, final_block :1392)."""
-    from .unet import _ConvW
-    cw = _ConvW(conv, True)
+    cw = _conv_pack(conv)
     logits = ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, pad=1, out_f32=True, w_tc=cw.w_tc)[0]
     return logits, dict(x=x, conv=conv)
 
@@ -352,26 +443,28 @@ def head_conv_backward(dlogits: torch.Tensor, saved: dict):
     """dlogits fp32 [B,h,w,d,Cout] -> (dx bf16, dW [Cout,Cin,3,3,3] fp32, dbias fp32).  The gradient is rounded to bf16 and
     zero-padded to a multiple of 8 channels (16-byte vectors of ltu_conv3d_wgrad); the padded filter rows are zero."""
     conv = saved["conv"]
-    cout, cin, k = conv.weight.shape[0], conv.weight.shape[1], conv.kernel_size[0]
+    cout, cin, k = conv.weight.shape[0], conv.weight.shape[1], conv.weight.shape[2]
     cp = (cout + 7) // 8 * 8
     dy = torch.zeros(*dlogits.shape[:-1], cp, dtype=_ACT, device=dlogits.device)
     dy[..., :cout] = dlogits.to(_ACT)
-    padded = torch.nn.Conv3d(cin, cp, k, padding=k // 2).to(conv.weight.device)
-    padded.weight.zero_()
-    padded.bias.zero_()
-    padded.weight[:cout].copy_(conv.weight.detach())
+
+    def build_padded():
+        w = conv.weight.detach().new_zeros(cp, cin, k, k, k)
+        w[:cout].copy_(conv.weight.detach())
+        return SimpleNamespace(weight=w, bias=None, stride=(1, 1, 1))
+    padded = _memo(("head_pad",), [conv.weight], build_padded)
     dx, dw, db = conv3d_backward(saved["x"], dy, padded)
     return dx, dw[:cout].contiguous(), db[:cout].contiguous()
 
 
 @torch.no_grad()
-def decoder_train(bottle: torch.Tensor, skips, dec, dim_output: int):
+def decoder_train(bottle: torch.Tensor, skips, dec, dim_output: int, drop: DropoutState = _NO_DROP):
     """ROIDecoder.forward (model/Unet_3Dblock.py:1359-1396) in training mode: returns (probs fp32 [B,C,H,W,D], mask_list,
     saved).  `dec` = lintransunet_b200.unet.ROIDecoder; bottle / skips from encoder_train."""
     from .unet import ROIBridge
     n = len(dec.num_layers)
     tr = dec.bridge_list[n - 1].transformer
-    x, sv_bottle = transformer_stack_train(bottle, tr.layers, tr.pos_encoders[0])
+    x, sv_bottle = transformer_stack_train(bottle, tr.layers, tr.pos_encoders[0], drop)
     levels, mask_list = [], []
     for i in range(1, n):
         fd = 2 if (n - i) % 2 == 0 else 1                                     # :1375-1378
@@ -383,8 +476,8 @@ def decoder_train(bottle: torch.Tensor, skips, dec, dim_output: int):
         skip, sv_g = gate_train(skips[-i], xu, dec.att_conv_list[lvl])         # :1384-1385
         bridge, sv_b = dec.bridge_list[lvl], None
         if isinstance(bridge, ROIBridge):
-            skip, sv_b = roi_bridge_train(skip, fg, bridge)                    # :1387-1388
-        x, sv_u = upblock_train(xu, skip, dec.block_list[i - 1])
+            skip, sv_b = roi_bridge_train(skip, fg, bridge, drop=drop)         # :1387-1388
+        x, sv_u = upblock_train(xu, skip, dec.block_list[i - 1], drop)
         levels.append(dict(fd=fd, lvl=lvl, logits=logits, m=sv_m, g=sv_g, b=sv_b, u=sv_u))
     logits, sv_f = head_conv_train(x, dec.final_block)                         # :1392
     probs = ops.head_d2s_softmax(logits, dim_output, want_probs=True, want_onehot=False, want_labels=False)[0]
@@ -425,14 +518,16 @@ def decoder_backward(dprobs: torch.Tensor, dmask_list, saved: dict):
     return d_bottle, d_skips, grads
 
 
-def model_loss_and_gradients(model, x: torch.Tensor, masks: torch.Tensor):
-    """One training step's loss and parameter gradients of a binary MaskTransUnet (dropout-free) on the bf16 path:
+def model_loss_and_gradients(model, x: torch.Tensor, masks: torch.Tensor, drop: DropoutState = _NO_DROP):
+    """One training step's loss and parameter gradients of a binary MaskTransUnet on the bf16 path (dropout-free unless a
+    DropoutState is passed):
     encoder_train -> decoder_train -> lintransunet_b200.losses.deep_supervision_loss (torch autograd on the outputs only)
     -> decoder_backward -> encoder_backward.  Returns (total, terms, grads keyed like model.state_dict())."""
     from . import losses
     with torch.no_grad():
-        bottle, skips, sv_e = encoder_train(x, model.encode)
-        probs, mask_list, sv_d = decoder_train(bottle, skips, model.decode, model.dim_output)
+        bottle, skips, sv_e = encoder_train(x, model.encode, drop)
+        probs, mask_list, sv_d = decoder_train(bottle, skips, model.decode, model.dim_output, drop)
+        drop.finish()
     p = probs.detach().requires_grad_(True)
     ms = [m.detach().requires_grad_(True) for m in mask_list]
     with torch.enable_grad():

@@ -63,8 +63,9 @@ struct T3Tail {
     float sred[8][128][2];
 };
 
+template <bool kMasked>
 __global__ void __launch_bounds__(kT3Threads, 1)
-conv3d_tc3_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
+conv3d_tc3_kernel_t(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
                   const __grid_constant__ CUtensorMap tm_w, const T3Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -137,7 +138,7 @@ conv3d_tc3_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_const
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         const uint32_t idesc = umma_idesc_bf16(128, p.N);
-        const int first_ks = __ffs((int)p.ksmask[0]) - 1;                           // first issued MMA of an item overwrites
+        const int first_ks = kMasked ? __ffs((int)p.ksmask[0]) - 1 : 0;             // first issued MMA of an item overwrites
         uint32_t nb = 0, nh = 0, it = 0;
         for (int i = 0; i < n_my; ++i)
         for (int pass = 0; pass < p.npass; ++pass, ++it) {
@@ -165,7 +166,7 @@ conv3d_tc3_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_const
                             }
                             auto pick = [&](int ax) { return ax == 0 ? k[0] : (ax == 1 ? k[1] : k[2]); };
                             const int row0 = (pick(p.axT) * 18 + pick(p.ax16)) * 10 + pick(p.ax8);
-                            const uint32_t kmask = p.ksmask[t];
+                            const uint32_t kmask = kMasked ? p.ksmask[t] : 0xFu;
                             const uint64_t bdesc = make_desc(sbase + p.off_b + s * b_bytes);
 #pragma unroll
                             for (int v = 0; v < 4; ++v) {
@@ -177,9 +178,13 @@ conv3d_tc3_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_const
                                 const uint32_t tacc = acc_base + (uint32_t)((zl * p.TH + v) * p.N);
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
-                                    if (!((kmask >> ks) & 1u)) continue;
-                                    umma_bf16_elect(tacc, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc,
-                                                    (uint32_t)((j | t) != 0 || ks != first_ks));
+                                    if (kMasked) {      // super-voxel form only: the plain kernel keeps its branch-free issue loop
+                                        if (!((kmask >> ks) & 1u)) continue;
+                                        umma_bf16_elect(tacc, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc,
+                                                        (uint32_t)((j | t) != 0 || ks != first_ks));
+                                    } else {
+                                        umma_bf16_elect(tacc, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, (j | t | ks) != 0);
+                                    }
                                 }
                             }
                             umma_commit_elect(smem_u32(&tail->b_empty[s]));
@@ -483,12 +488,14 @@ static int conv3d_tc3_impl(const void* in0, int C0, const void* in1, int C1, int
     static thread_local int configured_dev = -1;
     int dev; cudaGetDevice(&dev);
     if (configured_dev != dev) {
-        cudaFuncSetAttribute(conv3d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv3d_tc3_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv3d_tc3_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured_dev = dev;
     }
     int grid = sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;
-    conv3d_tc3_kernel<<<grid, kT3Threads, smem, (cudaStream_t)stream>>>(t0, t1, tw, p);
+    if (ks_mask) conv3d_tc3_kernel_t<true><<<grid, kT3Threads, smem, (cudaStream_t)stream>>>(t0, t1, tw, p);
+    else conv3d_tc3_kernel_t<false><<<grid, kT3Threads, smem, (cudaStream_t)stream>>>(t0, t1, tw, p);
     LTU_LAUNCH_CHECK("conv3d_tc3");
     count_launch(1);
     return LTU_OK;

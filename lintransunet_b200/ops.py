@@ -244,6 +244,25 @@ def gelu_(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int, channelwise: bool = False, inplace: bool = False) -> torch.Tensor:
+    """Training-mode nn.Dropout (or nn.Dropout3d: `channelwise`, one draw per sample and channel) on a channels-last
+    tensor [B, ..., C]: keep decisions are a pure function of (seed, offset, index), so the backward is the same call on
+    the gradient.  Consumes `dropout_counters(x, channelwise)` Philox counters from `offset` (include/ltu_b200.h)."""
+    dev = _chk(x)
+    y = x if inplace else torch.empty_like(x)
+    C = x.shape[-1]
+    per_sample = x.numel() // x.shape[0]
+    with _Guard(dev, ("dropout", 2 * x.numel() * x.element_size(), 0)) as st:
+        check(_native.lib().ltu_dropout(_p(x), _p(y), x.numel(), C, per_sample, float(p), int(seed) & (2 ** 64 - 1),
+                                        int(offset) & (2 ** 64 - 1), int(channelwise), _dt(x), st), "ltu_dropout")
+    return y
+
+
+def dropout_counters(x: torch.Tensor, channelwise: bool = False) -> int:
+    n = x.shape[0] * x.shape[-1] if channelwise else x.numel()
+    return (n + 3) // 4
+
+
 def posenc_dwconv3(x: torch.Tensor, w27c: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """x + depthwise 3x3x3 conv(x) + bias on [B,H,W,D,C] (model/trans_block.py:86-96)."""
     dev = _chk(x, w27c, bias)
@@ -339,7 +358,9 @@ def sv_pack(w: torch.Tensor, bias: Optional[torch.Tensor], n_main: int, n_aux: i
     return SVPack(out.contiguous(), b, bytes(mask), g, n_main, n_aux, ci, n_inputs)
 
 
-USE_SV_CONV = os.environ.get("LTU_DISABLE_SV", "0") != "1"         # A/B switch for the super-voxel form
+# Super-voxel form: measured SLOWER than conv3d_halo inside the step (r2_bench3: 54 ms for 133 launches vs 47 ms for the 190
+# launches of the mma.sync kernel; the block-Toeplitz weights execute 3-4x the useful flops) -> opt-in, LTU_SV=1
+USE_SV_CONV = os.environ.get("LTU_SV", "0") == "1"
 
 
 def _conv3d_sv(x0, x1, sv: SVPack, want_stats: bool):
@@ -844,6 +865,35 @@ def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
                                   c_void_p(bias.data_ptr() + n0 * 4), n, c_void_p(y.data_ptr() + n0 * 2), cout, epi,
                                   _p(residual), _p(gamma), _p(beta), eps, st), "ltu_linear_tc")
     return y
+
+
+def linear_fused_supported(k: int, n: int) -> bool:
+    """Shapes ltu_linear_fused takes (the encoder layers with d_model 256, the K/V projection of d_model 128)."""
+    return k % 64 == 0 and 64 <= k <= 1024 and n in (256, 512, 768)
+
+
+def linear_fused(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epi: int = EPI_BIAS,
+                 res_hi: Optional[torch.Tensor] = None, res_lo: Optional[torch.Tensor] = None,
+                 gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, eps: float = 1e-6,
+                 want_lo: bool = True):
+    """nn.Linear on bf16 tokens [..., K] with a fused epilogue, one persistent TMA + tcgen05 launch (csrc/linear_tma.cu):
+    EPI_BIAS -> x W^T + b; EPI_GELU -> gelu(x W^T + b); EPI_RES_LN -> LayerNorm(x W^T + b + res_hi + res_lo) returned as the
+    split pair (y_hi, y_lo) (y_lo None unless want_lo).  w: the nn.Linear weight [N, K] in bf16, bias / gamma / beta fp32."""
+    dev = _chk(x, w, bias, res_hi, res_lo, gamma, beta)
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise TypeError("linear_fused needs bf16 activations and bf16 weights")
+    n, k = w.shape
+    if x.shape[-1] != k:
+        raise ValueError(f"linear_fused: x has {x.shape[-1]} columns, the weight expects {k}")
+    rows = x.numel() // k
+    y = torch.empty(*x.shape[:-1], n, dtype=torch.bfloat16, device=dev)
+    y_lo = torch.empty_like(y) if (epi == EPI_RES_LN and want_lo) else None
+    nres = 0 if res_hi is None else (1 if res_lo is None else 2)
+    nbytes = (x.numel() + y.numel() * (2 if y_lo is not None else 1) + nres * rows * n) * 2
+    with _Guard(dev, ("linear_fused", nbytes, 2 * rows * k * n)) as st:
+        check(_native.lib().ltu_linear_fused(_p(x), rows, k, _p(w), _p(bias), n, epi, _p(res_hi), _p(res_lo), _p(gamma),
+                                             _p(beta), eps, _p(y), _p(y_lo), st), "ltu_linear_fused")
+    return (y, y_lo) if epi == EPI_RES_LN else y
 
 
 def ffn_fused_supported(c: int) -> bool:

@@ -285,6 +285,16 @@ class _LayerW:
         self.g1, self.be1 = f(layer.layer_norm1.weight), f(layer.layer_norm1.bias)
         self.g2, self.be2 = f(layer.layer_norm2.weight), f(layer.layer_norm2.bias)
         self.nhead = layer.self_attn.nhead
+        # TMA + tcgen05 Linear layers with fused epilogues (ltu_linear_fused): d_model 256 -> every Linear of the layer;
+        # d_model 128 -> the K/V projection.  The weights are the nn.Linear matrices themselves (bf16), biases fp32.
+        d = layer.linear1.in_features
+        self.lin = self.fused and d == 256 and ops.linear_fused_supported(d, 3 * d)
+        if self.lin:
+            self.bqkv_f32, self.bo_f32 = f(self.b_qkv), f(lin[3].bias)
+            self.b1_f32, self.b2_f32 = f(layer.linear1.bias), f(layer.linear2.bias)
+        self.lin_kv = self.attn_fused and ops.linear_fused_supported(d, 2 * d)
+        if self.lin_kv:
+            self.bkv_f32 = f(self.b_kv)
 
 
 def _pos_w(pe: Conv3dPosEmbedding):
@@ -356,15 +366,18 @@ class _NativeTrainFunction(torch.autograd.Function):
     """``(probs, *mask_list) = f(x, *parameters)`` with the native forward (training mode) and the native backward of
     lintransunet_b200/backward.py, so that ``loss.backward()`` of the reference's train step
     (utils/utils_3D_embed_full.py:63-91) fills ``p.grad`` of every parameter.  bf16 activations, fp32 gradients.
-    The functions it calls reproduce the reference's gradients on B200 (tests/test_train_step_gpu.py); this wrapper itself is
-    verified on the CPU with stand-in kernels only (tests/test_backward_composition_cpu.py) and therefore opt-in
-    (``model.native_backward`` / LTU_NATIVE_BACKWARD=1)."""
+    The functions it calls reproduce the reference's gradients on B200 (tests/test_train_step_gpu.py); the wrapper is
+    checked against them on the GPU (tests/test_train_step_gpu.py::test_autograd_wiring_fills_param_grads) and with fp64
+    stand-in kernels on the CPU (tests/test_backward_composition_cpu.py).  Training-mode dropout: one
+    backward.DropoutState per forward, masks re-generated in the backward."""
 
     @staticmethod
     def forward(ctx, model, x, *params):
         from . import backward as BW
-        bottle, skips, sv_e = BW.encoder_train(x, model.encode)
-        probs, mask_list, sv_d = BW.decoder_train(bottle, skips, model.decode, model.dim_output)
+        drop = BW.DropoutState(model.dropout, x.device)
+        bottle, skips, sv_e = BW.encoder_train(x, model.encode, drop)
+        probs, mask_list, sv_d = BW.decoder_train(bottle, skips, model.decode, model.dim_output, drop)
+        drop.finish()
         ctx.saved_state = (sv_e, sv_d)
         ctx.names = [n for n, _ in _named_weights(model)]
         ctx.dtypes = [p.dtype for p in params]
@@ -436,11 +449,22 @@ class MaskTransUnet(nn.Module):
         # bf16 words (hi + lo): the bf16 rounding of the LayerNorm outputs is the largest single term of the bf16
         # path's error (4.6e-2 -> 3.5e-2 on the 64x64x16 case); the reference keeps it in fp32.
         self.split_token_stream = os.environ.get("LTU_SPLIT_STREAM", "1") == "1"
-        # training with autograd through the native backward (bf16 path, dropout 0): opt-in until it has run on a GPU
-        self.native_backward = os.environ.get("LTU_NATIVE_BACKWARD", "0") == "1"
+        # bf16 path: the nn.Linear layers of the d_model-256 encoder layers (and bridge 1's K/V projection) on the native
+        # TMA + tcgen05 GEMM with fused epilogues instead of cuBLAS + gelu + add_layernorm.  LTU_NATIVE_LINEAR=0 = A/B.
+        self.use_native_linear = os.environ.get("LTU_NATIVE_LINEAR", "1") == "1"
+        # training: autograd through the native backward (bf16 path; loss.backward() fills p.grad).  LTU_NATIVE_BACKWARD=0
+        # turns a training forward with grad into an error instead (there is no other backward).
+        self.native_backward = os.environ.get("LTU_NATIVE_BACKWARD", "1") == "1"
         self.max_cached_graphs = 6                    # one graph (+ private memory pool) per input shape and head, LRU
         self._plans: Dict[tuple, tuple] = {}
         self._graphs: Dict[tuple, dict] = {}
+
+    # -- pickling (the reference saves whole modules: torch.save(model, ...), train3D.py:291) ------------------------------
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_plans"], state["_graphs"] = {}, {}        # derived weights and CUDA graphs are rebuilt on first use
+        state["record"], state["forced_boxes"] = None, None
+        return state
 
     # -- derived-weight cache ------------------------------------------------------------
     def _plan(self, device: torch.device, dtype: torch.dtype) -> _Plan:
@@ -490,7 +514,7 @@ class MaskTransUnet(nn.Module):
     def _knobs(self) -> tuple:
         """Every runtime switch that changes the launched kernels (part of the CUDA-graph cache key)."""
         return (self.use_tensor_cores, self.use_fused_linear, self.fuse_mask_head, self.use_fused_ffn, self.use_fused_attn,
-                self.split_token_stream, ops.USE_HALO_CONV, ops.USE_TC3_CONV)
+                self.split_token_stream, self.use_native_linear, ops.USE_HALO_CONV, ops.USE_TC3_CONV, ops.USE_SV_CONV)
 
     def _capture(self, x: torch.Tensor, plan: "_Plan", head: str) -> dict:
         static_x = x.clone()
@@ -534,7 +558,10 @@ class MaskTransUnet(nn.Module):
         if lw.attn_fused and self.use_fused_attn and not (lw.fused and self.use_fused_linear):
             # K/V projection (cuBLAS) -> kv_reduce -> ONE kernel for Q projection, readout, output projection,
             # residual and LayerNorm1; then ONE kernel for the feed-forward half
-            kv = F.linear(t, lw.w_kv, lw.b_kv)
+            if lw.lin_kv and self.use_native_linear:
+                kv = ops.linear_fused(t, lw.w_kv, lw.bkv_f32)
+            else:
+                kv = F.linear(t, lw.w_kv, lw.b_kv)
             ctx = ops.kv_reduce(kv[..., :C], kv[..., C:], lw.nhead)
             t = ops.attn_out_fused(t, lw.w_q, lw.bq_f32, ops.ctx_pack(ctx), lw.w_o, lw.bo_f32, lw.g1, lw.be1, lw.nhead)
             if lw.ffn and self.use_fused_ffn:
@@ -542,6 +569,15 @@ class MaskTransUnet(nn.Module):
             f = ops.gelu_(F.linear(t, lw.w_1, lw.b_1))
             f = F.linear(f, lw.w_2, lw.b_2)
             return ops.add_layernorm(t, f, lw.g2, lw.be2, 1e-6), None
+        if lw.lin and self.use_native_linear:
+            # d_model 256: four TMA + tcgen05 launches carry every Linear of the layer with its bias, GELU and
+            # residual + LayerNorm (the split stream rides the operand ring; ltu_linear_fused)
+            qkv = ops.linear_fused(t, lw.w_qkv, lw.bqkv_f32)
+            ctx = ops.kv_reduce(qkv[..., C:2 * C], qkv[..., 2 * C:], lw.nhead)
+            att = ops.q_readout(qkv[..., :C], ctx, lw.nhead)
+            t, lo = ops.linear_fused(att, lw.w_o, lw.bo_f32, ops.EPI_RES_LN, t, lo, lw.g1, lw.be1, 1e-6, want_lo=split)
+            f = ops.linear_fused(t, lw.w_1, lw.b1_f32, ops.EPI_GELU)
+            return ops.linear_fused(f, lw.w_2, lw.b2_f32, ops.EPI_RES_LN, t, lo, lw.g2, lw.be2, 1e-6, want_lo=split)
         qkv = F.linear(t, lw.w_qkv, lw.b_qkv)                           # cuBLAS: plain library GEMM
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         ctx = ops.kv_reduce(k, v, lw.nhead)
@@ -610,19 +646,19 @@ class MaskTransUnet(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("lintransunet_b200.MaskTransUnet runs on CUDA (sm_100a) only; there is no CPU path")
         if self.training:
-            if self.dropout and self.dropout > 0:
-                raise NotImplementedError("training-mode dropout is not implemented (forward hot path only); "
-                                          "construct with dropout=0.0 or call .eval()")
-            if torch.is_grad_enabled() and any(p.requires_grad for _, p in _named_weights(self)):
-                if not self.native_backward:
-                    raise NotImplementedError("the native backward (SURVEY 8f-1) is opt-in until it has run on a GPU: set "
-                                              "model.native_backward = True (or LTU_NATIVE_BACKWARD=1), or wrap the call "
-                                              "in torch.no_grad()")
+            # the reference's train-mode forward (trans_3DUnet.py:181-195) with its dropout (p = self.dropout) and, when a
+            # parameter requires grad, autograd through the native backward
+            want_grad = torch.is_grad_enabled() and any(p.requires_grad for _, p in _named_weights(self))
+            if want_grad or (self.dropout and self.dropout > 0):
+                if want_grad and not self.native_backward:
+                    raise NotImplementedError("model.native_backward is off (LTU_NATIVE_BACKWARD=0): a training forward "
+                                              "with grad needs it; wrap the call in torch.no_grad() or switch it on")
                 if self._compute_dtype() != torch.bfloat16:
-                    raise NotImplementedError("the native backward exists on the bf16 path only: call the model inside "
-                                              "torch.autocast (as the reference's train step does)")
+                    raise NotImplementedError("training (native backward, dropout) exists on the bf16 path only: call the "
+                                              "model inside torch.autocast, as the reference's train step does "
+                                              "(utils/utils_3D_embed_full.py:64), or set dropout=0.0 and use no_grad")
                 with torch.autocast("cuda", enabled=False):
-                    return self._forward_train(x)
+                    return self._forward_train(x, want_grad)
         B, _, H, W, D = x.shape
         if H % 32 or W % 32 or D % 4:
             raise ValueError("H and W must be multiples of 32 and D a multiple of 4")
@@ -632,13 +668,22 @@ class MaskTransUnet(nn.Module):
                 out = out.clone()          # the graph's output buffer is reused by the next call
         return out
 
-    def _forward_train(self, x: torch.Tensor):
-        """Training-mode forward with autograd through the native backward: returns (probs, mask_list) like the
-        reference's train-mode forward (model/trans_3DUnet.py:181-195)."""
+    def _forward_train(self, x: torch.Tensor, want_grad: bool = True):
+        """Training-mode forward (dropout active) with autograd through the native backward: returns (probs, mask_list)
+        like the reference's train-mode forward (model/trans_3DUnet.py:181-195)."""
         B, _, H, W, D = x.shape
         if H % 32 or W % 32 or D % 4:
             raise ValueError("H and W must be multiples of 32 and D a multiple of 4")
-        out = _NativeTrainFunction.apply(self, x.contiguous().float(), *[p for _, p in _named_weights(self)])
+        xin = x.contiguous().float()
+        if not want_grad:
+            from . import backward as BW
+            with torch.no_grad():
+                drop = BW.DropoutState(self.dropout, x.device)
+                bottle, skips, _ = BW.encoder_train(xin, self.encode, drop)
+                probs, mask_list, _ = BW.decoder_train(bottle, skips, self.decode, self.dim_output, drop)
+                drop.finish()
+            return probs, mask_list
+        out = _NativeTrainFunction.apply(self, xin, *[p for _, p in _named_weights(self)])
         return out[0], list(out[1:])
 
     def _forward_impl(self, x: torch.Tensor, P: _Plan, head: str):

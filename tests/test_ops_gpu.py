@@ -314,8 +314,12 @@ def test_conv3d_super_voxel_form(case):
     xin = x0 if x1 is None else torch.cat((x0, x1), 1)
     ref = F.conv3d(xin, conv.weight.detach().cpu(), conv.bias.detach().cpu(), padding=1)
     dev = lambda t: None if t is None else to_cl(t).to("cuda", bf)
-    res = ops.conv3d(dev(x0), cw.w, cw.b, cw.cout, 3, pad=1, x1=dev(x1), out_f32=f32_only, want_stats=not f32_only,
-                     w_tc=cw.w_tc, n_aux=0 if f32_only else n_aux, sv=cw.sv)
+    prev_sv, ops.USE_SV_CONV = ops.USE_SV_CONV, True            # opt-in form (slower than conv3d_halo inside the step)
+    try:
+        res = ops.conv3d(dev(x0), cw.w, cw.b, cw.cout, 3, pad=1, x1=dev(x1), out_f32=f32_only, want_stats=not f32_only,
+                         w_tc=cw.w_tc, n_aux=0 if f32_only else n_aux, sv=cw.sv)
+    finally:
+        ops.USE_SV_CONV = prev_sv
     if f32_only:
         y, partials, tiles = res
         assert y.dtype == torch.float32 and partials is None
@@ -330,11 +334,11 @@ def test_conv3d_super_voxel_form(case):
         ref_aux = F.conv3d(xin, aux.weight.detach().cpu(), aux.bias.detach().cpu(), padding=1)
         assert res[3].dtype == torch.float32 and rel_err(from_cl(res[3]), ref_aux) < 2e-5
     # the mma.sync halo kernel on the same operands: bf16 storage of the same fp32 sums
-    ops.USE_SV_CONV = False
+    prev_sv, ops.USE_SV_CONV = ops.USE_SV_CONV, False
     try:
         alt = ops.conv3d(dev(x0), cw.w, cw.b, cw.cout, 3, pad=1, x1=dev(x1), want_stats=True, w_tc=cw.w_tc, n_aux=n_aux)
     finally:
-        ops.USE_SV_CONV = True
+        ops.USE_SV_CONV = prev_sv
     assert rel_err(y.float(), alt[0].float()) < 8e-3
 
 
@@ -586,9 +590,11 @@ def test_encoder_layer_golden(dtype):
         m = MaskTransUnet.__new__(MaskTransUnet)      # only _encoder_layer is exercised
         torch.nn.Module.__init__(m)
         m.use_fused_linear, m.use_fused_ffn, m.use_fused_attn = fused_linear, fused_ffn, fused_attn
-        y, lo = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
-        assert lo is None
-        assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2), (fused_linear, fused_ffn, fused_attn)
+        for native_linear in (True, False):         # K/V projection on ltu_linear_fused / cuBLAS (fused_attn paths)
+            m.use_native_linear = native_linear
+            y, lo = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
+            assert lo is None
+            assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2), (fused_linear, fused_ffn, fused_attn)
     if dtype == torch.bfloat16:     # split token stream (separate-kernel path): hi + lo carries 16 significant bits
         m.use_fused_linear = m.use_fused_ffn = m.use_fused_attn = False
         xin = x.to("cuda", dtype)
@@ -598,6 +604,51 @@ def test_encoder_layer_golden(dtype):
         e_split, e_plain = rel_err(hi.float() + lo.float(), g["layer_out"]), rel_err(plain.float(), g["layer_out"])
         print(f"\n[encoder layer bf16] plain stream {e_plain:.2e}, split stream (hi + lo) {e_split:.2e}")
         assert e_split <= e_plain and e_split < 3e-2
+
+
+@pytest.mark.parametrize("B,N", [(1, 300), (2, 4320), (8, 512)])
+def test_encoder_layer_d256_native_linear(B, N):
+    """d_model-256 SelfAttentionLayer (bridges 2-4, trans_block.py:203-211) with every Linear on ltu_linear_fused
+    (bias / GELU / residual + LayerNorm in the GEMM epilogues, split token stream through the operand ring) against
+    the oracle in fp64 on the same bf16-rounded input, and against the cuBLAS + separate-kernel path."""
+    from lintransunet_b200 import MaskTransUnet
+    from lintransunet_b200.unet import SelfAttentionLayer, _LayerW
+    bf = torch.bfloat16
+    sd = O.make_state_dict(O.UnetConfig(), seed=5)
+    pre = "decode.bridge_list.2.transformer.layers.1"
+    sub = {k[len(pre) + 1:]: v for k, v in sd.items() if k.startswith(pre + ".")}
+    layer = SelfAttentionLayer(256, 8)
+    layer.load_state_dict(sub)
+    layer.cuda()
+    x = q_(rnd((B, N, 256), 95, 1.0), bf)
+    x_lo = q_(rnd((B, N, 256), 96, 2.0 ** -10), bf)
+    # oracle on the exact split input: the Linear layers see x_hi (autocast casts a Linear's input), the residual adds x_hi + x_lo
+    sdd = {pre + "." + k: v.double() for k, v in sub.items()}
+    ref_plain = O.encoder_layer(x.double(), sdd, pre, 8)
+    m = MaskTransUnet.__new__(MaskTransUnet)
+    torch.nn.Module.__init__(m)
+    m.use_fused_linear, m.use_fused_ffn, m.use_fused_attn = False, False, False
+    lw = _LayerW(layer, bf)
+    assert lw.lin
+    out = {}
+    for native in (True, False):
+        m.use_native_linear = native
+        hi, lo = MaskTransUnet._encoder_layer(m, x.to("cuda", bf), lw, None, True)
+        assert lo is not None
+        out[native] = (hi, lo)
+        assert rel_err(hi.float() + lo.float(), ref_plain) < 2.5e-2, native
+        hi1, lo1 = MaskTransUnet._encoder_layer(m, x.to("cuda", bf), lw, None, False)
+        assert lo1 is None and rel_err(hi1.float(), ref_plain) < 3e-2
+    e_nat = rel_err(out[True][0].float() + out[True][1].float(), ref_plain)
+    e_lib = rel_err(out[False][0].float() + out[False][1].float(), ref_plain)
+    print(f"\n[d256 layer B={B} N={N}] native Linear {e_nat:.2e}, cuBLAS + separate kernels {e_lib:.2e} (vs fp64 oracle)")
+    assert e_nat <= 1.5 * e_lib + 1e-3
+    # with a non-zero low word on the input (layers 1..7 of a bridge)
+    m.use_native_linear = True
+    hi2, lo2 = MaskTransUnet._encoder_layer(m, x.to("cuda", bf), lw, x_lo.to("cuda", bf), True)
+    m.use_native_linear = False
+    hi3, lo3 = MaskTransUnet._encoder_layer(m, x.to("cuda", bf), lw, x_lo.to("cuda", bf), True)
+    assert rel_err(hi2.float() + lo2.float(), hi3.float() + lo3.float()) < 2e-2
 
 
 @pytest.mark.parametrize("epi", [0, 1, 2])
@@ -624,6 +675,59 @@ def test_linear_tc_fused_epilogues(epi, rows, cin, cout):
                       gamma=g.cuda() if epi == 2 else None, beta=b.cuda() if epi == 2 else None)
     assert y.shape == (rows, cout)
     assert rel_err(y.float(), ref) < TOL[torch.bfloat16]
+
+
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+@pytest.mark.parametrize("rows,K,N", [(1000, 256, 256), (777, 256, 512), (300, 512, 256), (129, 128, 256), (1, 256, 768),
+                                      (40000, 256, 768), (148 * 128 * 2 + 77, 512, 256), (5000, 64, 256), (4096, 256, 512)])
+def test_linear_fused(epi, rows, K, N):
+    """TMA + tcgen05 Linear (csrc/linear_tma.cu): bias | bias + GELU(erf) | residual + LayerNorm on the split stream
+    (epi 3 = the same with res_lo absent and y_lo not requested) vs fp64 torch on the same bf16 operands."""
+    ops = _ops()
+    ln = epi >= 2
+    if ln and N != 256:
+        pytest.skip("the LayerNorm epilogue needs the whole 256-wide row in one tile")
+    lin = torch.nn.Linear(K, N)
+    with torch.no_grad():
+        lin.weight.copy_(q_(lin.weight * 2, torch.bfloat16))
+    x = q_(rnd((rows, K), 80 + rows % 5, 1.5), torch.bfloat16)
+    r_hi = q_(rnd((rows, N), 81, 2.0) + 0.7, torch.bfloat16)
+    r_lo = q_(rnd((rows, N), 84, 2.0 ** -9), torch.bfloat16)
+    g, b = 1 + 0.1 * rnd((N,), 82), 0.1 * rnd((N,), 83)
+    ref = F.linear(x.double(), lin.weight.detach().double(), lin.bias.detach().double())
+    if epi == 1:
+        ref = F.gelu(ref)
+    elif ln:
+        ref = F.layer_norm(ref + r_hi.double() + (r_lo.double() if epi == 2 else 0), (N,), g.double(), b.double(), eps=1e-6)
+    cu = lambda t: t.detach().to("cuda")
+    bf = torch.bfloat16
+    out = ops.linear_fused(cu(x).to(bf), cu(lin.weight).to(bf), cu(lin.bias).float(), min(epi, 2),
+                           res_hi=cu(r_hi).to(bf) if ln else None, res_lo=cu(r_lo).to(bf) if epi == 2 else None,
+                           gamma=cu(g) if ln else None, beta=cu(b) if ln else None, want_lo=(epi == 2))
+    if ln:
+        y, y_lo = out
+        assert (y_lo is None) == (epi == 3)
+        assert y.shape == (rows, N)
+        assert rel_err(y.float().cpu().double(), ref) < TOL[bf]
+        if y_lo is not None:        # hi + lo carries ~16 significant bits of the fp32 LayerNorm output
+            assert rel_err(y.double().cpu() + y_lo.double().cpu(), ref) < 2e-4
+            assert float((y_lo.float().abs() / y.float().abs().clamp_min(1e-30)).max()) <= 2.0 ** -8   # lo = rounding error of hi
+    else:
+        assert out.shape == (rows, N)
+        assert rel_err(out.float().cpu().double(), ref) < TOL[bf]
+
+
+def test_linear_fused_is_deterministic_and_rejects_bad_shapes():
+    ops = _ops()
+    bf = torch.bfloat16
+    x = rnd((5000, 256), 85).to("cuda", bf)
+    w = rnd((768, 256), 86, 0.1).to("cuda", bf)
+    b = rnd((768,), 87).cuda()
+    assert torch.equal(ops.linear_fused(x, w, b), ops.linear_fused(x, w, b))
+    with pytest.raises(RuntimeError):
+        ops.linear_fused(x, w[:200].contiguous(), b[:200].contiguous())        # N not a multiple of 256
+    with pytest.raises(RuntimeError):
+        ops.linear_fused(x, w, b, ops.EPI_RES_LN, res_hi=x)                     # LayerNorm epilogue needs N == 256
 
 
 @pytest.mark.parametrize("C", [128, 256])
