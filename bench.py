@@ -418,7 +418,7 @@ def run_ours(args):
         roofline = roof(dominant, bound_of.get(dominant, "hbm")) if dominant else None
         attn = {n: roof(n, "hbm") for n in ("kv_reduce", "q_readout") if n in ksum}
         # d_model=128 layers: the readout, both projections, the FFN and both LayerNorms run inside two fused kernels
-        fused = {n: roof(n, "hbm") for n in ("attn_out_fused", "ffn_fused") if n in ksum}
+        fused = {n: roof(n, "hbm") for n in ("attn_out_fused", "ffn_fused", "linear_fused") if n in ksum}
         conv_detail = {n: roof(n, bound_of.get(n, "hbm")) for n in ("conv3d_tc", "conv3d_tc3", "conv3d_sv", "conv3d_halo") if n in ksum}
         line = {"metric": METRIC, "value": win_vox / (ms_step / 1e3), "unit": "voxels/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -455,7 +455,90 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_config2(args):
+    """BASELINE config 2 (not the driver's headline; `--config 2`): the binary model's TRAINING step -- forward with the
+    reference's default dropout 0.3, deep-supervision loss, native backward, Adam step -- on batch 2 of synthetic
+    1x96x96x96 patches under bf16 autocast, inputs copied from pinned host memory every step (the body of the reference's
+    train_on_epoch, utils/utils_3D_embed_full.py:58-92)."""
+    from lintransunet_b200 import MaskTransUnet, _native
+    from lintransunet_b200.train import train_step
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    cfg = dict(MODEL_CFG, dim_output=2)
+    model = MaskTransUnet(**cfg).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    g = torch.Generator().manual_seed(2)
+    x_host = torch.randn((2, 1, 96, 96, 96), generator=g).pin_memory()
+    m_host = (torch.rand((2, 1, 96, 96, 96), generator=g) > 0.8).to(torch.uint8).pin_memory()
+
+    def step():
+        x, m = x_host.to(dev, non_blocking=True), m_host.to(dev, non_blocking=True).long()
+        return train_step(model, opt, x, m)
+
+    for _ in range(max(args.warmup, 3)):
+        loss, _ = step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(visible_index(dev.index))
+    sampler.start()
+    l0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, _ = step()
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms = e0.elapsed_time(e1) / args.steps
+    vox = 2 * 96 ** 3
+    line = {"metric": "voxels/sec fwd+bwd+step (batch 2 of 96^3, BASELINE config 2)", "value": vox / (ms / 1e3), "unit": "voxels/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "dtype": "bf16", "data": "synthetic", "vs_baseline": None,
+            "config": {"workload": "config2: binary MaskTransUnet train step (dropout 0.3, deep-supervision loss, native "
+                                   "backward, Adam), batch 2 x 1x96^3, bf16 autocast, host inputs copied every step"},
+            "clocks": sampler.result(), "gpu_launches": _native.launch_count() - l0, "last_loss": loss,
+            "peak_mem_GB": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)}
+    # the kernel-vs-library bar: the same step through the oracle port in eager PyTorch + autograd on the same B200
+    # (bf16 autocast, dropout-free: the port has no dropout; checker-side code, timed as a BASELINE only)
+    try:
+        from oracle import ltu_oracle as O
+        from oracle import train_step as T
+        ocfg = O.UnetConfig(dim_output=2)
+        sd = {k: v.to(dev).requires_grad_(v.is_floating_point()) for k, v in O.make_state_dict(ocfg, seed=0).items()}
+        params = [v for v in sd.values() if v.requires_grad]
+        oopt = torch.optim.Adam(params, lr=1e-4)
+        torch.cuda.reset_peak_memory_stats(dev)
+
+        def ostep():
+            x, m = x_host.to(dev, non_blocking=True), m_host.to(dev, non_blocking=True).long()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = O.mask_trans_unet_forward(x, sd, ocfg)
+                total, _ = T.train_loss(out["probs"], out["mask_list"], m)
+            total.backward()
+            oopt.step()
+            oopt.zero_grad()
+        for _ in range(2):
+            ostep()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            ostep()
+        e1.record()
+        torch.cuda.synchronize()
+        oms = e0.elapsed_time(e1) / 3
+        line["gpu_eager_baseline"] = {"ms_per_step": round(oms, 2), "voxels_per_s": vox / (oms / 1e3),
+                                      "peak_mem_GB": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2),
+                                      "what": "oracle port of the reference model + loss in eager PyTorch with autograd "
+                                              "(cuDNN / cuBLAS / ATen), bf16 autocast, dropout-free, same B200, same batch"}
+    except Exception as exc:                                  # the baseline must never break the bench line
+        line["gpu_eager_baseline"] = {"error": repr(exc)[:200]}
+    print(json.dumps(line), flush=True)
+
+
 ALGORITHMIC = {
+    "linear_fused": "(rows*K + rows*N (+ residual hi/lo and the lo output for the LayerNorm epilogue))*2 bytes: the nn.Linear "
+                    "layers of the d_model-256 encoder layers and bridge 1's K/V projection (TMA + tcgen05, fused epilogues)",
     "kv_reduce": "2*B*N*C*E bytes (K and V read once)",
     "q_readout": "2*B*N*C*E bytes (Q read, out written)",
     "attn_out_fused": "2*rows*C*E bytes (x read once, y written once)",
@@ -475,9 +558,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=5, choices=[2, 5],
+                    help="5 (default, the headline): sliding-window inference; 2: the training step of BASELINE config 2")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 2:
+        run_config2(args)
     else:
         run_ours(args)
 

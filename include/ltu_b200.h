@@ -345,6 +345,24 @@ size_t ltu_add_layernorm_bwd_workspace(int64_t rows, int C);
 int ltu_add_layernorm_bwd(const void* x, const void* res, const void* dy, const float* gamma,
                           void* dz, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes,
                           int64_t rows, int C, float eps, int dtype, ltu_stream_t stream);
+/* ---- f4: deep-supervision training loss, loss/criterions.py:35-69 (DiceClassLoss), :416-443 (BalanceDiceLoss),
+ * :696-718 (CrossEntroLoss) as driven by utils/utils_3D_embed_full.py:64-86.  Every criterion is a function of four sums
+ * over the voxels of each (sample, class):
+ *     sums[n][c] = ( sum p, sum onehot, sum p*onehot, sum -(1-p)*onehot*log(max(p,1e-6)) ),  onehot = (label == c)
+ * p fp32 [N][C][V] (the reference layout [N,C,H,W,D]), labels uint8 [N][V].  One pass over p; fixed-order fp32 block
+ * sums, fp64 across blocks.  workspace: ltu_loss_sums_workspace(N, C, V) bytes, 8-byte aligned.                  */
+size_t ltu_loss_sums_workspace(int N, int C, int64_t V);
+int ltu_loss_sums(const float* p, const uint8_t* labels, float* sums, void* workspace,
+                  size_t workspace_bytes, int N, int C, int64_t V, ltu_stream_t stream);
+/* backward: dp[n][c][v] = g[n][c][0] + onehot * (g[n][c][2] + g[n][c][3] * d/dp[-(1-p) log max(p,1e-6)]),
+ * g = d(loss)/d(sums) fp32 [N][C][4] (the clamp passes its gradient for p >= 1e-6, like torch.clamp)              */
+int ltu_loss_sums_bwd(const float* p, const uint8_t* labels, const float* gsums, float* dp, int N,
+                      int C, int64_t V, ltu_stream_t stream);
+/* label pyramid: F.max_pool3d(labels, kernel = stride = (kh,kw,kd)), utils/utils_3D_embed_full.py:65,:76-79, on uint8
+ * labels [N][H][W][D] (H, W, D multiples of the kernel)                                                           */
+int ltu_label_pool(const uint8_t* x, uint8_t* y, int N, int H, int W, int D, int kh, int kw, int kd,
+                   ltu_stream_t stream);
+
 /* Training-mode dropout (p = 0.3 by default, model/trans_3DUnet.py:162): nn.Dropout of
  * model/trans_block.py:205,:208,:209 and model/Unet_3Dblock.py:339,:382,:429,:556 (channelwise 0) and the nn.Dropout3d of
  * Conv3dPosEmbedding, model/trans_block.py:96 (channelwise 1: one draw per (sample, channel)) on a channels-last tensor:

@@ -30,6 +30,10 @@ SIGNATURES = {
     "ltu_add_layernorm": (I, [P, P, P, P, P, L, I, F, I, P]),
     "ltu_add_layernorm_split": (I, [P, P, P, P, P, P, P, L, I, F, P]),
     "ltu_gelu": (I, [P, L, I, P]),
+    "ltu_loss_sums_workspace": (Z, [I, I, L]),
+    "ltu_loss_sums": (I, [P, P, P, P, Z, I, I, L, P]),
+    "ltu_loss_sums_bwd": (I, [P, P, P, P, I, I, L, P]),
+    "ltu_label_pool": (I, [P, P, I, I, I, I, I, I, I, P]),
     "ltu_dropout": (I, [P, P, L, I, L, F, U64, U64, I, I, P]),
     "ltu_posenc_dwconv3": (I, [P, P, P, P, I, I, I, I, I, I, P]),
     "ltu_posenc_dwconv3_split": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),

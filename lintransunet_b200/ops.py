@@ -244,6 +244,49 @@ def gelu_(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
+def loss_sums(p: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """p fp32 [N, C, ...] (probabilities in the reference layout), labels uint8 [N, ...] -> fp32 [N, C, 4]:
+    (sum p, sum onehot, sum p*onehot, sum -(1-p)*onehot*log(max(p,1e-6))) per sample and class (include/ltu_b200.h)."""
+    dev = _chk(p, labels)
+    if p.dtype != torch.float32 or labels.dtype != torch.uint8:
+        raise TypeError("loss_sums: fp32 probabilities and uint8 labels")
+    N, C = p.shape[0], p.shape[1]
+    V = p.numel() // (N * C)
+    if labels.numel() != N * V:
+        raise ValueError(f"loss_sums: labels {tuple(labels.shape)} do not match probabilities {tuple(p.shape)}")
+    L = _native.lib()
+    nbytes = L.ltu_loss_sums_workspace(N, C, V)
+    ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=dev)
+    sums = torch.empty(N, C, 4, dtype=torch.float32, device=dev)
+    with _Guard(dev, ("loss_sums", p.numel() * 4 + labels.numel() * C, 0)) as st:
+        check(L.ltu_loss_sums(_p(p), _p(labels), _p(sums), _p(ws), nbytes, N, C, V, st), "ltu_loss_sums")
+    return sums
+
+
+def loss_sums_bwd(p: torch.Tensor, labels: torch.Tensor, gsums: torch.Tensor) -> torch.Tensor:
+    """d(loss)/dp (fp32, shape of p) from g = d(loss)/d(loss_sums(p, labels)) fp32 [N, C, 4]."""
+    dev = _chk(p, labels, gsums)
+    N, C = p.shape[0], p.shape[1]
+    V = p.numel() // (N * C)
+    dp = torch.empty_like(p)
+    with _Guard(dev, ("loss_sums_bwd", 2 * p.numel() * 4 + labels.numel() * C, 0)) as st:
+        check(_native.lib().ltu_loss_sums_bwd(_p(p), _p(labels), _p(gsums), _p(dp), N, C, V, st), "ltu_loss_sums_bwd")
+    return dp
+
+
+def label_pool(labels: torch.Tensor, kernel: Tuple[int, int, int]) -> torch.Tensor:
+    """F.max_pool3d(labels, kernel_size = stride = kernel) on uint8 labels [N, H, W, D] (the reference's label pyramid)."""
+    dev = _chk(labels)
+    if labels.dtype != torch.uint8 or labels.dim() != 4:
+        raise TypeError("label_pool: uint8 labels [N, H, W, D]")
+    N, H, W, D = labels.shape
+    kh, kw, kd = kernel
+    out = torch.empty(N, H // kh, W // kw, D // kd, dtype=torch.uint8, device=dev)
+    with _Guard(dev) as st:
+        check(_native.lib().ltu_label_pool(_p(labels), _p(out), N, H, W, D, kh, kw, kd, st), "ltu_label_pool")
+    return out
+
+
 def dropout(x: torch.Tensor, p: float, seed: int, offset: int, channelwise: bool = False, inplace: bool = False) -> torch.Tensor:
     """Training-mode nn.Dropout (or nn.Dropout3d: `channelwise`, one draw per sample and channel) on a channels-last
     tensor [B, ..., C]: keep decisions are a pure function of (seed, offset, index), so the backward is the same call on
@@ -865,6 +908,16 @@ def linear_tc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, cout:
                                   c_void_p(bias.data_ptr() + n0 * 4), n, c_void_p(y.data_ptr() + n0 * 2), cout, epi,
                                   _p(residual), _p(gamma), _p(beta), eps, st), "ltu_linear_tc")
     return y
+
+
+def linear_fma(x: torch.Tensor, w_kn: torch.Tensor, bias: torch.Tensor, n: int) -> torch.Tensor:
+    """nn.Linear on the fp32 path: y = x W^T + b as exact fp32 FMAs on CUDA cores -- the 1x1x1 case of ltu_conv3d (a
+    shared-memory tiled GEMM), so the fp32 forward launches no library GEMM either.  x [..., K] contiguous fp32,
+    w_kn = W^T as fp32 [1, K, N] (the [tap][Cin][Cout] packing of ltu_conv3d), bias fp32 [N]."""
+    k = x.shape[-1]
+    rows = x.numel() // k
+    out, _, _ = conv3d(x.reshape(1, rows, 1, 1, k), w_kn, bias, n, 1, pad=0)
+    return out.reshape(*x.shape[:-1], n)
 
 
 def linear_fused_supported(k: int, n: int) -> bool:

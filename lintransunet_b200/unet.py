@@ -295,6 +295,11 @@ class _LayerW:
         self.lin_kv = self.attn_fused and ops.linear_fused_supported(d, 2 * d)
         if self.lin_kv:
             self.bkv_f32 = f(self.b_kv)
+        # fp32 path: W^T as [1][K][N] for the CUDA-core GEMM (ops.linear_fma)
+        self.fma = dtype == torch.float32
+        if self.fma:
+            kn = lambda w: w.detach().float().t().contiguous().unsqueeze(0)
+            self.wp_qkv, self.wp_o, self.wp_1, self.wp_2 = kn(self.w_qkv), kn(self.w_o), kn(self.w_1), kn(self.w_2)
 
 
 def _pos_w(pe: Conv3dPosEmbedding):
@@ -578,7 +583,15 @@ class MaskTransUnet(nn.Module):
             t, lo = ops.linear_fused(att, lw.w_o, lw.bo_f32, ops.EPI_RES_LN, t, lo, lw.g1, lw.be1, 1e-6, want_lo=split)
             f = ops.linear_fused(t, lw.w_1, lw.b1_f32, ops.EPI_GELU)
             return ops.linear_fused(f, lw.w_2, lw.b2_f32, ops.EPI_RES_LN, t, lo, lw.g2, lw.be2, 1e-6, want_lo=split)
-        qkv = F.linear(t, lw.w_qkv, lw.b_qkv)                           # cuBLAS: plain library GEMM
+        if lw.fma and self.use_native_linear:
+            # fp32 path: exact-FMA GEMMs on CUDA cores (no TF32, no library call)
+            qkv = ops.linear_fma(t, lw.wp_qkv, lw.b_qkv, 3 * C)
+            ctx = ops.kv_reduce(qkv[..., C:2 * C], qkv[..., 2 * C:], lw.nhead)
+            att = ops.q_readout(qkv[..., :C], ctx, lw.nhead)
+            t = ops.add_layernorm(t, ops.linear_fma(att, lw.wp_o, lw.b_o, C), lw.g1, lw.be1, 1e-6)
+            f = ops.gelu_(ops.linear_fma(t, lw.wp_1, lw.b_1, 2 * C))
+            return ops.add_layernorm(t, ops.linear_fma(f, lw.wp_2, lw.b_2, C), lw.g2, lw.be2, 1e-6), None
+        qkv = F.linear(t, lw.w_qkv, lw.b_qkv)                           # LTU_NATIVE_LINEAR=0: cuBLAS, the A/B baseline
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         ctx = ops.kv_reduce(k, v, lw.nhead)
         att = ops.q_readout(q, ctx, lw.nhead)

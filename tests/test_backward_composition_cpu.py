@@ -245,6 +245,27 @@ def oracle_step():
                 grads={k: v.grad for k, v in sdd.items()})
 
 
+def _loss_sums_torch(p, labels):
+    """Definition of ltu_loss_sums in torch ops (differentiable in p)."""
+    n, c = p.shape[0], p.shape[1]
+    pf = p.reshape(n, c, -1)
+    lab = labels.reshape(n, 1, -1).long()
+    onehot = (lab == torch.arange(c).view(1, c, 1)).to(p.dtype)
+    s = -(1 - pf) * onehot * torch.log(torch.clamp(pf, min=1e-6))
+    return torch.stack([pf.sum(-1), onehot.sum(-1), (pf * onehot).sum(-1), s.sum(-1)], -1)
+
+
+def _install_loss_standins(monkeypatch):
+    from lintransunet_b200 import losses, ops
+    monkeypatch.setattr(ops, "loss_sums", _loss_sums_torch)
+    monkeypatch.setattr(ops, "loss_sums_bwd", lambda p, labels, g: vjp(lambda q: _loss_sums_torch(q, labels), [p], g)[0])
+    monkeypatch.setattr(ops, "label_pool", lambda lab, k: F.max_pool3d(lab.float().unsqueeze(1), kernel_size=k, stride=k)
+                        .squeeze(1).to(torch.uint8))
+    # keep fp64 probabilities in fp64 (the product casts to fp32 for the kernel)
+    monkeypatch.setattr(losses, "level_sums", lambda predict, lab: (losses._LossSums.apply(predict, lab),
+                                                                    predict.numel() // (predict.shape[0] * predict.shape[1])))
+
+
 @pytest.fixture()
 def standins(monkeypatch):
     from lintransunet_b200 import backward, ops
@@ -252,6 +273,7 @@ def standins(monkeypatch):
         if not name.startswith("_") and name not in ("ACT_NONE", "ACT_LRELU"):
             monkeypatch.setattr(ops, name, getattr(StandIns, name))
     monkeypatch.setattr(backward, "_ACT", DT)
+    _install_loss_standins(monkeypatch)
     return backward
 
 

@@ -61,7 +61,7 @@ def test_train_step_gradients_against_the_reference():
         n_checked += 1
         assert cos > 0.8, (name, cos)
     print(f"[train step] worst cosine similarity of a gradient subsample with the reference's: {cos_worst:.4f} over {n_checked} tensors")
-    assert n_checked > 100
+    assert n_checked > 50
 
 
 def _model(dropout=0.0, seed=0):
