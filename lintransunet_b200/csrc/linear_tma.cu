@@ -58,12 +58,14 @@ struct LinParams {
     int N, nkb;                      // output columns, 64-wide k-blocks of x
     int tiles_m, tiles_n;
     int epi, has_lo, want_lo;
+    int cl;                          // CTAs per cluster: 2 = a CTA pair walks two row blocks of the same n-tile in lock step
+                                     // and every W k-block is fetched ONCE per pair (each CTA loads half, TMA multicast)
     int mode;                        // debug ablations (LTU_LIN_MODE): 1 no output stores, 2 no GELU math, 4 no MMAs, 8 no W loads
 };
 
 __global__ void __launch_bounds__(kLinThreads, 1)
 linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                  const __grid_constant__ CUtensorMap tm_rhi, const __grid_constant__ CUtensorMap tm_rlo,
+                  const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_rhi, const __grid_constant__ CUtensorMap tm_rlo,
                   const __grid_constant__ CUtensorMap tm_yhi, const __grid_constant__ CUtensorMap tm_ylo,
                   const LinParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -71,12 +73,17 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     LinTail* tail = reinterpret_cast<LinTail*>(smem + kLinOffTail);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total = p.tiles_m * p.tiles_n;
+    // Work items: (row-block group, n-tile), n fastest; a group is p.cl consecutive 128-row blocks, one per CTA of the
+    // cluster.  Both CTAs of a pair run the same trip count (a row block past the end loads zeros and stores nothing).
+    const int crank = p.cl == 2 ? (int)cluster_ctarank() : 0;
+    const int ngroups = (int)gridDim.x / p.cl, group = (int)blockIdx.x / p.cl;
+    const int total = (p.tiles_m + p.cl - 1) / p.cl * p.tiles_n;
+    const uint16_t cmask = (uint16_t)((1u << p.cl) - 1);
     const int nres = p.epi == kLinResLN ? (p.has_lo ? 8 : 4) : 0;      // residual k-blocks (r_hi then r_lo)
     const int nkb_all = p.nkb + (nres + 2) / 3;                       // ring stages per tile: three residual k-blocks share a stage
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kLinStages; ++s) { mbar_init(smem_u32(&tail->full[s]), 1); mbar_init(smem_u32(&tail->empty[s]), 1); }
+        for (int s = 0; s < kLinStages; ++s) { mbar_init(smem_u32(&tail->full[s]), 1); mbar_init(smem_u32(&tail->empty[s]), (uint32_t)p.cl); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tail->tfull[i]), 1); mbar_init(smem_u32(&tail->tempty[i]), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -103,6 +110,7 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.cl == 2) cluster_sync_all();                  // the peer's barriers exist before anything is multicast to them
     const uint32_t tmem_base = tail->tmem_slot;
 
     if (warp == 0) {
@@ -110,17 +118,22 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (lane == 0) {
             pdl_prologue();                                              // inputs come from the previous kernel in the stream
             uint32_t kbc = 0;
-            for (int T = blockIdx.x; T < total; T += gridDim.x) {
-                const int row0 = (T / p.tiles_n) * 128, n0 = (T % p.tiles_n) * kLinBN;
+            for (int T = group; T < total; T += ngroups) {
+                const int row0 = ((T / p.tiles_n) * p.cl + crank) * 128, n0 = (T % p.tiles_n) * kLinBN;
                 for (int kb = 0; kb < nkb_all; ++kb, ++kbc) {
                     const int stage = kbc % kLinStages;
-                    mbar_wait(smem_u32(&tail->empty[stage]), ((kbc / kLinStages) & 1) ^ 1);
+                    mbar_wait(smem_u32(&tail->empty[stage]), ((kbc / kLinStages) & 1) ^ 1);     // free in BOTH CTAs of a pair
                     const uint32_t fb = smem_u32(&tail->full[stage]);
                     const uint32_t sa = sbase + stage * kLinStageBytes;
                     if (kb < p.nkb) {
                         mbar_expect_tx(fb, (p.mode & 8) ? kLinABytes : kLinStageBytes);
                         tma_load_2d(sa, &tm_x, kb * 64, row0, fb);
-                        if (!(p.mode & 8)) tma_load_2d(sa + kLinABytes, &tm_w, kb * 64, n0, fb);
+                        if (p.mode & 8) {
+                        } else if (p.cl == 2) {         // this CTA's 128-row half of the W k-block, delivered to both CTAs
+                            tma_load_2d_mc(sa + kLinABytes + (uint32_t)crank * (kLinBBytes / 2), &tm_wh, kb * 64, n0 + crank * 128, fb, cmask);
+                        } else {
+                            tma_load_2d(sa + kLinABytes, &tm_w, kb * 64, n0, fb);
+                        }
                     } else {                                             // up to three residual k-blocks fill one stage
                         const int j0 = (kb - p.nkb) * 3;
                         const int cnt = nres - j0 < 3 ? nres - j0 : 3;
@@ -138,7 +151,7 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         constexpr uint32_t idesc = umma_idesc_bf16(128, kLinBN), idesc_eye = umma_idesc_bf16(128, 64);
         const uint64_t eye = make_desc(sbase + kLinOffEye);
         uint32_t kbc = 0, it = 0;
-        for (int T = blockIdx.x; T < total; T += gridDim.x, ++it) {
+        for (int T = group; T < total; T += ngroups, ++it) {
             const uint32_t abuf = it & 1;
             mbar_wait(smem_u32(&tail->tempty[abuf]), ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
             tc_fence_after();
@@ -166,7 +179,8 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                             umma_bf16_elect(tacc + dcol, rdesc + (uint64_t)(k * 2), eye + (uint64_t)(k * 2), idesc_eye, 1u);
                     }
                 }
-                umma_commit_elect(smem_u32(&tail->empty[stage]));
+                if (p.cl == 2) umma_commit_mc_elect(smem_u32(&tail->empty[stage]), cmask);     // arrives in both CTAs
+                else umma_commit_elect(smem_u32(&tail->empty[stage]));
                 if (kb == nkb_all - 1) umma_commit_elect(smem_u32(&tail->tfull[abuf]));
             }
         }
@@ -180,8 +194,8 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const uint32_t stg_u = smem_u32(stg);
         const uint32_t swz = (uint32_t)(lane & 7);
         uint32_t it = 0;
-        for (int T = blockIdx.x; T < total; T += gridDim.x, ++it) {
-            const int row0 = (T / p.tiles_n) * 128, n0 = (T % p.tiles_n) * kLinBN;
+        for (int T = group; T < total; T += ngroups, ++it) {
+            const int row0 = ((T / p.tiles_n) * p.cl + crank) * 128, n0 = (T % p.tiles_n) * kLinBN;
             const uint32_t abuf = it & 1;
             const uint32_t tb = tmem_base + abuf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 128);
             const float* bs = tail->bias + n0 + hh * 128;
@@ -320,6 +334,7 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cl == 2) cluster_sync_all();                  // no CTA leaves while its peer may still multicast into it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -347,10 +362,11 @@ extern "C" int ltu_linear_fused(const void* x, int64_t rows, int K, const void* 
     LTU_ARG_CHECK(epi == kLinResLN || (!res_hi && !res_lo && !y_lo), "linear_fused: residual / y_lo only with epi 2");
     LTU_ARG_CHECK((((uintptr_t)x | (uintptr_t)w_bf16 | (uintptr_t)y_hi | (uintptr_t)y_lo | (uintptr_t)res_hi | (uintptr_t)res_lo) & 15) == 0,
                   "linear_fused: pointers must be 16-byte aligned");
-    CUtensorMap tx, tw, trh, trl, tyh, tyl;
+    CUtensorMap tx, tw, twh, trh, trl, tyh, tyl;
     int rc;
     if ((rc = make_tmap_bf16_2d(&tx, x, (uint64_t)rows, (uint64_t)K, 128)) != LTU_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&tw, w_bf16, (uint64_t)N, (uint64_t)K, kLinBN)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&twh, w_bf16, (uint64_t)N, (uint64_t)K, kLinBN / 2)) != LTU_OK) return rc;   // half boxes (pairs)
     if ((rc = make_tmap_bf16_2d(&tyh, y_hi, (uint64_t)rows, (uint64_t)N, 32)) != LTU_OK) return rc;
     trh = tx; trl = tx; tyl = tyh;
     if (res_hi && (rc = make_tmap_bf16_2d(&trh, res_hi, (uint64_t)rows, kLinBN, 128)) != LTU_OK) return rc;
@@ -365,16 +381,44 @@ extern "C" int ltu_linear_fused(const void* x, int64_t rows, int K, const void* 
     p.mode = dbg_mode;
     const size_t smem = 1024 + kLinOffTail + sizeof(LinTail);
     static thread_local int configured_dev = -1;
+    static thread_local int max_pairs = -1;
     int dev; cudaGetDevice(&dev);
     if (configured_dev != dev) {
         cudaFuncSetAttribute(linear_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured_dev = dev;
+        max_pairs = -1;
     }
-    int grid = sm_count();
-    const int total = p.tiles_m * p.tiles_n;
-    if (grid > total) grid = total;
-    cudaError_t e = launch_pdl(linear_tma_kernel, dim3(grid), dim3(kLinThreads), smem, (cudaStream_t)stream,
-                               tx, tw, trh, trl, tyh, tyl, p);
+    // CTA pairs (2-CTA clusters, W fetched once per pair) when the device can keep every pair resident at once
+    // Measured (tools/linear_probe.py, profiles/r2_linear_probe.md): correct, but no faster than independent CTAs -- these
+    // GEMMs sit at the HBM write rate, not at the L2 -> SM rate of the W re-reads -- so pairs are opt-in (LTU_LIN_CLUSTER=1).
+    static const int want_cl = [] { const char* e = getenv("LTU_LIN_CLUSTER"); return (e && e[0] == '1') ? 2 : 1; }();
+    if (want_cl == 2 && max_pairs < 0) {
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); q.blockDim = dim3(kLinThreads); q.dynamicSmemBytes = smem;
+        cudaLaunchAttribute a[1];
+        a[0].id = cudaLaunchAttributeClusterDimension;
+        a[0].val.clusterDim.x = 2; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+        q.attrs = a; q.numAttrs = 1;
+        int n = 0;
+        max_pairs = cudaOccupancyMaxActiveClusters(&n, linear_tma_kernel, &q) == cudaSuccess ? n : 0;
+        cudaGetLastError();
+    }
+    p.cl = (want_cl == 2 && p.tiles_m >= 2 && max_pairs >= 16) ? 2 : 1;
+    const int groups = (p.tiles_m + p.cl - 1) / p.cl * p.tiles_n;
+    int grid = p.cl == 2 ? max_pairs * 2 : sm_count();
+    if (grid > groups * p.cl) grid = groups * p.cl;
+    static const bool pdl = [] { const char* e = getenv("LTU_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kLinThreads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+    if (p.cl == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = (unsigned)na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, linear_tma_kernel, tx, tw, twh, trh, trl, tyh, tyl, p);
     if (e != cudaSuccess) { set_error("linear_fused: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     count_launch(1);
     return LTU_OK;

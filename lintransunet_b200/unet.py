@@ -450,6 +450,9 @@ class MaskTransUnet(nn.Module):
         self.use_fused_attn = os.environ.get("LTU_FUSED_ATTN", "1") == "1"
         # bf16 path: compute the mask head inside UpBlock.conv1's launch (same input), fp32 logits as a second output
         self.fuse_mask_head = os.environ.get("LTU_FUSE_MASK_HEAD", "1") != "0"
+        # inference: do not launch a mask head nobody reads (level without a ROI bridge); the outputs are bit-identical
+        # either way (tests/test_model_gpu.py::test_dead_mask_head_does_not_change_the_result).  LTU_KEEP_DEAD_HEAD=1 = A/B.
+        self.skip_dead_mask_head = os.environ.get("LTU_KEEP_DEAD_HEAD", "0") != "1"
         # bf16 path: carry the residual stream of the encoder layers that run as separate kernels (d_model 256) as two
         # bf16 words (hi + lo): the bf16 rounding of the LayerNorm outputs is the largest single term of the bf16
         # path's error (4.6e-2 -> 3.5e-2 on the 64x64x16 case); the reference keeps it in fp32.
@@ -519,7 +522,7 @@ class MaskTransUnet(nn.Module):
     def _knobs(self) -> tuple:
         """Every runtime switch that changes the launched kernels (part of the CUDA-graph cache key)."""
         return (self.use_tensor_cores, self.use_fused_linear, self.fuse_mask_head, self.use_fused_ffn, self.use_fused_attn,
-                self.split_token_stream, self.use_native_linear, ops.USE_HALO_CONV, ops.USE_TC3_CONV, ops.USE_SV_CONV)
+                self.split_token_stream, self.use_native_linear, self.skip_dead_mask_head, ops.USE_HALO_CONV, ops.USE_TC3_CONV, ops.USE_SV_CONV)
 
     def _capture(self, x: torch.Tensor, plan: "_Plan", head: str) -> dict:
         static_x = x.clone()
@@ -718,16 +721,23 @@ class MaskTransUnet(nn.Module):
         for i in range(1, n):
             x = ops.upsample_trilinear(x, 2 if (n - i) % 2 == 0 else 1)          # :1375-1378
             lvl = n - 1 - i
-            fused = P.up_dual is not None and self.use_tensor_cores and self.fuse_mask_head
+            # The mask head of a level feeds (a) the deep-supervision loss, through mask_list, in training mode and (b) the
+            # ROI box of that level's bridge (:1387).  A level without a ROI bridge (is_roi_list False: the finest one in
+            # the reference configuration) has no consumer in an inference forward, whose result (:199-201) is the argmax
+            # of the final block only: that head is dead code there and is not launched.
+            need_mask = head == "train" or P.bridges[lvl] is not None or not self.skip_dead_mask_head
+            fused = P.up_dual is not None and self.use_tensor_cores and self.fuse_mask_head and need_mask
+            fg = None
             if fused:    # mask head (:1380) + UpBlock.conv1 (:547) share their input: one conv, two outputs
                 cw = P.up_dual[i - 1]
                 raw1, part1, _, logits = ops.conv3d(x, cw.w, cw.b, cw.cout, cw.k, pad=1, want_stats=True, w_tc=cw.w_tc,
                                                     n_aux=cw.n_aux, sv=cw.sv)
-            else:
+            elif need_mask:
                 logits, _, _ = self._conv(x, P.mask[lvl], pad=1, out_f32=True)   # :1380
-            mask, fg = ops.mask_softmax(logits, want_mask=(head == "train"))
-            if mask is not None:
-                mask_list.append(mask)
+            if need_mask:
+                mask, fg = ops.mask_softmax(logits, want_mask=(head == "train"))
+                if mask is not None:
+                    mask_list.append(mask)
             skip = skips[-i]
             wx, wg, psi_w, psi_b = P.gate[lvl]
             ga, pa, _ = self._conv(skip, wx, pad=0, want_stats=True)             # SpatialAttention3DBlock :217-221

@@ -140,7 +140,7 @@ def test_module_api_contract():
     assert float(m(x)[:, 0].mean()) == 1.0
     m.train()
     with pytest.raises(NotImplementedError):
-        m(x)                                   # dropout 0.3 in training mode is not part of the hot path
+        m(x)                                   # training (dropout, native backward) exists under autocast only
     with pytest.raises(RuntimeError):
         m.eval()(x.cpu())                      # no CPU fallback
     with pytest.raises(ValueError):
@@ -164,6 +164,29 @@ def test_cuda_graph_replay_is_bit_identical_to_eager():
         assert torch.equal(e1, g1) and torch.equal(e2, g2) and torch.equal(g1, g1b), prec
         assert torch.equal(m.predict_labels(x2), l2)
         assert not torch.equal(e1, e2)
+
+
+def test_dead_mask_head_does_not_change_the_result():
+    """Inference does not launch the mask head of a level without a ROI bridge (nobody reads it: the eval result is
+    the argmax of the final block, model/trans_3DUnet.py:199-201): logits, one-hot and labels are bit-identical to
+    the forward that computes it, in both precisions; training mode always computes it (deep supervision)."""
+    g = load_golden("model_c3_64x96x32_b2.npz")
+    m, cfg, sd, x = build(g, "bf16")
+    m.eval()
+    xc = x.cuda()
+    for prec in ("bf16", "fp32"):
+        m.precision = prec
+        m.skip_dead_mask_head = False
+        full = (m.forward_logits(xc), m(xc), m.predict_labels(xc).clone())
+        m.skip_dead_mask_head = True
+        lean = (m.forward_logits(xc), m(xc), m.predict_labels(xc).clone())
+        for a, b in zip(full, lean):
+            assert torch.equal(a, b), prec
+    m.train()
+    m.precision = "bf16"
+    with torch.no_grad():
+        probs, mask_list = m(xc)
+    assert len(mask_list) == 4 and mask_list[-1].shape[2:] == (32, 48, 32)
 
 
 def test_result_does_not_depend_on_batch_composition():
