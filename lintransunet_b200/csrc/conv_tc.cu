@@ -28,7 +28,10 @@ void count_launch(int n = 1);
 int conv3d_tc2_launch(const TcParams& c, int B, int epi, const void* residual, const float* gamma, const float* beta,
                       float eps, int ld_out, cudaStream_t st);       // conv_tc2.cu: persistent variant
 static bool use_persistent_tc() {
-    static const bool v = [] { const char* e = getenv("LTU_TC_V1"); return !(e && e[0] == '1'); }();
+    // Round 2 (tools/layer_profile.py, batch 8 of 128^3): the four 1x1x1 gate convolutions of levels 2-3 take 46-85 us on
+    // the persistent kernel (<= 2 tiles per CTA: its per-CTA pipeline set-up is never amortised) and 20-31 us on this one
+    // -> the persistent variant is opt-in (LTU_TC_PERSISTENT=1) and keeps serving ltu_linear_tc.
+    static const bool v = [] { const char* e = getenv("LTU_TC_PERSISTENT"); return e && e[0] == '1'; }();
     return v;
 }
 

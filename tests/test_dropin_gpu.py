@@ -78,7 +78,10 @@ def test_dataparallel_replicas_follow_weight_changes_and_train():
         return {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
 
     g_dp, g_1 = step(dp), step(m)
-    assert g_dp.keys() == g_1.keys() and len(g_dp) > 500
+    # nn.DataParallel's Broadcast backward hands zero gradients to parameters the replicas never used (the dead
+    # pos_encoders.1-7, the unsupervised heads): extra keys are fine as long as they are exactly zero
+    assert set(g_1) <= set(g_dp) and len(g_1) > 500
+    assert all(float(g_dp[k].abs().max()) == 0.0 for k in set(g_dp) - set(g_1))
     worst = max(float((g_dp[k] - g_1[k]).abs().max() / g_1[k].abs().max().clamp_min(1e-12)) for k in g_1)
     print(f"\n[DataParallel] worst relative gradient difference vs the single-GPU step: {worst:.2e}")
     assert worst < 5e-2

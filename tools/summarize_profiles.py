@@ -66,27 +66,30 @@ def main():
     ap.add_argument("--round", default="r1")
     a = ap.parse_args()
     os.makedirs(PR, exist_ok=True)
-    lf = os.path.join(GP, "launches_forward.csv")
+    pre = "" if a.round == "r1" else a.round + "_"            # round >= 2: gpurun_out files already carry the round prefix
+    lf = os.path.join(GP, pre + "launches_forward.csv")
     if os.path.exists(lf):
         shutil.copy(lf, os.path.join(PR, f"{a.round}_launches_forward.csv"))
         launches(lf, os.path.join(PR, f"{a.round}_launches_forward.md"),
                  "Per-launch device times: two eager bf16 forwards, batch 8 x 128^3 (tools/ncu_target.py)")
-    lb = os.path.join(GP, "launches_bench.csv")
+    lb = os.path.join(GP, pre + "launches_bench.csv")
     if os.path.exists(lb):
         shutil.copy(lb, os.path.join(PR, f"{a.round}_launches_bench.csv"))
         launches(lb, os.path.join(PR, f"{a.round}_launches_bench.md"), "Per-launch device times inside `python bench.py --steps 1 --warmup 3`")
     out = os.path.join(PR, f"{a.round}_ncu_full.md")
     with open(out, "w") as f:
-        f.write("# `ncu --set full --clock-control none --import-source on` captures (tools/ncu_capture.sh)\n\n"
+        f.write(f"# `ncu --set full --clock-control none --import-source on` captures (tools/ncu_capture{'' if a.round == 'r1' else '_' + a.round}.sh)\n\n"
                 "Target: tools/ncu_target.py (second eager forward, batch 8 x 128^3, bf16).  Raw exports: "
                 f"`{a.round}_prof_*_raw.csv`.\n")
-    for name, title in (("kv", "kv_reduce (bridge 1: B=8, N=57408, C=128, 4 heads)"), ("kv8", "kv_reduce (bridge 2: N=10752, C=256, 8 heads)"),
+    for name, title in (("lin", "linear_tma_kernel (bridge 2, layer 0: QKV | O + LN | FFN1 + GELU | FFN2 + LN; 86016 rows, d_model 256)"),
+                        ("linkv", "linear_tma_kernel (bridge 1 K/V projection: 459264 rows, 128 -> 256)"),
+                        ("kv", "kv_reduce (bridge 1: B=8, N=57408, C=128, 4 heads)"), ("kv8", "kv_reduce (bridge 2: N=10752, C=256, 8 heads)"),
                         ("q", "q_readout (bridge 2: N=10752, C=256; bridge 1 runs inside attn_out128_kernel)"),
                         ("ffn", "ffn128_kernel (fused FFN half, bridge 1: 459264 rows, d_model 128)"),
                         ("attnout", "attn_out128_kernel (fused query half, bridge 1)"),
                         ("tc3", "conv3d_tc3 (TMA halo + tcgen05)"),
                         ("tc", "conv3d_tc (tcgen05 implicit GEMM, im2col per tap)"), ("halo", "conv3d_halo (smem halo + mma.sync)")):
-        raw = os.path.join(GP, f"prof_{name}_raw.csv")
+        raw = os.path.join(GP, f"{pre}prof_{name}_raw.csv")
         if os.path.exists(raw):
             shutil.copy(raw, os.path.join(PR, f"{a.round}_prof_{name}_raw.csv"))
             ncu_raw(raw, out, title)
