@@ -741,6 +741,132 @@ posenc_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ xlo, con
     }
 }
 
+// Round 2: shared-memory tiled version of the same arithmetic for C % 32 == 0.  posenc_bf16_kernel reads the nine
+// (kh, kw) neighbour columns of every output column through L1/L2 -- 9x the tensor through L2, 1.0 TB/s of its bytes on
+// bridge 1.  Here a block owns a 4 x 4 x 32 (h, w, d) tile of a 32-channel slice: the 6 x 6 x 34 halo is staged once
+// (16-byte cp.async, zero fill = the convolution's padding, so the tap loop has no bounds checks) in a
+// [channel chunk][voxel] layout whose chunk pitch is 1 mod 8 sixteen-byte units (conflict-free 16-byte LDS for a
+// quarter-warp of 4 chunks x 2 depth groups); the 27 x 32 weights and the bias sit in shared memory as well.  2.4x instead of
+// 9x re-read, same thread micro-kernel (8 channels x 4 outputs along D, six planes feed three taps each), same fma order.
+constexpr int kPeTH = 4, kPeTW = 4, kPeTD = 32, kPeCC = 32;
+constexpr int kPeHD = kPeTD + 2, kPeHW = kPeTW + 2, kPeHH = kPeTH + 2;
+constexpr int kPeNV = kPeHH * kPeHW * kPeHD;                  // 1224 halo voxels
+constexpr int kPePitch = kPeNV + 1;                            // 1225 = 1 mod 8
+constexpr int kPeSmem = 4 * kPePitch * 16 + 28 * kPeCC * 4;   // halo + weights [27][32] + bias [32]
+
+__global__ void __launch_bounds__(256, 2)
+posenc_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ xlo, const float* __restrict__ w,
+                   const float* __restrict__ bias, bf16* __restrict__ y, bf16* __restrict__ ylo, int H, int W, int D, int C,
+                   int tiles_w, int tiles_d, int slices) {
+    extern __shared__ __align__(16) unsigned char pe_smem[];
+    uint4* sx = reinterpret_cast<uint4*>(pe_smem);                              // [4][kPePitch]
+    float* sw = reinterpret_cast<float*>(pe_smem + 4 * kPePitch * 16);          // [27][32], then bias [32]
+    const int tid = threadIdx.x;
+    int t = blockIdx.x;
+    const int cs = t % slices; t /= slices;
+    const int td = t % tiles_d; t /= tiles_d;
+    const int tw = t % tiles_w;
+    const int th = t / tiles_w;
+    const int b = blockIdx.y;
+    const int h0 = th * kPeTH, w0 = tw * kPeTW, d0t = td * kPeTD, c0s = cs * kPeCC;
+    const bf16* xb = x + (int64_t)b * H * W * D * C + c0s;
+    for (int i = tid; i < kPeNV * 4; i += 256) {
+        const int chunk = i & 3, v = i >> 2;
+        const int hd = v % kPeHD, hw = (v / kPeHD) % kPeHW, hh = v / (kPeHD * kPeHW);
+        const int gh = h0 - 1 + hh, gw = w0 - 1 + hw, gd = d0t - 1 + hd;
+        const bool ok = gh >= 0 && gh < H && gw >= 0 && gw < W && gd >= 0 && gd < D;
+        const bf16* src = ok ? xb + (((int64_t)gh * W + gw) * D + gd) * C + chunk * 8 : x;
+        cp_async16_zfill(sx + chunk * kPePitch + v, src, ok ? 16 : 0);
+    }
+    for (int i = tid; i < 27 * kPeCC; i += 256) sw[i] = w[(i >> 5) * C + c0s + (i & 31)];
+    if (tid < kPeCC) sw[27 * kPeCC + tid] = bias[c0s + tid];
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int chunk = tid & 3, dg = (tid >> 2) & 7;
+    const uint4* sxc = sx + chunk * kPePitch;
+    const float* swc = sw + chunk * 8;
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+        const int col = (tid >> 5) + it * 8;                    // 0..15
+        const int lh = col >> 2, lw = col & 3;
+        const int gh = h0 + lh, gw = w0 + lw, gd0 = d0t + dg * 4;
+        if (gh >= H || gw >= W || gd0 >= D) continue;
+        float acc[4][8];
+        {
+            float b8[8];
+            load_vec(swc + 27 * kPeCC, *reinterpret_cast<float(*)[4]>(b8));
+            load_vec(swc + 27 * kPeCC + 4, *reinterpret_cast<float(*)[4]>(b8 + 4));
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[o][i] = b8[i];
+        }
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const uint4* colp = sxc + ((lh + kh) * kPeHW + (lw + kw)) * kPeHD + dg * 4;    // halo plane d0 - 1
+                uint4 raw[6];
+#pragma unroll
+                for (int pl = 0; pl < 6; ++pl) raw[pl] = colp[pl];
+                float wt[3][8];
+#pragma unroll
+                for (int kd = 0; kd < 3; ++kd) {
+                    const float* wp = swc + (kh * 9 + kw * 3 + kd) * kPeCC;
+                    load_vec(wp, *reinterpret_cast<float(*)[4]>(wt[kd]));
+                    load_vec(wp + 4, *reinterpret_cast<float(*)[4]>(wt[kd] + 4));
+                }
+#pragma unroll
+                for (int pl = 0; pl < 6; ++pl) {
+                    const uint32_t u[4] = {raw[pl].x, raw[pl].y, raw[pl].z, raw[pl].w};
+                    float xv[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        xv[2 * i] = __uint_as_float(u[i] << 16);
+                        xv[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+                    }
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const int o = pl - kd;
+                        if (o < 0 || o > 3) continue;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[o][i] = fmaf(xv[i], wt[kd][i], acc[o][i]);
+                    }
+                    if (kh == 1 && kw == 1 && pl >= 1 && pl <= 4) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[pl - 1][i] += xv[i];
+                    }
+                }
+            }
+        const int64_t off = ((((int64_t)b * H + gh) * W + gw) * D + gd0) * C + c0s + chunk * 8;
+        if (xlo) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (gd0 + o < D) {
+                    float l8[8];
+                    load_vec(xlo + off + (int64_t)o * C, l8);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[o][i] += l8[i];
+                }
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (gd0 + o < D) {
+                if (ylo) {
+                    float h8[8], l8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { h8[i] = __bfloat162float(__float2bfloat16_rn(acc[o][i])); l8[i] = acc[o][i] - h8[i]; }
+                    store_vec(y + off + (int64_t)o * C, h8);
+                    store_vec(ylo + off + (int64_t)o * C, l8);
+                } else {
+                    store_vec(y + off + (int64_t)o * C, acc[o]);
+                }
+            }
+    }
+}
+
 static int posenc_impl(const void* x, const void* xlo, const float* w, const float* bias, void* y, void* ylo, int B,
                        int H, int W, int D, int C, int dtype, ltu_stream_t stream) {
     LTU_ARG_CHECK(x && w && bias && y, "posenc_dwconv3: null pointer");
@@ -753,7 +879,21 @@ static int posenc_impl(const void* x, const void* xlo, const float* w, const flo
     // posenc2_kernel (register-sliding along D) measured 2x SLOWER than the plain 27-tap kernel on B200
     // (404 vs 219 us on [8,39,23,64,128]: a serial chain of dependent loads per thread at 114 registers);
     // kept for reference, not dispatched.
-    if (vec_ok) {
+    static const bool tiled = [] { const char* e = getenv("LTU_POSENC_TILED"); return !(e && e[0] == '0'); }();   // A/B switch
+    if (vec_ok && tiled && C % kPeCC == 0 && B <= 65535) {
+        const int tiles_h = (H + kPeTH - 1) / kPeTH, tiles_w = (W + kPeTW - 1) / kPeTW, tiles_d = (D + kPeTD - 1) / kPeTD;
+        const int slices = C / kPeCC;
+        const int64_t blocks = (int64_t)tiles_h * tiles_w * tiles_d * slices;
+        LTU_ARG_CHECK(blocks < ((int64_t)1 << 31), "posenc_dwconv3: tensor too large");
+        static thread_local int conf = -1;
+        int dev; cudaGetDevice(&dev);
+        if (conf != dev) {
+            cudaFuncSetAttribute(posenc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPeSmem);
+            conf = dev;
+        }
+        posenc_tile_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, kPeSmem, (cudaStream_t)stream>>>(
+            (const bf16*)x, (const bf16*)xlo, w, bias, (bf16*)y, (bf16*)ylo, H, W, D, C, tiles_w, tiles_d, slices);
+    } else if (vec_ok) {
         int64_t total = (int64_t)B * H * W * ((D + 3) / 4) * (C / 8);
         int64_t blocks = ceil_div64(total, 256);
         LTU_ARG_CHECK(blocks < ((int64_t)1 << 31), "posenc_dwconv3: tensor too large");

@@ -130,50 +130,62 @@ __device__ __forceinline__ Tap make_tap(float coord, int size) {
     return t;
 }
 
+// One block = one output row index oi x 4 column indices oj x every (depth, channel) vector of those four columns.  The
+// fisheye coordinates and bilinear taps depend on (oi, oj) only -- about twenty IEEE divisions -- and are computed ONCE per
+// block (five threads, shared memory) instead of once per 16-byte output vector as in round 1, where the kernel was bound
+// by that arithmetic (0.5-1.0 TB/s of its bytes); a warp then streams 512-byte segments of one column.  Same device
+// functions, same operands => the taps and the results are bit-identical to the per-element version.
 template <typename T>
 __global__ void __launch_bounds__(256)
 roi_resample_kernel(const T* __restrict__ x, const float* __restrict__ box, T* __restrict__ y, int ih, int iw,
                     int oh, int ow, int d, int C, int h_full, int w_full, int roi_h, int roi_w, int eval_h,
                     int eval_w, int direction) {
     constexpr int VN = Vec<T>::N;
-    const int b = blockIdx.y;
-    const int cv = C / VN;
-    const float x0 = box[b * 6 + 0], y0 = box[b * 6 + 1], x1 = box[b * 6 + 3], y1 = box[b * 6 + 4];
-    const int64_t total = (int64_t)oh * ow * d * cv;
-    const T* xb = x + (int64_t)b * ih * iw * d * C;
-    T* yb = y + (int64_t)b * oh * ow * d * C;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        int c0 = (int)(idx % cv) * VN;
-        int64_t t = idx / cv;
-        int dd = (int)(t % d); t /= d;
-        int oj = (int)(t % ow);
-        int oi = (int)(t / ow);
-        float ch, cw;
-        if (direction == 0) {
-            ch = fisheye_fwd(x0, x1, h_full - 1, roi_h, eval_h, oi);
-            cw = fisheye_fwd(y0, y1, w_full - 1, roi_w, eval_w, oj);
+    __shared__ Tap taps[5];                                    // [0] = row tap, [1..4] = column taps
+    const int b = blockIdx.z, oi = blockIdx.y, oj0 = (int)blockIdx.x * 4;
+    const int cv = C / VN, nvec = d * cv;
+    if (threadIdx.x < 5) {
+        const float x0 = box[b * 6 + 0], y0 = box[b * 6 + 1], x1 = box[b * 6 + 3], y1 = box[b * 6 + 4];
+        if (threadIdx.x == 0) {
+            const float ch = direction == 0 ? fisheye_fwd(x0, x1, h_full - 1, roi_h, eval_h, oi)
+                                            : fisheye_back(x0, x1, h_full - 1, roi_h, eval_h, oi);
+            taps[0] = make_tap(ch, ih);
         } else {
-            ch = fisheye_back(x0, x1, h_full - 1, roi_h, eval_h, oi);
-            cw = fisheye_back(y0, y1, w_full - 1, roi_w, eval_w, oj);
+            const int oj = oj0 + (int)threadIdx.x - 1;
+            const float cw = direction == 0 ? fisheye_fwd(y0, y1, w_full - 1, roi_w, eval_w, oj)
+                                            : fisheye_back(y0, y1, w_full - 1, roi_w, eval_w, oj);
+            taps[threadIdx.x] = make_tap(cw, iw);
         }
-        Tap th = make_tap(ch, ih), tw = make_tap(cw, iw);
+    }
+    __syncthreads();
+    const int q = threadIdx.x >> 6, oj = oj0 + q;
+    if (oj >= ow) return;
+    const Tap th = taps[0], tw = taps[1 + q];
+    const T* xb = x + (int64_t)b * ih * iw * d * C;
+    T* yb = y + (((int64_t)b * oh + oi) * ow + oj) * (int64_t)nvec * VN;
+    const T* src[4];
+    float wt[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+            wt[a * 2 + bb] = (a ? th.w1 : th.w0) * (bb ? tw.w1 : tw.w0);
+            const int hi = a ? th.i1 : th.i0, wi = bb ? tw.i1 : tw.i0;
+            src[a * 2 + bb] = xb + ((int64_t)hi * iw + wi) * (int64_t)nvec * VN;
+        }
+    for (int v = (int)(threadIdx.x & 63); v < nvec; v += 64) {
         float acc[VN];
 #pragma unroll
         for (int i = 0; i < VN; ++i) acc[i] = 0.f;
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+        for (int k = 0; k < 4; ++k) {
+            if (wt[k] == 0.f) continue;
+            float val[VN];
+            load_vec(src[k] + (int64_t)v * VN, val);
 #pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {
-                float wt = (a ? th.w1 : th.w0) * (bb ? tw.w1 : tw.w0);
-                if (wt == 0.f) continue;
-                int hi = a ? th.i1 : th.i0, wi = bb ? tw.i1 : tw.i0;
-                float v[VN];
-                load_vec(xb + (((int64_t)hi * iw + wi) * d + dd) * C + c0, v);
-#pragma unroll
-                for (int i = 0; i < VN; ++i) acc[i] = fmaf(wt, v[i], acc[i]);
-            }
-        store_vec(yb + idx * VN, acc);
+            for (int i = 0; i < VN; ++i) acc[i] = fmaf(wt[k], val[i], acc[i]);
+        }
+        store_vec(yb + (int64_t)v * VN, acc);
     }
 }
 
@@ -337,11 +349,8 @@ extern "C" int ltu_roi_resample(const void* x, const float* box, void* y, int B,
     LTU_ARG_CHECK(aligned16(x) && aligned16(y), "roi_resample: pointers must be 16-byte aligned");
     const int ih = direction == 0 ? h : eval_h, iw = direction == 0 ? w : eval_w;
     const int oh = direction == 0 ? eval_h : h, ow = direction == 0 ? eval_w : w;
-    int64_t total = (int64_t)oh * ow * d * (C / vn);
-    int64_t bx = ceil_div64(total, 256);
-    int64_t cap = ceil_div64((int64_t)sm_count() * 16, B);
-    if (bx > cap) bx = cap;
-    dim3 grid((unsigned)bx, B);
+    LTU_ARG_CHECK(oh <= 65535, "roi_resample: too many output rows");
+    dim3 grid((unsigned)((ow + 3) / 4), (unsigned)oh, (unsigned)B);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == LTU_F32)
         roi_resample_kernel<float><<<grid, 256, 0, st>>>((const float*)x, box, (float*)y, ih, iw, oh, ow, d, C, h, w, roi_h, roi_w, eval_h, eval_w, direction);

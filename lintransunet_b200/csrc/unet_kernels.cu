@@ -46,50 +46,58 @@ __device__ __forceinline__ void lin_tap(int o, int in_size, float ratio, int& i0
     l0 = 1.f - l1;
 }
 
+// One block = a 4 x 4 patch of output (oh, ow) positions x 64 consecutive 16-byte vectors along (od, c): the 16 positions
+// read at most 4 x 4 input columns between them (scale 2, align_corners), so 3 of 4 tap loads hit L1 and the kernel moves
+// about what it writes instead of 4-8x that through L2 (round 1: one output vector per thread in linear order, 64-bit
+// div/mod per element, 1.0-1.5 TB/s of its bytes).  A warp = 32 consecutive vectors of one position: 512-byte
+// segments.  The per-output arithmetic (tap weights, fma order) is unchanged, so results are bit-identical.
 template <typename T>
 __global__ void __launch_bounds__(256)
-upsample_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int D, int C, int fd) {
+upsample_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int D, int C, int fd, int tiles_h) {
     constexpr int VN = Vec<T>::N;
     const int Ho = 2 * H, Wo = 2 * W, Do = fd * D;
     const int cv = C / VN;
+    const int nvec = Do * cv;                                   // vectors of one output column
     const float rh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
     const float rw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
     const float rd = Do > 1 ? (float)(D - 1) / (float)(Do - 1) : 0.f;
-    const int64_t total = (int64_t)B * Ho * Wo * Do * cv;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        int c0 = (int)(idx % cv) * VN;
-        int64_t t = idx / cv;
-        int od = (int)(t % Do); t /= Do;
-        int ow = (int)(t % Wo); t /= Wo;
-        int oh = (int)(t % Ho);
-        int b = (int)(t / Ho);
-        int h0, h1, w0, w1, d0, d1;
-        float lh0, lh1, lw0, lw1, ld0, ld1;
+    const int v = (int)blockIdx.x * 64 + (int)(threadIdx.x & 63);
+    const int ow = (int)blockIdx.y * 4 + (int)(threadIdx.x >> 6);
+    const int b = (int)blockIdx.z / tiles_h, oh0 = ((int)blockIdx.z % tiles_h) * 4;
+    if (v >= nvec || ow >= Wo) return;
+    const int od = v / cv, c0 = (v - od * cv) * VN;
+    int w0, w1, d0, d1;
+    float lw0, lw1, ld0, ld1;
+    lin_tap(ow, W, rw, w0, w1, lw0, lw1);
+    if (fd == 1) { d0 = d1 = od; ld0 = 1.f; ld1 = 0.f; }
+    else lin_tap(od, D, rd, d0, d1, ld0, ld1);
+    const T* xb = x + (int64_t)b * H * W * D * C + c0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int oh = oh0 + j;
+        if (oh >= Ho) break;
+        int h0, h1;
+        float lh0, lh1;
         lin_tap(oh, H, rh, h0, h1, lh0, lh1);
-        lin_tap(ow, W, rw, w0, w1, lw0, lw1);
-        if (fd == 1) { d0 = d1 = od; ld0 = 1.f; ld1 = 0.f; }
-        else lin_tap(od, D, rd, d0, d1, ld0, ld1);
         float acc[VN];
 #pragma unroll
         for (int i = 0; i < VN; ++i) acc[i] = 0.f;
-        const T* xb = x + (int64_t)b * H * W * D * C + c0;
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int bb = 0; bb < 2; ++bb) {
-                int hh = a ? h1 : h0, ww = bb ? w1 : w0;
-                float whw = (a ? lh1 : lh0) * (bb ? lw1 : lw0);
+                const int hh = a ? h1 : h0, ww = bb ? w1 : w0;
+                const float whw = (a ? lh1 : lh0) * (bb ? lw1 : lw0);
                 const T* row = xb + ((int64_t)hh * W + ww) * D * C;
                 float v0[VN];
                 load_vec(row + (int64_t)d0 * C, v0);
-                float wt0 = whw * ld0;
+                const float wt0 = whw * ld0;
 #pragma unroll
                 for (int i = 0; i < VN; ++i) acc[i] = fmaf(wt0, v0[i], acc[i]);
                 if (ld1 != 0.f) {
                     float v1[VN];
                     load_vec(row + (int64_t)d1 * C, v1);
-                    float wt1 = whw * ld1;
+                    const float wt1 = whw * ld1;
 #pragma unroll
                     for (int i = 0; i < VN; ++i) acc[i] = fmaf(wt1, v1[i], acc[i]);
                 }
@@ -311,10 +319,11 @@ extern "C" int ltu_upsample_trilinear(const void* x, void* y, int B, int H, int 
     const int vn = dtype == LTU_F32 ? 4 : 8;
     LTU_ARG_CHECK(B > 0 && H > 0 && W > 0 && D > 0 && C % vn == 0 && (fd == 1 || fd == 2), "upsample_trilinear: bad shape");
     LTU_ARG_CHECK(aligned16(x) && aligned16(y), "upsample_trilinear: pointers must be 16-byte aligned");
-    int64_t total = (int64_t)B * 2 * H * 2 * W * fd * D * (C / vn);
-    unsigned g = grid_for(total, 256, 16);
-    if (dtype == LTU_F32) upsample_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, B, H, W, D, C, fd);
-    else upsample_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, D, C, fd);
+    const int nvec = fd * D * (C / vn), tiles_h = (2 * H + 3) / 4;
+    LTU_ARG_CHECK((int64_t)B * tiles_h <= 65535 && (2 * W + 3) / 4 <= 65535, "upsample_trilinear: grid too large");
+    const dim3 g((unsigned)((nvec + 63) / 64), (unsigned)((2 * W + 3) / 4), (unsigned)(B * tiles_h));
+    if (dtype == LTU_F32) upsample_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, H, W, D, C, fd, tiles_h);
+    else upsample_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, H, W, D, C, fd, tiles_h);
     LTU_LAUNCH_CHECK("upsample_trilinear");
     count_launch(1);
     return LTU_OK;

@@ -311,7 +311,7 @@ def posenc_dwconv3(x: torch.Tensor, w27c: torch.Tensor, bias: torch.Tensor) -> t
     dev = _chk(x, w27c, bias)
     B, H, W, D, C = x.shape
     y = torch.empty_like(x)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("posenc", 2 * x.numel() * x.element_size(), 2 * 27 * x.numel())) as st:
         check(_native.lib().ltu_posenc_dwconv3(_p(x), _p(w27c), _p(bias), _p(y), B, H, W, D, C, _dt(x), st),
               "ltu_posenc_dwconv3")
     return y
@@ -324,7 +324,7 @@ def posenc_dwconv3_split(x_hi: torch.Tensor, x_lo: Optional[torch.Tensor], w27c:
         raise TypeError("posenc_dwconv3_split: bf16 tokens only")
     B, H, W, D, C = x_hi.shape
     y_hi, y_lo = torch.empty_like(x_hi), torch.empty_like(x_hi)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("posenc", (4 if x_lo is not None else 3) * x_hi.numel() * 2, 2 * 27 * x_hi.numel())) as st:
         check(_native.lib().ltu_posenc_dwconv3_split(_p(x_hi), _p(x_lo), _p(w27c), _p(bias), _p(y_hi), _p(y_lo),
                                                      B, H, W, D, C, st), "ltu_posenc_dwconv3_split")
     return y_hi, y_lo
@@ -525,7 +525,7 @@ def instnorm_finalize(partials: torch.Tensor, voxels: int, eps: float = 1e-5) ->
     dev = _chk(partials)
     B, tiles, C, _ = partials.shape
     stats = torch.empty(B, C, 2, dtype=torch.float32, device=dev)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("instnorm_finalize", partials.numel() * 4, 0)) as st:
         check(_native.lib().ltu_instnorm_finalize(_p(partials), _p(stats), B, tiles, C, voxels, eps, st),
               "ltu_instnorm_finalize")
     return stats
@@ -626,7 +626,7 @@ def s2d_input(x: torch.Tensor, dtype: torch.dtype, cpad: int = 4) -> torch.Tenso
     if cin != 1:
         raise ValueError("windows_embedding requires dim_input == 1 (model/Unet_3Dblock.py:132)")
     y = torch.empty(B, H // 2, W // 2, D, cpad, dtype=dtype, device=dev)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("s2d_input", x.numel() * 4, 0)) as st:
         check(_native.lib().ltu_s2d_input(_p(x), _p(y), B, H, W, D, cpad, _dt(y), st), "ltu_s2d_input")
     return y
 
@@ -636,7 +636,7 @@ def upsample_trilinear(x: torch.Tensor, fd: int) -> torch.Tensor:
     dev = _chk(x)
     B, H, W, D, C = x.shape
     y = torch.empty(B, 2 * H, 2 * W, fd * D, C, dtype=x.dtype, device=dev)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("upsample", x.numel() * x.element_size() * (1 + 4 * fd), 0)) as st:
         check(_native.lib().ltu_upsample_trilinear(_p(x), _p(y), B, H, W, D, C, fd, _dt(x), st),
               "ltu_upsample_trilinear")
     return y
@@ -682,7 +682,7 @@ def mask_softmax(logits: torch.Tensor, want_mask: bool):
     B, h, w, d, C = logits.shape
     mask = torch.empty(B, C, h, w, d, dtype=torch.float32, device=dev) if want_mask else None
     fg = torch.empty(B, h, w, d, dtype=torch.float32, device=dev)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("mask_softmax", logits.numel() * 4, 0)) as st:
         check(_native.lib().ltu_mask_softmax(_p(logits), _p(mask), _p(fg), B, h * w * d, C, st), "ltu_mask_softmax")
     return mask, fg
 
@@ -693,7 +693,7 @@ def gate_fused(a: torch.Tensor, stats_a: torch.Tensor, g: torch.Tensor, stats_g:
     B, Ci = a.shape[0], a.shape[-1]
     V = a.numel() // (B * Ci)
     out = torch.empty_like(skip)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("gate", 4 * a.numel() * a.element_size(), 0)) as st:
         check(_native.lib().ltu_gate_fused(_p(a), _p(stats_a), _p(g), _p(stats_g), _p(psi_w), _p(psi_b), _p(skip),
                                            _p(out), B, V, Ci, _dt(a), st), "ltu_gate_fused")
     return out
@@ -739,7 +739,7 @@ def roi_resample(x: torch.Tensor, box: torch.Tensor, full_hw: Tuple[int, int], r
     h, w = full_hw
     oh, ow = (eval_h, eval_w) if direction == 0 else (h, w)
     y = torch.empty(B, oh, ow, d, C, dtype=x.dtype, device=dev)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("roi_resample", 2 * x.numel() * x.element_size(), 0)) as st:
         check(_native.lib().ltu_roi_resample(_p(x), _p(box), _p(y), B, h, w, d, C, roi_h, roi_w, eval_h, eval_w,
                                              direction, _dt(x), st), "ltu_roi_resample")
     return y
@@ -771,7 +771,7 @@ def head_d2s_softmax(logits: torch.Tensor, cout: int, want_probs: bool, want_one
     probs = torch.empty(shp, dtype=torch.float32, device=dev) if want_probs else None
     onehot = torch.empty(shp, dtype=torch.float32, device=dev) if want_onehot else None
     labels = torch.empty((B, 2 * H2, 2 * W2, D), dtype=torch.uint8, device=dev) if want_labels else None
-    with _Guard(dev) as st:
+    with _Guard(dev, ("head_d2s_softmax", logits.numel() * 4, 0)) as st:
         check(_native.lib().ltu_head_d2s_softmax(_p(logits), _p(probs), _p(onehot), _p(labels), B, H2, W2, D, cout, st),
               "ltu_head_d2s_softmax")
     return probs, onehot, labels
@@ -980,7 +980,7 @@ def ctx_pack(ctx: torch.Tensor) -> torch.Tensor:
     dev = _chk(ctx)
     B, heads = ctx.shape[0], ctx.shape[1]
     out = torch.empty(B * heads * 32, 64, dtype=torch.bfloat16, device=dev)
-    with _Guard(dev) as st:
+    with _Guard(dev, ("ctx_pack", ctx.numel() * 4, 0)) as st:
         check(_native.lib().ltu_ctx_pack_bf16(_p(ctx), _p(out), B, heads, st), "ltu_ctx_pack_bf16")
     return out
 

@@ -138,7 +138,8 @@ def test_gelu(dtype):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(1, 128, 5, 4, 6), (2, 256, 3, 3, 8), (1, 128, 1, 1, 1), (1, 256, 2, 7, 1),
-                                   (1, 128, 5, 4, 37), (2, 256, 3, 4, 16), (1, 128, 2, 2, 64)])
+                                   (1, 128, 5, 4, 37), (2, 256, 3, 4, 16), (1, 128, 2, 2, 64), (2, 128, 9, 7, 70),
+                                   (1, 64, 6, 5, 33), (1, 40, 3, 3, 9)])
 def test_posenc(dtype, shape):
     ops = _ops()
     from lintransunet_b200.unet import Conv3dPosEmbedding, _pos_w
