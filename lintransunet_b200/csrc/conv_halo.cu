@@ -45,6 +45,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 template <int CIN, int NT, int TH, int TW, int KS>
 __global__ void __launch_bounds__(256, (NT == 2 ? 2 : 1))
 conv3d_halo_kernel(const HaloParams p) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: instnorm_finalize / _apply may be scheduled under this grid's tail (no-op without a PDL dependent)
     constexpr int TD = 32, PAD = KS / 2, HH = TH + 2 * PAD, HW = TW + 2 * PAD, HD = TD + 2 * PAD;
     constexpr int TAPS = KS * KS * KS;
     constexpr int VB = CIN * 2;                               // bytes per halo voxel (no padding: swizzled)
@@ -249,6 +250,7 @@ conv3d_halo_kernel(const HaloParams p) {
 template <int CIN, int NT, int TH, int TW, int KS, int NW, int MG>
 __global__ void __launch_bounds__(NW * 32, 1)
 conv3d_halo_p_kernel(const HaloParams p, int total_tiles) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: instnorm_finalize / _apply may be scheduled under this grid's tail (no-op without a PDL dependent)
     constexpr int TD = 32, PAD = KS / 2, HH = TH + 2 * PAD, HW = TW + 2 * PAD, HD = TD + 2 * PAD;
     constexpr int TAPS = KS * KS * KS;
     constexpr int VB = CIN * 2;

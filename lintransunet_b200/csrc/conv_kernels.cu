@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(1024)
 instnorm_finalize_kernel(const float* __restrict__ partials, float* __restrict__ stats, int B, int tiles, int C,
                          double inv_vox, float eps) {
     __shared__ double red[32][32][2];
+    pdl_prologue();          // launched with programmatic stream serialisation: scheduled under the producing conv's tail
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * 32 + lane;
     double s = 0.0, q = 0.0;
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(256)
 instnorm_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const T* __restrict__ res,
                       T* __restrict__ y, int64_t V, int C, int act) {
     constexpr int VN = Vec<T>::N;
+    pdl_prologue();          // the statistics come from instnorm_finalize, which is still running when this grid is scheduled
     const int b = blockIdx.y;
     const int cv = C / VN;
     const int64_t total = V * cv;
@@ -404,8 +406,9 @@ extern "C" int ltu_instnorm_finalize(const float* partials, float* stats, int B,
                                      float eps, ltu_stream_t stream) {
     LTU_ARG_CHECK(partials && stats && B > 0 && tiles > 0 && C > 0 && voxels > 0, "instnorm_finalize: bad arguments");
     LTU_ARG_CHECK(B <= 65535, "instnorm_finalize: B too large");
-    instnorm_finalize_kernel<<<dim3((C + 31) / 32, B), 1024, 0, (cudaStream_t)stream>>>(partials, stats, B, tiles, C, 1.0 / (double)voxels, eps);
-    LTU_LAUNCH_CHECK("instnorm_finalize");
+    cudaError_t le = launch_pdl(instnorm_finalize_kernel, dim3((C + 31) / 32, B), dim3(1024), 0, (cudaStream_t)stream,
+                                partials, stats, B, tiles, C, 1.0 / (double)voxels, eps);
+    if (le != cudaSuccess) { set_error("instnorm_finalize: launch failed: %s", cudaGetErrorString(le)); return (int)le; }
     count_launch(1);
     return LTU_OK;
 }
@@ -437,9 +440,10 @@ extern "C" int ltu_instnorm_apply(const void* x, const float* stats, const void*
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, B);
-    if (dtype == LTU_F32) instnorm_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, stats, (const float*)residual, (float*)y, voxels, C, act);
-    else instnorm_apply_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, stats, (const bf16*)residual, (bf16*)y, voxels, C, act);
-    LTU_LAUNCH_CHECK("instnorm_apply");
+    cudaError_t le;
+    if (dtype == LTU_F32) le = launch_pdl(instnorm_apply_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)x, stats, (const float*)residual, (float*)y, voxels, C, act);
+    else le = launch_pdl(instnorm_apply_kernel<bf16>, grid, dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, stats, (const bf16*)residual, (bf16*)y, voxels, C, act);
+    if (le != cudaSuccess) { set_error("instnorm_apply: launch failed: %s", cudaGetErrorString(le)); return (int)le; }
     count_launch(1);
     return LTU_OK;
 }

@@ -37,6 +37,7 @@ static bool use_persistent_tc() {
 
 __global__ void __launch_bounds__(kTcThreads, 4)
 conv3d_tc_kernel(const TcParams p) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: instnorm_finalize / _apply may be scheduled under this grid's tail (no-op without a PDL dependent)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve: [stages][A 16 KB][B Cout*128 B] | barriers | tmem slot | stat staging
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);

@@ -67,6 +67,7 @@ template <bool kMasked>
 __global__ void __launch_bounds__(kT3Threads, 1)
 conv3d_tc3_kernel_t(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
                   const __grid_constant__ CUtensorMap tm_w, const T3Params p) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: instnorm_finalize / _apply may be scheduled under this grid's tail (no-op without a PDL dependent)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
