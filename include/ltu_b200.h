@@ -170,6 +170,18 @@ int ltu_linear_fused(const void* x, int64_t rows, int K, const void* w_bf16, con
                      int epi, const void* res_hi, const void* res_lo, const float* gamma,
                      const float* beta, float eps, void* y_hi, void* y_lo, ltu_stream_t stream);
 
+/* Key / value half of linear_attention for d_model 128, 4 heads, as ONE launch (+ the fixed-order merge):
+ *     ctx[b][h] = softmax_N(x_b Wk^T + bk)_h^T (x_b Wv^T + bv)_h
+ * i.e. the K and V projections of MultihAttention.forward (model/trans_block.py:155-156) fused with the context
+ * reduction of linear_attention (:59-60): K and V are never written to memory (the separate path, ltu_linear_fused +
+ * ltu_kv_reduce, writes and re-reads 4 x rows x C x 2 bytes).  x bf16 [B][N][128]; w_kv bf16 [256][128] = Wk rows then Wv
+ * rows; bias fp32 [256]; ctx fp32 [B][4][32][32] exactly as ltu_kv_reduce produces it (K, V rounded to bf16 the same way).
+ * N % 32 == 0, B <= 30.  workspace: ltu_kv_project_reduce_workspace(B, N) bytes.  supported(): dispatch hint.        */
+int ltu_kv_project_reduce_supported(int C, int heads, int64_t N);
+size_t ltu_kv_project_reduce_workspace(int B, int64_t N);
+int ltu_kv_project_reduce(const void* x, const void* w_kv, const float* bias, float* ctx, void* workspace,
+                          size_t workspace_bytes, int B, int64_t N, ltu_stream_t stream);
+
 /* Fused feed-forward half of SelfAttentionLayer (model/trans_block.py:207-210: linear1 -> erf GELU ->
  * linear2 -> residual -> layer_norm2, dropouts are identity in eval) as ONE persistent tcgen05 kernel:
  *     y = LayerNorm(x + W2 gelu(W1 x + b1) + b2) * gamma + beta

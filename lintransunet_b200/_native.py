@@ -49,6 +49,9 @@ SIGNATURES = {
     "ltu_conv3d_tc3_masked": (I, [P, I, P, I, I, I, I, I, P, I, I, P, I, P, P, I, P, P, P]),
     "ltu_linear_tc": (I, [P, I, L, P, P, I, P, I, I, P, P, P, F, P]),
     "ltu_linear_fused": (I, [P, L, I, P, P, I, I, P, P, P, P, F, P, P, P]),
+    "ltu_kv_project_reduce_supported": (I, [I, I, L]),
+    "ltu_kv_project_reduce_workspace": (Z, [I, L]),
+    "ltu_kv_project_reduce": (I, [P, P, P, P, P, Z, I, L, P]),
     "ltu_ffn_fused_supported": (I, [I]),
     "ltu_ffn_fused": (I, [P, L, I, P, P, P, P, P, P, F, P, P]),
     "ltu_ffn_fused_trace": (I, [P, L, I, P, P, P, P, P, P, F, P, P, P]),

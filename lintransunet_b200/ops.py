@@ -949,6 +949,27 @@ def linear_fused(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epi: int 
     return (y, y_lo) if epi == EPI_RES_LN else y
 
 
+def kv_project_reduce_supported(c: int, heads: int, n: int) -> bool:
+    return bool(_native.lib().ltu_kv_project_reduce_supported(c, heads, n))
+
+
+def kv_project_reduce(x: torch.Tensor, w_kv: torch.Tensor, b_kv: torch.Tensor, heads: int) -> torch.Tensor:
+    """ctx fp32 [B, heads, 32, 32] = kv_reduce(x Wk^T + bk, x Wv^T + bv) in one launch: the K/V projection's output tiles
+    are reduced in the GEMM epilogue, K and V never reach memory (csrc/kv_project.cu; d_model 128, 4 heads, bf16).
+    x [B, N, 128] bf16, w_kv [256, 128] bf16 (Wk rows, then Wv rows), b_kv fp32 [256]."""
+    dev = _chk(x, w_kv, b_kv)
+    B, N, C = x.shape
+    if x.dtype != torch.bfloat16 or w_kv.dtype != torch.bfloat16 or tuple(w_kv.shape) != (2 * C, C):
+        raise TypeError("kv_project_reduce needs bf16 tokens and the bf16 [2C, C] K/V weight")
+    L = _native.lib()
+    nbytes = L.ltu_kv_project_reduce_workspace(B, N)
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+    ctx = torch.empty(B, heads, 32, 32, dtype=torch.float32, device=dev)
+    with _Guard(dev, ("kv_project_reduce", B * N * C * 2, 2 * B * N * C * (2 * C + 32))) as st:
+        check(L.ltu_kv_project_reduce(_p(x), _p(w_kv), _p(b_kv), _p(ctx), _p(ws), nbytes, B, N, st), "ltu_kv_project_reduce")
+    return ctx
+
+
 def ffn_fused_supported(c: int) -> bool:
     return bool(_native.lib().ltu_ffn_fused_supported(c))
 

@@ -460,6 +460,8 @@ class MaskTransUnet(nn.Module):
         # bf16 path: the nn.Linear layers of the d_model-256 encoder layers (and bridge 1's K/V projection) on the native
         # TMA + tcgen05 GEMM with fused epilogues instead of cuBLAS + gelu + add_layernorm.  LTU_NATIVE_LINEAR=0 = A/B.
         self.use_native_linear = os.environ.get("LTU_NATIVE_LINEAR", "1") == "1"
+        # d_model 128: reduce K and V inside the K/V projection's epilogue (ltu_kv_project_reduce).  LTU_KV_PROJECT=0 = A/B.
+        self.fuse_kv_project = os.environ.get("LTU_KV_PROJECT", "1") == "1"
         # training: autograd through the native backward (bf16 path; loss.backward() fills p.grad).  LTU_NATIVE_BACKWARD=0
         # turns a training forward with grad into an error instead (there is no other backward).
         self.native_backward = os.environ.get("LTU_NATIVE_BACKWARD", "1") == "1"
@@ -522,7 +524,7 @@ class MaskTransUnet(nn.Module):
     def _knobs(self) -> tuple:
         """Every runtime switch that changes the launched kernels (part of the CUDA-graph cache key)."""
         return (self.use_tensor_cores, self.use_fused_linear, self.fuse_mask_head, self.use_fused_ffn, self.use_fused_attn,
-                self.split_token_stream, self.use_native_linear, self.skip_dead_mask_head, ops.USE_HALO_CONV, ops.USE_TC3_CONV, ops.USE_SV_CONV)
+                self.split_token_stream, self.use_native_linear, self.fuse_kv_project, self.skip_dead_mask_head, ops.USE_HALO_CONV, ops.USE_TC3_CONV, ops.USE_SV_CONV)
 
     def _capture(self, x: torch.Tensor, plan: "_Plan", head: str) -> dict:
         static_x = x.clone()
@@ -566,11 +568,15 @@ class MaskTransUnet(nn.Module):
         if lw.attn_fused and self.use_fused_attn and not (lw.fused and self.use_fused_linear):
             # K/V projection (cuBLAS) -> kv_reduce -> ONE kernel for Q projection, readout, output projection,
             # residual and LayerNorm1; then ONE kernel for the feed-forward half
-            if lw.lin_kv and self.use_native_linear:
-                kv = ops.linear_fused(t, lw.w_kv, lw.bkv_f32)
+            if lw.lin_kv and self.use_native_linear and self.fuse_kv_project and ops.kv_project_reduce_supported(C, lw.nhead, N):
+                # K/V projection and context reduction in ONE launch: K and V never reach memory
+                ctx = ops.kv_project_reduce(t, lw.w_kv, lw.bkv_f32, lw.nhead)
             else:
-                kv = F.linear(t, lw.w_kv, lw.b_kv)
-            ctx = ops.kv_reduce(kv[..., :C], kv[..., C:], lw.nhead)
+                if lw.lin_kv and self.use_native_linear:
+                    kv = ops.linear_fused(t, lw.w_kv, lw.bkv_f32)
+                else:
+                    kv = F.linear(t, lw.w_kv, lw.b_kv)
+                ctx = ops.kv_reduce(kv[..., :C], kv[..., C:], lw.nhead)
             t = ops.attn_out_fused(t, lw.w_q, lw.bq_f32, ops.ctx_pack(ctx), lw.w_o, lw.bo_f32, lw.g1, lw.be1, lw.nhead)
             if lw.ffn and self.use_fused_ffn:
                 return ops.ffn_fused(t, lw.w_1, lw.b1_f32, lw.w_2, lw.b2_f32, lw.g2, lw.be2, 1e-6), None

@@ -591,8 +591,9 @@ def test_encoder_layer_golden(dtype):
         m = MaskTransUnet.__new__(MaskTransUnet)      # only _encoder_layer is exercised
         torch.nn.Module.__init__(m)
         m.use_fused_linear, m.use_fused_ffn, m.use_fused_attn = fused_linear, fused_ffn, fused_attn
-        for native_linear in (True, False):         # K/V projection on ltu_linear_fused / cuBLAS (fused_attn paths)
-            m.use_native_linear = native_linear
+        # K/V half of the fused_attn paths: ltu_kv_project_reduce | ltu_linear_fused + kv_reduce | cuBLAS + kv_reduce
+        for native_linear, fuse_kv in ((True, True), (True, False), (False, False)):
+            m.use_native_linear, m.fuse_kv_project = native_linear, fuse_kv
             y, lo = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
             assert lo is None
             assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2), (fused_linear, fused_ffn, fused_attn)
@@ -628,7 +629,7 @@ def test_encoder_layer_d256_native_linear(B, N):
     ref_plain = O.encoder_layer(x.double(), sdd, pre, 8)
     m = MaskTransUnet.__new__(MaskTransUnet)
     torch.nn.Module.__init__(m)
-    m.use_fused_linear, m.use_fused_ffn, m.use_fused_attn = False, False, False
+    m.use_fused_linear, m.use_fused_ffn, m.use_fused_attn, m.fuse_kv_project = False, False, False, True
     lw = _LayerW(layer, bf)
     assert lw.lin
     out = {}
@@ -729,6 +730,52 @@ def test_linear_fused_is_deterministic_and_rejects_bad_shapes():
         ops.linear_fused(x, w[:200].contiguous(), b[:200].contiguous())        # N not a multiple of 256
     with pytest.raises(RuntimeError):
         ops.linear_fused(x, w, b, ops.EPI_RES_LN, res_hi=x)                     # LayerNorm epilogue needs N == 256
+
+
+@pytest.mark.parametrize("B,N", [(1, 32), (1, 96), (2, 160), (3, 4096), (8, 57408), (5, 7008), (2, 64 * 897), (8, 2976)])
+def test_kv_project_reduce(B, N):
+    """K/V projection + context reduction in one launch (csrc/kv_project.cu) against (a) the separate native path
+    linear_fused -> kv_reduce on the same operands and (b) fp64 torch on the same bf16-rounded K and V."""
+    ops = _ops()
+    bf = torch.bfloat16
+    C, h = 128, 4
+    g = torch.Generator().manual_seed(100 + N % 13)
+    x = (torch.randn(B, N, C, generator=g) * 1.3).to("cuda", bf)
+    w = (torch.randn(2 * C, C, generator=g) * 0.12).to("cuda", bf)
+    b = (torch.randn(2 * C, generator=g) * 0.3).cuda()
+    assert ops.kv_project_reduce_supported(C, h, N)
+    ctx = ops.kv_project_reduce(x, w, b, h)
+    kv = ops.linear_fused(x, w, b)
+    ref_native = ops.kv_reduce(kv[..., :C], kv[..., C:], h)
+    assert ctx.shape == (B, h, 32, 32)
+    assert rel_err(ctx, ref_native) < 2e-3                       # same bf16 K / V, same bf16 P: summation order only
+    k64 = kv[..., :C].double().reshape(B, N, h, 32).transpose(1, 2)
+    v64 = kv[..., C:].double().reshape(B, N, h, 32).transpose(1, 2)
+    ref = torch.softmax(k64, -2).transpose(-1, -2) @ v64
+    assert rel_err(ctx, ref) < 6e-3                              # P is rounded to bf16 (the kernels' tensor-pipe operand)
+    assert torch.equal(ctx, ops.kv_project_reduce(x, w, b, h))    # fixed-order merge: bit-reproducible
+
+
+def test_kv_project_reduce_rescale_path_and_limits():
+    """Keys that run away from the first tile's reference (exact rescale path) and unsupported shapes."""
+    ops = _ops()
+    bf = torch.bfloat16
+    B, N, C, h = 2, 2048, 128, 4
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, N, C, generator=g)
+    x[:, N // 2:] *= 6.0                                          # later tiles carry much larger keys
+    x = x.to("cuda", bf)
+    w = (torch.randn(2 * C, C, generator=g) * 0.5).to("cuda", bf)
+    b = torch.zeros(2 * C).cuda()
+    ctx = ops.kv_project_reduce(x, w, b, h)
+    kv = ops.linear_fused(x, w, b)
+    k64 = kv[..., :C].double().reshape(B, N, h, 32).transpose(1, 2)
+    v64 = kv[..., C:].double().reshape(B, N, h, 32).transpose(1, 2)
+    ref = torch.softmax(k64, -2).transpose(-1, -2) @ v64
+    assert torch.isfinite(ctx).all() and rel_err(ctx, ref) < 1e-2
+    assert not ops.kv_project_reduce_supported(C, h, 100) and not ops.kv_project_reduce_supported(256, 8, 512)
+    with pytest.raises(RuntimeError):
+        ops.kv_project_reduce(x[:, :100].contiguous(), w, b, h)
 
 
 @pytest.mark.parametrize("C", [128, 256])

@@ -59,6 +59,19 @@ def main():
             print(f"| {tag} {name} | {rows} | {K} | {N} | {tf_:.1f} | {io / tf_ / 1e3:.0f} | {io / tf_ / 1e3 / PEAK_BW * 100:.1f}% | "
                   f"{2 * rows * K * N / tf_ / 1e6:.0f} | {tc_:.1f} | {tc_ / tf_:.2f}x |", flush=True)
     print(f"\nper forward (8 layers x bridges 2-4, B=8): fused {tot_f:.0f} us, cuBLAS + separate kernels {tot_c:.0f} us")
+    # bridge 1: K/V projection + kv_reduce as one launch (K, V never written) against the two separate native launches
+    B, N, C, h = 8, 57408, 128, 4
+    xs = [torch.randn(B, N, C, device="cuda").to(bf) for _ in range(4)]
+    w = (torch.randn(2 * C, C, device="cuda") * 0.05).to(bf)
+    b32 = torch.randn(2 * C, device="cuda")
+    t_f = graph_time(lambda i: ops.kv_project_reduce(xs[i], w, b32, h), 4)
+
+    def sep(i):
+        kv = ops.linear_fused(xs[i], w, b32)
+        return ops.kv_reduce(kv[..., :C], kv[..., C:], h)
+    t_s = graph_time(sep, 4)
+    print(f"\nbridge 1 K/V half (B=8, N=57408, C=128): kv_project_reduce {t_f:.1f} us (x read once: "
+          f"{B * N * C * 2 / t_f / 1e3:.0f} GB/s) vs linear_fused + kv_reduce {t_s:.1f} us ({t_s / t_f:.2f}x)")
 
 
 if __name__ == "__main__":
