@@ -482,7 +482,7 @@ def run_ours(args):
         roofline = roof(dominant, bound_of.get(dominant, "hbm")) if dominant else None
         attn = {n: roof(n, "hbm") for n in ("kv_reduce", "q_readout") if n in ksum}
         # d_model=128 layers: the readout, both projections, the FFN and both LayerNorms run inside two fused kernels
-        fused = {n: roof(n, "hbm") for n in ("attn_out_fused", "ffn_fused", "linear_fused") if n in ksum}
+        fused = {n: roof(n, "hbm") for n in ("attn_out_fused", "ffn_fused", "linear_fused", "kv_project_reduce") if n in ksum}
         conv_detail = {n: roof(n, bound_of.get(n, "hbm")) for n in ("conv3d_tc", "conv3d_tc3", "conv3d_sv", "conv3d_halo") if n in ksum}
         line = {"metric": METRIC, "value": win_vox / (ms_step / 1e3), "unit": "voxels/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "step_ms_rank0": step_ms,
@@ -604,7 +604,9 @@ def run_config2(args):
 ALGORITHMIC = {
     "linear_fused": "(rows*K + rows*N (+ residual hi/lo and the lo output for the LayerNorm epilogue))*2 bytes: the nn.Linear "
                     "layers of the d_model-256 encoder layers and bridge 1's K/V projection (TMA + tcgen05, fused epilogues)",
-    "kv_reduce": "2*B*N*C*E bytes (K and V read once)",
+    "kv_reduce": "2*B*N*C*E bytes (K and V read once); bridge 1 (d_model 128) does not appear here: its K and V are reduced inside "
+                 "the projection kernel (kv_project_reduce) and never reach memory",
+    "kv_project_reduce": "rows*C*E bytes (x read once; K and V never written or read: the two launches it replaces move 5x that)",
     "q_readout": "2*B*N*C*E bytes (Q read, out written)",
     "attn_out_fused": "2*rows*C*E bytes (x read once, y written once)",
     "ffn_fused": "2*rows*C*E bytes (x read once, y written once)",

@@ -5,16 +5,16 @@
 // K and V are never written to memory.  The separate path writes them (2 x rows x 128 bf16 from ltu_linear_fused) and reads
 // them back (ltu_kv_reduce): 4 x rows x C x 2 bytes per layer, 470 MB at the benchmark's batch -- more than everything else
 // the layer moves.  Here a persistent TMA + tcgen05 CTA computes the [128 rows x 256] tile  [K | V] = x W_kv^T  into tensor
-// memory (W_kv = 64 KB, resident in shared memory; x streams through a 5-stage TMA ring), and the epilogue warps, which
+// memory (W_kv = 64 KB, resident in shared memory; x streams through a 6-stage TMA ring), and the epilogue warps, which
 // already turn accumulator columns into bf16 rows in a SWIZZLE_128B staging tile, run the kv_reduce warp routine of
 // attn_stream.cu on those staging tiles instead of storing them: K -> P = 2^(k log2e - r_j) in place, ctx += P^T V with
 // ldmatrix.trans + mma.sync m16n8k16, column sums from an all-ones B tile, per-warp reference with an exact rescale path.
 //
 //   warp 0      TMA producer (W once, then the x k-blocks of the CTA's tiles)
 //   warp 1      tcgen05.mma M128 N256 K16 into one of two TMEM accumulators
-//   warps 2-17  four warps per TMEM lane quarter q: warp (q, cg) stages accumulator columns [64 cg, 64 cg + 64) -- cg 0, 1 =
-//               K heads {0,1}, {2,3}; cg 2, 3 = V heads {0,1}, {2,3} -- and, after a 128-thread named barrier, reduces head
-//               cg over the quarter's 32 rows (16 reducing warps per SM, as many as two resident kv_stream CTAs)
+//   warps 2-17  four warps per TMEM lane quarter q: warp (q, cg) reads head cg's 32 K and 32 V accumulator columns of its 32
+//               lanes, stages them as bf16 in a PRIVATE SWIZZLE_128B chunk and reduces that head over the quarter's 32 rows
+//               -- no barrier between epilogue warps (16 reducing warps per SM, as many as two resident kv_stream CTAs)
 // A CTA owns a CONTIGUOUS range of row tiles, so it touches at most two or three samples; a warp keeps its 32 x 32
 // state in registers and flushes a partial (ctx, reference, column sums) when its rows move to the next sample.  The
 // partials (<= 4 per CTA and head, 80 per sample at the benchmark's batch) are merged by the same fixed-order kv_combine
@@ -32,15 +32,14 @@ int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts,
 namespace {
 
 constexpr int kKvpThreads = 576;                              // 18 warps: producer, MMA issue, 16 epilogue / reduce warps
-constexpr int kKvpStages = 2;                                 // x ring; the two TMEM accumulators already run a tile ahead
+constexpr int kKvpStages = 6;                                 // x ring: three tiles of look-ahead
 constexpr int kKvpPart = 32 * 32 + 64;                        // ctx[32][32], m[32], s[32] (the layout kv_combine reads)
 constexpr int kKvpHeads = 4;
 constexpr uint32_t kKvpWBytes = 256 * 128 * 2;                // W_kv: two k-blocks of [256 x 64] bf16
 constexpr uint32_t kKvpABytes = 128 * 128;                    // x k-block: 128 rows x 64 bf16
 constexpr uint32_t kKvpOffRing = kKvpWBytes;
 constexpr uint32_t kKvpOffStaging = kKvpOffRing + kKvpStages * kKvpABytes;
-constexpr uint32_t kKvpStagingBytes = 16 * 4096;               // one [32 rows x 64 columns] bf16 chunk per epilogue warp
-constexpr uint32_t kKvpOffTail = kKvpOffStaging + 2 * kKvpStagingBytes;   // double buffered: stage tile i+1, reduce tile i
+constexpr uint32_t kKvpOffTail = kKvpOffStaging + 16 * 4096;  // one PRIVATE [32 rows x (32 K + 32 V) columns] bf16 chunk per epilogue warp
 constexpr float kL2e = 1.4426950408889634f;
 
 struct KvpTail {
@@ -116,10 +115,12 @@ __device__ __forceinline__ void reset(HeadState& s) {
     s.have_ref = false;
 }
 
-// One head, the warp's 32 rows: tK / tV = shared addresses of the [32 x 64 channel] K and V staging tiles of the head pair,
-// half = head inside the pair.  The K tile is turned into P in place.  (attn_stream.cu, kv_stream_kernel, with sub = 0;
+// One head, the warp's 32 rows: `tile` = shared address of the warp's private [32 rows x 128 B] staging chunk, K of the head in
+// columns 0-31, V in columns 32-63.  The K half is turned into P in place.  (attn_stream.cu, kv_stream_kernel, with sub = 0;
 // the keys are read twice from shared memory -- check, then exponentials -- to keep the register footprint small.)
-__device__ __forceinline__ void reduce_head(HeadState& s, uint32_t tK, uint32_t tV, int half, int valid, int lane) {
+__device__ __forceinline__ void reduce_head(HeadState& s, uint32_t tile, int valid, int lane) {
+    const uint32_t tK = tile, tV = tile;
+    constexpr int half = 0, halfV = 1;                           // K in 16-byte chunks 0-3 of a row, V in chunks 4-7
     const int g = lane >> 2, cc = lane & 3, mi = lane >> 3, lr = lane & 7;
     const uint32_t ones = g == 0 ? 0x3F803F80u : 0u;
     uint32_t addr[4];
@@ -199,7 +200,7 @@ __device__ __forceinline__ void reduce_head(HeadState& s, uint32_t tK, uint32_t 
             ldsm4t(tK + swz(n0 + lr + 8 * (mi >> 1), half * 4 + mt * 2 + (mi & 1)), a[mt]);
 #pragma unroll
         for (int np = 0; np < 2; ++np)
-            ldsm4t(tV + swz(n0 + lr + 8 * (mi & 1), half * 4 + np * 2 + (mi >> 1)), bq[np]);
+            ldsm4t(tV + swz(n0 + lr + 8 * (mi & 1), halfV * 4 + np * 2 + (mi >> 1)), bq[np]);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
@@ -318,9 +319,12 @@ kv_project_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const int e = warp - 2;                          // 0..15
         const int q = warp & 3;                          // TMEM lane quarter (warp id % 4) = rows [32q, 32q + 32) of the tile
         const int cg = e >> 2;                           // stages accumulator columns [64 cg, +64); reduces head cg
-        const int pr = e & 3;                            // the four warps of a quarter share it
-        const uint32_t offK = (uint32_t)(((cg >> 1) * 4 + pr) * 4096);           // K chunk of head pair cg / 2 (this quarter)
-        const uint32_t offV = (uint32_t)(((2 + (cg >> 1)) * 4 + pr) * 4096);     // V chunk of the same pair
+        // Warp (q, cg) owns head cg of rows [32q, 32q + 32): it reads the head's 32 K columns and 32 V columns of its TMEM lanes
+        // itself and stages them in a PRIVATE chunk, so the epilogue has no cross-warp dependency at all: no block or named
+        // barrier, no double buffering (first version: column groups staged by one warp and reduced by another -- two 128-thread
+        // barriers per tile, 116 us; double-buffered staging with one barrier and a 2-stage x ring, 107 us).
+        unsigned char* stg = smem + kKvpOffStaging + e * 4096 + lane * 128;
+        const uint32_t tile_u = sbase + kKvpOffStaging + (uint32_t)(e * 4096);
         const uint32_t swzl = (uint32_t)(lane & 7);
         HeadState hs;
         reset(hs);
@@ -333,46 +337,39 @@ kv_project_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const int64_t slot = ((int64_t)blockIdx.x - c_lo) * 4 + q;
             return p.part + (((int64_t)b * p.nparts + slot) * kKvpHeads + cg) * kKvpPart;
         };
-        const float* bs = tail->bias + cg * 64;
-        // accumulator columns [64 cg, +64) of tile number `it` -> bias -> bf16 -> this warp's chunk of staging buffer it & 1
-        auto stage = [&](uint32_t it) {
+        uint32_t it = 0;
+        for (int T = t0; T < t1; ++T, ++it) {
             const uint32_t abuf = it & 1;
-            const uint32_t tb = tmem_base + abuf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 64);
-            unsigned char* buf = smem + kKvpOffStaging + abuf * kKvpStagingBytes + e * 4096 + lane * 128;
+            const uint32_t tb = tmem_base + abuf * 256u + ((uint32_t)(q * 32) << 16);
             mbar_wait_sleep(smem_u32(&tail->tfull[abuf]), (it >> 1) & 1, 64);
             tc_fence_after();
 #pragma unroll 1
-            for (int c2 = 0; c2 < 2; ++c2) {                                  // 32 accumulator columns at a time (registers)
-                uint32_t v[32];
-                tmem_ld32_nowait(tb + (uint32_t)(c2 * 32), v);
+            for (int c4 = 0; c4 < 4; ++c4) {              // 16 columns at a time: K [32 cg, +32) then V [128 + 32 cg, +32)
+                const int kv = c4 >> 1, off = kv * 128 + cg * 32 + (c4 & 1) * 16;
+                uint32_t v[16];
+                tmem_ld16_nowait(tb + (uint32_t)off, v);
                 tmem_ld_wait();
-                if (c2 == 1) {
+                if (c4 == 3) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&tail->tempty[abuf]));
                 }
+                const float* bs = tail->bias + off;
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
+                for (int jj = 0; jj < 2; ++jj) {
                     const uint32_t* src = v + 8 * jj;
-                    const float4 ba = *reinterpret_cast<const float4*>(bs + c2 * 32 + jj * 8);
-                    const float4 bb = *reinterpret_cast<const float4*>(bs + c2 * 32 + jj * 8 + 4);
+                    const float4 ba = *reinterpret_cast<const float4*>(bs + jj * 8);
+                    const float4 bb = *reinterpret_cast<const float4*>(bs + jj * 8 + 4);
                     uint4 ov;
                     ov.x = pack_bf16x2(__uint_as_float(src[0]) + ba.x, __uint_as_float(src[1]) + ba.y);
                     ov.y = pack_bf16x2(__uint_as_float(src[2]) + ba.z, __uint_as_float(src[3]) + ba.w);
                     ov.z = pack_bf16x2(__uint_as_float(src[4]) + bb.x, __uint_as_float(src[5]) + bb.y);
                     ov.w = pack_bf16x2(__uint_as_float(src[6]) + bb.z, __uint_as_float(src[7]) + bb.w);
-                    const uint32_t j = (uint32_t)(c2 * 4 + jj);
-                    *reinterpret_cast<uint4*>(buf + ((j ^ swzl) << 4)) = ov;
+                    const uint32_t j = (uint32_t)(c4 * 2 + jj);
+                    *reinterpret_cast<uint4*>(stg + ((j ^ swzl) << 4)) = ov;
                 }
             }
-        };
-        // ONE 128-thread barrier per tile: before it every warp of the quarter has reduced tile i (staging buffer i & 1) and
-        // staged tile i+1 (the other buffer); after it tile i+1 may be reduced and buffer i & 1 overwritten
-        if (t0 < t1) stage(0);
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + pr) : "memory");
-        uint32_t it = 0;
-        for (int T = t0; T < t1; ++T, ++it) {
-            if (T + 1 < t1) stage(it + 1);
+            __syncwarp();                                                     // the chunk is visible to the whole warp
             const int64_t row0w = (int64_t)T * 128 + q * 32;
             int valid = (int)(p.rows - row0w < 32 ? p.rows - row0w : 32);
             if (valid > 0) {
@@ -382,10 +379,9 @@ kv_project_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     reset(hs);
                     cur_b = b;
                 }
-                const uint32_t sb = sbase + kKvpOffStaging + (it & 1) * kKvpStagingBytes;
-                reduce_head(hs, sb + offK, sb + offV, cg & 1, valid, lane);
+                reduce_head(hs, tile_u, valid, lane);
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + pr) : "memory");
+            __syncwarp();                                                     // every lane is done with the chunk
         }
         if (cur_b >= 0) { flush_head(hs, slot_ptr(cur_b), lane); done_mask |= 1u << (int)(cur_b - b_first); }
         // slots nobody fills: samples of this CTA's range this warp never touched, and the padding of short ranges

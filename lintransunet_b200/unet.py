@@ -568,7 +568,8 @@ class MaskTransUnet(nn.Module):
         if lw.attn_fused and self.use_fused_attn and not (lw.fused and self.use_fused_linear):
             # K/V projection (cuBLAS) -> kv_reduce -> ONE kernel for Q projection, readout, output projection,
             # residual and LayerNorm1; then ONE kernel for the feed-forward half
-            if lw.lin_kv and self.use_native_linear and self.fuse_kv_project and ops.kv_project_reduce_supported(C, lw.nhead, N):
+            if (lw.lin_kv and self.use_native_linear and self.fuse_kv_project and B <= 30
+                    and ops.kv_project_reduce_supported(C, lw.nhead, N)):
                 # K/V projection and context reduction in ONE launch: K and V never reach memory
                 ctx = ops.kv_project_reduce(t, lw.w_kv, lw.bkv_f32, lw.nhead)
             else:
