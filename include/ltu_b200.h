@@ -170,6 +170,28 @@ int ltu_linear_fused(const void* x, int64_t rows, int K, const void* w_bf16, con
                      int epi, const void* res_hi, const void* res_lo, const float* gamma,
                      const float* beta, float eps, void* y_hi, void* y_lo, ltu_stream_t stream);
 
+/* The same launch with the query half of linear_attention (model/trans_block.py:50 softmax(q) / sqrt(d_k), :65 q . ctx)
+ * carried by the GEMMs around it, so that q_readout never runs and the attention output is never written:
+ *   softmax_cols (epi 0; 0 or a multiple of 256 <= N): output columns [0, softmax_cols) -- the Q third of the fused
+ *     [3C][C] QKV projection -- are written as softmax over each head's 32 columns, divided by sqrt(32);
+ *   samples > 1: x / residual / y are [samples][rows / samples][cols] and w_bf16 holds ONE [N][K] matrix per sample,
+ *     [samples][N][K].  With ltu_ctx_project's W_b the output projection (:166) of softmax(Q) equals readout + projection:
+ *     (P ctx_b) Wo^T = P (blockdiag(ctx_b) Wo^T).  Row tiles are aligned to samples.
+ *   ldx: elements between two rows of x (>= K, % 8 == 0): the operand may be a column slice of wider rows (P inside QKV).
+ * ltu_linear_fused(x, rows, K, ...) == ltu_linear_fused_ex(x, K, rows, K, ..., 0, 1, stream).                         */
+int ltu_linear_fused_ex(const void* x, int64_t ldx, int64_t rows, int K, const void* w_bf16, const float* bias, int N,
+                        int epi, const void* res_hi, const void* res_lo, const float* gamma,
+                        const float* beta, float eps, void* y_hi, void* y_lo, int softmax_cols, int samples,
+                        ltu_stream_t stream);
+/* ctx fp32 [B][heads][32][32] (ltu_kv_reduce: softmax_N(K)^T V per head) and the output projection's weight wo_bf16
+ * [C][C] (C = 32 heads) -> out bf16 [B][C][C]:  W_b[n][32h + j] = sum_e ctx[b][h][j][e] Wo[n][32h + e].             */
+int ltu_ctx_project(const float* ctx, const void* wo_bf16, void* out, int B, int heads, ltu_stream_t stream);
+/* ltu_kv_reduce (bf16 k / v, 4 or 8 heads) whose fixed-order merge kernel also writes ltu_ctx_project's W_b into w_out
+ * (bf16 [B][C][C]) -- no extra launch between the context reduction and the output projection.                      */
+int ltu_kv_reduce_project(const void* k, const void* v, int64_t ld, float* ctx, void* workspace,
+                          size_t workspace_bytes, int B, int64_t N, int heads, const void* wo_bf16,
+                          void* w_out, ltu_stream_t stream);
+
 /* Key / value half of linear_attention for d_model 128, 4 heads, as ONE launch (+ the fixed-order merge):
  *     ctx[b][h] = softmax_N(x_b Wk^T + bk)_h^T (x_b Wv^T + bv)_h
  * i.e. the K and V projections of MultihAttention.forward (model/trans_block.py:155-156) fused with the context

@@ -26,6 +26,7 @@ SIGNATURES = {
     "ltu_launch_count": (L, []),
     "ltu_kv_reduce_workspace": (Z, [I, L, I]),
     "ltu_kv_reduce": (I, [P, P, L, P, P, Z, I, L, I, I, P]),
+    "ltu_kv_reduce_project": (I, [P, P, L, P, P, Z, I, L, I, P, P, P]),
     "ltu_q_readout": (I, [P, L, P, P, L, I, L, I, I, P]),
     "ltu_add_layernorm": (I, [P, P, P, P, P, L, I, F, I, P]),
     "ltu_add_layernorm_split": (I, [P, P, P, P, P, P, P, L, I, F, P]),
@@ -49,6 +50,8 @@ SIGNATURES = {
     "ltu_conv3d_tc3_masked": (I, [P, I, P, I, I, I, I, I, P, I, I, P, I, P, P, I, P, P, P]),
     "ltu_linear_tc": (I, [P, I, L, P, P, I, P, I, I, P, P, P, F, P]),
     "ltu_linear_fused": (I, [P, L, I, P, P, I, I, P, P, P, P, F, P, P, P]),
+    "ltu_linear_fused_ex": (I, [P, L, L, I, P, P, I, I, P, P, P, P, F, P, P, I, I, P]),
+    "ltu_ctx_project": (I, [P, P, P, I, I, P]),
     "ltu_kv_project_reduce_supported": (I, [I, I, L]),
     "ltu_kv_project_reduce_workspace": (Z, [I, L]),
     "ltu_kv_project_reduce": (I, [P, P, P, P, P, Z, I, L, P]),

@@ -151,10 +151,22 @@ kv_reduce_kernel(const T* __restrict__ K, const T* __restrict__ V, int64_t ld, f
 // split the parts for the running-max / key-sum columns (exact max; butterfly sums) and the 32 weighted
 // accumulator loads of a block of parts are all issued before the first one is consumed.
 __global__ void __launch_bounds__(1024)
-kv_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx, int heads, int nparts) {
-    pdl_prologue();
+kv_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx, int heads, int nparts,
+                  const bf16* __restrict__ wo, bf16* __restrict__ wout) {
     const int hd = blockIdx.x, b = blockIdx.y;
     const int j = threadIdx.x >> 5, e = threadIdx.x & 31;
+    // optional tail (wo != null): the output projection's weight with this head's context folded in,
+    //   wout[b][n][32 hd + j'] = sum_e' ctx[b][hd][j'][e'] wo[n][32 hd + e'],   n < C = 32 heads
+    // (ltu_linear_fused_ex with per-sample weights).  wo is a parameter: its loads do not wait for the previous kernel.
+    const int C = heads * kHeadDim;
+    __shared__ float cs[32][33];                     // cs[e'][j'] = ctx[j'][e']
+    __shared__ __align__(16) float ws_[256][32];     // ws_[n][e'] = wo[n][32 hd + e']
+    if (wo != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < heads) ws_[j + 32 * i][e] = __bfloat162float(wo[(int64_t)(j + 32 * i) * C + 32 * hd + e]);
+    }
+    pdl_prologue();
     const float* base = part + ((int64_t)b * nparts * heads + hd) * kPartialFloats;
     const int64_t stride = (int64_t)heads * kPartialFloats;
     float M = -INFINITY;
@@ -176,7 +188,28 @@ kv_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx, int h
         for (int u = 0; u < 32; ++u) A8[u & 7] = fmaf(a[u], __shfl_sync(0xffffffffu, wl, u), A8[u & 7]);
     }
     const float A = ((A8[0] + A8[1]) + (A8[2] + A8[3])) + ((A8[4] + A8[5]) + (A8[6] + A8[7]));
-    ctx[(((int64_t)b * heads + hd) * kHeadDim + j) * kHeadDim + e] = A / S;
+    const float cv = A / S;
+    ctx[(((int64_t)b * heads + hd) * kHeadDim + j) * kHeadDim + e] = cv;
+    if (wo == nullptr) return;
+    cs[e][j] = cv;
+    __syncthreads();
+    float c[32];                                     // lane e holds row j' = e of the context: c[k] = ctx[e][k]
+#pragma unroll
+    for (int k = 0; k < 32; ++k) c[k] = cs[k][e];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < heads) {                             // thread (warp j, lane e): row n = j + 32 i, column 32 hd + e
+            const float4* w4 = reinterpret_cast<const float4*>(ws_[j + 32 * i]);      // warp-uniform: broadcast reads
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 w = w4[k];
+                acc = fmaf(w.x, c[4 * k], acc); acc = fmaf(w.y, c[4 * k + 1], acc);
+                acc = fmaf(w.z, c[4 * k + 2], acc); acc = fmaf(w.w, c[4 * k + 3], acc);
+            }
+            wout[((int64_t)b * C + j + 32 * i) * C + 32 * hd + e] = __float2bfloat16_rn(acc);
+        }
+    }
 }
 
 template <typename T>
@@ -465,8 +498,8 @@ int kv_reduce_bf16_mma(const void* k, const void* v, int64_t ld, float* ctx, voi
 int q_readout_bf16_mma(const void* q, int64_t ldq, const float* ctx, void* out, int64_t ldo, int B, int64_t N,
                        int heads, cudaStream_t st);
 int kv_chunks_per_batch_host(int B, int64_t N) { return kv_chunks_per_batch(B, N); }
-int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st) {
-    cudaError_t e = launch_pdl(kv_combine_kernel, dim3(heads, B), dim3(1024), 0, st, ws, ctx, heads, nparts);
+int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st, const void* wo, void* wout) {
+    cudaError_t e = launch_pdl(kv_combine_kernel, dim3(heads, B), dim3(1024), 0, st, ws, ctx, heads, nparts, (const bf16*)wo, (bf16*)wout);
     if (e != cudaSuccess) { set_error("kv_combine: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return LTU_OK;
 }
@@ -476,7 +509,7 @@ static bool use_stream_attention() {
     return v;
 }
 int kv_reduce_bf16_stream(const void* k, const void* v, int64_t ld, float* ctx, void* ws, int B, int64_t N, int heads,
-                          cudaStream_t st);                      // attn_stream.cu
+                          cudaStream_t st, const void* wo = nullptr, void* wout = nullptr);                      // attn_stream.cu
 int q_readout_bf16_stream(const void* q, int64_t ldq, const float* ctx, void* out, int64_t ldo, int B, int64_t N, int heads,
                           cudaStream_t st);
 static bool use_mma_attention() {
@@ -506,7 +539,7 @@ static int kv_reduce_impl(const void* k, const void* v, int64_t ld, float* ctx, 
     kv_reduce_kernel<T><<<dim3(chunks, B), kAttnThreads, smem, st>>>(
         (const T*)k, (const T*)v, ld, (float*)ws, N, heads, chunks, tiles_per_chunk);
     LTU_LAUNCH_CHECK("kv_reduce");
-    kv_combine_kernel<<<dim3(heads, B), 1024, 0, st>>>((const float*)ws, ctx, heads, chunks * wph);
+    kv_combine_kernel<<<dim3(heads, B), 1024, 0, st>>>((const float*)ws, ctx, heads, chunks * wph, nullptr, nullptr);
     LTU_LAUNCH_CHECK("kv_combine");
     count_launch(2);
     return LTU_OK;
@@ -568,6 +601,18 @@ extern "C" int ltu_kv_reduce(const void* k, const void* v, int64_t ld, float* ct
         return kv_reduce_bf16_mma(k, v, ld, ctx, ws, B, N, heads, (cudaStream_t)stream);
     }
     return kv_reduce_impl<bf16>(k, v, ld, ctx, ws, ws_bytes, B, N, heads, (cudaStream_t)stream);
+}
+
+// ltu_kv_reduce (bf16, 4 or 8 heads) whose merge kernel also writes W_b = blockdiag(ctx_b) Wo^T (see ltu_ctx_project)
+extern "C" int ltu_kv_reduce_project(const void* k, const void* v, int64_t ld, float* ctx, void* ws, size_t ws_bytes, int B,
+                                     int64_t N, int heads, const void* wo_bf16, void* w_out, ltu_stream_t stream) {
+    LTU_ARG_CHECK(k && v && ctx && ws && wo_bf16 && w_out, "kv_reduce_project: null pointer");
+    LTU_ARG_CHECK(B > 0 && N > 0 && B <= 65535 && N < ((int64_t)1 << 31), "kv_reduce_project: bad B=%d N=%lld", B, (long long)N);
+    LTU_ARG_CHECK(heads == 4 || heads == 8, "kv_reduce_project: heads must be 4 or 8 (got %d)", heads);
+    LTU_ARG_CHECK(ld >= heads * 32 && ld % 8 == 0, "kv_reduce_project: row stride %lld not a multiple of 8", (long long)ld);
+    LTU_ARG_CHECK(aligned16(k) && aligned16(v) && aligned16(ws), "kv_reduce_project: pointers must be 16-byte aligned");
+    LTU_ARG_CHECK(ws_bytes >= ltu_kv_reduce_workspace(B, N, heads), "kv_reduce_project: workspace too small");
+    return kv_reduce_bf16_stream(k, v, ld, ctx, ws, B, N, heads, (cudaStream_t)stream, wo_bf16, w_out);
 }
 
 extern "C" int ltu_q_readout(const void* q, int64_t ldq, const float* ctx, void* out, int64_t ldo, int B,

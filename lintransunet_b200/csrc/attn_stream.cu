@@ -24,7 +24,8 @@ namespace ltu {
 
 void count_launch(int n = 1);
 int kv_chunks_per_batch_host(int B, int64_t N);   // attn_kernels.cu (per-sample split: depends on N only)
-int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st);
+int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st, const void* wo = nullptr,
+                      void* wout = nullptr);
 
 namespace {
 
@@ -516,13 +517,13 @@ int q_stream_launch(const bf16* q, int64_t ldq, const float* ctx, bf16* out, int
 
 // entry points used by attn_kernels.cu for dtype == bf16, heads in {4, 8}, 16-byte aligned rows
 int kv_reduce_bf16_stream(const void* k, const void* v, int64_t ld, float* ctx, void* ws, int B, int64_t N, int heads,
-                          cudaStream_t st) {
+                          cudaStream_t st, const void* wo, void* wout) {
     const int chunks = kv_chunks_per_batch_host(B, N);
     const int tiles32_per_chunk = (int)ceil_div64(ceil_div64(N, 32), chunks);
     int rc = heads == 8 ? kv_stream_launch<8>((const bf16*)k, (const bf16*)v, ld, (float*)ws, B, N, chunks, tiles32_per_chunk, st)
                         : kv_stream_launch<4>((const bf16*)k, (const bf16*)v, ld, (float*)ws, B, N, chunks, tiles32_per_chunk, st);
     if (rc != LTU_OK) return rc;
-    rc = kv_combine_launch((const float*)ws, ctx, heads, B, chunks * (kConsumers / heads), st);
+    rc = kv_combine_launch((const float*)ws, ctx, heads, B, chunks * (kConsumers / heads), st, wo, wout);
     if (rc != LTU_OK) return rc;
     count_launch(2);
     return LTU_OK;

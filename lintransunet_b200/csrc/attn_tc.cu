@@ -438,7 +438,8 @@ q_readout_mma_kernel(const bf16* __restrict__ Q, int64_t ldq, const float* __res
 
 // ------------------------------------------------------------------------------------------------
 int kv_chunks_per_batch_host(int B, int64_t N);   // attn_kernels.cu (same split as the fp32 path)
-int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st);
+int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st, const void* wo = nullptr,
+                      void* wout = nullptr);
 
 template <int HEADS>
 static int kv_mma_launch(const bf16* k, const bf16* v, int64_t ld, float* ws, int B, int64_t N, int chunks,

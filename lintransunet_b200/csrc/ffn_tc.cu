@@ -356,6 +356,24 @@ int make_tmap_bf16_2d_w(CUtensorMap* map, const void* base, uint64_t rows, uint6
     return LTU_OK;
 }
 
+// [batch][rows][cols] bf16 (dense) as a 3-D map with [1][box_rows][64] boxes, SWIZZLE_128B: rows past the end of a SAMPLE
+// are zero-filled on loads and clipped on stores, so a kernel may tile every sample separately
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint64_t ld = 0) {
+    if (ld == 0) ld = cols;                           // elements between two rows (a column slice of wider rows)
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LTU_ERR_ARG; }
+    const cuuint64_t gdim[3] = {cols, rows, batch};
+    const cuuint64_t gstride[2] = {ld * 2, rows * ld * 2};
+    const cuuint32_t box[3] = {64, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (3-D) failed (CUresult %d)", (int)r); return LTU_ERR_ARG; }
+    return LTU_OK;
+}
+
 }  // namespace ltu
 
 using namespace ltu;

@@ -27,7 +27,8 @@ namespace ltu {
 
 void count_launch(int n = 1);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);   // ffn_tc.cu
-int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st);            // attn_kernels.cu
+int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st, const void* wo = nullptr,
+                      void* wout = nullptr);            // attn_kernels.cu
 
 namespace {
 

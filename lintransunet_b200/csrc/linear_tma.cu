@@ -5,6 +5,13 @@
 //     epi 1   y = gelu(x W^T + b)                             (linear1)
 //     epi 2   (y_hi, y_lo) = split(LayerNorm(x W^T + b + r_hi + r_lo) * gamma + beta)      (output projection, linear2)
 //
+// Two options carry the query half of linear_attention (:50, :65) through the same launches (ltu_linear_fused_ex):
+//   * softmax_cols > 0 (epi 0): output columns [0, softmax_cols) -- the Q third of the QKV projection -- are written as
+//     softmax over each head's 32 columns / sqrt(32) (one thread owns a row: the head is 32 of its registers);
+//   * samples > 1: W is one [N][K] matrix PER SAMPLE.  With W_b = (blockdiag(ctx_b) Wo^T)^T (ltu_ctx_project) the output
+//     projection of softmax(Q) IS the readout followed by the output projection: (P ctx_b) Wo^T = P (ctx_b Wo^T), so
+//     q_readout never runs and its result is never written.  Row tiles are then aligned to samples (3-D tensor maps clip).
+//
 // One persistent, warp-specialised TMA + tcgen05 kernel; every byte that moves between HBM and the SM moves through TMA
 // (coalesced by construction), the epilogue warps only touch tensor memory and shared memory:
 //
@@ -30,6 +37,8 @@ namespace ltu {
 
 void count_launch(int n = 1);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);   // ffn_tc.cu
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint64_t ld = 0);
 
 constexpr int kLinThreads = 320;
 constexpr int kLinStages = 3;
@@ -61,7 +70,14 @@ struct LinParams {
     int cl;                          // CTAs per cluster: 2 = a CTA pair walks two row blocks of the same n-tile in lock step
                                      // and every W k-block is fetched ONCE per pair (each CTA loads half, TMA multicast)
     int mode;                        // debug ablations (LTU_LIN_MODE): 1 no output stores, 2 no GELU math, 4 no MMAs, 8 no W loads
+    int tps;                         // 128-row tiles per sample (x, residual and y are [samples][rows per sample][cols] maps)
+    int w_rows;                      // rows between the weight matrices of two samples (0: one weight for all)
+    int qsm_tiles;                   // n-tiles [0, qsm_tiles) are written as per-head softmax / sqrt(32) (epi 0)
 };
+
+// first row (inside its sample) and sample of m-tile `mt`
+struct LinTile { int r0, b; };
+__device__ __forceinline__ LinTile lin_tile(int mt, int tps) { LinTile t; t.b = mt / tps; t.r0 = (mt - t.b * tps) * 128; return t; }
 
 __global__ void __launch_bounds__(kLinThreads, 1)
 linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
@@ -119,7 +135,8 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             pdl_prologue();                                              // inputs come from the previous kernel in the stream
             uint32_t kbc = 0;
             for (int T = group; T < total; T += ngroups) {
-                const int row0 = ((T / p.tiles_n) * p.cl + crank) * 128, n0 = (T % p.tiles_n) * kLinBN;
+                const LinTile tl = lin_tile((T / p.tiles_n) * p.cl + crank, p.tps);
+                const int n0 = (T % p.tiles_n) * kLinBN, wrow = n0 + tl.b * p.w_rows;
                 for (int kb = 0; kb < nkb_all; ++kb, ++kbc) {
                     const int stage = kbc % kLinStages;
                     mbar_wait(smem_u32(&tail->empty[stage]), ((kbc / kLinStages) & 1) ^ 1);     // free in BOTH CTAs of a pair
@@ -127,12 +144,12 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     const uint32_t sa = sbase + stage * kLinStageBytes;
                     if (kb < p.nkb) {
                         mbar_expect_tx(fb, (p.mode & 8) ? kLinABytes : kLinStageBytes);
-                        tma_load_2d(sa, &tm_x, kb * 64, row0, fb);
+                        tma_load_3d(sa, &tm_x, kb * 64, tl.r0, tl.b, fb);
                         if (p.mode & 8) {
                         } else if (p.cl == 2) {         // this CTA's 128-row half of the W k-block, delivered to both CTAs
-                            tma_load_2d_mc(sa + kLinABytes + (uint32_t)crank * (kLinBBytes / 2), &tm_wh, kb * 64, n0 + crank * 128, fb, cmask);
+                            tma_load_2d_mc(sa + kLinABytes + (uint32_t)crank * (kLinBBytes / 2), &tm_wh, kb * 64, wrow + crank * 128, fb, cmask);
                         } else {
-                            tma_load_2d(sa + kLinABytes, &tm_w, kb * 64, n0, fb);
+                            tma_load_2d(sa + kLinABytes, &tm_w, kb * 64, wrow, fb);
                         }
                     } else {                                             // up to three residual k-blocks fill one stage
                         const int j0 = (kb - p.nkb) * 3;
@@ -140,7 +157,7 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         mbar_expect_tx(fb, (uint32_t)cnt * kLinABytes);
                         for (int i = 0; i < cnt; ++i) {
                             const int j = j0 + i;
-                            tma_load_2d(sa + (uint32_t)i * kLinABytes, j < 4 ? &tm_rhi : &tm_rlo, (j & 3) * 64, row0, fb);
+                            tma_load_3d(sa + (uint32_t)i * kLinABytes, j < 4 ? &tm_rhi : &tm_rlo, (j & 3) * 64, tl.r0, tl.b, fb);
                         }
                     }
                 }
@@ -195,7 +212,9 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const uint32_t swz = (uint32_t)(lane & 7);
         uint32_t it = 0;
         for (int T = group; T < total; T += ngroups, ++it) {
-            const int row0 = ((T / p.tiles_n) * p.cl + crank) * 128, n0 = (T % p.tiles_n) * kLinBN;
+            const LinTile tl = lin_tile((T / p.tiles_n) * p.cl + crank, p.tps);
+            const int n0 = (T % p.tiles_n) * kLinBN;
+            const bool qsm = (T % p.tiles_n) < p.qsm_tiles;
             const uint32_t abuf = it & 1;
             const uint32_t tb = tmem_base + abuf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 128);
             const float* bs = tail->bias + n0 + hh * 128;
@@ -217,6 +236,41 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         if (lane == 0) mbar_arrive(smem_u32(&tail->tempty[abuf]));
                     }
                     unsigned char* buf = stg + c * 4096 + lane * 128;
+                    if (qsm) {
+                        // the thread's 64 columns are two complete heads: softmax over 32 registers, scaled by 1/sqrt(32)
+#pragma unroll
+                        for (int hx = 0; hx < 2; ++hx) {
+                            const uint32_t* src = hx ? v1 : v0;
+                            const float4* b4 = reinterpret_cast<const float4*>(bs + c * 64 + hx * 32);
+                            float o[32];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b = b4[i];
+                                o[4 * i] = __uint_as_float(src[4 * i]) + b.x; o[4 * i + 1] = __uint_as_float(src[4 * i + 1]) + b.y;
+                                o[4 * i + 2] = __uint_as_float(src[4 * i + 2]) + b.z; o[4 * i + 3] = __uint_as_float(src[4 * i + 3]) + b.w;
+                            }
+                            float m = o[0];
+#pragma unroll
+                            for (int i = 1; i < 32; ++i) m = fmaxf(m, o[i]);
+                            const float mneg = -m * 1.4426950408889634f;
+                            float sum = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                float ex;
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(o[i], 1.4426950408889634f, mneg)));
+                                o[i] = ex;
+                                sum += ex;
+                            }
+                            const float inv = 0.17677669529663687f / sum;            // 1 / (sqrt(32) * sum)
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                uint4 ov;
+                                ov.x = pack_bf16x2(o[8 * jj] * inv, o[8 * jj + 1] * inv); ov.y = pack_bf16x2(o[8 * jj + 2] * inv, o[8 * jj + 3] * inv);
+                                ov.z = pack_bf16x2(o[8 * jj + 4] * inv, o[8 * jj + 5] * inv); ov.w = pack_bf16x2(o[8 * jj + 6] * inv, o[8 * jj + 7] * inv);
+                                *reinterpret_cast<uint4*>(buf + (((uint32_t)(hx * 4 + jj) ^ swz) << 4)) = ov;
+                            }
+                        }
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint32_t* src = j < 4 ? v0 + 8 * j : v1 + 8 * (j - 4);
@@ -235,10 +289,11 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
                         *reinterpret_cast<uint4*>(buf + (((uint32_t)j ^ swz) << 4)) = ov;
                     }
+                    }
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0 && !(p.mode & 1)) {
-                        tma_store_2d(&tm_yhi, stg_u + c * 4096, n0 + hh * 128 + c * 64, row0 + q * 32);
+                        tma_store_3d(&tm_yhi, stg_u + c * 4096, n0 + hh * 128 + c * 64, tl.r0 + q * 32, tl.b);
                         tma_store_commit();
                     }
                 }
@@ -323,8 +378,8 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0 && !(p.mode & 1)) {
-                        tma_store_2d(&tm_yhi, stg_u, hh * 128 + c * 64, row0 + q * 32);
-                        if (p.want_lo) tma_store_2d(&tm_ylo, stg_u + 4096, hh * 128 + c * 64, row0 + q * 32);
+                        tma_store_3d(&tm_yhi, stg_u, hh * 128 + c * 64, tl.r0 + q * 32, tl.b);
+                        if (p.want_lo) tma_store_3d(&tm_ylo, stg_u + 4096, hh * 128 + c * 64, tl.r0 + q * 32, tl.b);
                         tma_store_commit();
                     }
                 }
@@ -349,9 +404,12 @@ using namespace ltu;
 // (row-major, K innermost), bias fp32 [N], N % 256 == 0 and N <= 768; y_hi bf16 [rows][N].
 //   epi 0: bias | 1: bias + exact-erf GELU | 2: LayerNorm(x W^T + b + res_hi + res_lo) * gamma + beta with N == 256,
 //   res_hi / res_lo bf16 [rows][256] (res_lo may be null), result split into y_hi + y_lo (y_lo may be null).
-extern "C" int ltu_linear_fused(const void* x, int64_t rows, int K, const void* w_bf16, const float* bias, int N, int epi,
-                                const void* res_hi, const void* res_lo, const float* gamma, const float* beta, float eps,
-                                void* y_hi, void* y_lo, ltu_stream_t stream) {
+//   ldx: elements between two rows of x (>= K; a column slice of wider rows is read in place).
+//   softmax_cols (epi 0; 0 or a multiple of 256): columns [0, softmax_cols) are written as softmax over each group of 32
+//   columns, divided by sqrt(32).  samples > 1: rows = samples x (rows / samples) tokens and w_bf16 is [samples][N][K].
+extern "C" int ltu_linear_fused_ex(const void* x, int64_t ldx, int64_t rows, int K, const void* w_bf16, const float* bias, int N, int epi,
+                                   const void* res_hi, const void* res_lo, const float* gamma, const float* beta, float eps,
+                                   void* y_hi, void* y_lo, int softmax_cols, int samples, ltu_stream_t stream) {
     LTU_ARG_CHECK(x && w_bf16 && bias && y_hi, "linear_fused: null pointer");
     LTU_ARG_CHECK(rows > 0 && rows < ((int64_t)1 << 31) - 256, "linear_fused: bad row count");
     LTU_ARG_CHECK(K >= 64 && K <= 1024 && K % 64 == 0, "linear_fused: K must be a multiple of 64 in [64,1024] (got %d)", K);
@@ -362,20 +420,28 @@ extern "C" int ltu_linear_fused(const void* x, int64_t rows, int K, const void* 
     LTU_ARG_CHECK(epi == kLinResLN || (!res_hi && !res_lo && !y_lo), "linear_fused: residual / y_lo only with epi 2");
     LTU_ARG_CHECK((((uintptr_t)x | (uintptr_t)w_bf16 | (uintptr_t)y_hi | (uintptr_t)y_lo | (uintptr_t)res_hi | (uintptr_t)res_lo) & 15) == 0,
                   "linear_fused: pointers must be 16-byte aligned");
+    LTU_ARG_CHECK(softmax_cols >= 0 && softmax_cols <= N && softmax_cols % kLinBN == 0 && (softmax_cols == 0 || epi == kLinBias),
+                  "linear_fused: softmax_cols must be a multiple of 256 within N, with epi 0 (got %d)", softmax_cols);
+    LTU_ARG_CHECK(ldx >= K && ldx % 8 == 0, "linear_fused: ldx (%lld) must be >= K and a multiple of 8", (long long)ldx);
+    LTU_ARG_CHECK(samples >= 1 && rows % samples == 0, "linear_fused: rows (%lld) must be a multiple of samples (%d)", (long long)rows, samples);
+    const uint64_t nper = (uint64_t)(rows / samples);
     CUtensorMap tx, tw, twh, trh, trl, tyh, tyl;
     int rc;
-    if ((rc = make_tmap_bf16_2d(&tx, x, (uint64_t)rows, (uint64_t)K, 128)) != LTU_OK) return rc;
-    if ((rc = make_tmap_bf16_2d(&tw, w_bf16, (uint64_t)N, (uint64_t)K, kLinBN)) != LTU_OK) return rc;
-    if ((rc = make_tmap_bf16_2d(&twh, w_bf16, (uint64_t)N, (uint64_t)K, kLinBN / 2)) != LTU_OK) return rc;   // half boxes (pairs)
-    if ((rc = make_tmap_bf16_2d(&tyh, y_hi, (uint64_t)rows, (uint64_t)N, 32)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_3d(&tx, x, (uint64_t)samples, nper, (uint64_t)K, 128, (uint64_t)ldx)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&tw, w_bf16, (uint64_t)N * samples, (uint64_t)K, kLinBN)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&twh, w_bf16, (uint64_t)N * samples, (uint64_t)K, kLinBN / 2)) != LTU_OK) return rc;   // half boxes (pairs)
+    if ((rc = make_tmap_bf16_3d(&tyh, y_hi, (uint64_t)samples, nper, (uint64_t)N, 32)) != LTU_OK) return rc;
     trh = tx; trl = tx; tyl = tyh;
-    if (res_hi && (rc = make_tmap_bf16_2d(&trh, res_hi, (uint64_t)rows, kLinBN, 128)) != LTU_OK) return rc;
-    if (res_lo && (rc = make_tmap_bf16_2d(&trl, res_lo, (uint64_t)rows, kLinBN, 128)) != LTU_OK) return rc;
-    if (y_lo && (rc = make_tmap_bf16_2d(&tyl, y_lo, (uint64_t)rows, (uint64_t)N, 32)) != LTU_OK) return rc;
+    if (res_hi && (rc = make_tmap_bf16_3d(&trh, res_hi, (uint64_t)samples, nper, kLinBN, 128)) != LTU_OK) return rc;
+    if (res_lo && (rc = make_tmap_bf16_3d(&trl, res_lo, (uint64_t)samples, nper, kLinBN, 128)) != LTU_OK) return rc;
+    if (y_lo && (rc = make_tmap_bf16_3d(&tyl, y_lo, (uint64_t)samples, nper, (uint64_t)N, 32)) != LTU_OK) return rc;
     LinParams p;
     p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
     p.N = N; p.nkb = K / 64;
-    p.tiles_m = (int)((rows + 127) / 128); p.tiles_n = N / kLinBN;
+    p.tps = (int)((nper + 127) / 128);
+    p.tiles_m = p.tps * samples; p.tiles_n = N / kLinBN;
+    p.w_rows = samples > 1 ? N : 0;
+    p.qsm_tiles = softmax_cols / kLinBN;
     p.epi = epi; p.has_lo = res_lo != nullptr; p.want_lo = y_lo != nullptr;
     static const int dbg_mode = [] { const char* e = getenv("LTU_LIN_MODE"); return e ? atoi(e) : 0; }();
     p.mode = dbg_mode;
@@ -403,7 +469,7 @@ extern "C" int ltu_linear_fused(const void* x, int64_t rows, int K, const void* 
         max_pairs = cudaOccupancyMaxActiveClusters(&n, linear_tma_kernel, &q) == cudaSuccess ? n : 0;
         cudaGetLastError();
     }
-    p.cl = (want_cl == 2 && p.tiles_m >= 2 && max_pairs >= 16) ? 2 : 1;
+    p.cl = (want_cl == 2 && p.tiles_m >= 2 && max_pairs >= 16 && samples == 1) ? 2 : 1;
     const int groups = (p.tiles_m + p.cl - 1) / p.cl * p.tiles_n;
     int grid = p.cl == 2 ? max_pairs * 2 : sm_count();
     if (grid > groups * p.cl) grid = groups * p.cl;
@@ -420,6 +486,52 @@ extern "C" int ltu_linear_fused(const void* x, int64_t rows, int K, const void* 
     cfg.attrs = attr; cfg.numAttrs = (unsigned)na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, linear_tma_kernel, tx, tw, twh, trh, trl, tyh, tyl, p);
     if (e != cudaSuccess) { set_error("linear_fused: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    count_launch(1);
+    return LTU_OK;
+}
+
+extern "C" int ltu_linear_fused(const void* x, int64_t rows, int K, const void* w_bf16, const float* bias, int N, int epi,
+                                const void* res_hi, const void* res_lo, const float* gamma, const float* beta, float eps,
+                                void* y_hi, void* y_lo, ltu_stream_t stream) {
+    return ltu_linear_fused_ex(x, K, rows, K, w_bf16, bias, N, epi, res_hi, res_lo, gamma, beta, eps, y_hi, y_lo, 0, 1, stream);
+}
+
+namespace ltu {
+// out[b][n][32h + j] = sum_e ctx[b][h][j][e] * Wo[n][32h + e]: the output projection with the sample's context folded in
+__global__ void __launch_bounds__(1024)
+ctx_project_kernel(const float* __restrict__ ctx, const bf16* __restrict__ wo, bf16* __restrict__ out, int C) {
+    __shared__ float cs[32][33];                     // cs[e][j]
+    __shared__ __align__(16) float ws_[256][32];     // ws_[n][e] = wo[n][32 h + e]
+    const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
+    const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = wrp; n < C; n += 32) ws_[n][lane] = __bfloat162float(wo[(int64_t)n * C + 32 * h + lane]);   // a parameter: no wait
+    pdl_prologue();
+    cs[lane][wrp] = ctx[(((int64_t)b * heads + h) * 32 + wrp) * 32 + lane];
+    __syncthreads();
+    float c[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) c[k] = cs[k][lane];
+    for (int n = wrp; n < C; n += 32) {
+        const float4* w4 = reinterpret_cast<const float4*>(ws_[n]);
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 w = w4[k];
+            acc = fmaf(w.x, c[4 * k], acc); acc = fmaf(w.y, c[4 * k + 1], acc);
+            acc = fmaf(w.z, c[4 * k + 2], acc); acc = fmaf(w.w, c[4 * k + 3], acc);
+        }
+        out[((int64_t)b * C + n) * C + 32 * h + lane] = __float2bfloat16_rn(acc);
+    }
+}
+}  // namespace ltu
+
+// ctx fp32 [B][heads][32][32] (ltu_kv_reduce), wo_bf16 [C][C] (C = 32 heads) -> out bf16 [B][C][C], the per-sample weight
+// W_b[n][32h + j] = sum_e ctx[b][h][j][e] Wo[n][32h + e] of ltu_linear_fused_ex(samples = B)
+extern "C" int ltu_ctx_project(const float* ctx, const void* wo_bf16, void* out, int B, int heads, ltu_stream_t stream) {
+    LTU_ARG_CHECK(ctx && wo_bf16 && out && B > 0 && heads > 0 && heads <= 8, "ctx_project: bad arguments (heads <= 8)");
+    cudaError_t e = launch_pdl(ctx_project_kernel, dim3(heads, B), dim3(1024), 0, (cudaStream_t)stream, ctx, (const bf16*)wo_bf16,
+                               (bf16*)out, heads * 32);
+    if (e != cudaSuccess) { set_error("ctx_project: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     count_launch(1);
     return LTU_OK;
 }

@@ -113,9 +113,11 @@ class _Guard:
 
 
 # ------------------------------------------------------------------ a1: attention core
-def kv_reduce(k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+def kv_reduce(k: torch.Tensor, v: torch.Tensor, heads: int, w_o: Optional[torch.Tensor] = None):
     """k, v: [B, N, C] views with a common row stride (e.g. slices of a fused QKV buffer).
-    Returns ctx fp32 [B, heads, 32, 32] (model/trans_block.py:59-60)."""
+    Returns ctx fp32 [B, heads, 32, 32] (model/trans_block.py:59-60).  With w_o (the output projection's bf16 weight
+    [C, C]; bf16 k / v, 4 or 8 heads) the merge kernel also writes the per-sample weight of ctx_project and the result is
+    (ctx, W_b)."""
     B, N, C = k.shape
     assert C == heads * 32 and v.shape == k.shape
     assert k.stride(2) == 1 and v.stride(2) == 1 and k.stride(1) == v.stride(1)
@@ -127,6 +129,13 @@ def kv_reduce(k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
         ws_bytes = L.ltu_kv_reduce_workspace(B, N, heads)
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=k.device)
         ctx = torch.empty(B, heads, 32, 32, dtype=torch.float32, device=k.device)
+        if w_o is not None:
+            if k.dtype != torch.bfloat16 or w_o.dtype != torch.bfloat16 or tuple(w_o.shape) != (C, C) or not w_o.is_contiguous():
+                raise TypeError("kv_reduce(w_o=...) needs bf16 k / v and the contiguous bf16 [C, C] weight")
+            wb = torch.empty(B, C, C, dtype=torch.bfloat16, device=k.device)
+            check(L.ltu_kv_reduce_project(_p(k), _p(v), k.stride(1), _p(ctx), _p(ws), ws_bytes, B, N, heads, _p(w_o), _p(wb), st),
+                  "ltu_kv_reduce_project")
+            return ctx, wb
         check(L.ltu_kv_reduce(_p(k), _p(v), k.stride(1), _p(ctx), _p(ws), ws_bytes, B, N, heads, _dt(k), st),
               "ltu_kv_reduce")
     return ctx
@@ -928,25 +937,50 @@ def linear_fused_supported(k: int, n: int) -> bool:
 def linear_fused(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, epi: int = EPI_BIAS,
                  res_hi: Optional[torch.Tensor] = None, res_lo: Optional[torch.Tensor] = None,
                  gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, eps: float = 1e-6,
-                 want_lo: bool = True):
+                 want_lo: bool = True, softmax_cols: int = 0, x_cols: Optional[int] = None):
     """nn.Linear on bf16 tokens [..., K] with a fused epilogue, one persistent TMA + tcgen05 launch (csrc/linear_tma.cu):
     EPI_BIAS -> x W^T + b; EPI_GELU -> gelu(x W^T + b); EPI_RES_LN -> LayerNorm(x W^T + b + res_hi + res_lo) returned as the
-    split pair (y_hi, y_lo) (y_lo None unless want_lo).  w: the nn.Linear weight [N, K] in bf16, bias / gamma / beta fp32."""
+    split pair (y_hi, y_lo) (y_lo None unless want_lo).  w: the nn.Linear weight [N, K] in bf16, bias / gamma / beta fp32.
+    softmax_cols: output columns [0, softmax_cols) come out as softmax over each head's 32 columns / sqrt(32) (the Q third
+    of a QKV projection, model/trans_block.py:50).  w of shape [B, N, K] with x [B, tokens, K]: one weight per sample
+    (ctx_project: the readout folded into the output projection).  x_cols: the operand is columns [0, x_cols) of x (a
+    column slice of a wider row, e.g. the Q third of a QKV tensor, read in place)."""
     dev = _chk(x, w, bias, res_hi, res_lo, gamma, beta)
     if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
         raise TypeError("linear_fused needs bf16 activations and bf16 weights")
-    n, k = w.shape
-    if x.shape[-1] != k:
-        raise ValueError(f"linear_fused: x has {x.shape[-1]} columns, the weight expects {k}")
-    rows = x.numel() // k
+    samples = 1
+    if w.dim() == 3:
+        samples = w.shape[0]
+        if x.dim() != 3 or x.shape[0] != samples:
+            raise ValueError(f"linear_fused: per-sample weights {tuple(w.shape)} need x [B, tokens, K], got {tuple(x.shape)}")
+    n, k = w.shape[-2:]
+    ldx = x.shape[-1]
+    if (x_cols if x_cols is not None else ldx) != k or ldx < k:
+        raise ValueError(f"linear_fused: x has {x.shape[-1]} columns (x_cols {x_cols}), the weight expects {k}")
+    rows = x.numel() // ldx
     y = torch.empty(*x.shape[:-1], n, dtype=torch.bfloat16, device=dev)
     y_lo = torch.empty_like(y) if (epi == EPI_RES_LN and want_lo) else None
     nres = 0 if res_hi is None else (1 if res_lo is None else 2)
-    nbytes = (x.numel() + y.numel() * (2 if y_lo is not None else 1) + nres * rows * n) * 2
+    nbytes = (rows * k + y.numel() * (2 if y_lo is not None else 1) + nres * rows * n) * 2
     with _Guard(dev, ("linear_fused", nbytes, 2 * rows * k * n)) as st:
-        check(_native.lib().ltu_linear_fused(_p(x), rows, k, _p(w), _p(bias), n, epi, _p(res_hi), _p(res_lo), _p(gamma),
-                                             _p(beta), eps, _p(y), _p(y_lo), st), "ltu_linear_fused")
+        check(_native.lib().ltu_linear_fused_ex(_p(x), ldx, rows, k, _p(w), _p(bias), n, epi, _p(res_hi), _p(res_lo), _p(gamma),
+                                                _p(beta), eps, _p(y), _p(y_lo), softmax_cols, samples, st), "ltu_linear_fused_ex")
     return (y, y_lo) if epi == EPI_RES_LN else y
+
+
+def ctx_project(ctx: torch.Tensor, w_o: torch.Tensor) -> torch.Tensor:
+    """ctx fp32 [B, heads, 32, 32] (kv_reduce) and the output projection's bf16 weight [C, C] -> bf16 [B, C, C],
+    W_b[n, 32h + j] = sum_e ctx[b, h, j, e] Wo[n, 32h + e]: linear_fused(softmax(Q), W_b) is readout + projection
+    (model/trans_block.py:65, :166)."""
+    dev = _chk(ctx, w_o)
+    B, heads = ctx.shape[:2]
+    C = heads * 32
+    if ctx.dtype != torch.float32 or w_o.dtype != torch.bfloat16 or tuple(w_o.shape) != (C, C) or tuple(ctx.shape[2:]) != (32, 32):
+        raise TypeError("ctx_project needs ctx fp32 [B, heads, 32, 32] and the bf16 [C, C] weight with C = 32 heads")
+    out = torch.empty(B, C, C, dtype=torch.bfloat16, device=dev)
+    with _Guard(dev, ("ctx_project", B * C * C * 2, 2 * B * C * C * 32)) as st:
+        check(_native.lib().ltu_ctx_project(_p(ctx), _p(w_o), _p(out), B, heads, st), "ltu_ctx_project")
+    return out
 
 
 def kv_project_reduce_supported(c: int, heads: int, n: int) -> bool:

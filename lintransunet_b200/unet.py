@@ -462,6 +462,7 @@ class MaskTransUnet(nn.Module):
         self.use_native_linear = os.environ.get("LTU_NATIVE_LINEAR", "1") == "1"
         # d_model 128: reduce K and V inside the K/V projection's epilogue (ltu_kv_project_reduce).  LTU_KV_PROJECT=0 = A/B.
         self.fuse_kv_project = os.environ.get("LTU_KV_PROJECT", "1") == "1"
+        self.fold_readout = os.environ.get("LTU_FOLD_READOUT", "1") == "1"      # d_model 256: q_readout folded into the GEMMs around it
         # training: autograd through the native backward (bf16 path; loss.backward() fills p.grad).  LTU_NATIVE_BACKWARD=0
         # turns a training forward with grad into an error instead (there is no other backward).
         self.native_backward = os.environ.get("LTU_NATIVE_BACKWARD", "1") == "1"
@@ -524,7 +525,7 @@ class MaskTransUnet(nn.Module):
     def _knobs(self) -> tuple:
         """Every runtime switch that changes the launched kernels (part of the CUDA-graph cache key)."""
         return (self.use_tensor_cores, self.use_fused_linear, self.fuse_mask_head, self.use_fused_ffn, self.use_fused_attn,
-                self.split_token_stream, self.use_native_linear, self.fuse_kv_project, self.skip_dead_mask_head, ops.USE_HALO_CONV, ops.USE_TC3_CONV, ops.USE_SV_CONV)
+                self.split_token_stream, self.use_native_linear, self.fuse_kv_project, self.fold_readout, self.skip_dead_mask_head, ops.USE_HALO_CONV, ops.USE_TC3_CONV, ops.USE_SV_CONV)
 
     def _capture(self, x: torch.Tensor, plan: "_Plan", head: str) -> dict:
         static_x = x.clone()
@@ -587,10 +588,19 @@ class MaskTransUnet(nn.Module):
         if lw.lin and self.use_native_linear:
             # d_model 256: four TMA + tcgen05 launches carry every Linear of the layer with its bias, GELU and
             # residual + LayerNorm (the split stream rides the operand ring; ltu_linear_fused)
-            qkv = ops.linear_fused(t, lw.w_qkv, lw.bqkv_f32)
-            ctx = ops.kv_reduce(qkv[..., C:2 * C], qkv[..., 2 * C:], lw.nhead)
-            att = ops.q_readout(qkv[..., :C], ctx, lw.nhead)
-            t, lo = ops.linear_fused(att, lw.w_o, lw.bo_f32, ops.EPI_RES_LN, t, lo, lw.g1, lw.be1, 1e-6, want_lo=split)
+            if self.fold_readout:
+                # the query half of linear_attention rides the GEMMs around it: the QKV launch writes softmax(Q) / sqrt(32),
+                # and the output projection runs with the sample's W_b = blockdiag(ctx_b) Wo^T -- (P ctx_b) Wo^T = P (ctx_b Wo^T):
+                # q_readout never runs, the attention output is never written
+                qkv = ops.linear_fused(t, lw.w_qkv, lw.bqkv_f32, softmax_cols=C)
+                _, w_b = ops.kv_reduce(qkv[..., C:2 * C], qkv[..., 2 * C:], lw.nhead, w_o=lw.w_o)
+                t, lo = ops.linear_fused(qkv, w_b, lw.bo_f32, ops.EPI_RES_LN, t, lo, lw.g1, lw.be1, 1e-6,
+                                         want_lo=split, x_cols=C)             # P = columns [0, C) of the QKV rows
+            else:
+                qkv = ops.linear_fused(t, lw.w_qkv, lw.bqkv_f32)
+                ctx = ops.kv_reduce(qkv[..., C:2 * C], qkv[..., 2 * C:], lw.nhead)
+                att = ops.q_readout(qkv[..., :C], ctx, lw.nhead)
+                t, lo = ops.linear_fused(att, lw.w_o, lw.bo_f32, ops.EPI_RES_LN, t, lo, lw.g1, lw.be1, 1e-6, want_lo=split)
             f = ops.linear_fused(t, lw.w_1, lw.b1_f32, ops.EPI_GELU)
             return ops.linear_fused(f, lw.w_2, lw.b2_f32, ops.EPI_RES_LN, t, lo, lw.g2, lw.be2, 1e-6, want_lo=split)
         if lw.fma and self.use_native_linear:

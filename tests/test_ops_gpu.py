@@ -630,11 +630,13 @@ def test_encoder_layer_d256_native_linear(B, N):
     m = MaskTransUnet.__new__(MaskTransUnet)
     torch.nn.Module.__init__(m)
     m.use_fused_linear, m.use_fused_ffn, m.use_fused_attn, m.fuse_kv_project = False, False, False, True
+    m.fold_readout = True
     lw = _LayerW(layer, bf)
     assert lw.lin
     out = {}
-    for native in (True, False):
-        m.use_native_linear = native
+    for native in (True, "separate readout", False):
+        m.use_native_linear = bool(native)
+        m.fold_readout = native is True
         hi, lo = MaskTransUnet._encoder_layer(m, x.to("cuda", bf), lw, None, True)
         assert lo is not None
         out[native] = (hi, lo)
@@ -643,8 +645,11 @@ def test_encoder_layer_d256_native_linear(B, N):
         assert lo1 is None and rel_err(hi1.float(), ref_plain) < 3e-2
     e_nat = rel_err(out[True][0].float() + out[True][1].float(), ref_plain)
     e_lib = rel_err(out[False][0].float() + out[False][1].float(), ref_plain)
-    print(f"\n[d256 layer B={B} N={N}] native Linear {e_nat:.2e}, cuBLAS + separate kernels {e_lib:.2e} (vs fp64 oracle)")
-    assert e_nat <= 1.5 * e_lib + 1e-3
+    e_sep = rel_err(out["separate readout"][0].float() + out["separate readout"][1].float(), ref_plain)
+    print(f"\n[d256 layer B={B} N={N}] native Linear, readout folded into the GEMMs {e_nat:.2e}, native Linear + q_readout "
+          f"{e_sep:.2e}, cuBLAS + separate kernels {e_lib:.2e} (vs fp64 oracle)")
+    assert e_nat <= 1.5 * e_lib + 1e-3 and e_nat <= 1.5 * e_sep + 1e-3
+    m.fold_readout = True
     # with a non-zero low word on the input (layers 1..7 of a bridge)
     m.use_native_linear = True
     hi2, lo2 = MaskTransUnet._encoder_layer(m, x.to("cuda", bf), lw, x_lo.to("cuda", bf), True)
@@ -717,6 +722,61 @@ def test_linear_fused(epi, rows, K, N):
     else:
         assert out.shape == (rows, N)
         assert rel_err(out.float().cpu().double(), ref) < TOL[bf]
+
+
+@pytest.mark.parametrize("B,N", [(1, 300), (3, 4320), (8, 512), (2, 10752), (5, 97)])
+def test_linear_fused_folded_readout(B, N):
+    """The query half of linear_attention (trans_block.py:50, :65) carried by the GEMMs around it: (a) the QKV launch writes
+    softmax(Q) / sqrt(32) per head in its first C columns, K and V unchanged; (b) ctx_project builds the per-sample weight
+    W_b = blockdiag(ctx_b) Wo^T; (c) the output projection with per-sample weights, reading P in place inside the QKV rows,
+    equals q_readout followed by the projection -- against fp64 torch on the same bf16 operands, with sample-aligned row
+    tiles (N not a multiple of 128: nothing may leak across samples)."""
+    ops = _ops()
+    bf, C, h = torch.bfloat16, 256, 8
+    cu = lambda t: t.detach().to("cuda")
+    x = q_(rnd((B, N, C), 180 + N % 7, 1.5), bf)
+    w = q_(rnd((3 * C, C), 181, 0.08), bf)
+    b = rnd((3 * C,), 182, 0.3)
+    qkv_ref = x.double() @ w.double().t() + b.double()
+    p_ref = torch.softmax(qkv_ref[..., :C].reshape(B, N, h, 32), dim=-1).reshape(B, N, C) / math.sqrt(32.0)
+    qkv = ops.linear_fused(cu(x).to(bf), cu(w).to(bf), cu(b), softmax_cols=C)
+    assert qkv.shape == (B, N, 3 * C)
+    plain = ops.linear_fused(cu(x).to(bf), cu(w).to(bf), cu(b))
+    assert torch.equal(qkv[..., C:], plain[..., C:])                            # K and V are untouched
+    assert rel_err(qkv[..., :C].float().cpu().double(), p_ref) < TOL[bf]
+    # (b) per-sample weight
+    ctx = rnd((B, h, 32, 32), 183, 1.0)
+    wo = q_(rnd((C, C), 184, 0.1), bf)
+    bo = rnd((C,), 185, 0.2)
+    wb = ops.ctx_project(cu(ctx), cu(wo).to(bf))
+    wb_ref = torch.einsum("bhje,nhe->bnhj", ctx.double(), wo.double().reshape(C, h, 32)).reshape(B, C, C)
+    assert wb.shape == (B, C, C) and rel_err(wb.float().cpu().double(), wb_ref) < TOL[bf]
+    # (c) output projection of P with W_b + residual + LayerNorm == readout, projection, residual, LayerNorm
+    r_hi = q_(rnd((B, N, C), 186, 2.0) + 0.5, bf)
+    r_lo = q_(rnd((B, N, C), 187, 2.0 ** -9), bf)
+    g, be = 1 + 0.1 * rnd((C,), 188), 0.1 * rnd((C,), 189)
+    P = qkv[..., :C].float().cpu().double()
+    att = torch.einsum("bnhj,bhje->bnhe", P.reshape(B, N, h, 32), ctx.double()).reshape(B, N, C)
+    ref = F.layer_norm(att @ wo.double().t() + bo.double() + r_hi.double() + r_lo.double(), (C,), g.double(), be.double(), eps=1e-6)
+    y, y_lo = ops.linear_fused(qkv, wb, cu(bo), ops.EPI_RES_LN, cu(r_hi).to(bf), cu(r_lo).to(bf), cu(g), cu(be), 1e-6,
+                               want_lo=True, x_cols=C)
+    assert y.shape == (B, N, C) and torch.isfinite(y.float()).all()
+    assert rel_err(y.float().cpu().double(), ref) < TOL[bf]
+    assert rel_err(y.double().cpu() + y_lo.double().cpu(), ref) < 3e-3          # W_b is rounded to bf16 once per sample
+    # every sample alone gives the same bits (a sample's rows never see a neighbour's weight or rows)
+    for s_ in (0, B - 1):
+        y1, _ = ops.linear_fused(qkv[s_:s_ + 1].contiguous(), wb[s_:s_ + 1].contiguous(), cu(bo), ops.EPI_RES_LN,
+                                 cu(r_hi[s_:s_ + 1]).to(bf), cu(r_lo[s_:s_ + 1]).to(bf), cu(g), cu(be), 1e-6, want_lo=True, x_cols=C)
+        assert torch.equal(y1[0], y[s_])
+    with pytest.raises(RuntimeError):
+        ops.linear_fused(cu(x).to(bf), cu(w).to(bf), cu(b), softmax_cols=100)
+    if B > 1:
+        with pytest.raises(ValueError):
+            ops.linear_fused(qkv[:1].contiguous(), wb, cu(bo), ops.EPI_RES_LN, cu(r_hi).to(bf), None, cu(g), cu(be), x_cols=C)
+    # the merge kernel of kv_reduce writes the same W_b for the context it produces
+    ctx2, wb2 = ops.kv_reduce(qkv[..., C:2 * C], qkv[..., 2 * C:], h, w_o=cu(wo).to(bf))
+    assert torch.equal(ctx2, ops.kv_reduce(qkv[..., C:2 * C], qkv[..., 2 * C:], h))
+    assert torch.equal(wb2, ops.ctx_project(ctx2, cu(wo).to(bf)))
 
 
 def test_linear_fused_is_deterministic_and_rejects_bad_shapes():
