@@ -198,11 +198,13 @@ int ltu_kv_reduce_project(const void* k, const void* v, int64_t ld, float* ctx, 
  * reduction of linear_attention (:59-60): K and V are never written to memory (the separate path, ltu_linear_fused +
  * ltu_kv_reduce, writes and re-reads 4 x rows x C x 2 bytes).  x bf16 [B][N][128]; w_kv bf16 [256][128] = Wk rows then Wv
  * rows; bias fp32 [256]; ctx fp32 [B][4][32][32] exactly as ltu_kv_reduce produces it (K, V rounded to bf16 the same way).
- * N % 32 == 0, B <= 30.  workspace: ltu_kv_project_reduce_workspace(B, N) bytes.  supported(): dispatch hint.        */
+ * N % 32 == 0, B <= 30.  workspace: ltu_kv_project_reduce_workspace(B, N) bytes.  supported(): dispatch hint.
+ * wo_bf16 [128][128] and w_out bf16 [B][128][128] (both or neither): the merge kernel also writes ltu_ctx_project's W_b. */
 int ltu_kv_project_reduce_supported(int C, int heads, int64_t N);
 size_t ltu_kv_project_reduce_workspace(int B, int64_t N);
 int ltu_kv_project_reduce(const void* x, const void* w_kv, const float* bias, float* ctx, void* workspace,
-                          size_t workspace_bytes, int B, int64_t N, ltu_stream_t stream);
+                          size_t workspace_bytes, int B, int64_t N, const void* wo_bf16, void* w_out,
+                          ltu_stream_t stream);
 
 /* Fused feed-forward half of SelfAttentionLayer (model/trans_block.py:207-210: linear1 -> erf GELU ->
  * linear2 -> residual -> layer_norm2, dropouts are identity in eval) as ONE persistent tcgen05 kernel:
@@ -236,6 +238,13 @@ int ltu_ctx_pack_bf16(const float* ctx, void* out, int B, int heads, ltu_stream_
 int ltu_attn_out_fused(const void* x, int B, int64_t N, int C, int heads, const void* wq_bf16,
                        const float* bq, const void* ctx_bf16, const void* wo_bf16, const float* bo,
                        const float* gamma, const float* beta, float eps, void* y, ltu_stream_t stream);
+/* The same half-layer with the readout folded into the output projection: (P ctx_b) Wo^T = P (blockdiag(ctx_b) Wo^T).
+ * w_b bf16 [B][128][128] = ltu_ctx_project's per-sample weight (written by the merge kernel of ltu_kv_project_reduce /
+ * ltu_kv_reduce_project).  Two chained GEMMs per tile instead of three; the residual is read from the x tile in shared
+ * memory (x is read from HBM once and never re-read).                                                          */
+int ltu_attn_out_fused_w(const void* x, int B, int64_t N, int C, int heads, const void* wq_bf16,
+                         const float* bq, const void* w_b, const float* bo, const float* gamma,
+                         const float* beta, float eps, void* y, ltu_stream_t stream);
 
 /* Small-channel stride-1 3x3x3 convolution for bf16 activations (stem, enc.block0/1 conv1,
  * dec.block3, finest mask head, final_block): the input halo of a 3-D output tile and all weights are

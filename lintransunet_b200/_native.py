@@ -54,13 +54,14 @@ SIGNATURES = {
     "ltu_ctx_project": (I, [P, P, P, I, I, P]),
     "ltu_kv_project_reduce_supported": (I, [I, I, L]),
     "ltu_kv_project_reduce_workspace": (Z, [I, L]),
-    "ltu_kv_project_reduce": (I, [P, P, P, P, P, Z, I, L, P]),
+    "ltu_kv_project_reduce": (I, [P, P, P, P, P, Z, I, L, P, P, P]),
     "ltu_ffn_fused_supported": (I, [I]),
     "ltu_ffn_fused": (I, [P, L, I, P, P, P, P, P, P, F, P, P]),
     "ltu_ffn_fused_trace": (I, [P, L, I, P, P, P, P, P, P, F, P, P, P]),
     "ltu_attn_out_fused_supported": (I, [I, I]),
     "ltu_ctx_pack_bf16": (I, [P, P, I, I, P]),
     "ltu_attn_out_fused": (I, [P, I, L, I, I, P, P, P, P, P, P, P, F, P, P]),
+    "ltu_attn_out_fused_w": (I, [P, I, L, I, I, P, P, P, P, P, P, F, P, P]),
     "ltu_conv3d_halo_supported": (I, [I, I, I, I, I, I, I, I, I]),
     "ltu_conv3d_halo_tiles": (I, [I, I, I, I]),
     "ltu_conv3d_halo": (I, [P, I, P, I, I, I, I, I, I, P, I, P, I, P, I, P, I, P, P]),

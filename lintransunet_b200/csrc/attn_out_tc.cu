@@ -33,6 +33,8 @@ namespace ltu {
 
 void count_launch(int n = 1);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint64_t ld = 0);
 
 constexpr int kAoThreads = 512;
 constexpr int kAoGroup = 256;
@@ -354,6 +356,273 @@ attn_out128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Second form (ltu_attn_out_fused_w): the readout folded into the output projection.  (P ctx_b) Wo^T = P (ctx_b Wo^T), and
+// W_b = blockdiag(ctx_b) Wo^T is one [128 x 128] bf16 matrix per SAMPLE (written by the kv_combine tail), so a tile needs TWO
+// chained GEMMs instead of three and the attention output never exists, not even in tensor memory:
+//
+//       GQ   R1[128x128] = X . Wq^T            A, B from smem
+//       GO   R2[128x128] = P . W_b^T           A = softmax(Q) as bf16 pairs in R1 (tensor memory), B = the sample's W_b (smem)
+//
+//   warps 0-7    softmax of Q per head (in place, R1)                        warp 16   MMA issue (GQ one tile ahead of GO)
+//   warps 8-15   + bo + residual -> LayerNorm1 -> y (reads R2)               warp 17   TMA: Wq once; x and W_b per tile
+// GQ(t+2) may overwrite R1 as soon as GO(t) has completed; R2 is free again when the LayerNorm warps have read it.
+// An x tile serves three times in its shared-memory slot: A operand of GQ, residual of the LayerNorm (each thread reads its own
+// row half) and, overwritten in place by the same thread, staging tile of the TMA store of y -- no per-thread global access.
+constexpr int kAmThreads = 576;
+constexpr uint32_t kAmOffWq = 0;
+constexpr uint32_t kAmOffX = kAoWBytes;
+constexpr int kAmXSlots = 3;                    // an x tile is the A operand of GQ and, later, the residual of the LayerNorm
+constexpr uint32_t kAmOffM = kAmOffX + kAmXSlots * kAoXBytes;
+constexpr uint32_t kAmOffTail = kAmOffM + 2 * kAoWBytes;
+
+struct AmTail {
+    uint64_t w_full, x_full[kAmXSlots], x_free[kAmXSlots], m_full[2], q_full[2], p_full[2], o_full[2], r2_free[2];
+    uint32_t tmem_slot, pad_;
+    alignas(16) float bq[128], bo[128], gamma[128], beta[128];
+    float2 xs[2][2][128];
+};
+
+__global__ void __launch_bounds__(kAmThreads, 1)
+attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wq,
+                    const __grid_constant__ CUtensorMap tm_m, const __grid_constant__ CUtensorMap tm_y, const AoParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    AmTail* tail = reinterpret_cast<AmTail*>(smem + kAmOffTail);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&tail->w_full), 1);
+        for (int s = 0; s < kAmXSlots; ++s) { mbar_init(smem_u32(&tail->x_full[s]), 1); mbar_init(smem_u32(&tail->x_free[s]), 8); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tail->m_full[s]), 1);
+            mbar_init(smem_u32(&tail->q_full[s]), 1);
+            mbar_init(smem_u32(&tail->p_full[s]), kAoGroup);
+            mbar_init(smem_u32(&tail->o_full[s]), 1);
+            mbar_init(smem_u32(&tail->r2_free[s]), kAoGroup);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 128; i += kAmThreads) {        // parameters: no dependency on the previous kernel
+        tail->bq[i] = p.bq[i]; tail->bo[i] = p.bo[i]; tail->gamma[i] = p.gamma[i]; tail->beta[i] = p.beta[i];
+    }
+    if (warp == 16) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tail->tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_slot;
+    constexpr uint32_t idescQ = umma_idesc_bf16(128, 128);
+
+    if (warp == 17) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            const uint32_t wbar = smem_u32(&tail->w_full);
+            mbar_expect_tx(wbar, kAoWBytes);
+            for (int kb = 0; kb < 2; ++kb) tma_load_2d(sbase + kAmOffWq + kb * 16384, &tm_wq, kb * 64, 0, wbar);
+            pdl_prologue();                                  // x and W_b come from the previous kernels in the stream
+            for (int t = 0; t < n_my; ++t) {
+                const int b = t & 1;
+                const uint32_t ph = (t >> 1) & 1;
+                const int T = (int)blockIdx.x + t * (int)gridDim.x;
+                const int smp = T / p.tps;
+                const int row0 = (int)((int64_t)smp * p.N + (int64_t)(T % p.tps) * 128);
+                const int xs = t % kAmXSlots;
+                if (t >= kAmXSlots) mbar_wait(smem_u32(&tail->x_free[xs]), ((t / kAmXSlots) & 1) ^ 1);   // the stores of y(t-3) have read the slot
+                const uint32_t xb = smem_u32(&tail->x_full[xs]), xd = sbase + kAmOffX + xs * kAoXBytes;
+                mbar_expect_tx(xb, kAoXBytes);
+                tma_load_2d(xd, &tm_x, 0, row0, xb);
+                tma_load_2d(xd + 16384, &tm_x, 64, row0, xb);
+                if (t >= 2) mbar_wait(smem_u32(&tail->o_full[b]), ph ^ 1);      // GO(t-2) has read the W_b slot
+                const uint32_t mb = smem_u32(&tail->m_full[b]), md = sbase + kAmOffM + b * kAoWBytes;
+                mbar_expect_tx(mb, kAoWBytes);
+                tma_load_2d(md, &tm_m, 0, smp * 128, mb);
+                tma_load_2d(md + 16384, &tm_m, 64, smp * 128, mb);
+            }
+        }
+    } else if (warp == 16) {
+        // =========================== MMA issue (whole warp, one elected lane) ===========================
+        mbar_wait(smem_u32(&tail->w_full), 0);
+        for (int t = 0; t <= n_my; ++t) {
+            if (t < n_my) {                                                     // GQ(t)
+                const int b = t & 1;
+                const uint32_t ph = (t >> 1) & 1;
+                if (t >= 2) mbar_wait(smem_u32(&tail->o_full[b]), ph ^ 1);      // GO(t-2) has read P out of R1
+                mbar_wait(smem_u32(&tail->x_full[t % kAmXSlots]), (t / kAmXSlots) & 1);
+                tc_fence_after();
+                const uint32_t xs = sbase + kAmOffX + (t % kAmXSlots) * kAoXBytes;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t adesc = make_desc(xs + kb * 16384), bdesc = make_desc(sbase + kAmOffWq + kb * 16384);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_elect(tmem_base + (uint32_t)(b * 256), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idescQ, (kb | k) != 0);
+                }
+                umma_commit_elect(smem_u32(&tail->q_full[b]));
+            }
+            if (t >= 1) {                                                       // GO(t-1)
+                const int u = t - 1, b = u & 1;
+                const uint32_t ph = (u >> 1) & 1;
+                const uint32_t tacc = tmem_base + (uint32_t)(b * 256);
+                mbar_wait(smem_u32(&tail->m_full[b]), ph);
+                if (u >= 2) mbar_wait(smem_u32(&tail->r2_free[b]), ph ^ 1);     // LayerNorm(u-2) has read R2
+                mbar_wait(smem_u32(&tail->p_full[b]), ph);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {                                   // K-step k = head k/2, j in [16 (k%2), +16)
+                    const uint64_t bdesc = make_desc(sbase + kAmOffM + b * kAoWBytes + (k >> 2) * 16384) + (uint64_t)((k & 3) * 2);
+                    umma_bf16_ts_elect(tacc + 128u, tacc + (uint32_t)(32 * (k >> 1) + 8 * (k & 1)), bdesc, idescQ, k != 0);
+                }
+                umma_commit_elect(smem_u32(&tail->o_full[b]));
+            }
+        }
+    } else {
+        pdl_prologue();
+        const int role = warp >> 3;                // 0: softmax warps, 1: LayerNorm warps
+        const int e = warp & 7;
+        const int q = e & 3;                       // TMEM lane quarter (== warp % 4)
+        const int hh = e >> 2;                     // column half [64hh, 64hh+64): heads 2hh, 2hh+1
+        const int row = q * 32 + lane;             // tile row == TMEM lane
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        if (role == 0) {
+            // =========================== softmax over each head's 32 columns, scaled by 1/sqrt(32); P replaces Q in place
+            for (int t = 0; t < n_my; ++t) {
+                const int b = t & 1;
+                const uint32_t ph = (t >> 1) & 1;
+                const uint32_t tb = tmem_base + lane_off + (uint32_t)(b * 256);
+                mbar_wait(smem_u32(&tail->q_full[b]), ph);
+                tc_fence_after();
+#pragma unroll 1
+                for (int i = 0; i < 2; ++i) {
+                    const int col0 = hh * 64 + i * 32;
+                    uint32_t raw[32];
+                    tmem_ld32_nowait(tb + (uint32_t)col0, raw);
+                    tmem_ld_wait();
+                    float v[32];
+                    const float4* bv = reinterpret_cast<const float4*>(tail->bq + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bb = bv[j];
+                        v[4 * j] = __uint_as_float(raw[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + bb.y;
+                        v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + bb.w;
+                    }
+                    float m = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                    const float mneg = -m * 1.4426950408889634f;
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float ex;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(v[j], 1.4426950408889634f, mneg)));
+                        v[j] = ex;
+                        s += ex;
+                    }
+                    const float inv = 0.17677669529663687f / s;            // 1 / (sqrt(32) * sum)
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j] * inv, v[2 * j + 1] * inv);
+                    tmem_st16(tb + (uint32_t)col0, pk);                    // head h = col0/32: packed columns [32h, 32h+16)
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&tail->p_full[b]));
+            }
+        } else {
+            // =========================== + bo + residual -> LayerNorm1 -> y ===========================
+            for (int t = 0; t < n_my; ++t) {
+                const int b = t & 1;
+                const uint32_t ph = (t >> 1) & 1;
+                const uint32_t tb = tmem_base + lane_off + (uint32_t)(b * 256 + 128);
+                const int T = (int)blockIdx.x + t * (int)gridDim.x;
+                mbar_wait_sleep(smem_u32(&tail->o_full[b]), ph, 32);
+                mbar_wait(smem_u32(&tail->x_full[t % kAmXSlots]), (t / kAmXSlots) & 1);     // completed long ago: makes the TMA write visible here
+                tc_fence_after();
+                float y[64];
+                {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32_nowait(tb + (uint32_t)(64 * hh), v0);
+                    tmem_ld32_nowait(tb + (uint32_t)(64 * hh + 32), v1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&tail->r2_free[b]));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { y[j] = __uint_as_float(v0[j]); y[32 + j] = __uint_as_float(v1[j]); }
+                }
+                float s1 = 0.f;
+                const float4* b2v = reinterpret_cast<const float4*>(tail->bo + hh * 64);
+                // the residual is the row's own x, still in the tile's shared-memory slot (k-block hh, SWIZZLE_128B row)
+                unsigned char* xrow = smem + kAmOffX + (t % kAmXSlots) * kAoXBytes + hh * 16384 + row * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 rv = *reinterpret_cast<const uint4*>(xrow + ((j ^ (row & 7)) << 4));
+                    const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+                    const float4 ba = b2v[2 * j], bb = b2v[2 * j + 1];
+                    const float bs[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float lo = __uint_as_float(w[u] << 16), hi = __uint_as_float(w[u] & 0xffff0000u);
+                        y[j * 8 + 2 * u] += bs[2 * u] + lo;
+                        y[j * 8 + 2 * u + 1] += bs[2 * u + 1] + hi;
+                        s1 += y[j * 8 + 2 * u] + y[j * 8 + 2 * u + 1];
+                    }
+                }
+                const float m_loc = s1 * (1.f / 64.f);
+                float m2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) { const float d = y[j] - m_loc; m2 = fmaf(d, d, m2); }
+                tail->xs[b][hh][row] = make_float2(m_loc, m2);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float2 other = tail->xs[b][hh ^ 1][row];
+                const float mean = 0.5f * (m_loc + other.x);
+                const float dm = m_loc - other.x;
+                const float var = (m2 + other.y + dm * dm * 32.f) * (1.f / 128.f);      // Chan: n_a n_b / (n_a + n_b) = 32
+                const float rstd = rsqrtf(var + p.eps);
+                {
+                    const float4* gv = reinterpret_cast<const float4*>(tail->gamma + hh * 64);
+                    const float4* bv = reinterpret_cast<const float4*>(tail->beta + hh * 64);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 g0 = gv[2 * j], g1 = gv[2 * j + 1], e0 = bv[2 * j], e1 = bv[2 * j + 1];
+                        const float gs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                        const float es[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                        float o[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) o[u] = fmaf((y[j * 8 + u] - mean) * rstd, gs[u], es[u]);
+                        uint4 ov;
+                        ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
+                        ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+                        *reinterpret_cast<uint4*>(xrow + ((j ^ (row & 7)) << 4)) = ov;       // over the residual it was read from
+                    }
+                }
+                // the warp's [32 rows x 64 columns] of y sit in the x slot in the TMA (SWIZZLE_128B) layout: one bulk store per
+                // warp, rows past the end of the sample are clipped by the 3-D map; the slot is free once the store has read it
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&tm_y, sbase + kAmOffX + (t % kAmXSlots) * kAoXBytes + hh * 16384 + q * 4096, hh * 64,
+                                 (T % p.tps) * 128 + q * 32, T / p.tps);
+                    tma_store_commit();
+                    tma_store_wait_read();
+                    mbar_arrive(smem_u32(&tail->x_free[t % kAmXSlots]));
+                }
+            }
+            if (lane == 0) tma_store_wait_all();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ctx fp32 [B][4][32 j][32 e] -> the bf16 B operand of GATT: out[(b*128 + h*32 + e)*64 + j] = ctx[b][h][j][e], j < 32; 0 for j >= 32
 __global__ void ctx_pack_kernel(const float* __restrict__ ctx, bf16* __restrict__ out, int total_rows) {
     const int r = blockIdx.x * (blockDim.x >> 6) + (threadIdx.x >> 6);       // row b*128 + h*32 + e
@@ -406,6 +675,41 @@ extern "C" int ltu_attn_out_fused(const void* x, int B, int64_t N, int C, int he
     if (grid > p.tiles) grid = p.tiles;
     attn_out128_kernel<<<grid, kAoThreads, smem, (cudaStream_t)stream>>>(tx, twq, two, tc, p);
     LTU_LAUNCH_CHECK("attn_out_fused");
+    count_launch(1);
+    return LTU_OK;
+}
+
+// y = LayerNorm(x + softmax_d(x Wq^T + bq)/sqrt(32) . W_b^T + bo): ltu_attn_out_fused with the readout folded into the output
+// projection; w_b bf16 [B][128][128] = blockdiag(ctx_b) Wo^T from ltu_kv_project_reduce / ltu_kv_reduce_project / ltu_ctx_project
+extern "C" int ltu_attn_out_fused_w(const void* x, int B, int64_t N, int C, int heads, const void* wq_bf16, const float* bq,
+                                    const void* w_b, const float* bo, const float* gamma, const float* beta, float eps, void* y,
+                                    ltu_stream_t stream) {
+    LTU_ARG_CHECK(C == 128 && heads == 4, "attn_out_fused_w: d_model %d / heads %d not supported (128 / 4)", C, heads);
+    LTU_ARG_CHECK(x && y && wq_bf16 && w_b && bq && bo && gamma && beta, "attn_out_fused_w: null pointer");
+    LTU_ARG_CHECK(B > 0 && N > 0 && (int64_t)B * N < ((int64_t)1 << 31) - 256, "attn_out_fused_w: bad shape");
+    LTU_ARG_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)wq_bf16 & 15) == 0 && ((uintptr_t)w_b & 15) == 0,
+                  "attn_out_fused_w: pointers must be 16-byte aligned");
+    CUtensorMap tx, twq, tm;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(&tx, x, (uint64_t)B * (uint64_t)N, 128, 128)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&twq, wq_bf16, 128, 128, 128)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm, w_b, (uint64_t)B * 128, 128, 128)) != LTU_OK) return rc;
+    CUtensorMap ty;
+    if ((rc = make_tmap_bf16_3d(&ty, y, (uint64_t)B, (uint64_t)N, 128, 32)) != LTU_OK) return rc;
+    AoParams p;
+    p.x = (const bf16*)x; p.y = (bf16*)y; p.bq = bq; p.bo = bo; p.gamma = gamma; p.beta = beta; p.eps = eps;
+    p.N = N; p.tps = (int)((N + 127) / 128); p.tiles = p.tps * B;
+    const size_t smem = 1024 + kAmOffTail + sizeof(AmTail);
+    static thread_local int configured_dev = -1;
+    int dev; cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaFuncSetAttribute(attn_out128w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured_dev = dev;
+    }
+    int grid = sm_count();
+    if (grid > p.tiles) grid = p.tiles;
+    cudaError_t e = launch_pdl(attn_out128w_kernel, dim3(grid), dim3(kAmThreads), smem, (cudaStream_t)stream, tx, twq, tm, ty, p);
+    if (e != cudaSuccess) { set_error("attn_out_fused_w: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     count_launch(1);
     return LTU_OK;
 }

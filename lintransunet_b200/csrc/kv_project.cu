@@ -438,8 +438,11 @@ extern "C" size_t ltu_kv_project_reduce_workspace(int B, int64_t N) {
 // ctx fp32 [B][4][32][32] = softmax over the N tokens of (x Wk^T + bk), transposed, times (x Wv^T + bv), per head:
 // x bf16 [B][N][128], w_kv bf16 [256][128] = rows 0-127 Wk, rows 128-255 Wv (the nn.Linear weights rounded to bf16),
 // bias fp32 [256]; K and V are rounded to bf16 exactly as the separate projection stores them.  N % 32 == 0.
+// wo_bf16 / w_out (both or neither): the merge kernel also writes W_b = blockdiag(ctx_b) Wo^T, bf16 [B][128][128]
 extern "C" int ltu_kv_project_reduce(const void* x, const void* w_kv, const float* bias, float* ctx, void* workspace,
-                                     size_t workspace_bytes, int B, int64_t N, ltu_stream_t stream) {
+                                     size_t workspace_bytes, int B, int64_t N, const void* wo_bf16, void* w_out,
+                                     ltu_stream_t stream) {
+    LTU_ARG_CHECK((wo_bf16 == nullptr) == (w_out == nullptr), "kv_project_reduce: wo_bf16 and w_out go together");
     LTU_ARG_CHECK(x && w_kv && bias && ctx && workspace, "kv_project_reduce: null pointer");
     LTU_ARG_CHECK(B > 0 && N > 0 && N % 32 == 0 && (int64_t)B * N < ((int64_t)1 << 31) - 256, "kv_project_reduce: bad shape (N %% 32 == 0)");
     LTU_ARG_CHECK((((uintptr_t)x | (uintptr_t)w_kv | (uintptr_t)workspace) & 15) == 0, "kv_project_reduce: pointers must be 16-byte aligned");
@@ -462,7 +465,7 @@ extern "C" int ltu_kv_project_reduce(const void* x, const void* w_kv, const floa
     }
     cudaError_t e = launch_pdl(kv_project_kernel, dim3(pl.grid), dim3(kKvpThreads), smem, (cudaStream_t)stream, tx, tw, p);
     if (e != cudaSuccess) { set_error("kv_project_reduce: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
-    rc = kv_combine_launch((const float*)workspace, ctx, kKvpHeads, B, pl.nparts, (cudaStream_t)stream);
+    rc = kv_combine_launch((const float*)workspace, ctx, kKvpHeads, B, pl.nparts, (cudaStream_t)stream, wo_bf16, w_out);
     if (rc != LTU_OK) return rc;
     count_launch(2);
     return LTU_OK;

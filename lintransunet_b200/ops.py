@@ -987,11 +987,12 @@ def kv_project_reduce_supported(c: int, heads: int, n: int) -> bool:
     return bool(_native.lib().ltu_kv_project_reduce_supported(c, heads, n))
 
 
-def kv_project_reduce(x: torch.Tensor, w_kv: torch.Tensor, b_kv: torch.Tensor, heads: int) -> torch.Tensor:
+def kv_project_reduce(x: torch.Tensor, w_kv: torch.Tensor, b_kv: torch.Tensor, heads: int, w_o: Optional[torch.Tensor] = None):
     """ctx fp32 [B, heads, 32, 32] = kv_reduce(x Wk^T + bk, x Wv^T + bv) in one launch: the K/V projection's output tiles
     are reduced in the GEMM epilogue, K and V never reach memory (csrc/kv_project.cu; d_model 128, 4 heads, bf16).
-    x [B, N, 128] bf16, w_kv [256, 128] bf16 (Wk rows, then Wv rows), b_kv fp32 [256]."""
-    dev = _chk(x, w_kv, b_kv)
+    x [B, N, 128] bf16, w_kv [256, 128] bf16 (Wk rows, then Wv rows), b_kv fp32 [256].  With w_o (the output projection's
+    bf16 weight [128, 128]) the merge kernel also writes ctx_project's per-sample weight and the result is (ctx, W_b)."""
+    dev = _chk(x, w_kv, b_kv, w_o)
     B, N, C = x.shape
     if x.dtype != torch.bfloat16 or w_kv.dtype != torch.bfloat16 or tuple(w_kv.shape) != (2 * C, C):
         raise TypeError("kv_project_reduce needs bf16 tokens and the bf16 [2C, C] K/V weight")
@@ -1000,8 +1001,14 @@ def kv_project_reduce(x: torch.Tensor, w_kv: torch.Tensor, b_kv: torch.Tensor, h
     ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
     ctx = torch.empty(B, heads, 32, 32, dtype=torch.float32, device=dev)
     with _Guard(dev, ("kv_project_reduce", B * N * C * 2, 2 * B * N * C * (2 * C + 32))) as st:
-        check(L.ltu_kv_project_reduce(_p(x), _p(w_kv), _p(b_kv), _p(ctx), _p(ws), nbytes, B, N, st), "ltu_kv_project_reduce")
-    return ctx
+        wb = None
+        if w_o is not None:
+            if w_o.dtype != torch.bfloat16 or tuple(w_o.shape) != (C, C):
+                raise TypeError("kv_project_reduce(w_o=...) needs the bf16 [C, C] weight")
+            wb = torch.empty(B, C, C, dtype=torch.bfloat16, device=dev)
+        check(L.ltu_kv_project_reduce(_p(x), _p(w_kv), _p(b_kv), _p(ctx), _p(ws), nbytes, B, N, _p(w_o), _p(wb), st),
+              "ltu_kv_project_reduce")
+    return ctx if w_o is None else (ctx, wb)
 
 
 def ffn_fused_supported(c: int) -> bool:
@@ -1054,4 +1061,21 @@ def attn_out_fused(x: torch.Tensor, wq: torch.Tensor, bq: torch.Tensor, ctx16: t
     with _Guard(dev, ("attn_out_fused", 2 * x.numel() * 2, 2 * B * N * C * (2 * C + 32))) as st:
         check(_native.lib().ltu_attn_out_fused(_p(x), B, N, C, heads, _p(wq), _p(bq), _p(ctx16), _p(wo), _p(bo),
                                                _p(gamma), _p(beta), eps, _p(y), st), "ltu_attn_out_fused")
+    return y
+
+
+def attn_out_fused_w(x: torch.Tensor, wq: torch.Tensor, bq: torch.Tensor, w_b: torch.Tensor, bo: torch.Tensor,
+                     gamma: torch.Tensor, beta: torch.Tensor, heads: int, eps: float = 1e-6) -> torch.Tensor:
+    """attn_out_fused with the readout folded into the output projection: w_b bf16 [B, C, C] = blockdiag(ctx_b) Wo^T
+    (ctx_project / the merge kernel of kv_project_reduce, kv_reduce).  LayerNorm(x + softmax(x Wq^T + bq)/sqrt(32) W_b^T + bo)."""
+    dev = _chk(x, wq, bq, w_b, bo, gamma, beta)
+    B, N, C = x.shape
+    if x.dtype != torch.bfloat16 or wq.dtype != torch.bfloat16 or w_b.dtype != torch.bfloat16:
+        raise TypeError("attn_out_fused_w needs bf16 activations and weights")
+    if tuple(wq.shape) != (C, C) or tuple(w_b.shape) != (B, C, C):
+        raise ValueError("attn_out_fused_w: operand shapes do not match")
+    y = torch.empty_like(x)
+    with _Guard(dev, ("attn_out_fused", 2 * x.numel() * 2, 2 * B * N * C * 2 * C)) as st:
+        check(_native.lib().ltu_attn_out_fused_w(_p(x), B, N, C, heads, _p(wq), _p(bq), _p(w_b), _p(bo), _p(gamma), _p(beta),
+                                                 eps, _p(y), st), "ltu_attn_out_fused_w")
     return y

@@ -569,17 +569,23 @@ class MaskTransUnet(nn.Module):
         if lw.attn_fused and self.use_fused_attn and not (lw.fused and self.use_fused_linear):
             # K/V projection (cuBLAS) -> kv_reduce -> ONE kernel for Q projection, readout, output projection,
             # residual and LayerNorm1; then ONE kernel for the feed-forward half
+            # fold_readout: the merge kernel of the context reduction also writes W_b = blockdiag(ctx_b) Wo^T and the fused
+            # kernel runs two chained GEMMs per tile (Q projection, P W_b^T) instead of three
+            w_o = lw.w_o if self.fold_readout else None
             if (lw.lin_kv and self.use_native_linear and self.fuse_kv_project and B <= 30
                     and ops.kv_project_reduce_supported(C, lw.nhead, N)):
                 # K/V projection and context reduction in ONE launch: K and V never reach memory
-                ctx = ops.kv_project_reduce(t, lw.w_kv, lw.bkv_f32, lw.nhead)
+                ctx = ops.kv_project_reduce(t, lw.w_kv, lw.bkv_f32, lw.nhead, w_o=w_o)
             else:
                 if lw.lin_kv and self.use_native_linear:
                     kv = ops.linear_fused(t, lw.w_kv, lw.bkv_f32)
                 else:
                     kv = F.linear(t, lw.w_kv, lw.b_kv)
-                ctx = ops.kv_reduce(kv[..., :C], kv[..., C:], lw.nhead)
-            t = ops.attn_out_fused(t, lw.w_q, lw.bq_f32, ops.ctx_pack(ctx), lw.w_o, lw.bo_f32, lw.g1, lw.be1, lw.nhead)
+                ctx = ops.kv_reduce(kv[..., :C], kv[..., C:], lw.nhead, w_o=w_o)
+            if self.fold_readout:
+                t = ops.attn_out_fused_w(t, lw.w_q, lw.bq_f32, ctx[1], lw.bo_f32, lw.g1, lw.be1, lw.nhead)
+            else:
+                t = ops.attn_out_fused(t, lw.w_q, lw.bq_f32, ops.ctx_pack(ctx), lw.w_o, lw.bo_f32, lw.g1, lw.be1, lw.nhead)
             if lw.ffn and self.use_fused_ffn:
                 return ops.ffn_fused(t, lw.w_1, lw.b1_f32, lw.w_2, lw.b2_f32, lw.g2, lw.be2, 1e-6), None
             f = ops.gelu_(F.linear(t, lw.w_1, lw.b_1))

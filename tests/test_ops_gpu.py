@@ -592,8 +592,9 @@ def test_encoder_layer_golden(dtype):
         torch.nn.Module.__init__(m)
         m.use_fused_linear, m.use_fused_ffn, m.use_fused_attn = fused_linear, fused_ffn, fused_attn
         # K/V half of the fused_attn paths: ltu_kv_project_reduce | ltu_linear_fused + kv_reduce | cuBLAS + kv_reduce
-        for native_linear, fuse_kv in ((True, True), (True, False), (False, False)):
-            m.use_native_linear, m.fuse_kv_project = native_linear, fuse_kv
+        for native_linear, fuse_kv, fold in ((True, True, True), (True, True, False), (True, False, True), (True, False, False),
+                                             (False, False, False)):
+            m.use_native_linear, m.fuse_kv_project, m.fold_readout = native_linear, fuse_kv, fold and dtype == torch.bfloat16
             y, lo = MaskTransUnet._encoder_layer(m, x.to("cuda", dtype), _LayerW(layer, dtype))
             assert lo is None
             assert rel_err(y.float(), g["layer_out"]) < (1e-4 if dtype == torch.float32 else 3e-2), (fused_linear, fused_ffn, fused_attn)
@@ -889,3 +890,14 @@ def test_attn_out_fused(B, N):
                            cu(lo.weight).to(torch.bfloat16), cu(lo.bias), cu(g), cu(b), h)
     assert y.shape == (B, N, C)
     assert rel_err(y.float(), ref) < TOL[torch.bfloat16]
+    # the readout folded into the output projection (W_b = blockdiag(ctx_b) Wo^T): two chained GEMMs per tile
+    wb = ops.ctx_project(cu(ctx).contiguous(), cu(lo.weight).to(torch.bfloat16))
+    yw = ops.attn_out_fused_w(x.to("cuda", torch.bfloat16), cu(lq.weight).to(torch.bfloat16), cu(lq.bias), wb, cu(lo.bias),
+                              cu(g), cu(b), h)
+    ref64 = F.layer_norm(x.double() + F.linear(torch.einsum("bnhj,bhje->bnhe", pr.double(), ctx.double()).reshape(B, N, C),
+                                                lo.weight.detach().double(), lo.bias.detach().double()), (C,), g.double(), b.double(), eps=1e-6)
+    e_w, e_3 = rel_err(yw.float().cpu().double(), ref64), rel_err(y.float().cpu().double(), ref64)
+    print(f"\n[attn_out B={B} N={N}] vs fp64: three-GEMM kernel {e_3:.2e}, folded readout {e_w:.2e}")
+    assert yw.shape == (B, N, C) and e_w < TOL[torch.bfloat16] and e_w <= 1.5 * e_3 + 1e-3
+    assert torch.equal(yw, ops.attn_out_fused_w(x.to("cuda", torch.bfloat16), cu(lq.weight).to(torch.bfloat16), cu(lq.bias), wb,
+                                                cu(lo.bias), cu(g), cu(b), h))
