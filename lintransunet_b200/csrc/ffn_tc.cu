@@ -11,15 +11,17 @@
 //   lane quarter, one row per thread:
 //     warps 0-7   e1: acc1 -> +b1 -> erf-GELU -> bf16 pairs -> tcgen05.st over the thread's OWN acc1
 //                 columns (128 hidden columns per thread)
-//     warps 8-15  e2: acc2 -> +b2 + residual (re-read from L2) -> LayerNorm (per-thread mean/M2 merged
-//                 with the row partner by Chan's formula, one smem exchange) -> bf16 -> global
-//                 (64 output columns per thread)
+//     warps 8-15  e2: acc2 -> +b2 + residual (the row's own x, read from the tile's shared-memory slot) ->
+//                 LayerNorm (per-thread mean/M2 merged with the row partner by Chan's formula, one smem
+//                 exchange) -> bf16 written over the residual in the slot -> one TMA store per warp
+//                 (64 output columns per thread; no per-thread global access: a row per lane costs 32 L1
+//                 wavefronts per instruction, which the GELU warps' shared-memory reads had to share)
 //   The GELU warps carry ~75 % of the instructions and never wait for the tensor pipe: acc1 of tile t+1
 //   is complete long before e1(t) ends.  There are no dedicated producer / MMA warps (they would only
 //   spin on barriers and cost issue slots).  MMA issue is warp-uniform (the whole warp runs the descriptor
 //   arithmetic, one elected lane issues):
-//     warp 0 lane 0 : TMA load of tile t+2 (2 x [128 x 64] boxes, SWIZZLE_128B) once acc1(t) is complete
-//                     (GEMM1 has consumed the slot) -- two instructions, no waiting
+//     warp 12 lane 0: TMA load of tile t+2 (2 x [128 x 64] boxes, SWIZZLE_128B) once the stores of y(t) have
+//                     read the slot (the GELU of tile t+1 runs meanwhile)
 //     warp 8        : GEMM2(t)  acc2[128x128] = H . W2^T  (A from TENSOR MEMORY) once H is published; a
 //                     tcgen05.mma issue blocks for about the duration of the MMA, so this must not sit in
 //                     a GELU warp (measured: +2300 cycles per tile on the critical path)
@@ -50,7 +52,7 @@ constexpr uint32_t kFfnOffX = kFfnOffW2 + kFfnW2Bytes;
 constexpr uint32_t kFfnOffTail = kFfnOffX + 2 * kFfnXBytes;
 
 struct FfnTail {
-    uint64_t w_full, x_full[2], acc1_full[2], h_full[2], acc2_full[2], buf_free[2];
+    uint64_t w_full, x_full[2], x_free[2], acc1_full[2], h_full[2], acc2_full[2], buf_free[2];
     uint32_t tmem_slot, pad_;
     alignas(16) float b1[256], b2[128], gamma[128], beta[128];       // read as float4
     float2 xs[2][2][128];           // [tile parity][column half][row] = (mean, M2)
@@ -69,7 +71,7 @@ struct FfnParams {
 // gelu_erf(): common.cuh (A&S 7.1.28 erfc, |error| 3e-7, 16th power on the MUFU pipe)
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
-              const __grid_constant__ CUtensorMap tm_w2, const FfnParams p) {
+              const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_y, const FfnParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // keep the shared address space visible to the compiler (LDS/STS instead of generic accesses)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -82,6 +84,7 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
         mbar_init(smem_u32(&tail->w_full), 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tail->x_full[s]), 1);
+            mbar_init(smem_u32(&tail->x_free[s]), 8);
             mbar_init(smem_u32(&tail->acc1_full[s]), 1);
             mbar_init(smem_u32(&tail->h_full[s]), kFfnGroupThreads);
             mbar_init(smem_u32(&tail->acc2_full[s]), 1);
@@ -154,8 +157,6 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
             mbar_wait(smem_u32(&tail->acc1_full[b]), ph);
             tc_fence_after();
             stamp(t, 1);
-            if (leader && t + 2 < n_my) load_tile(t + 2);       // GEMM1(t) is complete: the slot is free
-            __syncwarp();
             // 16 accumulator columns per step (few live registers -> the 16 independent GELU chains of a step
             // interleave); the 8 packed result columns go back over columns this thread has already consumed
             {
@@ -208,12 +209,7 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
             const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256);
             const int64_t grow = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * 128 + row;
             const bool row_ok = grow < p.rows;
-            uint4 res[8];
-            {
-                const uint4* src = reinterpret_cast<const uint4*>(p.x + (row_ok ? grow : 0) * 128 + hh * 64);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) res[j] = (p.mode & 16) ? make_uint4(0, 0, 0, 0) : __ldg(src + j);
-            }
+            unsigned char* xrow = smem + kFfnOffX + b * kFfnXBytes + hh * 16384 + row * 128;     // this thread's half row of x
             if (e == 0) {                                       // GEMM2 as soon as the GELU group has published H
                 const uint32_t tacc = tmem_base + (uint32_t)(b * 256);
                 mbar_wait_sleep(smem_u32(&tail->h_full[b]), ph, 32);
@@ -244,27 +240,20 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&tail->buf_free[b]));
-                if (e == 4 && t + 2 < n_my) {                   // GEMM1 of tile t+2 into the drained buffer (whole warp, elected issue)
-                    mbar_wait(smem_u32(&tail->buf_free[b]), ph);
-                    stamp(t, 2);
-                    mbar_wait(smem_u32(&tail->x_full[b]), ph ^ 1);
-                    tc_fence_after();
-                    stamp(t, 3);
-                    gemm1(b);
-                }
-                __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { y[j] = __uint_as_float(v0[j]); y[32 + j] = __uint_as_float(v1[j]); }
             }
             if (p.mode & 2) {
-                if (y[0] == 123.456f && row_ok) p.y[grow * 128 + hh * 64] = __float2bfloat16_rn(y[1] + __uint_as_float(res[0].x));
-                continue;
-            }
+                if (y[0] == 123.456f && row_ok) p.y[grow * 128 + hh * 64] = __float2bfloat16_rn(y[1]);
+                if (lane == 0) mbar_arrive(smem_u32(&tail->x_free[b]));
+            } else {
+            mbar_wait(smem_u32(&tail->x_full[b]), ph);          // completed long ago: makes the TMA write visible to this thread
             float s1 = 0.f;
             const float4* b2v = reinterpret_cast<const float4*>(tail->b2 + hh * 64);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint32_t w[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+                const uint4 rv = (p.mode & 16) ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(xrow + ((j ^ (row & 7)) << 4));
+                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
                 const float4 ba = b2v[2 * j], bb = b2v[2 * j + 1];
                 const float bs[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -288,8 +277,7 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
             const float dm = m_loc - other.x;
             const float var = (m2 + other.y + dm * dm * 32.f) * (1.f / 128.f);      // Chan: n_a n_b / (n_a + n_b) = 32
             const float rstd = rsqrtf(var + p.eps);
-            if (row_ok) {
-                uint4* dst = reinterpret_cast<uint4*>(p.y + grow * 128 + hh * 64);
+            {
                 const float4* gv = reinterpret_cast<const float4*>(tail->gamma + hh * 64);
                 const float4* bv = reinterpret_cast<const float4*>(tail->beta + hh * 64);
 #pragma unroll
@@ -303,11 +291,36 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                     uint4 ov;
                     ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
                     ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
-                    dst[j] = ov;
+                    *reinterpret_cast<uint4*>(xrow + ((j ^ (row & 7)) << 4)) = ov;        // over the residual it was read from
                 }
             }
+            // the warp's [32 rows x 64 columns] of y sit in the x slot in the TMA (SWIZZLE_128B) layout: one bulk store per warp,
+            // rows past the end are clipped by the tensor map; the slot is free once the store has read it
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tm_y, sbase + kFfnOffX + b * kFfnXBytes + hh * 16384 + q * 4096, hh * 64,
+                             ((int)blockIdx.x + t * (int)gridDim.x) * 128 + q * 32);
+                tma_store_commit();
+                tma_store_wait_read();
+                mbar_arrive(smem_u32(&tail->x_free[b]));
+            }
+            }
             stamp(t, 6);
+            if (e == 4 && t + 2 < n_my) {                       // whole warp: tile t+2 into the slot and the TMEM buffer of tile t
+                mbar_wait(smem_u32(&tail->x_free[b]), ph);      // every warp's store has read the slot
+                mbar_wait(smem_u32(&tail->buf_free[b]), ph);
+                stamp(t, 2);
+                if (lane == 0) load_tile(t + 2);
+                __syncwarp();
+                mbar_wait(smem_u32(&tail->x_full[b]), ph ^ 1);
+                tc_fence_after();
+                stamp(t, 3);
+                gemm1(b);
+            }
+            __syncwarp();
         }
+        if (lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -409,6 +422,8 @@ static int ffn_launch(const void* x, int64_t rows, int C, const void* w1_bf16, c
     if ((rc = make_tmap_bf16_2d(&tx, x, (uint64_t)rows, 128, 128)) != LTU_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&tw1, w1_bf16, 256, 128, 256)) != LTU_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&tw2, w2_bf16, 128, 256, 128)) != LTU_OK) return rc;
+    CUtensorMap ty;
+    if ((rc = make_tmap_bf16_2d(&ty, y, (uint64_t)rows, 128, 32)) != LTU_OK) return rc;
     FfnParams p;
     p.x = (const bf16*)x; p.y = (bf16*)y; p.rows = rows;
     p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps;
@@ -424,7 +439,7 @@ static int ffn_launch(const void* x, int64_t rows, int C, const void* w1_bf16, c
     }
     int grid = sm_count();
     if (grid > p.tiles) grid = p.tiles;
-    ffn128_kernel<<<grid, kFfnThreads, smem, (cudaStream_t)stream>>>(tx, tw1, tw2, p);
+    ffn128_kernel<<<grid, kFfnThreads, smem, (cudaStream_t)stream>>>(tx, tw1, tw2, ty, p);
     LTU_LAUNCH_CHECK("ffn_fused");
     count_launch(1);
     return LTU_OK;
