@@ -350,7 +350,7 @@ add_layernorm_kernel(const T* __restrict__ x, const T* __restrict__ xlo, const T
 
 template <typename T> __device__ __forceinline__ float gelu_of(float v);
 template <> __device__ __forceinline__ float gelu_of<float>(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
-template <> __device__ __forceinline__ float gelu_of<bf16>(float v) { return gelu_erf(v); }   // |error| 3e-7, then rounded to bf16
+template <> __device__ __forceinline__ float gelu_of<bf16>(float v) { return gelu_erf(v); }   // relative error 8e-5 (common.cuh), then rounded to bf16
 
 template <typename T>
 __global__ void __launch_bounds__(256) gelu_kernel(T* __restrict__ x, int64_t nvec) {

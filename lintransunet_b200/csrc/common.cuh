@@ -90,23 +90,60 @@ __device__ __forceinline__ void store4(bf16* p, const float (&r)[4]) {
     *reinterpret_cast<uint2*>(p) = v;
 }
 
-// erf-based GELU, x * Phi(x), with erfc from Abramowitz & Stegun 7.1.28
-//   erfc(z) = (1 + a1 z + ... + a6 z^6)^-16,  |error| <= 3e-7   (z = |x| / sqrt(2), folded into the a_k)
-// gelu(x) = max(x,0) - |x| erfc(z) / 2.  The 16th power goes to the MUFU pipe, p^-16 = ex2(-16 lg2 p), and every
-// multiply-add has an immediate operand: 6 FFMA + 2 FMUL + 1 FFMA on the FMA pipe, 2 MUFU, 1 FMNMX, no branches.
-// Used where the result is rounded to bf16 (the fp32 path keeps erff).
+// erf-based GELU, x * Phi(x) = max(x,0) - |x| erfc(z) / 2, z = |x| / sqrt(2), with
+//   erfc(z) = exp(-z^2) erfcx(z),   erfcx(z) ~ P9(z/2 - 1) on [0, 4]   (weighted Chebyshev fit, relative error 8.3e-5 in fp32
+//   Horner form; z is clamped at 4, beyond which the term is below 6e-8 in absolute value).
+// The exponential carries the decay, so the RELATIVE accuracy holds along the whole negative tail (the Abramowitz & Stegun
+// 7.1.28 form used before, (1 + a1 z + ... + a6 z^6)^-16, is accurate to 3e-7 ABSOLUTE: 14 % relative at x = -5, 16 % of the
+// bf16-rounded results off by an ulp against 0.4 % here) and it costs ONE MUFU (ex2) instead of two (lg2, ex2): the XU pipe,
+// 4 lanes per clock and scheduler, was the busiest pipe of the GELU epilogues.  Used where the result is rounded to bf16
+// (the fp32 path keeps erff).
+#define LTU_GELU_C0 2.554074526e-01f
+#define LTU_GELU_C1 -2.135173380e-01f
+#define LTU_GELU_C2 1.665058434e-01f
+#define LTU_GELU_C3 -1.244897023e-01f
+#define LTU_GELU_C4 9.327740967e-02f
+#define LTU_GELU_C5 -5.744498968e-02f
+#define LTU_GELU_C6 1.998868026e-02f
+#define LTU_GELU_C7 -2.029449306e-02f
+#define LTU_GELU_C8 3.327577561e-02f
+#define LTU_GELU_C9 -1.571550407e-02f
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x);
-    float p = fmaf(z, 0.0000430638f * 0.125f, 0.0002765672f * 0.17677669529663687f);
-    p = fmaf(p, z, 0.0001520143f * 0.25f);
-    p = fmaf(p, z, 0.0092705272f * 0.35355339059327373f);
-    p = fmaf(p, z, 0.0422820123f * 0.5f);
-    p = fmaf(p, z, 0.0705230784f * 0.70710678118654752f);
-    p = fmaf(p, z, 1.0f);
-    float l, r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(p));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -16.f));
-    return fmaf(-0.5f * z, r, fmaxf(x, 0.f));
+    const float ax = fabsf(x);
+    const float s = fminf(fmaf(ax, 0.35355339059327373f, -1.f), 1.f);        // z / 2 - 1
+    float p = fmaf(LTU_GELU_C9, s, LTU_GELU_C8);
+    p = fmaf(p, s, LTU_GELU_C7); p = fmaf(p, s, LTU_GELU_C6); p = fmaf(p, s, LTU_GELU_C5); p = fmaf(p, s, LTU_GELU_C4);
+    p = fmaf(p, s, LTU_GELU_C3); p = fmaf(p, s, LTU_GELU_C2); p = fmaf(p, s, LTU_GELU_C1); p = fmaf(p, s, LTU_GELU_C0);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * -0.7213475108f) * x));   // exp(-x^2 / 2)
+    return fmaf((p * e) * ax, -0.5f, fmaxf(x, 0.f));
+}
+
+// Two elements per instruction on the packed fp32 pipe (fma.rn.f32x2 / mul.rn.f32x2): the same arithmetic as gelu_erf,
+// bit for bit (every operation is the same IEEE fp32 operation, only issued in pairs).
+__device__ __forceinline__ uint64_t f32x2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f32x2_get(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ void gelu_erf_pair(float x0, float x1, float& y0, float& y1) {
+    const float a0 = fabsf(x0), a1 = fabsf(x1);
+    const uint64_t S = f32x2(fminf(fmaf(a0, 0.35355339059327373f, -1.f), 1.f), fminf(fmaf(a1, 0.35355339059327373f, -1.f), 1.f));
+    uint64_t P = fma2(0xBC80BDCDBC80BDCDULL, S, 0x3D084C2E3D084C2EULL);      // c9 s + c8
+    P = fma2(P, S, 0xBCA640A3BCA640A3ULL);                                    // c7
+    P = fma2(P, S, 0x3CA3BF4D3CA3BF4DULL);                                    // c6
+    P = fma2(P, S, 0xBD6B4B70BD6B4B70ULL);                                    // c5
+    P = fma2(P, S, 0x3DBF083A3DBF083AULL);                                    // c4
+    P = fma2(P, S, 0xBDFEF475BDFEF475ULL);                                    // c3
+    P = fma2(P, S, 0x3E2A80823E2A8082ULL);                                    // c2
+    P = fma2(P, S, 0xBE5AA44ABE5AA44AULL);                                    // c1
+    P = fma2(P, S, 0x3E82C4C43E82C4C4ULL);                                    // c0
+    const uint64_t X = f32x2(x0, x1);
+    float t0, t1, e0, e1;
+    f32x2_get(mul2(mul2(X, 0xBF38AA3BBF38AA3BULL), X), t0, t1);               // (x * -log2(e)/2) * x
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+    const uint64_t W = mul2(mul2(P, f32x2(e0, e1)), f32x2(a0, a1));           // (p e) |x|
+    f32x2_get(fma2(W, 0xBF000000BF000000ULL, f32x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), y0, y1);
 }
 
 // ---------------------------------------------------------------- warp helpers

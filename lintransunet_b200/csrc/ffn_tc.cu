@@ -68,7 +68,7 @@ struct FfnParams {
     long long* trace;       // debug: [2 roles][64 tiles][8 events] clock64 stamps of CTA 0 (nullptr = off)
 };
 
-// gelu_erf(): common.cuh (A&S 7.1.28 erfc, |error| 3e-7, 16th power on the MUFU pipe)
+// gelu_erf_pair(): common.cuh (erfc = exp(-z^2) P9(z/2 - 1), one MUFU, packed fp32 pipe)
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
               const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_y, const FfnParams p) {
@@ -178,8 +178,11 @@ ffn128_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
                     } else
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        pk[2 * j] = pack_bf16x2(gelu_erf(__uint_as_float(cur[4 * j]) + bb[j].x), gelu_erf(__uint_as_float(cur[4 * j + 1]) + bb[j].y));
-                        pk[2 * j + 1] = pack_bf16x2(gelu_erf(__uint_as_float(cur[4 * j + 2]) + bb[j].z), gelu_erf(__uint_as_float(cur[4 * j + 3]) + bb[j].w));
+                        float g0, g1, g2, g3;
+                        gelu_erf_pair(__uint_as_float(cur[4 * j]) + bb[j].x, __uint_as_float(cur[4 * j + 1]) + bb[j].y, g0, g1);
+                        gelu_erf_pair(__uint_as_float(cur[4 * j + 2]) + bb[j].z, __uint_as_float(cur[4 * j + 3]) + bb[j].w, g2, g3);
+                        pk[2 * j] = pack_bf16x2(g0, g1);
+                        pk[2 * j + 1] = pack_bf16x2(g2, g3);
                     }
                     tmem_st8(abase + (uint32_t)(8 * s8), pk);
                     if (s8 < 7) {

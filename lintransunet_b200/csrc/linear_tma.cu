@@ -282,7 +282,7 @@ linear_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                                       __uint_as_float(src[6]) + bb.z, __uint_as_float(src[7]) + bb.w};
                         if (p.epi == kLinGelu && !(p.mode & 2)) {
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) o[u] = gelu_erf(o[u]);
+                            for (int u = 0; u < 8; u += 2) gelu_erf_pair(o[u], o[u + 1], o[u], o[u + 1]);
                         }
                         uint4 ov;
                         ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
