@@ -30,6 +30,12 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 int kv_combine_launch(const float* ws, float* ctx, int heads, int B, int nparts, cudaStream_t st, const void* wo = nullptr,
                       void* wout = nullptr);            // attn_kernels.cu
 
+// second form (kv_project2.cu): G = P^T x on the tensor pipe, V never computed per token
+bool kv_project2_enabled();
+size_t kv_project2_workspace(int B, int64_t N);
+int kv_project2_launch(const void* x, const void* w_kv, const float* bias, float* ctx, void* workspace, int B, int64_t N,
+                       const void* wo_bf16, void* w_out, cudaStream_t stream);
+
 namespace {
 
 constexpr int kKvpThreads = 576;                              // 18 warps: producer, MMA issue, 16 epilogue / reduce warps
@@ -432,7 +438,8 @@ extern "C" int ltu_kv_project_reduce_supported(int C, int heads, int64_t N) {
 
 extern "C" size_t ltu_kv_project_reduce_workspace(int B, int64_t N) {
     const KvpPlan pl = kvp_plan(B, N);
-    return (size_t)B * pl.nparts * kKvpHeads * kKvpPart * sizeof(float);
+    const size_t a = (size_t)B * pl.nparts * kKvpHeads * kKvpPart * sizeof(float), b = kv_project2_workspace(B, N);
+    return a > b ? a : b;
 }
 
 // ctx fp32 [B][4][32][32] = softmax over the N tokens of (x Wk^T + bk), transposed, times (x Wv^T + bv), per head:
@@ -449,6 +456,7 @@ extern "C" int ltu_kv_project_reduce(const void* x, const void* w_kv, const floa
     const KvpPlan pl = kvp_plan(B, N);
     LTU_ARG_CHECK(workspace_bytes >= ltu_kv_project_reduce_workspace(B, N), "kv_project_reduce: workspace too small");
     LTU_ARG_CHECK(B <= 30, "kv_project_reduce: at most 30 samples per call (sample mask of a warp)");
+    if (kv_project2_enabled()) return kv_project2_launch(x, w_kv, bias, ctx, workspace, B, N, wo_bf16, w_out, (cudaStream_t)stream);
     CUtensorMap tx, tw;
     int rc;
     if ((rc = make_tmap_bf16_2d(&tx, x, (uint64_t)B * N, 128, 128)) != LTU_OK) return rc;

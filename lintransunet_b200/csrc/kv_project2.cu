@@ -1,0 +1,496 @@
+// Key / value half of the linear-attention core for d_model 128, second form: V is never computed per token at all.
+//
+//     ctx[b][h][j][e] = sum_n P[n][j] V[n][e] / sum_n P[n][j],      P = exp(K - r_j),  K = x Wk^T + bk,  V = x Wv^T + bv
+//                     = ( (P^T x) Wv^T )[j][e] / s_j + bv[e],       s_j = sum_n P[n][j]            (trans_block.py:59-60, :155-156)
+//
+// The value projection is linear, so it commutes with the sum over tokens: a CTA accumulates  G = P^T x  ([128 j] x [128 c],
+// all four heads at once, no block-diagonal waste) and the column sums s over its tokens ENTIRELY on the tensor pipe, in
+// tensor memory, across all of its tiles; the [128 x 128] x [128 x 32] product with Wv happens once per sample and head in
+// the merge kernel.  Per 128-token tile:
+//
+//     MMA1   Kacc[128 n x 128 j]  = x . Wk^T            A = the x tile (K-major), B = Wk (shared memory, resident)
+//     warps  P = 2^(K log2e - r_j) as bf16 -> shared memory, in the layout the x tile itself has
+//     MMA2   G[128 j x 128 c]    += P^T . x             A = P, B = the SAME x tile, both read MN-major (token axis = K)
+//     MMA3   S[128 j x 16]       += P^T . 1             column sums of the bf16-rounded P (what the numerator uses)
+//
+// against kv_project.cu (K | V accumulators, both halves staged as bf16 and reduced with mma.sync behind a serial TMEM ->
+// register -> shared-memory chain per warp): half the epilogue work, no mma.sync, x read from HBM once.
+//
+//   warp 0      TMA producer (Wk once, then the x tiles of the CTA's contiguous tile range, 3-stage ring)
+//   warp 1      tcgen05.mma issue: MMA1 of tile i, then MMA2 / MMA3 of tile i-1 (P of tile i-1 is computed under MMA1 of tile i)
+//   warps 2-9   two warps per TMEM lane quarter (64 key columns each), one token row per thread
+// Tiles are aligned to samples (3-D tensor map: rows past a sample's end load as zeros and get P = 0).  The reference r_j
+// (log2 units) is the column maximum of the CTA's first tile of a sample; one `bar.red.or` per tile tells every warp
+// whether any key ran away from it by more than 64 -- only then the CTA raises the reference and rescales G and S in
+// tensor memory by 2^(r_old - r_new) (per TMEM lane = per key column), exactly.  When its tile range leaves a sample the
+// CTA writes (G, s, r) as one partial; kvg_combine_kernel merges a sample's partials in a fixed order, applies Wv, bv and
+// 1 / s, and (optionally) folds the context into the output projection's weight like kv_combine_kernel's tail.
+#include <cuda.h>
+
+#include "tc_common.cuh"
+
+namespace ltu {
+
+void count_launch(int n = 1);
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);   // ffn_tc.cu
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint64_t ld = 0);
+
+namespace {
+
+constexpr int kK2Threads = 320;                               // producer, MMA issue, 8 softmax warps
+constexpr int kK2Stages = 3;
+constexpr int kK2PartFloats = 128 * 128 + 256;                // G[128 j][128 c], r[128] (log2 units), s[128]
+constexpr uint32_t kK2WBytes = 128 * 128 * 2;                 // Wk: two k-blocks of [128 x 64] bf16
+constexpr uint32_t kK2XBytes = 128 * 128 * 2;                 // x tile / P tile: two blocks of [128 rows x 64] bf16
+constexpr uint32_t kK2OffRing = kK2WBytes;
+constexpr uint32_t kK2OffP = kK2OffRing + kK2Stages * kK2XBytes;
+constexpr uint32_t kK2OffOnes = kK2OffP + 2 * kK2XBytes;
+constexpr uint32_t kK2OffTail = kK2OffOnes + 2048;
+constexpr float kL2e = 1.4426950408889634f;
+constexpr uint32_t kColG = 256, kColS = 384;                  // tensor memory: Kacc 0 / 128, G, S
+
+struct K2Tail {
+    uint64_t w_full, x_full[kK2Stages], x_empty[kK2Stages], kacc_full[2], kacc_free[2], p_full[2], p_free[2], g_ready, g_flushed;
+    uint32_t tmem_slot, pad_;
+    alignas(16) float bias[128];        // bk * log2(e)
+    alignas(16) float ref[128];         // reference of the current sample (log2 units)
+    alignas(16) float fac[128];
+    alignas(16) float cmax[4][128];
+};
+
+struct K2Params {
+    const float* bias;                  // [256]: bk | bv
+    float* part;                        // [B][nparts][kK2PartFloats]
+    int64_t N;
+    int B, tps, tiles_m, nparts;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// MN-major SWIZZLE_128B operand: 64-element blocks 16 KB apart (LBO), 8-row K groups 1 KB apart (SBO)   (tools/umma_probe_mn.py)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(16384 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// column maxima of a [32 lanes][32 columns] register tile with 31 shuffles: afterwards lane l holds the maximum of column l
+__device__ __forceinline__ float transpose_max32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = upper ? v[i] : v[i + s];
+            const float keep = upper ? v[i + s] : v[i];
+            v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, s));
+        }
+    }
+    return v[0];
+}
+__device__ __forceinline__ bool bar_red_or_256(bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "bar.red.or.pred p, 1, 256, q;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(r) : "r"((uint32_t)pred) : "memory");
+    return r != 0;
+}
+__device__ __forceinline__ void bar_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// contiguous tile ranges: CTA c owns tiles [c * M / G, (c + 1) * M / G)
+__host__ __device__ __forceinline__ int64_t k2_begin(int64_t c, int64_t M, int64_t G) { return c * M / G; }
+__host__ __device__ __forceinline__ int64_t k2_owner(int64_t t, int64_t M, int64_t G) { return ((t + 1) * G - 1) / M; }
+
+__global__ void __launch_bounds__(kK2Threads, 1)
+kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const K2Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    K2Tail* tail = reinterpret_cast<K2Tail*>(smem + kK2OffTail);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t G = gridDim.x, M = p.tiles_m;
+    const int t0 = (int)k2_begin(blockIdx.x, M, G), t1 = (int)k2_begin(blockIdx.x + 1, M, G);
+    const int n_my = t1 - t0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&tail->w_full), 1);
+        for (int s = 0; s < kK2Stages; ++s) { mbar_init(smem_u32(&tail->x_full[s]), 1); mbar_init(smem_u32(&tail->x_empty[s]), 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&tail->kacc_full[i]), 1); mbar_init(smem_u32(&tail->kacc_free[i]), 8);
+            mbar_init(smem_u32(&tail->p_full[i]), 8); mbar_init(smem_u32(&tail->p_free[i]), 1);
+        }
+        mbar_init(smem_u32(&tail->g_ready), 1);
+        mbar_init(smem_u32(&tail->g_flushed), 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 128; i += kK2Threads) tail->bias[i] = p.bias[i] * kL2e;
+    for (int i = threadIdx.x; i < 2048 / 4; i += kK2Threads) reinterpret_cast<uint32_t*>(smem + kK2OffOnes)[i] = 0x3F803F80u;   // bf16 1.0
+    fence_async_smem();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tail->tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_slot;
+    // tile i of this CTA: sample, first row inside it, and whether it opens / closes the CTA's stretch of that sample
+    auto tile_b = [&](int i) { return (t0 + i) / p.tps; };
+    auto opens = [&](int i) { return i == 0 || tile_b(i) != tile_b(i - 1); };
+    auto closes = [&](int i) { return i == n_my - 1 || tile_b(i) != tile_b(i + 1); };
+
+    if (warp == 0) {
+        // =========================== producer ===========================
+        if (lane == 0) {
+            const uint32_t wb = smem_u32(&tail->w_full);
+            mbar_expect_tx(wb, kK2WBytes);
+            tma_load_2d(sbase, &tm_w, 0, 0, wb);                             // Wk is a parameter: no dependency to wait for
+            tma_load_2d(sbase + kK2WBytes / 2, &tm_w, 64, 0, wb);
+            pdl_prologue();                                                  // x comes from the previous kernel in the stream
+            for (int i = 0; i < n_my; ++i) {
+                const int stage = i % kK2Stages, T = t0 + i, b = T / p.tps, r0 = (T - b * p.tps) * 128;
+                mbar_wait(smem_u32(&tail->x_empty[stage]), ((i / kK2Stages) & 1) ^ 1);
+                const uint32_t fb = smem_u32(&tail->x_full[stage]), dst = sbase + kK2OffRing + stage * kK2XBytes;
+                mbar_expect_tx(fb, kK2XBytes);
+                tma_load_3d(dst, &tm_x, 0, r0, b, fb);
+                tma_load_3d(dst + kK2XBytes / 2, &tm_x, 64, r0, b, fb);
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issue ===========================
+        constexpr uint32_t idesc1 = umma_idesc_bf16(128, 128);
+        constexpr uint32_t idesc2 = umma_idesc_bf16(128, 128) | (1u << 15) | (1u << 16);     // A = P and B = x read MN-major
+        constexpr uint32_t idesc3 = umma_idesc_bf16(128, 16) | (1u << 15) | (1u << 16);
+        const uint64_t ones = make_desc_mn(sbase + kK2OffOnes);
+        mbar_wait(smem_u32(&tail->w_full), 0);
+        uint32_t nflush = 0;
+        for (int i = 0; i <= n_my; ++i) {
+            if (i < n_my) {                                                   // MMA1(i): Kacc = x Wk^T
+                const uint32_t ab = i & 1;
+                const int stage = i % kK2Stages;
+                mbar_wait(smem_u32(&tail->kacc_free[ab]), ((i >> 1) & 1) ^ 1);
+                mbar_wait(smem_u32(&tail->x_full[stage]), (i / kK2Stages) & 1);
+                tc_fence_after();
+                const uint32_t xs = sbase + kK2OffRing + stage * kK2XBytes;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t adesc = make_desc(xs + kb * (kK2XBytes / 2)), bdesc = make_desc(sbase + kb * (kK2WBytes / 2));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_elect(tmem_base + ab * 128u, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
+                }
+                umma_commit_elect(smem_u32(&tail->kacc_full[ab]));
+            }
+            if (i >= 1) {                                                     // MMA2 / MMA3 of tile u = i - 1
+                const int u = i - 1;
+                const uint32_t pb = u & 1;
+                const int stage = u % kK2Stages;
+                const bool first = opens(u);
+                if (first && nflush > 0) {                                    // the previous sample's G and S have been read out
+                    mbar_wait(smem_u32(&tail->g_flushed), (nflush - 1) & 1);
+                }
+                mbar_wait(smem_u32(&tail->p_full[pb]), (u >> 1) & 1);
+                tc_fence_after();
+                const uint32_t ps = sbase + kK2OffP + pb * kK2XBytes, xs = sbase + kK2OffRing + stage * kK2XBytes;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {                                 // K-step = 16 tokens = 2 KB down both tiles
+                    const uint64_t adesc = make_desc_mn(ps + (uint32_t)(k * 2048));
+                    umma_bf16_elect(tmem_base + kColG, adesc, make_desc_mn(xs + (uint32_t)(k * 2048)), idesc2, (uint32_t)(!first || k != 0));
+                    umma_bf16_elect(tmem_base + kColS, adesc, ones, idesc3, (uint32_t)(!first || k != 0));
+                }
+                umma_commit_elect(smem_u32(&tail->x_empty[stage]));
+                umma_commit_elect(smem_u32(&tail->p_free[pb]));
+                if (closes(u)) { umma_commit_elect(smem_u32(&tail->g_ready)); ++nflush; }
+            }
+        }
+    } else {
+        // =========================== softmax numerators, reference, flush ===========================
+        pdl_prologue();
+        const int e = warp - 2;
+        const int q = warp & 3;                          // TMEM lane quarter (warp id % 4)
+        const int hh = e >> 2;                           // key columns [64 hh, +64)
+        const int row = q * 32 + lane;                   // token row of a tile; key column j = row when reading G
+        const int et = threadIdx.x - 64;                 // 0..255
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const uint32_t swz = (uint32_t)(lane & 7);
+        uint32_t nflush = 0;
+        for (int i = 0; i < n_my; ++i) {
+            const uint32_t ab = i & 1;
+            const int T = t0 + i, b = T / p.tps, r0 = (T - b * p.tps) * 128;
+            const bool valid = (int64_t)(r0 + row) < p.N;
+            const bool first = opens(i);
+            mbar_wait_sleep(smem_u32(&tail->kacc_full[ab]), (i >> 1) & 1, 32);
+            tc_fence_after();
+            float d[64];                                 // k log2e (+ bias), then minus the reference
+            {
+                uint32_t v0[32], v1[32];
+                tmem_ld32_nowait(tmem_base + lane_off + ab * 128u + (uint32_t)(hh * 64), v0);
+                tmem_ld32_nowait(tmem_base + lane_off + ab * 128u + (uint32_t)(hh * 64 + 32), v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tail->kacc_free[ab]));
+                const float4* bs = reinterpret_cast<const float4*>(tail->bias + hh * 64);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float4 bb = bs[c];
+                    const uint32_t* src = c < 8 ? v0 + 4 * c : v1 + 4 * (c - 8);
+                    d[4 * c] = fmaf(__uint_as_float(src[0]), kL2e, bb.x); d[4 * c + 1] = fmaf(__uint_as_float(src[1]), kL2e, bb.y);
+                    d[4 * c + 2] = fmaf(__uint_as_float(src[2]), kL2e, bb.z); d[4 * c + 3] = fmaf(__uint_as_float(src[3]), kL2e, bb.w);
+                }
+            }
+            // has any key of this tile run away from the sample's reference?  (one block-wide vote per tile)
+            bool away = first;
+            if (!first && valid) {
+                const float4* rf = reinterpret_cast<const float4*>(tail->ref + hh * 64);
+                float dmax = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float4 r = rf[c];
+                    dmax = fmaxf(dmax, fmaxf(fmaxf(d[4 * c] - r.x, d[4 * c + 1] - r.y), fmaxf(d[4 * c + 2] - r.z, d[4 * c + 3] - r.w)));
+                }
+                away = dmax > 64.f;
+            }
+            if (bar_red_or_256(away)) {
+                // ---- new reference = max(old reference, column maxima of this tile); rescale what has been accumulated
+                float m0[32], m1[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) { m0[c] = valid ? d[c] : -INFINITY; m1[c] = valid ? d[32 + c] : -INFINITY; }
+                const float c0 = transpose_max32(m0, lane), c1 = transpose_max32(m1, lane);
+                tail->cmax[q][hh * 64 + lane] = c0;
+                tail->cmax[q][hh * 64 + 32 + lane] = c1;
+                bar_sync_256();
+                if (et < 128) {
+                    const float m = fmaxf(fmaxf(tail->cmax[0][et], tail->cmax[1][et]), fmaxf(tail->cmax[2][et], tail->cmax[3][et]));
+                    const float r_old = tail->ref[et];
+                    const float r_new = first ? m : fmaxf(r_old, m);
+                    tail->fac[et] = first ? 1.f : ex2(r_old - r_new);
+                    tail->ref[et] = r_new;
+                }
+                bar_sync_256();
+                if (!first) {
+                    // every MMA2 issued so far (tiles < i) must have landed: the last one signals p_free of tile i - 1
+                    mbar_wait(smem_u32(&tail->p_free[(i - 1) & 1]), ((i - 1) >> 1) & 1);
+                    tc_fence_after();
+                    const float f = tail->fac[row];                        // G / S lane = key column
+                    {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32_nowait(tmem_base + lane_off + kColG + (uint32_t)(hh * 64), v0);
+                        tmem_ld32_nowait(tmem_base + lane_off + kColG + (uint32_t)(hh * 64 + 32), v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) { v0[c] = __float_as_uint(__uint_as_float(v0[c]) * f); v1[c] = __float_as_uint(__uint_as_float(v1[c]) * f); }
+                        tmem_st32u(tmem_base + lane_off + kColG + (uint32_t)(hh * 64), v0);
+                        tmem_st32u(tmem_base + lane_off + kColG + (uint32_t)(hh * 64 + 32), v1);
+                    }
+                    if (hh == 0) {
+                        uint32_t s16[16];
+                        tmem_ld16_nowait(tmem_base + lane_off + kColS, s16);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) s16[c] = __float_as_uint(__uint_as_float(s16[c]) * f);
+                        tmem_st16(tmem_base + lane_off + kColS, s16);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    bar_sync_256();
+                }
+            }
+            // ---- P = 2^(d - r) as bf16 into the P tile (the layout of an x tile: two [128 rows x 64] SWIZZLE_128B blocks)
+            mbar_wait(smem_u32(&tail->p_free[ab]), ((i >> 1) & 1) ^ 1);      // MMA2(i - 2) has read this buffer
+            {
+                unsigned char* prow = smem + kK2OffP + ab * kK2XBytes + hh * (kK2XBytes / 2) + row * 128;
+                const float4* rf = reinterpret_cast<const float4*>(tail->ref + hh * 64);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 ra = rf[2 * c], rb = rf[2 * c + 1];
+                    uint4 ov;
+                    if (valid) {
+                        ov.x = pack_bf16x2(ex2(d[8 * c] - ra.x), ex2(d[8 * c + 1] - ra.y));
+                        ov.y = pack_bf16x2(ex2(d[8 * c + 2] - ra.z), ex2(d[8 * c + 3] - ra.w));
+                        ov.z = pack_bf16x2(ex2(d[8 * c + 4] - rb.x), ex2(d[8 * c + 5] - rb.y));
+                        ov.w = pack_bf16x2(ex2(d[8 * c + 6] - rb.z), ex2(d[8 * c + 7] - rb.w));
+                    } else {
+                        ov = make_uint4(0, 0, 0, 0);
+                    }
+                    *reinterpret_cast<uint4*>(prow + (((uint32_t)c ^ swz) << 4)) = ov;
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tail->p_full[ab]));
+            // ---- the CTA's stretch of this sample ends here: write (G, r, s) as one partial
+            if (closes(i)) {
+                const int64_t c_lo = k2_owner((int64_t)b * p.tps, M, G);
+                float* out = p.part + ((int64_t)b * p.nparts + ((int64_t)blockIdx.x - c_lo)) * kK2PartFloats;
+                mbar_wait(smem_u32(&tail->g_ready), nflush & 1);
+                tc_fence_after();
+                float g[32];
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    tmem_ld32(tmem_base + lane_off + kColG + (uint32_t)(hh * 64 + c * 32), g);
+                    float4* dst = reinterpret_cast<float4*>(out + row * 128 + hh * 64 + c * 32);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) dst[k] = make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
+                }
+                if (hh == 0) {
+                    uint32_t s16[16];
+                    tmem_ld16_nowait(tmem_base + lane_off + kColS, s16);
+                    tmem_ld_wait();
+                    out[128 * 128 + row] = tail->ref[row];
+                    out[128 * 128 + 128 + row] = __uint_as_float(s16[0]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tail->g_flushed));
+                ++nflush;
+                bar_sync_256();                          // nobody may overwrite the reference (next sample) before everyone has written it out
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// Merge of a sample's partials (fixed order), the value projection, and the optional fold into the output projection:
+//   grid (4 heads, B), 1024 threads: warp jj = key column j = 32 h + jj of the head, lane = 4 x-channels / value column e
+__global__ void __launch_bounds__(1024)
+kvg_combine_kernel(const float* __restrict__ part, const bf16* __restrict__ w_kv, const float* __restrict__ bias,
+                   float* __restrict__ ctx, int nparts, int tps, int tiles_m, int grid_main,
+                   const bf16* __restrict__ wo, bf16* __restrict__ wout) {
+    extern __shared__ __align__(16) float sm[];
+    float* Gs = sm;                                   // [32 jj][128 c]
+    float* Wv = Gs + 32 * 128;                        // [32 e][129]
+    float* cs = Wv + 32 * 129;                        // [32 e][33]   ctx[jj][e] transposed
+    float* ws_ = cs + 32 * 33;                        // [128 n][32 e]  Wo[n][32 h + e]
+    const int hd = blockIdx.x, b = blockIdx.y;
+    const int jj = threadIdx.x >> 5, e = threadIdx.x & 31;
+    // parameters first: they do not depend on the previous kernel
+    for (int c = e; c < 128; c += 32) Wv[jj * 129 + c] = __bfloat162float(w_kv[(int64_t)(128 + 32 * hd + jj) * 128 + c]);
+    if (wo != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ws_[(jj + 32 * i) * 32 + e] = __bfloat162float(wo[(int64_t)(jj + 32 * i) * 128 + 32 * hd + e]);
+    }
+    const float bv = bias[128 + 32 * hd + e];
+    pdl_prologue();
+    const int64_t c_lo = k2_owner((int64_t)b * tps, tiles_m, grid_main), c_hi = k2_owner((int64_t)(b + 1) * tps - 1, tiles_m, grid_main);
+    const int nvalid = (int)(c_hi - c_lo + 1);
+    const float* base = part + (int64_t)b * nparts * kK2PartFloats;
+    const int j = 32 * hd + jj;
+    float Mx = -INFINITY;
+    for (int q = e; q < nvalid; q += 32) Mx = fmaxf(Mx, base[(int64_t)q * kK2PartFloats + 128 * 128 + j]);
+    Mx = warp_max(Mx);
+    float S = 0.f;
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q0 = 0; q0 < nvalid; q0 += 32) {
+        const int q = q0 + e;
+        float wl = 0.f, sp = 0.f;
+        if (q < nvalid) {
+            wl = ex2(base[(int64_t)q * kK2PartFloats + 128 * 128 + j] - Mx);
+            sp = base[(int64_t)q * kK2PartFloats + 128 * 128 + 128 + j];
+        }
+        S += warp_sum(sp * wl);
+        const int cnt = nvalid - q0 < 32 ? nvalid - q0 : 32;
+        for (int u = 0; u < cnt; ++u) {
+            const float w = __shfl_sync(0xffffffffu, wl, u);
+            const float4 gq = *reinterpret_cast<const float4*>(base + (int64_t)(q0 + u) * kK2PartFloats + j * 128 + 4 * e);
+            A.x = fmaf(gq.x, w, A.x); A.y = fmaf(gq.y, w, A.y); A.z = fmaf(gq.z, w, A.z); A.w = fmaf(gq.w, w, A.w);
+        }
+    }
+    *reinterpret_cast<float4*>(Gs + jj * 128 + 4 * e) = A;
+    __syncthreads();
+    // ctx[jj][e] = (sum_c G[jj][c] Wv[e][c]) / s + bv[e]
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < 128; ++c) acc = fmaf(Gs[jj * 128 + c], Wv[e * 129 + c], acc);
+    const float cv = acc / S + bv;
+    ctx[(((int64_t)b * 4 + hd) * 32 + jj) * 32 + e] = cv;
+    if (wo == nullptr) return;
+    cs[e * 33 + jj] = cv;
+    __syncthreads();
+    float c[32];                                     // lane e holds row j' = e of the context: c[k] = ctx[e][k]
+#pragma unroll
+    for (int k = 0; k < 32; ++k) c[k] = cs[k * 33 + e];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                    // thread (warp jj, lane e): row n = jj + 32 i, column 32 hd + e
+        const float4* w4 = reinterpret_cast<const float4*>(ws_ + (jj + 32 * i) * 32);
+        float a2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 w = w4[k];
+            a2 = fmaf(w.x, c[4 * k], a2); a2 = fmaf(w.y, c[4 * k + 1], a2);
+            a2 = fmaf(w.z, c[4 * k + 2], a2); a2 = fmaf(w.w, c[4 * k + 3], a2);
+        }
+        wout[((int64_t)b * 128 + jj + 32 * i) * 128 + 32 * hd + e] = __float2bfloat16_rn(a2);
+    }
+}
+
+struct K2Plan { int grid, tps, tiles_m, nparts; };
+
+K2Plan k2_plan(int B, int64_t N) {
+    K2Plan pl;
+    pl.tps = (int)((N + 127) / 128);
+    pl.tiles_m = pl.tps * B;
+    pl.grid = sm_count() < pl.tiles_m ? sm_count() : pl.tiles_m;
+    int64_t worst = 1;
+    for (int b = 0; b < B; ++b) {
+        const int64_t c_lo = k2_owner((int64_t)b * pl.tps, pl.tiles_m, pl.grid);
+        const int64_t c_hi = k2_owner((int64_t)(b + 1) * pl.tps - 1, pl.tiles_m, pl.grid);
+        if (c_hi - c_lo + 1 > worst) worst = c_hi - c_lo + 1;
+    }
+    pl.nparts = (int)worst;
+    return pl;
+}
+
+}  // namespace
+
+bool kv_project2_enabled() {
+    static const bool on = [] { const char* e = getenv("LTU_KV_PROJECT2"); return !(e && e[0] == '0'); }();   // A/B switch
+    return on;
+}
+
+size_t kv_project2_workspace(int B, int64_t N) {
+    const K2Plan pl = k2_plan(B, N);
+    return (size_t)B * pl.nparts * kK2PartFloats * sizeof(float);
+}
+
+// x bf16 [B][N][128]; w_kv bf16 [256][128] (Wk rows, then Wv rows); bias fp32 [256]; ctx fp32 [B][4][32][32]
+int kv_project2_launch(const void* x, const void* w_kv, const float* bias, float* ctx, void* workspace, int B, int64_t N,
+                       const void* wo_bf16, void* w_out, cudaStream_t stream) {
+    const K2Plan pl = k2_plan(B, N);
+    CUtensorMap tx, tw;
+    int rc;
+    if ((rc = make_tmap_bf16_3d(&tx, x, (uint64_t)B, (uint64_t)N, 128, 128)) != LTU_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&tw, w_kv, 128, 128, 128)) != LTU_OK) return rc;          // the Wk half
+    K2Params p;
+    p.bias = bias; p.part = (float*)workspace; p.N = N; p.B = B;
+    p.tps = pl.tps; p.tiles_m = pl.tiles_m; p.nparts = pl.nparts;
+    const size_t smem = 1024 + kK2OffTail + sizeof(K2Tail);
+    const size_t smem_c = (size_t)(32 * 128 + 32 * 129 + 32 * 33 + 128 * 32) * sizeof(float);
+    static thread_local int configured_dev = -1;
+    int dev; cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaFuncSetAttribute(kv_project2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kvg_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+        configured_dev = dev;
+    }
+    cudaError_t e = launch_pdl(kv_project2_kernel, dim3(pl.grid), dim3(kK2Threads), smem, stream, tx, tw, p);
+    if (e != cudaSuccess) { set_error("kv_project_reduce: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    e = launch_pdl(kvg_combine_kernel, dim3(4, B), dim3(1024), smem_c, stream, (const float*)workspace, (const bf16*)w_kv, bias, ctx,
+                   pl.nparts, pl.tps, pl.tiles_m, pl.grid, (const bf16*)wo_bf16, (bf16*)w_out);
+    if (e != cudaSuccess) { set_error("kv_project_reduce: merge launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    count_launch(2);
+    return LTU_OK;
+}
+
+}  // namespace ltu
