@@ -50,8 +50,8 @@ def main():
     tot = collections.Counter()
     for n in sorted(names, key=lambda n: demangle[n]):
         c = counts[n]
-        short = re.sub(r"\(.*", "", demangle[n]).replace("void ", "").replace("ltu::", "")
-        short = re.sub(r"\(anonymous namespace\)::", "", short)
+        short = demangle[n].replace("(anonymous namespace)::", "")
+        short = re.sub(r"\(.*", "", short).replace("void ", "").replace("ltu::", "")
         print(f"| `{short}` | {c['_total']} | " + " | ".join(str(c[k]) if c[k] else "" for k in KEYS) + " |")
         tot.update(c)
     print(f"| **all {len(names)} kernels** | {tot['_total']} | " + " | ".join(str(tot[k]) for k in KEYS) + " |")

@@ -81,7 +81,14 @@ def main():
         f.write(f"# `ncu --set full --clock-control none --import-source on` captures (tools/ncu_capture{'' if a.round == 'r1' else '_' + a.round}.sh)\n\n"
                 "Target: tools/ncu_target.py (second eager forward, batch 8 x 128^3, bf16).  Raw exports: "
                 f"`{a.round}_prof_*_raw.csv`.\n")
-    for name, title in (("lin", "linear_tma_kernel (bridge 2, layer 0: QKV | O + LN | FFN1 + GELU | FFN2 + LN; 86016 rows, d_model 256)"),
+    final = (("kvp2", "kv_project2_kernel + kvg_combine_kernel (bridge 1 key / value half: B=8, N=57408, d_model 128; G = P^T x on tcgen05)"),
+             ("kv8", "kv_stream_kernel<8> (bridge 2: N=10752, C=256, 8 heads)"),
+             ("lin", "linear_tma_kernel (bridge 2, layer 0: QKV with softmax(Q) | P W_b^T + LN | FFN1 + GELU | FFN2 + LN; 86016 rows, d_model 256)"),
+             ("ffn", "ffn128_kernel (fused FFN half, bridge 1: 459264 rows, d_model 128; residual and y through the x tile's smem slot)"),
+             ("attnout", "attn_out128w_kernel (fused query half, bridge 1: Q projection, softmax, P W_b^T, LayerNorm)"),
+             ("tc3", "conv3d_tc3 (TMA halo + tcgen05)"), ("tc", "conv3d_tc (tcgen05 implicit GEMM, im2col per tap)"),
+             ("halo", "conv3d_halo (smem halo + mma.sync)"))
+    for name, title in final if a.round == "r2b" else (("lin", "linear_tma_kernel (bridge 2, layer 0: QKV | O + LN | FFN1 + GELU | FFN2 + LN; 86016 rows, d_model 256)"),
                         ("linkv", "linear_tma_kernel (bridge 1 K/V projection: 459264 rows, 128 -> 256)"),
                         ("kv", "kv_reduce (bridge 1: B=8, N=57408, C=128, 4 heads)"), ("kv8", "kv_reduce (bridge 2: N=10752, C=256, 8 heads)"),
                         ("q", "q_readout (bridge 2: N=10752, C=256; bridge 1 runs inside attn_out128_kernel)"),
