@@ -278,6 +278,11 @@ int ltu_instnorm_apply(const void* x, const float* stats, const void* residual, 
 int ltu_s2d_input(const float* x, void* y, int B, int H, int W, int D, int cpad, int dtype,
                   ltu_stream_t stream);
 
+/* torch.cat([a, b], dim=1) of the UpBlock (model/Unet_3Dblock.py:553) on channels-last rows: out [rows][Ca + Cb].  Used
+ * where the two inputs have 32 channels each: the concatenation is ONE 64-channel input of ltu_conv3d_tc3 (TMA halo +
+ * tcgen05), which the two-input form of that kernel cannot take (64-channel TMA boxes).                          */
+int ltu_concat2(const void* a, int Ca, const void* b, int Cb, void* out, int64_t rows, int dtype, ltu_stream_t stream);
+
 /* ---- a12: nn.Upsample(trilinear, align_corners=True), model/Unet_3Dblock.py:1341-1345 ------
  * scale factors (2,2,fd) with fd in {1,2}; channels-last                                     */
 int ltu_upsample_trilinear(const void* x, void* y, int B, int H, int W, int D, int C, int fd,

@@ -36,6 +36,7 @@ SIGNATURES = {
     "ltu_loss_sums_bwd": (I, [P, P, P, P, I, I, L, P]),
     "ltu_label_pool": (I, [P, P, I, I, I, I, I, I, I, P]),
     "ltu_dropout": (I, [P, P, L, I, L, F, U64, U64, I, I, P]),
+    "ltu_concat2": (I, [P, I, P, I, P, L, I, P]),
     "ltu_posenc_dwconv3": (I, [P, P, P, P, I, I, I, I, I, I, P]),
     "ltu_posenc_dwconv3_split": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "ltu_conv3d_tiles": (I, [L, I]),

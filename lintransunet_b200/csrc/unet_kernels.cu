@@ -435,3 +435,37 @@ extern "C" int ltu_gather_windows(const float* volume, const int32_t* starts, fl
     count_launch(1);
     return LTU_OK;
 }
+
+namespace ltu {
+// out[r][0 : Ca) = a[r], out[r][Ca : Ca + Cb) = b[r]   (16-byte vectors; Ca, Cb multiples of 8 bf16 / 4 fp32 elements)
+__global__ void __launch_bounds__(256)
+concat2_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, int64_t rows, int va, int vb) {
+    pdl_prologue();
+    const int vo = va + vb;
+    const int64_t total = rows * vo;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vo;
+        const int c = (int)(i - r * vo);
+        out[i] = c < va ? __ldg(a + r * va + c) : __ldg(b + r * vb + (c - va));
+    }
+}
+}  // namespace ltu
+
+// torch.cat([a, b], dim=channel) of two channels-last tensors with the same rows (model/Unet_3Dblock.py:553): lets a layer
+// whose two inputs have 32 channels each run as ONE 64-channel input of the TMA-halo tcgen05 kernel (ltu_conv3d_tc3)
+extern "C" int ltu_concat2(const void* a, int Ca, const void* b, int Cb, void* out, int64_t rows, int dtype, ltu_stream_t stream) {
+    LTU_ARG_CHECK(a && b && out && rows > 0, "concat2: bad arguments");
+    LTU_ARG_CHECK(dtype == LTU_F32 || dtype == LTU_BF16, "concat2: bad dtype %d", dtype);
+    const int vn = dtype == LTU_F32 ? 4 : 8;
+    LTU_ARG_CHECK(Ca > 0 && Cb > 0 && Ca % vn == 0 && Cb % vn == 0, "concat2: channel counts must be multiples of %d", vn);
+    LTU_ARG_CHECK((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0, "concat2: pointers must be 16-byte aligned");
+    const int64_t total = rows * ((Ca + Cb) / vn);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    cudaError_t e = launch_pdl(concat2_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const uint4*)a, (const uint4*)b,
+                               (uint4*)out, rows, Ca / vn, Cb / vn);
+    if (e != cudaSuccess) { set_error("concat2: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    count_launch(1);
+    return LTU_OK;
+}

@@ -20,6 +20,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_LRELU = 0, 1
 USE_HALO_CONV = os.environ.get("LTU_DISABLE_HALO", "0") != "1"     # A/B switch for the small-channel conv kernel
 USE_TC3_CONV = os.environ.get("LTU_DISABLE_TC3", "0") != "1"       # A/B switch for the TMA-halo tcgen05 conv kernel
+USE_CONCAT_TC3 = os.environ.get("LTU_CONCAT_TC3", "1") == "1"      # 32 + 32 input channels: concatenate once, run on the TMA-halo kernel
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -450,6 +451,18 @@ def conv_out_size(n: int, k: int, s: int, pad: int) -> int:
     return (n + 2 * pad - k) // s + 1
 
 
+def concat2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """torch.cat([a, b], dim=-1) of two channels-last tensors (model/Unet_3Dblock.py:553), one native copy kernel."""
+    dev = _chk(a, b)
+    if a.shape[:-1] != b.shape[:-1] or a.dtype != b.dtype:
+        raise ValueError("concat2: inputs must agree in everything but the channel count")
+    out = torch.empty(*a.shape[:-1], a.shape[-1] + b.shape[-1], dtype=a.dtype, device=dev)
+    rows = a.numel() // a.shape[-1]
+    with _Guard(dev, ("concat", 2 * out.numel() * out.element_size(), 0)) as st:
+        check(_native.lib().ltu_concat2(_p(a), a.shape[-1], _p(b), b.shape[-1], _p(out), rows, _dt(a), st), "ltu_concat2")
+    return out
+
+
 def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ksize: int,
            stride: Tuple[int, int, int] = (1, 1, 1), pad: int = 1, x1: Optional[torch.Tensor] = None,
            up2: bool = False, out_f32: bool = False, want_stats: bool = False,
@@ -474,6 +487,13 @@ def conv3d(x0: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     C1 = 0 if x1 is None else x1.shape[-1]
     if x1 is not None:
         assert x1.shape[:4] == x0.shape[:4] and x1.dtype == x0.dtype
+    if (x1 is not None and USE_CONCAT_TC3 and USE_TC3_CONV and w_tc is not None and x0.dtype == torch.bfloat16 and C0 % 64 != 0
+            and (C0 + C1) % 64 == 0 and w_tc.shape[-2] % 32 == 0 and (out_f32 or cout % 8 == 0)
+            and L.ltu_conv3d_tc_supported(C0, C1, cout + n_aux, ksize, pad) == 1
+            and L.ltu_conv3d_tc3_supported(C0 + C1, 0, cout, ksize, stride[0], stride[1], stride[2], pad, int(up2), int(out_f32), n_aux) == 1):
+        # two 32-channel inputs: written side by side once, the layer runs as ONE 64-channel input of the TMA-halo tcgen05
+        # kernel (its packed weight already has the inputs' channels in this order) instead of the im2col gather kernel
+        x0, x1, C0, C1 = concat2(x0, x1), None, C0 + C1, 0
     He, We, De = (2 * Hi, 2 * Wi, 2 * Di) if up2 else (Hi, Wi, Di)
     Ho, Wo, Do = (conv_out_size(He, ksize, stride[0], pad), conv_out_size(We, ksize, stride[1], pad),
                   conv_out_size(De, ksize, stride[2], pad))

@@ -525,7 +525,7 @@ class MaskTransUnet(nn.Module):
     def _knobs(self) -> tuple:
         """Every runtime switch that changes the launched kernels (part of the CUDA-graph cache key)."""
         return (self.use_tensor_cores, self.use_fused_linear, self.fuse_mask_head, self.use_fused_ffn, self.use_fused_attn,
-                self.split_token_stream, self.use_native_linear, self.fuse_kv_project, self.fold_readout, self.skip_dead_mask_head, ops.USE_HALO_CONV, ops.USE_TC3_CONV, ops.USE_SV_CONV)
+                self.split_token_stream, self.use_native_linear, self.fuse_kv_project, self.fold_readout, self.skip_dead_mask_head, ops.USE_HALO_CONV, ops.USE_TC3_CONV, ops.USE_SV_CONV, ops.USE_CONCAT_TC3)
 
     def _capture(self, x: torch.Tensor, plan: "_Plan", head: str) -> dict:
         static_x = x.clone()

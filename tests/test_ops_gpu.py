@@ -780,6 +780,40 @@ def test_linear_fused_folded_readout(B, N):
     assert torch.equal(wb2, ops.ctx_project(ctx2, cu(wo).to(bf)))
 
 
+def test_concat2_and_the_concatenated_tc3_path():
+    """ltu_concat2 == torch.cat on channels-last rows; a 3x3x3 layer with two 32-channel inputs (dec.block2.conv2) runs as ONE
+    64-channel input of the TMA-halo tcgen05 kernel and gives the bits of ... the same exact bf16 products, fp32 accumulation
+    (summation order differs from the im2col kernel: compared to fp64)."""
+    ops = _ops()
+    bf = torch.bfloat16
+    a = rnd((2, 6, 10, 16, 32), 300).to("cuda", bf)
+    b = rnd((2, 6, 10, 16, 32), 301).to("cuda", bf)
+    assert torch.equal(ops.concat2(a, b), torch.cat([a, b], -1))
+    af = rnd((3, 5, 8), 302).cuda()
+    assert torch.equal(ops.concat2(af, rnd((3, 5, 4), 303).cuda())[..., :8], af)
+    from lintransunet_b200.unet import _ConvW
+    conv = torch.nn.Conv3d(64, 32, 3, padding=1)
+    with torch.no_grad():
+        conv.weight.copy_(q_(conv.weight, bf))
+    conv.cuda()
+    cw = _ConvW(conv, want_tc=True, n_inputs=2)
+    xin = torch.cat([a, b], -1).float().permute(0, 4, 1, 2, 3).double().cpu()
+    ref = F.conv3d(xin, conv.weight.detach().double().cpu(), conv.bias.detach().double().cpu(), padding=1).permute(0, 2, 3, 4, 1)
+    outs = {}
+    for knob in (True, False):
+        ops.USE_CONCAT_TC3 = knob
+        try:
+            y, part, _ = ops.conv3d(a, cw.w, cw.b, cw.cout, 3, pad=1, x1=b, want_stats=True, w_tc=cw.w_tc)
+        finally:
+            ops.USE_CONCAT_TC3 = True
+        outs[knob] = y
+        assert rel_err(y.float().cpu().double(), ref) < TOL[bf]
+        V = y.shape[1] * y.shape[2] * y.shape[3]
+        st = ops.instnorm_finalize(part, V)
+        assert rel_err(st[..., 0].cpu().double(), y.float().cpu().double().reshape(2, V, 32).mean(1)) < 1e-3
+    assert rel_err(outs[True].float(), outs[False].float()) < 1e-2
+
+
 def test_linear_fused_is_deterministic_and_rejects_bad_shapes():
     ops = _ops()
     bf = torch.bfloat16
