@@ -16,7 +16,7 @@
 // against kv_project.cu (K | V accumulators, both halves staged as bf16 and reduced with mma.sync behind a serial TMEM ->
 // register -> shared-memory chain per warp): half the epilogue work, no mma.sync, x read from HBM once.
 //
-//   warp 0      TMA producer (Wk once, then the x tiles of the CTA's contiguous tile range, 3-stage ring)
+//   warp 0      TMA producer (Wk once, then the x tiles of the CTA's contiguous tile range inside ONE sample, 3-stage ring)
 //   warp 1      tcgen05.mma issue: MMA1 of tile i, then MMA2 / MMA3 of tile i-1 (P of tile i-1 is computed under MMA1 of tile i)
 //   warps 2-17  four warps per TMEM lane quarter (32 key columns each), one token row per thread
 // Tiles are aligned to samples (3-D tensor map: rows past a sample's end load as zeros and get P = 0).  The reference r_j
@@ -68,6 +68,7 @@ struct K2Params {
     int64_t N;
     int B, tps, tiles_m, nparts;
     int mode;                           // debug ablations (LTU_KVP_MODE): 1 no MMA3 (sums), 2 no MMA2 / MMA3, 4 no exponentials, 8 no vote
+    long long* trace;                   // debug (LTU_KVP_TRACE_PTR): [3 roles][64 tiles][8 events] clock64 stamps of CTA 0, nullptr = off
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -108,7 +109,6 @@ __device__ __forceinline__ void bar_sync_256() { asm volatile("bar.sync 1, %0;" 
 
 // contiguous tile ranges: CTA c owns tiles [c * M / G, (c + 1) * M / G)
 __host__ __device__ __forceinline__ int64_t k2_begin(int64_t c, int64_t M, int64_t G) { return c * M / G; }
-__host__ __device__ __forceinline__ int64_t k2_owner(int64_t t, int64_t M, int64_t G) { return ((t + 1) * G - 1) / M; }
 
 __global__ void __launch_bounds__(kK2Threads, 1)
 kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const K2Params p) {
@@ -117,10 +117,13 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     K2Tail* tail = reinterpret_cast<K2Tail*>(smem + kK2OffTail);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t G = gridDim.x, M = p.tiles_m;
-    const int t0 = (int)k2_begin(blockIdx.x, M, G), t1 = (int)k2_begin(blockIdx.x + 1, M, G);
+    // CTA (k, b) owns tiles [k tps / cps, (k + 1) tps / cps) of sample b: the split of a sample depends on its token count ONLY,
+    // never on the batch size, so a sample gives the same bits in any batch (the N-GPU sliding window equals the 1-GPU one)
+    const int sample = blockIdx.y;
+    const int t0 = (int)k2_begin(blockIdx.x, p.tps, gridDim.x), t1 = (int)k2_begin(blockIdx.x + 1, p.tps, gridDim.x);
     const int n_my = t1 - t0;
 
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.trace[(0 * 64 + 63) * 8 + 7] = clock64();   // kernel entry
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&tail->w_full), 1);
         for (int s = 0; s < kK2Stages; ++s) { mbar_init(smem_u32(&tail->x_full[s]), 1); mbar_init(smem_u32(&tail->x_empty[s]), 1); }
@@ -144,10 +147,11 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tail->tmem_slot;
-    // tile i of this CTA: sample, first row inside it, and whether it opens / closes the CTA's stretch of that sample
-    auto tile_b = [&](int i) { return (t0 + i) / p.tps; };
-    auto opens = [&](int i) { return i == 0 || tile_b(i) != tile_b(i - 1); };
-    auto closes = [&](int i) { return i == n_my - 1 || tile_b(i) != tile_b(i + 1); };
+    auto opens = [&](int i) { return i == 0; };                 // a CTA works on ONE sample: one reference, one partial
+    auto closes = [&](int i) { return i == n_my - 1; };
+    auto stamp = [&](int role, int i, int ev) {
+        if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && i < 64) p.trace[(role * 64 + i) * 8 + ev] = clock64();
+    };
 
     if (warp == 0) {
         // =========================== producer ===========================
@@ -158,8 +162,9 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             tma_load_2d(sbase + kK2WBytes / 2, &tm_w, 64, 0, wb);
             pdl_prologue();                                                  // x comes from the previous kernel in the stream
             for (int i = 0; i < n_my; ++i) {
-                const int stage = i % kK2Stages, T = t0 + i, b = T / p.tps, r0 = (T - b * p.tps) * 128;
+                const int stage = i % kK2Stages, b = sample, r0 = (t0 + i) * 128;
                 mbar_wait(smem_u32(&tail->x_empty[stage]), ((i / kK2Stages) & 1) ^ 1);
+                stamp(0, i, 0);                                              // x load of tile i issued
                 const uint32_t fb = smem_u32(&tail->x_full[stage]), dst = sbase + kK2OffRing + stage * kK2XBytes;
                 mbar_expect_tx(fb, kK2XBytes);
                 tma_load_3d(dst, &tm_x, 0, r0, b, fb);
@@ -179,7 +184,9 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const uint32_t ab = i & 1;
                 const int stage = i % kK2Stages;
                 mbar_wait(smem_u32(&tail->kacc_free[ab]), ((i >> 1) & 1) ^ 1);
+                stamp(1, i, 0);                                              // Kacc buffer free
                 mbar_wait(smem_u32(&tail->x_full[stage]), (i / kK2Stages) & 1);
+                stamp(1, i, 1);                                              // x tile landed: MMA1(i) issued
                 tc_fence_after();
                 const uint32_t xs = sbase + kK2OffRing + stage * kK2XBytes;
 #pragma unroll
@@ -199,7 +206,9 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 if (first && nflush > 0) {                                    // the previous sample's G and S have been read out
                     mbar_wait(smem_u32(&tail->g_flushed), (nflush - 1) & 1);
                 }
+                stamp(1, u, 2);                                              // waiting for P(u)
                 mbar_wait(smem_u32(&tail->p_full[pb]), (u >> 1) & 1);
+                stamp(1, u, 3);                                              // P(u) published: MMA2 / MMA3 issued
                 tc_fence_after();
                 const uint32_t ps = sbase + kK2OffP + pb * kK2XBytes, xs = sbase + kK2OffRing + stage * kK2XBytes;
 #pragma unroll
@@ -228,10 +237,12 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         uint32_t nflush = 0;
         for (int i = 0; i < n_my; ++i) {
             const uint32_t ab = i & 1;
-            const int T = t0 + i, b = T / p.tps, r0 = (T - b * p.tps) * 128;
+            const int b = sample, r0 = (t0 + i) * 128;
             const bool valid = (int64_t)(r0 + row) < p.N;
             const bool first = opens(i);
+            if (e == 0) stamp(2, i, 0);                      // softmax warp 2: waiting for Kacc(i)
             mbar_wait_sleep(smem_u32(&tail->kacc_full[ab]), (i >> 1) & 1, 32);
+            if (e == 0) stamp(2, i, 1);                      // Kacc(i) complete
             tc_fence_after();
             float d[NC];                                 // k log2e (+ bias), then minus the reference
             {
@@ -262,7 +273,10 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 }
                 away = dmax > 64.f;
             }
-            if ((p.mode & 8) ? first : bar_red_or_256(away)) {
+            if (e == 0) stamp(2, i, 2);                      // accumulator read, runaway check done
+            const bool slow = (p.mode & 8) ? first : bar_red_or_256(away);
+            if (e == 0) stamp(2, i, 3);                      // vote done
+            if (slow) {
                 // ---- new reference = max(old reference, column maxima of this tile); rescale what has been accumulated
 #pragma unroll
                 for (int c = 0; c < NC; c += 32) {
@@ -309,6 +323,7 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             }
             // ---- P = 2^(d - r) as bf16 into the P tile (the layout of an x tile: two [128 rows x 64] SWIZZLE_128B blocks)
             mbar_wait(smem_u32(&tail->p_free[ab]), ((i >> 1) & 1) ^ 1);      // MMA2(i - 2) has read this buffer
+            if (e == 0) stamp(2, i, 4);                      // P buffer free
             {
                 unsigned char* prow = smem + kK2OffP + ab * kK2XBytes + (col0 >> 6) * (kK2XBytes / 2) + row * 128;
                 const uint32_t ch0 = (uint32_t)((col0 & 63) >> 3);           // first 16-byte chunk of this thread inside the row
@@ -334,10 +349,10 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tail->p_full[ab]));
+            if (e == 0) stamp(2, i, 5);                      // P(i) published
             // ---- the CTA's stretch of this sample ends here: write (G, r, s) as one partial
             if (closes(i)) {
-                const int64_t c_lo = k2_owner((int64_t)b * p.tps, M, G);
-                float* out = p.part + ((int64_t)b * p.nparts + ((int64_t)blockIdx.x - c_lo)) * kK2PartFloats;
+                float* out = p.part + ((int64_t)b * p.nparts + (int64_t)blockIdx.x) * kK2PartFloats;
                 mbar_wait(smem_u32(&tail->g_ready), nflush & 1);
                 tc_fence_after();
                 float g[32];
@@ -359,12 +374,14 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&tail->g_flushed));
                 ++nflush;
+                if (e == 0) stamp(2, i, 6);                  // partial written
                 bar_sync_256();                          // nobody may overwrite the reference (next sample) before everyone has written it out
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.trace[(1 * 64 + 63) * 8 + 7] = clock64();   // all roles done
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -375,8 +392,7 @@ kv_project2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 //   grid (4 heads, B), 1024 threads: warp jj = key column j = 32 h + jj of the head, lane = 4 x-channels / value column e
 __global__ void __launch_bounds__(1024)
 kvg_combine_kernel(const float* __restrict__ part, const bf16* __restrict__ w_kv, const float* __restrict__ bias,
-                   float* __restrict__ ctx, int nparts, int tps, int tiles_m, int grid_main,
-                   const bf16* __restrict__ wo, bf16* __restrict__ wout) {
+                   float* __restrict__ ctx, int nparts, const bf16* __restrict__ wo, bf16* __restrict__ wout) {
     extern __shared__ __align__(16) float sm[];
     float* Gs = sm;                                   // [32 jj][128 c]
     float* Wv = Gs + 32 * 128;                        // [32 e][129]
@@ -392,8 +408,7 @@ kvg_combine_kernel(const float* __restrict__ part, const bf16* __restrict__ w_kv
     }
     const float bv = bias[128 + 32 * hd + e];
     pdl_prologue();
-    const int64_t c_lo = k2_owner((int64_t)b * tps, tiles_m, grid_main), c_hi = k2_owner((int64_t)(b + 1) * tps - 1, tiles_m, grid_main);
-    const int nvalid = (int)(c_hi - c_lo + 1);
+    const int nvalid = nparts;
     const float* base = part + (int64_t)b * nparts * kK2PartFloats;
     const int j = 32 * hd + jj;
     float Mx = -INFINITY;
@@ -444,20 +459,14 @@ kvg_combine_kernel(const float* __restrict__ part, const bf16* __restrict__ w_kv
     }
 }
 
-struct K2Plan { int grid, tps, tiles_m, nparts; };
+struct K2Plan { int tps, nparts; };
 
-K2Plan k2_plan(int B, int64_t N) {
+// CTAs per sample: a function of the token count only.  18 x 8 samples = 144 CTAs = one wave at the benchmark's batch.
+K2Plan k2_plan(int /*B*/, int64_t N) {
     K2Plan pl;
     pl.tps = (int)((N + 127) / 128);
-    pl.tiles_m = pl.tps * B;
-    pl.grid = sm_count() < pl.tiles_m ? sm_count() : pl.tiles_m;
-    int64_t worst = 1;
-    for (int b = 0; b < B; ++b) {
-        const int64_t c_lo = k2_owner((int64_t)b * pl.tps, pl.tiles_m, pl.grid);
-        const int64_t c_hi = k2_owner((int64_t)(b + 1) * pl.tps - 1, pl.tiles_m, pl.grid);
-        if (c_hi - c_lo + 1 > worst) worst = c_hi - c_lo + 1;
-    }
-    pl.nparts = (int)worst;
+    const int per_cta = (pl.tps + 17) / 18;
+    pl.nparts = (pl.tps + per_cta - 1) / per_cta;
     return pl;
 }
 
@@ -483,9 +492,10 @@ int kv_project2_launch(const void* x, const void* w_kv, const float* bias, float
     if ((rc = make_tmap_bf16_2d(&tw, w_kv, 128, 128, 128)) != LTU_OK) return rc;          // the Wk half
     K2Params p;
     p.bias = bias; p.part = (float*)workspace; p.N = N; p.B = B;
-    p.tps = pl.tps; p.tiles_m = pl.tiles_m; p.nparts = pl.nparts;
+    p.tps = pl.tps; p.tiles_m = pl.tps * B; p.nparts = pl.nparts;
     static const int dbg_mode = [] { const char* e = getenv("LTU_KVP_MODE"); return e ? atoi(e) : 0; }();
     p.mode = dbg_mode;
+    { const char* e = getenv("LTU_KVP_TRACE_PTR"); p.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }   // tools/kvp_trace.py
     const size_t smem = 1024 + kK2OffTail + sizeof(K2Tail);
     const size_t smem_c = (size_t)(32 * 128 + 32 * 129 + 32 * 33 + 128 * 32) * sizeof(float);
     static thread_local int configured_dev = -1;
@@ -495,10 +505,10 @@ int kv_project2_launch(const void* x, const void* w_kv, const float* bias, float
         cudaFuncSetAttribute(kvg_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
         configured_dev = dev;
     }
-    cudaError_t e = launch_pdl(kv_project2_kernel, dim3(pl.grid), dim3(kK2Threads), smem, stream, tx, tw, p);
+    cudaError_t e = launch_pdl(kv_project2_kernel, dim3(pl.nparts, B), dim3(kK2Threads), smem, stream, tx, tw, p);
     if (e != cudaSuccess) { set_error("kv_project_reduce: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     e = launch_pdl(kvg_combine_kernel, dim3(4, B), dim3(1024), smem_c, stream, (const float*)workspace, (const bf16*)w_kv, bias, ctx,
-                   pl.nparts, pl.tps, pl.tiles_m, pl.grid, (const bf16*)wo_bf16, (bf16*)w_out);
+                   pl.nparts, (const bf16*)wo_bf16, (bf16*)w_out);
     if (e != cudaSuccess) { set_error("kv_project_reduce: merge launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     count_launch(2);
     return LTU_OK;

@@ -853,6 +853,9 @@ def test_kv_project_reduce(B, N):
     assert e_new < 6e-3                                          # P is rounded to bf16 (the kernels' tensor-pipe operand)
     assert rel_err(ctx, ref_native) < 1.5e-2                     # the separate path rounds K and V to bf16 as well
     assert torch.equal(ctx, ops.kv_project_reduce(x, w, b, h))    # fixed-order merge: bit-reproducible
+    if B > 1:   # a sample is split by a rule of its token count only: the same bits alone or in any batch (N-GPU sliding window == 1 GPU)
+        assert torch.equal(ops.kv_project_reduce(x[1:2].contiguous(), w, b, h), ctx[1:2])
+        assert torch.equal(ops.kv_project_reduce(x[:B - 1].contiguous(), w, b, h), ctx[:B - 1])
     # with the output projection's weight the merge kernel also writes W_b (ctx_project of the same context)
     wo = (torch.randn(C, C, generator=g) * 0.1).to("cuda", bf)
     ctx2, wb = ops.kv_project_reduce(x, w, b, h, w_o=wo)
