@@ -60,6 +60,7 @@ struct AoParams {
     float eps;
     int tiles, tps;                 // total tiles, tiles per sample
     int64_t N;                      // tokens per sample
+    long long* trace;               // debug (LTU_AO_TRACE_PTR, attn_out128w only): [4 roles][64 tiles][8 events] clock64 stamps of CTA 0
 };
 
 __global__ void __launch_bounds__(kAoThreads, 1)
@@ -392,6 +393,9 @@ attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_my = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto stamp = [&](int role, int t, int ev) {
+        if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && t < 64) p.trace[(role * 64 + t) * 8 + ev] = clock64();
+    };
 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&tail->w_full), 1);
@@ -434,11 +438,13 @@ attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 const int row0 = (int)((int64_t)smp * p.N + (int64_t)(T % p.tps) * 128);
                 const int xs = t % kAmXSlots;
                 if (t >= kAmXSlots) mbar_wait(smem_u32(&tail->x_free[xs]), ((t / kAmXSlots) & 1) ^ 1);   // the stores of y(t-3) have read the slot
+                stamp(0, t, 0);                                                 // x(t) load issued
                 const uint32_t xb = smem_u32(&tail->x_full[xs]), xd = sbase + kAmOffX + xs * kAoXBytes;
                 mbar_expect_tx(xb, kAoXBytes);
                 tma_load_2d(xd, &tm_x, 0, row0, xb);
                 tma_load_2d(xd + 16384, &tm_x, 64, row0, xb);
                 if (t >= 2) mbar_wait(smem_u32(&tail->o_full[b]), ph ^ 1);      // GO(t-2) has read the W_b slot
+                stamp(0, t, 1);                                                 // W_b(t) load issued
                 const uint32_t mb = smem_u32(&tail->m_full[b]), md = sbase + kAmOffM + b * kAoWBytes;
                 mbar_expect_tx(mb, kAoWBytes);
                 tma_load_2d(md, &tm_m, 0, smp * 128, mb);
@@ -454,6 +460,7 @@ attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 const uint32_t ph = (t >> 1) & 1;
                 if (t >= 2) mbar_wait(smem_u32(&tail->o_full[b]), ph ^ 1);      // GO(t-2) has read P out of R1
                 mbar_wait(smem_u32(&tail->x_full[t % kAmXSlots]), (t / kAmXSlots) & 1);
+                stamp(1, t, 0);                                                 // GQ(t) issued
                 tc_fence_after();
                 const uint32_t xs = sbase + kAmOffX + (t % kAmXSlots) * kAoXBytes;
 #pragma unroll
@@ -472,6 +479,7 @@ attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 mbar_wait(smem_u32(&tail->m_full[b]), ph);
                 if (u >= 2) mbar_wait(smem_u32(&tail->r2_free[b]), ph ^ 1);     // LayerNorm(u-2) has read R2
                 mbar_wait(smem_u32(&tail->p_full[b]), ph);
+                stamp(1, u, 1);                                                 // GO(u) issued
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {                                   // K-step k = head k/2, j in [16 (k%2), +16)
@@ -495,7 +503,9 @@ attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 const int b = t & 1;
                 const uint32_t ph = (t >> 1) & 1;
                 const uint32_t tb = tmem_base + lane_off + (uint32_t)(b * 256);
+                if (e == 0) stamp(2, t, 0);                                     // softmax warp 0: waiting for Q(t)
                 mbar_wait(smem_u32(&tail->q_full[b]), ph);
+                if (e == 0) stamp(2, t, 1);                                     // Q(t) complete
                 tc_fence_after();
 #pragma unroll 1
                 for (int i = 0; i < 2; ++i) {
@@ -532,6 +542,7 @@ attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&tail->p_full[b]));
+                if (e == 0) stamp(2, t, 2);                                     // P(t) published
             }
         } else {
             // =========================== + bo + residual -> LayerNorm1 -> y ===========================
@@ -540,7 +551,9 @@ attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 const uint32_t ph = (t >> 1) & 1;
                 const uint32_t tb = tmem_base + lane_off + (uint32_t)(b * 256 + 128);
                 const int T = (int)blockIdx.x + t * (int)gridDim.x;
+                if (e == 0) stamp(3, t, 0);                                     // LayerNorm warp 8: waiting for GO(t)
                 mbar_wait_sleep(smem_u32(&tail->o_full[b]), ph, 32);
+                if (e == 0) stamp(3, t, 1);                                     // GO(t) complete
                 mbar_wait(smem_u32(&tail->x_full[t % kAmXSlots]), (t / kAmXSlots) & 1);     // completed long ago: makes the TMA write visible here
                 tc_fence_after();
                 float y[64];
@@ -577,7 +590,9 @@ attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 #pragma unroll
                 for (int j = 0; j < 64; ++j) { const float d = y[j] - m_loc; m2 = fmaf(d, d, m2); }
                 tail->xs[b][hh][row] = make_float2(m_loc, m2);
+                if (e == 0) stamp(3, t, 2);                                     // accumulator read, residual added, partial statistics
                 asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (e == 0) stamp(3, t, 3);                                     // partner's statistics visible
                 const float2 other = tail->xs[b][hh ^ 1][row];
                 const float mean = 0.5f * (m_loc + other.x);
                 const float dm = m_loc - other.x;
@@ -602,6 +617,7 @@ attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 }
                 // the warp's [32 rows x 64 columns] of y sit in the x slot in the TMA (SWIZZLE_128B) layout: one bulk store per
                 // warp, rows past the end of the sample are clipped by the 3-D map; the slot is free once the store has read it
+                if (e == 0) stamp(3, t, 4);                                     // normalised row written to the slot
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -611,6 +627,7 @@ attn_out128w_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     tma_store_wait_read();
                     mbar_arrive(smem_u32(&tail->x_free[t % kAmXSlots]));
                 }
+                if (e == 0) stamp(3, t, 5);                                     // store has read the slot
             }
             if (lane == 0) tma_store_wait_all();
         }
@@ -663,7 +680,7 @@ extern "C" int ltu_attn_out_fused(const void* x, int B, int64_t N, int C, int he
     if ((rc = make_tmap_bf16_2d(&tc, ctx_bf16, (uint64_t)B * 128, 64, 128)) != LTU_OK) return rc;
     AoParams p;
     p.x = (const bf16*)x; p.y = (bf16*)y; p.bq = bq; p.bo = bo; p.gamma = gamma; p.beta = beta; p.eps = eps;
-    p.N = N; p.tps = (int)((N + 127) / 128); p.tiles = p.tps * B;
+    p.N = N; p.tps = (int)((N + 127) / 128); p.tiles = p.tps * B; p.trace = nullptr;
     const size_t smem = 1024 + kAoOffTail + sizeof(AoTail);
     static thread_local int configured_dev = -1;
     int dev; cudaGetDevice(&dev);
@@ -699,6 +716,7 @@ extern "C" int ltu_attn_out_fused_w(const void* x, int B, int64_t N, int C, int 
     AoParams p;
     p.x = (const bf16*)x; p.y = (bf16*)y; p.bq = bq; p.bo = bo; p.gamma = gamma; p.beta = beta; p.eps = eps;
     p.N = N; p.tps = (int)((N + 127) / 128); p.tiles = p.tps * B;
+    { const char* e = getenv("LTU_AO_TRACE_PTR"); p.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }   // tools/ao_trace.py
     const size_t smem = 1024 + kAmOffTail + sizeof(AmTail);
     static thread_local int configured_dev = -1;
     int dev; cudaGetDevice(&dev);
