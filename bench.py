@@ -495,6 +495,10 @@ def run_ours(args):
         dominant = max(ksum.items(), key=lambda kv: kv[1]["ms"])[0] if ksum else None
         roofline = roof(dominant, bound_of.get(dominant, "hbm")) if dominant else None
         attn = {n: roof(n, "hbm") for n in ("kv_reduce", "kv_project_reduce", "q_readout") if n in ksum}
+        if "q_readout" not in attn:
+            attn["q_readout"] = {"kernel": None, "note": "no launch: softmax(Q)/sqrt(32) is an epilogue of the QKV projection (d_model 256) or stays "
+                                                         "in tensor memory (d_model 128), and the readout P.ctx is folded into the output projection "
+                                                         "through the per-sample weight W_b = blockdiag(ctx_b) Wo^T (linear_fused, attn_out_fused)"}
         # d_model=128 layers: the readout, both projections, the FFN and both LayerNorms run inside two fused kernels
         fused = {n: roof(n, "hbm") for n in ("attn_out_fused", "ffn_fused", "linear_fused") if n in ksum}
         conv_detail = {n: roof(n, bound_of.get(n, "hbm")) for n in ("conv3d_tc", "conv3d_tc3", "conv3d_sv", "conv3d_halo") if n in ksum}
@@ -621,8 +625,9 @@ ALGORITHMIC = {
                     "output projection runs with the per-sample weight W_b = blockdiag(ctx) Wo^T: q_readout is not a kernel any more)",
     "kv_reduce": "2*B*N*C*E bytes (K and V read once; the merge kernel also writes W_b); bridge 1 (d_model 128) does not appear here: "
                  "its K is reduced inside the projection kernel (kv_project_reduce) and its V is never computed per token",
-    "kv_project_reduce": "rows*C*E bytes (x read once; K never written, V = x Wv^T never computed per token: ctx = (P^T x) Wv^T / s + bv; "
-                         "the two launches it replaces move 5x that)",
+    "kv_project_reduce": "2*B*N*C*E bytes = SURVEY 8(d)'s figure for the op it implements (kv_reduce: K and V read once), although the launch "
+                         "moves HALF of that (x read once; K never written, V = x Wv^T never computed per token: ctx = (P^T x) Wv^T / s + bv) "
+                         "and also contains the K projection; the two launches it replaces move 5x its bytes",
     "q_readout": "2*B*N*C*E bytes (Q read, out written)",
     "attn_out_fused": "2*rows*C*E bytes (x read once, y written once; Q projection and P W_b^T chained in tensor memory)",
     "ffn_fused": "2*rows*C*E bytes (x read once, y written once)",

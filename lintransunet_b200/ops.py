@@ -1020,7 +1020,9 @@ def kv_project_reduce(x: torch.Tensor, w_kv: torch.Tensor, b_kv: torch.Tensor, h
     nbytes = L.ltu_kv_project_reduce_workspace(B, N)
     ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
     ctx = torch.empty(B, heads, 32, 32, dtype=torch.float32, device=dev)
-    with _Guard(dev, ("kv_project_reduce", B * N * C * 2, 2 * B * N * C * (2 * C + 32))) as st:
+    # algorithmic bytes = SURVEY 8(d)'s figure for the op this launch implements (kv_reduce: K and V read once, 2*B*N*C*E);
+    # what it actually moves is half of that (x once: K is never stored, V never computed per token)
+    with _Guard(dev, ("kv_project_reduce", 2 * B * N * C * 2, 2 * B * N * C * (2 * C + 32))) as st:
         wb = None
         if w_o is not None:
             if w_o.dtype != torch.bfloat16 or tuple(w_o.shape) != (C, C):
