@@ -20,6 +20,7 @@ restatement lives in oracle/sliding_window.py, which is the checker -- "parity u
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -27,6 +28,17 @@ import torch.distributed as dist
 
 from . import ops
 from .unet import MaskTransUnet
+
+SW_STREAMS = max(1, int(os.environ.get("LTU_SW_STREAMS", "2")))     # forwards in flight per rank (A/B switch: 1 = one stream)
+_STREAMS = {}
+
+
+def _side_streams(dev, n):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), n)
+    if key not in _STREAMS:
+        _STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+    return _STREAMS[key]
+
 
 __all__ = ["scan_plan", "shard_windows", "reduce_votes", "max_coverage", "balanced_batches", "sliding_window_inference"]
 
@@ -222,15 +234,39 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
         else:
             vol = inputs[b, 0]
         g0 = 0
-        for nb in balanced_batches(len(mine), sw_batch_size):
+        batches = balanced_batches(len(mine), sw_batch_size)
+        # Two forwards in flight: consecutive batches alternate between two streams, each replaying its own instance of the
+        # forward's CUDA graph (predictor.graph_slot).  A forward spends about a quarter of its time in layers that cannot fill
+        # the GPU (the small bridges, the coarse convolutions: 2.9 ms of 12.2 ms at batch 8, tools/batch_sweep.py); those
+        # now run under the other batch's large kernels.  The votes are integer atomics: the result does not depend on the
+        # interleaving.
+        n_streams = SW_STREAMS if (len(batches) > 1 and hasattr(predictor, "graph_slot")
+                                   and getattr(predictor, "use_cuda_graphs", False)) else 1
+        cur = torch.cuda.current_stream(dev)
+        lanes = [cur] if n_streams == 1 else _side_streams(dev, n_streams)
+        for s in lanes:
+            if s is not cur:
+                s.wait_stream(cur)
+        for k, nb in enumerate(batches):
             st = starts_dev[g0:g0 + nb].contiguous()
-            if stream_upload:                                             # wait for the last row this batch reads
-                need = max(starts[i][0] for i in mine[g0:g0 + nb]) + roi[0]
-                main_stream.wait_event(ready[next(e for e in piece_ends if e >= need)])
-            win = ops.gather_windows(vol, st, roi)
-            lab = predictor.predict_labels(win)
-            ops.vote_accumulate(lab, st, votes)
+            lane = lanes[k % n_streams]
+            with torch.cuda.stream(lane):
+                if stream_upload:                                         # wait for the last row this batch reads
+                    need = max(starts[i][0] for i in mine[g0:g0 + nb]) + roi[0]
+                    lane.wait_event(ready[next(e for e in piece_ends if e >= need)])
+                if n_streams > 1:
+                    predictor.graph_slot = k % n_streams
+                    st.record_stream(lane)
+                win = ops.gather_windows(vol, st, roi)
+                lab = predictor.predict_labels(win)
+                ops.vote_accumulate(lab, st, votes)
             g0 += nb
+        if n_streams > 1:
+            predictor.graph_slot = 0
+            for s in lanes:
+                cur.wait_stream(s)
+                vol.record_stream(s)
+                votes.record_stream(s)
         if slab_exchange:
             # reduce-scatter by H-slab (one collective per class volume: votes[c] is contiguous [H,W,D]), argmax on the
             # owned slab, then (optionally) all-gather the uint8 label slabs

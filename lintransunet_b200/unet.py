@@ -466,7 +466,8 @@ class MaskTransUnet(nn.Module):
         # training: autograd through the native backward (bf16 path; loss.backward() fills p.grad).  LTU_NATIVE_BACKWARD=0
         # turns a training forward with grad into an error instead (there is no other backward).
         self.native_backward = os.environ.get("LTU_NATIVE_BACKWARD", "1") == "1"
-        self.max_cached_graphs = 6                    # one graph (+ private memory pool) per input shape and head, LRU
+        self.max_cached_graphs = 6                    # one graph (+ private memory pool) per input shape, head and slot, LRU
+        self.graph_slot = 0                           # which instance of a shape's graph _run replays (sliding_window.py)
         self._plans: Dict[tuple, tuple] = {}
         self._graphs: Dict[tuple, dict] = {}
 
@@ -507,7 +508,9 @@ class MaskTransUnet(nn.Module):
                          and not torch.cuda.is_current_stream_capturing())
             if not graphable:
                 return self._forward_impl(x, plan, head)
-            key = (x.device.index, dtype, head, tuple(x.shape)) + self._knobs()
+            # graph_slot: the sliding-window driver replays two instances of the same forward on two streams (two static
+            # input / output buffers, two memory pools), so that the latency-bound layers of one batch run under the other's
+            key = (x.device.index, dtype, head, tuple(x.shape), int(getattr(self, "graph_slot", 0))) + self._knobs()
             ent = self._graphs.get(key)
             if ent is None or ent["plan"] is not plan:
                 ent = self._capture(x, plan, head)
