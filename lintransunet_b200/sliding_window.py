@@ -29,7 +29,7 @@ import torch.distributed as dist
 from . import ops
 from .unet import MaskTransUnet
 
-SW_STREAMS = max(1, int(os.environ.get("LTU_SW_STREAMS", "2")))     # forwards in flight per rank (A/B switch: 1 = one stream)
+SW_STREAMS = max(1, int(os.environ.get("LTU_SW_STREAMS", "3")))     # forwards in flight per rank (A/B switch: 1 = one stream)
 _STREAMS = {}
 
 

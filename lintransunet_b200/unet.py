@@ -466,7 +466,7 @@ class MaskTransUnet(nn.Module):
         # training: autograd through the native backward (bf16 path; loss.backward() fills p.grad).  LTU_NATIVE_BACKWARD=0
         # turns a training forward with grad into an error instead (there is no other backward).
         self.native_backward = os.environ.get("LTU_NATIVE_BACKWARD", "1") == "1"
-        self.max_cached_graphs = 6                    # one graph (+ private memory pool) per input shape, head and slot, LRU
+        self.max_cached_graphs = 16                   # one graph (+ private memory pool) per input shape, head and slot, LRU
         self.graph_slot = 0                           # which instance of a shape's graph _run replays (sliding_window.py)
         self._plans: Dict[tuple, tuple] = {}
         self._graphs: Dict[tuple, dict] = {}
