@@ -49,3 +49,31 @@ def test_host_memory_input_is_streamed_and_bit_identical():
         f_host, l_host = sw.sliding_window_inference(vol, roi, 4, m, overlap=0.5, return_labels=True)
     assert sw.last_h2d_bytes == vol.numel() * 4
     assert torch.equal(f_dev, f_host) and torch.equal(l_dev, l_host)
+
+
+def test_forwards_in_flight_do_not_change_the_result():
+    """Consecutive batches run on alternating streams, each replaying its own instance of the forward's CUDA graph
+    (sliding_window.SW_STREAMS): votes are integer atomics and every batch keeps its composition, so labels and vote fractions
+    equal the one-stream schedule bit for bit -- device and pinned-host input, repeated calls (graph instances are reused)."""
+    from lintransunet_b200 import MaskTransUnet, sliding_window as sw
+    torch.manual_seed(0)
+    m = MaskTransUnet([16, 32, 64, 128, 256], [100, 65, 40, 25, 10], [False, True, True, True, True], 1, 3).cuda().eval()
+    vol = torch.randn(1, 1, 160, 160, 48, generator=torch.Generator().manual_seed(3)).pin_memory()
+    roi = (64, 64, 16)                                              # 4 x 4 x 5 = 80 windows: 27 batches of 3
+    prev = sw.SW_STREAMS
+    out = {}
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            for n in (1, 3, 2):
+                sw.SW_STREAMS = n
+                for rep in range(2):
+                    f, l = sw.sliding_window_inference(vol.cuda(), roi, 3, m, overlap=0.5, return_labels=True)
+                    lab_only = sw.sliding_window_inference(vol, roi, 3, m, overlap=0.5, labels_only=True)
+                    out[(n, rep)] = (f.clone(), l.clone(), lab_only.clone())
+    finally:
+        sw.SW_STREAMS = prev
+    assert m.graph_slot == 0
+    f0, l0, o0 = out[(1, 0)]
+    for key, (f, l, o) in out.items():
+        assert torch.equal(f, f0) and torch.equal(l, l0) and torch.equal(o, o0), key
+    assert torch.equal(l0, o0)
