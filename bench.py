@@ -68,6 +68,8 @@ def config_dict(n_gpus):
                         "50% overlap (147 windows), sw_batch_size 8 (= config4 forward per batch), "
                         "multi-class MaskTransUnet dim_output=3, eval, bf16 autocast",
             "windows": 147, "sw_batch_size": SW_BATCH, "parallelism": f"window-sharded dp{n_gpus}",
+            "forwards_in_flight": "3 per rank: consecutive batches of 8 windows alternate between three CUDA streams, each replaying "
+                                  "its own instance of the forward's CUDA graph (LTU_SW_STREAMS; the result is bit-identical)",
             "l2": "inputs larger than L2 (268 MB volume, 134 MB+ activations per layer)"}
 
 
